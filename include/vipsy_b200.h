@@ -1,0 +1,224 @@
+/* vipsy_b200.h -- C ABI of the B200-native ELBO + gradient path.
+ *
+ * The reference (inuyasha2012/vipsy) has no native ABI: its hot path is reached
+ * through Pyro's ELBO-object protocol
+ *     loss_and_grads(model, guide, data)      vi.py:507  (SVI.step, vi.py:503-516)
+ *     loss(model, guide, data)                vi.py:770, vi.py:942 (evaluate_loss)
+ * selected by the `loss=` kwarg of fit() (vi.py:627, 758, 862, 936).  These
+ * entry points are what a binding of that protocol calls:
+ * one call = one ELBO + gradient evaluation over a batch of persons.
+ *
+ * Conventions
+ *  - every pointer is a DEVICE pointer unless the name ends in `_host`;
+ *  - parameters are the CONSTRAINED values pyro.param() returns (a, b, c, d,
+ *    sigma, g, s, lam1 ...); gradients are w.r.t. those values (the chain rule
+ *    through sigmoid / exp stays with the caller) -- except `chol` with
+ *    chol_raw=1, which is consumed raw (LowerCholeskyTransform fused, A.4);
+ *  - `stream` is a cudaStream_t passed as void*; calls are stream-ordered, never
+ *    synchronise, never allocate; the caller owns every buffer incl. workspace;
+ *  - return value: 0 or a negative VIPSY_ERR_*; vipsy_last_error() gives text;
+ *  - responses are one byte per cell: 0, 1, or VIPSY_Y_MISSING (NaN in the
+ *    reference's float matrix, vi.py:621-624).
+ */
+#ifndef VIPSY_B200_H
+#define VIPSY_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VIPSY_ABI_VERSION 1
+
+enum {
+  VIPSY_OK = 0,
+  VIPSY_ERR_ARG = -1,         /* null / inconsistent argument            */
+  VIPSY_ERR_UNSUPPORTED = -2, /* size or mode this build does not cover   */
+  VIPSY_ERR_WORKSPACE = -3,   /* workspace too small                      */
+  VIPSY_ERR_CUDA = -4         /* a CUDA runtime call failed               */
+};
+
+enum { VIPSY_Y_MISSING = 255 };
+
+/* BaseIRT.IRT_FUN keys, vi.py:538-543 */
+enum { VIPSY_IRT_1PL = 1, VIPSY_IRT_2PL = 2, VIPSY_IRT_3PL = 3, VIPSY_IRT_4PL = 4 };
+/* BaseCDM.CDM_FUN keys, vi.py:728-731 */
+enum { VIPSY_CDM_DINA = 0, VIPSY_CDM_DINO = 1 };
+/* gradient estimator for the Gaussian guide (SURVEY Finding 1 / Appendix A.2) */
+enum { VIPSY_EST_PATHWISE = 0, VIPSY_EST_SCORE = 1 };
+/* guide covariance, VIRT.guide vi.py:701-723 */
+enum { VIPSY_COV_DIAG1 = 0,   /* K == 1: sigma[B]                                     */
+       VIPSY_COV_SHARED = 1,  /* share_cov=True: one K x K factor                     */
+       VIPSY_COV_PERSON = 2 };/* one factor per person                                */
+/* flags: STRICT keeps the reference's formula class (sigmoid -> c+(d-c)s -> clamp)
+ * everywhere; without it the 4PL kernel switches, per launch and on the device,
+ * to an algebraically equal rational form when every item has 1e-3 <= c, d <= 1-1e-3
+ * (where the probability clamp cannot fire). */
+enum { VIPSY_IRT_FLAG_STRICT = 1 };
+enum { VIPSY_CHOL_DENSE = 0,  /* row-major K x K, strict upper triangle ignored        */
+       VIPSY_CHOL_PACKED = 1 };/* torch.tril_indices row-major order, K(K+1)/2 (vi.py:453) */
+
+/* ------------------------------------------------------------------------
+ * IRT: Trace_ELBO over BaseIRT.model (vi.py:574-625) with the VIRT / VaeIRT
+ * Gaussian guide (vi.py:673-723), S particles, on a batch of B persons.
+ *
+ *   loss = -(scale/S) * sum_s sum_b [ sum_j m_bj lb(y_bj, P_bjs) + log p(x_bs) - log q(x_bs) ]
+ *
+ * x_bs = mu_b + sigma_b eps_bs (K==1) or mu_b + L_b eps_bs.  All S particles of
+ * one call share the batch (idx); a caller that re-draws the minibatch per
+ * particle (Pyro does when subsample_size < N) issues one call per particle
+ * or stacks the particles along the batch axis with S=1.
+ * ---------------------------------------------------------------------- */
+typedef struct VipsyIrtArgs {
+  /* sizes */
+  int64_t n_rows;          /* rows of y                                         */
+  int64_t batch;           /* B persons evaluated                               */
+  int32_t n_items;         /* J                                                 */
+  int32_t n_dims;          /* K                                                 */
+  int32_t n_particles;     /* S                                                 */
+  int32_t model;           /* VIPSY_IRT_*                                       */
+  int32_t estimator;       /* VIPSY_EST_*                                       */
+  int32_t cov_mode;        /* VIPSY_COV_*                                       */
+  int32_t chol_layout;     /* VIPSY_CHOL_* (K > 1)                              */
+  int32_t chol_raw;        /* 1: diag of chol is log-scale (exp fused), grads raw */
+  float D;                 /* scaling constant, vi.py:549                        */
+  float scale;             /* N / B of the `data` plate                         */
+  float baseline;          /* score estimator control variate (0 = reference)   */
+  int32_t flags;           /* VIPSY_IRT_FLAG_*                                  */
+  /* inputs */
+  const uint8_t* y;        /* n_rows x J response codes                          */
+  int64_t y_row_stride;    /* bytes between rows of y (>= J)                     */
+  const int64_t* idx;      /* B row indices into y, or NULL for rows 0..B-1      */
+  const float* mu;         /* B x K variational means (already gathered)         */
+  const float* sigma;      /* K==1: B std-devs                                   */
+  const float* chol;       /* K>1: K x K | B x K x K | B x K(K+1)/2              */
+  const float* eps;        /* S x B x K injected N(0,1) noise, or NULL = Philox  */
+  uint64_t seed;           /* Philox key   (eps == NULL)                         */
+  uint64_t offset;         /* Philox counter offset, bump once per call          */
+  int64_t person_offset;   /* global index of batch row 0 (multi-GPU shards)     */
+  const float* a;          /* K x J slopes (ignored for 1PL)                     */
+  const float* b;          /* J intercepts                                       */
+  const float* c;          /* J lower asymptotes (3PL, 4PL)                      */
+  const float* d;          /* J upper asymptotes (4PL)                           */
+  const uint8_t* a_free;   /* K x J 0/1 mask applied to d_a (vi.py:511-512) or NULL */
+  /* outputs */
+  double* loss;            /* 1                                                 */
+  float* d_mu;             /* B x K                                             */
+  float* d_sigma;          /* K==1: B                                           */
+  float* d_chol;           /* same layout as chol                               */
+  float* d_a;              /* K x J                                             */
+  float* d_b;              /* J                                                 */
+  float* d_c;              /* J                                                 */
+  float* d_d;              /* J                                                 */
+  /* scratch */
+  void* workspace;
+  size_t workspace_bytes;
+} VipsyIrtArgs;
+
+/* Bytes of workspace vipsy_irt_elbo_grad needs for these sizes (0 on bad args). */
+size_t vipsy_irt_workspace_bytes(const VipsyIrtArgs* args);
+/* loss + every gradient (SVI.step's loss_and_grads, vi.py:507).  Pass NULL
+ * gradient pointers + estimator PATHWISE for the value only (evaluate_loss). */
+int vipsy_irt_elbo_grad(const VipsyIrtArgs* args, void* stream);
+
+/* ------------------------------------------------------------------------
+ * Enumerated CDMs: TraceEnum_ELBO over VCCDM.model (vi.py:839-857), optionally
+ * with the HO-DINA pattern prior and Gaussian guide of VCHoDina (vi.py:897-934).
+ *
+ *   loss = -(scale/S) sum_s sum_b [ logsumexp_c( log prior_bc + sum_j m_bj lb(y_bj, p_cj) )
+ *                                   (+ log N(theta_bs;0,1) - log q(theta_bs)) ]
+ * Pattern c has attribute k mastered iff bit k of c is set (vi.py:825-837).
+ * ---------------------------------------------------------------------- */
+typedef struct VipsyCdmEnumArgs {
+  int64_t n_rows;
+  int64_t batch;
+  int32_t n_items;         /* J                                                 */
+  int32_t n_attrs;         /* K  (C = 2^K patterns)                             */
+  int32_t n_particles;     /* S (HO-DINA noise draws; 1 otherwise)              */
+  int32_t model;           /* VIPSY_CDM_*  (HO-DINA is always DINA, vi.py:905)  */
+  int32_t hodina;          /* 1: VCHoDina prior + theta guide                   */
+  int32_t reserved0;
+  float scale;
+  float reserved1;
+  const uint8_t* y;
+  int64_t y_row_stride;
+  const int64_t* idx;
+  const uint32_t* qmask;   /* J bit masks: bit k = Q[k][j] (vi.py:741)          */
+  const float* g;          /* J guess                                            */
+  const float* s;          /* J slip                                             */
+  const float* lam0;       /* K  (hodina)                                        */
+  const float* lam1;       /* K  (hodina, positive)                              */
+  const float* mu;         /* B  (hodina) theta_local                            */
+  const float* sigma;      /* B  (hodina) theta_scale                            */
+  const float* eps;        /* S x B injected noise or NULL = Philox              */
+  uint64_t seed, offset;
+  int64_t person_offset;
+  double* loss;
+  float* d_g;              /* J                                                  */
+  float* d_s;              /* J                                                  */
+  float* d_lam0;           /* K                                                  */
+  float* d_lam1;           /* K                                                  */
+  float* d_mu;             /* B                                                  */
+  float* d_sigma;          /* B                                                  */
+  float* posterior;        /* optional B x C pattern posterior (read-out), or NULL */
+  void* workspace;
+  size_t workspace_bytes;
+} VipsyCdmEnumArgs;
+
+size_t vipsy_cdm_enum_workspace_bytes(const VipsyCdmEnumArgs* args);
+int vipsy_cdm_enum_elbo_grad(const VipsyCdmEnumArgs* args, void* stream);
+
+/* ------------------------------------------------------------------------
+ * REINFORCE CDM: Trace_ELBO over BaseCDM.model (vi.py:745-756) with the
+ * Bernoulli guide of VCDM / VaeCDM (vi.py:796-816): the score-function path
+ * the reference actually executes.  attr_bk = [u_bk < attr_p_bk].
+ * ---------------------------------------------------------------------- */
+typedef struct VipsyCdmScoreArgs {
+  int64_t n_rows;
+  int64_t batch;
+  int32_t n_items, n_attrs, n_particles, model;
+  float scale, baseline;
+  const uint8_t* y;
+  int64_t y_row_stride;
+  const int64_t* idx;
+  const uint32_t* qmask;
+  const float* g;
+  const float* s;
+  const float* attr_p;     /* B x K guide probabilities (gathered)               */
+  const float* u;          /* S x B x K injected U(0,1) or NULL = Philox          */
+  uint64_t seed, offset;
+  int64_t person_offset;
+  double* loss;
+  float* d_g;
+  float* d_s;
+  float* d_attr_p;         /* B x K                                              */
+  void* workspace;
+  size_t workspace_bytes;
+} VipsyCdmScoreArgs;
+
+size_t vipsy_cdm_score_workspace_bytes(const VipsyCdmScoreArgs* args);
+int vipsy_cdm_score_elbo_grad(const VipsyCdmScoreArgs* args, void* stream);
+
+/* ------------------------------------------------------------------------
+ * Data-format helpers either side of the path
+ * ---------------------------------------------------------------------- */
+/* float response matrix with NaN = missing (the reference's `data`) -> codes */
+int vipsy_pack_responses(const float* y_f32, int64_t n_cells, uint8_t* codes, void* stream);
+/* eta table, bit-exact: out[c*J + j] = eta_cj in {0,1} (dina/dino, vi.py:78-81/95-98) */
+int vipsy_cdm_eta_table(const uint32_t* qmask, int32_t n_items, int32_t n_attrs, int32_t model,
+                        uint8_t* eta, void* stream);
+/* the in-kernel noise generator, exposed: out[s*B*K + b*K + k] (Philox4x32-10 + Box-Muller) */
+int vipsy_fill_normal(float* out, int32_t n_particles, int64_t batch, int32_t n_dims,
+                      uint64_t seed, uint64_t offset, int64_t person_offset, void* stream);
+int vipsy_fill_uniform(float* out, int32_t n_particles, int64_t batch, int32_t n_dims,
+                       uint64_t seed, uint64_t offset, int64_t person_offset, void* stream);
+
+int vipsy_abi_version(void);
+const char* vipsy_last_error(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VIPSY_B200_H */

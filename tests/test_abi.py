@@ -1,0 +1,66 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library builds, loads and
+exports every symbol include/vipsy_b200.h declares; ctypes mirrors the structs."""
+import ctypes as C
+import os
+import re
+import subprocess
+import tempfile
+
+import pytest
+
+from vipsy_b200 import _native as N
+from vipsy_b200 import build as B
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "vipsy_b200.h")
+
+
+@pytest.fixture(scope="module")
+def lib():
+    B.build()
+    return N.lib()
+
+
+def declared_functions():
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(vipsy_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_every_declared_symbol_is_exported(lib):
+    names = declared_functions()
+    assert len(names) >= 12
+    for n in names:
+        assert n in N.SYMBOLS, f"{n} declared in the header but not bound"
+        assert getattr(lib, n) is not None
+    assert lib.vipsy_abi_version() == 1
+
+
+def test_struct_layout_matches_header():
+    structs = {"VipsyIrtArgs": N.IrtArgs, "VipsyCdmEnumArgs": N.CdmEnumArgs, "VipsyCdmScoreArgs": N.CdmScoreArgs}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', f'#include "{HEADER}"', "int main(void){"]
+    for cname, st in structs.items():
+        lines.append(f'printf("{cname} %zu\\n", sizeof({cname}));')
+        for f, _ in st._fields_:
+            lines.append(f'printf("{cname}.{f} %zu\\n", offsetof({cname}, {f}));')
+    lines.append("return 0;}")
+    with tempfile.TemporaryDirectory() as td:
+        src, exe = os.path.join(td, "l.c"), os.path.join(td, "l")
+        open(src, "w").write("\n".join(lines))
+        subprocess.run(["gcc", "-std=c99", "-o", exe, src], check=True)
+        out = subprocess.run([exe], check=True, capture_output=True, text=True).stdout
+    got = dict(l.split() for l in out.strip().splitlines())
+    for cname, st in structs.items():
+        assert int(got[cname]) == C.sizeof(st), cname
+        for f, _ in st._fields_:
+            assert int(got[f"{cname}.{f}"]) == getattr(st, f).offset, f"{cname}.{f}"
+
+
+def test_bad_arguments_are_rejected_without_a_gpu(lib):
+    a = N.IrtArgs()
+    assert lib.vipsy_irt_elbo_grad(C.byref(a), None) == N.ERR_ARG
+    assert b"model" in lib.vipsy_last_error()
+    assert lib.vipsy_irt_elbo_grad(None, None) == N.ERR_ARG
+    assert lib.vipsy_irt_workspace_bytes(C.byref(a)) == 0
+    with pytest.raises(N.VipsyError):
+        N.check(lib.vipsy_pack_responses(None, 4, None, None))

@@ -1,0 +1,203 @@
+"""GPU parity: the fused K=1 IRT kernel (through the C ABI) against the oracle."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import vipsy_oracle as o
+from tests.util import assert_close, codes_from_float
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from vipsy_b200 import build
+    build.build()
+    from vipsy_b200 import ops as _ops
+    return _ops
+
+
+def make_case(B, J, S, model, missing=0.0, seed=0, sat=False):
+    g = torch.Generator().manual_seed(seed)
+    y = (torch.rand(B, J, generator=g) < 0.55).float()
+    if missing:
+        y[torch.rand(B, J, generator=g) < missing] = float("nan")
+    mu = torch.randn(B, 1, generator=g) * (3.0 if sat else 0.7)
+    sigma = torch.exp(torch.randn(B, 1, generator=g) * 0.3)
+    eps = torch.randn(S, B, 1, generator=g)
+    a = torch.rand(1, J, generator=g) * 2.5 + 0.5
+    b = torch.randn(1, J, generator=g) * (3.0 if sat else 1.0)
+    c = torch.rand(1, J, generator=g) * 0.15 + 0.05
+    d = torch.rand(1, J, generator=g) * 0.15 + 0.8
+    return dict(y=y, mu=mu, sigma=sigma, eps=eps, a=a, b=b, c=c, d=d, model=model)
+
+
+def run_both(ops, cs, D=1.0, scale=1.0, estimator="pathwise", baseline=0.0, strict=False, idx=None, y_full=None):
+    m = cs["model"]
+    dev = "cuda"
+    kw = dict(a=cs["a"] if m != "irt_1pl" else None, b=cs["b"],
+              c=cs["c"] if m in ("irt_3pl", "irt_4pl") else None, d=cs["d"] if m == "irt_4pl" else None)
+    ref = o.irt_elbo_grad(cs["y"], cs["mu"], cs["sigma"], cs["eps"], kw["a"], kw["b"], kw["c"], kw["d"],
+                          model=m, D=D, scale=scale, estimator=estimator, baseline=baseline)
+    ysrc = cs["y"] if y_full is None else y_full
+    codes = codes_from_float(ysrc).to(dev)
+    got = ops.irt_elbo_grad(codes, cs["mu"].to(dev), sigma=cs["sigma"].to(dev), eps=cs["eps"].to(dev),
+                            **{k: (v.to(dev) if v is not None else None) for k, v in kw.items()},
+                            model=m, D=D, scale=scale, estimator=estimator, baseline=baseline, strict=strict,
+                            idx=None if idx is None else idx.to(dev))
+    torch.cuda.synchronize()
+    return got, ref
+
+
+def check(got, ref, model, tol=1e-5):
+    assert_close(got["loss"], ref["loss"], tol, tol, "loss")
+    assert_close(got["d_mu"], ref["d_mu"], tol, tol, "d_mu")
+    assert_close(got["d_sigma"], ref["d_scale"], tol, tol, "d_sigma")
+    assert_close(got["d_b"], ref["d_b"], tol, tol, "d_b")
+    if model != "irt_1pl":
+        assert_close(got["d_a"], ref["d_a"], tol, tol, "d_a")
+    if model in ("irt_3pl", "irt_4pl"):
+        assert_close(got["d_c"], ref["d_c"], tol, tol, "d_c")
+    if model == "irt_4pl":
+        assert_close(got["d_d"], ref["d_d"], tol, tol, "d_d")
+
+
+@pytest.mark.parametrize("model", ["irt_1pl", "irt_2pl", "irt_3pl", "irt_4pl"])
+@pytest.mark.parametrize("S", [1, 2, 3, 4, 8, 20, 32, 64])
+def test_parity_models_and_particles(ops, model, S):
+    cs = make_case(B=203, J=37, S=S, model=model, missing=0.15, seed=S)
+    got, ref = run_both(ops, cs, D=1.702, scale=2.5)
+    check(got, ref, model)
+
+
+@pytest.mark.parametrize("model", ["irt_2pl", "irt_4pl"])
+@pytest.mark.parametrize("B,J", [(1, 1), (31, 5), (32, 100), (33, 7), (1000, 5), (4097, 100), (257, 333)])
+def test_ragged_shapes(ops, model, B, J):
+    cs = make_case(B=B, J=J, S=4, model=model, missing=0.1, seed=B + J)
+    got, ref = run_both(ops, cs)
+    check(got, ref, model)
+
+
+def test_strict_and_fast_4pl_agree(ops):
+    cs = make_case(B=777, J=100, S=32, model="irt_4pl", seed=5)
+    fast, ref = run_both(ops, cs)
+    strict, _ = run_both(ops, cs, strict=True)
+    check(fast, ref, "irt_4pl")
+    check(strict, ref, "irt_4pl")
+
+
+def test_fast_path_falls_back_when_items_touch_the_clamp(ops):
+    cs = make_case(B=300, J=20, S=8, model="irt_4pl", seed=6, sat=True)
+    cs["c"][0, :5] = 0.0          # lower asymptote exactly 0: clamp reachable
+    cs["d"][0, 5:9] = 1.0
+    got, ref = run_both(ops, cs)
+    check(got, ref, "irt_4pl", tol=2e-5)
+
+
+@pytest.mark.parametrize("model", ["irt_1pl", "irt_2pl", "irt_3pl"])
+def test_saturated_regime(ops, model):
+    """Large |logit|: clamp fires, zero-gradient cells, reference formula class."""
+    cs = make_case(B=500, J=40, S=4, model=model, seed=11, sat=True)
+    got, ref = run_both(ops, cs)
+    # per-cell 1-P rounding differs by ulps of P near saturation: allow 5e-5 on the sums
+    check(got, ref, model, tol=5e-5)
+
+
+@pytest.mark.parametrize("estimator,baseline", [("score", 0.0), ("score", -35.0)])
+@pytest.mark.parametrize("model", ["irt_2pl", "irt_4pl"])
+def test_score_function_estimator(ops, model, estimator, baseline):
+    cs = make_case(B=301, J=29, S=8, model=model, missing=0.1, seed=3)
+    got, ref = run_both(ops, cs, scale=1.5, estimator=estimator, baseline=baseline)
+    check(got, ref, model, tol=2e-5)
+
+
+def test_all_missing_rows_and_items(ops):
+    cs = make_case(B=100, J=12, S=2, model="irt_2pl", missing=0.3, seed=9)
+    cs["y"][:40] = float("nan")        # a whole warp of persons unobserved
+    cs["y"][:, 3] = float("nan")       # an item nobody answered
+    got, ref = run_both(ops, cs)
+    check(got, ref, "irt_2pl")
+    assert float(got["d_b"][0, 3]) == 0.0 and float(got["d_a"][0, 3]) == 0.0
+
+
+def test_idx_gather_matches_contiguous(ops):
+    cs = make_case(B=150, J=23, S=4, model="irt_3pl", missing=0.1, seed=21)
+    g = torch.Generator().manual_seed(1)
+    y_full = (torch.rand(900, 23, generator=g) < 0.5).float()
+    idx = torch.randperm(900, generator=g)[:150]
+    y_full[idx] = cs["y"]
+    got, ref = run_both(ops, cs, idx=idx, y_full=y_full, scale=6.0)
+    check(got, ref, "irt_3pl")
+
+
+def test_golden_fixtures_through_the_abi(ops, golden):
+    g = golden
+    for name, model in [("irt1", "irt_1pl"), ("irt2", "irt_2pl"), ("irt3", "irt_3pl"), ("irt4", "irt_4pl")]:
+        K, S, D, scale = g[f"{name}_meta"]
+        t = lambda k: torch.from_numpy(g[f"{name}_{k}"])
+        dev = "cuda"
+        got = ops.irt_elbo_grad(codes_from_float(t("y")).to(dev), t("mu").to(dev), sigma=t("sp").to(dev),
+                                eps=t("eps").to(dev), a=t("a").to(dev), b=t("b").to(dev), c=t("c").to(dev),
+                                d=t("d").to(dev), model=model, D=float(D), scale=float(scale))
+        tol = 2e-5   # golden is the reference's fp32 arithmetic
+        assert_close(got["loss"], t("loss"), tol, tol, name)
+        assert_close(got["d_mu"], t("d_mu"), tol, tol, name)
+        assert_close(got["d_sigma"], t("d_sp"), tol, tol, name)
+        assert_close(got["d_b"], t("d_b"), tol, tol, name)
+        if model != "irt_1pl":
+            assert_close(got["d_a"], t("d_a"), tol, tol, name)
+
+
+def test_lsat_first_iteration_known_answer(ops, golden):
+    """BASELINE config 1: lsat.dat 2PL at the reference's init (SURVEY 8c KAT)."""
+    y = torch.from_numpy(golden["lsat_y"]).cuda()
+    torch.manual_seed(0)
+    eps = torch.randn(1000, 1)
+    got = ops.irt_elbo_grad(y, torch.zeros(1000, 1).cuda(), sigma=torch.ones(1000, 1).cuda(),
+                            eps=eps[None].cuda(), a=torch.ones(1, 5).cuda(), b=torch.zeros(1, 5).cuda(),
+                            model="irt_2pl")
+    assert abs(float(got["loss"]) - 4056.5154) < 4e-2
+    assert_close(got["d_b"], torch.tensor([[-419.5977, -204.5977, -48.5977, -258.5977, -365.5977]]), 1e-5, 1e-5)
+    assert_close(got["d_a"], torch.tensor([[205.3315, 198.5405, 226.3220, 225.7764, 212.9940]]), 1e-5, 1e-5)
+
+
+def test_bitwise_deterministic(ops):
+    cs = make_case(B=5000, J=64, S=8, model="irt_4pl", missing=0.05, seed=2)
+    a, _ = run_both(ops, cs)
+    b, _ = run_both(ops, cs)
+    for k in ("loss", "d_mu", "d_sigma", "item_grads"):
+        assert torch.equal(a[k], b[k]), k
+
+
+def test_in_kernel_philox_equals_injected_noise(ops):
+    cs = make_case(B=999, J=31, S=12, model="irt_4pl", seed=8)
+    dev = "cuda"
+    eps = ops.fill_normal(12, 999, 1, seed=1234, offset=7, person_offset=100)
+    common = dict(sigma=cs["sigma"].to(dev), a=cs["a"].to(dev), b=cs["b"].to(dev), c=cs["c"].to(dev),
+                  d=cs["d"].to(dev), model="irt_4pl")
+    codes = codes_from_float(cs["y"]).to(dev)
+    inj = ops.irt_elbo_grad(codes, cs["mu"].to(dev), eps=eps, **common)
+    rng = ops.irt_elbo_grad(codes, cs["mu"].to(dev), n_particles=12, seed=1234, offset=7, person_offset=100, **common)
+    for k in ("loss", "d_mu", "d_sigma", "d_b", "d_a", "d_c", "d_d"):
+        assert_close(rng[k], inj[k], 1e-6, 1e-6, k)
+    e = eps.cpu().double()
+    assert abs(float(e.mean())) < 0.03 and abs(float(e.std()) - 1.0) < 0.03
+    other = ops.fill_normal(12, 999, 1, seed=1234, offset=8, person_offset=100)
+    assert not torch.equal(other, eps)
+
+
+def test_pack_responses_kernel(ops):
+    g = torch.Generator().manual_seed(4)
+    y = (torch.rand(1237, 13, generator=g) < 0.5).float()
+    y[torch.rand(1237, 13, generator=g) < 0.2] = float("nan")
+    assert torch.equal(ops.pack_responses(y.cuda()).cpu(), codes_from_float(y))
+
+
+def test_loss_only_call(ops):
+    cs = make_case(B=100, J=10, S=4, model="irt_2pl", seed=1)
+    dev = "cuda"
+    full, ref = run_both(ops, cs)
+    val = ops.irt_elbo_grad(codes_from_float(cs["y"]).to(dev), cs["mu"].to(dev), sigma=cs["sigma"].to(dev),
+                            eps=cs["eps"].to(dev), a=cs["a"].to(dev), b=cs["b"].to(dev), model="irt_2pl",
+                            want_grad=False)
+    assert torch.equal(val["loss"], full["loss"]) and "d_mu" not in val

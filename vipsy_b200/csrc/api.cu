@@ -1,0 +1,66 @@
+// extern "C" entry points: argument validation and dispatch to the kernel families.
+#include "common.cuh"
+
+namespace vipsy {
+size_t irt_uni_workspace_bytes(const VipsyIrtArgs* a);
+int irt_uni_launch(const VipsyIrtArgs* a, cudaStream_t st);
+}  // namespace vipsy
+
+using namespace vipsy;
+
+static int check_irt(const VipsyIrtArgs* a) {
+  VIPSY_REQUIRE(a != nullptr, VIPSY_ERR_ARG, "vipsy_irt: args is NULL");
+  VIPSY_REQUIRE(a->model >= VIPSY_IRT_1PL && a->model <= VIPSY_IRT_4PL, VIPSY_ERR_ARG,
+                "vipsy_irt: unknown model %d (IRT_FUN has irt_1pl..irt_4pl)", a->model);
+  VIPSY_REQUIRE(a->estimator == VIPSY_EST_PATHWISE || a->estimator == VIPSY_EST_SCORE, VIPSY_ERR_ARG,
+                "vipsy_irt: unknown estimator %d", a->estimator);
+  VIPSY_REQUIRE(a->batch >= 0 && a->n_items > 0 && a->n_dims > 0 && a->n_particles > 0, VIPSY_ERR_ARG,
+                "vipsy_irt: bad sizes B=%lld J=%d K=%d S=%d", (long long)a->batch, a->n_items, a->n_dims,
+                a->n_particles);
+  VIPSY_REQUIRE(a->idx != nullptr || a->batch <= a->n_rows, VIPSY_ERR_ARG,
+                "vipsy_irt: batch %lld > rows %lld without idx", (long long)a->batch, (long long)a->n_rows);
+  VIPSY_REQUIRE(a->y_row_stride >= a->n_items, VIPSY_ERR_ARG, "vipsy_irt: y_row_stride < J");
+  VIPSY_REQUIRE(a->y && a->mu && a->b && a->loss, VIPSY_ERR_ARG, "vipsy_irt: y, mu, b, loss are required");
+  VIPSY_REQUIRE(a->model < VIPSY_IRT_2PL || a->a, VIPSY_ERR_ARG, "vipsy_irt: a is required for 2PL+");
+  VIPSY_REQUIRE(a->model < VIPSY_IRT_3PL || a->c, VIPSY_ERR_ARG, "vipsy_irt: c is required for 3PL+");
+  VIPSY_REQUIRE(a->model < VIPSY_IRT_4PL || a->d, VIPSY_ERR_ARG, "vipsy_irt: d is required for 4PL");
+  VIPSY_REQUIRE(a->n_particles <= (1 << 20), VIPSY_ERR_UNSUPPORTED, "vipsy_irt: S too large");
+  if (a->n_dims == 1) {
+    VIPSY_REQUIRE(a->sigma, VIPSY_ERR_ARG, "vipsy_irt: sigma is required for K == 1");
+    VIPSY_REQUIRE((a->d_mu == nullptr) == (a->d_sigma == nullptr), VIPSY_ERR_ARG,
+                  "vipsy_irt: d_mu and d_sigma go together");
+  }
+  return VIPSY_OK;
+}
+
+extern "C" {
+
+size_t vipsy_irt_workspace_bytes(const VipsyIrtArgs* a) {
+  if (!a || a->n_items <= 0 || a->n_dims <= 0 || a->model < 1 || a->model > 4) return 0;
+  if (a->n_dims == 1) return irt_uni_workspace_bytes(a);
+  return 0;
+}
+
+int vipsy_irt_elbo_grad(const VipsyIrtArgs* a, void* stream) {
+  int rc = check_irt(a);
+  if (rc != VIPSY_OK) return rc;
+  if (a->n_dims == 1) return irt_uni_launch(a, (cudaStream_t)stream);
+  set_error("vipsy_irt_elbo_grad: K=%d not built yet", a->n_dims);
+  return VIPSY_ERR_UNSUPPORTED;
+}
+
+// -- CDM entry points: implemented in cdm_enum.cu / cdm_score.cu once built ------
+#ifndef VIPSY_HAVE_CDM
+size_t vipsy_cdm_enum_workspace_bytes(const VipsyCdmEnumArgs*) { return 0; }
+int vipsy_cdm_enum_elbo_grad(const VipsyCdmEnumArgs*, void*) {
+  set_error("vipsy_cdm_enum_elbo_grad: not built yet");
+  return VIPSY_ERR_UNSUPPORTED;
+}
+size_t vipsy_cdm_score_workspace_bytes(const VipsyCdmScoreArgs*) { return 0; }
+int vipsy_cdm_score_elbo_grad(const VipsyCdmScoreArgs*, void*) {
+  set_error("vipsy_cdm_score_elbo_grad: not built yet");
+  return VIPSY_ERR_UNSUPPORTED;
+}
+#endif
+
+}  // extern "C"

@@ -1,0 +1,416 @@
+// Unidimensional IRT (K == 1): fused sampling + 1..4PL link + masked Bernoulli
+// log-likelihood + every gradient, S Monte-Carlo particles per person, one pass.
+//
+// Replaces, per SVI.step (vi.py:503-516), the whole Trace_ELBO evaluation of
+// BaseIRT.model (vi.py:574-595, _get_p_data vi.py:617-625, irt_1pl..4pl
+// vi.py:22-66) under the VIRT / VaeIRT Normal guide (vi.py:701-705, 677-684).
+//
+// Mapping: one lane = one person, a warp = 32 consecutive persons (a "tile").
+// The tile's response codes are staged in shared memory with 16-byte loads;
+// item parameters sit in shared memory as one float4 per item (broadcast reads).
+// For each item the lane runs the S particles out of registers (eps[SC]) -- the
+// logits never leave the register file.  Per-item gradient sums are reduced
+// across the warp with a transposing butterfly (6 shuffles for 4 quantities)
+// into warp-private shared-memory accumulators; CTAs write one partial row each
+// and a second tiny kernel sums the rows in a fixed order => bit-reproducible.
+//
+// Arithmetic follows the reference's formula class: P in fp32,
+// clamp to [eps, 1-eps], log P / log(1-P), zero gradient where the clamp fires.
+// Roof: 3-4 MUFU per (person, item, particle) evaluation => SFU-bound, not HBM.
+#include "common.cuh"
+
+namespace vipsy {
+
+constexpr int kUniWarps = 4;
+constexpr int kUniThreads = kUniWarps * 32;
+
+struct IrtUniParams {
+  const uint8_t* y;
+  int64_t ld_y;
+  const int64_t* idx;
+  const float* mu;
+  const float* sigma;
+  const float* eps;
+  const float *a, *b, *c, *d;
+  int64_t B;
+  int J, S;
+  float D, scale, baseline;
+  uint64_t seed, offset;
+  int64_t person_offset;
+  float* d_mu;
+  float* d_sigma;
+  float* item_partial;    // [grid][NQ*J]
+  double* loss_partial;   // [grid]
+  int contiguous;         // rows of the batch are contiguous in y (no idx, ld == J)
+  int want_grad;
+};
+
+__host__ __device__ inline size_t align16(size_t x) { return (x + 15) & ~size_t(15); }
+
+__host__ __device__ inline size_t uni_smem_bytes(int J, int NQ) {
+  size_t s = (size_t)J * 16;                        // float4 item table
+  s += align16((size_t)J * 4);                      // D*a*(d-c)
+  s += align16((size_t)kUniWarps * NQ * J * 4);     // warp-private item accumulators
+  s += (size_t)kUniWarps * align16((size_t)32 * J + 16);  // response tiles
+  return s;
+}
+
+// All SC particles of one (person, item) cell.  it = {A', B', c, d-c} with
+// A' = -D a log2(e), B' = -D b log2(e); t = T1*eps + T0 = -logit*log2(e).
+// Outputs (sums over the SC particles): W1 = sum w, W2 = sum w*eps with
+// w = dlb/dP * s(1-s); Gc = sum dlb/dP (1-s); Gd = sum dlb/dP s; Lj = sum log2 q
+// (SCORE: added per particle into lls instead).
+// FASTPATH (4PL, every item 1e-3 <= c, d <= 1-1e-3, d-c >= 1e-3): rational form
+// q = |cY e + dY| / (1+e), one reciprocal R = 1/((cY e + dY)(1+e)) yields both the
+// sigmoid and 1/q: 2.25 MUFU per evaluation instead of 3.25.
+template <int MODEL, bool SCORE, int SC, bool FASTPATH>
+__device__ __forceinline__ void item_evals(const float4 it, const float T0, const float T1, const float yflag,
+                                           const float (&eps)[SC], float (&lls)[SCORE ? SC : 1], float& W1,
+                                           float& W2, float& Gc, float& Gd, float& Lj) {
+  float prod = 1.f;
+  const float cY = it.z - yflag, dY = (it.z + it.w) - yflag;   // (c,d) for y=1, (c-1,d-1) for y=0
+#pragma unroll
+  for (int i = 0; i < SC; ++i) {
+    float t = fmaf(T1, eps[i], T0);
+    float w, q;
+    if constexpr (FASTPATH) {
+      t = fminf(fmaxf(t, -60.f), 60.f);
+      const float e = ex2_approx(t);
+      const float ope = 1.f + e;
+      const float num = fmaf(cY, e, dY);
+      const float R = rcp_approx(num * ope);
+      const float sgm = num * R;                   // 1/(1+e)
+      q = fabsf(num * sgm);                        // P or 1-P
+      const float us = ope * R;                    // u*s = 1/num  (u = dlb/dP)
+      const float uc = us * e;                     // u*(1-s)
+      w = uc * sgm;
+      Gc += uc;
+      Gd += us;
+    } else {
+      const float e = ex2_approx(t);
+      const float sgm = rcp_approx(1.f + e);
+      const float P = MODEL >= 3 ? fmaf(it.w, sgm, it.z) : sgm;
+      const float Pc = fminf(fmaxf(P, kEps32), kOneMinusEps32);
+      const float qs = Pc - yflag;
+      q = fabsf(qs);
+      if constexpr (MODEL >= 3) {
+        float u = rcp_approx(qs);
+        u = (P == Pc) ? u : 0.f;
+        const float us = u * sgm;
+        const float uc = u - us;
+        w = uc * sgm;
+        Gc += uc;
+        if constexpr (MODEL == 4) Gd += us;
+      } else {
+        w = (P == Pc) ? ((1.f - yflag) - sgm) : 0.f;
+      }
+    }
+    if constexpr (SCORE) {
+      lls[i] += lg2_approx(q);
+    } else {
+      prod *= q;                                   // q >= eps => 4 factors stay normal
+      if ((i & 3) == 3 || i == SC - 1) { Lj += lg2_approx(prod); prod = 1.f; }
+    }
+    W1 += w;
+    W2 = fmaf(w, eps[i], W2);
+  }
+}
+
+// MODEL: 1..4 (number of item parameters).  SCORE: REINFORCE estimator for the
+// guide parameters.  SC: particles kept in registers at once (S % SC == 0).
+// FAST (4PL only): compile in the rational-form path; each CTA checks the item
+// table once and uses it only if no item can reach the probability clamp.
+template <int MODEL, bool SCORE, int SC, bool FAST>
+__global__ void __launch_bounds__(kUniThreads, 4) irt_uni_kernel(const IrtUniParams p) {
+  constexpr int NQ = MODEL;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int J = p.J;
+  float4* tab = reinterpret_cast<float4*>(smem_raw);
+  float* agx = reinterpret_cast<float*>(smem_raw + (size_t)J * 16);
+  float* acc_all = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(agx) + align16((size_t)J * 4));
+  unsigned char* ytiles = reinterpret_cast<unsigned char*>(acc_all) + align16((size_t)kUniWarps * NQ * J * 4);
+  const size_t ytile_bytes = align16((size_t)32 * J + 16);
+
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float* acc = acc_all + (size_t)warp * NQ * J;
+  unsigned char* ytile = ytiles + (size_t)warp * ytile_bytes;
+
+  for (int j = threadIdx.x; j < J; j += kUniThreads) {
+    const float aj = MODEL >= 2 ? p.a[j] : 1.f;
+    const float cj = MODEL >= 3 ? p.c[j] : 0.f;
+    const float dj = MODEL == 4 ? p.d[j] : 1.f;
+    tab[j] = make_float4(-p.D * kLog2e * aj, -p.D * kLog2e * p.b[j], cj, dj - cj);
+    agx[j] = p.D * aj * (dj - cj);
+  }
+  for (int i = threadIdx.x; i < kUniWarps * NQ * J; i += kUniThreads) acc_all[i] = 0.f;
+  bool use_fast = false;
+  if (FAST) {   // every item bounded away from the clamp => rational form is safe
+    int ok = 1;
+    for (int j = threadIdx.x; j < J; j += kUniThreads) {
+      const float cj = p.c[j], dj = p.d[j];
+      ok &= (cj >= 1e-3f) && (dj <= 1.f - 1e-3f) && (dj - cj >= 1e-3f);
+    }
+    use_fast = __syncthreads_and(ok) != 0;
+  } else {
+    __syncthreads();
+  }
+
+  const float S_f = (float)p.S;
+  const float k_scale = p.scale / S_f;
+  double loss_acc = 0.0;
+
+  const int64_t ntiles = (p.B + 31) / 32;
+  const int64_t gwarp = (int64_t)blockIdx.x * kUniWarps + warp;
+  const int64_t nwarps = (int64_t)gridDim.x * kUniWarps;
+
+  for (int64_t tile = gwarp; tile < ntiles; tile += nwarps) {
+    const int64_t b0 = tile * 32;
+    const int64_t bi = b0 + lane;
+    const bool valid = bi < p.B;
+    const int rows = (int)min((int64_t)32, p.B - b0);
+
+    // ---- stage the tile's response codes ---------------------------------
+    int mis = 0;
+    if (p.contiguous) {
+      const unsigned char* g0 = p.y + b0 * (int64_t)J;
+      mis = (int)(reinterpret_cast<uintptr_t>(g0) & 15);
+      const int4* gal = reinterpret_cast<const int4*>(g0 - mis);
+      const int nvec = (mis + rows * J + 15) >> 4;
+      int4* dst = reinterpret_cast<int4*>(ytile);
+      int v = lane;
+      for (; v + 96 < nvec; v += 128) {
+        const int4 r0 = __ldg(gal + v), r1 = __ldg(gal + v + 32), r2 = __ldg(gal + v + 64), r3 = __ldg(gal + v + 96);
+        dst[v] = r0; dst[v + 32] = r1; dst[v + 64] = r2; dst[v + 96] = r3;
+      }
+      for (; v < nvec; v += 32) dst[v] = __ldg(gal + v);
+    } else {
+      for (int r = 0; r < rows; ++r) {
+        const int64_t row = p.idx ? p.idx[b0 + r] : (b0 + r);
+        const unsigned char* g = p.y + row * p.ld_y;
+        for (int i = lane; i < J; i += 32) ytile[r * J + i] = g[i];
+      }
+    }
+    __syncwarp();
+    const unsigned char* yrow = ytile + mis + lane * J;
+
+    const float mu = valid ? p.mu[bi] : 0.f;
+    const float sg = valid ? p.sigma[bi] : 1.f;
+    float se = 0.f, see = 0.f, G1 = 0.f, G2 = 0.f, Lsum = 0.f, sw1 = 0.f, sw2 = 0.f;
+
+    for (int s0 = 0; s0 < p.S; s0 += SC) {
+      // ---- noise for SC particles ----------------------------------------
+      float eps[SC];
+      if (p.eps) {
+#pragma unroll
+        for (int i = 0; i < SC; ++i) eps[i] = valid ? __ldg(p.eps + (int64_t)(s0 + i) * p.B + bi) : 0.f;
+      } else {
+        const uint64_t person = (uint64_t)(p.person_offset + bi);
+        if (SC >= 4) {
+#pragma unroll
+          for (int i = 0; i < SC; i += 4) {
+            const float4 z = normal4(p.seed, p.offset, person, (uint32_t)((s0 + i) >> 2));
+            eps[i] = z.x;
+            if (i + 1 < SC) eps[i + 1] = z.y;
+            if (i + 2 < SC) eps[i + 2] = z.z;
+            if (i + 3 < SC) eps[i + 3] = z.w;
+          }
+        } else {
+          const float4 z = normal4(p.seed, p.offset, person, (uint32_t)(s0 >> 2));
+          const float zz[4] = {z.x, z.y, z.z, z.w};
+#pragma unroll
+          for (int i = 0; i < SC; ++i) eps[i] = zz[(s0 + i) & 3];
+        }
+      }
+      float lls[SCORE ? SC : 1];
+#pragma unroll
+      for (int i = 0; i < SC; ++i) {
+        se += eps[i];
+        see = fmaf(eps[i], eps[i], see);
+        if (SCORE) lls[i] = 0.f;
+      }
+
+      // ---- items ----------------------------------------------------------
+      for (int j = 0; j < J; ++j) {
+        const unsigned code = valid ? (unsigned)yrow[j] : 255u;
+        const bool obs = code != 255u;
+        if (!__any_sync(0xffffffffu, obs)) continue;
+        float v[NQ];
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) v[q] = 0.f;
+        if (obs) {
+          const float4 it = tab[j];
+          const float yflag = code ? 0.f : 1.f;          // qs = P - yflag: P (y=1) or P-1 (y=0)
+          const float T0 = fmaf(it.x, mu, it.y), T1 = it.x * sg;
+          float W1 = 0.f, W2 = 0.f, Gc = 0.f, Gd = 0.f, Lj = 0.f;
+          if (FAST && use_fast)
+            item_evals<MODEL, SCORE, SC, true>(it, T0, T1, yflag, eps, lls, W1, W2, Gc, Gd, Lj);
+          else
+            item_evals<MODEL, SCORE, SC, false>(it, T0, T1, yflag, eps, lls, W1, W2, Gc, Gd, Lj);
+          Lsum += Lj;
+          G1 = fmaf(agx[j], W1, G1);
+          G2 = fmaf(agx[j], W2, G2);
+          v[0] = W1;
+          if constexpr (NQ >= 2) v[1] = fmaf(sg, W2, mu * W1);   // sum_s w x_s
+          if constexpr (NQ >= 3) v[2] = Gc;
+          if constexpr (NQ >= 4) v[3] = Gd;
+        }
+        if (p.want_grad) {
+          const float r = warp_sum_multi<NQ>(v, lane);
+          const int own = warp_sum_multi_owner<NQ>(lane);
+          if (own >= 0) acc[own * J + j] += r;
+        }
+      }
+
+      if (SCORE) {
+        const float lsg = __logf(sg);
+#pragma unroll
+        for (int i = 0; i < SC; ++i) {
+          const float x = fmaf(sg, eps[i], mu);
+          const float e2 = eps[i] * eps[i];
+          const float wgt = p.scale * (kLn2 * lls[i] - 0.5f * x * x + 0.5f * e2 + lsg) - p.baseline;
+          sw1 = fmaf(wgt, eps[i], sw1);
+          sw2 = fmaf(wgt, e2 - 1.f, sw2);
+          Lsum += lls[i];
+        }
+      }
+    }
+    __syncwarp();   // everyone is done with ytile before the next tile overwrites it
+
+    // ---- per-person epilogue ---------------------------------------------
+    if (valid) {
+      const float sumx = fmaf(sg, se, S_f * mu);
+      const float sumxe = fmaf(sg, see, mu * se);
+      const float sumx2 = fmaf(S_f * mu, mu, fmaf(2.f * mu * sg, se, sg * sg * see));
+      const float elbo = kLn2 * Lsum - 0.5f * sumx2 + 0.5f * see + S_f * logf(sg);
+      loss_acc -= (double)(k_scale * elbo);
+      if (p.d_mu) {
+        if (SCORE) {
+          const float inv = 1.f / (S_f * sg);
+          p.d_mu[bi] = -sw1 * inv;
+          p.d_sigma[bi] = -sw2 * inv;
+        } else {
+          p.d_mu[bi] = -k_scale * (G1 - sumx);
+          p.d_sigma[bi] = -k_scale * (G2 - sumxe) - p.scale / sg;
+        }
+      }
+    }
+  }
+
+  // ---- CTA partials ---------------------------------------------------------
+  __shared__ double loss_sm[kUniWarps];
+  loss_acc = warp_sum(loss_acc);
+  if (lane == 0) loss_sm[warp] = loss_acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+#pragma unroll
+    for (int w = 0; w < kUniWarps; ++w) t += loss_sm[w];
+    p.loss_partial[blockIdx.x] = t;
+  }
+  if (p.want_grad) {
+    for (int i = threadIdx.x; i < NQ * J; i += kUniThreads) {
+      float t = 0.f;
+#pragma unroll
+      for (int w = 0; w < kUniWarps; ++w) t += acc_all[(size_t)w * NQ * J + i];
+      const int q = i / J, j = i - q * J;
+      if (q < 2) t *= p.D * tab[j].w;     // d l / d(b, a) carry D (d - c)
+      p.item_partial[(size_t)blockIdx.x * NQ * J + i] = t;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+constexpr int kUniMaxCtasPerSM = 8;
+
+template <int MODEL, bool SCORE, int SC, bool FAST>
+static int launch_one(IrtUniParams& p, size_t smem, cudaStream_t st, int* grid_out) {
+  auto k = irt_uni_kernel<MODEL, SCORE, SC, FAST>;
+  static int occ = 0;   // per instantiation
+  static size_t occ_smem = ~size_t(0);
+  if (smem > 48 * 1024) VIPSY_CUDA_CHECK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  if (occ == 0 || occ_smem != smem) {
+    VIPSY_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, kUniThreads, smem));
+    occ_smem = smem;
+    if (occ < 1) occ = 1;
+    if (occ > kUniMaxCtasPerSM) occ = kUniMaxCtasPerSM;
+  }
+  const int64_t ntiles = (p.B + 31) / 32;
+  int64_t ctas = (ntiles + kUniWarps - 1) / kUniWarps;
+  const int64_t cap = (int64_t)num_sms() * occ;
+  if (ctas > cap) ctas = cap;
+  if (ctas < 1) ctas = 1;
+  *grid_out = (int)ctas;
+  k<<<(int)ctas, kUniThreads, smem, st>>>(p);
+  VIPSY_CUDA_CHECK(cudaGetLastError());
+  return VIPSY_OK;
+}
+
+template <int MODEL, bool SCORE, bool FAST>
+static int launch_sc(int SC, IrtUniParams& p, size_t smem, cudaStream_t st, int* grid) {
+  switch (SC) {
+    case 32: return launch_one<MODEL, SCORE, 32, FAST>(p, smem, st, grid);
+    case 16: return launch_one<MODEL, SCORE, 16, FAST>(p, smem, st, grid);
+    case 8: return launch_one<MODEL, SCORE, 8, FAST>(p, smem, st, grid);
+    case 4: return launch_one<MODEL, SCORE, 4, FAST>(p, smem, st, grid);
+    case 2: return launch_one<MODEL, SCORE, 2, FAST>(p, smem, st, grid);
+    default: return launch_one<MODEL, SCORE, 1, FAST>(p, smem, st, grid);
+  }
+}
+
+template <bool SCORE>
+static int launch_model(int model, bool fast, int SC, IrtUniParams& p, size_t smem, cudaStream_t st, int* grid) {
+  switch (model) {
+    case VIPSY_IRT_1PL: return launch_sc<1, SCORE, false>(SC, p, smem, st, grid);
+    case VIPSY_IRT_2PL: return launch_sc<2, SCORE, false>(SC, p, smem, st, grid);
+    case VIPSY_IRT_3PL: return launch_sc<3, SCORE, false>(SC, p, smem, st, grid);
+    default:
+      return fast ? launch_sc<4, SCORE, true>(SC, p, smem, st, grid)
+                  : launch_sc<4, SCORE, false>(SC, p, smem, st, grid);
+  }
+}
+
+size_t irt_uni_workspace_bytes(const VipsyIrtArgs* a) {
+  const int rows = num_sms() * kUniMaxCtasPerSM;
+  return align16((size_t)rows * 8) + (size_t)rows * a->model * a->n_items * 4;
+}
+
+int irt_uni_launch(const VipsyIrtArgs* a, cudaStream_t st) {
+  const int J = a->n_items, NQ = a->model;
+  const size_t smem = uni_smem_bytes(J, NQ);
+  VIPSY_REQUIRE(smem <= 227 * 1024, VIPSY_ERR_UNSUPPORTED,
+                "vipsy_irt_elbo_grad(K=1): J=%d needs %zu B of shared memory (max 232448)", J, smem);
+  VIPSY_REQUIRE(a->workspace && a->workspace_bytes >= irt_uni_workspace_bytes(a), VIPSY_ERR_WORKSPACE,
+                "vipsy_irt_elbo_grad: workspace %zu B < required %zu B", a->workspace_bytes,
+                irt_uni_workspace_bytes(a));
+  IrtUniParams p;
+  p.y = a->y; p.ld_y = a->y_row_stride; p.idx = a->idx;
+  p.mu = a->mu; p.sigma = a->sigma; p.eps = a->eps;
+  p.a = a->a; p.b = a->b; p.c = a->c; p.d = a->d;
+  p.B = a->batch; p.J = J; p.S = a->n_particles;
+  p.D = a->D; p.scale = a->scale; p.baseline = a->baseline;
+  p.seed = a->seed; p.offset = a->offset; p.person_offset = a->person_offset;
+  p.d_mu = a->d_mu; p.d_sigma = a->d_sigma;
+  p.loss_partial = reinterpret_cast<double*>(a->workspace);
+  p.item_partial = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(a->workspace) +
+                                            align16((size_t)num_sms() * kUniMaxCtasPerSM * 8));
+  p.contiguous = (a->idx == nullptr && a->y_row_stride == J) ? 1 : 0;
+  p.want_grad = (a->d_b || a->d_a || a->d_c || a->d_d) ? 1 : 0;
+
+  int SC = 32;
+  while (SC > 1 && (a->n_particles % SC) != 0) SC >>= 1;
+  const bool fast = a->model == VIPSY_IRT_4PL && !(a->flags & VIPSY_IRT_FLAG_STRICT);
+  int grid = 0;
+  int rc = a->estimator == VIPSY_EST_SCORE ? launch_model<true>(a->model, fast, SC, p, smem, st, &grid)
+                                           : launch_model<false>(a->model, fast, SC, p, smem, st, &grid);
+  if (rc != VIPSY_OK) return rc;
+
+  FinalizeSegs segs{};
+  segs.n = NQ;
+  float* outs[4] = {a->d_b, a->d_a, a->d_c, a->d_d};
+  for (int q = 0; q < NQ; ++q) { segs.out[q] = outs[q]; segs.cols[q] = J; segs.mask[q] = nullptr; }
+  if (NQ >= 2) segs.mask[1] = a->a_free;
+  return launch_finalize(p.want_grad ? p.item_partial : nullptr, p.want_grad ? grid : 0, p.want_grad ? NQ * J : 0,
+                         -a->scale / (float)a->n_particles, segs, p.loss_partial, grid, a->loss, st);
+}
+
+}  // namespace vipsy

@@ -1,0 +1,224 @@
+// Error reporting, deterministic partial-sum finalisation and the data-format
+// helpers either side of the ELBO path (response packing, eta table, noise fill).
+#include <stdarg.h>
+#include <string.h>
+
+#include "common.cuh"
+
+namespace vipsy {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+// ---------------------------------------------------------------------------
+// out[c] = alpha * sum_r partial[r][c], rows summed in a fixed order with fp64
+// accumulation.  One CTA per 32 columns; warp w walks rows w, w+8, ...
+// (coalesced 128-byte row segments), the 8 warp totals are combined in order.
+// ---------------------------------------------------------------------------
+struct FinalizeArgs {
+  const float* partial;
+  int rows, cols;
+  float alpha;
+  FinalizeSegs segs;
+  const double* loss_partial;
+  int loss_rows;
+  double* loss_out;
+};
+
+constexpr int kFinWarps = 8;
+
+__global__ void __launch_bounds__(kFinWarps * 32) finalize_kernel(const FinalizeArgs a) {
+  __shared__ double sm[kFinWarps][33];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int col = blockIdx.x * 32 + lane;
+  if (blockIdx.x * 32 < a.cols) {
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    if (col < a.cols) {
+      int r = warp;
+      for (; r + 3 * kFinWarps < a.rows; r += 4 * kFinWarps) {
+        const float v0 = a.partial[(size_t)r * a.cols + col];
+        const float v1 = a.partial[(size_t)(r + kFinWarps) * a.cols + col];
+        const float v2 = a.partial[(size_t)(r + 2 * kFinWarps) * a.cols + col];
+        const float v3 = a.partial[(size_t)(r + 3 * kFinWarps) * a.cols + col];
+        s0 += v0; s1 += v1; s2 += v2; s3 += v3;
+      }
+      for (; r < a.rows; r += kFinWarps) s0 += a.partial[(size_t)r * a.cols + col];
+    }
+    sm[warp][lane] = (s0 + s1) + (s2 + s3);
+    __syncthreads();
+    if (warp == 0 && col < a.cols) {
+      double t = 0.0;
+#pragma unroll
+      for (int w = 0; w < kFinWarps; ++w) t += sm[w][lane];
+      int c = col;
+      for (int i = 0; i < a.segs.n; ++i) {
+        if (c < a.segs.cols[i]) {
+          if (a.segs.out[i]) {
+            float v = a.alpha * (float)t;
+            if (a.segs.mask[i] && !a.segs.mask[i][c]) v = 0.f;
+            a.segs.out[i][c] = v;
+          }
+          break;
+        }
+        c -= a.segs.cols[i];
+      }
+    }
+  }
+  if (blockIdx.x == gridDim.x - 1 && a.loss_out) {   // last CTA also folds the loss partials
+    __syncthreads();
+    double t = 0.0;
+    for (int r = threadIdx.x; r < a.loss_rows; r += blockDim.x) t += a.loss_partial[r];
+    t = warp_sum(t);
+    if (lane == 0) sm[warp][32] = t;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double tot = 0.0;
+      for (int w = 0; w < kFinWarps; ++w) tot += sm[w][32];
+      *a.loss_out = tot;
+    }
+  }
+}
+
+int launch_finalize(const float* partial, int rows, int cols, float alpha, const FinalizeSegs& segs,
+                    const double* loss_partial, int loss_rows, double* loss_out, cudaStream_t stream) {
+  FinalizeArgs a{partial, rows, cols, alpha, segs, loss_partial, loss_rows, loss_out};
+  int grid = (cols + 31) / 32;
+  if (grid < 1) grid = 1;
+  finalize_kernel<<<grid, kFinWarps * 32, 0, stream>>>(a);
+  VIPSY_CUDA_CHECK(cudaGetLastError());
+  return VIPSY_OK;
+}
+
+// ---------------------------------------------------------------------------
+// float responses with NaN = missing (vi.py:621) -> one byte per cell
+// ---------------------------------------------------------------------------
+__global__ void pack_responses_kernel(const float* __restrict__ y, int64_t n, uint8_t* __restrict__ out) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x * 4;
+  for (int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < n; i += stride) {
+    if (i + 3 < n && ((reinterpret_cast<uintptr_t>(y + i) & 15) == 0) &&
+        ((reinterpret_cast<uintptr_t>(out + i) & 3) == 0)) {
+      const float4 v = *reinterpret_cast<const float4*>(y + i);
+      uchar4 c;
+      c.x = v.x != v.x ? 255 : (v.x != 0.f);
+      c.y = v.y != v.y ? 255 : (v.y != 0.f);
+      c.z = v.z != v.z ? 255 : (v.z != 0.f);
+      c.w = v.w != v.w ? 255 : (v.w != 0.f);
+      *reinterpret_cast<uchar4*>(out + i) = c;
+    } else {
+      for (int64_t k = i; k < n && k < i + 4; ++k) {
+        const float v = y[k];
+        out[k] = v != v ? 255 : (v != 0.f);
+      }
+    }
+  }
+}
+
+// eta table, exactly 0/1.  DINA: every required attribute mastered.  DINO as the
+// reference executes it (vi.py:95-98): 1 iff the item needs at
+// least two attributes and at least one of them is mastered.
+__global__ void eta_table_kernel(const uint32_t* __restrict__ qmask, int J, int K, int model,
+                                 uint8_t* __restrict__ eta) {
+  const int64_t n = (int64_t)J << K;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const uint32_t c = (uint32_t)(i / J);
+    const uint32_t q = qmask[i % J];
+    uint8_t e;
+    if (model == VIPSY_CDM_DINA) e = (c & q) == q;
+    else e = (__popc(q) >= 2) && ((c & q) != 0);
+    eta[i] = e;
+  }
+}
+
+template <bool NORMAL>
+__global__ void fill_noise_kernel(float* __restrict__ out, int S, int64_t B, int K, uint64_t seed,
+                                  uint64_t offset, int64_t person_offset) {
+  const int64_t per_person = (int64_t)S * K;
+  const int64_t blocks_pp = (per_person + 3) / 4;
+  const int64_t total = B * blocks_pp;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t b = i / blocks_pp;
+    const uint32_t blk = (uint32_t)(i % blocks_pp);
+    const uint4 r = philox_draw(seed, offset, (uint64_t)(person_offset + b), blk);
+    float4 z;
+    if (NORMAL) z = box_muller4(r);
+    else z = make_float4(u01(r.x), u01(r.y), u01(r.z), u01(r.w));
+    const float zz[4] = {z.x, z.y, z.z, z.w};
+    for (int e = 0; e < 4; ++e) {
+      const int64_t n = (int64_t)blk * 4 + e;
+      if (n < per_person) {
+        const int64_t s = n / K, k = n % K;
+        out[(s * B + b) * K + k] = zz[e];
+      }
+    }
+  }
+}
+
+}  // namespace vipsy
+
+using namespace vipsy;
+
+extern "C" {
+
+int vipsy_abi_version(void) { return VIPSY_ABI_VERSION; }
+const char* vipsy_last_error(void) { return g_err; }
+
+int vipsy_pack_responses(const float* y_f32, int64_t n_cells, uint8_t* codes, void* stream) {
+  VIPSY_REQUIRE(y_f32 && codes && n_cells >= 0, VIPSY_ERR_ARG, "vipsy_pack_responses: null argument");
+  if (n_cells == 0) return VIPSY_OK;
+  int64_t blocks = (n_cells / 4 + 255) / 256;
+  const int64_t cap = (int64_t)num_sms() * 16;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  pack_responses_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(y_f32, n_cells, codes);
+  VIPSY_CUDA_CHECK(cudaGetLastError());
+  return VIPSY_OK;
+}
+
+int vipsy_cdm_eta_table(const uint32_t* qmask, int32_t n_items, int32_t n_attrs, int32_t model,
+                        uint8_t* eta, void* stream) {
+  VIPSY_REQUIRE(qmask && eta, VIPSY_ERR_ARG, "vipsy_cdm_eta_table: null argument");
+  VIPSY_REQUIRE(n_items > 0 && n_attrs > 0 && n_attrs <= 20, VIPSY_ERR_UNSUPPORTED,
+                "vipsy_cdm_eta_table: need 0 < J, 0 < K <= 20 (got J=%d K=%d)", n_items, n_attrs);
+  VIPSY_REQUIRE(model == VIPSY_CDM_DINA || model == VIPSY_CDM_DINO, VIPSY_ERR_ARG,
+                "vipsy_cdm_eta_table: unknown model %d", model);
+  const int64_t n = (int64_t)n_items << n_attrs;
+  int64_t blocks = (n + 255) / 256;
+  if (blocks > num_sms() * 8) blocks = num_sms() * 8;
+  eta_table_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(qmask, n_items, n_attrs, model, eta);
+  VIPSY_CUDA_CHECK(cudaGetLastError());
+  return VIPSY_OK;
+}
+
+static int fill_noise(bool normal, float* out, int32_t S, int64_t B, int32_t K, uint64_t seed,
+                      uint64_t offset, int64_t person_offset, void* stream) {
+  VIPSY_REQUIRE(out && S > 0 && B >= 0 && K > 0, VIPSY_ERR_ARG, "vipsy_fill_*: bad argument");
+  if (B == 0) return VIPSY_OK;
+  const int64_t total = B * (((int64_t)S * K + 3) / 4);
+  int64_t blocks = (total + 255) / 256;
+  if (blocks > num_sms() * 8) blocks = num_sms() * 8;
+  if (normal)
+    fill_noise_kernel<true><<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(out, S, B, K, seed, offset, person_offset);
+  else
+    fill_noise_kernel<false><<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(out, S, B, K, seed, offset, person_offset);
+  VIPSY_CUDA_CHECK(cudaGetLastError());
+  return VIPSY_OK;
+}
+
+int vipsy_fill_normal(float* out, int32_t S, int64_t B, int32_t K, uint64_t seed, uint64_t offset,
+                      int64_t person_offset, void* stream) {
+  return fill_noise(true, out, S, B, K, seed, offset, person_offset, stream);
+}
+int vipsy_fill_uniform(float* out, int32_t S, int64_t B, int32_t K, uint64_t seed, uint64_t offset,
+                       int64_t person_offset, void* stream) {
+  return fill_noise(false, out, S, B, K, seed, offset, person_offset, stream);
+}
+
+}  // extern "C"

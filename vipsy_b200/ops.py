@@ -1,0 +1,209 @@
+"""Tensor-level wrappers over the C ABI (include/vipsy_b200.h).
+
+Each function takes CUDA tensors, launches on torch's current stream and returns
+CUDA tensors without synchronising.  These are what the estimator classes in
+``vipsy_b200.models`` call once per ``SVI.step`` (vi.py:503-516).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, Optional
+
+import torch
+
+from . import _native as N
+
+_workspaces: Dict[tuple, torch.Tensor] = {}
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _f32(t: Optional[torch.Tensor], name: str, numel: Optional[int] = None):
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise ValueError(f"{name} must be a CUDA tensor (no CPU fallback)")
+    t = t.detach()
+    if t.dtype != torch.float32:
+        t = t.float()
+    t = t.contiguous()
+    if numel is not None and t.numel() != numel:
+        raise ValueError(f"{name}: expected {numel} elements, got {tuple(t.shape)}")
+    return t
+
+
+def _workspace(kind: str, nbytes: int, device) -> torch.Tensor:
+    key = (kind, device.index, torch.cuda.current_stream().cuda_stream)
+    w = _workspaces.get(key)
+    if w is None or w.numel() < nbytes:
+        w = torch.empty(max(nbytes, 1), dtype=torch.uint8, device=device)
+        _workspaces[key] = w
+    return w
+
+
+def pack_responses(y: torch.Tensor) -> torch.Tensor:
+    """float matrix with NaN = missing (the reference's ``data``) -> uint8 codes 0/1/255."""
+    if y.dtype == torch.uint8:
+        return y.contiguous()
+    yf = _f32(y, "y")
+    out = torch.empty(yf.shape, dtype=torch.uint8, device=yf.device)
+    N.check(N.lib().vipsy_pack_responses(_ptr(yf), yf.numel(), _ptr(out), _stream()))
+    return out
+
+
+def fill_normal(S: int, B: int, K: int, seed: int, offset: int, person_offset: int = 0, device="cuda"):
+    out = torch.empty((S, B, K), dtype=torch.float32, device=device)
+    N.check(N.lib().vipsy_fill_normal(_ptr(out), S, B, K, seed, offset, person_offset, _stream()))
+    return out
+
+
+def fill_uniform(S: int, B: int, K: int, seed: int, offset: int, person_offset: int = 0, device="cuda"):
+    out = torch.empty((S, B, K), dtype=torch.float32, device=device)
+    N.check(N.lib().vipsy_fill_uniform(_ptr(out), S, B, K, seed, offset, person_offset, _stream()))
+    return out
+
+
+def qmask_from_q(q: torch.Tensor) -> torch.Tensor:
+    """K x J 0/1 Q-matrix (vi.py:741) -> J uint32-in-int32 bit masks, bit k = Q[k][j]."""
+    K, J = q.shape
+    w = (2 ** torch.arange(K, dtype=torch.int64, device=q.device)).unsqueeze(1)
+    return ((q != 0).to(torch.int64) * w).sum(0).to(torch.int32).contiguous()
+
+
+def cdm_eta_table(qmask: torch.Tensor, K: int, model: str) -> torch.Tensor:
+    J = qmask.numel()
+    out = torch.empty((2 ** K, J), dtype=torch.uint8, device=qmask.device)
+    N.check(N.lib().vipsy_cdm_eta_table(_ptr(qmask), J, K, N.CDM_MODEL[model], _ptr(out), _stream()))
+    return out
+
+
+def irt_elbo_grad(
+    y: torch.Tensor,                       # n_rows x J uint8 codes (pack_responses)
+    mu: torch.Tensor,                      # B x K
+    *,
+    sigma: Optional[torch.Tensor] = None,  # K == 1: B (x1)
+    chol: Optional[torch.Tensor] = None,   # K > 1: K x K | B x K x K | B x K(K+1)/2
+    eps: Optional[torch.Tensor] = None,    # S x B x K, or None -> in-kernel Philox
+    n_particles: Optional[int] = None,
+    a: Optional[torch.Tensor] = None, b: torch.Tensor = None,
+    c: Optional[torch.Tensor] = None, d: Optional[torch.Tensor] = None,
+    model: str = "irt_2pl", D: float = 1.0, scale: float = 1.0,
+    estimator: str = "pathwise", baseline: float = 0.0,
+    idx: Optional[torch.Tensor] = None,
+    a_free: Optional[torch.Tensor] = None,
+    chol_packed: bool = False, chol_raw: bool = False,
+    seed: int = 0, offset: int = 0, person_offset: int = 0,
+    want_grad: bool = True, strict: bool = False,
+) -> Dict[str, Optional[torch.Tensor]]:
+    """One fused ELBO + gradient evaluation (Trace_ELBO.loss_and_grads, vi.py:507)."""
+    if not y.is_cuda or y.dtype != torch.uint8:
+        raise ValueError("y must be a CUDA uint8 code matrix (see pack_responses)")
+    if y.dim() != 2 or y.stride(1) != 1:
+        raise ValueError("y must be 2-D with unit column stride")
+    dev = y.device
+    n_rows, J = y.shape
+    mu_ = _f32(mu, "mu")
+    if mu_.dim() == 1:
+        mu_ = mu_.unsqueeze(1)
+    B, K = mu_.shape
+    if eps is not None:
+        eps_ = _f32(eps, "eps")
+        S = eps_.numel() // max(B * K, 1)
+        if eps_.numel() != S * B * K:
+            raise ValueError(f"eps must be S x B x K, got {tuple(eps.shape)}")
+    else:
+        eps_ = None
+        S = int(n_particles or 1)
+    m = N.IRT_MODEL[model]
+    args = N.IrtArgs()
+    args.n_rows, args.batch, args.n_items, args.n_dims, args.n_particles = n_rows, B, J, K, S
+    args.model, args.estimator = m, N.EST[estimator]
+    args.D, args.scale, args.baseline = float(D), float(scale), float(baseline)
+    args.flags = N.IRT_FLAG_STRICT if strict else 0
+    args.y, args.y_row_stride = _ptr(y), y.stride(0)
+    idx_ = None
+    if idx is not None:
+        idx_ = idx.to(device=dev, dtype=torch.int64).contiguous()
+        if idx_.numel() != B:
+            raise ValueError("idx must have B entries")
+    args.idx = _ptr(idx_)
+    args.mu, args.eps = _ptr(mu_), _ptr(eps_)
+    args.seed, args.offset, args.person_offset = seed, offset, person_offset
+    a_ = _f32(a, "a", K * J) if m >= 2 else None
+    b_ = _f32(b, "b", J)
+    c_ = _f32(c, "c", J) if m >= 3 else None
+    d_ = _f32(d, "d", J) if m >= 4 else None
+    args.a, args.b, args.c, args.d = _ptr(a_), _ptr(b_), _ptr(c_), _ptr(d_)
+    af_ = None
+    if a_free is not None and m >= 2:
+        af_ = a_free.to(device=dev, dtype=torch.uint8).contiguous()
+    args.a_free = _ptr(af_)
+
+    out: Dict[str, Optional[torch.Tensor]] = {}
+    loss = torch.empty(1, dtype=torch.float64, device=dev)
+    args.loss = _ptr(loss)
+    sg_ = ch_ = None
+    if K == 1:
+        sg_ = _f32(sigma, "sigma", B)
+        args.sigma, args.cov_mode = _ptr(sg_), N.COV_DIAG1
+    else:
+        ch_ = _f32(chol, "chol")
+        tri = K * (K + 1) // 2
+        if ch_.numel() == K * K and not chol_packed and ch_.dim() == 2:
+            args.cov_mode, args.chol_layout = N.COV_SHARED, N.CHOL_DENSE
+        elif chol_packed:
+            if ch_.numel() == tri:
+                args.cov_mode = N.COV_SHARED
+            elif ch_.numel() == B * tri:
+                args.cov_mode = N.COV_PERSON
+            else:
+                raise ValueError("packed chol must hold K(K+1)/2 or B*K(K+1)/2 values")
+            args.chol_layout = N.CHOL_PACKED
+        elif ch_.numel() == B * K * K:
+            args.cov_mode, args.chol_layout = N.COV_PERSON, N.CHOL_DENSE
+        else:
+            raise ValueError(f"chol shape {tuple(chol.shape)} does not match K={K}, B={B}")
+        args.chol, args.chol_raw = _ptr(ch_), int(bool(chol_raw))
+    if want_grad:
+        d_mu = torch.empty((B, K), dtype=torch.float32, device=dev)
+        args.d_mu = _ptr(d_mu)
+        out["d_mu"] = d_mu
+        if K == 1:
+            d_sigma = torch.empty((B, 1), dtype=torch.float32, device=dev)
+            args.d_sigma = _ptr(d_sigma)
+            out["d_sigma"] = d_sigma
+        else:
+            d_chol = torch.zeros_like(ch_)
+            args.d_chol = _ptr(d_chol)
+            out["d_chol"] = d_chol
+        # item gradients live in one packed fp32 buffer [d_b | d_a | d_c | d_d] so a
+        # person-sharded job all-reduces it with a single collective
+        ncol = J + (K * J if m >= 2 else 0) + (J if m >= 3 else 0) + (J if m >= 4 else 0)
+        packed = torch.empty(ncol, dtype=torch.float32, device=dev)
+        out["item_grads"] = packed
+        o = 0
+        out["d_b"] = packed[o:o + J].view(1, J); o += J
+        args.d_b = out["d_b"].data_ptr()
+        if m >= 2:
+            out["d_a"] = packed[o:o + K * J].view(K, J); o += K * J
+            args.d_a = out["d_a"].data_ptr()
+        if m >= 3:
+            out["d_c"] = packed[o:o + J].view(1, J); o += J
+            args.d_c = out["d_c"].data_ptr()
+        if m >= 4:
+            out["d_d"] = packed[o:o + J].view(1, J); o += J
+            args.d_d = out["d_d"].data_ptr()
+    L = N.lib()
+    nbytes = L.vipsy_irt_workspace_bytes(C.byref(args))
+    ws = _workspace("irt", nbytes, dev)
+    args.workspace, args.workspace_bytes = _ptr(ws), ws.numel()
+    N.check(L.vipsy_irt_elbo_grad(C.byref(args), _stream()))
+    out["loss"] = loss
+    out["_keepalive"] = (mu_, sg_, ch_, eps_, a_, b_, c_, d_, af_, idx_, ws)
+    return out
