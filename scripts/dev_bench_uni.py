@@ -3,6 +3,7 @@ import sys, time, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from vipsy_b200 import ops
+from vipsy_b200.clocks import ClockSampler
 
 
 def timeit(fn, warm=3, it=10):
@@ -36,10 +37,12 @@ def case(N, J, S, model, missing=0.0, strict=False, inject=False):
         off[0] += 1
         return ops.irt_elbo_grad(y, mu, sigma=sg, eps=eps, n_particles=S, a=a, b=b, c=c, d=d, model=model,
                                  seed=1, offset=off[0], strict=strict)
-    ms = timeit(run)
+    with ClockSampler() as cs:
+        ms = timeit(run, it=30)
     ev = N * J * S
+    ck = cs.summary()
     print(f"N={N} J={J} S={S} {model} missing={missing} strict={strict} inject={inject}: "
-          f"{ms:.3f} ms  {ev / ms * 1e3:.3e} evals/s", flush=True)
+          f"{ms:.3f} ms  {ev / ms * 1e3:.3e} evals/s  clk={ck['sm_mhz']} {ck['reasons']} {ck['power_w_max']}W", flush=True)
 
 
 if __name__ == "__main__":

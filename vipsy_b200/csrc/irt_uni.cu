@@ -14,8 +14,8 @@
 // into warp-private shared-memory accumulators; CTAs write one partial row each
 // and a second tiny kernel sums the rows in a fixed order => bit-reproducible.
 //
-// Arithmetic follows the reference's formula class: P in fp32,
-// clamp to [eps, 1-eps], log P / log(1-P), zero gradient where the clamp fires.
+// Arithmetic follows the reference's formulas: probability, clamp to
+// [eps, 1-eps], log, zero gradient where the clamp fires -- see item_evals().
 // Roof: 3-4 MUFU per (person, item, particle) evaluation => SFU-bound, not HBM.
 #include "common.cuh"
 
@@ -49,71 +49,129 @@ __host__ __device__ inline size_t align16(size_t x) { return (x + 15) & ~size_t(
 
 __host__ __device__ inline size_t uni_smem_bytes(int J, int NQ) {
   size_t s = (size_t)J * 16;                        // float4 item table
-  s += align16((size_t)J * 4);                      // D*a*(d-c)
+  s += align16((size_t)J * 8);                      // {D*a*(d-c), 1-d}
   s += align16((size_t)kUniWarps * NQ * J * 4);     // warp-private item accumulators
   s += (size_t)kUniWarps * align16((size_t)32 * J + 16);  // response tiles
   return s;
 }
 
-// All SC particles of one (person, item) cell.  it = {A', B', c, d-c} with
-// A' = -D a log2(e), B' = -D b log2(e); t = T1*eps + T0 = -logit*log2(e).
-// Outputs (sums over the SC particles): W1 = sum w, W2 = sum w*eps with
-// w = dlb/dP * s(1-s); Gc = sum dlb/dP (1-s); Gd = sum dlb/dP s; Lj = sum log2 q
-// (SCORE: added per particle into lls instead).
-// FASTPATH (4PL, every item 1e-3 <= c, d <= 1-1e-3, d-c >= 1e-3): rational form
-// q = |cY e + dY| / (1+e), one reciprocal R = 1/((cY e + dY)(1+e)) yields both the
-// sigmoid and 1/q: 2.25 MUFU per evaluation instead of 3.25.
+// ---- 1- and 2-wide fp32 helpers: sm_100's packed FFMA2/FADD2/FMUL2 halve the
+// issue slots of the non-SFU math, which is what this kernel runs out of first.
+__device__ __forceinline__ float vfma(float a, float b, float c) { return fmaf(a, b, c); }
+__device__ __forceinline__ float2 vfma(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
+__device__ __forceinline__ float vmul(float a, float b) { return a * b; }
+__device__ __forceinline__ float2 vmul(float2 a, float2 b) { return __fmul2_rn(a, b); }
+__device__ __forceinline__ float vadd(float a, float b) { return a + b; }
+__device__ __forceinline__ float2 vadd(float2 a, float2 b) { return __fadd2_rn(a, b); }
+__device__ __forceinline__ float vex2(float a) { return ex2_approx(a); }
+__device__ __forceinline__ float2 vex2(float2 a) { return make_float2(ex2_approx(a.x), ex2_approx(a.y)); }
+__device__ __forceinline__ float vrcp(float a) { return rcp_approx(a); }
+__device__ __forceinline__ float2 vrcp(float2 a) { return make_float2(rcp_approx(a.x), rcp_approx(a.y)); }
+__device__ __forceinline__ float vmin(float a, float m) { return fminf(a, m); }
+__device__ __forceinline__ float2 vmin(float2 a, float m) { return make_float2(fminf(a.x, m), fminf(a.y, m)); }
+__device__ __forceinline__ float vclampp(float a) { return fminf(fmaxf(a, kEps32), kOneMinusEps32); }
+__device__ __forceinline__ float2 vclampp(float2 a) { return make_float2(vclampp(a.x), vclampp(a.y)); }
+// keep v where the probability clamp did not fire (q == qc), else 0
+__device__ __forceinline__ float vkeep(float v, float q, float qc) { return q == qc ? v : 0.f; }
+__device__ __forceinline__ float2 vkeep(float2 v, float2 q, float2 qc) {
+  return make_float2(q.x == qc.x ? v.x : 0.f, q.y == qc.y ? v.y : 0.f);
+}
+__device__ __forceinline__ float vhsum(float a) { return a; }
+__device__ __forceinline__ float vhsum(float2 a) { return a.x + a.y; }
+__device__ __forceinline__ float vhprod(float a) { return a; }
+__device__ __forceinline__ float vhprod(float2 a) { return a.x * a.y; }
+template <typename V> __device__ __forceinline__ V vbcast(float a);
+template <> __device__ __forceinline__ float vbcast<float>(float a) { return a; }
+template <> __device__ __forceinline__ float2 vbcast<float2>(float a) { return make_float2(a, a); }
+__device__ __forceinline__ void vlg2_add(float q, float* lls) { lls[0] += lg2_approx(q); }
+__device__ __forceinline__ void vlg2_add(float2 q, float* lls) { lls[0] += lg2_approx(q.x); lls[1] += lg2_approx(q.y); }
+
+template <int SC> struct NoiseVec { using type = float2; static constexpr int W = 2; };
+template <> struct NoiseVec<1> { using type = float; static constexpr int W = 1; };
+
+// All SC particles of one (person, item) cell, two particles per instruction.
+// it = {A', B', c, d-c}, omd = 1-d, A' = -D a log2(e), B' = -D b log2(e).
+// The caller passes T0, T1 already signed by the response: tt = T1*eps + T0 is
+// -l*log2(e) for y=1 and +l*log2(e) for y=0, so with e' = 2^tt
+//     sp = 1/(1+e')  is  s   for y=1  and  1-s  for y=0       (no cancellation)
+//     q  = base + (d-c) sp,   base = c (y=1) | 1-d (y=0)       (= P | 1-P)
+// i.e. the same instruction stream serves both responses.  Then torch's
+// Bernoulli(probs) rule: clamp q to [eps, 1-eps], log, zero gradient
+// where the clamp fired.  Sums over the SC particles (all non-negative; the caller
+// applies the signs):  W1 = sum w, W2 = sum w*eps with w = s(1-s)/q;
+// A1 = sum sp/q; A2 = sum (1-sp)/q; Lj = sum log2 q (SCORE: per particle into lls).
+//
+// FASTPATH (4PL, every item 1e-3 <= c, d <= 1-1e-3, d-c >= 1e-3: the clamp is
+// unreachable): q = (base e' + base + (d-c)) / (1+e') =: num/ope, and the single
+// reciprocal R = 1/(num ope) yields sp = num R, sp/q = ope R, w = e' R:
+// 2.125 MUFU per evaluation instead of 3.25.
 template <int MODEL, bool SCORE, int SC, bool FASTPATH>
-__device__ __forceinline__ void item_evals(const float4 it, const float T0, const float T1, const float yflag,
-                                           const float (&eps)[SC], float (&lls)[SCORE ? SC : 1], float& W1,
-                                           float& W2, float& Gc, float& Gd, float& Lj) {
-  float prod = 1.f;
-  const float cY = it.z - yflag, dY = (it.z + it.w) - yflag;   // (c,d) for y=1, (c-1,d-1) for y=0
+__device__ __forceinline__ void item_evals(const float dmc, const float base, const float T0, const float T1,
+                                           const typename NoiseVec<SC>::type (&eps)[SC / NoiseVec<SC>::W],
+                                           float (&lls)[SCORE ? SC : 1], float& W1o, float& W2o, float& A1o,
+                                           float& A2o, float& Lj) {
+  using V = typename NoiseVec<SC>::type;
+  constexpr int W = NoiseVec<SC>::W;
+  constexpr int NV = SC / W;
+  constexpr int GROUP = FASTPATH ? 8 / W : 4 / W;     // factors multiplied before one lg2 (>= 1e-24 / 2e-28)
+  const V T0v = vbcast<V>(T0), T1v = vbcast<V>(T1), one = vbcast<V>(1.f);
+  V W1 = vbcast<V>(0.f), W2 = W1, A1 = W1, A2 = W1, prod = one;
+  if constexpr (FASTPATH) {
+    const V basev = vbcast<V>(base), bdv = vbcast<V>(base + dmc);
 #pragma unroll
-  for (int i = 0; i < SC; ++i) {
-    float t = fmaf(T1, eps[i], T0);
-    float w, q;
-    if constexpr (FASTPATH) {
-      t = fminf(fmaxf(t, -60.f), 60.f);
-      const float e = ex2_approx(t);
-      const float ope = 1.f + e;
-      const float num = fmaf(cY, e, dY);
-      const float R = rcp_approx(num * ope);
-      const float sgm = num * R;                   // 1/(1+e)
-      q = fabsf(num * sgm);                        // P or 1-P
-      const float us = ope * R;                    // u*s = 1/num  (u = dlb/dP)
-      const float uc = us * e;                     // u*(1-s)
-      w = uc * sgm;
-      Gc += uc;
-      Gd += us;
-    } else {
-      const float e = ex2_approx(t);
-      const float sgm = rcp_approx(1.f + e);
-      const float P = MODEL >= 3 ? fmaf(it.w, sgm, it.z) : sgm;
-      const float Pc = fminf(fmaxf(P, kEps32), kOneMinusEps32);
-      const float qs = Pc - yflag;
-      q = fabsf(qs);
-      if constexpr (MODEL >= 3) {
-        float u = rcp_approx(qs);
-        u = (P == Pc) ? u : 0.f;
-        const float us = u * sgm;
-        const float uc = u - us;
-        w = uc * sgm;
-        Gc += uc;
-        if constexpr (MODEL == 4) Gd += us;
+    for (int i = 0; i < NV; ++i) {
+      const V tt = vmin(vfma(T1v, eps[i], T0v), 60.f);
+      const V e = vex2(tt);
+      const V ope = vadd(e, one);
+      const V num = vfma(basev, e, bdv);
+      const V R = vrcp(vmul(num, ope));
+      const V sp = vmul(num, R);
+      const V q = vmul(num, sp);
+      const V us = vmul(ope, R);                                 // sp / q = 1 / num
+      const V w = vmul(e, R);                                    // sp (1-sp) / q
+      A1 = vadd(A1, us);
+      A2 = vfma(us, e, A2);                                      // (1-sp) / q = e' / num
+      W1 = vadd(W1, w);
+      W2 = vfma(w, eps[i], W2);
+      if constexpr (SCORE) {
+        vlg2_add(q, &lls[i * W]);
       } else {
-        w = (P == Pc) ? ((1.f - yflag) - sgm) : 0.f;
+        prod = vmul(prod, q);
+        if ((i % GROUP) == GROUP - 1 || i == NV - 1) { Lj += lg2_approx(vhprod(prod)); prod = one; }
       }
     }
-    if constexpr (SCORE) {
-      lls[i] += lg2_approx(q);
-    } else {
-      prod *= q;                                   // q >= eps => 4 factors stay normal
-      if ((i & 3) == 3 || i == SC - 1) { Lj += lg2_approx(prod); prod = 1.f; }
+  } else {
+    const V dmcv = vbcast<V>(dmc), basev = vbcast<V>(base);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const V tt = vmin(vfma(T1v, eps[i], T0v), 126.f);          // e' finite: sp, e' sp never NaN
+      const V e = vex2(tt);
+      const V sp = vrcp(vadd(e, one));
+      const V es = vmul(e, sp);                                  // 1 - sp
+      V q;
+      if constexpr (MODEL >= 3) q = vfma(dmcv, sp, basev); else q = sp;
+      const V qc = vclampp(q);
+      V w;
+      if constexpr (MODEL >= 3) {
+        const V r = vkeep(vrcp(qc), q, qc);
+        const V us = vmul(r, sp);
+        A1 = vadd(A1, us);
+        A2 = vfma(r, es, A2);
+        w = vmul(us, es);
+      } else {
+        w = vkeep(es, q, qc);                                    // |y - s|
+      }
+      W1 = vadd(W1, w);
+      W2 = vfma(w, eps[i], W2);
+      if constexpr (SCORE) {
+        vlg2_add(qc, &lls[i * W]);
+      } else {
+        prod = vmul(prod, qc);
+        if ((i % GROUP) == GROUP - 1 || i == NV - 1) { Lj += lg2_approx(vhprod(prod)); prod = one; }
+      }
     }
-    W1 += w;
-    W2 = fmaf(w, eps[i], W2);
   }
+  W1o = vhsum(W1); W2o = vhsum(W2); A1o = vhsum(A1); A2o = vhsum(A2);
 }
 
 // MODEL: 1..4 (number of item parameters).  SCORE: REINFORCE estimator for the
@@ -126,8 +184,8 @@ __global__ void __launch_bounds__(kUniThreads, 4) irt_uni_kernel(const IrtUniPar
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int J = p.J;
   float4* tab = reinterpret_cast<float4*>(smem_raw);
-  float* agx = reinterpret_cast<float*>(smem_raw + (size_t)J * 16);
-  float* acc_all = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(agx) + align16((size_t)J * 4));
+  float2* tab2 = reinterpret_cast<float2*>(smem_raw + (size_t)J * 16);
+  float* acc_all = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(tab2) + align16((size_t)J * 8));
   unsigned char* ytiles = reinterpret_cast<unsigned char*>(acc_all) + align16((size_t)kUniWarps * NQ * J * 4);
   const size_t ytile_bytes = align16((size_t)32 * J + 16);
 
@@ -140,7 +198,7 @@ __global__ void __launch_bounds__(kUniThreads, 4) irt_uni_kernel(const IrtUniPar
     const float cj = MODEL >= 3 ? p.c[j] : 0.f;
     const float dj = MODEL == 4 ? p.d[j] : 1.f;
     tab[j] = make_float4(-p.D * kLog2e * aj, -p.D * kLog2e * p.b[j], cj, dj - cj);
-    agx[j] = p.D * aj * (dj - cj);
+    tab2[j] = make_float2(p.D * aj * (dj - cj), 1.f - dj);
   }
   for (int i = threadIdx.x; i < kUniWarps * NQ * J; i += kUniThreads) acc_all[i] = 0.f;
   bool use_fast = false;
@@ -199,34 +257,48 @@ __global__ void __launch_bounds__(kUniThreads, 4) irt_uni_kernel(const IrtUniPar
 
     for (int s0 = 0; s0 < p.S; s0 += SC) {
       // ---- noise for SC particles ----------------------------------------
-      float eps[SC];
-      if (p.eps) {
+      using V = typename NoiseVec<SC>::type;
+      constexpr int VW = NoiseVec<SC>::W;
+      V eps[SC / VW];
+      {
+        float ef[SC];
+        if (p.eps) {
 #pragma unroll
-        for (int i = 0; i < SC; ++i) eps[i] = valid ? __ldg(p.eps + (int64_t)(s0 + i) * p.B + bi) : 0.f;
-      } else {
-        const uint64_t person = (uint64_t)(p.person_offset + bi);
-        if (SC >= 4) {
-#pragma unroll
-          for (int i = 0; i < SC; i += 4) {
-            const float4 z = normal4(p.seed, p.offset, person, (uint32_t)((s0 + i) >> 2));
-            eps[i] = z.x;
-            if (i + 1 < SC) eps[i + 1] = z.y;
-            if (i + 2 < SC) eps[i + 2] = z.z;
-            if (i + 3 < SC) eps[i + 3] = z.w;
-          }
+          for (int i = 0; i < SC; ++i) ef[i] = valid ? __ldg(p.eps + (int64_t)(s0 + i) * p.B + bi) : 0.f;
         } else {
-          const float4 z = normal4(p.seed, p.offset, person, (uint32_t)(s0 >> 2));
-          const float zz[4] = {z.x, z.y, z.z, z.w};
+          const uint64_t person = (uint64_t)(p.person_offset + bi);
+          if (SC >= 4) {
 #pragma unroll
-          for (int i = 0; i < SC; ++i) eps[i] = zz[(s0 + i) & 3];
+            for (int i = 0; i < SC; i += 4) {
+              const float4 z = normal4(p.seed, p.offset, person, (uint32_t)((s0 + i) >> 2));
+              ef[i] = z.x;
+              if (i + 1 < SC) ef[i + 1] = z.y;
+              if (i + 2 < SC) ef[i + 2] = z.z;
+              if (i + 3 < SC) ef[i + 3] = z.w;
+            }
+          } else {
+            const float4 z = normal4(p.seed, p.offset, person, (uint32_t)(s0 >> 2));
+            const float zz[4] = {z.x, z.y, z.z, z.w};
+#pragma unroll
+            for (int i = 0; i < SC; ++i) ef[i] = zz[(s0 + i) & 3];
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < SC; ++i) {
+          se += ef[i];
+          see = fmaf(ef[i], ef[i], see);
+        }
+        if constexpr (VW == 2) {
+#pragma unroll
+          for (int i = 0; i < SC / 2; ++i) eps[i] = make_float2(ef[2 * i], ef[2 * i + 1]);
+        } else {
+          eps[0] = ef[0];
         }
       }
       float lls[SCORE ? SC : 1];
+      if (SCORE) {
 #pragma unroll
-      for (int i = 0; i < SC; ++i) {
-        se += eps[i];
-        see = fmaf(eps[i], eps[i], see);
-        if (SCORE) lls[i] = 0.f;
+        for (int i = 0; i < SC; ++i) lls[i] = 0.f;
       }
 
       // ---- items ----------------------------------------------------------
@@ -239,20 +311,28 @@ __global__ void __launch_bounds__(kUniThreads, 4) irt_uni_kernel(const IrtUniPar
         for (int q = 0; q < NQ; ++q) v[q] = 0.f;
         if (obs) {
           const float4 it = tab[j];
-          const float yflag = code ? 0.f : 1.f;          // qs = P - yflag: P (y=1) or P-1 (y=0)
-          const float T0 = fmaf(it.x, mu, it.y), T1 = it.x * sg;
-          float W1 = 0.f, W2 = 0.f, Gc = 0.f, Gd = 0.f, Lj = 0.f;
+          const float2 it2 = tab2[j];
+          const bool y1 = code != 0u;
+          // sign the logit by the response: sp = s (y=1) | 1-s (y=0)
+          const float A = y1 ? it.x : -it.x, Bc = y1 ? it.y : -it.y;
+          const float T0 = fmaf(A, mu, Bc), T1 = A * sg;
+          const float base = MODEL >= 3 ? (y1 ? it.z : it2.y) : 0.f;   // c | 1-d (exact)
+          float W1, W2, A1, A2, Lj = 0.f;
           if (FAST && use_fast)
-            item_evals<MODEL, SCORE, SC, true>(it, T0, T1, yflag, eps, lls, W1, W2, Gc, Gd, Lj);
+            item_evals<MODEL, SCORE, SC, true>(it.w, base, T0, T1, eps, lls, W1, W2, A1, A2, Lj);
           else
-            item_evals<MODEL, SCORE, SC, false>(it, T0, T1, yflag, eps, lls, W1, W2, Gc, Gd, Lj);
+            item_evals<MODEL, SCORE, SC, false>(it.w, base, T0, T1, eps, lls, W1, W2, A1, A2, Lj);
+          // undo the signing: dlb/dl = +w (y=1) | -w (y=0); W2 pairs with the true eps
+          const float sgn = y1 ? 1.f : -1.f;
+          W1 *= sgn; W2 *= sgn;
           Lsum += Lj;
-          G1 = fmaf(agx[j], W1, G1);
-          G2 = fmaf(agx[j], W2, G2);
+          G1 = fmaf(it2.x, W1, G1);
+          G2 = fmaf(it2.x, W2, G2);
           v[0] = W1;
-          if constexpr (NQ >= 2) v[1] = fmaf(sg, W2, mu * W1);   // sum_s w x_s
-          if constexpr (NQ >= 3) v[2] = Gc;
-          if constexpr (NQ >= 4) v[3] = Gd;
+          if constexpr (NQ >= 2) v[1] = fmaf(sg, W2, mu * W1);   // sum_s dlb/dl * x_s
+          // dlb/dc = (1-s)/q (y=1) | -s/q (y=0);  dlb/dd = s/q (y=1) | -(1-s)/q (y=0)
+          if constexpr (NQ >= 3) v[2] = y1 ? A2 : -A1;
+          if constexpr (NQ >= 4) v[3] = y1 ? A1 : -A2;
         }
         if (p.want_grad) {
           const float r = warp_sum_multi<NQ>(v, lane);
@@ -265,10 +345,12 @@ __global__ void __launch_bounds__(kUniThreads, 4) irt_uni_kernel(const IrtUniPar
         const float lsg = __logf(sg);
 #pragma unroll
         for (int i = 0; i < SC; ++i) {
-          const float x = fmaf(sg, eps[i], mu);
-          const float e2 = eps[i] * eps[i];
+          float ei;
+          if constexpr (VW == 2) ei = (i & 1) ? eps[i >> 1].y : eps[i >> 1].x; else ei = eps[0];
+          const float x = fmaf(sg, ei, mu);
+          const float e2 = ei * ei;
           const float wgt = p.scale * (kLn2 * lls[i] - 0.5f * x * x + 0.5f * e2 + lsg) - p.baseline;
-          sw1 = fmaf(wgt, eps[i], sw1);
+          sw1 = fmaf(wgt, ei, sw1);
           sw2 = fmaf(wgt, e2 - 1.f, sw2);
           Lsum += lls[i];
         }
