@@ -1,0 +1,295 @@
+#!/usr/bin/env python
+"""bench.py -- BASELINE.json's metric on its quoted configuration.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+Workload (config[1] of BASELINE.json, SURVEY 8d "c2"): unidimensional 4PL IRT,
+amortised-VI shaped inputs (per-person mu, sigma as the encoder would emit them),
+1,000,000 persons x 100 items PER GPU, S = 32 Monte-Carlo particles, in-kernel
+Philox noise.  One step = one fused ELBO + gradient evaluation over all persons
+(kernels (a)+(b)+(d) of the north star) and, for N > 1, the all-reduce of the
+packed item-gradient buffer + loss.  Persons are sharded, per-GPU work is fixed:
+weak scaling.  metric = person.item.particle evaluations per second, whole job.
+
+`value`   : inputs resident in HBM, CUDA-event time per step, max over ranks.
+`e2e`     : same step through the host-buffer entry (vipsy_b200.host_api):
+            pinned host responses / variational parameters copied in, per-person
+            and item gradients + loss copied out, every step.
+`roofline`: the contract's HBM roofline for the dominant kernel, plus the SFU
+            (MUFU) roofline that actually binds this workload (SURVEY Finding 4).
+`cpu_baseline` / `--impl reference`: the reference's CPU path.  Pyro 1.4.0 is
+            not installable (no network), so this is the torch-CPU oracle
+            restatement (oracle/, kind "port") on a bounded person sample.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "elbo_grad_person_item_sample_evals_per_sec"
+UNIT = "evals/s"
+N_PERSONS, N_ITEMS, N_PARTICLES, MODEL = 1_000_000, 100, 32, "irt_4pl"
+WORKLOAD = "c2: uni 4PL IRT amortized-VI inputs, 1M persons x 100 items per GPU, S=32"
+
+
+def measured_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return json.load(f), "measured"
+    except Exception:
+        return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "sm_max_mhz": 1965.0}, "fallback"
+
+
+def cpu_sample(n_persons, seed=1234):
+    """The c2 workload at a bounded person count, on the CPU, NaN-coded floats."""
+    import torch
+    from vipsy_b200 import workloads
+    w = workloads.uni_irt(n_persons, N_ITEMS, MODEL, seed=seed, device="cpu", chunk=1 << 16)
+    y = w["y"].float()
+    eps = torch.randn(N_PARTICLES, n_persons, 1, generator=torch.Generator().manual_seed(seed + 1))
+    return w, y, eps
+
+
+def time_oracle(n_persons, steps, warmup):
+    """Seconds per ELBO+grad evaluation of the CPU oracle on `n_persons` persons."""
+    import torch
+    from oracle import vipsy_oracle as orc
+    torch.set_num_threads(os.cpu_count() or 1)
+    w, y, eps = cpu_sample(n_persons)
+
+    def step():
+        return orc.irt_elbo_grad(y, w["mu"], w["sigma"], eps, w["a"], w["b"], w["c"], w["d"], model=MODEL,
+                                 dtype=torch.float32)
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = (time.perf_counter() - t0) / max(steps, 1)
+    return dt, torch.get_num_threads()
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    n = 20_000
+    dt, threads = time_oracle(n, args.steps, args.warmup)
+    value = n * N_ITEMS * N_PARTICLES / dt
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "sample": f"{n} persons x {N_ITEMS} items x S={N_PARTICLES} per step"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
+                         "sample": f"{n} persons x {N_ITEMS} items x S={N_PARTICLES}, torch-CPU oracle "
+                                   "(restated Pyro Trace_ELBO, no Pyro overhead), fp32"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+    from vipsy_b200 import build, ops, workloads
+    from vipsy_b200.clocks import ClockSampler
+    from vipsy_b200.host_api import IrtHostStep
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the B200 path has no CPU fallback")
+    build.build()
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1 and not dist.is_initialized():
+        dist.init_process_group("nccl", device_id=dev)
+
+    w = workloads.uni_irt(N_PERSONS, N_ITEMS, MODEL, seed=1234 + rank, device=dev)
+    # item parameters are replicated: take rank 0's
+    if world > 1:
+        for k in ("a", "b", "c", "d"):
+            dist.broadcast(w[k], 0)
+    person_offset = rank * N_PERSONS
+    scale = 1.0
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    d_mu = torch.empty((N_PERSONS, 1), dtype=torch.float32, device=dev)
+    d_sigma = torch.empty((N_PERSONS, 1), dtype=torch.float32, device=dev)
+    state = {"offset": 0, "launches": 0}
+
+    def step():
+        state["offset"] += 1
+        r = ops.irt_elbo_grad(w["y"], w["mu"], sigma=w["sigma"], n_particles=N_PARTICLES, a=w["a"], b=w["b"],
+                              c=w["c"], d=w["d"], model=MODEL, scale=scale, seed=20261017, offset=state["offset"],
+                              person_offset=person_offset, d_mu_out=d_mu, d_scale_out=d_sigma)
+        state["launches"] += 2                      # fused kernel + fixed-order finalize
+        if world > 1:                               # item gradients + loss: the only exchange
+            dist.all_reduce(r["item_grads"])
+            dist.all_reduce(r["loss"])
+        return r
+
+    def sync_all():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    sync_all()
+    # ---- timed: K steps, each bracketed by events on the launch stream; L2 flushed between steps
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    state["launches"] = 0
+    last = None
+    with ClockSampler(local_rank) as clk:
+        sync_all()
+        t_wall0 = time.perf_counter()
+        for i in range(args.steps):
+            flush.zero_()
+            ev[i][0].record()
+            last = step()
+            ev[i][1].record()
+        sync_all()
+        t_wall = time.perf_counter() - t_wall0
+    step_ms = sum(a.elapsed_time(b) for a, b in ev)
+    t = torch.tensor([step_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms = float(t.item())
+    ms_per_step = total_ms / args.steps
+    evals_per_step = world * N_PERSONS * N_ITEMS * N_PARTICLES
+    value = evals_per_step / (ms_per_step * 1e-3)
+    gpu_launches = state["launches"]
+    loss_val = float(last["loss"].item())
+
+    # ---- dominant kernel alone (no collective), events on the launch stream
+    kms = []
+    for i in range(min(args.steps, 10)):
+        flush.zero_()
+        a, b = kev[i]
+        a.record()
+        ops.irt_elbo_grad(w["y"], w["mu"], sigma=w["sigma"], n_particles=N_PARTICLES, a=w["a"], b=w["b"],
+                          c=w["c"], d=w["d"], model=MODEL, scale=scale, seed=1, offset=1000 + i,
+                          person_offset=person_offset, d_mu_out=d_mu, d_scale_out=d_sigma)
+        b.record()
+    torch.cuda.synchronize()
+    kms = [a.elapsed_time(b) for a, b in kev[:min(args.steps, 10)]]
+    kernel_ms = sum(kms) / len(kms)
+
+    # ---- e2e: host buffers in, host results out, every step -----------------
+    host = IrtHostStep(N_PERSONS, N_ITEMS, MODEL, n_chunks=8, device=dev)
+    hy = torch.empty(w["y"].shape, dtype=torch.uint8, pin_memory=True).copy_(w["y"])
+    hmu = torch.empty(w["mu"].shape, dtype=torch.float32, pin_memory=True).copy_(w["mu"])
+    hsg = torch.empty(w["sigma"].shape, dtype=torch.float32, pin_memory=True).copy_(w["sigma"])
+    hp = {k: w[k].cpu() for k in ("a", "b", "c", "d")}
+    e2e_steps = max(3, min(args.steps, 10))
+
+    def e2e_step(i):
+        r = host(hy, hmu, hsg, hp["a"], hp["b"], hp["c"], hp["d"], n_particles=N_PARTICLES, scale=scale,
+                 seed=20261017, offset=5000 + i, person_offset=person_offset)
+        if world > 1:
+            g = r["item_grads"].to(dev, non_blocking=True)
+            dist.all_reduce(g)
+            r["item_grads"].copy_(g)
+        return r
+    for i in range(2):
+        e2e_step(i)
+    sync_all()
+    t0 = time.perf_counter()
+    for i in range(e2e_steps):
+        e2e_step(10 + i)
+    sync_all()
+    e2e_s = (time.perf_counter() - t0) / e2e_steps
+    te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = evals_per_step / float(te.item())
+
+    if rank != 0:
+        return
+    peaks, peaks_src = measured_peaks()
+    # algorithmic bytes per launch: y 1 B/cell + mu, sigma read + d_mu, d_sigma written
+    algo_bytes = N_PERSONS * (N_ITEMS + 16)
+    achieved_gbs = algo_bytes / (kernel_ms * 1e-3) / 1e9
+    traffic = None
+    prof = os.path.join(ROOT, "profiles", "r01_irt_uni_c2_summary.json")
+    if os.path.exists(prof):
+        try:
+            traffic = json.load(open(prof)).get("dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+    ck = clk.summary()
+    clk_hz = (ck["sm_mhz"] or peaks.get("sm_max_mhz", 1965.0)) * 1e6
+    mufu_per_eval = 2.125            # ex2 + rcp + lg2/8 (fast 4PL path)
+    sfu_peak = 148 * 16 * clk_hz     # 16 MUFU lanes per SM per clock
+    sfu_ach = N_PERSONS * N_ITEMS * N_PARTICLES * mufu_per_eval / (kernel_ms * 1e-3)
+
+    cpu_n = 20_000
+    cpu_dt, cpu_threads = time_oracle(cpu_n, steps=3, warmup=1) if world == 1 else (None, None)
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "persons_per_gpu": N_PERSONS, "items": N_ITEMS, "particles": N_PARTICLES,
+                   "model": MODEL, "noise": "in-kernel Philox4x32-10", "parallelism": f"person-shard x{world}",
+                   "l2": "flushed between steps (256 MiB memset outside the per-step events)",
+                   "timing": "sum of per-step CUDA-event intervals, max over ranks"},
+        "clocks": {"sm_mhz": ck["sm_mhz"], "sm_max_mhz": ck["sm_max_mhz"], "reasons": ck["reasons"],
+                   "power_w_max": ck["power_w_max"]},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": host.h2d_bytes,
+                "d2h_bytes_per_step": host.d2h_bytes, "ms_per_step": e2e_s * 1e3,
+                "how": "vipsy_b200.host_api.IrtHostStep: pinned host y/mu/sigma -> 8-chunk 3-stream pipeline -> host grads"},
+        "gpu_launches": gpu_launches,
+        "roofline": {"bound": "hbm", "achieved": achieved_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                     "frac": achieved_gbs / peaks["hbm_gbs"], "traffic": traffic, "peak_source": peaks_src,
+                     "kernel": "irt_uni_kernel<4PL,pathwise,SC=32>", "kernel_ms": kernel_ms,
+                     "algorithmic_bytes": algo_bytes,
+                     "note": "S=32 makes this workload SFU-bound by construction (830 flop/B); see sfu_roofline"},
+        "sfu_roofline": {"bound": "sfu", "achieved": sfu_ach, "peak": sfu_peak, "unit": "MUFU op/s",
+                         "frac": sfu_ach / sfu_peak, "mufu_per_eval": mufu_per_eval,
+                         "peak_source": "148 SM x 16 lanes x sampled SM clock"},
+        "wall_s_timed_region": t_wall, "loss_last_step": loss_val,
+    }
+    if cpu_dt is not None:
+        line["cpu_baseline"] = {
+            "value": cpu_n * N_ITEMS * N_PARTICLES / cpu_dt, "unit": UNIT, "cores": cpu_threads, "kind": "port",
+            "sample": f"{cpu_n} persons x {N_ITEMS} items x S={N_PARTICLES}, 3 evaluations, torch-CPU oracle "
+                      "(restated Pyro Trace_ELBO without Pyro's handler overhead), fp32"}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    if world != args.gpus and world == 1 and args.gpus > 1:
+        raise SystemExit("launch with torch.distributed.run --nproc-per-node N for --gpus N > 1")
+    try:
+        run_ours(args, rank, world, local_rank)
+    finally:
+        try:
+            import torch.distributed as dist
+            if dist.is_initialized():
+                dist.destroy_process_group()
+        except Exception:
+            pass
+
+
+if __name__ == "__main__":
+    main()

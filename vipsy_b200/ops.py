@@ -7,6 +7,7 @@ CUDA tensors without synchronising.  These are what the estimator classes in
 from __future__ import annotations
 
 import ctypes as C
+import math
 from typing import Dict, Optional
 
 import torch
@@ -100,8 +101,12 @@ def irt_elbo_grad(
     chol_packed: bool = False, chol_raw: bool = False,
     seed: int = 0, offset: int = 0, person_offset: int = 0,
     want_grad: bool = True, strict: bool = False,
+    d_mu_out: Optional[torch.Tensor] = None, d_scale_out: Optional[torch.Tensor] = None,
 ) -> Dict[str, Optional[torch.Tensor]]:
-    """One fused ELBO + gradient evaluation (Trace_ELBO.loss_and_grads, vi.py:507)."""
+    """One fused ELBO + gradient evaluation (Trace_ELBO.loss_and_grads, vi.py:507).
+
+    ``d_mu_out`` / ``d_scale_out``: optional preallocated fp32 CUDA buffers for the
+    per-person gradients (d_sigma for K == 1, d_chol otherwise)."""
     if not y.is_cuda or y.dtype != torch.uint8:
         raise ValueError("y must be a CUDA uint8 code matrix (see pack_responses)")
     if y.dim() != 2 or y.stride(1) != 1:
@@ -171,15 +176,22 @@ def irt_elbo_grad(
             raise ValueError(f"chol shape {tuple(chol.shape)} does not match K={K}, B={B}")
         args.chol, args.chol_raw = _ptr(ch_), int(bool(chol_raw))
     if want_grad:
-        d_mu = torch.empty((B, K), dtype=torch.float32, device=dev)
+        def _out(buf, shape, zero=False):
+            if buf is None:
+                return (torch.zeros if zero else torch.empty)(shape, dtype=torch.float32, device=dev)
+            if not (buf.is_cuda and buf.dtype == torch.float32 and buf.is_contiguous()
+                    and buf.numel() == math.prod(shape)):
+                raise ValueError("preallocated gradient buffer has the wrong dtype/size/layout")
+            return buf
+        d_mu = _out(d_mu_out, (B, K))
         args.d_mu = _ptr(d_mu)
         out["d_mu"] = d_mu
         if K == 1:
-            d_sigma = torch.empty((B, 1), dtype=torch.float32, device=dev)
+            d_sigma = _out(d_scale_out, (B, 1))
             args.d_sigma = _ptr(d_sigma)
             out["d_sigma"] = d_sigma
         else:
-            d_chol = torch.zeros_like(ch_)
+            d_chol = _out(d_scale_out, tuple(ch_.shape), zero=d_scale_out is None)
             args.d_chol = _ptr(d_chol)
             out["d_chol"] = d_chol
         # item gradients live in one packed fp32 buffer [d_b | d_a | d_c | d_d] so a
