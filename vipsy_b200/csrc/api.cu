@@ -49,13 +49,8 @@ int vipsy_irt_elbo_grad(const VipsyIrtArgs* a, void* stream) {
   return VIPSY_ERR_UNSUPPORTED;
 }
 
-// -- CDM entry points: implemented in cdm_enum.cu / cdm_score.cu once built ------
-#ifndef VIPSY_HAVE_CDM
-size_t vipsy_cdm_enum_workspace_bytes(const VipsyCdmEnumArgs*) { return 0; }
-int vipsy_cdm_enum_elbo_grad(const VipsyCdmEnumArgs*, void*) {
-  set_error("vipsy_cdm_enum_elbo_grad: not built yet");
-  return VIPSY_ERR_UNSUPPORTED;
-}
+// -- REINFORCE CDM entry points: implemented in cdm_score.cu once built ------------
+#ifndef VIPSY_HAVE_CDM_SCORE
 size_t vipsy_cdm_score_workspace_bytes(const VipsyCdmScoreArgs*) { return 0; }
 int vipsy_cdm_score_elbo_grad(const VipsyCdmScoreArgs*, void*) {
   set_error("vipsy_cdm_score_elbo_grad: not built yet");

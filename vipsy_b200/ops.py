@@ -219,3 +219,84 @@ def irt_elbo_grad(
     out["loss"] = loss
     out["_keepalive"] = (mu_, sg_, ch_, eps_, a_, b_, c_, d_, af_, idx_, ws)
     return out
+
+
+def cdm_enum_elbo_grad(
+    y: torch.Tensor,                     # n_rows x J uint8 codes
+    q: torch.Tensor,                     # K x J 0/1 Q-matrix (or J int32 masks from qmask_from_q)
+    g: torch.Tensor, s: torch.Tensor,    # J guess / slip (constrained values)
+    *,
+    n_attrs: Optional[int] = None,
+    model: str = "dina", scale: float = 1.0,
+    batch: Optional[int] = None, idx: Optional[torch.Tensor] = None,
+    lam0: Optional[torch.Tensor] = None, lam1: Optional[torch.Tensor] = None,     # HO-DINA (vi.py:901-902)
+    mu: Optional[torch.Tensor] = None, sigma: Optional[torch.Tensor] = None,      # theta guide (vi.py:928-929)
+    eps: Optional[torch.Tensor] = None, n_particles: int = 1,
+    seed: int = 0, offset: int = 0, person_offset: int = 0,
+    want_grad: bool = True, want_posterior: bool = False,
+) -> Dict[str, Optional[torch.Tensor]]:
+    """TraceEnum_ELBO.loss_and_grads for VCCDM.model (vi.py:839-857) or, when lam0/lam1/mu/sigma
+    are given, VCHoDina (vi.py:897-934): exact marginal over the 2^K attribute patterns."""
+    if not y.is_cuda or y.dtype != torch.uint8 or y.dim() != 2 or y.stride(1) != 1:
+        raise ValueError("y must be a CUDA uint8 code matrix with unit column stride")
+    dev = y.device
+    n_rows, J = y.shape
+    if q.dim() == 2:
+        K = q.shape[0]
+        qm = qmask_from_q(q.to(dev))
+    else:
+        if n_attrs is None:
+            raise ValueError("n_attrs is required when q is given as bit masks")
+        K, qm = int(n_attrs), q.to(device=dev, dtype=torch.int32).contiguous()
+    hod = lam0 is not None
+    args = N.CdmEnumArgs()
+    idx_ = None
+    if idx is not None:
+        idx_ = idx.to(device=dev, dtype=torch.int64).contiguous()
+        B = idx_.numel()
+    else:
+        B = n_rows if batch is None else int(batch)
+    g_, s_ = _f32(g, "g", J), _f32(s, "s", J)
+    eps_ = None
+    S = 1
+    if hod:
+        l0_, l1_ = _f32(lam0, "lam0", K), _f32(lam1, "lam1", K)
+        mu_, sg_ = _f32(mu, "mu", B), _f32(sigma, "sigma", B)
+        if eps is not None:
+            eps_ = _f32(eps, "eps")
+            S = eps_.numel() // max(B, 1)
+            if eps_.numel() != S * B:
+                raise ValueError("eps must be S x B (x 1)")
+        else:
+            S = int(n_particles)
+        args.lam0, args.lam1, args.mu, args.sigma, args.eps = _ptr(l0_), _ptr(l1_), _ptr(mu_), _ptr(sg_), _ptr(eps_)
+    args.n_rows, args.batch, args.n_items, args.n_attrs, args.n_particles = n_rows, B, J, K, S
+    args.model, args.hodina, args.scale = N.CDM_MODEL[model], int(hod), float(scale)
+    args.y, args.y_row_stride, args.idx, args.qmask = _ptr(y), y.stride(0), _ptr(idx_), _ptr(qm)
+    args.g, args.s = _ptr(g_), _ptr(s_)
+    args.seed, args.offset, args.person_offset = seed, offset, person_offset
+    out: Dict[str, Optional[torch.Tensor]] = {}
+    loss = torch.empty(1, dtype=torch.float64, device=dev)
+    args.loss = _ptr(loss)
+    if want_grad:
+        ncol = 2 * J + (2 * K if hod else 0)
+        packed = torch.zeros(ncol, dtype=torch.float32, device=dev)
+        out["item_grads"] = packed
+        out["d_g"], out["d_s"] = packed[:J].view(1, J), packed[J:2 * J].view(1, J)
+        args.d_g, args.d_s = out["d_g"].data_ptr(), out["d_s"].data_ptr()
+        if hod:
+            out["d_lam0"], out["d_lam1"] = packed[2 * J:2 * J + K].view(1, K), packed[2 * J + K:].view(1, K)
+            args.d_lam0, args.d_lam1 = out["d_lam0"].data_ptr(), out["d_lam1"].data_ptr()
+            out["d_mu"] = torch.empty((B, 1), dtype=torch.float32, device=dev)
+            out["d_sigma"] = torch.empty((B, 1), dtype=torch.float32, device=dev)
+            args.d_mu, args.d_sigma = _ptr(out["d_mu"]), _ptr(out["d_sigma"])
+    if want_posterior:
+        out["posterior"] = torch.zeros((B, 2 ** K), dtype=torch.float32, device=dev)
+        args.posterior = _ptr(out["posterior"])
+    L = N.lib()
+    ws = _workspace("cdm_enum", L.vipsy_cdm_enum_workspace_bytes(C.byref(args)), dev)
+    args.workspace, args.workspace_bytes = _ptr(ws), ws.numel()
+    N.check(L.vipsy_cdm_enum_elbo_grad(C.byref(args), _stream()))
+    out["loss"] = loss
+    out["_keepalive"] = (qm, g_, s_, idx_, eps_, ws, args)
+    return out
