@@ -4,6 +4,8 @@
 namespace vipsy {
 size_t irt_uni_workspace_bytes(const VipsyIrtArgs* a);
 int irt_uni_launch(const VipsyIrtArgs* a, cudaStream_t st);
+size_t mirt_workspace_bytes(const VipsyIrtArgs* a);
+int mirt_launch(const VipsyIrtArgs* a, cudaStream_t st);
 }  // namespace vipsy
 
 using namespace vipsy;
@@ -38,15 +40,17 @@ extern "C" {
 size_t vipsy_irt_workspace_bytes(const VipsyIrtArgs* a) {
   if (!a || a->n_items <= 0 || a->n_dims <= 0 || a->model < 1 || a->model > 4) return 0;
   if (a->n_dims == 1) return irt_uni_workspace_bytes(a);
-  return 0;
+  if (a->batch < 0 || a->n_particles <= 0) return 0;
+  return mirt_workspace_bytes(a);
 }
 
 int vipsy_irt_elbo_grad(const VipsyIrtArgs* a, void* stream) {
   int rc = check_irt(a);
   if (rc != VIPSY_OK) return rc;
   if (a->n_dims == 1) return irt_uni_launch(a, (cudaStream_t)stream);
-  set_error("vipsy_irt_elbo_grad: K=%d not built yet", a->n_dims);
-  return VIPSY_ERR_UNSUPPORTED;
+  VIPSY_REQUIRE(a->model != VIPSY_IRT_1PL, VIPSY_ERR_ARG,
+                "vipsy_irt_elbo_grad: irt_1pl is D*(x+b) (vi.py:29): defined for K == 1 only");
+  return mirt_launch(a, (cudaStream_t)stream);
 }
 
 // -- REINFORCE CDM entry points: implemented in cdm_score.cu once built ------------
