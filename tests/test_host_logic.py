@@ -1,0 +1,144 @@
+"""CPU tests of the host-side mirror of the reference interface: param store + constraint
+transforms, per-parameter Adam / MultiStepLR, SVI.step order, person sharding over gloo."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from oracle import vipsy_oracle as o
+from vipsy_b200 import infer
+from vipsy_b200.dist import GradReducer, shard_bounds
+
+
+def test_constraint_transforms_round_trip():
+    torch.manual_seed(0)
+    for c, v in [(infer.REAL, torch.randn(3, 4)), (infer.POSITIVE, torch.rand(5) + 0.1),
+                 (infer.UNIT_INTERVAL, torch.rand(2, 6) * 0.9 + 0.05),
+                 (infer.LOWER_CHOLESKY, o.lower_cholesky(torch.randn(4, 3, 3) * 0.3))]:
+        u = infer.inverse_transform(c, v)
+        assert torch.allclose(infer.transform(c, u), v, atol=1e-6)
+    # lower_cholesky transform == oracle's LowerCholeskyTransform restatement
+    raw = torch.randn(2, 5, 5)
+    assert torch.equal(infer.transform(infer.LOWER_CHOLESKY, raw), o.lower_cholesky(raw))
+
+
+def test_param_store_semantics():
+    infer.clear_param_store()
+    c = infer.param("c", torch.zeros(1, 4) + 0.1, constraint=infer.constraints.unit_interval)
+    assert torch.allclose(c, torch.full((1, 4), 0.1))
+    again = infer.param("c", torch.zeros(1, 4) + 0.7, constraint=infer.constraints.unit_interval)
+    assert torch.allclose(again, c)                       # later calls ignore init
+    st = infer.get_param_store()
+    assert st.unconstrained("c").requires_grad and st.constraint("c") == infer.UNIT_INTERVAL
+    assert infer.constraints.interval(0, 1) == infer.UNIT_INTERVAL
+    infer.clear_param_store()
+    assert "c" not in st
+
+
+def test_adam_per_parameter_args_and_scheduler():
+    seen = []
+
+    def args(module_name, param_name):                    # test.py:321-327 style callable
+        seen.append((module_name, param_name))
+        return {"lr": 1e-2} if param_name == "a" else {"lr": 1e-3}
+    a = torch.zeros(3, requires_grad=True)
+    w = torch.zeros(3, requires_grad=True)
+    opt = infer.Adam(args)
+    a.grad, w.grad = torch.ones(3), torch.ones(3)
+    opt([("a", a), ("encoder$$$fc1.weight", w)])
+    assert ("a", "a") in seen and ("encoder", "fc1.weight") in seen
+    assert torch.allclose(a.detach(), torch.full((3,), -1e-2), atol=1e-6)
+    assert torch.allclose(w.detach(), torch.full((3,), -1e-3), atol=1e-6)
+    sched = infer.MultiStepLR({"optimizer": torch.optim.Adam, "optim_args": {"lr": 0.1}, "milestones": [2], "gamma": 0.1})
+    p = torch.zeros(1, requires_grad=True)
+    lrs = []
+    for _ in range(4):
+        p.grad = torch.ones(1)
+        sched([("p", p)])
+        sched.step()                                      # vi.py:639-640: once per iteration
+        lrs.append(sched.optim_objs[p].param_groups[0]["lr"])
+    assert lrs[0] == pytest.approx(0.1) and lrs[-1] == pytest.approx(0.01)
+    assert isinstance(sched, infer.PyroLRScheduler)
+
+
+def test_svi_step_order_free_mask_and_zero_grads():
+    class Owner:
+        def __init__(self):
+            self.a = torch.ones(2, 3, requires_grad=True)
+            self.free = torch.tensor([[1, 1, 1], [1, 1, 0]], dtype=torch.bool)
+
+        def model(self, data):
+            pass
+        guide = model
+
+        def loss_and_grads(self, cfg, data):
+            self.a.grad = torch.ones(2, 3)
+            return torch.tensor(3.5), [("a", self.a, self.free)]
+
+        def loss(self, cfg, data):
+            return torch.tensor(1.25)
+    ow = Owner()
+    svi = infer.SVI(ow.model, ow.guide, infer.Adam({"lr": 0.5}), infer.Trace_ELBO(num_particles=2))
+    assert svi.step(None) == 3.5
+    assert ow.a.grad is None                              # zero_grads after the optimiser step
+    assert float(ow.a[1, 2]) == 1.0                       # frozen entry did not move (vi.py:511-512)
+    assert float(ow.a[0, 0]) == pytest.approx(0.5)
+    assert svi.evaluate_loss(None) == 1.25
+
+
+def test_shard_bounds_cover_everything():
+    for n in (0, 1, 7, 1000, 1_000_003):
+        for world in (1, 2, 3, 8):
+            spans = [shard_bounds(n, world, r) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(spans[i][1] == spans[i + 1][0] for i in range(world - 1))
+            sizes = [b - a for a, b in spans]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _worker(rank, world, port, ret):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        g = torch.Generator().manual_seed(11)
+        N, J, S = 101, 9, 3
+        y = (torch.rand(N, J, generator=g) < 0.5).float()
+        y[torch.rand(N, J, generator=g) < 0.2] = float("nan")
+        mu, sg = torch.randn(N, 1, generator=g) * 0.5, torch.exp(torch.randn(N, 1, generator=g) * 0.2)
+        a, b = torch.rand(1, J, generator=g) + 0.5, torch.randn(1, J, generator=g)
+        eps = torch.randn(S, N, 1, generator=g)
+        lo, hi = shard_bounds(N, world, rank)
+        r = o.irt_elbo_grad(y[lo:hi], mu[lo:hi], sg[lo:hi], eps[:, lo:hi], a, b, model="irt_2pl", scale=1.0)
+        la, lb = a.clone().requires_grad_(True), b.clone().requires_grad_(True)
+        la.grad, lb.grad = r["d_a"].float(), r["d_b"].float()
+        red = GradReducer()
+        loss = red(torch.tensor(r["loss"], dtype=torch.float64), [la, lb])
+        full = o.irt_elbo_grad(y, mu, sg, eps, a, b, model="irt_2pl")
+        ok = (abs(float(loss) - full["loss"]) < 1e-4 * abs(full["loss"])
+              and torch.allclose(la.grad.double(), full["d_a"], rtol=1e-5, atol=1e-4)
+              and torch.allclose(lb.grad.double(), full["d_b"], rtol=1e-5, atol=1e-4)
+              and torch.allclose(r["d_mu"], full["d_mu"][lo:hi])          # per-person grads stay local
+              and red.bytes_last == 4 * (2 + 2 * J))
+        ret[rank] = bool(ok)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_person_sharding_world2_gloo():
+    """Sum of per-shard item gradients == full-batch gradients; one packed all-reduce per step."""
+    world = 2
+    mgr = mp.get_context("spawn").Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker, args=(world, _free_port(), ret), nprocs=world, join=True)
+    assert all(ret.get(r) for r in range(world)), dict(ret)

@@ -53,13 +53,4 @@ int vipsy_irt_elbo_grad(const VipsyIrtArgs* a, void* stream) {
   return mirt_launch(a, (cudaStream_t)stream);
 }
 
-// -- REINFORCE CDM entry points: implemented in cdm_score.cu once built ------------
-#ifndef VIPSY_HAVE_CDM_SCORE
-size_t vipsy_cdm_score_workspace_bytes(const VipsyCdmScoreArgs*) { return 0; }
-int vipsy_cdm_score_elbo_grad(const VipsyCdmScoreArgs*, void*) {
-  set_error("vipsy_cdm_score_elbo_grad: not built yet");
-  return VIPSY_ERR_UNSUPPORTED;
-}
-#endif
-
 }  // extern "C"

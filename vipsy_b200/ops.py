@@ -300,3 +300,53 @@ def cdm_enum_elbo_grad(
     out["loss"] = loss
     out["_keepalive"] = (qm, g_, s_, idx_, eps_, ws, args)
     return out
+
+
+def cdm_score_elbo_grad(
+    y: torch.Tensor, q: torch.Tensor, g: torch.Tensor, s: torch.Tensor, attr_p: torch.Tensor, *,
+    n_attrs: Optional[int] = None, u: Optional[torch.Tensor] = None, n_particles: int = 1,
+    model: str = "dina", scale: float = 1.0, baseline: float = 0.0, idx: Optional[torch.Tensor] = None,
+    seed: int = 0, offset: int = 0, person_offset: int = 0, want_grad: bool = True,
+) -> Dict[str, Optional[torch.Tensor]]:
+    """Trace_ELBO.loss_and_grads for BaseCDM.model + the Bernoulli guide of VCDM / VaeCDM
+    (vi.py:745-756, 796-816): REINFORCE.  attr = [u < attr_p] with u injected or Philox."""
+    if not y.is_cuda or y.dtype != torch.uint8 or y.dim() != 2 or y.stride(1) != 1:
+        raise ValueError("y must be a CUDA uint8 code matrix with unit column stride")
+    dev = y.device
+    n_rows, J = y.shape
+    if q.dim() == 2:
+        K, qm = q.shape[0], qmask_from_q(q.to(dev))
+    else:
+        K, qm = int(n_attrs), q.to(device=dev, dtype=torch.int32).contiguous()
+    ap_ = _f32(attr_p, "attr_p")
+    B = ap_.numel() // K
+    u_ = None
+    S = int(n_particles)
+    if u is not None:
+        u_ = _f32(u, "u")
+        S = u_.numel() // max(B * K, 1)
+    idx_ = None if idx is None else idx.to(device=dev, dtype=torch.int64).contiguous()
+    g_, s_ = _f32(g, "g", J), _f32(s, "s", J)
+    args = N.CdmScoreArgs()
+    args.n_rows, args.batch, args.n_items, args.n_attrs, args.n_particles = n_rows, B, J, K, S
+    args.model, args.scale, args.baseline = N.CDM_MODEL[model], float(scale), float(baseline)
+    args.y, args.y_row_stride, args.idx, args.qmask = _ptr(y), y.stride(0), _ptr(idx_), _ptr(qm)
+    args.g, args.s, args.attr_p, args.u = _ptr(g_), _ptr(s_), _ptr(ap_), _ptr(u_)
+    args.seed, args.offset, args.person_offset = seed, offset, person_offset
+    out: Dict[str, Optional[torch.Tensor]] = {}
+    loss = torch.empty(1, dtype=torch.float64, device=dev)
+    args.loss = _ptr(loss)
+    if want_grad:
+        packed = torch.zeros(2 * J, dtype=torch.float32, device=dev)
+        out["item_grads"] = packed
+        out["d_g"], out["d_s"] = packed[:J].view(1, J), packed[J:].view(1, J)
+        args.d_g, args.d_s = out["d_g"].data_ptr(), out["d_s"].data_ptr()
+        out["d_attr_p"] = torch.empty((B, K), dtype=torch.float32, device=dev)
+        args.d_attr_p = _ptr(out["d_attr_p"])
+    L = N.lib()
+    ws = _workspace("cdm_score", L.vipsy_cdm_score_workspace_bytes(C.byref(args)), dev)
+    args.workspace, args.workspace_bytes = _ptr(ws), ws.numel()
+    N.check(L.vipsy_cdm_score_elbo_grad(C.byref(args), _stream()))
+    out["loss"] = loss
+    out["_keepalive"] = (qm, g_, s_, ap_, u_, idx_, ws)
+    return out
