@@ -215,6 +215,17 @@ int vipsy_fill_normal(float* out, int32_t n_particles, int64_t batch, int32_t n_
 int vipsy_fill_uniform(float* out, int32_t n_particles, int64_t batch, int32_t n_dims,
                        uint64_t seed, uint64_t offset, int64_t person_offset, void* stream);
 
+/* ------------------------------------------------------------------------
+ * Diagnostics: one 128-row tcgen05 tile product per operand orientation of the
+ * tensor-core MIRT kernel (fp16 hi/lo split, fp32 accumulation in TMEM).
+ *   variant 0: out[128 x c2] = t1[r1 x c1] . t2[r2 x c2]        (c1 == r2)
+ *   variant 1: out[128 x r2] = t1[r1 x c1] . t2[r2 x c2]^T      (c1 == c2)
+ *   variant 2: out[128 x c2] = t1[r1 x c1]^T . t2[r2 x c2]      (r1 == r2; rows >= c1 of out undefined)
+ * n_split = 1 (hi*hi only) .. 3 (+ hi*lo + lo*hi).  Used by tests/test_umma_selftest.py.
+ * ---------------------------------------------------------------------- */
+int vipsy_selftest_umma(const float* t1, int32_t r1, int32_t c1, const float* t2, int32_t r2, int32_t c2,
+                        float* out, int32_t variant, int32_t swap_mn_strides, int32_t n_split, void* stream);
+
 int vipsy_abi_version(void);
 const char* vipsy_last_error(void);
 

@@ -82,6 +82,8 @@ SYMBOLS = {
     "vipsy_pack_responses": (C.c_int, [_p, C.c_int64, _p, _p]),
     "vipsy_cdm_eta_table": (C.c_int, [_p, C.c_int32, C.c_int32, C.c_int32, _p, _p]),
     "vipsy_fill_normal": (C.c_int, [_p, C.c_int32, C.c_int64, C.c_int32, C.c_uint64, C.c_uint64, C.c_int64, _p]),
+    "vipsy_selftest_umma": (C.c_int, [_p, C.c_int32, C.c_int32, _p, C.c_int32, C.c_int32, _p, C.c_int32, C.c_int32,
+                                      C.c_int32, _p]),
     "vipsy_fill_uniform": (C.c_int, [_p, C.c_int32, C.c_int64, C.c_int32, C.c_uint64, C.c_uint64, C.c_int64, _p]),
 }
 

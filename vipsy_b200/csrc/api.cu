@@ -6,6 +6,8 @@ size_t irt_uni_workspace_bytes(const VipsyIrtArgs* a);
 int irt_uni_launch(const VipsyIrtArgs* a, cudaStream_t st);
 size_t mirt_workspace_bytes(const VipsyIrtArgs* a);
 int mirt_launch(const VipsyIrtArgs* a, cudaStream_t st);
+int umma_selftest_launch(const float* t1, int R1, int C1, const float* t2, int R2, int C2, float* out, int variant,
+                         int swap, int n_split, cudaStream_t st);
 }  // namespace vipsy
 
 using namespace vipsy;
@@ -51,6 +53,11 @@ int vipsy_irt_elbo_grad(const VipsyIrtArgs* a, void* stream) {
   VIPSY_REQUIRE(a->model != VIPSY_IRT_1PL, VIPSY_ERR_ARG,
                 "vipsy_irt_elbo_grad: irt_1pl is D*(x+b) (vi.py:29): defined for K == 1 only");
   return mirt_launch(a, (cudaStream_t)stream);
+}
+
+int vipsy_selftest_umma(const float* t1, int32_t r1, int32_t c1, const float* t2, int32_t r2, int32_t c2, float* out,
+                        int32_t variant, int32_t swap_mn_strides, int32_t n_split, void* stream) {
+  return umma_selftest_launch(t1, r1, c1, t2, r2, c2, out, variant, swap_mn_strides, n_split, (cudaStream_t)stream);
 }
 
 }  // extern "C"
