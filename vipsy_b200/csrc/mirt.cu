@@ -12,41 +12,9 @@
 //   (3) mirt_cholgrad  d mu, d L = -(scale/S) tril(sum_s g_x eps^T) - scale diag(1/L_ii)
 //                      written coalesced in the caller's layout (packed/dense, raw chain rule).
 // HBM traffic is the per-person Cholesky factor in and its gradient out.
-#include "common.cuh"
+#include "mirt.cuh"
 
 namespace vipsy {
-
-// ----------------------------------------------------------------------------------------
-struct MirtParams {
-  const uint8_t* y; int64_t ld_y; const int64_t* idx;
-  const float *mu, *chol, *eps;
-  const float *a, *b, *c, *d;
-  int64_t B;
-  int J, K, S, model, cov_mode, chol_layout, chol_raw;
-  float D, scale;
-  uint64_t seed, offset; int64_t person_offset;
-  // workspace
-  float* x;        // [S*B][K]
-  float* gx;       // [S*B][K]   d(sum_j lb)/dx - x
-  float* ell;      // [S*B]      sum_j lb - 0.5 |x|^2
-  float* aux;      // [B]        S sum_i log L_ii + 0.5 sum_s |eps_s|^2
-  float* diagL;    // [B][K]
-  float* item_partial;   // [grid2][K*J + 3J]   (d_a | d_b | d_c | d_d)
-  float* chol_partial;   // [grid3][tri]        (shared covariance only)
-  double* loss_partial;  // [grid3]
-  // outputs
-  float *d_mu, *d_chol;
-};
-
-__device__ __forceinline__ int tri_off(int i) { return (i * (i + 1)) >> 1; }
-
-__device__ __forceinline__ float noise_at(const MirtParams& p, int s, int64_t b, int k) {
-  if (p.eps) return p.eps[((int64_t)s * p.B + b) * p.K + k];
-  const uint32_t n = (uint32_t)(s * p.K + k);
-  const float4 z = normal4(p.seed, p.offset, (uint64_t)(p.person_offset + b), n >> 2);
-  const float zz[4] = {z.x, z.y, z.z, z.w};
-  return zz[n & 3];
-}
 
 // ----------------------------------------------------------------------------------------
 // (1) sampling.  RT threads per person (RT = 32/64/128 >= K), 128/RT persons per CTA pass.
@@ -128,6 +96,7 @@ __global__ void __launch_bounds__(kSampThreads) mirt_sample_kernel(const MirtPar
             p.x[((int64_t)(s0 + s) * p.B + b) * K + t] = acc[s];
             const float e = es[s * K + t];
             auxp = fmaf(0.5f * e, e, auxp);
+            auxp = fmaf(-0.5f * acc[s], acc[s], auxp);      // log N(x; 0, I) up to the constant
           }
       }
     }
@@ -368,7 +337,7 @@ __global__ void __launch_bounds__(kLikThreads, 2) mirt_lik_kernel(const MirtPara
         }
       }
     }
-    // ---- per-row outputs: g_x = d x - x (prior), ell = ll - 0.5 |x|^2 -------------
+    // ---- per-row outputs: d x and the log-likelihood (prior terms live in aux / cholgrad) ----
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const int pr = ty * 4 + i;
@@ -377,21 +346,12 @@ __global__ void __launch_bounds__(kLikThreads, 2) mirt_lik_kernel(const MirtPara
       ll += __shfl_xor_sync(0xffffffffu, ll, 4);
       ll += __shfl_xor_sync(0xffffffffu, ll, 2);
       ll += __shfl_xor_sync(0xffffffffu, ll, 1);
-      float x2 = 0.f;
 #pragma unroll
       for (int kk = 0; kk < KI; ++kk) {
         const int k = tx + 16 * kk;
-        if (k < K) {
-          const float xv = Xs[pr * KP + k];
-          x2 = fmaf(xv, xv, x2);
-          if (r0 + pr < R) p.gx[(r0 + pr) * K + k] = acc2[i][kk] - xv;
-        }
+        if (k < K && r0 + pr < R) p.gx[(r0 + pr) * K + k] = acc2[i][kk];
       }
-      x2 += __shfl_xor_sync(0xffffffffu, x2, 8);
-      x2 += __shfl_xor_sync(0xffffffffu, x2, 4);
-      x2 += __shfl_xor_sync(0xffffffffu, x2, 2);
-      x2 += __shfl_xor_sync(0xffffffffu, x2, 1);
-      if (tx == 0 && r0 + pr < R) p.ell[r0 + pr] = ll - 0.5f * x2;
+      if (tx == 0 && r0 + pr < R) p.ell[r0 + pr] = ll;
     }
   }
 }
@@ -420,13 +380,18 @@ __global__ void __launch_bounds__(kCgThreads) mirt_cholgrad_kernel(const MirtPar
   for (int64_t b = blockIdx.x; b < p.B; b += gridDim.x) {
     __syncthreads();
     float ellsum = 0.f;
+    const int64_t Rrows = (int64_t)S * p.B;
     for (int e = threadIdx.x; e < S * K; e += kCgThreads) {
       const int s = e / K, k = e - s * K;
-      gs[e] = kf * p.gx[((int64_t)s * p.B + b) * K + k];
+      const int64_t at = ((int64_t)s * p.B + b) * K + k;
+      float g = -p.x[at];                                   // d log N(x; 0, I) / dx
+      for (int part = 0; part < p.n_parts; ++part) g += p.gx[(int64_t)part * Rrows * K + at];
+      gs[e] = kf * g;
       es[e] = noise_at(p, s, b, k);
     }
     if (threadIdx.x == 0) {
-      for (int s = 0; s < S; ++s) ellsum += p.ell[(int64_t)s * p.B + b];
+      for (int s = 0; s < S; ++s)
+        for (int part = 0; part < p.n_parts; ++part) ellsum += p.ell[(int64_t)part * Rrows + (int64_t)s * p.B + b];
       loss_acc += (double)(kf * (ellsum + p.aux[b]));
     }
     __syncthreads();
@@ -489,9 +454,10 @@ static MirtLayout mirt_layout(const VipsyIrtArgs* a) {
   const size_t R = (size_t)a->n_particles * a->batch, K = a->n_dims, J = a->n_items, tri = K * (K + 1) / 2;
   MirtLayout L;
   size_t o = 0;
+  const size_t parts = (size_t)mirt_tc_parts((int)J);      // >= 1: planes of d x / log-lik partials
   L.x = o; o += a16(R * K * 4);
-  L.gx = o; o += a16(R * K * 4);
-  L.ell = o; o += a16(R * 4);
+  L.gx = o; o += a16(parts * R * K * 4);
+  L.ell = o; o += a16(parts * R * 4);
   L.aux = o; o += a16((size_t)a->batch * 4);
   L.diag = o; o += a16((size_t)a->batch * K * 4);
   L.item_part = o; o += a16((size_t)kMirtMaxGrid * (K * J + 3 * J) * 4);
@@ -579,9 +545,14 @@ int mirt_launch(const VipsyIrtArgs* a, cudaStream_t st) {
     int rc = RT == 32 ? launch(mirt_sample_kernel<32>) : (RT == 64 ? launch(mirt_sample_kernel<64>) : launch(mirt_sample_kernel<128>));
     if (rc != VIPSY_OK) return rc;
   }
-  // (2) likelihood + backward contractions
+  // (2) likelihood + backward contractions: tcgen05 for K >= 8 (2PL), SIMT otherwise
   int grid2 = 0;
-  {
+  p.n_parts = 1;
+  const bool want_tc = !(a->flags & VIPSY_IRT_FLAG_NO_TENSOR) && mirt_tc_supported(p);
+  if (want_tc) {
+    int rc = launch_lik_tc(p, &grid2, &p.n_parts, st);
+    if (rc != VIPSY_OK) return rc;
+  } else {
     const int KI = (K + 15) / 16;
     int rc;
     switch (KI) {

@@ -1,0 +1,48 @@
+// Shared declarations of the K > 1 kernels (mirt.cu: sampling, SIMT contraction, guide gradients;
+// mirt_tc.cu: tcgen05 contraction).
+#pragma once
+#include "common.cuh"
+
+namespace vipsy {
+
+// ----------------------------------------------------------------------------------------
+struct MirtParams {
+  const uint8_t* y; int64_t ld_y; const int64_t* idx;
+  const float *mu, *chol, *eps;
+  const float *a, *b, *c, *d;
+  int64_t B;
+  int J, K, S, model, cov_mode, chol_layout, chol_raw;
+  float D, scale;
+  uint64_t seed, offset; int64_t person_offset;
+  // workspace
+  float* x;        // [S*B][K]
+  float* gx;       // [n_parts][S*B][K]  partial d(sum_j lb)/dx, one plane per item tile of the contraction
+  float* ell;      // [n_parts][S*B]     partial sum_j lb
+  float* aux;      // [B]        S sum_i log L_ii + 0.5 sum_s (|eps_s|^2 - |x_s|^2)
+  int n_parts;     // planes of gx / ell the contraction kernel wrote (1 for the SIMT kernel)
+  float* diagL;    // [B][K]
+  float* item_partial;   // [grid2][K*J + 3J]   (d_a | d_b | d_c | d_d)
+  float* chol_partial;   // [grid3][tri]        (shared covariance only)
+  double* loss_partial;  // [grid3]
+  // outputs
+  float *d_mu, *d_chol;
+};
+
+__device__ __forceinline__ int tri_off(int i) { return (i * (i + 1)) >> 1; }
+
+__device__ __forceinline__ float noise_at(const MirtParams& p, int s, int64_t b, int k) {
+  if (p.eps) return p.eps[((int64_t)s * p.B + b) * p.K + k];
+  const uint32_t n = (uint32_t)(s * p.K + k);
+  const float4 z = normal4(p.seed, p.offset, (uint64_t)(p.person_offset + b), n >> 2);
+  const float zz[4] = {z.x, z.y, z.z, z.w};
+  return zz[n & 3];
+}
+
+
+// tcgen05 likelihood contraction (mirt_tc.cu).  rows_out = partial rows written to item_partial,
+// parts_out = number of d x / log-lik partial planes (one per 128-item tile).
+bool mirt_tc_supported(const MirtParams& p);
+int mirt_tc_parts(int J);
+int launch_lik_tc(const MirtParams& p, int* rows_out, int* parts_out, cudaStream_t st);
+
+}  // namespace vipsy

@@ -1,0 +1,350 @@
+// Tensor-core (tcgen05 / TMEM) likelihood contraction of the multidimensional 2PL model
+// (vi.py:32-41 irt_2pl `x.mm(a)`, vi.py:596-615 model, vi.py:617-625 masked Bernoulli likelihood).
+//
+// One CTA owns one 128-item tile (column block of `a`) and walks 128-row tiles of person-samples:
+//
+//   logits[128 x 128] = [x | 1 | 0] [a ; b ; 0]          tcgen05.mma, fp16 hi/lo split (3 MMAs per
+//                                                         16-deep k-step), fp32 accumulation in TMEM
+//   epilogue (TMEM -> registers): 2PL link, clamp, masked Bernoulli log-lik, G = d lb / d logit
+//                                 -> G written back to shared memory as fp16 hi/lo operand tiles
+//   d x [128 x KP]   = G a^T                              (same `a` tile, K-major this time)
+//   d a [KP  x 128] += x^T G                              (same x and G tiles, MN-major), accumulated
+//                                                         in TMEM over every row tile of the CTA;
+//                                                         row K of it is d b (the ones column of x)
+//
+// Neither logits nor G ever reach HBM.  fp16 hi/lo: v = hi + lo with |v - hi - lo| <= 2^-22 |v|
+// (absolute floor 2^-25); the three products hi*hi + hi*lo + lo*hi are exact in the fp32
+// accumulator, so the contraction is fp32-class accurate (measured 6e-7, tests/test_umma_selftest.py)
+// at half the shared-memory footprint and twice the tensor throughput of a 3xTF32 split.
+#include "mirt.cuh"
+#include "umma.cuh"
+
+namespace vipsy {
+
+constexpr int kTcThreads = 256;
+constexpr int kTcTM = 128;                 // person-sample rows per tile (UMMA M)
+constexpr int kTcTN = 128;                 // items per CTA (UMMA N of the forward product)
+constexpr int kTcYStride = kTcTN + 4;      // response tile row stride (bank-conflict-free row reads)
+constexpr uint32_t kCS = 128;              // byte stride between core matrices along the contiguous dim
+constexpr uint32_t kTmemCols = 512;
+constexpr uint32_t kColLogit = 0, kColDx = 128, kColDa = 256;
+
+__host__ __device__ inline int tc_kp(int K) { return ((K + 1 + 15) / 16) * 16; }   // + ones column, k-step 16
+
+struct TcSmem {
+  uint32_t rsA, rsX, rsG, bytesA, bytesX, bytesG;
+  uint32_t offAh, offAl, offXh, offXl, offGh, offGl, offY, offLL, total;
+};
+__host__ __device__ inline TcSmem tc_smem(int K) {
+  const int KP = tc_kp(K);
+  TcSmem s;
+  s.rsA = (kTcTN / 8) * kCS;              // a tile: rows k (KP), cols j (128)
+  s.rsX = (uint32_t)(KP / 8) * kCS;       // x tile: rows person-sample (128), cols k (KP)
+  s.rsG = (kTcTN / 8) * kCS;              // G tile: rows person-sample (128), cols j (128)
+  s.bytesA = (uint32_t)(KP / 8) * s.rsA;
+  s.bytesX = (kTcTM / 8) * s.rsX;
+  s.bytesG = (kTcTM / 8) * s.rsG;
+  uint32_t o = 0;
+  s.offAh = o; o += s.bytesA;
+  s.offAl = o; o += s.bytesA;
+  s.offXh = o; o += s.bytesX;
+  s.offXl = o; o += s.bytesX;             // the M = 128 read of x^T runs up to 2 KB past a tile: lands in Xl / Gh
+  s.offGh = o; o += s.bytesG;
+  s.offGl = o; o += s.bytesG;
+  s.offY = o; o += kTcTM * kTcYStride;
+  s.offLL = o; o += 2 * kTcTM * 4;
+  s.total = o;
+  return s;
+}
+
+__device__ __forceinline__ uint32_t pack_half2(float a, float b) {
+  __half2 h = __floats2half2_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+// 8 floats -> one 16-byte chunk of fp16 "hi" and one of fp16 "lo"
+__device__ __forceinline__ void split_store8(const float (&v)[8], unsigned char* hi_dst, unsigned char* lo_dst) {
+  uint32_t h[4], l[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    __half2 hh = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
+    const float2 hf = __half22float2(hh);
+    h[i] = *reinterpret_cast<uint32_t*>(&hh);
+    l[i] = pack_half2(v[2 * i] - hf.x, v[2 * i + 1] - hf.y);
+  }
+  *reinterpret_cast<uint4*>(hi_dst) = make_uint4(h[0], h[1], h[2], h[3]);
+  *reinterpret_cast<uint4*>(lo_dst) = make_uint4(l[0], l[1], l[2], l[3]);
+}
+
+__global__ void __launch_bounds__(kTcThreads, 1) mirt_tc_lik_kernel(const MirtParams p, const int n_jt, const int G) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_base_sm;
+  const int K = p.K, J = p.J, KP = tc_kp(K);
+  const TcSmem L = tc_smem(K);
+  unsigned char* Ah = smem + L.offAh;
+  unsigned char* Al = smem + L.offAl;
+  unsigned char* Xh = smem + L.offXh;
+  unsigned char* Xl = smem + L.offXl;
+  unsigned char* Gh = smem + L.offGh;
+  unsigned char* Gl = smem + L.offGl;
+  unsigned char* ytile = smem + L.offY;
+  float* llsm = reinterpret_cast<float*>(smem + L.offLL);     // [2][128]
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int quad = warp & 3, half = warp >> 2;                // TMEM lane quadrant, column half
+  const int jt = blockIdx.x % n_jt, g = blockIdx.x / n_jt;
+  const int j0 = jt * kTcTN;
+  const int64_t R = (int64_t)p.S * p.B;
+  const int64_t ntile_m = (R + kTcTM - 1) / kTcTM;
+  const int nck = KP / 8;                                      // 16-byte chunks per x row
+  const float negDl2e = -p.D * kLog2e;
+
+  // ---- one-time: a tile (rows k < K: a[k][j]; row K: b[j]; rows > K: 0), barrier, TMEM ----------
+  for (int e = tid; e < KP * (kTcTN / 8); e += kTcThreads) {
+    const int k = e / (kTcTN / 8), c8 = e - k * (kTcTN / 8);
+    float v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int j = j0 + c8 * 8 + i;
+      float t = 0.f;
+      if (j < J) {
+        if (k < K) t = p.a[(size_t)k * J + j];
+        else if (k == K) t = p.b[j];
+      }
+      v[i] = t;
+    }
+    const uint32_t o = umma::tile_off(k, c8 * 8, L.rsA, kCS);
+    split_store8(v, Ah + o, Al + o);
+  }
+  if (warp == 0) umma::tmem_alloc(&tmem_base_sm, kTmemCols);
+  if (tid == 0) {
+    umma::mbar_init(&bar, 1);
+    umma::fence_mbar_init();
+  }
+  umma::fence_before_sync();
+  __syncthreads();
+  umma::fence_after_sync();
+  const uint32_t tmem = tmem_base_sm;
+  const uint32_t tmem_row = tmem + ((uint32_t)(quad * 32) << 16);
+  uint32_t phase = 0;
+
+  const uint32_t idesc_fwd = umma::make_idesc_f16(kTcTM, kTcTN, umma::kMajorK, umma::kMajorMN);
+  const uint32_t idesc_dx = umma::make_idesc_f16(kTcTM, KP, umma::kMajorK, umma::kMajorK);
+  const uint32_t idesc_da = umma::make_idesc_f16(128, kTcTN, umma::kMajorMN, umma::kMajorMN);
+  const uint32_t sAh = umma::smem_u32(Ah), sAl = umma::smem_u32(Al), sXh = umma::smem_u32(Xh), sXl = umma::smem_u32(Xl),
+                 sGh = umma::smem_u32(Gh), sGl = umma::smem_u32(Gl);
+  const bool y_fast = ((p.ld_y & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.y) & 3) == 0) && (j0 + kTcTN <= J);
+  bool first_tile = true;
+
+  for (int64_t tm = g; tm < ntile_m; tm += G) {
+    const int64_t r0 = tm * kTcTM;
+    // ---- stage x tile as fp16 hi/lo: [x_0..x_{K-1} | 1 | 0...]; invalid rows all zero ----------
+    for (int e = tid; e < kTcTM * nck; e += kTcThreads) {
+      const int pr = e / nck, c8 = e - pr * nck;
+      const int64_t r = r0 + pr;
+      float v[8];
+      if (r < R) {
+        const float* src = p.x + r * K + c8 * 8;
+        if ((K & 3) == 0 && c8 * 8 + 8 <= K) {
+          const float4 u0 = *reinterpret_cast<const float4*>(src);
+          const float4 u1 = *reinterpret_cast<const float4*>(src + 4);
+          v[0] = u0.x; v[1] = u0.y; v[2] = u0.z; v[3] = u0.w;
+          v[4] = u1.x; v[5] = u1.y; v[6] = u1.z; v[7] = u1.w;
+        } else {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int k = c8 * 8 + i;
+            v[i] = k < K ? src[i] : (k == K ? 1.f : 0.f);
+          }
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = 0.f;
+      }
+      const uint32_t o = umma::tile_off(pr, c8 * 8, L.rsX, kCS);
+      split_store8(v, Xh + o, Xl + o);
+    }
+    // ---- response tile ---------------------------------------------------------------------------
+    if (y_fast) {
+      for (int e = tid; e < kTcTM * (kTcTN / 4); e += kTcThreads) {
+        const int pr = e / (kTcTN / 4), w = e - pr * (kTcTN / 4);
+        uint32_t code4 = 0xffffffffu;
+        if (r0 + pr < R) {
+          const int64_t bb = (r0 + pr) % p.B;
+          const int64_t row = p.idx ? p.idx[bb] : bb;
+          code4 = *reinterpret_cast<const uint32_t*>(p.y + row * p.ld_y + j0 + w * 4);
+        }
+        *reinterpret_cast<uint32_t*>(ytile + pr * kTcYStride + w * 4) = code4;
+      }
+    } else {
+      for (int e = tid; e < kTcTM * kTcTN; e += kTcThreads) {
+        const int pr = e / kTcTN, jj = e - pr * kTcTN;
+        unsigned char code = 255;
+        if (r0 + pr < R && j0 + jj < J) {
+          const int64_t bb = (r0 + pr) % p.B;
+          const int64_t row = p.idx ? p.idx[bb] : bb;
+          code = p.y[row * p.ld_y + j0 + jj];
+        }
+        ytile[pr * kTcYStride + jj] = code;
+      }
+    }
+    umma::fence_proxy_async();
+    __syncthreads();
+
+    // ---- forward: logits = [x|1] [a;b]  (A operand K-major from the x tile, B MN-major from the a tile)
+    if (tid == 0) {
+      umma::fence_after_sync();
+      uint32_t acc = 0;
+      for (int ks = 0; ks < KP / 16; ++ks) {
+#pragma unroll
+        for (int term = 0; term < 3; ++term) {               // hi*hi, hi*lo, lo*hi
+          const uint64_t da = umma::make_desc((term == 2 ? sXl : sXh) + ks * 2 * kCS, kCS, L.rsX);
+          const uint64_t db = umma::make_desc((term == 1 ? sAl : sAh) + ks * 2 * L.rsA, L.rsA, kCS);
+          umma::mma_f16_ss(tmem + kColLogit, da, db, idesc_fwd, acc);
+          acc = 1;
+        }
+      }
+      umma::commit(&bar);
+    }
+    umma::mbar_wait(&bar, phase);
+    phase ^= 1;
+    umma::fence_after_sync();
+
+    // ---- epilogue: this thread owns row (quad*32 + lane), columns [half*64, half*64 + 64) ---------
+    const int pr = quad * 32 + lane;
+    float ll = 0.f;
+#pragma unroll 1
+    for (int cc = 0; cc < 2; ++cc) {
+      const int c0 = half * 64 + cc * 32;
+      float v[32];
+      umma::tmem_ld32(tmem_row + kColLogit + c0, v);
+      uint32_t yw[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) yw[i] = *reinterpret_cast<const uint32_t*>(ytile + pr * kTcYStride + c0 + i * 4);
+#pragma unroll
+      for (int c8 = 0; c8 < 4; ++c8) {
+        float gl8[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int cidx = c8 * 8 + i;
+          const uint32_t code = (yw[cidx >> 2] >> ((cidx & 3) * 8)) & 0xffu;
+          float gl = 0.f;
+          if (code != 255u) {
+            const bool y1 = code != 0u;
+            float t = negDl2e * v[cidx];                      // -l log2e, l = D (x.a + b)
+            t = y1 ? t : -t;
+            t = fminf(t, 126.f);
+            const float e = ex2_approx(t);
+            const float sp = rcp_approx(1.f + e);             // s (y=1) | 1-s (y=0)
+            const float es = e * sp;
+            const float qc = fminf(fmaxf(sp, kEps32), kOneMinusEps32);
+            ll += kLn2 * lg2_approx(qc);
+            if (sp == qc) gl = (y1 ? p.D : -p.D) * es;
+          }
+          gl8[i] = gl;
+        }
+        const uint32_t o = umma::tile_off(pr, c0 + c8 * 8, L.rsG, kCS);
+        split_store8(gl8, Gh + o, Gl + o);
+      }
+    }
+    llsm[half * kTcTM + pr] = ll;
+    umma::fence_before_sync();
+    umma::fence_proxy_async();
+    __syncthreads();
+
+    // ---- backward: d x = G a^T (cols kColDx..), d a += x^T G (cols kColDa.., lives across row tiles)
+    if (tid == 0) {
+      umma::fence_after_sync();
+      uint32_t acc = 0;
+      for (int ks = 0; ks < kTcTN / 16; ++ks) {
+#pragma unroll
+        for (int term = 0; term < 3; ++term) {
+          const uint64_t da = umma::make_desc((term == 2 ? sGl : sGh) + ks * 2 * kCS, kCS, L.rsG);
+          const uint64_t db = umma::make_desc((term == 1 ? sAl : sAh) + ks * 2 * kCS, kCS, L.rsA);
+          umma::mma_f16_ss(tmem + kColDx, da, db, idesc_dx, acc);
+          acc = 1;
+        }
+      }
+      acc = first_tile ? 0u : 1u;
+      for (int ks = 0; ks < kTcTM / 16; ++ks) {
+#pragma unroll
+        for (int term = 0; term < 3; ++term) {
+          const uint64_t da = umma::make_desc((term == 2 ? sXl : sXh) + ks * 2 * L.rsX, L.rsX, kCS);
+          const uint64_t db = umma::make_desc((term == 1 ? sGl : sGh) + ks * 2 * L.rsG, L.rsG, kCS);
+          umma::mma_f16_ss(tmem + kColDa, da, db, idesc_da, acc);
+          acc = 1;
+        }
+      }
+      umma::commit(&bar);
+    }
+    first_tile = false;
+    // per-row log-likelihood partial of this item tile (both column halves)
+    if (tid < kTcTM && r0 + tid < R) p.ell[(int64_t)jt * R + r0 + tid] = llsm[tid] + llsm[kTcTM + tid];
+    umma::mbar_wait(&bar, phase);
+    phase ^= 1;
+    umma::fence_after_sync();
+
+    // ---- d x read-out: 16-column groups alternate between the two column halves --------------------
+    {
+      float* dst = p.gx + ((int64_t)jt * R + r0 + pr) * K;
+      const bool rvalid = r0 + pr < R;
+      for (int c0 = half * 16; c0 < K; c0 += 32) {
+        float v[16];
+        umma::tmem_ld16(tmem_row + kColDx + c0, v);
+        if (rvalid) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i)
+            if (c0 + i < K) dst[c0 + i] = v[i];
+        }
+      }
+    }
+    umma::fence_before_sync();
+    __syncthreads();
+  }
+
+  // ---- flush d a (rows k < K) and d b (row K) of this CTA's item tile --------------------------------
+  umma::fence_after_sync();
+  {
+    const int k = quad * 32 + lane;
+    float* part = p.item_partial + (size_t)g * ((size_t)K * J + 3 * (size_t)J);
+    for (int cc = 0; cc < 4; ++cc) {
+      const int c0 = half * 64 + cc * 16;
+      float v[16];
+      umma::tmem_ld16(tmem_row + kColDa + c0, v);
+      if (k <= K) {
+        float* dst = part + (size_t)k * J + j0 + c0;          // k == K lands on the d_b segment (offset K*J)
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+          if (j0 + c0 + i < J) dst[i] = v[i];
+      }
+    }
+  }
+  umma::fence_before_sync();
+  __syncthreads();
+  if (warp == 0) umma::tmem_dealloc(tmem, kTmemCols);
+}
+
+// ----------------------------------------------------------------------------------------------------
+int mirt_tc_parts(int J) { return (J + kTcTN - 1) / kTcTN; }
+
+bool mirt_tc_supported(const MirtParams& p) {
+  return p.model == VIPSY_IRT_2PL && p.K >= 8 && tc_kp(p.K) <= 128;
+}
+
+int launch_lik_tc(const MirtParams& p, int* rows_out, int* parts_out, cudaStream_t st) {
+  const int n_jt = mirt_tc_parts(p.J);
+  const int64_t ntile_m = ((int64_t)p.S * p.B + kTcTM - 1) / kTcTM;
+  int64_t G = num_sms() / n_jt;
+  if (G < 1) G = 1;
+  if (G > ntile_m) G = ntile_m;
+  const TcSmem L = tc_smem(p.K);
+  VIPSY_REQUIRE(L.total <= 227 * 1024, VIPSY_ERR_UNSUPPORTED, "mirt_tc: shared memory %u B exceeds 227 KB", L.total);
+  VIPSY_CUDA_CHECK(cudaFuncSetAttribute(mirt_tc_lik_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
+  mirt_tc_lik_kernel<<<(int)(G * n_jt), kTcThreads, L.total, st>>>(p, n_jt, (int)G);
+  VIPSY_CUDA_CHECK(cudaGetLastError());
+  *rows_out = (int)G;
+  *parts_out = n_jt;
+  return VIPSY_OK;
+}
+
+}  // namespace vipsy
