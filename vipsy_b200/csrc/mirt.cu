@@ -529,8 +529,12 @@ int mirt_launch(const VipsyIrtArgs* a, cudaStream_t st) {
   }
   const bool shared_cov = a->cov_mode == VIPSY_COV_SHARED;
 
+  const bool stream = mirt_stream_supported(p);
   // (1) sample
-  {
+  if (stream) {
+    int rc = launch_sample_stream(p, kMirtMaxGrid, st);
+    if (rc != VIPSY_OK) return rc;
+  } else {
     const int RT = K <= 32 ? 32 : (K <= 64 ? 64 : 128);
     const int slots = kSampThreads / RT;
     const size_t smem = ((size_t)(shared_cov ? 1 : slots) * tri + (size_t)slots * kSampChunk * K) * 4;
@@ -569,7 +573,10 @@ int mirt_launch(const VipsyIrtArgs* a, cudaStream_t st) {
   }
   // (3) guide gradients + loss partials
   int grid3;
-  {
+  if (stream) {
+    int rc = launch_cholgrad_stream(p, kMirtMaxGrid, &grid3, st);
+    if (rc != VIPSY_OK) return rc;
+  } else {
     const size_t smem = ((size_t)2 * a->n_particles * K + (shared_cov ? tri : 0)) * 4;
     int64_t g = a->batch;
     const int64_t cap = shared_cov ? (int64_t)num_sms() * 2 : kMirtMaxGrid;

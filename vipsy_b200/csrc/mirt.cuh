@@ -45,4 +45,10 @@ bool mirt_tc_supported(const MirtParams& p);
 int mirt_tc_parts(int J);
 int launch_lik_tc(const MirtParams& p, int* rows_out, int* parts_out, cudaStream_t st);
 
+
+// streaming sampler / guide-gradient kernels for per-person factors, S <= 2 (mirt_stream.cu)
+bool mirt_stream_supported(const MirtParams& p);
+int launch_sample_stream(const MirtParams& p, int max_grid, cudaStream_t st);
+int launch_cholgrad_stream(const MirtParams& p, int max_grid, int* grid_out, cudaStream_t st);
+
 }  // namespace vipsy

@@ -33,7 +33,7 @@ __host__ __device__ inline int tc_kp(int K) { return ((K + 1 + 15) / 16) * 16; }
 
 struct TcSmem {
   uint32_t rsA, rsX, rsG, bytesA, bytesX, bytesG;
-  uint32_t offAh, offAl, offXh, offXl, offGh, offGl, offY, offLL, total;
+  uint32_t offAh, offAl, offXh, offXl, offGh, offGl, offY, offLL, offRow, total;
 };
 __host__ __device__ inline TcSmem tc_smem(int K) {
   const int KP = tc_kp(K);
@@ -53,6 +53,7 @@ __host__ __device__ inline TcSmem tc_smem(int K) {
   s.offGl = o; o += s.bytesG;
   s.offY = o; o += kTcTM * kTcYStride;
   s.offLL = o; o += 2 * kTcTM * 4;
+  s.offRow = o; o += kTcTM * 8;
   s.total = o;
   return s;
 }
@@ -89,6 +90,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) mirt_tc_lik_kernel(const MirtPa
   unsigned char* Gl = smem + L.offGl;
   unsigned char* ytile = smem + L.offY;
   float* llsm = reinterpret_cast<float*>(smem + L.offLL);     // [2][128]
+  int64_t* rowsm = reinterpret_cast<int64_t*>(smem + L.offRow);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int quad = warp & 3, half = warp >> 2;                // TMEM lane quadrant, column half
@@ -133,58 +135,96 @@ __global__ void __launch_bounds__(kTcThreads, 1) mirt_tc_lik_kernel(const MirtPa
   const uint32_t idesc_da = umma::make_idesc_f16(128, kTcTN, umma::kMajorMN, umma::kMajorMN);
   const uint32_t sAh = umma::smem_u32(Ah), sAl = umma::smem_u32(Al), sXh = umma::smem_u32(Xh), sXl = umma::smem_u32(Xl),
                  sGh = umma::smem_u32(Gh), sGl = umma::smem_u32(Gl);
-  const bool y_fast = ((p.ld_y & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.y) & 3) == 0) && (j0 + kTcTN <= J);
+  const bool y_words = ((p.ld_y & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.y) & 3) == 0);
   bool first_tile = true;
 
   for (int64_t tm = g; tm < ntile_m; tm += G) {
     const int64_t r0 = tm * kTcTM;
-    // ---- stage x tile as fp16 hi/lo: [x_0..x_{K-1} | 1 | 0...]; invalid rows all zero ----------
-    for (int e = tid; e < kTcTM * nck; e += kTcThreads) {
-      const int pr = e / nck, c8 = e - pr * nck;
-      const int64_t r = r0 + pr;
-      float v[8];
+    // ---- y-row index of each tile row (one 64-bit modulo per row, not per cell) -----------------------
+    if (tid < kTcTM) {
+      const int64_t r = r0 + tid;
+      int64_t row = -1;
       if (r < R) {
-        const float* src = p.x + r * K + c8 * 8;
-        if ((K & 3) == 0 && c8 * 8 + 8 <= K) {
-          const float4 u0 = *reinterpret_cast<const float4*>(src);
-          const float4 u1 = *reinterpret_cast<const float4*>(src + 4);
-          v[0] = u0.x; v[1] = u0.y; v[2] = u0.z; v[3] = u0.w;
-          v[4] = u1.x; v[5] = u1.y; v[6] = u1.z; v[7] = u1.w;
+        const int64_t bb = r % p.B;
+        row = p.idx ? p.idx[bb] : bb;
+      }
+      rowsm[tid] = row;
+    }
+    // ---- stage x tile as fp16 hi/lo: [x_0..x_{K-1} | 1 | 0...]; invalid rows all zero ----------
+    // four independent 32-byte loads in flight per thread before the first conversion
+    for (int e0 = tid; e0 < kTcTM * nck; e0 += 4 * kTcThreads) {
+      float v[4][8];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int e = e0 + u * kTcThreads;
+        const int pr = e / nck, c8 = e - pr * nck;
+        const int64_t r = r0 + pr;
+        if (e < kTcTM * nck && r < R) {
+          const float* src = p.x + r * K + c8 * 8;
+          if ((K & 3) == 0 && c8 * 8 + 8 <= K) {
+            const float4 u0 = *reinterpret_cast<const float4*>(src);
+            const float4 u1 = *reinterpret_cast<const float4*>(src + 4);
+            v[u][0] = u0.x; v[u][1] = u0.y; v[u][2] = u0.z; v[u][3] = u0.w;
+            v[u][4] = u1.x; v[u][5] = u1.y; v[u][6] = u1.z; v[u][7] = u1.w;
+          } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int k = c8 * 8 + i;
+              v[u][i] = k < K ? src[i] : (k == K ? 1.f : 0.f);
+            }
+          }
         } else {
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int k = c8 * 8 + i;
-            v[i] = k < K ? src[i] : (k == K ? 1.f : 0.f);
-          }
+          for (int i = 0; i < 8; ++i) v[u][i] = 0.f;
         }
-      } else {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) v[i] = 0.f;
       }
-      const uint32_t o = umma::tile_off(pr, c8 * 8, L.rsX, kCS);
-      split_store8(v, Xh + o, Xl + o);
-    }
-    // ---- response tile ---------------------------------------------------------------------------
-    if (y_fast) {
-      for (int e = tid; e < kTcTM * (kTcTN / 4); e += kTcThreads) {
-        const int pr = e / (kTcTN / 4), w = e - pr * (kTcTN / 4);
-        uint32_t code4 = 0xffffffffu;
-        if (r0 + pr < R) {
-          const int64_t bb = (r0 + pr) % p.B;
-          const int64_t row = p.idx ? p.idx[bb] : bb;
-          code4 = *reinterpret_cast<const uint32_t*>(p.y + row * p.ld_y + j0 + w * 4);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int e = e0 + u * kTcThreads;
+        if (e < kTcTM * nck) {
+          const int pr = e / nck, c8 = e - pr * nck;
+          const uint32_t o = umma::tile_off(pr, c8 * 8, L.rsX, kCS);
+          split_store8(v[u], Xh + o, Xl + o);
         }
-        *reinterpret_cast<uint32_t*>(ytile + pr * kTcYStride + w * 4) = code4;
+      }
+    }
+    __syncthreads();                                        // rowsm visible
+    // ---- response tile: 32-bit loads (8 in flight per thread) when rows are word-aligned ---------------
+    if (y_words) {
+      for (int e0 = tid; e0 < kTcTM * (kTcTN / 4); e0 += 8 * kTcThreads) {
+        uint32_t code4[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int e = e0 + u * kTcThreads;
+          const int pr = e / (kTcTN / 4), w = e - pr * (kTcTN / 4);
+          const int64_t row = rowsm[pr];
+          const int j = j0 + w * 4;
+          uint32_t c4 = 0xffffffffu;
+          if (row >= 0 && j < J) {
+            const unsigned char* src = p.y + row * p.ld_y + j;
+            if (j + 4 <= J) {
+              c4 = *reinterpret_cast<const uint32_t*>(src);
+            } else {                                        // ragged tail word of the last item tile
+              c4 = 0;
+#pragma unroll
+              for (int i = 0; i < 4; ++i) c4 |= (uint32_t)(j + i < J ? src[i] : 255u) << (8 * i);
+            }
+          }
+          code4[u] = c4;
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int e = e0 + u * kTcThreads;
+          const int pr = e / (kTcTN / 4), w = e - pr * (kTcTN / 4);
+          *reinterpret_cast<uint32_t*>(ytile + pr * kTcYStride + w * 4) = code4[u];
+        }
       }
     } else {
       for (int e = tid; e < kTcTM * kTcTN; e += kTcThreads) {
         const int pr = e / kTcTN, jj = e - pr * kTcTN;
+        const int64_t row = rowsm[pr];
         unsigned char code = 255;
-        if (r0 + pr < R && j0 + jj < J) {
-          const int64_t bb = (r0 + pr) % p.B;
-          const int64_t row = p.idx ? p.idx[bb] : bb;
-          code = p.y[row * p.ld_y + j0 + jj];
-        }
+        if (row >= 0 && j0 + jj < J) code = p.y[row * p.ld_y + j0 + jj];
         ytile[pr * kTcYStride + jj] = code;
       }
     }
