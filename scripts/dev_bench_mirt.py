@@ -7,7 +7,8 @@ from scripts.dev_bench_uni import timeit
 
 if __name__ == "__main__":
     N = int(sys.argv[1]) if len(sys.argv) > 1 else 200_000
-    for (K, J, S) in ((100, 500, 1), (10, 100, 8), (2, 50, 8)):
+    cfgs = ((100, 500, 1),) if os.environ.get('VIPSY_C3_ONLY') else ((100, 500, 1), (10, 100, 8), (2, 50, 8))
+    for (K, J, S) in cfgs:
         n = N if K == 100 else 500_000
         w = workloads.mirt(n, J, K)
         off = [0]

@@ -54,3 +54,11 @@ def test_tc_saturated_logits(ops):
     cs["a"] = torch.ones_like(cs["a"]) * cs["free"]
     cs["mu"] = cs["mu"] * 3.0
     run(ops, cs, layout="packed", raw=True)
+
+
+@pytest.mark.parametrize("B,K,S", [(37, 100, 1), (64, 33, 2), (5, 16, 1), (131, 64, 2), (19, 127, 1), (257, 18, 1)])
+def test_streamed_guide_kernels(ops, B, K, S):
+    """Warp-per-person streaming sampler / guide-gradient kernels (per-person factors, S <= 2), packed and dense."""
+    cs = make(B=B, J=40, K=K, S=S, model="irt_2pl", seed=B + K)
+    run(ops, cs, layout="packed", raw=True, scale=2.0)
+    run(ops, cs, layout="dense", raw=False, scale=0.5)

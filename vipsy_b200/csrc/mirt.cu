@@ -12,6 +12,8 @@
 //   (3) mirt_cholgrad  d mu, d L = -(scale/S) tril(sum_s g_x eps^T) - scale diag(1/L_ii)
 //                      written coalesced in the caller's layout (packed/dense, raw chain rule).
 // HBM traffic is the per-person Cholesky factor in and its gradient out.
+#include <stdlib.h>
+
 #include "mirt.cuh"
 
 namespace vipsy {
@@ -108,7 +110,7 @@ __global__ void __launch_bounds__(kSampThreads) mirt_sample_kernel(const MirtPar
     if (valid && t == 0) {
       float tot = 0.f;
       for (int w = 0; w < RT / 32; ++w) tot += red_sm[slot * (RT / 32) + w];
-      p.aux[b] = tot;
+      *reinterpret_cast<float4*>(p.aux + 4 * b) = make_float4(tot, 0.f, 0.f, 0.f);
     }
   }
 }
@@ -392,7 +394,8 @@ __global__ void __launch_bounds__(kCgThreads) mirt_cholgrad_kernel(const MirtPar
     if (threadIdx.x == 0) {
       for (int s = 0; s < S; ++s)
         for (int part = 0; part < p.n_parts; ++part) ellsum += p.ell[(int64_t)part * Rrows + (int64_t)s * p.B + b];
-      loss_acc += (double)(kf * (ellsum + p.aux[b]));
+      const float4 ax = *reinterpret_cast<const float4*>(p.aux + 4 * b);
+      loss_acc += (double)(kf * (ellsum + ((ax.x + ax.y) + (ax.z + ax.w))));
     }
     __syncthreads();
     if (p.d_mu)
@@ -458,7 +461,7 @@ static MirtLayout mirt_layout(const VipsyIrtArgs* a) {
   L.x = o; o += a16(R * K * 4);
   L.gx = o; o += a16(parts * R * K * 4);
   L.ell = o; o += a16(parts * R * 4);
-  L.aux = o; o += a16((size_t)a->batch * 4);
+  L.aux = o; o += a16((size_t)a->batch * 16);
   L.diag = o; o += a16((size_t)a->batch * K * 4);
   L.item_part = o; o += a16((size_t)kMirtMaxGrid * (K * J + 3 * J) * 4);
   L.chol_part = o; o += a16(a->cov_mode == VIPSY_COV_SHARED ? (size_t)kMirtMaxGrid * tri * 4 : 0);
@@ -523,6 +526,7 @@ int mirt_launch(const VipsyIrtArgs* a, cudaStream_t st) {
   p.chol_partial = reinterpret_cast<float*>(ws + L.chol_part);
   p.loss_partial = reinterpret_cast<double*>(ws + L.loss_part);
   p.d_mu = a->d_mu; p.d_chol = a->d_chol;
+  { const char* e = getenv("VIPSY_DBG"); p.dbg = e ? atoi(e) : 0; }
   if (a->batch == 0) {
     VIPSY_CUDA_CHECK(cudaMemsetAsync(a->loss, 0, 8, st));
     return VIPSY_OK;

@@ -18,7 +18,8 @@ struct MirtParams {
   float* x;        // [S*B][K]
   float* gx;       // [n_parts][S*B][K]  partial d(sum_j lb)/dx, one plane per item tile of the contraction
   float* ell;      // [n_parts][S*B]     partial sum_j lb
-  float* aux;      // [B]        S sum_i log L_ii + 0.5 sum_s (|eps_s|^2 - |x_s|^2)
+  float* aux;      // [B][4]     S sum_i log L_ii + 0.5 sum_s (|eps_s|^2 - |x_s|^2), split over up to 4 row blocks
+  int dbg;         // development switches (VIPSY_DBG), 0 in production
   int n_parts;     // planes of gx / ell the contraction kernel wrote (1 for the SIMT kernel)
   float* diagL;    // [B][K]
   float* item_partial;   // [grid2][K*J + 3J]   (d_a | d_b | d_c | d_d)
@@ -32,12 +33,30 @@ __device__ __forceinline__ int tri_off(int i) { return (i * (i + 1)) >> 1; }
 
 __device__ __forceinline__ float noise_at(const MirtParams& p, int s, int64_t b, int k) {
   if (p.eps) return p.eps[((int64_t)s * p.B + b) * p.K + k];
-  const uint32_t n = (uint32_t)(s * p.K + k);
-  const float4 z = normal4(p.seed, p.offset, (uint64_t)(p.person_offset + b), n >> 2);
-  const float zz[4] = {z.x, z.y, z.z, z.w};
-  return zz[n & 3];
+  uint32_t block;
+  int comp;
+  noise_coord(s, k, p.K, block, comp);
+  const float4 z = normal4(p.seed, p.offset, (uint64_t)(p.person_offset + b), block);
+  return comp == 0 ? z.x : (comp == 1 ? z.y : (comp == 2 ? z.z : z.w));
 }
 
+// N(0,1) draws of the dimensions lane, lane+32, lane+64, lane+96 of person b, particle s (0 beyond K):
+// one Philox call per lane thanks to noise_coord()'s K > 1 layout.
+__device__ __forceinline__ void noise_lane4(const MirtParams& p, int s, int64_t b, int lane, float (&z)[4]) {
+  if (p.eps) {
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const int m = lane + 32 * c;
+      z[c] = m < p.K ? p.eps[((int64_t)s * p.B + b) * p.K + m] : 0.f;
+    }
+  } else {
+    const float4 v = normal4(p.seed, p.offset, (uint64_t)(p.person_offset + b), (uint32_t)s * 32u + (uint32_t)lane);
+    z[0] = lane < p.K ? v.x : 0.f;
+    z[1] = lane + 32 < p.K ? v.y : 0.f;
+    z[2] = lane + 64 < p.K ? v.z : 0.f;
+    z[3] = lane + 96 < p.K ? v.w : 0.f;
+  }
+}
 
 // tcgen05 likelihood contraction (mirt_tc.cu).  rows_out = partial rows written to item_partial,
 // parts_out = number of d x / log-lik partial planes (one per 128-item tile).

@@ -50,9 +50,9 @@ __global__ void __launch_bounds__(kStreamThreads) mirt_sample_stream_kernel(cons
       float dg = ok ? Lp[PACKED ? tri_off(m) + m : m * K + m] : 0.f;
       if (p.chol_raw) dg = __expf(dg);
       lii[c] = ok ? dg : 1.f;
-#pragma unroll
-      for (int s = 0; s < S; ++s) e[s][c] = ok ? noise_at(p, s, b, m) : 0.f;
     }
+#pragma unroll
+    for (int s = 0; s < S; ++s) noise_lane4(p, s, b, lane, e[s]);
     float auxp = 0.f;
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
@@ -107,8 +107,40 @@ __global__ void __launch_bounds__(kStreamThreads) mirt_sample_stream_kernel(cons
       }
     }
     auxp = warp_sum(auxp);
-    if (lane == 0) p.aux[b] = auxp;
+    if (lane == 0) *reinterpret_cast<float4*>(p.aux + 4 * b) = make_float4(auxp, 0.f, 0.f, 0.f);
   }
+}
+
+// Raw inputs of one person for the guide-gradient stream, fetched one person AHEAD of their use so the
+// global-load latency hides behind the previous person's row stores.
+template <int S>
+struct CgInputs {
+  float x[S][4], g[S][4][4], lii[4], ev;
+};
+
+template <int S>
+__device__ __forceinline__ void cg_fetch(const MirtParams& p, int64_t b, int lane, int nrb, int64_t Rrows, CgInputs<S>& in) {
+  const int K = p.K;
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    const int m = lane + 32 * c;
+    const bool ok = c < nrb && m < K;
+    in.lii[c] = ok ? p.diagL[b * K + m] : 1.f;
+#pragma unroll
+    for (int s = 0; s < S; ++s) {
+      const int64_t at = ((int64_t)s * p.B + b) * K + m;
+      in.x[s][c] = ok ? p.x[at] : 0.f;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) in.g[s][c][u] = (ok && u < p.n_parts) ? p.gx[(int64_t)u * Rrows * K + at] : 0.f;
+    }
+  }
+  // loss inputs: lanes fetch the 4 aux words and the S * n_parts log-likelihood partials in parallel
+  float ev = lane < 4 ? p.aux[4 * b + lane] : 0.f;
+  for (int q = lane; q < S * p.n_parts; q += 32) {
+    const int s = q / p.n_parts, part = q - s * p.n_parts;
+    ev += p.ell[(int64_t)part * Rrows + (int64_t)s * p.B + b];
+  }
+  in.ev = ev;
 }
 
 template <int S, bool PACKED>
@@ -119,40 +151,40 @@ __global__ void __launch_bounds__(kStreamThreads) mirt_cholgrad_stream_kernel(co
   const int nrb = (K + 31) >> 5;
   const float kf = -p.scale / (float)S;
   const int64_t Rrows = (int64_t)S * p.B;
+  const int64_t step = (int64_t)gridDim.x * kStreamWarps;
   double loss_acc = 0.0;
 
-  for (int64_t b = (int64_t)blockIdx.x * kStreamWarps + warp; b < p.B; b += (int64_t)gridDim.x * kStreamWarps) {
+  int64_t b = (int64_t)blockIdx.x * kStreamWarps + warp;
+  CgInputs<S> cur, nxt;
+  if (b < p.B) cg_fetch<S>(p, b, lane, nrb, Rrows, cur);
+  for (; b < p.B; b += step) {
+    if (b + step < p.B) cg_fetch<S>(p, b + step, lane, nrb, Rrows, nxt);
     // per-lane state for columns m = lane + 32 c; the diagonal entry of row m is v * dmul + dadd
     float e[S][4], gk[S][4], dmul[4], dadd[4];
+#pragma unroll
+    for (int s = 0; s < S; ++s) noise_lane4(p, s, b, lane, e[s]);
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
       const int m = lane + 32 * c;
       const bool ok = c < nrb && m < K;
-      const float lii = ok ? p.diagL[b * K + m] : 1.f;
-      dmul[c] = p.chol_raw ? lii : 1.f;                      // LowerCholeskyTransform chain rule
-      dadd[c] = p.chol_raw ? -p.scale : -p.scale / lii;      // - scale d(sum log L_ii)/dL_ii
+      dmul[c] = p.chol_raw ? cur.lii[c] : 1.f;                  // LowerCholeskyTransform chain rule
+      dadd[c] = p.chol_raw ? -p.scale : -p.scale / cur.lii[c];  // - scale d(sum log L_ii)/dL_ii
       float dmu = 0.f;
 #pragma unroll
       for (int s = 0; s < S; ++s) {
-        float g = 0.f, z = 0.f;
-        if (ok) {
-          const int64_t at = ((int64_t)s * p.B + b) * K + m;
-          g = -p.x[at];                                     // d log N(x; 0, I) / dx
-          for (int part = 0; part < p.n_parts; ++part) g += p.gx[(int64_t)part * Rrows * K + at];
-          g *= kf;
-          z = noise_at(p, s, b, m);
-        }
+        float g = -cur.x[s][c] + ((cur.g[s][c][0] + cur.g[s][c][1]) + (cur.g[s][c][2] + cur.g[s][c][3]));
+        if (ok)
+          for (int part = 4; part < p.n_parts; ++part)          // item tiles beyond 512 items (rare)
+            g += p.gx[(int64_t)part * Rrows * K + ((int64_t)s * p.B + b) * K + m];
+        g *= kf;
         gk[s][c] = g;
-        e[s][c] = z;
         dmu += g;
       }
       if (ok && p.d_mu) p.d_mu[b * K + m] = dmu;
     }
-    if (lane == 0) {
-      float ellsum = 0.f;
-      for (int s = 0; s < S; ++s)
-        for (int part = 0; part < p.n_parts; ++part) ellsum += p.ell[(int64_t)part * Rrows + (int64_t)s * p.B + b];
-      loss_acc += (double)(kf * (ellsum + p.aux[b]));
+    {
+      const float ev = warp_sum(cur.ev);
+      if (lane == 0) loss_acc += (double)(kf * ev);
     }
     if (p.d_chol) {
       float* out = p.d_chol + b * stride_L;
@@ -186,6 +218,7 @@ __global__ void __launch_bounds__(kStreamThreads) mirt_cholgrad_stream_kernel(co
         }
       }
     }
+    cur = nxt;
   }
   loss_acc = warp_sum(loss_acc);
   if (lane == 0) loss_sm[warp] = loss_acc;

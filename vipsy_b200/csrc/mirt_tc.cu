@@ -21,7 +21,9 @@
 
 namespace vipsy {
 
-constexpr int kTcThreads = 256;
+constexpr int kTcEpiThreads = 256, kTcProducerThreads = 128;
+constexpr int kTcMmaWarp = (kTcEpiThreads + kTcProducerThreads) / 32;      // warp 12
+constexpr int kTcThreads = kTcEpiThreads + kTcProducerThreads + 32;
 constexpr int kTcTM = 128;                 // person-sample rows per tile (UMMA M)
 constexpr int kTcTN = 128;                 // items per CTA (UMMA N of the forward product)
 constexpr int kTcYStride = kTcTN + 4;      // response tile row stride (bank-conflict-free row reads)
@@ -51,9 +53,9 @@ __host__ __device__ inline TcSmem tc_smem(int K) {
   s.offXl = o; o += s.bytesX;             // the M = 128 read of x^T runs up to 2 KB past a tile: lands in Xl / Gh
   s.offGh = o; o += s.bytesG;
   s.offGl = o; o += s.bytesG;
-  s.offY = o; o += kTcTM * kTcYStride;
+  s.offY = o; o += 2 * kTcTM * kTcYStride;       // response tile, double-buffered
   s.offLL = o; o += 2 * kTcTM * 4;
-  s.offRow = o; o += kTcTM * 8;
+  s.offRow = o; o += 2 * kTcTM * 8;
   s.total = o;
   return s;
 }
@@ -76,9 +78,27 @@ __device__ __forceinline__ void split_store8(const float (&v)[8], unsigned char*
   *reinterpret_cast<uint4*>(lo_dst) = make_uint4(l[0], l[1], l[2], l[3]);
 }
 
+// mbarrier slots of the pipeline (one completion per row tile each)
+enum { kBarXFull = 0,   // producers -> MMA/epilogue: x tile + response tile staged            (128 arrivals)
+       kBarXFree,       // MMA commit -> producers: backward MMAs done, x and G tiles reusable
+       kBarLFull,       // MMA commit -> epilogue: logits in TMEM
+       kBarGFull,       // epilogue -> MMA: G tile written, logits consumed                     (256 arrivals)
+       kBarDxFull,      // MMA commit -> epilogue: d x in TMEM
+       kBarDxFree,      // epilogue -> MMA: d x read out                                        (256 arrivals)
+       kNumBars };
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(umma::smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+// Warp roles: warps 0-7 epilogue (TMEM lane quadrant = warp & 3, column half = warp >> 2),
+// warps 8-11 producers (stage the next x / response tiles while the epilogue runs), warp 12 issues the MMAs.
 __global__ void __launch_bounds__(kTcThreads, 1) mirt_tc_lik_kernel(const MirtParams p, const int n_jt, const int G) {
   extern __shared__ __align__(128) unsigned char smem[];
-  __shared__ uint64_t bar;
+  __shared__ uint64_t bars[kNumBars];
   __shared__ uint32_t tmem_base_sm;
   const int K = p.K, J = p.J, KP = tc_kp(K);
   const TcSmem L = tc_smem(K);
@@ -88,20 +108,16 @@ __global__ void __launch_bounds__(kTcThreads, 1) mirt_tc_lik_kernel(const MirtPa
   unsigned char* Xl = smem + L.offXl;
   unsigned char* Gh = smem + L.offGh;
   unsigned char* Gl = smem + L.offGl;
-  unsigned char* ytile = smem + L.offY;
-  float* llsm = reinterpret_cast<float*>(smem + L.offLL);     // [2][128]
-  int64_t* rowsm = reinterpret_cast<int64_t*>(smem + L.offRow);
+  float* llsm_all = reinterpret_cast<float*>(smem + L.offLL); // [2][128]: column-half 1's log-lik partial, by tile parity
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int quad = warp & 3, half = warp >> 2;                // TMEM lane quadrant, column half
   const int jt = blockIdx.x % n_jt, g = blockIdx.x / n_jt;
   const int j0 = jt * kTcTN;
   const int64_t R = (int64_t)p.S * p.B;
   const int64_t ntile_m = (R + kTcTM - 1) / kTcTM;
   const int nck = KP / 8;                                      // 16-byte chunks per x row
-  const float negDl2e = -p.D * kLog2e;
 
-  // ---- one-time: a tile (rows k < K: a[k][j]; row K: b[j]; rows > K: 0), barrier, TMEM ----------
+  // ---- one-time: a tile (rows k < K: a[k][j]; row K: b[j]; rows > K: 0), barriers, TMEM ----------
   for (int e = tid; e < KP * (kTcTN / 8); e += kTcThreads) {
     const int k = e / (kTcTN / 8), c8 = e - k * (kTcTN / 8);
     float v[8];
@@ -118,257 +134,293 @@ __global__ void __launch_bounds__(kTcThreads, 1) mirt_tc_lik_kernel(const MirtPa
     const uint32_t o = umma::tile_off(k, c8 * 8, L.rsA, kCS);
     split_store8(v, Ah + o, Al + o);
   }
-  if (warp == 0) umma::tmem_alloc(&tmem_base_sm, kTmemCols);
+  if (warp == kTcMmaWarp) umma::tmem_alloc(&tmem_base_sm, kTmemCols);
   if (tid == 0) {
-    umma::mbar_init(&bar, 1);
+    umma::mbar_init(&bars[kBarXFull], kTcProducerThreads);
+    umma::mbar_init(&bars[kBarXFree], 1);
+    umma::mbar_init(&bars[kBarLFull], 1);
+    umma::mbar_init(&bars[kBarGFull], kTcEpiThreads);
+    umma::mbar_init(&bars[kBarDxFull], 1);
+    umma::mbar_init(&bars[kBarDxFree], kTcEpiThreads);
     umma::fence_mbar_init();
   }
+  umma::fence_proxy_async();
   umma::fence_before_sync();
   __syncthreads();
   umma::fence_after_sync();
   const uint32_t tmem = tmem_base_sm;
-  const uint32_t tmem_row = tmem + ((uint32_t)(quad * 32) << 16);
-  uint32_t phase = 0;
 
-  const uint32_t idesc_fwd = umma::make_idesc_f16(kTcTM, kTcTN, umma::kMajorK, umma::kMajorMN);
-  const uint32_t idesc_dx = umma::make_idesc_f16(kTcTM, KP, umma::kMajorK, umma::kMajorK);
-  const uint32_t idesc_da = umma::make_idesc_f16(128, kTcTN, umma::kMajorMN, umma::kMajorMN);
-  const uint32_t sAh = umma::smem_u32(Ah), sAl = umma::smem_u32(Al), sXh = umma::smem_u32(Xh), sXl = umma::smem_u32(Xl),
-                 sGh = umma::smem_u32(Gh), sGl = umma::smem_u32(Gl);
-  const bool y_words = ((p.ld_y & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.y) & 3) == 0);
-  bool first_tile = true;
-
-  for (int64_t tm = g; tm < ntile_m; tm += G) {
-    const int64_t r0 = tm * kTcTM;
-    // ---- y-row index of each tile row (one 64-bit modulo per row, not per cell) -----------------------
-    if (tid < kTcTM) {
-      const int64_t r = r0 + tid;
-      int64_t row = -1;
-      if (r < R) {
-        const int64_t bb = r % p.B;
-        row = p.idx ? p.idx[bb] : bb;
+  if (warp >= kTcEpiThreads / 32 && warp < kTcMmaWarp) {
+    // =========================== PRODUCERS ===========================================================
+    const int ptid = tid - kTcEpiThreads;
+    const bool y_words = ((p.ld_y & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.y) & 3) == 0);
+    int64_t n = 0;
+    for (int64_t tm = g; tm < ntile_m; tm += G, ++n) {
+      const int64_t r0 = tm * kTcTM;
+      unsigned char* ytile = smem + L.offY + (n & 1) * (kTcTM * kTcYStride);
+      int64_t* rowsm = reinterpret_cast<int64_t*>(smem + L.offRow) + (n & 1) * kTcTM;
+      // y-row index of each tile row (one 64-bit modulo per row, not per cell)
+      {
+        const int64_t r = r0 + ptid;
+        int64_t row = -1;
+        if (r < R) {
+          const int64_t bb = r % p.B;
+          row = p.idx ? p.idx[bb] : bb;
+        }
+        rowsm[ptid] = row;
       }
-      rowsm[tid] = row;
-    }
-    // ---- stage x tile as fp16 hi/lo: [x_0..x_{K-1} | 1 | 0...]; invalid rows all zero ----------
-    // four independent 32-byte loads in flight per thread before the first conversion
-    for (int e0 = tid; e0 < kTcTM * nck; e0 += 4 * kTcThreads) {
-      float v[4][8];
+      named_bar_sync(1, kTcProducerThreads);
+      // ---- response tile n -> buffer n & 1 (free: the epilogue of tile n-2 finished long ago) ----------
+      if (y_words) {
+        for (int e0 = ptid; e0 < kTcTM * (kTcTN / 4); e0 += 8 * kTcProducerThreads) {
+          uint32_t code4[8];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int e = e0 + u * kTcThreads;
-        const int pr = e / nck, c8 = e - pr * nck;
-        const int64_t r = r0 + pr;
-        if (e < kTcTM * nck && r < R) {
-          const float* src = p.x + r * K + c8 * 8;
-          if ((K & 3) == 0 && c8 * 8 + 8 <= K) {
-            const float4 u0 = *reinterpret_cast<const float4*>(src);
-            const float4 u1 = *reinterpret_cast<const float4*>(src + 4);
-            v[u][0] = u0.x; v[u][1] = u0.y; v[u][2] = u0.z; v[u][3] = u0.w;
-            v[u][4] = u1.x; v[u][5] = u1.y; v[u][6] = u1.z; v[u][7] = u1.w;
+          for (int u = 0; u < 8; ++u) {
+            const int e = e0 + u * kTcProducerThreads;
+            const int pr = e / (kTcTN / 4), w = e - pr * (kTcTN / 4);
+            const int64_t row = rowsm[pr];
+            const int j = j0 + w * 4;
+            uint32_t c4 = 0xffffffffu;
+            if (row >= 0 && j < J) {
+              const unsigned char* src = p.y + row * p.ld_y + j;
+              if (j + 4 <= J) {
+                c4 = *reinterpret_cast<const uint32_t*>(src);
+              } else {                                        // ragged tail word of the last item tile
+                c4 = 0;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) c4 |= (uint32_t)(j + i < J ? src[i] : 255u) << (8 * i);
+              }
+            }
+            code4[u] = c4;
+          }
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const int e = e0 + u * kTcProducerThreads;
+            const int pr = e / (kTcTN / 4), w = e - pr * (kTcTN / 4);
+            *reinterpret_cast<uint32_t*>(ytile + pr * kTcYStride + w * 4) = code4[u];
+          }
+        }
+      } else {
+        for (int e = ptid; e < kTcTM * kTcTN; e += kTcProducerThreads) {
+          const int pr = e / kTcTN, jj = e - pr * kTcTN;
+          const int64_t row = rowsm[pr];
+          unsigned char code = 255;
+          if (row >= 0 && j0 + jj < J) code = p.y[row * p.ld_y + j0 + jj];
+          ytile[pr * kTcYStride + jj] = code;
+        }
+      }
+      // ---- x tile n: fp16 hi/lo of [x_0..x_{K-1} | 1 | 0...]; invalid rows all zero.  The single x buffer is
+      //      free once the backward MMAs of tile n-1 have completed. -------------------------------------
+      if (n > 0) umma::mbar_wait(&bars[kBarXFree], (uint32_t)((n - 1) & 1));
+      for (int e0 = ptid; e0 < kTcTM * nck; e0 += 4 * kTcProducerThreads) {
+        float v[4][8];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int e = e0 + u * kTcProducerThreads;
+          const int pr = e / nck, c8 = e - pr * nck;
+          const int64_t r = r0 + pr;
+          if (e < kTcTM * nck && r < R) {
+            const float* src = p.x + r * K + c8 * 8;
+            if ((K & 3) == 0 && c8 * 8 + 8 <= K) {
+              const float4 u0 = *reinterpret_cast<const float4*>(src);
+              const float4 u1 = *reinterpret_cast<const float4*>(src + 4);
+              v[u][0] = u0.x; v[u][1] = u0.y; v[u][2] = u0.z; v[u][3] = u0.w;
+              v[u][4] = u1.x; v[u][5] = u1.y; v[u][6] = u1.z; v[u][7] = u1.w;
+            } else {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const int k = c8 * 8 + i;
+                v[u][i] = k < K ? src[i] : (k == K ? 1.f : 0.f);
+              }
+            }
           } else {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const int k = c8 * 8 + i;
-              v[u][i] = k < K ? src[i] : (k == K ? 1.f : 0.f);
-            }
+            for (int i = 0; i < 8; ++i) v[u][i] = 0.f;
           }
-        } else {
+        }
 #pragma unroll
-          for (int i = 0; i < 8; ++i) v[u][i] = 0.f;
+        for (int u = 0; u < 4; ++u) {
+          const int e = e0 + u * kTcProducerThreads;
+          if (e < kTcTM * nck) {
+            const int pr = e / nck, c8 = e - pr * nck;
+            const uint32_t o = umma::tile_off(pr, c8 * 8, L.rsX, kCS);
+            split_store8(v[u], Xh + o, Xl + o);
+          }
         }
       }
+      umma::fence_proxy_async();                            // generic-proxy writes -> visible to the tensor core
+      mbar_arrive(&bars[kBarXFull]);
+    }
+  } else if (warp == kTcMmaWarp) {
+    // =========================== MMA ISSUER (one thread) =============================================
+    if (lane == 0) {
+      const uint32_t idesc_fwd = umma::make_idesc_f16(kTcTM, kTcTN, umma::kMajorK, umma::kMajorMN);
+      const uint32_t idesc_dx = umma::make_idesc_f16(kTcTM, KP, umma::kMajorK, umma::kMajorK);
+      const uint32_t idesc_da = umma::make_idesc_f16(128, kTcTN, umma::kMajorMN, umma::kMajorMN);
+      const uint32_t sAh = umma::smem_u32(Ah), sAl = umma::smem_u32(Al), sXh = umma::smem_u32(Xh),
+                     sXl = umma::smem_u32(Xl), sGh = umma::smem_u32(Gh), sGl = umma::smem_u32(Gl);
+      int64_t n = 0;
+      for (int64_t tm = g; tm < ntile_m; tm += G, ++n) {
+        const uint32_t par = (uint32_t)(n & 1);
+        // forward: logits = [x|1] [a;b]  (A operand K-major from the x tile, B MN-major from the a tile)
+        umma::mbar_wait(&bars[kBarXFull], par);
+        umma::fence_after_sync();
+        uint32_t acc = 0;
+        for (int ks = 0; ks < KP / 16; ++ks) {
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int e = e0 + u * kTcThreads;
-        if (e < kTcTM * nck) {
-          const int pr = e / nck, c8 = e - pr * nck;
-          const uint32_t o = umma::tile_off(pr, c8 * 8, L.rsX, kCS);
-          split_store8(v[u], Xh + o, Xl + o);
+          for (int term = 0; term < 3; ++term) {             // hi*hi, hi*lo, lo*hi
+            const uint64_t da = umma::make_desc((term == 2 ? sXl : sXh) + ks * 2 * kCS, kCS, L.rsX);
+            const uint64_t db = umma::make_desc((term == 1 ? sAl : sAh) + ks * 2 * L.rsA, L.rsA, kCS);
+            umma::mma_f16_ss(tmem + kColLogit, da, db, idesc_fwd, acc);
+            acc = 1;
+          }
         }
+        umma::commit(&bars[kBarLFull]);
+        // backward: d x = G a^T (cols kColDx..), d a += x^T G (cols kColDa.., lives across row tiles)
+        umma::mbar_wait(&bars[kBarGFull], par);
+        if (n > 0) umma::mbar_wait(&bars[kBarDxFree], (uint32_t)((n - 1) & 1));
+        umma::fence_after_sync();
+        acc = 0;
+        for (int ks = 0; ks < kTcTN / 16; ++ks) {
+#pragma unroll
+          for (int term = 0; term < 3; ++term) {
+            const uint64_t da = umma::make_desc((term == 2 ? sGl : sGh) + ks * 2 * kCS, kCS, L.rsG);
+            const uint64_t db = umma::make_desc((term == 1 ? sAl : sAh) + ks * 2 * kCS, kCS, L.rsA);
+            umma::mma_f16_ss(tmem + kColDx, da, db, idesc_dx, acc);
+            acc = 1;
+          }
+        }
+        acc = n > 0 ? 1u : 0u;
+        for (int ks = 0; ks < kTcTM / 16; ++ks) {
+#pragma unroll
+          for (int term = 0; term < 3; ++term) {
+            const uint64_t da = umma::make_desc((term == 2 ? sXl : sXh) + ks * 2 * L.rsX, L.rsX, kCS);
+            const uint64_t db = umma::make_desc((term == 1 ? sGl : sGh) + ks * 2 * L.rsG, L.rsG, kCS);
+            umma::mma_f16_ss(tmem + kColDa, da, db, idesc_da, acc);
+            acc = 1;
+          }
+        }
+        umma::commit(&bars[kBarXFree]);
+        umma::commit(&bars[kBarDxFull]);
       }
     }
-    __syncthreads();                                        // rowsm visible
-    // ---- response tile: 32-bit loads (8 in flight per thread) when rows are word-aligned ---------------
-    if (y_words) {
-      for (int e0 = tid; e0 < kTcTM * (kTcTN / 4); e0 += 8 * kTcThreads) {
-        uint32_t code4[8];
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          const int e = e0 + u * kTcThreads;
-          const int pr = e / (kTcTN / 4), w = e - pr * (kTcTN / 4);
-          const int64_t row = rowsm[pr];
-          const int j = j0 + w * 4;
-          uint32_t c4 = 0xffffffffu;
-          if (row >= 0 && j < J) {
-            const unsigned char* src = p.y + row * p.ld_y + j;
-            if (j + 4 <= J) {
-              c4 = *reinterpret_cast<const uint32_t*>(src);
-            } else {                                        // ragged tail word of the last item tile
-              c4 = 0;
-#pragma unroll
-              for (int i = 0; i < 4; ++i) c4 |= (uint32_t)(j + i < J ? src[i] : 255u) << (8 * i);
-            }
-          }
-          code4[u] = c4;
-        }
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          const int e = e0 + u * kTcThreads;
-          const int pr = e / (kTcTN / 4), w = e - pr * (kTcTN / 4);
-          *reinterpret_cast<uint32_t*>(ytile + pr * kTcYStride + w * 4) = code4[u];
-        }
-      }
-    } else {
-      for (int e = tid; e < kTcTM * kTcTN; e += kTcThreads) {
-        const int pr = e / kTcTN, jj = e - pr * kTcTN;
-        const int64_t row = rowsm[pr];
-        unsigned char code = 255;
-        if (row >= 0 && j0 + jj < J) code = p.y[row * p.ld_y + j0 + jj];
-        ytile[pr * kTcYStride + jj] = code;
-      }
-    }
-    umma::fence_proxy_async();
-    __syncthreads();
-
-    // ---- forward: logits = [x|1] [a;b]  (A operand K-major from the x tile, B MN-major from the a tile)
-    if (tid == 0) {
+  } else {
+    // =========================== EPILOGUE (256 threads) ===============================================
+    const int quad = warp & 3, half = warp >> 2;             // TMEM lane quadrant, column half
+    const uint32_t tmem_row = tmem + ((uint32_t)(quad * 32) << 16);
+    const int pr = quad * 32 + lane;                         // this thread's tile row
+    const float negDl2e = -p.D * kLog2e;
+    int64_t n = 0;
+    for (int64_t tm = g; tm < ntile_m; tm += G, ++n) {
+      const int64_t r0 = tm * kTcTM;
+      const uint32_t par = (uint32_t)(n & 1);
+      const unsigned char* ytile = smem + L.offY + (n & 1) * (kTcTM * kTcYStride);
+      umma::mbar_wait(&bars[kBarXFull], par);                // response tile visible to this thread
+      umma::mbar_wait(&bars[kBarLFull], par);
       umma::fence_after_sync();
-      uint32_t acc = 0;
-      for (int ks = 0; ks < KP / 16; ++ks) {
-#pragma unroll
-        for (int term = 0; term < 3; ++term) {               // hi*hi, hi*lo, lo*hi
-          const uint64_t da = umma::make_desc((term == 2 ? sXl : sXh) + ks * 2 * kCS, kCS, L.rsX);
-          const uint64_t db = umma::make_desc((term == 1 ? sAl : sAh) + ks * 2 * L.rsA, L.rsA, kCS);
-          umma::mma_f16_ss(tmem + kColLogit, da, db, idesc_fwd, acc);
-          acc = 1;
-        }
-      }
-      umma::commit(&bar);
-    }
-    umma::mbar_wait(&bar, phase);
-    phase ^= 1;
-    umma::fence_after_sync();
-
-    // ---- epilogue: this thread owns row (quad*32 + lane), columns [half*64, half*64 + 64) ---------
-    const int pr = quad * 32 + lane;
-    float ll = 0.f;
+      float ll = 0.f;
 #pragma unroll 1
-    for (int cc = 0; cc < 2; ++cc) {
-      const int c0 = half * 64 + cc * 32;
-      float v[32];
-      umma::tmem_ld32(tmem_row + kColLogit + c0, v);
-      uint32_t yw[8];
+      for (int cc = 0; cc < 2; ++cc) {
+        const int c0 = half * 64 + cc * 32;
+        float v[32];
+        umma::tmem_ld32(tmem_row + kColLogit + c0, v);
+        uint32_t yw[8];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) yw[i] = *reinterpret_cast<const uint32_t*>(ytile + pr * kTcYStride + c0 + i * 4);
+        for (int i = 0; i < 8; ++i) yw[i] = *reinterpret_cast<const uint32_t*>(ytile + pr * kTcYStride + c0 + i * 4);
 #pragma unroll
-      for (int c8 = 0; c8 < 4; ++c8) {
-        float gl8[8];
+        for (int c8 = 0; c8 < 4; ++c8) {
+          float gl8[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int cidx = c8 * 8 + i;
-          const uint32_t code = (yw[cidx >> 2] >> ((cidx & 3) * 8)) & 0xffu;
-          float gl = 0.f;
-          if (code != 255u) {
-            const bool y1 = code != 0u;
-            float t = negDl2e * v[cidx];                      // -l log2e, l = D (x.a + b)
-            t = y1 ? t : -t;
-            t = fminf(t, 126.f);
-            const float e = ex2_approx(t);
-            const float sp = rcp_approx(1.f + e);             // s (y=1) | 1-s (y=0)
-            const float es = e * sp;
-            const float qc = fminf(fmaxf(sp, kEps32), kOneMinusEps32);
-            ll += kLn2 * lg2_approx(qc);
-            if (sp == qc) gl = (y1 ? p.D : -p.D) * es;
+          for (int h4 = 0; h4 < 2; ++h4) {
+            float prod = 1.f;                                // one lg2 per 4 cells: each factor >= 1.19e-7
+#pragma unroll
+            for (int i4 = 0; i4 < 4; ++i4) {
+              const int i = h4 * 4 + i4;
+              const int cidx = c8 * 8 + i;
+              const uint32_t code = (yw[cidx >> 2] >> ((cidx & 3) * 8)) & 0xffu;
+              // branch-free: every cell runs the same chain (eight chains interleave), missing cells are
+              // neutralised by selects at the end
+              const bool valid = code != 255u, y1 = code == 1u;
+              float t = negDl2e * v[cidx];                    // -l log2e, l = D (x.a + b)
+              t = y1 ? t : -t;
+              t = fminf(t, 126.f);
+              const float e = ex2_approx(t);
+              const float sp = rcp_approx(1.f + e);           // s (y=1) | 1-s (y=0)
+              const float es = e * sp;
+              const float qc = fminf(fmaxf(sp, kEps32), kOneMinusEps32);
+              prod *= valid ? qc : 1.f;
+              const float gl = (valid && sp == qc) ? (y1 ? p.D : -p.D) * es : 0.f;
+              gl8[i] = gl;
+            }
+            ll = fmaf(kLn2, lg2_approx(prod), ll);
           }
-          gl8[i] = gl;
+          const uint32_t o = umma::tile_off(pr, c0 + c8 * 8, L.rsG, kCS);
+          split_store8(gl8, Gh + o, Gl + o);
         }
-        const uint32_t o = umma::tile_off(pr, c0 + c8 * 8, L.rsG, kCS);
-        split_store8(gl8, Gh + o, Gl + o);
       }
-    }
-    llsm[half * kTcTM + pr] = ll;
-    umma::fence_before_sync();
-    umma::fence_proxy_async();
-    __syncthreads();
+      umma::fence_before_sync();
+      umma::fence_proxy_async();
+      mbar_arrive(&bars[kBarGFull]);
+      // per-row log-likelihood partial of this item tile: column half 1 hands its sum to half 0
+      float* llsm = llsm_all + (n & 1) * kTcTM;
+      if (half == 1) llsm[pr] = ll;
+      named_bar_sync(2, kTcEpiThreads);
+      if (half == 0 && r0 + pr < R) p.ell[(int64_t)jt * R + r0 + pr] = ll + llsm[pr];
 
-    // ---- backward: d x = G a^T (cols kColDx..), d a += x^T G (cols kColDa.., lives across row tiles)
-    if (tid == 0) {
+      // ---- d x read-out: 16-column groups alternate between the two column halves --------------------
+      umma::mbar_wait(&bars[kBarDxFull], par);
       umma::fence_after_sync();
-      uint32_t acc = 0;
-      for (int ks = 0; ks < kTcTN / 16; ++ks) {
+      {
+        float* dst = p.gx + ((int64_t)jt * R + r0 + pr) * K;
+        const bool rvalid = r0 + pr < R;
+        for (int c0 = half * 16; c0 < K; c0 += 32) {
+          float v[16];
+          umma::tmem_ld16(tmem_row + kColDx + c0, v);
+          if (rvalid) {
+            if ((K & 3) == 0) {
 #pragma unroll
-        for (int term = 0; term < 3; ++term) {
-          const uint64_t da = umma::make_desc((term == 2 ? sGl : sGh) + ks * 2 * kCS, kCS, L.rsG);
-          const uint64_t db = umma::make_desc((term == 1 ? sAl : sAh) + ks * 2 * kCS, kCS, L.rsA);
-          umma::mma_f16_ss(tmem + kColDx, da, db, idesc_dx, acc);
-          acc = 1;
+              for (int i = 0; i < 16; i += 4)
+                if (c0 + i < K) *reinterpret_cast<float4*>(dst + c0 + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+            } else {
+#pragma unroll
+              for (int i = 0; i < 16; ++i)
+                if (c0 + i < K) dst[c0 + i] = v[i];
+            }
+          }
         }
       }
-      acc = first_tile ? 0u : 1u;
-      for (int ks = 0; ks < kTcTM / 16; ++ks) {
-#pragma unroll
-        for (int term = 0; term < 3; ++term) {
-          const uint64_t da = umma::make_desc((term == 2 ? sXl : sXh) + ks * 2 * L.rsX, L.rsX, kCS);
-          const uint64_t db = umma::make_desc((term == 1 ? sGl : sGh) + ks * 2 * L.rsG, L.rsG, kCS);
-          umma::mma_f16_ss(tmem + kColDa, da, db, idesc_da, acc);
-          acc = 1;
-        }
-      }
-      umma::commit(&bar);
+      umma::fence_before_sync();
+      mbar_arrive(&bars[kBarDxFree]);
     }
-    first_tile = false;
-    // per-row log-likelihood partial of this item tile (both column halves)
-    if (tid < kTcTM && r0 + tid < R) p.ell[(int64_t)jt * R + r0 + tid] = llsm[tid] + llsm[kTcTM + tid];
-    umma::mbar_wait(&bar, phase);
-    phase ^= 1;
-    umma::fence_after_sync();
 
-    // ---- d x read-out: 16-column groups alternate between the two column halves --------------------
+    // ---- flush d a (rows k < K) and d b (row K) of this CTA's item tile: the last kBarDxFull wait above
+    //      covers every MMA of the CTA ------------------------------------------------------------------
     {
-      float* dst = p.gx + ((int64_t)jt * R + r0 + pr) * K;
-      const bool rvalid = r0 + pr < R;
-      for (int c0 = half * 16; c0 < K; c0 += 32) {
+      const int k = quad * 32 + lane;
+      float* part = p.item_partial + (size_t)g * ((size_t)K * J + 3 * (size_t)J);
+      for (int cc = 0; cc < 4; ++cc) {
+        const int c0 = half * 64 + cc * 16;
         float v[16];
-        umma::tmem_ld16(tmem_row + kColDx + c0, v);
-        if (rvalid) {
+        umma::tmem_ld16(tmem_row + kColDa + c0, v);
+        if (k <= K) {
+          float* dst = part + (size_t)k * J + j0 + c0;        // k == K lands on the d_b segment (offset K*J)
 #pragma unroll
           for (int i = 0; i < 16; ++i)
-            if (c0 + i < K) dst[c0 + i] = v[i];
+            if (j0 + c0 + i < J) dst[i] = v[i];
         }
-      }
-    }
-    umma::fence_before_sync();
-    __syncthreads();
-  }
-
-  // ---- flush d a (rows k < K) and d b (row K) of this CTA's item tile --------------------------------
-  umma::fence_after_sync();
-  {
-    const int k = quad * 32 + lane;
-    float* part = p.item_partial + (size_t)g * ((size_t)K * J + 3 * (size_t)J);
-    for (int cc = 0; cc < 4; ++cc) {
-      const int c0 = half * 64 + cc * 16;
-      float v[16];
-      umma::tmem_ld16(tmem_row + kColDa + c0, v);
-      if (k <= K) {
-        float* dst = part + (size_t)k * J + j0 + c0;          // k == K lands on the d_b segment (offset K*J)
-#pragma unroll
-        for (int i = 0; i < 16; ++i)
-          if (j0 + c0 + i < J) dst[i] = v[i];
       }
     }
   }
   umma::fence_before_sync();
   __syncthreads();
-  if (warp == 0) umma::tmem_dealloc(tmem, kTmemCols);
+  if (warp == kTcMmaWarp) umma::tmem_dealloc(tmem, kTmemCols);
 }
 
 // ----------------------------------------------------------------------------------------------------
 int mirt_tc_parts(int J) { return (J + kTcTN - 1) / kTcTN; }
 
 bool mirt_tc_supported(const MirtParams& p) {
-  return p.model == VIPSY_IRT_2PL && p.K >= 8 && tc_kp(p.K) <= 128;
+  return p.model == VIPSY_IRT_2PL && p.K >= 8 && tc_kp(p.K) <= 128 && tc_smem(p.K).total <= 227u * 1024u;
 }
 
 int launch_lik_tc(const MirtParams& p, int* rows_out, int* parts_out, cudaStream_t st) {

@@ -139,6 +139,21 @@ __global__ void eta_table_kernel(const uint32_t* __restrict__ qmask, int J, int 
 template <bool NORMAL>
 __global__ void fill_noise_kernel(float* __restrict__ out, int S, int64_t B, int K, uint64_t seed,
                                   uint64_t offset, int64_t person_offset) {
+  if (NORMAL && K > 1 && K <= 128) {          // the K > 1 layout of noise_coord(): one element per thread
+    const int64_t total = (int64_t)S * B * K;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (int64_t)gridDim.x * blockDim.x) {
+      const int k = (int)(i % K);
+      const int64_t b = (i / K) % B;
+      const int s = (int)(i / ((int64_t)K * B));
+      uint32_t blk;
+      int comp;
+      noise_coord(s, k, K, blk, comp);
+      const float4 z = normal4(seed, offset, (uint64_t)(person_offset + b), blk);
+      out[i] = comp == 0 ? z.x : (comp == 1 ? z.y : (comp == 2 ? z.z : z.w));
+    }
+    return;
+  }
   const int64_t per_person = (int64_t)S * K;
   const int64_t blocks_pp = (per_person + 3) / 4;
   const int64_t total = B * blocks_pp;
