@@ -21,9 +21,17 @@
 
 namespace vipsy {
 
-constexpr int kTcEpiThreads = 256, kTcProducerThreads = 128;
-constexpr int kTcMmaWarp = (kTcEpiThreads + kTcProducerThreads) / 32;      // warp 12
-constexpr int kTcThreads = kTcEpiThreads + kTcProducerThreads + 32;
+__device__ long long g_tc_dbg[3 * 8 * 4];   // development: clock64 stamps [role][tile][event] of CTA 0
+#define TC_STAMP(role, ev)                                                             \
+  do {                                                                                 \
+    if ((p.dbg & 32) && blockIdx.x == 0 && n < 8) g_tc_dbg[((role) * 8 + n) * 4 + (ev)] = clock64(); \
+  } while (0)
+
+constexpr int kTcEpiThreads = 256;         // warps 0-7: epilogue
+constexpr int kTcXThreads = 256;           // warps 8-15: x-tile producers + d x drain
+constexpr int kTcYThreads = 128;           // warps 16-19: response-tile producers
+constexpr int kTcMmaWarp = (kTcEpiThreads + kTcXThreads + kTcYThreads) / 32;      // warp 20
+constexpr int kTcThreads = kTcEpiThreads + kTcXThreads + kTcYThreads + 32;
 constexpr int kTcTM = 128;                 // person-sample rows per tile (UMMA M)
 constexpr int kTcTN = 128;                 // items per CTA (UMMA N of the forward product)
 constexpr int kTcYStride = kTcTN + 4;      // response tile row stride (bank-conflict-free row reads)
@@ -55,7 +63,7 @@ __host__ __device__ inline TcSmem tc_smem(int K) {
   s.offGl = o; o += s.bytesG;
   s.offY = o; o += 2 * kTcTM * kTcYStride;       // response tile, double-buffered
   s.offLL = o; o += 2 * kTcTM * 4;
-  s.offRow = o; o += 2 * kTcTM * 8;
+  s.offRow = o; o += kTcTM * 8;
   s.total = o;
   return s;
 }
@@ -78,13 +86,15 @@ __device__ __forceinline__ void split_store8(const float (&v)[8], unsigned char*
   *reinterpret_cast<uint4*>(lo_dst) = make_uint4(l[0], l[1], l[2], l[3]);
 }
 
-// mbarrier slots of the pipeline (one completion per row tile each)
-enum { kBarXFull = 0,   // producers -> MMA/epilogue: x tile + response tile staged            (128 arrivals)
-       kBarXFree,       // MMA commit -> producers: backward MMAs done, x and G tiles reusable
+// mbarrier slots of the pipeline (one completion per row tile each; the response ring has one pair per buffer)
+enum { kBarXFull = 0,   // x producers -> MMA: x tile staged                                    (256 arrivals)
+       kBarXFree,       // MMA commit -> x producers: backward MMAs done, x and G tiles reusable
        kBarLFull,       // MMA commit -> epilogue: logits in TMEM
        kBarGFull,       // epilogue -> MMA: G tile written, logits consumed                     (256 arrivals)
-       kBarDxFull,      // MMA commit -> epilogue: d x in TMEM
-       kBarDxFree,      // epilogue -> MMA: d x read out                                        (256 arrivals)
+       kBarDxFull,      // MMA commit -> x producers (+ epilogue at the end): d x / d a in TMEM
+       kBarDxFree,      // x producers -> MMA: d x drained to global memory                     (256 arrivals)
+       kBarYFull0, kBarYFull1,   // y producers -> epilogue: response buffer b staged           (128 arrivals)
+       kBarYFree0, kBarYFree1,   // epilogue -> y producers: response buffer b consumed         (256 arrivals)
        kNumBars };
 
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
@@ -136,12 +146,16 @@ __global__ void __launch_bounds__(kTcThreads, 1) mirt_tc_lik_kernel(const MirtPa
   }
   if (warp == kTcMmaWarp) umma::tmem_alloc(&tmem_base_sm, kTmemCols);
   if (tid == 0) {
-    umma::mbar_init(&bars[kBarXFull], kTcProducerThreads);
+    umma::mbar_init(&bars[kBarXFull], kTcXThreads);
+    umma::mbar_init(&bars[kBarYFull0], kTcYThreads);
+    umma::mbar_init(&bars[kBarYFull1], kTcYThreads);
+    umma::mbar_init(&bars[kBarYFree0], kTcEpiThreads);
+    umma::mbar_init(&bars[kBarYFree1], kTcEpiThreads);
     umma::mbar_init(&bars[kBarXFree], 1);
     umma::mbar_init(&bars[kBarLFull], 1);
     umma::mbar_init(&bars[kBarGFull], kTcEpiThreads);
     umma::mbar_init(&bars[kBarDxFull], 1);
-    umma::mbar_init(&bars[kBarDxFree], kTcEpiThreads);
+    umma::mbar_init(&bars[kBarDxFree], kTcXThreads);
     umma::fence_mbar_init();
   }
   umma::fence_proxy_async();
@@ -150,15 +164,109 @@ __global__ void __launch_bounds__(kTcThreads, 1) mirt_tc_lik_kernel(const MirtPa
   umma::fence_after_sync();
   const uint32_t tmem = tmem_base_sm;
 
-  if (warp >= kTcEpiThreads / 32 && warp < kTcMmaWarp) {
-    // =========================== PRODUCERS ===========================================================
+  if (warp >= kTcEpiThreads / 32 && warp < (kTcEpiThreads + kTcXThreads) / 32) {
+    // =========================== X PRODUCERS =========================================================
+    // Per tile n: put the global loads of x tile n in flight (registers) while tile n-1 is still being
+    // computed, wait for the single x buffer to be released by the backward MMAs of tile n-1, convert to
+    // fp16 hi/lo + store, then drain d x of tile n-1 from TMEM to global memory.
     const int ptid = tid - kTcEpiThreads;
+    const int pquad = warp & 3, phalf = (warp >> 2) & 1;     // TMEM lane quadrant / column interleave of this warp
+    const uint32_t ptmem_row = tmem + ((uint32_t)(pquad * 32) << 16);
+    constexpr int kPre = 8;                                  // 32-byte chunks per thread (16 x 128 / 256)
+    const bool xvec = (K & 3) == 0;
+
+    auto load_chunk = [&](int e, int64_t r0, float (&v)[8]) {
+      const int pr = e / nck, c8 = e - pr * nck;
+      const int64_t r = r0 + pr;
+      if (e < kTcTM * nck && r < R && !(p.dbg & 4)) {
+        const float* src = p.x + r * K + c8 * 8;
+        if (xvec && c8 * 8 + 8 <= K) {
+          const float4 u0 = *reinterpret_cast<const float4*>(src);
+          const float4 u1 = *reinterpret_cast<const float4*>(src + 4);
+          v[0] = u0.x; v[1] = u0.y; v[2] = u0.z; v[3] = u0.w;
+          v[4] = u1.x; v[5] = u1.y; v[6] = u1.z; v[7] = u1.w;
+        } else {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int k = c8 * 8 + i;
+            v[i] = k < K ? src[i] : (k == K ? 1.f : 0.f);
+          }
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = 0.f;
+      }
+    };
+    auto drain_dx = [&](int64_t r0) {                        // this thread's row of d x: TMEM -> global
+      const int dpr = pquad * 32 + lane;
+      float* dst = p.gx + ((int64_t)jt * R + r0 + dpr) * K;
+      const bool rvalid = r0 + dpr < R && !(p.dbg & 16);
+      for (int c0 = phalf * 16; c0 < K; c0 += 32) {          // the two warps of a quadrant interleave 16-column groups
+        float v[16];
+        umma::tmem_ld16(ptmem_row + kColDx + c0, v);
+        if (rvalid) {
+          if (xvec) {
+#pragma unroll
+            for (int i = 0; i < 16; i += 4)
+              if (c0 + i < K) *reinterpret_cast<float4*>(dst + c0 + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+          } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+              if (c0 + i < K) dst[c0 + i] = v[i];
+          }
+        }
+      }
+      umma::fence_before_sync();
+      mbar_arrive(&bars[kBarDxFree]);
+    };
+
+    int64_t n = 0, r0_prev = 0;
+    for (int64_t tm = g; tm < ntile_m; tm += G, ++n) {
+      const int64_t r0 = tm * kTcTM;
+      if (ptid == 0) TC_STAMP(0, 0);
+      float xv[kPre][8];
+#pragma unroll
+      for (int u = 0; u < kPre; ++u) load_chunk(ptid + u * kTcXThreads, r0, xv[u]);
+      if (ptid == 0) TC_STAMP(0, 1);
+      // ---- the single x buffer is free once the backward MMAs of tile n-1 have completed ---------------
+      if (n > 0) umma::mbar_wait(&bars[kBarXFree], (uint32_t)((n - 1) & 1));
+      if (ptid == 0) TC_STAMP(0, 2);
+#pragma unroll
+      for (int u = 0; u < kPre; ++u) {
+        const int e = ptid + u * kTcXThreads;
+        if (e < kTcTM * nck) {
+          const int pr = e / nck, c8 = e - pr * nck;
+          const uint32_t o = umma::tile_off(pr, c8 * 8, L.rsX, kCS);
+          split_store8(xv[u], Xh + o, Xl + o);
+        }
+      }
+      umma::fence_proxy_async();                            // generic-proxy writes -> visible to the tensor core
+      mbar_arrive(&bars[kBarXFull]);
+      if (ptid == 0) TC_STAMP(0, 3);
+      // ---- d x of tile n-1 (kBarXFree and kBarDxFull complete together) --------------------------------
+      if (n > 0) {
+        umma::mbar_wait(&bars[kBarDxFull], (uint32_t)((n - 1) & 1));
+        umma::fence_after_sync();
+        drain_dx(r0_prev);
+      }
+      r0_prev = r0;
+    }
+    if (n > 0) {
+      umma::mbar_wait(&bars[kBarDxFull], (uint32_t)((n - 1) & 1));
+      umma::fence_after_sync();
+      drain_dx(r0_prev);
+    }
+  } else if (warp >= (kTcEpiThreads + kTcXThreads) / 32 && warp < kTcMmaWarp) {
+    // =========================== Y PRODUCERS =========================================================
+    // Response tile n -> ring buffer n & 1, as far ahead of the epilogue as the two buffers allow.
+    const int ptid = tid - kTcEpiThreads - kTcXThreads;
     const bool y_words = ((p.ld_y & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.y) & 3) == 0);
+    int64_t* rowsm = reinterpret_cast<int64_t*>(smem + L.offRow);
     int64_t n = 0;
     for (int64_t tm = g; tm < ntile_m; tm += G, ++n) {
       const int64_t r0 = tm * kTcTM;
-      unsigned char* ytile = smem + L.offY + (n & 1) * (kTcTM * kTcYStride);
-      int64_t* rowsm = reinterpret_cast<int64_t*>(smem + L.offRow) + (n & 1) * kTcTM;
+      const int buf = (int)(n & 1);
+      unsigned char* ytile = smem + L.offY + buf * (kTcTM * kTcYStride);
       // y-row index of each tile row (one 64-bit modulo per row, not per cell)
       {
         const int64_t r = r0 + ptid;
@@ -167,16 +275,18 @@ __global__ void __launch_bounds__(kTcThreads, 1) mirt_tc_lik_kernel(const MirtPa
           const int64_t bb = r % p.B;
           row = p.idx ? p.idx[bb] : bb;
         }
+        named_bar_sync(1, kTcYThreads);                      // previous tile's readers of rowsm are done
         rowsm[ptid] = row;
       }
-      named_bar_sync(1, kTcProducerThreads);
-      // ---- response tile n -> buffer n & 1 (free: the epilogue of tile n-2 finished long ago) ----------
+      named_bar_sync(1, kTcYThreads);
       if (y_words) {
-        for (int e0 = ptid; e0 < kTcTM * (kTcTN / 4); e0 += 8 * kTcProducerThreads) {
-          uint32_t code4[8];
+        // buffer `buf` was last read by the epilogue of tile n-2 (waited for after the first loads are in flight)
+#pragma unroll 1
+        for (int h = 0; h < 2; ++h) {
+          uint32_t code4[16];                                // 16 words in flight per thread and round
 #pragma unroll
-          for (int u = 0; u < 8; ++u) {
-            const int e = e0 + u * kTcProducerThreads;
+          for (int u = 0; u < 16; ++u) {
+            const int e = ptid + (h * 16 + u) * kTcYThreads;
             const int pr = e / (kTcTN / 4), w = e - pr * (kTcTN / 4);
             const int64_t row = rowsm[pr];
             const int j = j0 + w * 4;
@@ -193,15 +303,17 @@ __global__ void __launch_bounds__(kTcThreads, 1) mirt_tc_lik_kernel(const MirtPa
             }
             code4[u] = c4;
           }
+          if (h == 0 && n >= 2) umma::mbar_wait(&bars[kBarYFree0 + buf], (uint32_t)(((n >> 1) - 1) & 1));
 #pragma unroll
-          for (int u = 0; u < 8; ++u) {
-            const int e = e0 + u * kTcProducerThreads;
+          for (int u = 0; u < 16; ++u) {
+            const int e = ptid + (h * 16 + u) * kTcYThreads;
             const int pr = e / (kTcTN / 4), w = e - pr * (kTcTN / 4);
             *reinterpret_cast<uint32_t*>(ytile + pr * kTcYStride + w * 4) = code4[u];
           }
         }
       } else {
-        for (int e = ptid; e < kTcTM * kTcTN; e += kTcProducerThreads) {
+        if (n >= 2) umma::mbar_wait(&bars[kBarYFree0 + buf], (uint32_t)(((n >> 1) - 1) & 1));
+        for (int e = ptid; e < kTcTM * kTcTN; e += kTcYThreads) {
           const int pr = e / kTcTN, jj = e - pr * kTcTN;
           const int64_t row = rowsm[pr];
           unsigned char code = 255;
@@ -209,47 +321,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) mirt_tc_lik_kernel(const MirtPa
           ytile[pr * kTcYStride + jj] = code;
         }
       }
-      // ---- x tile n: fp16 hi/lo of [x_0..x_{K-1} | 1 | 0...]; invalid rows all zero.  The single x buffer is
-      //      free once the backward MMAs of tile n-1 have completed. -------------------------------------
-      if (n > 0) umma::mbar_wait(&bars[kBarXFree], (uint32_t)((n - 1) & 1));
-      for (int e0 = ptid; e0 < kTcTM * nck; e0 += 4 * kTcProducerThreads) {
-        float v[4][8];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int e = e0 + u * kTcProducerThreads;
-          const int pr = e / nck, c8 = e - pr * nck;
-          const int64_t r = r0 + pr;
-          if (e < kTcTM * nck && r < R) {
-            const float* src = p.x + r * K + c8 * 8;
-            if ((K & 3) == 0 && c8 * 8 + 8 <= K) {
-              const float4 u0 = *reinterpret_cast<const float4*>(src);
-              const float4 u1 = *reinterpret_cast<const float4*>(src + 4);
-              v[u][0] = u0.x; v[u][1] = u0.y; v[u][2] = u0.z; v[u][3] = u0.w;
-              v[u][4] = u1.x; v[u][5] = u1.y; v[u][6] = u1.z; v[u][7] = u1.w;
-            } else {
-#pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                const int k = c8 * 8 + i;
-                v[u][i] = k < K ? src[i] : (k == K ? 1.f : 0.f);
-              }
-            }
-          } else {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) v[u][i] = 0.f;
-          }
-        }
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int e = e0 + u * kTcProducerThreads;
-          if (e < kTcTM * nck) {
-            const int pr = e / nck, c8 = e - pr * nck;
-            const uint32_t o = umma::tile_off(pr, c8 * 8, L.rsX, kCS);
-            split_store8(v[u], Xh + o, Xl + o);
-          }
-        }
-      }
-      umma::fence_proxy_async();                            // generic-proxy writes -> visible to the tensor core
-      mbar_arrive(&bars[kBarXFull]);
+      mbar_arrive(&bars[kBarYFull0 + buf]);
     }
   } else if (warp == kTcMmaWarp) {
     // =========================== MMA ISSUER (one thread) =============================================
@@ -265,6 +337,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) mirt_tc_lik_kernel(const MirtPa
         // forward: logits = [x|1] [a;b]  (A operand K-major from the x tile, B MN-major from the a tile)
         umma::mbar_wait(&bars[kBarXFull], par);
         umma::fence_after_sync();
+        TC_STAMP(1, 0);
         uint32_t acc = 0;
         for (int ks = 0; ks < KP / 16; ++ks) {
 #pragma unroll
@@ -276,11 +349,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) mirt_tc_lik_kernel(const MirtPa
           }
         }
         umma::commit(&bars[kBarLFull]);
+        TC_STAMP(1, 1);
         // backward: d x = G a^T (cols kColDx..), d a += x^T G (cols kColDa.., lives across row tiles)
         umma::mbar_wait(&bars[kBarGFull], par);
         if (n > 0) umma::mbar_wait(&bars[kBarDxFree], (uint32_t)((n - 1) & 1));
         umma::fence_after_sync();
+        TC_STAMP(1, 2);
         acc = 0;
+        if (!(p.dbg & 8))
         for (int ks = 0; ks < kTcTN / 16; ++ks) {
 #pragma unroll
           for (int term = 0; term < 3; ++term) {
@@ -291,6 +367,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) mirt_tc_lik_kernel(const MirtPa
           }
         }
         acc = n > 0 ? 1u : 0u;
+        if (!(p.dbg & 8))
         for (int ks = 0; ks < kTcTM / 16; ++ks) {
 #pragma unroll
           for (int term = 0; term < 3; ++term) {
@@ -302,6 +379,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) mirt_tc_lik_kernel(const MirtPa
         }
         umma::commit(&bars[kBarXFree]);
         umma::commit(&bars[kBarDxFull]);
+        TC_STAMP(1, 3);
       }
     }
   } else {
@@ -315,20 +393,21 @@ __global__ void __launch_bounds__(kTcThreads, 1) mirt_tc_lik_kernel(const MirtPa
       const int64_t r0 = tm * kTcTM;
       const uint32_t par = (uint32_t)(n & 1);
       const unsigned char* ytile = smem + L.offY + (n & 1) * (kTcTM * kTcYStride);
-      umma::mbar_wait(&bars[kBarXFull], par);                // response tile visible to this thread
+      umma::mbar_wait(&bars[kBarYFull0 + (n & 1)], (uint32_t)((n >> 1) & 1));   // response tile n staged
       umma::mbar_wait(&bars[kBarLFull], par);
       umma::fence_after_sync();
+      if (tid == 0) TC_STAMP(2, 0);
       float ll = 0.f;
 #pragma unroll 1
-      for (int cc = 0; cc < 2; ++cc) {
-        const int c0 = half * 64 + cc * 32;
-        float v[32];
-        umma::tmem_ld32(tmem_row + kColLogit + c0, v);
-        uint32_t yw[8];
+      for (int cc = 0; cc < 4; ++cc) {
+        const int c0 = half * 64 + cc * 16;
+        float v[16];
+        umma::tmem_ld16(tmem_row + kColLogit + c0, v);
+        uint32_t yw[4];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) yw[i] = *reinterpret_cast<const uint32_t*>(ytile + pr * kTcYStride + c0 + i * 4);
+        for (int i = 0; i < 4; ++i) yw[i] = *reinterpret_cast<const uint32_t*>(ytile + pr * kTcYStride + c0 + i * 4);
 #pragma unroll
-        for (int c8 = 0; c8 < 4; ++c8) {
+        for (int c8 = 0; c8 < 2; ++c8) {
           float gl8[8];
 #pragma unroll
           for (int h4 = 0; h4 < 2; ++h4) {
@@ -338,7 +417,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) mirt_tc_lik_kernel(const MirtPa
               const int i = h4 * 4 + i4;
               const int cidx = c8 * 8 + i;
               const uint32_t code = (yw[cidx >> 2] >> ((cidx & 3) * 8)) & 0xffu;
-              // branch-free: every cell runs the same chain (eight chains interleave), missing cells are
+              // branch-free: every cell runs the same chain (the chains interleave), missing cells are
               // neutralised by selects at the end
               const bool valid = code != 255u, y1 = code == 1u;
               float t = negDl2e * v[cidx];                    // -l log2e, l = D (x.a + b)
@@ -361,37 +440,18 @@ __global__ void __launch_bounds__(kTcThreads, 1) mirt_tc_lik_kernel(const MirtPa
       umma::fence_before_sync();
       umma::fence_proxy_async();
       mbar_arrive(&bars[kBarGFull]);
+      mbar_arrive(&bars[kBarYFree0 + (n & 1)]);
+      if (tid == 0) TC_STAMP(2, 1);
       // per-row log-likelihood partial of this item tile: column half 1 hands its sum to half 0
       float* llsm = llsm_all + (n & 1) * kTcTM;
       if (half == 1) llsm[pr] = ll;
       named_bar_sync(2, kTcEpiThreads);
       if (half == 0 && r0 + pr < R) p.ell[(int64_t)jt * R + r0 + pr] = ll + llsm[pr];
 
-      // ---- d x read-out: 16-column groups alternate between the two column halves --------------------
-      umma::mbar_wait(&bars[kBarDxFull], par);
-      umma::fence_after_sync();
-      {
-        float* dst = p.gx + ((int64_t)jt * R + r0 + pr) * K;
-        const bool rvalid = r0 + pr < R;
-        for (int c0 = half * 16; c0 < K; c0 += 32) {
-          float v[16];
-          umma::tmem_ld16(tmem_row + kColDx + c0, v);
-          if (rvalid) {
-            if ((K & 3) == 0) {
-#pragma unroll
-              for (int i = 0; i < 16; i += 4)
-                if (c0 + i < K) *reinterpret_cast<float4*>(dst + c0 + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
-            } else {
-#pragma unroll
-              for (int i = 0; i < 16; ++i)
-                if (c0 + i < K) dst[c0 + i] = v[i];
-            }
-          }
-        }
-      }
-      umma::fence_before_sync();
-      mbar_arrive(&bars[kBarDxFree]);
     }
+    // every MMA of the CTA must have completed before d a is read
+    if (n > 0) umma::mbar_wait(&bars[kBarDxFull], (uint32_t)((n - 1) & 1));
+    umma::fence_after_sync();
 
     // ---- flush d a (rows k < K) and d b (row K) of this CTA's item tile: the last kBarDxFull wait above
     //      covers every MMA of the CTA ------------------------------------------------------------------
@@ -420,7 +480,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) mirt_tc_lik_kernel(const MirtPa
 int mirt_tc_parts(int J) { return (J + kTcTN - 1) / kTcTN; }
 
 bool mirt_tc_supported(const MirtParams& p) {
-  return p.model == VIPSY_IRT_2PL && p.K >= 8 && tc_kp(p.K) <= 128 && tc_smem(p.K).total <= 227u * 1024u;
+  return p.model == VIPSY_IRT_2PL && p.K >= 8 && tc_kp(p.K) <= 128 && tc_smem(p.K).total + 1024u <= 227u * 1024u;   // + static barriers
 }
 
 int launch_lik_tc(const MirtParams& p, int* rows_out, int* parts_out, cudaStream_t st) {
@@ -434,6 +494,20 @@ int launch_lik_tc(const MirtParams& p, int* rows_out, int* parts_out, cudaStream
   VIPSY_CUDA_CHECK(cudaFuncSetAttribute(mirt_tc_lik_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
   mirt_tc_lik_kernel<<<(int)(G * n_jt), kTcThreads, L.total, st>>>(p, n_jt, (int)G);
   VIPSY_CUDA_CHECK(cudaGetLastError());
+  if (p.dbg & 32) {
+    long long h[3 * 8 * 4];
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(h, g_tc_dbg, sizeof(h));
+    const long long t0 = h[0];
+    const char* names[3] = {"producer: start | y staged | x free | x staged", "mma: x full | fwd issued | G full | bwd issued",
+                            "epilogue: logits | G done | dx full | dx stored"};
+    for (int r = 0; r < 3; ++r) {
+      fprintf(stderr, "%s\n", names[r]);
+      for (int n = 0; n < 6; ++n)
+        fprintf(stderr, "  tile %d: %8lld %8lld %8lld %8lld\n", n, h[(r * 8 + n) * 4] - t0, h[(r * 8 + n) * 4 + 1] - t0,
+                h[(r * 8 + n) * 4 + 2] - t0, h[(r * 8 + n) * 4 + 3] - t0);
+    }
+  }
   *rows_out = (int)G;
   *parts_out = n_jt;
   return VIPSY_OK;
