@@ -62,3 +62,21 @@ def test_streamed_guide_kernels(ops, B, K, S):
     cs = make(B=B, J=40, K=K, S=S, model="irt_2pl", seed=B + K)
     run(ops, cs, layout="packed", raw=True, scale=2.0)
     run(ops, cs, layout="dense", raw=False, scale=0.5)
+
+
+@pytest.mark.parametrize("model", ["irt_3pl", "irt_4pl"])
+@pytest.mark.parametrize("B,J,K,S", [(300, 140, 10, 2), (129, 257, 20, 1), (64, 500, 100, 1)])
+def test_tc_3pl_4pl(ops, model, B, J, K, S):
+    """10-dim 3PL / 4PL are the reference's own MIRT settings (test.py:363-416); d_c, d_d come from the
+    warp column-sum butterfly of the tensor-core epilogue."""
+    cs = make(B=B, J=J, K=K, S=S, model=model, seed=B + J + K)
+    run(ops, cs, layout="packed", raw=True, scale=1.5, D=1.702)
+    dev = "cuda"
+    kw = dict(chol=packed_of(cs["raw"]).to(dev), eps=cs["eps"].to(dev), a=cs["a"].to(dev), b=cs["b"].to(dev),
+              c=cs["c"].to(dev), d=cs["d"].to(dev) if model == "irt_4pl" else None, model=model, chol_packed=True,
+              chol_raw=True, a_free=cs["free"].to(dev), D=1.702)
+    codes = codes_from_float(cs["y"]).to(dev)
+    tc = ops.irt_elbo_grad(codes, cs["mu"].to(dev), **kw)
+    simt = ops.irt_elbo_grad(codes, cs["mu"].to(dev), tensor_cores=False, **kw)
+    for k in ("loss", "d_mu", "d_chol", "d_a", "d_b", "d_c") + (("d_d",) if model == "irt_4pl" else ()):
+        assert_close(tc[k], simt[k], 1e-5, 1e-5, k)

@@ -43,7 +43,7 @@ __host__ __device__ inline int tc_kp(int K) { return ((K + 1 + 15) / 16) * 16; }
 
 struct TcSmem {
   uint32_t rsA, rsX, rsG, bytesA, bytesX, bytesG;
-  uint32_t offAh, offAl, offXh, offXl, offGh, offGl, offY, offLL, offRow, total;
+  uint32_t offAh, offAl, offXh, offXl, offGh, offGl, offY, offLL, offRow, offItc, offCs, total;
 };
 __host__ __device__ inline TcSmem tc_smem(int K) {
   const int KP = tc_kp(K);
@@ -64,6 +64,8 @@ __host__ __device__ inline TcSmem tc_smem(int K) {
   s.offY = o; o += 2 * kTcTM * kTcYStride;       // response tile, double-buffered
   s.offLL = o; o += 2 * kTcTM * 4;
   s.offRow = o; o += kTcTM * 8;
+  s.offItc = o; o += 3 * kTcTN * 4;              // c | d - c | 1 - d per item (3PL / 4PL)
+  s.offCs = o; o += 4 * 2 * kTcTN * 4;           // [quadrant][d_c | d_d][item] column sums at the end
   s.total = o;
   return s;
 }
@@ -104,8 +106,27 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
+// Sum of v[c] over the 32 lanes of the warp for each of 16 columns; on return every lane l holds the
+// total of column l & 15.  Fixed butterfly order -> deterministic.
+__device__ __forceinline__ float colsum16(float (&v)[16], int lane) {
+#pragma unroll
+  for (int j = 0; j < 16; ++j) v[j] += __shfl_xor_sync(0xffffffffu, v[j], 16);
+#pragma unroll
+  for (int off = 8; off >= 1; off >>= 1) {
+    const bool up = lane & off;
+#pragma unroll
+    for (int j = 0; j < off; ++j) {
+      const float keep = up ? v[j + off] : v[j];
+      const float send = up ? v[j] : v[j + off];
+      v[j] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  }
+  return v[0];
+}
+
 // Warp roles: warps 0-7 epilogue (TMEM lane quadrant = warp & 3, column half = warp >> 2),
 // warps 8-11 producers (stage the next x / response tiles while the epilogue runs), warp 12 issues the MMAs.
+template <int MODEL>
 __global__ void __launch_bounds__(kTcThreads, 1) mirt_tc_lik_kernel(const MirtParams p, const int n_jt, const int G) {
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ uint64_t bars[kNumBars];
@@ -143,6 +164,16 @@ __global__ void __launch_bounds__(kTcThreads, 1) mirt_tc_lik_kernel(const MirtPa
     }
     const uint32_t o = umma::tile_off(k, c8 * 8, L.rsA, kCS);
     split_store8(v, Ah + o, Al + o);
+  }
+  float* itc = reinterpret_cast<float*>(smem + L.offItc);
+  if (MODEL >= VIPSY_IRT_3PL && tid < kTcTN) {
+    const int j = j0 + tid;
+    const bool ok = j < J;
+    const float cj = ok ? p.c[j] : 0.f;
+    const float dj = (ok && MODEL == VIPSY_IRT_4PL) ? p.d[j] : 1.f;
+    itc[tid] = cj;
+    itc[kTcTN + tid] = dj - cj;
+    itc[2 * kTcTN + tid] = 1.f - dj;
   }
   if (warp == kTcMmaWarp) umma::tmem_alloc(&tmem_base_sm, kTmemCols);
   if (tid == 0) {
@@ -388,6 +419,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) mirt_tc_lik_kernel(const MirtPa
     const uint32_t tmem_row = tmem + ((uint32_t)(quad * 32) << 16);
     const int pr = quad * 32 + lane;                         // this thread's tile row
     const float negDl2e = -p.D * kLog2e;
+    float cs_acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};   // lane (l & 15): column l & 15 of chunk cc: d_c | d_d
     int64_t n = 0;
     for (int64_t tm = g; tm < ntile_m; tm += G, ++n) {
       const int64_t r0 = tm * kTcTM;
@@ -406,6 +438,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) mirt_tc_lik_kernel(const MirtPa
         uint32_t yw[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) yw[i] = *reinterpret_cast<const uint32_t*>(ytile + pr * kTcYStride + c0 + i * 4);
+        float csc[16], csd[16];                              // 3PL / 4PL: this row's d lb/dc, d lb/dd per column
 #pragma unroll
         for (int c8 = 0; c8 < 2; ++c8) {
           float gl8[8];
@@ -426,15 +459,36 @@ __global__ void __launch_bounds__(kTcThreads, 1) mirt_tc_lik_kernel(const MirtPa
               const float e = ex2_approx(t);
               const float sp = rcp_approx(1.f + e);           // s (y=1) | 1-s (y=0)
               const float es = e * sp;
-              const float qc = fminf(fmaxf(sp, kEps32), kOneMinusEps32);
-              prod *= valid ? qc : 1.f;
-              const float gl = (valid && sp == qc) ? (y1 ? p.D : -p.D) * es : 0.f;
+              float gl;
+              if (MODEL >= VIPSY_IRT_3PL) {                   // q = c + (d-c) s  |  (1-d) + (d-c)(1-s)   (vi.py:44-66)
+                const int jl = c0 + cidx;
+                const float dmc = itc[kTcTN + jl];
+                const float base = y1 ? itc[jl] : itc[2 * kTcTN + jl];
+                const float q = fmaf(dmc, sp, base);
+                const float qc = fminf(fmaxf(q, kEps32), kOneMinusEps32);
+                prod *= valid ? qc : 1.f;
+                const bool live = valid && q == qc;           // clamp fired: zero gradient
+                const float r = rcp_approx(qc);
+                const float us = r * sp, uc = r * es;
+                gl = live ? (y1 ? p.D : -p.D) * dmc * us * es : 0.f;
+                csc[cidx] = live ? (y1 ? uc : -us) : 0.f;
+                csd[cidx] = live ? (y1 ? us : -uc) : 0.f;
+              } else {
+                const float qc = fminf(fmaxf(sp, kEps32), kOneMinusEps32);
+                prod *= valid ? qc : 1.f;
+                gl = (valid && sp == qc) ? (y1 ? p.D : -p.D) * es : 0.f;
+              }
               gl8[i] = gl;
             }
             ll = fmaf(kLn2, lg2_approx(prod), ll);
           }
           const uint32_t o = umma::tile_off(pr, c0 + c8 * 8, L.rsG, kCS);
           split_store8(gl8, Gh + o, Gl + o);
+        }
+        if (MODEL >= VIPSY_IRT_3PL) {                         // column sums over the warp's 32 rows (fixed order)
+          const float tc = colsum16(csc, lane);
+          cs_acc[cc] += tc;
+          if (MODEL == VIPSY_IRT_4PL) cs_acc[4 + cc] += colsum16(csd, lane);
         }
       }
       umma::fence_before_sync();
@@ -469,6 +523,26 @@ __global__ void __launch_bounds__(kTcThreads, 1) mirt_tc_lik_kernel(const MirtPa
             if (j0 + c0 + i < J) dst[i] = v[i];
         }
       }
+      if (MODEL >= VIPSY_IRT_3PL) {                           // d_c, d_d: combine the four row quadrants in order
+        float* cs = reinterpret_cast<float*>(smem + L.offCs);
+        if (lane < 16) {
+#pragma unroll
+          for (int cc = 0; cc < 4; ++cc) {
+            cs[(quad * 2 + 0) * kTcTN + half * 64 + cc * 16 + lane] = cs_acc[cc];
+            cs[(quad * 2 + 1) * kTcTN + half * 64 + cc * 16 + lane] = cs_acc[4 + cc];
+          }
+        }
+        named_bar_sync(2, kTcEpiThreads);
+        if (tid < 2 * kTcTN) {
+          const int which = tid / kTcTN, jl = tid - which * kTcTN;
+          if (j0 + jl < J && (which == 0 || MODEL == VIPSY_IRT_4PL)) {
+            float t = 0.f;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) t += cs[(q * 2 + which) * kTcTN + jl];
+            part[(size_t)K * J + (size_t)(1 + which) * J + j0 + jl] = t;
+          }
+        }
+      }
     }
   }
   umma::fence_before_sync();
@@ -480,7 +554,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) mirt_tc_lik_kernel(const MirtPa
 int mirt_tc_parts(int J) { return (J + kTcTN - 1) / kTcTN; }
 
 bool mirt_tc_supported(const MirtParams& p) {
-  return p.model == VIPSY_IRT_2PL && p.K >= 8 && tc_kp(p.K) <= 128 && tc_smem(p.K).total + 1024u <= 227u * 1024u;   // + static barriers
+  return p.model >= VIPSY_IRT_2PL && p.model <= VIPSY_IRT_4PL && p.K >= 8 && tc_kp(p.K) <= 128 && tc_smem(p.K).total + 1024u <= 227u * 1024u;   // + static barriers
 }
 
 int launch_lik_tc(const MirtParams& p, int* rows_out, int* parts_out, cudaStream_t st) {
@@ -491,8 +565,10 @@ int launch_lik_tc(const MirtParams& p, int* rows_out, int* parts_out, cudaStream
   if (G > ntile_m) G = ntile_m;
   const TcSmem L = tc_smem(p.K);
   VIPSY_REQUIRE(L.total <= 227 * 1024, VIPSY_ERR_UNSUPPORTED, "mirt_tc: shared memory %u B exceeds 227 KB", L.total);
-  VIPSY_CUDA_CHECK(cudaFuncSetAttribute(mirt_tc_lik_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
-  mirt_tc_lik_kernel<<<(int)(G * n_jt), kTcThreads, L.total, st>>>(p, n_jt, (int)G);
+  auto kern = p.model == VIPSY_IRT_2PL ? mirt_tc_lik_kernel<VIPSY_IRT_2PL>
+              : (p.model == VIPSY_IRT_3PL ? mirt_tc_lik_kernel<VIPSY_IRT_3PL> : mirt_tc_lik_kernel<VIPSY_IRT_4PL>);
+  VIPSY_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
+  kern<<<(int)(G * n_jt), kTcThreads, L.total, st>>>(p, n_jt, (int)G);
   VIPSY_CUDA_CHECK(cudaGetLastError());
   if (p.dbg & 32) {
     long long h[3 * 8 * 4];
