@@ -147,11 +147,12 @@ __device__ __forceinline__ float4 normal4(uint64_t seed, uint64_t offset, uint64
 }
 
 // Where element (particle s, dimension k) of a person's N(0,1) draw lives in the Philox stream.
-// K == 1 (and K > 128): flattened n = s*K + k, four consecutive n per block.  1 < K <= 128: block
-// s*32 + (k mod 32), component k / 32 -- lane l of a warp that owns dimensions l, l+32, l+64, l+96
-// gets all four of its values from one Philox call.
+// K <= 32 (and K > 128): flattened n = s*K + k, four consecutive n per block (a thread that owns one
+// (person, particle) draws its K values from K/4 calls).  32 < K <= 128: block s*32 + (k mod 32),
+// component k / 32 -- lane l of a warp that owns dimensions l, l+32, l+64, l+96 gets all four of its
+// values from one Philox call.
 __device__ __forceinline__ void noise_coord(int s, int k, int K, uint32_t& block, int& comp) {
-  if (K > 1 && K <= 128) {
+  if (K > 32 && K <= 128) {
     block = (uint32_t)s * 32u + (uint32_t)(k & 31);
     comp = k >> 5;
   } else {

@@ -534,8 +534,12 @@ int mirt_launch(const VipsyIrtArgs* a, cudaStream_t st) {
   const bool shared_cov = a->cov_mode == VIPSY_COV_SHARED;
 
   const bool stream = mirt_stream_supported(p);
+  const bool small = !stream && mirt_small_supported(p);
   // (1) sample
-  if (stream) {
+  if (small) {
+    int rc = launch_sample_small(p, kMirtMaxGrid, st);
+    if (rc != VIPSY_OK) return rc;
+  } else if (stream) {
     int rc = launch_sample_stream(p, kMirtMaxGrid, st);
     if (rc != VIPSY_OK) return rc;
   } else {
@@ -577,7 +581,10 @@ int mirt_launch(const VipsyIrtArgs* a, cudaStream_t st) {
   }
   // (3) guide gradients + loss partials
   int grid3;
-  if (stream) {
+  if (small) {
+    int rc = launch_cholgrad_small(p, kMirtMaxGrid, &grid3, st);
+    if (rc != VIPSY_OK) return rc;
+  } else if (stream) {
     int rc = launch_cholgrad_stream(p, kMirtMaxGrid, &grid3, st);
     if (rc != VIPSY_OK) return rc;
   } else {

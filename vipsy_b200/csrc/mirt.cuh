@@ -70,4 +70,9 @@ bool mirt_stream_supported(const MirtParams& p);
 int launch_sample_stream(const MirtParams& p, int max_grid, cudaStream_t st);
 int launch_cholgrad_stream(const MirtParams& p, int max_grid, int* grid_out, cudaStream_t st);
 
+// thread-per-(person, particle) / thread-per-element kernels for K <= 32, any S (mirt_small.cu)
+bool mirt_small_supported(const MirtParams& p);
+int launch_sample_small(const MirtParams& p, int max_grid, cudaStream_t st);
+int launch_cholgrad_small(const MirtParams& p, int max_grid, int* grid_out, cudaStream_t st);
+
 }  // namespace vipsy

@@ -231,7 +231,7 @@ __global__ void __launch_bounds__(kStreamThreads) mirt_cholgrad_stream_kernel(co
 }
 
 bool mirt_stream_supported(const MirtParams& p) {
-  return p.cov_mode == VIPSY_COV_PERSON && p.S <= 2 && p.K <= 128 && p.K >= 16;
+  return p.cov_mode == VIPSY_COV_PERSON && p.S <= 2 && p.K <= 128 && p.K > 32;   // noise_lane4 needs the K > 32 layout
 }
 
 static int stream_grid(const MirtParams& p, int max_grid) {

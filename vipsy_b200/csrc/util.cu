@@ -139,7 +139,7 @@ __global__ void eta_table_kernel(const uint32_t* __restrict__ qmask, int J, int 
 template <bool NORMAL>
 __global__ void fill_noise_kernel(float* __restrict__ out, int S, int64_t B, int K, uint64_t seed,
                                   uint64_t offset, int64_t person_offset) {
-  if (NORMAL && K > 1 && K <= 128) {          // the K > 1 layout of noise_coord(): one element per thread
+  if (NORMAL && K > 32 && K <= 128) {         // the 32 < K <= 128 layout of noise_coord(): one element per thread
     const int64_t total = (int64_t)S * B * K;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
          i += (int64_t)gridDim.x * blockDim.x) {
