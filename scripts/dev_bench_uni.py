@@ -19,7 +19,7 @@ def timeit(fn, warm=3, it=10):
     return e0.elapsed_time(e1) / it
 
 
-def case(N, J, S, model, missing=0.0, strict=False, inject=False):
+def case(N, J, S, model, missing=0.0, strict=False, inject=False, sparse=False):
     g = torch.Generator(device="cuda").manual_seed(1)
     y = (torch.rand(N, J, device="cuda", generator=g) < 0.6).to(torch.uint8)
     if missing:
@@ -36,12 +36,12 @@ def case(N, J, S, model, missing=0.0, strict=False, inject=False):
     def run():
         off[0] += 1
         return ops.irt_elbo_grad(y, mu, sigma=sg, eps=eps, n_particles=S, a=a, b=b, c=c, d=d, model=model,
-                                 seed=1, offset=off[0], strict=strict)
+                                 seed=1, offset=off[0], strict=strict, sparse=sparse)
     with ClockSampler() as cs:
         ms = timeit(run, it=30)
     ev = N * J * S
     ck = cs.summary()
-    print(f"N={N} J={J} S={S} {model} missing={missing} strict={strict} inject={inject}: "
+    print(f"N={N} J={J} S={S} {model} missing={missing} strict={strict} inject={inject} sparse={sparse}: "
           f"{ms:.3f} ms  {ev / ms * 1e3:.3e} evals/s  clk={ck['sm_mhz']} {ck['reasons']} {ck['power_w_max']}W", flush=True)
 
 
@@ -57,4 +57,8 @@ if __name__ == "__main__":
     case(1_000_000, 100, 1, "irt_4pl")
     case(2_000_000, 200, 1, "irt_2pl", missing=0.9)
     case(2_000_000, 200, 32, "irt_2pl", missing=0.9)
+    case(2_000_000, 200, 1, "irt_2pl", missing=0.9, sparse=True)
+    case(2_000_000, 200, 32, "irt_2pl", missing=0.9, sparse=True)
+    case(2_000_000, 200, 1, "irt_2pl", missing=0.5, sparse=True)
+    case(2_000_000, 200, 1, "irt_2pl", missing=0.5)
     case(1000, 5, 1, "irt_2pl")

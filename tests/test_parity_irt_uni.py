@@ -32,7 +32,8 @@ def make_case(B, J, S, model, missing=0.0, seed=0, sat=False):
     return dict(y=y, mu=mu, sigma=sigma, eps=eps, a=a, b=b, c=c, d=d, model=model)
 
 
-def run_both(ops, cs, D=1.0, scale=1.0, estimator="pathwise", baseline=0.0, strict=False, idx=None, y_full=None):
+def run_both(ops, cs, D=1.0, scale=1.0, estimator="pathwise", baseline=0.0, strict=False, idx=None, y_full=None,
+             sparse=False):
     m = cs["model"]
     dev = "cuda"
     kw = dict(a=cs["a"] if m != "irt_1pl" else None, b=cs["b"],
@@ -44,7 +45,7 @@ def run_both(ops, cs, D=1.0, scale=1.0, estimator="pathwise", baseline=0.0, stri
     got = ops.irt_elbo_grad(codes, cs["mu"].to(dev), sigma=cs["sigma"].to(dev), eps=cs["eps"].to(dev),
                             **{k: (v.to(dev) if v is not None else None) for k, v in kw.items()},
                             model=m, D=D, scale=scale, estimator=estimator, baseline=baseline, strict=strict,
-                            idx=None if idx is None else idx.to(dev))
+                            idx=None if idx is None else idx.to(dev), sparse=sparse)
     torch.cuda.synchronize()
     return got, ref
 
@@ -208,3 +209,39 @@ def test_loss_only_call(ops):
                             eps=cs["eps"].to(dev), a=cs["a"].to(dev), b=cs["b"].to(dev), model="irt_2pl",
                             want_grad=False)
     assert torch.equal(val["loss"], full["loss"]) and "d_mu" not in val
+
+
+@pytest.mark.parametrize("model", ["irt_1pl", "irt_2pl", "irt_3pl", "irt_4pl"])
+@pytest.mark.parametrize("S,missing,J", [(1, 0.9, 200), (4, 0.9, 37), (32, 0.95, 101), (3, 0.0, 20), (8, 1.0, 16)])
+def test_sparse_compaction_path(ops, model, S, missing, J):
+    """VIPSY_IRT_FLAG_SPARSE (BASELINE config 4: 90 % missing): per-person compaction + fixed-point item sums
+    give the same loss and gradients as the oracle -- incl. fully observed and fully missing matrices."""
+    cs = make_case(B=333, J=J, S=S, model=model, missing=missing, seed=S + J)
+    if missing >= 1.0:
+        cs["y"][:] = float("nan")
+    got, ref = run_both(ops, cs, D=1.702, scale=4.0, sparse=True)
+    check(got, ref, model)
+
+
+def test_sparse_matches_dense_and_is_deterministic(ops):
+    cs = make_case(B=4000, J=200, S=2, model="irt_2pl", missing=0.9, seed=5)
+    dev = "cuda"
+    codes = codes_from_float(cs["y"]).to(dev)
+    kw = dict(sigma=cs["sigma"].to(dev), a=cs["a"].to(dev), b=cs["b"].to(dev), model="irt_2pl", n_particles=2,
+              seed=3, offset=9)
+    dense = ops.irt_elbo_grad(codes, cs["mu"].to(dev), **kw)
+    sp1 = ops.irt_elbo_grad(codes, cs["mu"].to(dev), sparse=True, **kw)
+    sp2 = ops.irt_elbo_grad(codes, cs["mu"].to(dev), sparse=True, **kw)
+    for k in ("loss", "d_mu", "d_sigma", "d_a", "d_b"):
+        assert_close(sp1[k], dense[k], 2e-6, 2e-6, k)
+        assert torch.equal(sp1[k], sp2[k]), k
+
+
+def test_sparse_idx_gather(ops):
+    cs = make_case(B=150, J=24, S=4, model="irt_3pl", missing=0.8, seed=21)
+    g = torch.Generator().manual_seed(1)
+    y_full = (torch.rand(600, 24, generator=g) < 0.5).float()
+    idx = torch.randperm(600, generator=g)[:150]
+    y_full[idx] = cs["y"]
+    got, ref = run_both(ops, cs, scale=4.0, idx=idx, y_full=y_full, sparse=True)
+    check(got, ref, "irt_3pl")

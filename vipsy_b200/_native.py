@@ -20,6 +20,7 @@ COV_DIAG1, COV_SHARED, COV_PERSON = 0, 1, 2
 CHOL_DENSE, CHOL_PACKED = 0, 1
 IRT_FLAG_STRICT = 1
 IRT_FLAG_NO_TENSOR = 2
+IRT_FLAG_SPARSE = 4
 
 _p = C.c_void_p
 

@@ -112,6 +112,8 @@ class BasePsy(nn.Module):               # vi.py:521-533
         self.kwargs = kwargs
         self._data_dev = data.to(self.device, torch.float32)
         self._codes = ops.pack_responses(self._data_dev)        # uint8 0/1/255, stays resident
+        # mostly-missing matrices take the compaction path of the K = 1 kernel (same results)
+        self._sparse = bool((self._codes == 255).float().mean() > 0.5) if self._codes.numel() else False
         self._seed, self._calls = int(seed), 0
         # optional person sharding (vipsy_b200.dist.attach): this rank holds rows
         # [person_offset, person_offset + sample_size) of a global_size-person job
@@ -226,7 +228,8 @@ class BaseIRT(BasePsy):                 # vi.py:536-656
                                   a=items["a"][1] if "a" in items else None, b=items["b"][1],
                                   c=items["c"][1] if "c" in items else None, d=items["d"][1] if "d" in items else None,
                                   idx=idx, a_free=self._a_free_dev, estimator=cfg.estimator, baseline=cfg.baseline,
-                                  want_grad=want_grad, **gkw, **self._noise_args())
+                                  want_grad=want_grad, sparse=self._sparse and self.x_feature == 1,
+                                  **gkw, **self._noise_args())
             w = 1.0 / len(groups)
             total = r["loss"] * w if total is None else total + r["loss"] * w
             if want_grad:

@@ -100,14 +100,15 @@ def irt_elbo_grad(
     a_free: Optional[torch.Tensor] = None,
     chol_packed: bool = False, chol_raw: bool = False,
     seed: int = 0, offset: int = 0, person_offset: int = 0,
-    want_grad: bool = True, strict: bool = False, tensor_cores: bool = True,
+    want_grad: bool = True, strict: bool = False, tensor_cores: bool = True, sparse: bool = False,
     d_mu_out: Optional[torch.Tensor] = None, d_scale_out: Optional[torch.Tensor] = None,
 ) -> Dict[str, Optional[torch.Tensor]]:
     """One fused ELBO + gradient evaluation (Trace_ELBO.loss_and_grads, vi.py:507).
 
     ``d_mu_out`` / ``d_scale_out``: optional preallocated fp32 CUDA buffers for the
     per-person gradients (d_sigma for K == 1, d_chol otherwise).  ``tensor_cores=False``
-    forces the SIMT contraction for K > 1 (default: tcgen05 for 2PL with K >= 8)."""
+    forces the SIMT contraction for K > 1 (default: tcgen05 for K >= 8).  ``sparse=True`` (K == 1)
+    tells the kernel most cells are missing: it compacts each person's observed cells first."""
     if not y.is_cuda or y.dtype != torch.uint8:
         raise ValueError("y must be a CUDA uint8 code matrix (see pack_responses)")
     if y.dim() != 2 or y.stride(1) != 1:
@@ -131,7 +132,8 @@ def irt_elbo_grad(
     args.n_rows, args.batch, args.n_items, args.n_dims, args.n_particles = n_rows, B, J, K, S
     args.model, args.estimator = m, N.EST[estimator]
     args.D, args.scale, args.baseline = float(D), float(scale), float(baseline)
-    args.flags = (N.IRT_FLAG_STRICT if strict else 0) | (0 if tensor_cores else N.IRT_FLAG_NO_TENSOR)
+    args.flags = (N.IRT_FLAG_STRICT if strict else 0) | (0 if tensor_cores else N.IRT_FLAG_NO_TENSOR) \
+        | (N.IRT_FLAG_SPARSE if sparse else 0)
     args.y, args.y_row_stride = _ptr(y), y.stride(0)
     idx_ = None
     if idx is not None:
