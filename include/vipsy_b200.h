@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define VIPSY_ABI_VERSION 1
+#define VIPSY_ABI_VERSION 2
 
 enum {
   VIPSY_OK = 0,
@@ -58,8 +58,10 @@ enum { VIPSY_COV_DIAG1 = 0,   /* K == 1: sigma[B]                               
  * (where the probability clamp cannot fire). */
 enum { VIPSY_IRT_FLAG_STRICT = 1,
        VIPSY_IRT_FLAG_NO_TENSOR = 2,    /* K > 1: force the SIMT contraction (default: tcgen05 when K >= 8) */
-       VIPSY_IRT_FLAG_SPARSE = 4 };     /* K == 1 hint: most cells are missing -> per-person compaction of the
+       VIPSY_IRT_FLAG_SPARSE = 4,       /* K == 1 hint: most cells are missing -> per-person compaction of the
                                           observed cells (same results; pays off below ~50 % density)        */
+       VIPSY_IRT_FLAG_NO_ROW = 8 };     /* K == 1, S == 1: force the lane-per-person kernels (default: the
+                                          warp-per-person row kernels when J % 4 == 0, 64 <= J <= 512)       */
 enum { VIPSY_CHOL_DENSE = 0,  /* row-major K x K, strict upper triangle ignored        */
        VIPSY_CHOL_PACKED = 1 };/* torch.tril_indices row-major order, K(K+1)/2 (vi.py:453) */
 
@@ -118,6 +120,13 @@ typedef struct VipsyIrtArgs {
   /* scratch */
   void* workspace;
   size_t workspace_bytes;
+  /* optional (ABI 2): the observed cells of y as a CSR, built once per response matrix with
+   * vipsy_observed_row_ptr + vipsy_observed_fill.  Row r of y owns entries[row_ptr[r] .. row_ptr[r+1]);
+   * an entry is item | response << 15.  Used when K == 1, S == 1 (pathwise): work and traffic scale with
+   * the observed cells, not with n_rows x J.  y must still be valid (other S / estimators read it). */
+  const int64_t* obs_row_ptr;   /* n_rows + 1, or NULL                               */
+  const uint16_t* obs_entries;  /* obs_nnz entries, or NULL                          */
+  int64_t obs_nnz;              /* host copy of row_ptr[n_rows] (picks the lane mapping; 0 = unknown) */
 } VipsyIrtArgs;
 
 /* Bytes of workspace vipsy_irt_elbo_grad needs for these sizes (0 on bad args). */
@@ -209,6 +218,13 @@ int vipsy_cdm_score_elbo_grad(const VipsyCdmScoreArgs* args, void* stream);
  * ---------------------------------------------------------------------- */
 /* float response matrix with NaN = missing (the reference's `data`) -> codes */
 int vipsy_pack_responses(const float* y_f32, int64_t n_cells, uint8_t* codes, void* stream);
+/* CSR of the observed cells (the "2-byte per response" layout for mostly-missing matrices, J <= 32768).
+ * Step 1 writes row_ptr[0..n_rows] (counts_scratch: n_rows int32 of scratch); the caller reads
+ * row_ptr[n_rows] to size `entries`; step 2 writes entry = item | (response != 0) << 15 in item order. */
+int vipsy_observed_row_ptr(const uint8_t* y, int64_t n_rows, int32_t n_items, int64_t y_row_stride,
+                           int32_t* counts_scratch, int64_t* row_ptr, void* stream);
+int vipsy_observed_fill(const uint8_t* y, int64_t n_rows, int32_t n_items, int64_t y_row_stride,
+                        const int64_t* row_ptr, uint16_t* entries, void* stream);
 /* eta table, bit-exact: out[c*J + j] = eta_cj in {0,1} (dina/dino, vi.py:78-81/95-98) */
 int vipsy_cdm_eta_table(const uint32_t* qmask, int32_t n_items, int32_t n_attrs, int32_t model,
                         uint8_t* eta, void* stream);

@@ -33,7 +33,7 @@ def test_every_declared_symbol_is_exported(lib):
     for n in names:
         assert n in N.SYMBOLS, f"{n} declared in the header but not bound"
         assert getattr(lib, n) is not None
-    assert lib.vipsy_abi_version() == 1
+    assert lib.vipsy_abi_version() == 2
 
 
 def test_struct_layout_matches_header():

@@ -245,3 +245,128 @@ def test_sparse_idx_gather(ops):
     y_full[idx] = cs["y"]
     got, ref = run_both(ops, cs, scale=4.0, idx=idx, y_full=y_full, sparse=True)
     check(got, ref, "irt_3pl")
+
+
+# ---- S == 1 row kernels (irt_uni_row.cu): warp per person, lanes over items ---------------------------
+@pytest.mark.parametrize("model", ["irt_1pl", "irt_2pl", "irt_3pl", "irt_4pl"])
+@pytest.mark.parametrize("J,missing,sparse", [(64, 0.0, False), (100, 0.15, False), (200, 0.9, True), (200, 0.9, False),
+                                              (256, 0.3, True), (132, 0.0, True), (128, 1.0, True), (128, 1.0, False)])
+def test_row_kernels_parity(ops, model, J, missing, sparse):
+    """One particle, J % 4 == 0, 64 <= J: dense (register-resident item sums) and sparse (ballot compaction)
+    row kernels against the oracle, incl. fully observed / fully missing matrices and ragged last tiles."""
+    cs = make_case(B=1237, J=J, S=1, model=model, missing=missing, seed=J + int(10 * missing))
+    if missing >= 1.0:
+        cs["y"][:] = float("nan")
+    got, ref = run_both(ops, cs, D=1.702, scale=4.0, sparse=sparse)
+    check(got, ref, model)
+
+
+@pytest.mark.parametrize("model,J", [("irt_2pl", 512), ("irt_2pl", 388), ("irt_1pl", 300), ("irt_4pl", 256)])
+@pytest.mark.parametrize("sparse", [False, True])
+def test_row_kernels_wide(ops, model, J, sparse):
+    cs = make_case(B=515, J=J, S=1, model=model, missing=0.5, seed=J)
+    got, ref = run_both(ops, cs, scale=2.0, sparse=sparse)
+    check(got, ref, model)
+
+
+@pytest.mark.parametrize("sparse", [False, True])
+def test_row_kernels_strict_4pl_and_saturation(ops, sparse):
+    cs = make_case(B=700, J=100, S=1, model="irt_4pl", missing=0.2, seed=3, sat=True)
+    cs["c"][0, :5] = 0.0          # items that can reach the clamp: the rational form must switch itself off
+    cs["d"][0, 5:9] = 1.0
+    got, ref = run_both(ops, cs, D=1.702, scale=1.5, sparse=sparse)
+    check(got, ref, "irt_4pl", tol=2e-5)
+    got, ref = run_both(ops, cs, D=1.702, scale=1.5, sparse=sparse, strict=True)
+    check(got, ref, "irt_4pl", tol=2e-5)
+
+
+@pytest.mark.parametrize("sparse", [False, True])
+def test_row_kernels_idx_gather_and_loss_only(ops, sparse):
+    cs = make_case(B=150, J=96, S=1, model="irt_3pl", missing=0.6, seed=21)
+    g = torch.Generator().manual_seed(1)
+    y_full = (torch.rand(600, 96, generator=g) < 0.5).float()
+    idx = torch.randperm(600, generator=g)[:150]
+    y_full[idx] = cs["y"]
+    got, ref = run_both(ops, cs, scale=4.0, idx=idx, y_full=y_full, sparse=sparse)
+    check(got, ref, "irt_3pl")
+    dev = "cuda"
+    val = ops.irt_elbo_grad(codes_from_float(y_full).to(dev), cs["mu"].to(dev), sigma=cs["sigma"].to(dev),
+                            eps=cs["eps"].to(dev), a=cs["a"].to(dev), b=cs["b"].to(dev), c=cs["c"].to(dev),
+                            model="irt_3pl", scale=4.0, idx=idx.to(dev), sparse=sparse, want_grad=False)
+    assert torch.equal(val["loss"], got["loss"]) and "d_mu" not in val
+
+
+def test_row_kernels_match_lane_kernels_same_philox_stream(ops):
+    """In-kernel noise: the row kernels draw particle 0 of the same Philox stream as the lane-per-person
+    kernels, so the two mappings agree to rounding on every output; and they are bit-reproducible."""
+    cs = make_case(B=5000, J=200, S=1, model="irt_2pl", missing=0.9, seed=5)
+    dev = "cuda"
+    codes = codes_from_float(cs["y"]).to(dev)
+    kw = dict(sigma=cs["sigma"].to(dev), a=cs["a"].to(dev), b=cs["b"].to(dev), model="irt_2pl", n_particles=1,
+              seed=3, offset=9, person_offset=17)
+    lane = ops.irt_elbo_grad(codes, cs["mu"].to(dev), row_kernel=False, **kw)
+    for sparse in (False, True):
+        r1 = ops.irt_elbo_grad(codes, cs["mu"].to(dev), sparse=sparse, **kw)
+        r2 = ops.irt_elbo_grad(codes, cs["mu"].to(dev), sparse=sparse, **kw)
+        for k in ("loss", "d_mu", "d_sigma", "d_a", "d_b"):
+            assert_close(r1[k], lane[k], 2e-6, 2e-6, k)
+            assert torch.equal(r1[k], r2[k]), k
+
+
+# ---- observed-cell CSR layout (irt_uni_csr.cu) -----------------------------------------------------------
+def test_observed_csr_layout_is_exact(ops):
+    g = torch.Generator().manual_seed(4)
+    y = (torch.rand(777, 53, generator=g) < 0.5).float()
+    y[torch.rand(777, 53, generator=g) < 0.8] = float("nan")
+    y[5] = float("nan")                                   # an empty row
+    y[6] = 1.0                                            # a full row
+    codes = codes_from_float(y)
+    rp, en, nnz = ops.observed_csr(codes.cuda())
+    rp, en = rp.cpu(), en.cpu().to(torch.int32)
+    obs = codes != 255
+    assert nnz == int(obs.sum()) and torch.equal(rp[1:] - rp[:-1], obs.sum(1))
+    rows, cols = obs.nonzero(as_tuple=True)               # row-major = item order within a row
+    assert torch.equal(en[:nnz] & 0x7fff, cols.to(torch.int32))
+    assert torch.equal((en[:nnz] >> 15).to(torch.uint8), codes[rows, cols])
+
+
+@pytest.mark.parametrize("model", ["irt_1pl", "irt_2pl", "irt_3pl", "irt_4pl"])
+@pytest.mark.parametrize("J,missing", [(200, 0.9), (37, 0.5), (300, 0.97), (64, 0.0), (50, 1.0)])
+def test_csr_path_parity(ops, model, J, missing):
+    """S == 1 over the CSR of observed cells: every sub-warp width (8 / 16 / 32 lanes per person), empty and
+    full rows, ragged last tile."""
+    cs = make_case(B=1237, J=J, S=1, model=model, missing=missing, seed=J)
+    if missing >= 1.0:
+        cs["y"][:] = float("nan")
+    m = cs["model"]
+    dev = "cuda"
+    kw = dict(a=cs["a"] if m != "irt_1pl" else None, b=cs["b"],
+              c=cs["c"] if m in ("irt_3pl", "irt_4pl") else None, d=cs["d"] if m == "irt_4pl" else None)
+    ref = o.irt_elbo_grad(cs["y"], cs["mu"], cs["sigma"], cs["eps"], kw["a"], kw["b"], kw["c"], kw["d"],
+                          model=m, D=1.702, scale=3.0)
+    codes = codes_from_float(cs["y"]).to(dev)
+    got = ops.irt_elbo_grad(codes, cs["mu"].to(dev), sigma=cs["sigma"].to(dev), eps=cs["eps"].to(dev),
+                            **{k: (v.to(dev) if v is not None else None) for k, v in kw.items()},
+                            model=m, D=1.702, scale=3.0, obs=ops.observed_csr(codes))
+    check(got, ref, m)
+
+
+def test_csr_path_idx_gather_deterministic(ops):
+    cs = make_case(B=150, J=96, S=1, model="irt_2pl", missing=0.85, seed=2)
+    g = torch.Generator().manual_seed(1)
+    y_full = (torch.rand(600, 96, generator=g) < 0.5).float()
+    y_full[torch.rand(600, 96, generator=g) < 0.85] = float("nan")
+    idx = torch.randperm(600, generator=g)[:150]
+    y_full[idx] = cs["y"]
+    dev = "cuda"
+    ref = o.irt_elbo_grad(cs["y"], cs["mu"], cs["sigma"], cs["eps"], cs["a"], cs["b"], None, None,
+                          model="irt_2pl", scale=4.0)
+    codes = codes_from_float(y_full).to(dev)
+    obs = ops.observed_csr(codes)
+    kw = dict(sigma=cs["sigma"].to(dev), eps=cs["eps"].to(dev), a=cs["a"].to(dev), b=cs["b"].to(dev),
+              model="irt_2pl", scale=4.0, idx=idx.to(dev), obs=obs)
+    r1 = ops.irt_elbo_grad(codes, cs["mu"].to(dev), **kw)
+    r2 = ops.irt_elbo_grad(codes, cs["mu"].to(dev), **kw)
+    check(r1, ref, "irt_2pl")
+    for k in ("loss", "d_mu", "d_sigma", "d_a", "d_b"):
+        assert torch.equal(r1[k], r2[k]), k

@@ -21,6 +21,7 @@ CHOL_DENSE, CHOL_PACKED = 0, 1
 IRT_FLAG_STRICT = 1
 IRT_FLAG_NO_TENSOR = 2
 IRT_FLAG_SPARSE = 4
+IRT_FLAG_NO_ROW = 8
 
 _p = C.c_void_p
 
@@ -43,6 +44,7 @@ class IrtArgs(C.Structure):
         ("loss", _p), ("d_mu", _p), ("d_sigma", _p), ("d_chol", _p),
         ("d_a", _p), ("d_b", _p), ("d_c", _p), ("d_d", _p),
         ("workspace", _p), ("workspace_bytes", C.c_size_t),
+        ("obs_row_ptr", _p), ("obs_entries", _p), ("obs_nnz", C.c_int64),
     ]
 
 
@@ -82,6 +84,8 @@ SYMBOLS = {
     "vipsy_cdm_score_workspace_bytes": (C.c_size_t, [C.POINTER(CdmScoreArgs)]),
     "vipsy_cdm_score_elbo_grad": (C.c_int, [C.POINTER(CdmScoreArgs), _p]),
     "vipsy_pack_responses": (C.c_int, [_p, C.c_int64, _p, _p]),
+    "vipsy_observed_row_ptr": (C.c_int, [_p, C.c_int64, C.c_int32, C.c_int64, _p, _p, _p]),
+    "vipsy_observed_fill": (C.c_int, [_p, C.c_int64, C.c_int32, C.c_int64, _p, _p, _p]),
     "vipsy_cdm_eta_table": (C.c_int, [_p, C.c_int32, C.c_int32, C.c_int32, _p, _p]),
     "vipsy_fill_normal": (C.c_int, [_p, C.c_int32, C.c_int64, C.c_int32, C.c_uint64, C.c_uint64, C.c_int64, _p]),
     "vipsy_selftest_umma": (C.c_int, [_p, C.c_int32, C.c_int32, _p, C.c_int32, C.c_int32, _p, C.c_int32, C.c_int32,
@@ -103,7 +107,7 @@ def lib():
         for name, (res, args) in SYMBOLS.items():
             fn = getattr(L, name)
             fn.restype, fn.argtypes = res, args
-        if L.vipsy_abi_version() != 1:
+        if L.vipsy_abi_version() != 2:
             raise VipsyError(ERR_ARG, "ABI version mismatch")
         _lib = L
     return _lib

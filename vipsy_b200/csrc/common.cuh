@@ -11,6 +11,9 @@ namespace vipsy {
 constexpr float kEps32 = 1.1920928955078125e-07f;        // torch clamp_probs eps
 constexpr float kOneMinusEps32 = 1.0f - kEps32;
 constexpr float kLogEps32 = -15.942385152878742f;
+// A masked cell is scored as Bernoulli(probs=0).log_prob(0) (vi.py:621-624): probs clamp to eps and the
+// cell contributes log(1 - eps) = -1.19e-7 (torch 1.6 fp32 and the fp64 oracle; no gradient).
+constexpr float kMaskedLogProb = -1.1920929665620834e-07f;
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kLn2 = 0.6931471805599453f;
 constexpr int kNumSMs = 148;

@@ -101,6 +101,7 @@ __global__ void __launch_bounds__(kUniThreads, 4) irt_uni_kernel(const IrtUniPar
     const float mu = valid ? p.mu[bi] : 0.f;
     const float sg = valid ? p.sigma[bi] : 1.f;
     float se = 0.f, see = 0.f, G1 = 0.f, G2 = 0.f, Lsum = 0.f, sw1 = 0.f, sw2 = 0.f;
+    int n_obs = 0;        // counted once per particle chunk; masked cells score log(1 - eps) each (kMaskedLogProb)
 
     for (int s0 = 0; s0 < p.S; s0 += SC) {
       // ---- noise for SC particles ----------------------------------------
@@ -157,6 +158,7 @@ __global__ void __launch_bounds__(kUniThreads, 4) irt_uni_kernel(const IrtUniPar
 #pragma unroll
         for (int q = 0; q < NQ; ++q) v[q] = 0.f;
         if (obs) {
+          ++n_obs;
           const float4 it = tab[j];
           const float2 it2 = tab2[j];
           const bool y1 = code != 0u;
@@ -210,7 +212,8 @@ __global__ void __launch_bounds__(kUniThreads, 4) irt_uni_kernel(const IrtUniPar
       const float sumx = fmaf(sg, se, S_f * mu);
       const float sumxe = fmaf(sg, see, mu * se);
       const float sumx2 = fmaf(S_f * mu, mu, fmaf(2.f * mu * sg, se, sg * sg * see));
-      const float elbo = kLn2 * Lsum - 0.5f * sumx2 + 0.5f * see + S_f * logf(sg);
+      const float elbo = kLn2 * Lsum - 0.5f * sumx2 + 0.5f * see + S_f * logf(sg) +
+                         (S_f * (float)J - (float)n_obs * (float)SC) * kMaskedLogProb;
       loss_acc -= (double)(k_scale * elbo);
       if (p.d_mu) {
         if (SCORE) {
@@ -324,6 +327,7 @@ int irt_uni_launch(const VipsyIrtArgs* a, cudaStream_t st) {
                                             align16((size_t)num_sms() * kUniMaxCtasPerSM * 8));
   p.contiguous = (a->idx == nullptr && a->y_row_stride == J) ? 1 : 0;
   p.want_grad = (a->d_b || a->d_a || a->d_c || a->d_d) ? 1 : 0;
+  p.row_ptr = a->obs_row_ptr; p.entries = a->obs_entries;
 
   int SC = 32;
   while (SC > 1 && (a->n_particles % SC) != 0) SC >>= 1;
@@ -332,7 +336,12 @@ int irt_uni_launch(const VipsyIrtArgs* a, cudaStream_t st) {
   int rc;
   const bool sparse = (a->flags & VIPSY_IRT_FLAG_SPARSE) && a->estimator == VIPSY_EST_PATHWISE && J < 32768 &&
                       irt_uni_sparse_smem_bytes(J, NQ) <= 227 * 1024;
-  if (sparse)
+  const bool want_sparse = (a->flags & VIPSY_IRT_FLAG_SPARSE) && a->estimator == VIPSY_EST_PATHWISE;
+  if (irt_uni_csr_supported(a))
+    rc = irt_uni_csr_launch(a, fast, p, st, &grid);                          // S == 1 over the observed-cell CSR
+  else if (!(a->flags & VIPSY_IRT_FLAG_NO_ROW) && irt_uni_row_supported(a, want_sparse))
+    rc = irt_uni_row_launch(a->model, fast, want_sparse, p, st, &grid);     // S == 1: warp per person
+  else if (sparse)
     rc = irt_uni_sparse_launch(a->model, fast, SC, p, st, &grid);
   else
     rc = a->estimator == VIPSY_EST_SCORE ? launch_model<true>(a->model, fast, SC, p, smem, st, &grid)

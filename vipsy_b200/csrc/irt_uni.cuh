@@ -27,6 +27,8 @@ struct IrtUniParams {
   double* loss_partial;   // [grid]
   int contiguous;         // rows of the batch are contiguous in y (no idx, ld == J)
   int want_grad;
+  const int64_t* row_ptr;   // CSR of the observed cells (irt_uni_csr.cu), or null
+  const uint16_t* entries;
 };
 
 __host__ __device__ inline size_t align16(size_t x) { return (x + 15) & ~size_t(15); }
@@ -162,5 +164,15 @@ __device__ __forceinline__ void item_evals(const float dmc, const float base, co
 // sparse (compacted) variant, irt_uni_sparse.cu
 size_t irt_uni_sparse_smem_bytes(int J, int NQ);
 int irt_uni_sparse_launch(int model, bool fast, int SC, IrtUniParams& p, cudaStream_t st, int* grid_out);
+
+
+// S == 1 row kernels (warp per person, lanes over items), irt_uni_row.cu
+bool irt_uni_row_supported(const VipsyIrtArgs* a, bool sparse);
+int irt_uni_row_launch(int model, bool fast, bool sparse, IrtUniParams& p, cudaStream_t st, int* grid_out);
+
+
+// S == 1 over a CSR of the observed cells, irt_uni_csr.cu
+bool irt_uni_csr_supported(const VipsyIrtArgs* a);
+int irt_uni_csr_launch(const VipsyIrtArgs* a, bool fast, IrtUniParams& p, cudaStream_t st, int* grid_out);
 
 }  // namespace vipsy

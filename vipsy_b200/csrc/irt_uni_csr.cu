@@ -1,0 +1,334 @@
+// K == 1, one particle, responses given as a CSR of the OBSERVED cells (BASELINE config 4: 2M persons x
+// 200 items, 90 % NaN).  The reference keeps the NaN-coded float matrix and masks it on every step
+// (vi.py:617-625); the response matrix never changes between steps, so the compaction is done once
+// (vipsy_observed_row_ptr / vipsy_observed_fill below, the "CSR-of-observed" layout of SURVEY 8f-3) and the
+// per-step kernel streams 2 bytes per observed cell instead of 1 byte per cell: c4 moves 80 + 16 MB of
+// response data per step instead of 400 MB, and does arithmetic only where there is a response.
+//
+// Mapping: a sub-warp of SW lanes (8, 16 or 32, chosen from the mean row length) owns a person; its
+// lanes take that person's entries SW at a time.  32 / SW persons are in flight per warp instruction, so
+// short rows still fill the lanes.  Entries of one person are distinct items, and every sub-warp has its
+// own shared-memory item accumulators: plain read-modify-writes in a fixed order, deterministic, no atomics.
+#include <algorithm>
+
+#include "irt_uni.cuh"
+
+namespace vipsy {
+
+template <int MODEL, bool FASTPATH>
+__device__ __forceinline__ void csr_cell(const float t, const float dmc, const float base, const bool obs,
+                                         float& w, float& a1, float& a2, float& qc) {
+  if constexpr (FASTPATH) {
+    const float e = ex2_approx(fminf(t, 60.f));
+    const float ope = e + 1.f;
+    const float num = fmaf(base, e, base + dmc);
+    float R = rcp_approx(num * ope);
+    R = obs ? R : 0.f;
+    const float sp = num * R;
+    a1 = ope * R;
+    a2 = a1 * e;
+    w = e * R;
+    qc = obs ? num * sp : 1.f;
+  } else {
+    const float e = ex2_approx(fminf(t, 126.f));
+    const float sp = rcp_approx(e + 1.f);
+    const float es = e * sp;
+    float q;
+    if constexpr (MODEL >= 3) q = fmaf(dmc, sp, base); else q = sp;
+    const float qcl = vclampp(q);
+    const bool keep = obs && (q == qcl);
+    if constexpr (MODEL >= 3) {
+      const float r = keep ? rcp_approx(qcl) : 0.f;
+      a1 = r * sp;
+      a2 = r * es;
+      w = a1 * es;
+    } else {
+      a1 = 0.f; a2 = 0.f;
+      w = keep ? es : 0.f;
+    }
+    qc = obs ? qcl : 1.f;
+  }
+}
+
+__host__ __device__ inline size_t csr_smem_bytes(int J, int NQ, int SW) {
+  return (size_t)J * 16 + align16((size_t)J * 8) + (size_t)kUniWarps * (32 / SW) * align16((size_t)NQ * J * 4);
+}
+
+template <int MODEL, int SW, bool FAST>
+__global__ void __launch_bounds__(kUniThreads) irt_uni_csr_kernel(const IrtUniParams p) {
+  constexpr int NQ = MODEL;
+  constexpr int NSUB = 32 / SW;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int J = p.J;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int sub = lane / SW, sl = lane % SW;
+  float4* tab = reinterpret_cast<float4*>(smem_raw);                                   // {A', B', c, d-c}
+  float2* tab2 = reinterpret_cast<float2*>(smem_raw + (size_t)J * 16);                 // {D a (d-c), 1-d}
+  unsigned char* q0 = reinterpret_cast<unsigned char*>(tab2) + align16((size_t)J * 8);
+  const size_t acc_bytes = align16((size_t)NQ * J * 4);
+  float* acc_all = reinterpret_cast<float*>(q0);
+  float* acc = reinterpret_cast<float*>(q0 + (size_t)(warp * NSUB + sub) * acc_bytes);   // [NQ][J], sub-warp-private
+
+  int ok = 1;
+  for (int j = threadIdx.x; j < J; j += kUniThreads) {
+    const float aj = MODEL >= 2 ? p.a[j] : 1.f;
+    const float cj = MODEL >= 3 ? p.c[j] : 0.f;
+    const float dj = MODEL == 4 ? p.d[j] : 1.f;
+    tab[j] = make_float4(-p.D * kLog2e * aj, -p.D * kLog2e * p.b[j], cj, dj - cj);
+    tab2[j] = make_float2(p.D * aj * (dj - cj), 1.f - dj);
+    if (FAST) ok &= (cj >= 1e-3f) && (dj <= 1.f - 1e-3f) && (dj - cj >= 1e-3f);
+  }
+  for (int i = threadIdx.x; i < (int)(kUniWarps * NSUB * acc_bytes / 4); i += kUniThreads) acc_all[i] = 0.f;
+  const bool use_fast = FAST ? (__syncthreads_and(ok) != 0) : (__syncthreads(), false);
+
+  double loss_acc = 0.0;
+  const int64_t ntiles = (p.B + 31) / 32;
+  const int64_t gwarp = (int64_t)blockIdx.x * kUniWarps + warp;
+  const int64_t nwarps = (int64_t)gridDim.x * kUniWarps;
+
+  for (int64_t tile = gwarp; tile < ntiles; tile += nwarps) {
+    const int64_t b0 = tile * 32;
+    const int64_t bi = b0 + lane;
+    // ---- per lane: one person's variational inputs and its slice of the entry array -----------------------
+    float mu = 0.f, sg = 1.f, eps = 0.f;
+    int64_t beg_l = 0;
+    int cnt_l = 0;
+    const bool valid = bi < p.B;
+    if (valid) {
+      mu = p.mu[bi];
+      sg = p.sigma[bi];
+      const int64_t row = p.idx ? __ldg(p.idx + bi) : bi;
+      beg_l = __ldg(p.row_ptr + row);
+      cnt_l = (int)(__ldg(p.row_ptr + row + 1) - beg_l);
+    }
+    if (p.eps) eps = valid ? __ldg(p.eps + bi) : 0.f;
+    else eps = normal4(p.seed, p.offset, (uint64_t)(p.person_offset + bi), 0u).x;
+    const float x_l = fmaf(sg, eps, mu);
+    float Gmine = 0.f, Ltile = 0.f;
+
+    // ---- SW rounds, NSUB persons per round; the first SW entries of the next round are loaded ahead -----
+    int pi = sub;
+    float x = __shfl_sync(0xffffffffu, x_l, pi);
+    int cnt = __shfl_sync(0xffffffffu, cnt_l, pi);
+    int64_t beg = __shfl_sync(0xffffffffu, beg_l, pi);
+    uint32_t ent = sl < cnt ? (uint32_t)__ldg(p.entries + beg + sl) : 0u;
+#pragma unroll 1
+    for (int r = 0; r < SW; ++r) {
+      const int pn = (r + 1 < SW ? (r + 1) * NSUB : 0) + sub;
+      const float xn = __shfl_sync(0xffffffffu, x_l, pn);
+      const int cntn = __shfl_sync(0xffffffffu, cnt_l, pn);
+      const int64_t begn = __shfl_sync(0xffffffffu, beg_l, pn);
+      const uint32_t entn = (r + 1 < SW && sl < cntn) ? (uint32_t)__ldg(p.entries + begn + sl) : 0u;
+
+      float Gi = 0.f;
+      for (int t0 = 0; __any_sync(0xffffffffu, t0 < cnt); t0 += SW) {
+        const bool obs = t0 + sl < cnt;
+        if (t0 > 0) ent = obs ? (uint32_t)__ldg(p.entries + beg + t0 + sl) : 0u;
+        const int j = (int)(ent & 0x7fffu);
+        const bool y1 = (ent & 0x8000u) != 0u;
+        const float4 it = tab[j];
+        const float2 it2 = tab2[j];
+        const float tt0 = fmaf(it.x, x, it.y);
+        const float t = y1 ? tt0 : -tt0;
+        const float base = MODEL >= 3 ? (y1 ? it.z : it2.y) : 0.f;
+        float w, a1, a2, qc;
+        if (FAST && use_fast) csr_cell<MODEL, true>(t, it.w, base, obs, w, a1, a2, qc);
+        else csr_cell<MODEL, false>(t, it.w, base, obs, w, a1, a2, qc);
+        const float ws = y1 ? w : -w;
+        Gi = fmaf(it2.x, ws, Gi);
+        Ltile += lg2_approx(qc);
+        if (obs && p.want_grad) {
+          acc[j] += ws;
+          if constexpr (NQ >= 2) acc[J + j] = fmaf(ws, x, acc[J + j]);
+          if constexpr (NQ >= 3) acc[2 * J + j] += y1 ? a2 : -a1;
+          if constexpr (NQ >= 4) acc[3 * J + j] += y1 ? a1 : -a2;
+        }
+      }
+      __syncwarp();                                   // orders the accumulator updates of consecutive persons
+#pragma unroll
+      for (int o = SW / 2; o > 0; o >>= 1) Gi += __shfl_xor_sync(0xffffffffu, Gi, o);
+      const float v = __shfl_sync(0xffffffffu, Gi, (lane % NSUB) * SW);    // person r*NSUB + s was done by sub-warp s
+      if (lane / NSUB == r) Gmine = v;
+      x = xn; cnt = cntn; beg = begn; ent = entn;
+    }
+
+    float prior = 0.f;
+    if (valid) {
+      prior = -0.5f * x_l * x_l + 0.5f * eps * eps + logf(sg) + (float)(J - cnt_l) * kMaskedLogProb;
+      if (p.d_mu) {
+        p.d_mu[bi] = -p.scale * (Gmine - x_l);
+        p.d_sigma[bi] = -p.scale * (Gmine - x_l) * eps - p.scale / sg;
+      }
+    }
+    loss_acc -= (double)(p.scale * fmaf(kLn2, Ltile, prior));
+  }
+
+  __shared__ double loss_sm[kUniWarps];
+  loss_acc = warp_sum(loss_acc);
+  if (lane == 0) loss_sm[warp] = loss_acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+#pragma unroll
+    for (int w = 0; w < kUniWarps; ++w) t += loss_sm[w];
+    p.loss_partial[blockIdx.x] = t;
+  }
+  if (p.want_grad) {
+    for (int i = threadIdx.x; i < NQ * J; i += kUniThreads) {
+      float t = 0.f;
+#pragma unroll
+      for (int w = 0; w < kUniWarps * NSUB; ++w) t += acc_all[(size_t)w * (acc_bytes / 4) + i];
+      const int q = i / J, j = i - q * J;
+      if (q < 2) t *= p.D * tab[j].w;
+      p.item_partial[(size_t)blockIdx.x * NQ * J + i] = t;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+template <int MODEL, int SW, bool FAST>
+static int launch_csr_one(IrtUniParams& p, cudaStream_t st, int* grid_out) {
+  auto k = irt_uni_csr_kernel<MODEL, SW, FAST>;
+  static int occ = 0;
+  static size_t occ_smem = ~size_t(0);
+  const size_t smem = csr_smem_bytes(p.J, MODEL, SW);
+  if (smem > 48 * 1024) VIPSY_CUDA_CHECK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  if (occ == 0 || occ_smem != smem) {
+    VIPSY_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, kUniThreads, smem));
+    occ_smem = smem;
+    if (occ < 1) occ = 1;
+    if (occ > 8) occ = 8;
+  }
+  const int64_t ntiles = (p.B + 31) / 32;
+  int64_t ctas = (ntiles + kUniWarps - 1) / kUniWarps;
+  const int64_t cap = (int64_t)num_sms() * occ;
+  if (ctas > cap) ctas = cap;
+  if (ctas < 1) ctas = 1;
+  *grid_out = (int)ctas;
+  k<<<(int)ctas, kUniThreads, smem, st>>>(p);
+  VIPSY_CUDA_CHECK(cudaGetLastError());
+  return VIPSY_OK;
+}
+
+template <int MODEL, bool FAST>
+static int launch_csr_sw(int SW, IrtUniParams& p, cudaStream_t st, int* grid) {
+  switch (SW) {
+    case 8: return launch_csr_one<MODEL, 8, FAST>(p, st, grid);
+    case 16: return launch_csr_one<MODEL, 16, FAST>(p, st, grid);
+    default: return launch_csr_one<MODEL, 32, FAST>(p, st, grid);
+  }
+}
+
+bool irt_uni_csr_supported(const VipsyIrtArgs* a) {
+  return a->obs_row_ptr && a->obs_entries && a->n_particles == 1 && a->estimator == VIPSY_EST_PATHWISE &&
+         a->n_items <= 32768 && csr_smem_bytes(a->n_items, a->model, 32) <= 200 * 1024;
+}
+
+int irt_uni_csr_launch(const VipsyIrtArgs* a, bool fast, IrtUniParams& p, cudaStream_t st, int* grid_out) {
+  // sub-warp width from the mean row length (obs_nnz / n_rows); fall back to wider sub-warps when the
+  // per-sub-warp accumulators would not fit
+  const double mean = a->n_rows > 0 && a->obs_nnz > 0 ? (double)a->obs_nnz / (double)a->n_rows : (double)a->n_items;
+  int SW = mean <= 28.0 ? 8 : (mean <= 80.0 ? 16 : 32);
+  while (SW < 32 && csr_smem_bytes(a->n_items, a->model, SW) > 48 * 1024) SW *= 2;
+  switch (a->model) {
+    case VIPSY_IRT_1PL: return launch_csr_sw<1, false>(SW, p, st, grid_out);
+    case VIPSY_IRT_2PL: return launch_csr_sw<2, false>(SW, p, st, grid_out);
+    case VIPSY_IRT_3PL: return launch_csr_sw<3, false>(SW, p, st, grid_out);
+    default:
+      return fast ? launch_csr_sw<4, true>(SW, p, st, grid_out) : launch_csr_sw<4, false>(SW, p, st, grid_out);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// one-time construction of the layout: counts -> exclusive scan -> fill
+// ---------------------------------------------------------------------------------------------------------
+__global__ void observed_count_kernel(const uint8_t* __restrict__ y, int64_t n_rows, int J, int64_t ld,
+                                      int32_t* __restrict__ counts) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t r = warp; r < n_rows; r += nw) {
+    const uint8_t* g = y + r * ld;
+    int c = 0;
+    for (int j = lane; j < J; j += 32) c += g[j] != 255;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    if (lane == 0) counts[r] = c;
+  }
+}
+
+// row_ptr[i] = sum_{r < i} counts[r], i = 0..n; one CTA, each thread owns a contiguous chunk
+__global__ void __launch_bounds__(1024) exclusive_scan_kernel(const int32_t* __restrict__ counts, int64_t n,
+                                                              int64_t* __restrict__ row_ptr) {
+  __shared__ int64_t part[1024];
+  const int t = threadIdx.x;
+  const int64_t chunk = (n + 1023) / 1024;
+  const int64_t lo = min(n, (int64_t)t * chunk), hi = min(n, lo + chunk);
+  int64_t s = 0;
+  for (int64_t i = lo; i < hi; ++i) s += counts[i];
+  part[t] = s;
+  __syncthreads();
+  for (int o = 1; o < 1024; o <<= 1) {           // Hillis-Steele inclusive scan of the 1024 chunk sums
+    const int64_t v = t >= o ? part[t - o] : 0;
+    __syncthreads();
+    part[t] += v;
+    __syncthreads();
+  }
+  int64_t run = part[t] - s;
+  for (int64_t i = lo; i < hi; ++i) { row_ptr[i] = run; run += counts[i]; }
+  if (t == 1023) row_ptr[n] = part[1023];
+}
+
+__global__ void observed_fill_kernel(const uint8_t* __restrict__ y, int64_t n_rows, int J, int64_t ld,
+                                     const int64_t* __restrict__ row_ptr, uint16_t* __restrict__ entries) {
+  const int lane = threadIdx.x & 31;
+  const uint32_t lt = (1u << lane) - 1u;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t r = warp; r < n_rows; r += nw) {
+    const uint8_t* g = y + r * ld;
+    int64_t o = row_ptr[r];
+    for (int j0 = 0; j0 < J; j0 += 32) {
+      const int j = j0 + lane;
+      const uint32_t code = j < J ? g[j] : 255u;
+      const bool obs = code != 255u;
+      const uint32_t m = __ballot_sync(0xffffffffu, obs);
+      if (obs) entries[o + __popc(m & lt)] = (uint16_t)(j | (code != 0u ? 0x8000u : 0u));
+      o += __popc(m);
+    }
+  }
+}
+
+}  // namespace vipsy
+
+using namespace vipsy;
+
+extern "C" {
+
+int vipsy_observed_row_ptr(const uint8_t* y, int64_t n_rows, int32_t n_items, int64_t y_row_stride,
+                           int32_t* counts_scratch, int64_t* row_ptr, void* stream) {
+  VIPSY_REQUIRE(y && counts_scratch && row_ptr && n_rows >= 0 && n_items > 0 && n_items <= 32768 &&
+                    y_row_stride >= n_items,
+                VIPSY_ERR_ARG, "vipsy_observed_row_ptr: bad arguments (J must be <= 32768)");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (n_rows > 0) {
+    const int blocks = (int)std::min<int64_t>((n_rows + 7) / 8, (int64_t)num_sms() * 16);
+    observed_count_kernel<<<blocks, 256, 0, st>>>(y, n_rows, n_items, y_row_stride, counts_scratch);
+  }
+  exclusive_scan_kernel<<<1, 1024, 0, st>>>(counts_scratch, n_rows, row_ptr);
+  VIPSY_CUDA_CHECK(cudaGetLastError());
+  return VIPSY_OK;
+}
+
+int vipsy_observed_fill(const uint8_t* y, int64_t n_rows, int32_t n_items, int64_t y_row_stride,
+                        const int64_t* row_ptr, uint16_t* entries, void* stream) {
+  VIPSY_REQUIRE(y && row_ptr && entries && n_rows >= 0 && n_items > 0 && n_items <= 32768 && y_row_stride >= n_items,
+                VIPSY_ERR_ARG, "vipsy_observed_fill: bad arguments");
+  if (n_rows == 0) return VIPSY_OK;
+  const int blocks = (int)std::min<int64_t>((n_rows + 7) / 8, (int64_t)num_sms() * 16);
+  observed_fill_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(y, n_rows, n_items, y_row_stride, row_ptr, entries);
+  VIPSY_CUDA_CHECK(cudaGetLastError());
+  return VIPSY_OK;
+}
+
+}  // extern "C"

@@ -242,7 +242,7 @@ __global__ void __launch_bounds__(kUniThreads, 3) irt_uni_sparse_kernel(const Ir
       const float sumx = fmaf(sg, se, S_f * mu);
       const float sumxe = fmaf(sg, see, mu * se);
       const float sumx2 = fmaf(S_f * mu, mu, fmaf(2.f * mu * sg, se, sg * sg * see));
-      const float elbo = kLn2 * Lsum - 0.5f * sumx2 + 0.5f * see + S_f * logf(sg);
+      const float elbo = kLn2 * Lsum - 0.5f * sumx2 + 0.5f * see + S_f * (logf(sg) + (float)(J - cnt) * kMaskedLogProb);
       loss_acc -= (double)(k_scale * elbo);
       if (p.d_mu) {
         p.d_mu[bi] = -k_scale * (G1 - sumx);

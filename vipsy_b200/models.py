@@ -114,12 +114,19 @@ class BasePsy(nn.Module):               # vi.py:521-533
         self._codes = ops.pack_responses(self._data_dev)        # uint8 0/1/255, stays resident
         # mostly-missing matrices take the compaction path of the K = 1 kernel (same results)
         self._sparse = bool((self._codes == 255).float().mean() > 0.5) if self._codes.numel() else False
+        self._obs_csr = None          # CSR of the observed cells, built on first use (K = 1, S = 1 path)
         self._seed, self._calls = int(seed), 0
         # optional person sharding (vipsy_b200.dist.attach): this rank holds rows
         # [person_offset, person_offset + sample_size) of a global_size-person job
         self.global_size = self.sample_size
         self.person_offset = 0
         self.reducer = None
+
+    def _observed_csr(self):
+        """(row_ptr, entries, nnz) of the observed cells; the matrix is constant, so this is built once."""
+        if self._obs_csr is None and self.item_size <= 32768:
+            self._obs_csr = ops.observed_csr(self._codes)
+        return self._obs_csr
 
     # ---- plate('data', N, subsample_size=B): idx + scale (SURVEY A.1) -------------
     def _plate(self):
@@ -229,6 +236,7 @@ class BaseIRT(BasePsy):                 # vi.py:536-656
                                   c=items["c"][1] if "c" in items else None, d=items["d"][1] if "d" in items else None,
                                   idx=idx, a_free=self._a_free_dev, estimator=cfg.estimator, baseline=cfg.baseline,
                                   want_grad=want_grad, sparse=self._sparse and self.x_feature == 1,
+                                  obs=self._observed_csr() if (self._sparse and self.x_feature == 1 and s == 1) else None,
                                   **gkw, **self._noise_args())
             w = 1.0 / len(groups)
             total = r["loss"] * w if total is None else total + r["loss"] * w

@@ -58,6 +58,23 @@ def pack_responses(y: torch.Tensor) -> torch.Tensor:
     return out
 
 
+def observed_csr(y: torch.Tensor):
+    """uint8 code matrix -> (row_ptr int64[n_rows+1], entries uint16[nnz], nnz): the observed cells only,
+    entry = item | response << 15.  Built once per response matrix (the matrix is constant across SVI steps);
+    ``irt_elbo_grad(..., obs=...)`` then streams 2 bytes per OBSERVED cell instead of 1 byte per cell."""
+    if not y.is_cuda or y.dtype != torch.uint8 or y.dim() != 2 or y.stride(1) != 1:
+        raise ValueError("y must be a CUDA uint8 code matrix with unit column stride")
+    n_rows, J = y.shape
+    counts = torch.empty(max(n_rows, 1), dtype=torch.int32, device=y.device)
+    row_ptr = torch.empty(n_rows + 1, dtype=torch.int64, device=y.device)
+    L = N.lib()
+    N.check(L.vipsy_observed_row_ptr(_ptr(y), n_rows, J, y.stride(0), _ptr(counts), _ptr(row_ptr), _stream()))
+    nnz = int(row_ptr[-1].item())
+    entries = torch.empty(max(nnz, 1), dtype=torch.uint16, device=y.device)
+    N.check(L.vipsy_observed_fill(_ptr(y), n_rows, J, y.stride(0), _ptr(row_ptr), _ptr(entries), _stream()))
+    return row_ptr, entries, nnz
+
+
 def fill_normal(S: int, B: int, K: int, seed: int, offset: int, person_offset: int = 0, device="cuda"):
     out = torch.empty((S, B, K), dtype=torch.float32, device=device)
     N.check(N.lib().vipsy_fill_normal(_ptr(out), S, B, K, seed, offset, person_offset, _stream()))
@@ -101,6 +118,7 @@ def irt_elbo_grad(
     chol_packed: bool = False, chol_raw: bool = False,
     seed: int = 0, offset: int = 0, person_offset: int = 0,
     want_grad: bool = True, strict: bool = False, tensor_cores: bool = True, sparse: bool = False,
+    row_kernel: bool = True, obs=None,
     d_mu_out: Optional[torch.Tensor] = None, d_scale_out: Optional[torch.Tensor] = None,
 ) -> Dict[str, Optional[torch.Tensor]]:
     """One fused ELBO + gradient evaluation (Trace_ELBO.loss_and_grads, vi.py:507).
@@ -108,7 +126,9 @@ def irt_elbo_grad(
     ``d_mu_out`` / ``d_scale_out``: optional preallocated fp32 CUDA buffers for the
     per-person gradients (d_sigma for K == 1, d_chol otherwise).  ``tensor_cores=False``
     forces the SIMT contraction for K > 1 (default: tcgen05 for K >= 8).  ``sparse=True`` (K == 1)
-    tells the kernel most cells are missing: it compacts each person's observed cells first."""
+    tells the kernel most cells are missing: it compacts each person's observed cells first.
+    ``obs``: the (row_ptr, entries, nnz) triple of ``observed_csr(y)``; used by the K == 1, S == 1 path.
+    ``row_kernel=False`` (K == 1, S == 1) forces the lane-per-person kernels instead of the warp-per-person ones."""
     if not y.is_cuda or y.dtype != torch.uint8:
         raise ValueError("y must be a CUDA uint8 code matrix (see pack_responses)")
     if y.dim() != 2 or y.stride(1) != 1:
@@ -133,8 +153,13 @@ def irt_elbo_grad(
     args.model, args.estimator = m, N.EST[estimator]
     args.D, args.scale, args.baseline = float(D), float(scale), float(baseline)
     args.flags = (N.IRT_FLAG_STRICT if strict else 0) | (0 if tensor_cores else N.IRT_FLAG_NO_TENSOR) \
-        | (N.IRT_FLAG_SPARSE if sparse else 0)
+        | (N.IRT_FLAG_SPARSE if sparse else 0) | (0 if row_kernel else N.IRT_FLAG_NO_ROW)
     args.y, args.y_row_stride = _ptr(y), y.stride(0)
+    if obs is not None:
+        rp, en, nnz = obs
+        if rp.numel() != n_rows + 1 or rp.dtype != torch.int64 or en.dtype != torch.uint16:
+            raise ValueError("obs must be the (row_ptr, entries, nnz) triple of observed_csr(y)")
+        args.obs_row_ptr, args.obs_entries, args.obs_nnz = _ptr(rp), _ptr(en), int(nnz)
     idx_ = None
     if idx is not None:
         idx_ = idx.to(device=dev, dtype=torch.int64).contiguous()
@@ -220,7 +245,7 @@ def irt_elbo_grad(
     args.workspace, args.workspace_bytes = _ptr(ws), ws.numel()
     N.check(L.vipsy_irt_elbo_grad(C.byref(args), _stream()))
     out["loss"] = loss
-    out["_keepalive"] = (mu_, sg_, ch_, eps_, a_, b_, c_, d_, af_, idx_, ws)
+    out["_keepalive"] = (mu_, sg_, ch_, eps_, a_, b_, c_, d_, af_, idx_, ws, obs)
     return out
 
 
