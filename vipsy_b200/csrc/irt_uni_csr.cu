@@ -50,32 +50,69 @@ __device__ __forceinline__ void csr_cell(const float t, const float dmc, const f
   }
 }
 
+// accumulator row of one item: NQ sums padded to 1, 2 or 4 floats so that one LDS/STS moves the row
+__host__ __device__ constexpr int csr_acc_width(int NQ) { return NQ <= 2 ? NQ : 4; }
+// item table: {A', B'} (1PL / 2PL; D a = -A' / log2 e) or {A', B', c, d-c} + {D a (d-c), 1-d}
+__host__ __device__ inline size_t csr_tab_bytes(int J, int NQ) {
+  return NQ <= 2 ? align16((size_t)J * 8) : (size_t)J * 16 + align16((size_t)J * 8);
+}
 __host__ __device__ inline size_t csr_smem_bytes(int J, int NQ, int SW) {
-  return (size_t)J * 16 + align16((size_t)J * 8) + (size_t)kUniWarps * (32 / SW) * align16((size_t)NQ * J * 4);
+  return csr_tab_bytes(J, NQ) + (size_t)kUniWarps * (32 / SW) * align16((size_t)csr_acc_width(NQ) * J * 4);
+}
+
+// per-lane view of one person of a 32-person tile
+struct CsrLane {
+  float mu, sg, eps, x;
+  int64_t beg;
+  int cnt;
+  bool valid;
+};
+__device__ __forceinline__ CsrLane csr_lane(const IrtUniParams& p, int64_t bi) {
+  CsrLane t;
+  t.valid = bi < p.B;
+  t.mu = 0.f; t.sg = 1.f; t.beg = 0; t.cnt = 0;
+  if (t.valid) {
+    t.mu = p.mu[bi];
+    t.sg = p.sigma[bi];
+    const int64_t row = p.idx ? __ldg(p.idx + bi) : bi;
+    t.beg = __ldg(p.row_ptr + row);
+    t.cnt = (int)(__ldg(p.row_ptr + row + 1) - t.beg);
+  }
+  if (p.eps) t.eps = t.valid ? __ldg(p.eps + bi) : 0.f;
+  else t.eps = t.valid ? normal4(p.seed, p.offset, (uint64_t)(p.person_offset + bi), 0u).x : 0.f;
+  t.x = fmaf(t.sg, t.eps, t.mu);
+  return t;
 }
 
 template <int MODEL, int SW, bool FAST>
 __global__ void __launch_bounds__(kUniThreads) irt_uni_csr_kernel(const IrtUniParams p) {
   constexpr int NQ = MODEL;
+  constexpr int AW = csr_acc_width(NQ);
   constexpr int NSUB = 32 / SW;
+  constexpr int NBP = SW == 8 ? 3 : 2;          // batches of the next round whose entries are loaded ahead
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int J = p.J;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int sub = lane / SW, sl = lane % SW;
-  float4* tab = reinterpret_cast<float4*>(smem_raw);                                   // {A', B', c, d-c}
-  float2* tab2 = reinterpret_cast<float2*>(smem_raw + (size_t)J * 16);                 // {D a (d-c), 1-d}
-  unsigned char* q0 = reinterpret_cast<unsigned char*>(tab2) + align16((size_t)J * 8);
-  const size_t acc_bytes = align16((size_t)NQ * J * 4);
+  float2* tabAB = reinterpret_cast<float2*>(smem_raw);                                 // MODEL <= 2
+  float4* tab = reinterpret_cast<float4*>(smem_raw);                                   // MODEL >= 3
+  float2* tab2 = reinterpret_cast<float2*>(smem_raw + (size_t)J * 16);
+  unsigned char* q0 = smem_raw + csr_tab_bytes(J, NQ);
+  const size_t acc_bytes = align16((size_t)AW * J * 4);
   float* acc_all = reinterpret_cast<float*>(q0);
-  float* acc = reinterpret_cast<float*>(q0 + (size_t)(warp * NSUB + sub) * acc_bytes);   // [NQ][J], sub-warp-private
+  float* acc = reinterpret_cast<float*>(q0 + (size_t)(warp * NSUB + sub) * acc_bytes);   // [J][AW], sub-warp-private
 
   int ok = 1;
   for (int j = threadIdx.x; j < J; j += kUniThreads) {
     const float aj = MODEL >= 2 ? p.a[j] : 1.f;
     const float cj = MODEL >= 3 ? p.c[j] : 0.f;
     const float dj = MODEL == 4 ? p.d[j] : 1.f;
-    tab[j] = make_float4(-p.D * kLog2e * aj, -p.D * kLog2e * p.b[j], cj, dj - cj);
-    tab2[j] = make_float2(p.D * aj * (dj - cj), 1.f - dj);
+    if constexpr (MODEL <= 2) {
+      tabAB[j] = make_float2(-p.D * kLog2e * aj, -p.D * kLog2e * p.b[j]);
+    } else {
+      tab[j] = make_float4(-p.D * kLog2e * aj, -p.D * kLog2e * p.b[j], cj, dj - cj);
+      tab2[j] = make_float2(p.D * aj * (dj - cj), 1.f - dj);
+    }
     if (FAST) ok &= (cj >= 1e-3f) && (dj <= 1.f - 1e-3f) && (dj - cj >= 1e-3f);
   }
   for (int i = threadIdx.x; i < (int)(kUniWarps * NSUB * acc_bytes / 4); i += kUniThreads) acc_all[i] = 0.f;
@@ -86,81 +123,118 @@ __global__ void __launch_bounds__(kUniThreads) irt_uni_csr_kernel(const IrtUniPa
   const int64_t gwarp = (int64_t)blockIdx.x * kUniWarps + warp;
   const int64_t nwarps = (int64_t)gridDim.x * kUniWarps;
 
-  for (int64_t tile = gwarp; tile < ntiles; tile += nwarps) {
-    const int64_t b0 = tile * 32;
-    const int64_t bi = b0 + lane;
-    // ---- per lane: one person's variational inputs and its slice of the entry array -----------------------
-    float mu = 0.f, sg = 1.f, eps = 0.f;
-    int64_t beg_l = 0;
-    int cnt_l = 0;
-    const bool valid = bi < p.B;
-    if (valid) {
-      mu = p.mu[bi];
-      sg = p.sigma[bi];
-      const int64_t row = p.idx ? __ldg(p.idx + bi) : bi;
-      beg_l = __ldg(p.row_ptr + row);
-      cnt_l = (int)(__ldg(p.row_ptr + row + 1) - beg_l);
+  // one batch: this lane's entry `ent` (valid iff obs) of the person whose latent is x
+  float Gi, Lr;
+  auto batch = [&](uint32_t ent, bool obs, float x) {
+    const int j = (int)(ent & 0x7fffu);
+    if constexpr (MODEL <= 2) {
+      // lean 1PL / 2PL form: sign flip by XOR, one select puts an idle lane at t = -126 (sp = 1, 1 - sp = 0),
+      // the probability clamp is the min at t = 23 (sp = eps) with the gradient switched off beyond it
+      const float2 ab = tabAB[j];
+      const uint32_t flip = (~ent << 16) & 0x80000000u;                  // y == 0: negate
+      float t = __uint_as_float(__float_as_uint(fmaf(ab.x, x, ab.y)) ^ flip);
+      t = obs ? t : -126.f;
+      const float e = ex2_approx(fminf(t, 23.f));
+      const float sp = rcp_approx(e + 1.f);
+      const float w = t < 23.f ? e * sp : 0.f;
+      const float ws = __uint_as_float(__float_as_uint(w) ^ flip);
+      Gi = fmaf(ab.x, ws, Gi);
+      Lr *= sp;
+      if (obs && p.want_grad) {
+        if constexpr (NQ == 2) {
+          float2* ap = reinterpret_cast<float2*>(acc) + j;
+          float2 v = *ap;
+          v.x += ws;
+          v.y = fmaf(ws, x, v.y);
+          *ap = v;
+        } else {
+          acc[j] += ws;
+        }
+      }
+    } else {
+      const bool y1 = (ent & 0x8000u) != 0u;
+      const float4 it = tab[j];
+      const float2 it2 = tab2[j];
+      const float tt0 = fmaf(it.x, x, it.y);
+      const float t = y1 ? tt0 : -tt0;
+      const float base = y1 ? it.z : it2.y;
+      float w, a1, a2, qc;
+      if (FAST && use_fast) csr_cell<MODEL, true>(t, it.w, base, obs, w, a1, a2, qc);
+      else csr_cell<MODEL, false>(t, it.w, base, obs, w, a1, a2, qc);
+      const float ws = y1 ? w : -w;
+      Gi = fmaf(it2.x, ws, Gi);
+      Lr *= qc;
+      if (obs && p.want_grad) {
+        float4* ap = reinterpret_cast<float4*>(acc) + j;
+        float4 v = *ap;
+        v.x += ws;
+        v.y = fmaf(ws, x, v.y);
+        v.z += y1 ? a2 : -a1;
+        v.w += y1 ? a1 : -a2;
+        *ap = v;
+      }
     }
-    if (p.eps) eps = valid ? __ldg(p.eps + bi) : 0.f;
-    else eps = normal4(p.seed, p.offset, (uint64_t)(p.person_offset + bi), 0u).x;
-    const float x_l = fmaf(sg, eps, mu);
+  };
+
+  CsrLane cur = csr_lane(p, gwarp * 32 + lane);
+  for (int64_t tile = gwarp; tile < ntiles; tile += nwarps) {
+    const int64_t bi = tile * 32 + lane;
+    const CsrLane nxt = csr_lane(p, (tile + nwarps) * 32 + lane);     // next tile's inputs, in flight during this one
     float Gmine = 0.f, Ltile = 0.f;
 
-    // ---- SW rounds, NSUB persons per round; the first SW entries of the next round are loaded ahead -----
-    int pi = sub;
-    float x = __shfl_sync(0xffffffffu, x_l, pi);
-    int cnt = __shfl_sync(0xffffffffu, cnt_l, pi);
-    int64_t beg = __shfl_sync(0xffffffffu, beg_l, pi);
-    uint32_t ent = sl < cnt ? (uint32_t)__ldg(p.entries + beg + sl) : 0u;
+    // ---- SW rounds, NSUB persons per round; the first NBP batches of the next round are loaded ahead ------
+    float x = __shfl_sync(0xffffffffu, cur.x, sub);
+    int cnt = __shfl_sync(0xffffffffu, cur.cnt, sub);
+    const uint16_t* pe = p.entries + __shfl_sync(0xffffffffu, cur.beg, sub) + sl;
+    uint32_t ent[NBP];
+#pragma unroll
+    for (int b = 0; b < NBP; ++b) ent[b] = b * SW + sl < cnt ? (uint32_t)__ldg(pe + b * SW) : 0u;
 #pragma unroll 1
     for (int r = 0; r < SW; ++r) {
       const int pn = (r + 1 < SW ? (r + 1) * NSUB : 0) + sub;
-      const float xn = __shfl_sync(0xffffffffu, x_l, pn);
-      const int cntn = __shfl_sync(0xffffffffu, cnt_l, pn);
-      const int64_t begn = __shfl_sync(0xffffffffu, beg_l, pn);
-      const uint32_t entn = (r + 1 < SW && sl < cntn) ? (uint32_t)__ldg(p.entries + begn + sl) : 0u;
+      const float xn = __shfl_sync(0xffffffffu, cur.x, pn);
+      const int cntn = r + 1 < SW ? __shfl_sync(0xffffffffu, cur.cnt, pn) : 0;
+      const uint16_t* pen = p.entries + __shfl_sync(0xffffffffu, cur.beg, pn) + sl;
+      uint32_t entn[NBP];
+#pragma unroll
+      for (int b = 0; b < NBP; ++b) entn[b] = b * SW + sl < cntn ? (uint32_t)__ldg(pen + b * SW) : 0u;
 
-      float Gi = 0.f;
-      for (int t0 = 0; __any_sync(0xffffffffu, t0 < cnt); t0 += SW) {
+      int cmax = cnt;                                  // longest row among this round's NSUB persons
+#pragma unroll
+      for (int o = SW; o < 32; o <<= 1) cmax = max(cmax, __shfl_xor_sync(0xffffffffu, cmax, o));
+      Gi = 0.f;
+      Lr = 1.f;
+#pragma unroll
+      for (int b = 0; b < NBP; ++b)
+        if (b * SW < cmax) batch(ent[b], b * SW + sl < cnt, x);
+      Ltile += lg2_approx(Lr);                         // <= 3 factors >= eps each: no underflow
+      for (int t0 = NBP * SW; t0 < cmax; t0 += SW) {   // rows longer than the look-ahead
         const bool obs = t0 + sl < cnt;
-        if (t0 > 0) ent = obs ? (uint32_t)__ldg(p.entries + beg + t0 + sl) : 0u;
-        const int j = (int)(ent & 0x7fffu);
-        const bool y1 = (ent & 0x8000u) != 0u;
-        const float4 it = tab[j];
-        const float2 it2 = tab2[j];
-        const float tt0 = fmaf(it.x, x, it.y);
-        const float t = y1 ? tt0 : -tt0;
-        const float base = MODEL >= 3 ? (y1 ? it.z : it2.y) : 0.f;
-        float w, a1, a2, qc;
-        if (FAST && use_fast) csr_cell<MODEL, true>(t, it.w, base, obs, w, a1, a2, qc);
-        else csr_cell<MODEL, false>(t, it.w, base, obs, w, a1, a2, qc);
-        const float ws = y1 ? w : -w;
-        Gi = fmaf(it2.x, ws, Gi);
-        Ltile += lg2_approx(qc);
-        if (obs && p.want_grad) {
-          acc[j] += ws;
-          if constexpr (NQ >= 2) acc[J + j] = fmaf(ws, x, acc[J + j]);
-          if constexpr (NQ >= 3) acc[2 * J + j] += y1 ? a2 : -a1;
-          if constexpr (NQ >= 4) acc[3 * J + j] += y1 ? a1 : -a2;
-        }
+        Lr = 1.f;
+        batch(obs ? (uint32_t)__ldg(pe + t0) : 0u, obs, x);
+        Ltile += lg2_approx(Lr);
       }
-      __syncwarp();                                   // orders the accumulator updates of consecutive persons
+      __syncwarp();                                    // orders the accumulator updates of consecutive persons
 #pragma unroll
       for (int o = SW / 2; o > 0; o >>= 1) Gi += __shfl_xor_sync(0xffffffffu, Gi, o);
       const float v = __shfl_sync(0xffffffffu, Gi, (lane % NSUB) * SW);    // person r*NSUB + s was done by sub-warp s
       if (lane / NSUB == r) Gmine = v;
-      x = xn; cnt = cntn; beg = begn; ent = entn;
+      x = xn; cnt = cntn; pe = pen;
+#pragma unroll
+      for (int b = 0; b < NBP; ++b) ent[b] = entn[b];
     }
+    if constexpr (MODEL <= 2) Gmine *= -kLn2;          // D a = -A' / log2(e)
 
     float prior = 0.f;
-    if (valid) {
-      prior = -0.5f * x_l * x_l + 0.5f * eps * eps + logf(sg) + (float)(J - cnt_l) * kMaskedLogProb;
+    if (cur.valid) {
+      prior = -0.5f * cur.x * cur.x + 0.5f * cur.eps * cur.eps + logf(cur.sg) + (float)(J - cur.cnt) * kMaskedLogProb;
       if (p.d_mu) {
-        p.d_mu[bi] = -p.scale * (Gmine - x_l);
-        p.d_sigma[bi] = -p.scale * (Gmine - x_l) * eps - p.scale / sg;
+        p.d_mu[bi] = -p.scale * (Gmine - cur.x);
+        p.d_sigma[bi] = -p.scale * (Gmine - cur.x) * cur.eps - p.scale / cur.sg;
       }
     }
     loss_acc -= (double)(p.scale * fmaf(kLn2, Ltile, prior));
+    cur = nxt;
   }
 
   __shared__ double loss_sm[kUniWarps];
@@ -175,11 +249,14 @@ __global__ void __launch_bounds__(kUniThreads) irt_uni_csr_kernel(const IrtUniPa
   }
   if (p.want_grad) {
     for (int i = threadIdx.x; i < NQ * J; i += kUniThreads) {
+      const int q = i / J, j = i - q * J;
       float t = 0.f;
 #pragma unroll
-      for (int w = 0; w < kUniWarps * NSUB; ++w) t += acc_all[(size_t)w * (acc_bytes / 4) + i];
-      const int q = i / J, j = i - q * J;
-      if (q < 2) t *= p.D * tab[j].w;
+      for (int w = 0; w < kUniWarps * NSUB; ++w) t += acc_all[(size_t)w * (acc_bytes / 4) + j * AW + q];
+      if (q < 2) {
+        const float cj = MODEL >= 3 ? p.c[j] : 0.f, dj = MODEL == 4 ? p.d[j] : 1.f;
+        t *= p.D * (dj - cj);
+      }
       p.item_partial[(size_t)blockIdx.x * NQ * J + i] = t;
     }
   }

@@ -126,8 +126,14 @@ __device__ __forceinline__ void row_group_reduce(const float (&Gl)[kRowGroup], i
 // ---------------------------------------------------------------------------------------------------
 // dense
 // ---------------------------------------------------------------------------------------------------
+// register budget: measured on B200, 5-6 CTAs/SM beat both the unconstrained allocation (3-4 CTAs) and the
+// spilling 6-8 CTA one for the packed 1PL / 2PL path
+constexpr int row_min_ctas(int MODEL, int NP) {
+  if (MODEL > 2) return 1;
+  return NP == 1 ? 6 : NP == 2 ? 5 : 3;
+}
 template <int MODEL, int NP, bool FAST>
-__global__ void __launch_bounds__(kUniThreads) irt_uni_row_kernel(const IrtUniParams p) {
+__global__ void __launch_bounds__(kUniThreads, row_min_ctas(MODEL, NP)) irt_uni_row_kernel(const IrtUniParams p) {
   constexpr int NQ = MODEL;
   constexpr int JP = NP * 128;
   extern __shared__ __align__(16) unsigned char smem_raw[];
