@@ -95,6 +95,85 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+def other_configs(dev, peaks, flush, iters=5):
+    """Kernel-only device timings (CUDA events, L2 flushed between launches, inputs resident) of the other
+    BASELINE.json configurations, each with the roof that binds it.  Not the headline: context for it."""
+    import torch
+    from vipsy_b200 import ops, workloads
+    hbm = peaks["hbm_gbs"]
+    out = {}
+
+    def timed(fn):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        ms = []
+        for _ in range(iters):
+            flush.zero_()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            fn()
+            b.record()
+            torch.cuda.synchronize()
+            ms.append(a.elapsed_time(b))
+        return sum(ms) / len(ms)
+
+    off = [0]
+
+    def nxt():
+        off[0] += 1
+        return off[0]
+
+    # c1: lsat-shaped 2PL, 1000 x 5, S = 1 (launch-latency bound; two launches per evaluation)
+    w = workloads.uni_irt(1000, 5, "irt_2pl", seed=11, device=dev)
+    ms = timed(lambda: ops.irt_elbo_grad(w["y"], w["mu"], sigma=w["sigma"], n_particles=1, a=w["a"], b=w["b"],
+                                         model="irt_2pl", seed=1, offset=nxt()))
+    out["c1_lsat_shape_2pl_1000x5_S1"] = {"ms": ms, "evals_per_s": 5000 / ms * 1e3, "bound": "launch latency"}
+    del w
+
+    # c4: 2PL, 2M x 200, 90 % missing, S = 1, observed-cell CSR layout (built once, outside the timing)
+    w = workloads.uni_irt(2_000_000, 200, "irt_2pl", missing=0.9, seed=12, device=dev)
+    obs = ops.observed_csr(w["y"])
+    ms = timed(lambda: ops.irt_elbo_grad(w["y"], w["mu"], sigma=w["sigma"], n_particles=1, a=w["a"], b=w["b"],
+                                         model="irt_2pl", seed=1, offset=nxt(), obs=obs))
+    algo = 2 * obs[2] + 8 * 2_000_001 + 16 * 2_000_000      # entries + row_ptr + mu, sigma in + d_mu, d_sigma out
+    out["c4_2pl_2Mx200_90pct_missing_S1"] = {
+        "ms": ms, "nominal_cells_per_s": 4e8 / ms * 1e3, "observed_cells_per_s": obs[2] / ms * 1e3,
+        "layout": "CSR of observed cells, 2 B per response", "algorithmic_bytes": algo,
+        "roofline": {"bound": "hbm", "achieved": algo / ms / 1e6, "peak": hbm, "unit": "GB/s",
+                     "frac": algo / ms / 1e6 / hbm}}
+    ms32 = timed(lambda: ops.irt_elbo_grad(w["y"], w["mu"], sigma=w["sigma"], n_particles=32, a=w["a"], b=w["b"],
+                                           model="irt_2pl", seed=1, offset=nxt(), sparse=True))
+    out["c4_2pl_2Mx200_90pct_missing_S32"] = {"ms": ms32, "nominal_evals_per_s": 4e8 * 32 / ms32 * 1e3,
+                                              "observed_evals_per_s": obs[2] * 32 / ms32 * 1e3, "bound": "sfu"}
+    del w, obs
+
+    # c5: enumerated DINA and HO-DINA, 1M x 60, K = 10 (1024 patterns)
+    for hod in (False, True):
+        w = workloads.cdm(1_000_000, 60, 10, hodina=hod, seed=13, device=dev)
+        qm = ops.qmask_from_q(w["q"])
+        kw = dict(lam0=w["lam0"], lam1=w["lam1"], mu=w["mu"], sigma=w["sigma"], n_particles=1) if hod else {}
+        ms = timed(lambda: ops.cdm_enum_elbo_grad(w["y"], qm, w["g"], w["s"], n_attrs=10, seed=1, offset=nxt(), **kw))
+        out["c5_hodina_1Mx60_K10" if hod else "c5_dina_1Mx60_K10"] = {
+            "ms": ms, "person_item_pattern_per_s": 1e6 * 60 * 1024 / ms * 1e3, "bound": "fp32 add / sfu"}
+        del w
+
+    # c3: 2PL MIRT K = 100, 200k x 500, per-person packed Cholesky, S = 1 (tcgen05 contraction; HBM-bound by L)
+    n3 = 200_000
+    w = workloads.mirt(n3, 500, 100, seed=14, device=dev)
+    dchol = torch.zeros_like(w["chol_packed_raw"])
+    dmu = torch.empty_like(w["mu"])
+    ms = timed(lambda: ops.irt_elbo_grad(w["y"], w["mu"], chol=w["chol_packed_raw"], chol_packed=True, chol_raw=True,
+                                         n_particles=1, a=w["a"], b=w["b"], model="irt_2pl", a_free=w["a_free"],
+                                         seed=1, offset=nxt(), d_mu_out=dmu, d_scale_out=dchol))
+    algo = n3 * (500 + 8 * 100 + 8 * 5050)
+    out["c3_mirt_2pl_K100_200kx500_S1"] = {
+        "ms": ms, "evals_per_s": n3 * 500 / ms * 1e3, "algorithmic_bytes": algo,
+        "roofline": {"bound": "hbm", "achieved": algo / ms / 1e6, "peak": hbm, "unit": "GB/s",
+                     "frac": algo / ms / 1e6 / hbm}}
+    return out
+
+
 def run_ours(args, rank, world, local_rank):
     import torch
     import torch.distributed as dist
@@ -121,13 +200,14 @@ def run_ours(args, rank, world, local_rank):
     d_mu = torch.empty((N_PERSONS, 1), dtype=torch.float32, device=dev)
     d_sigma = torch.empty((N_PERSONS, 1), dtype=torch.float32, device=dev)
     state = {"offset": 0, "launches": 0}
+    n_masked = int((w["y"] == 255).sum().item())          # constant of the (fixed) response matrix, counted once
 
     def step():
         state["offset"] += 1
         r = ops.irt_elbo_grad(w["y"], w["mu"], sigma=w["sigma"], n_particles=N_PARTICLES, a=w["a"], b=w["b"],
                               c=w["c"], d=w["d"], model=MODEL, scale=scale, seed=20261017, offset=state["offset"],
-                              person_offset=person_offset, d_mu_out=d_mu, d_scale_out=d_sigma)
-        state["launches"] += 2                      # fused kernel + fixed-order finalize
+                              person_offset=person_offset, d_mu_out=d_mu, d_scale_out=d_sigma, n_masked=n_masked)
+        state["launches"] += 3                      # fused kernel + masked-cell constant + fixed-order finalize
         if world > 1:                               # item gradients + loss: the only exchange
             dist.all_reduce(r["item_grads"])
             dist.all_reduce(r["loss"])
@@ -175,15 +255,16 @@ def run_ours(args, rank, world, local_rank):
         a.record()
         ops.irt_elbo_grad(w["y"], w["mu"], sigma=w["sigma"], n_particles=N_PARTICLES, a=w["a"], b=w["b"],
                           c=w["c"], d=w["d"], model=MODEL, scale=scale, seed=1, offset=1000 + i,
-                          person_offset=person_offset, d_mu_out=d_mu, d_scale_out=d_sigma)
+                          person_offset=person_offset, d_mu_out=d_mu, d_scale_out=d_sigma, n_masked=n_masked)
         b.record()
     torch.cuda.synchronize()
     kms = [a.elapsed_time(b) for a, b in kev[:min(args.steps, 10)]]
     kernel_ms = sum(kms) / len(kms)
 
     # ---- e2e: host buffers in, host results out, every step -----------------
-    host = IrtHostStep(N_PERSONS, N_ITEMS, MODEL, n_chunks=8, device=dev)
-    hy = torch.empty(w["y"].shape, dtype=torch.uint8, pin_memory=True).copy_(w["y"])
+    host = IrtHostStep(N_PERSONS, N_ITEMS, MODEL, n_chunks=4, device=dev)
+    # responses in the 2-bit host transport format (4 cells per byte, packed once when the data are loaded)
+    hy = ops.pack_responses_2bit_host(w["y"].cpu(), pin=True)
     hmu = torch.empty(w["mu"].shape, dtype=torch.float32, pin_memory=True).copy_(w["mu"])
     hsg = torch.empty(w["sigma"].shape, dtype=torch.float32, pin_memory=True).copy_(w["sigma"])
     hp = {k: w[k].cpu() for k in ("a", "b", "c", "d")}
@@ -231,6 +312,7 @@ def run_ours(args, rank, world, local_rank):
 
     cpu_n = 20_000
     cpu_dt, cpu_threads = time_oracle(cpu_n, steps=3, warmup=1) if world == 1 else (None, None)
+    others = other_configs(dev, peaks, flush) if (world == 1 and not args.no_other_configs) else None
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -244,7 +326,8 @@ def run_ours(args, rank, world, local_rank):
                    "power_w_max": ck["power_w_max"]},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": host.h2d_bytes,
                 "d2h_bytes_per_step": host.d2h_bytes, "ms_per_step": e2e_s * 1e3,
-                "how": "vipsy_b200.host_api.IrtHostStep: pinned host y/mu/sigma -> 8-chunk 3-stream pipeline -> host grads"},
+                "how": "vipsy_b200.host_api.IrtHostStep: pinned host y (2-bit transport rows) / mu / sigma -> 4-chunk "
+                       "3-stream pipeline (copy, expand + fused kernel, copy back) -> host per-person and item grads + loss"},
         "gpu_launches": gpu_launches,
         "roofline": {"bound": "hbm", "achieved": achieved_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                      "frac": achieved_gbs / peaks["hbm_gbs"], "traffic": traffic, "peak_source": peaks_src,
@@ -256,6 +339,8 @@ def run_ours(args, rank, world, local_rank):
                          "peak_source": "148 SM x 16 lanes x sampled SM clock"},
         "wall_s_timed_region": t_wall, "loss_last_step": loss_val,
     }
+    if others is not None:
+        line["other_configs"] = others
     if cpu_dt is not None:
         line["cpu_baseline"] = {
             "value": cpu_n * N_ITEMS * N_PARTICLES / cpu_dt, "unit": UNIT, "cores": cpu_threads, "kind": "port",
@@ -270,6 +355,8 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-other-configs", action="store_true",
+                    help="skip the kernel-only timings of the other BASELINE configs (c1, c3, c4, c5)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     rank = int(os.environ.get("RANK", "0"))

@@ -60,8 +60,10 @@ enum { VIPSY_IRT_FLAG_STRICT = 1,
        VIPSY_IRT_FLAG_NO_TENSOR = 2,    /* K > 1: force the SIMT contraction (default: tcgen05 when K >= 8) */
        VIPSY_IRT_FLAG_SPARSE = 4,       /* K == 1 hint: most cells are missing -> per-person compaction of the
                                           observed cells (same results; pays off below ~50 % density)        */
-       VIPSY_IRT_FLAG_NO_ROW = 8 };     /* K == 1, S == 1: force the lane-per-person kernels (default: the
+       VIPSY_IRT_FLAG_NO_ROW = 8,       /* K == 1, S == 1: force the lane-per-person kernels (default: the
                                           warp-per-person row kernels when J % 4 == 0, 64 <= J <= 512)       */
+       VIPSY_IRT_FLAG_MASKED_KNOWN = 16 };/* n_masked_cells is valid: saves one counting pass over the batch rows
+                                          in the K == 1, S > 1 path (the matrix is constant between steps)   */
 enum { VIPSY_CHOL_DENSE = 0,  /* row-major K x K, strict upper triangle ignored        */
        VIPSY_CHOL_PACKED = 1 };/* torch.tril_indices row-major order, K(K+1)/2 (vi.py:453) */
 
@@ -127,6 +129,7 @@ typedef struct VipsyIrtArgs {
   const int64_t* obs_row_ptr;   /* n_rows + 1, or NULL                               */
   const uint16_t* obs_entries;  /* obs_nnz entries, or NULL                          */
   int64_t obs_nnz;              /* host copy of row_ptr[n_rows] (picks the lane mapping; 0 = unknown) */
+  int64_t n_masked_cells;       /* missing cells among the B batch rows (with VIPSY_IRT_FLAG_MASKED_KNOWN) */
 } VipsyIrtArgs;
 
 /* Bytes of workspace vipsy_irt_elbo_grad needs for these sizes (0 on bad args). */
@@ -218,6 +221,14 @@ int vipsy_cdm_score_elbo_grad(const VipsyCdmScoreArgs* args, void* stream);
  * ---------------------------------------------------------------------- */
 /* float response matrix with NaN = missing (the reference's `data`) -> codes */
 int vipsy_pack_responses(const float* y_f32, int64_t n_cells, uint8_t* codes, void* stream);
+/* 2-bit host transport format: byte i of a row = cells 4i..4i+3, two bits each (0, 1, 3 = missing), rows
+ * padded to (J+3)/4 bytes.  The packer runs on the HOST (both pointers are host memory; done once when the
+ * response matrix is loaded); the expander runs on the device, stream-ordered, after the packed rows were
+ * copied in -- 4x fewer PCIe bytes than the code matrix, 16x fewer than the NaN-coded float matrix. */
+int vipsy_pack_responses_2bit_host(const uint8_t* codes_host, int64_t n_rows, int32_t n_items, int64_t row_stride,
+                                   uint8_t* packed_host);
+int vipsy_unpack_responses_2bit(const uint8_t* packed, int64_t n_rows, int32_t n_items, uint8_t* codes,
+                                int64_t codes_row_stride, void* stream);
 /* CSR of the observed cells (the "2-byte per response" layout for mostly-missing matrices, J <= 32768).
  * Step 1 writes row_ptr[0..n_rows] (counts_scratch: n_rows int32 of scratch); the caller reads
  * row_ptr[n_rows] to size `entries`; step 2 writes entry = item | (response != 0) << 15 in item order. */

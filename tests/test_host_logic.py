@@ -142,3 +142,23 @@ def test_person_sharding_world2_gloo():
     ret = mgr.dict()
     mp.spawn(_worker, args=(world, _free_port(), ret), nprocs=world, join=True)
     assert all(ret.get(r) for r in range(world)), dict(ret)
+
+
+def test_two_bit_transport_packer_host():
+    """vipsy_pack_responses_2bit_host: 4 cells per byte, codes 0/1/255 -> 0/1/3, ragged last byte padded with 3."""
+    from vipsy_b200 import build, ops
+    build.build()
+    g = torch.Generator().manual_seed(3)
+    for J in (1, 4, 5, 100, 203):
+        codes = (torch.rand(37, J, generator=g) < 0.5).to(torch.uint8)
+        codes[torch.rand(37, J, generator=g) < 0.3] = 255
+        packed = ops.pack_responses_2bit_host(codes, pin=False)
+        assert packed.shape == (37, (J + 3) // 4)
+        pad = torch.full((37, 4 * packed.shape[1]), 255, dtype=torch.uint8)
+        pad[:, :J] = codes
+        two = (pad & 3).view(37, -1, 4).to(torch.int32)
+        want = two[..., 0] | (two[..., 1] << 2) | (two[..., 2] << 4) | (two[..., 3] << 6)
+        assert torch.equal(packed.to(torch.int32), want)
+    bad = torch.full((2, 8), 7, dtype=torch.uint8)
+    with pytest.raises(Exception):
+        ops.pack_responses_2bit_host(bad, pin=False)

@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "_lib", "libvipsy_b200.so")
+LIB_PATH = os.environ.get("VIPSY_B200_LIB") or os.path.join(HERE, "_lib", "libvipsy_b200.so")
 
 OK, ERR_ARG, ERR_UNSUPPORTED, ERR_WORKSPACE, ERR_CUDA = 0, -1, -2, -3, -4
 Y_MISSING = 255
@@ -22,6 +22,7 @@ IRT_FLAG_STRICT = 1
 IRT_FLAG_NO_TENSOR = 2
 IRT_FLAG_SPARSE = 4
 IRT_FLAG_NO_ROW = 8
+IRT_FLAG_MASKED_KNOWN = 16
 
 _p = C.c_void_p
 
@@ -44,7 +45,7 @@ class IrtArgs(C.Structure):
         ("loss", _p), ("d_mu", _p), ("d_sigma", _p), ("d_chol", _p),
         ("d_a", _p), ("d_b", _p), ("d_c", _p), ("d_d", _p),
         ("workspace", _p), ("workspace_bytes", C.c_size_t),
-        ("obs_row_ptr", _p), ("obs_entries", _p), ("obs_nnz", C.c_int64),
+        ("obs_row_ptr", _p), ("obs_entries", _p), ("obs_nnz", C.c_int64), ("n_masked_cells", C.c_int64),
     ]
 
 
@@ -84,6 +85,8 @@ SYMBOLS = {
     "vipsy_cdm_score_workspace_bytes": (C.c_size_t, [C.POINTER(CdmScoreArgs)]),
     "vipsy_cdm_score_elbo_grad": (C.c_int, [C.POINTER(CdmScoreArgs), _p]),
     "vipsy_pack_responses": (C.c_int, [_p, C.c_int64, _p, _p]),
+    "vipsy_pack_responses_2bit_host": (C.c_int, [_p, C.c_int64, C.c_int32, C.c_int64, _p]),
+    "vipsy_unpack_responses_2bit": (C.c_int, [_p, C.c_int64, C.c_int32, _p, C.c_int64, _p]),
     "vipsy_observed_row_ptr": (C.c_int, [_p, C.c_int64, C.c_int32, C.c_int64, _p, _p, _p]),
     "vipsy_observed_fill": (C.c_int, [_p, C.c_int64, C.c_int32, C.c_int64, _p, _p, _p]),
     "vipsy_cdm_eta_table": (C.c_int, [_p, C.c_int32, C.c_int32, C.c_int32, _p, _p]),
@@ -107,7 +110,7 @@ def lib():
         for name, (res, args) in SYMBOLS.items():
             fn = getattr(L, name)
             fn.restype, fn.argtypes = res, args
-        if L.vipsy_abi_version() != 2:
+        if L.vipsy_abi_version() != 2 and not os.environ.get("VIPSY_B200_LIB"):
             raise VipsyError(ERR_ARG, "ABI version mismatch")
         _lib = L
     return _lib

@@ -17,9 +17,72 @@
 // Arithmetic follows the reference's formulas: probability, clamp to
 // [eps, 1-eps], log, zero gradient where the clamp fires -- see item_evals().
 // Roof: 3-4 MUFU per (person, item, particle) evaluation => SFU-bound, not HBM.
+#include <algorithm>
+
 #include "irt_uni.cuh"
 
 namespace vipsy {
+
+// Masked cells score log(1 - eps) each (kMaskedLogProb) and nothing else.  The particle kernel sits at its
+// register cap (any extra work in it costs 3-5 % through re-planned register allocation, measured), so this
+// constant of the batch is produced by a side kernel: CTA b writes -scale * log(1-eps) * (masked cells of its
+// rows) as one more fp64 loss partial; integer counts, fixed order => deterministic.  With the count known to
+// the caller (the response matrix never changes between steps) one thread just writes it.
+constexpr int kMaskCtas = 296;
+__device__ __forceinline__ int missing_in(const int4& v) {      // codes are 0 / 1 / 255: bit 1 marks a missing cell
+  return __popc((uint32_t)v.x & 0x02020202u) + __popc((uint32_t)v.y & 0x02020202u) +
+         __popc((uint32_t)v.z & 0x02020202u) + __popc((uint32_t)v.w & 0x02020202u);
+}
+__global__ void __launch_bounds__(256) masked_term_kernel(const uint8_t* __restrict__ y, int64_t ld,
+                                                          const int64_t* __restrict__ idx, int64_t B, int J,
+                                                          float scale, int64_t known, double* __restrict__ out) {
+  if (known >= 0) {
+    if (threadIdx.x == 0) out[blockIdx.x] = blockIdx.x == 0 ? -(double)scale * (double)kMaskedLogProb * (double)known : 0.0;
+    return;
+  }
+  __shared__ long long part[8];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  long long n = 0;
+  if (idx == nullptr && ld == J) {
+    // contiguous batch: one flat byte range, 16-byte loads, four in flight per thread
+    const int64_t total = B * (int64_t)J;
+    const uintptr_t base = reinterpret_cast<uintptr_t>(y);
+    int64_t head = (int64_t)((16 - (base & 15)) & 15);
+    if (head > total) head = total;
+    const int64_t nvec = (total - head) >> 4;
+    const int4* v = reinterpret_cast<const int4*>(y + head);
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (int64_t)gridDim.x * blockDim.x;
+    int64_t i = tid;
+    for (; i + 3 * nth < nvec; i += 4 * nth) {
+      const int4 a = __ldg(v + i), b = __ldg(v + i + nth), c = __ldg(v + i + 2 * nth), d = __ldg(v + i + 3 * nth);
+      n += missing_in(a) + missing_in(b) + missing_in(c) + missing_in(d);
+    }
+    for (; i < nvec; i += nth) n += missing_in(__ldg(v + i));
+    if (blockIdx.x == 0) {
+      for (int64_t k = threadIdx.x; k < head; k += blockDim.x) n += y[k] == 255;
+      for (int64_t k = head + (nvec << 4) + threadIdx.x; k < total; k += blockDim.x) n += y[k] == 255;
+    }
+  } else {
+    for (int64_t r = (int64_t)blockIdx.x * 8 + warp; r < B; r += (int64_t)gridDim.x * 8) {
+      const uint8_t* g = y + (idx ? idx[r] : r) * ld;
+      if (((reinterpret_cast<uintptr_t>(g) | (uintptr_t)J) & 3) == 0) {
+        const uint32_t* gw = reinterpret_cast<const uint32_t*>(g);
+        for (int w = lane; w < (J >> 2); w += 32) n += __popc(__ldg(gw + w) & 0x02020202u);
+      } else {
+        for (int j = lane; j < J; j += 32) n += g[j] == 255;
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) n += __shfl_xor_sync(0xffffffffu, n, o);
+  if (lane == 0) part[warp] = n;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    long long t = 0;
+    for (int w = 0; w < 8; ++w) t += part[w];
+    out[blockIdx.x] = -(double)scale * (double)kMaskedLogProb * (double)t;
+  }
+}
 
 // MODEL: 1..4 (number of item parameters).  SCORE: REINFORCE estimator for the
 // guide parameters.  SC: particles kept in registers at once (S % SC == 0).
@@ -101,7 +164,6 @@ __global__ void __launch_bounds__(kUniThreads, 4) irt_uni_kernel(const IrtUniPar
     const float mu = valid ? p.mu[bi] : 0.f;
     const float sg = valid ? p.sigma[bi] : 1.f;
     float se = 0.f, see = 0.f, G1 = 0.f, G2 = 0.f, Lsum = 0.f, sw1 = 0.f, sw2 = 0.f;
-    int n_obs = 0;        // counted once per particle chunk; masked cells score log(1 - eps) each (kMaskedLogProb)
 
     for (int s0 = 0; s0 < p.S; s0 += SC) {
       // ---- noise for SC particles ----------------------------------------
@@ -158,7 +220,6 @@ __global__ void __launch_bounds__(kUniThreads, 4) irt_uni_kernel(const IrtUniPar
 #pragma unroll
         for (int q = 0; q < NQ; ++q) v[q] = 0.f;
         if (obs) {
-          ++n_obs;
           const float4 it = tab[j];
           const float2 it2 = tab2[j];
           const bool y1 = code != 0u;
@@ -212,8 +273,7 @@ __global__ void __launch_bounds__(kUniThreads, 4) irt_uni_kernel(const IrtUniPar
       const float sumx = fmaf(sg, se, S_f * mu);
       const float sumxe = fmaf(sg, see, mu * se);
       const float sumx2 = fmaf(S_f * mu, mu, fmaf(2.f * mu * sg, se, sg * sg * see));
-      const float elbo = kLn2 * Lsum - 0.5f * sumx2 + 0.5f * see + S_f * logf(sg) +
-                         (S_f * (float)J - (float)n_obs * (float)SC) * kMaskedLogProb;
+      const float elbo = kLn2 * Lsum - 0.5f * sumx2 + 0.5f * see + S_f * logf(sg);
       loss_acc -= (double)(k_scale * elbo);
       if (p.d_mu) {
         if (SCORE) {
@@ -301,9 +361,11 @@ static int launch_model(int model, bool fast, int SC, IrtUniParams& p, size_t sm
   }
 }
 
+static size_t uni_loss_rows() { return (size_t)num_sms() * kUniMaxCtasPerSM + kMaskCtas; }
+
 size_t irt_uni_workspace_bytes(const VipsyIrtArgs* a) {
   const int rows = num_sms() * kUniMaxCtasPerSM;
-  return align16((size_t)rows * 8) + (size_t)rows * a->model * a->n_items * 4;
+  return align16(uni_loss_rows() * 8) + (size_t)rows * a->model * a->n_items * 4;
 }
 
 int irt_uni_launch(const VipsyIrtArgs* a, cudaStream_t st) {
@@ -324,7 +386,7 @@ int irt_uni_launch(const VipsyIrtArgs* a, cudaStream_t st) {
   p.d_mu = a->d_mu; p.d_sigma = a->d_sigma;
   p.loss_partial = reinterpret_cast<double*>(a->workspace);
   p.item_partial = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(a->workspace) +
-                                            align16((size_t)num_sms() * kUniMaxCtasPerSM * 8));
+                                            align16(uni_loss_rows() * 8));
   p.contiguous = (a->idx == nullptr && a->y_row_stride == J) ? 1 : 0;
   p.want_grad = (a->d_b || a->d_a || a->d_c || a->d_d) ? 1 : 0;
   p.row_ptr = a->obs_row_ptr; p.entries = a->obs_entries;
@@ -337,16 +399,26 @@ int irt_uni_launch(const VipsyIrtArgs* a, cudaStream_t st) {
   const bool sparse = (a->flags & VIPSY_IRT_FLAG_SPARSE) && a->estimator == VIPSY_EST_PATHWISE && J < 32768 &&
                       irt_uni_sparse_smem_bytes(J, NQ) <= 227 * 1024;
   const bool want_sparse = (a->flags & VIPSY_IRT_FLAG_SPARSE) && a->estimator == VIPSY_EST_PATHWISE;
+  int mask_rows = 0;        // extra loss partials written by masked_term_kernel (lane-per-person dense kernel only)
   if (irt_uni_csr_supported(a))
     rc = irt_uni_csr_launch(a, fast, p, st, &grid);                          // S == 1 over the observed-cell CSR
   else if (!(a->flags & VIPSY_IRT_FLAG_NO_ROW) && irt_uni_row_supported(a, want_sparse))
     rc = irt_uni_row_launch(a->model, fast, want_sparse, p, st, &grid);     // S == 1: warp per person
   else if (sparse)
     rc = irt_uni_sparse_launch(a->model, fast, SC, p, st, &grid);
-  else
+  else {
     rc = a->estimator == VIPSY_EST_SCORE ? launch_model<true>(a->model, fast, SC, p, smem, st, &grid)
                                          : launch_model<false>(a->model, fast, SC, p, smem, st, &grid);
+    mask_rows = (a->flags & VIPSY_IRT_FLAG_MASKED_KNOWN) ? 1 : (int)std::min<int64_t>(kMaskCtas, (a->batch + 63) / 64);
+    if (mask_rows < 1) mask_rows = 1;
+  }
   if (rc != VIPSY_OK) return rc;
+  if (mask_rows) {
+    const int64_t known = (a->flags & VIPSY_IRT_FLAG_MASKED_KNOWN) ? a->n_masked_cells : -1;
+    masked_term_kernel<<<mask_rows, 256, 0, st>>>(a->y, a->y_row_stride, a->idx, a->batch, J, a->scale, known,
+                                                  p.loss_partial + grid);
+    VIPSY_CUDA_CHECK(cudaGetLastError());
+  }
 
   FinalizeSegs segs{};
   segs.n = NQ;
@@ -354,7 +426,7 @@ int irt_uni_launch(const VipsyIrtArgs* a, cudaStream_t st) {
   for (int q = 0; q < NQ; ++q) { segs.out[q] = outs[q]; segs.cols[q] = J; segs.mask[q] = nullptr; }
   if (NQ >= 2) segs.mask[1] = a->a_free;
   return launch_finalize(p.want_grad ? p.item_partial : nullptr, p.want_grad ? grid : 0, p.want_grad ? NQ * J : 0,
-                         -a->scale / (float)a->n_particles, segs, p.loss_partial, grid, a->loss, st);
+                         -a->scale / (float)a->n_particles, segs, p.loss_partial, grid + mask_rows, a->loss, st);
 }
 
 }  // namespace vipsy

@@ -2,6 +2,10 @@
 ``loss_and_grads(model, guide, data)`` (vi.py:507) calls when the response
 matrix and the variational parameters live in (pinned) host memory.
 
+The response matrix may be handed over in the 2-bit transport format of
+``ops.pack_responses_2bit_host`` (4 cells per byte; packed once when the data are
+loaded): the chunk is expanded to byte codes on the device right after its copy.
+
 The persons are cut into chunks; chunk i+1's host->device copy and chunk i-1's
 device->host copy of the per-person gradients overlap chunk i's kernel on three
 CUDA streams.  Item-level gradients and the loss are accumulated on the device
@@ -26,6 +30,7 @@ class IrtHostStep:
         self.bounds = [(s, min(s + per, n_persons)) for s in range(0, n_persons, per)]
         d = self.dev
         self.y = torch.empty((n_persons, n_items), dtype=torch.uint8, device=d)
+        self.y2 = None                                # device staging of 2-bit rows, allocated on first use
         self.mu = torch.empty((n_persons, 1), dtype=torch.float32, device=d)
         self.sigma = torch.empty((n_persons, 1), dtype=torch.float32, device=d)
         self.d_mu = torch.empty((n_persons, 1), dtype=torch.float32, device=d)
@@ -43,8 +48,15 @@ class IrtHostStep:
     def __call__(self, y: torch.Tensor, mu: torch.Tensor, sigma: torch.Tensor, a, b, c=None, d=None, *,
                  n_particles: int = 1, D: float = 1.0, scale: float = 1.0, seed: int = 0, offset: int = 0,
                  person_offset: int = 0, estimator: str = "pathwise", baseline: float = 0.0) -> Dict[str, torch.Tensor]:
-        """All tensor arguments are HOST tensors (y: uint8 codes; pinned for async copies)."""
+        """All tensor arguments are HOST tensors (pinned for async copies).  y: N x J uint8 codes, or
+        N x ceil(J/4) uint8 rows in the 2-bit transport format."""
         J = self.J
+        packed = y.shape[1] != J
+        if packed:
+            if y.shape[1] != (J + 3) // 4:
+                raise ValueError("y must be N x J codes or N x ceil(J/4) 2-bit rows")
+            if self.y2 is None:
+                self.y2 = torch.empty((self.N, (J + 3) // 4), dtype=torch.uint8, device=self.dev)
         cur = torch.cuda.current_stream(self.dev)
         for s in (self.s_in, self.s_run, self.s_out):
             s.wait_stream(cur)
@@ -61,19 +73,25 @@ class IrtHostStep:
         for (s, e) in self.bounds:
             ev_in, ev_run = torch.cuda.Event(), torch.cuda.Event()
             with torch.cuda.stream(self.s_in):
-                self.y[s:e].copy_(y[s:e], non_blocking=True)
+                if packed:
+                    self.y2[s:e].copy_(y[s:e], non_blocking=True)
+                else:
+                    self.y[s:e].copy_(y[s:e], non_blocking=True)
                 self.mu[s:e].copy_(mu[s:e], non_blocking=True)
                 self.sigma[s:e].copy_(sigma[s:e], non_blocking=True)
                 ev_in.record()
-                h2d += (e - s) * (J + 8)
+                h2d += (e - s) * (y.shape[1] + 8)
             with torch.cuda.stream(self.s_run):
                 self.s_run.wait_event(ev_in)
+                if packed:
+                    ops.unpack_responses_2bit(self.y2[s:e], J, out=self.y[s:e])
+                    self.kernel_launches += 1
                 r = ops.irt_elbo_grad(self.y[s:e], self.mu[s:e], sigma=self.sigma[s:e], n_particles=n_particles,
                                       a=self.items[1], b=self.items[0], c=self.items[2], d=self.items[3],
                                       model=self.model, D=D, scale=scale, seed=seed, offset=offset,
                                       person_offset=person_offset + s, estimator=estimator, baseline=baseline,
                                       d_mu_out=self.d_mu[s:e], d_scale_out=self.d_sigma[s:e])
-                self.kernel_launches += 2
+                self.kernel_launches += 3
                 if item_acc is None:
                     item_acc, loss_acc = r["item_grads"], r["loss"]
                 else:

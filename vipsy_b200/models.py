@@ -113,7 +113,8 @@ class BasePsy(nn.Module):               # vi.py:521-533
         self._data_dev = data.to(self.device, torch.float32)
         self._codes = ops.pack_responses(self._data_dev)        # uint8 0/1/255, stays resident
         # mostly-missing matrices take the compaction path of the K = 1 kernel (same results)
-        self._sparse = bool((self._codes == 255).float().mean() > 0.5) if self._codes.numel() else False
+        self._n_missing = int((self._codes == 255).sum().item()) if self._codes.numel() else 0
+        self._sparse = self._n_missing > 0.5 * self._codes.numel()
         self._obs_csr = None          # CSR of the observed cells, built on first use (K = 1, S = 1 path)
         self._seed, self._calls = int(seed), 0
         # optional person sharding (vipsy_b200.dist.attach): this rank holds rows
@@ -236,6 +237,7 @@ class BaseIRT(BasePsy):                 # vi.py:536-656
                                   c=items["c"][1] if "c" in items else None, d=items["d"][1] if "d" in items else None,
                                   idx=idx, a_free=self._a_free_dev, estimator=cfg.estimator, baseline=cfg.baseline,
                                   want_grad=want_grad, sparse=self._sparse and self.x_feature == 1,
+                                  n_masked=self._n_missing if idx is None else None,
                                   obs=self._observed_csr() if (self._sparse and self.x_feature == 1 and s == 1) else None,
                                   **gkw, **self._noise_args())
             w = 1.0 / len(groups)

@@ -58,6 +58,29 @@ def pack_responses(y: torch.Tensor) -> torch.Tensor:
     return out
 
 
+def pack_responses_2bit_host(codes: torch.Tensor, pin: bool = True) -> torch.Tensor:
+    """HOST uint8 code matrix (0/1/255) -> HOST 2-bit transport format, n_rows x ceil(J/4) bytes (done once)."""
+    if codes.is_cuda or codes.dtype != torch.uint8 or codes.dim() != 2 or codes.stride(1) != 1:
+        raise ValueError("codes must be a host uint8 matrix with unit column stride")
+    n_rows, J = codes.shape
+    out = torch.empty((n_rows, (J + 3) // 4), dtype=torch.uint8, pin_memory=pin)
+    N.check(N.lib().vipsy_pack_responses_2bit_host(codes.data_ptr(), n_rows, J, codes.stride(0), out.data_ptr()))
+    return out
+
+
+def unpack_responses_2bit(packed: torch.Tensor, n_items: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """DEVICE 2-bit rows -> uint8 code matrix (stream-ordered)."""
+    if not packed.is_cuda or packed.dtype != torch.uint8 or packed.dim() != 2 or not packed.is_contiguous():
+        raise ValueError("packed must be a contiguous CUDA uint8 matrix")
+    n_rows = packed.shape[0]
+    if packed.shape[1] != (n_items + 3) // 4:
+        raise ValueError("packed rows must hold ceil(J/4) bytes")
+    if out is None:
+        out = torch.empty((n_rows, n_items), dtype=torch.uint8, device=packed.device)
+    N.check(N.lib().vipsy_unpack_responses_2bit(_ptr(packed), n_rows, n_items, _ptr(out), out.stride(0), _stream()))
+    return out
+
+
 def observed_csr(y: torch.Tensor):
     """uint8 code matrix -> (row_ptr int64[n_rows+1], entries uint16[nnz], nnz): the observed cells only,
     entry = item | response << 15.  Built once per response matrix (the matrix is constant across SVI steps);
@@ -118,7 +141,7 @@ def irt_elbo_grad(
     chol_packed: bool = False, chol_raw: bool = False,
     seed: int = 0, offset: int = 0, person_offset: int = 0,
     want_grad: bool = True, strict: bool = False, tensor_cores: bool = True, sparse: bool = False,
-    row_kernel: bool = True, obs=None,
+    row_kernel: bool = True, obs=None, n_masked: Optional[int] = None,
     d_mu_out: Optional[torch.Tensor] = None, d_scale_out: Optional[torch.Tensor] = None,
 ) -> Dict[str, Optional[torch.Tensor]]:
     """One fused ELBO + gradient evaluation (Trace_ELBO.loss_and_grads, vi.py:507).
@@ -128,6 +151,7 @@ def irt_elbo_grad(
     forces the SIMT contraction for K > 1 (default: tcgen05 for K >= 8).  ``sparse=True`` (K == 1)
     tells the kernel most cells are missing: it compacts each person's observed cells first.
     ``obs``: the (row_ptr, entries, nnz) triple of ``observed_csr(y)``; used by the K == 1, S == 1 path.
+    ``n_masked``: number of missing cells among the batch rows, if the caller knows it (saves a counting pass).
     ``row_kernel=False`` (K == 1, S == 1) forces the lane-per-person kernels instead of the warp-per-person ones."""
     if not y.is_cuda or y.dtype != torch.uint8:
         raise ValueError("y must be a CUDA uint8 code matrix (see pack_responses)")
@@ -155,6 +179,9 @@ def irt_elbo_grad(
     args.flags = (N.IRT_FLAG_STRICT if strict else 0) | (0 if tensor_cores else N.IRT_FLAG_NO_TENSOR) \
         | (N.IRT_FLAG_SPARSE if sparse else 0) | (0 if row_kernel else N.IRT_FLAG_NO_ROW)
     args.y, args.y_row_stride = _ptr(y), y.stride(0)
+    if n_masked is not None:
+        args.flags |= N.IRT_FLAG_MASKED_KNOWN
+        args.n_masked_cells = int(n_masked)
     if obs is not None:
         rp, en, nnz = obs
         if rp.numel() != n_rows + 1 or rp.dtype != torch.int64 or en.dtype != torch.uint16:
