@@ -245,6 +245,34 @@ int vipsy_fill_normal(float* out, int32_t n_particles, int64_t batch, int32_t n_
 int vipsy_fill_uniform(float* out, int32_t n_particles, int64_t batch, int32_t n_dims,
                        uint64_t seed, uint64_t offset, int64_t person_offset, void* stream);
 
+/* Same generators with the call counter read from device memory (offset = *offset_dev at execution time): a
+ * captured CUDA graph of the whole SVI iteration draws fresh noise on every replay. */
+int vipsy_fill_normal_dev(float* out, int32_t n_particles, int64_t batch, int32_t n_dims, uint64_t seed,
+                          const uint64_t* offset_dev, int64_t person_offset, void* stream);
+int vipsy_fill_uniform_dev(float* out, int32_t n_particles, int64_t batch, int32_t n_dims, uint64_t seed,
+                           const uint64_t* offset_dev, int64_t person_offset, void* stream);
+
+/* ------------------------------------------------------------------------
+ * The tail of the patched SVI.step (vi.py:508-515) on the device: multiply the gradient by the site's `free`
+ * mask (vi.py:511-512), torch.optim.Adam's default update (one state per parameter tensor, as pyro.optim.Adam
+ * keeps them), zero the gradient (vi.py:515) -- one launch for all parameter tensors of the step.
+ * *step_dev is the optimiser's global step count AFTER this step's increment; a tensor that joined later has
+ * step_offset > 0.  lr_dev (optional) overrides lr so that schedulers work under CUDA-graph replay.
+ * ---------------------------------------------------------------------- */
+typedef struct VipsyAdamTensor {
+  float* param;              /* unconstrained values, updated in place     */
+  float* grad;               /* gradient, zeroed when zero_grad != 0       */
+  float* exp_avg;            /* first moment                               */
+  float* exp_avg_sq;         /* second moment                              */
+  const uint8_t* free_mask;  /* 0/1 per element or NULL                    */
+  const float* lr_dev;       /* device learning rate or NULL               */
+  int64_t n;                 /* elements                                   */
+  int64_t step_offset;       /* global steps taken before this tensor's first */
+  float lr, beta1, beta2, eps;
+} VipsyAdamTensor;
+int vipsy_adam_step(const VipsyAdamTensor* tensors_host, int32_t n_tensors, const int64_t* step_dev,
+                    int32_t zero_grad, void* stream);
+
 /* ------------------------------------------------------------------------
  * Diagnostics: one 128-row tcgen05 tile product per operand orientation of the
  * tensor-core MIRT kernel (fp16 hi/lo split, fp32 accumulation in TMEM).

@@ -179,3 +179,125 @@ def test_host_step_two_bit_transport_matches_device_call():
         assert float(got["loss"]) == float(ref["loss"])
     assert host.h2d_bytes == N * (25 + 8) + 4 * J * 4
     assert torch.equal(ops.unpack_responses_2bit(ops.pack_responses_2bit_host(hy).cuda(), J).cpu(), hy)
+
+
+# ---- device-resident iteration: fused Adam, device RNG counters, CUDA graph ----------------
+def test_fused_adam_matches_torch_adam():
+    from vipsy_b200 import ops
+    torch.manual_seed(0)
+    shapes = [(7, 13), (1, 5), (1000, 1)]
+    ps = [torch.randn(s, device="cuda") for s in shapes]
+    ref = [p.clone().requires_grad_(True) for p in ps]
+    opts = [torch.optim.Adam([r], lr=lr) for r, lr in zip(ref, (1e-2, 5e-2, 1e-3))]
+    free = (torch.rand(shapes[0], device="cuda") < 0.7)
+    st = [dict(param=p, exp_avg=torch.zeros_like(p), exp_avg_sq=torch.zeros_like(p), lr=lr, beta1=0.9, beta2=0.999,
+               eps=1e-8, step_offset=0) for p, lr in zip(ps, (1e-2, 5e-2, 1e-3))]
+    st[0]["free_mask"] = free.to(torch.uint8)
+    st[1]["lr_dev"] = torch.full((1,), 5e-2, device="cuda")          # device learning rate overrides lr
+    st[1]["lr"] = 123.0
+    step = torch.zeros(1, dtype=torch.int64, device="cuda")
+    for it in range(6):
+        gs = [torch.randn(s, device="cuda") * (it + 1) for s in shapes]
+        for r, g, o_ in zip(ref, gs, opts):
+            r.grad = (g * free if r.shape == free.shape else g).clone()
+            o_.step()
+        for t, g in zip(st, gs):
+            t["grad"] = g.clone()
+        step.add_(1)
+        ops.adam_step(st, step)
+    for p, r in zip(ps, ref):
+        assert_close(p, r.detach(), 2e-6, 2e-6, "param")
+
+
+def test_fill_normal_device_counter_is_the_same_stream():
+    from vipsy_b200 import ops
+    ctr = torch.tensor([41], dtype=torch.int64, device="cuda")
+    a = ops.fill_normal(3, 50, 4, seed=9, offset=41)
+    b = ops.fill_normal(3, 50, 4, seed=9, offset=ctr)
+    assert torch.equal(a, b)
+    ctr.add_(1)
+    assert torch.equal(ops.fill_uniform(2, 10, 3, seed=9, offset=42), ops.fill_uniform(2, 10, 3, seed=9, offset=ctr))
+
+
+def _fit_pair(make, steps, **fit_kw):
+    """The same fit twice -- eager torch.optim objects vs the captured device-resident iteration."""
+    out = []
+    for graph in (False, True):
+        vb.clear_param_store()
+        torch.manual_seed(3)
+        m = make()
+        m._device_rng = True            # both runs draw noise through the device counter: identical streams
+        losses = []
+        svi = infer.SVI(m.model, m.guide, optim=fit_kw["optim"](), loss=fit_kw["loss"], cuda_graph=graph)
+        for _ in range(steps):
+            losses.append(svi.step(m.data))
+        out.append((losses, {n: vb.get_param_store().get(n).clone() for n in vb.get_param_store().names()}))
+    return out
+
+
+def test_cuda_graph_step_equals_eager_virt_4pl():
+    g = torch.Generator().manual_seed(0)
+    y = (torch.rand(600, 24, generator=g) < 0.6).float()
+    y[torch.rand(600, 24, generator=g) < 0.1] = float("nan")
+    (le, pe), (lg, pg) = _fit_pair(lambda: vb.VIRT(data=y, model="irt_4pl", seed=4), 12,
+                                   optim=lambda: vb.Adam({"lr": 2e-2}), loss=vb.Trace_ELBO(num_particles=2))
+    assert np.allclose(le, lg, rtol=2e-5), (le, lg)
+    for n in pe:
+        assert_close(pg[n], pe[n], 1e-4, 1e-4, n)
+    assert lg[-1] < lg[0]
+
+
+def test_cuda_graph_step_equals_eager_vaeirt_mirt_with_scheduler():
+    """Encoder forward + backward inside the captured graph, staircase free mask, MultiStepLR through lr_dev."""
+    g = torch.Generator().manual_seed(1)
+    y = (torch.rand(300, 40, generator=g) < 0.5).float()
+    sched = lambda: vb.MultiStepLR({"optimizer": torch.optim.Adam, "optim_args": {"lr": 1e-2}, "milestones": [4, 8],
+                                    "gamma": 0.5})
+    out = []
+    for graph in (False, True):
+        vb.clear_param_store()
+        torch.manual_seed(3)
+        m = vb.VaeIRT(data=y, model="irt_2pl", x_feature=3, hidden_dim=8, seed=4)
+        m._device_rng = True
+        opt = sched()
+        svi = infer.SVI(m.model, m.guide, optim=opt, loss=vb.Trace_ELBO(num_particles=1), cuda_graph=graph)
+        losses = []
+        for _ in range(12):
+            losses.append(svi.step(m.data))
+            opt.step()
+        out.append((losses, vb.param("a").clone(), [p.detach().clone() for p in m.encoder.parameters()]))
+    (le, ae, ee), (lg, ag, eg) = out
+    assert np.allclose(le, lg, rtol=1e-4), (le, lg)
+    assert_close(ag, ae, 1e-3, 1e-3, "a")
+    assert float(ag[2, -1]) == 0.0 and float(ag[1, -1]) == 0.0          # frozen staircase entries never move
+    for x, r in zip(eg, ee):
+        assert_close(x, r, 2e-3, 2e-3, "encoder")
+
+
+def test_cuda_graph_minibatch_fit_lsat(golden):
+    """The reference's default usage shape: subsample_size < N, many cheap iterations, one graph launch each;
+    fresh minibatch and noise on every replay (the fit converges to the literature estimates)."""
+    y = lsat(golden)
+    torch.manual_seed(0)
+    m = vb.VIRT(data=y, model="irt_2pl", subsample_size=250)
+    m.fit(optim=vb.Adam({"lr": 5e-2}), loss=vb.Trace_ELBO(num_particles=1), max_iter=3000, cuda_graph=True)
+    b = vb.param("b").cpu().reshape(-1)
+    assert torch.allclose(b, torch.tensor([2.72, 0.95, 0.21, 1.24, 2.01]), atol=0.45), b
+
+
+@pytest.mark.parametrize("cls", ["VCDM", "VCCDM", "VCHoDina", "VaeCHoDina"])
+def test_cuda_graph_cdm_families(cls):
+    g = torch.Generator().manual_seed(2)
+    K, J, N = 3, 20, 400
+    q = (torch.rand(K, J, generator=g) < 0.5).float()
+    q[0, q.sum(0) == 0] = 1.0
+    y = (torch.rand(N, J, generator=g) < 0.5).float()
+    res = []
+    for graph in (False, True):
+        vb.clear_param_store()
+        torch.manual_seed(3)
+        m = getattr(vb, cls)(data=y, q=q, seed=2, **({"hidden_dim": 8} if cls.startswith("Vae") else {}))
+        m._device_rng = True
+        svi = infer.SVI(m.model, m.guide, optim=vb.Adam({"lr": 1e-2}), loss=m._default_loss() if hasattr(m, "_default_loss") else vb.TraceEnum_ELBO(), cuda_graph=graph)
+        res.append([svi.step(m.data) for _ in range(8)])
+    assert np.allclose(res[0], res[1], rtol=1e-4), res

@@ -74,6 +74,14 @@ class CdmScoreArgs(C.Structure):
     ]
 
 
+class AdamTensor(C.Structure):
+    _fields_ = [
+        ("param", _p), ("grad", _p), ("exp_avg", _p), ("exp_avg_sq", _p), ("free_mask", _p), ("lr_dev", _p),
+        ("n", C.c_int64), ("step_offset", C.c_int64),
+        ("lr", C.c_float), ("beta1", C.c_float), ("beta2", C.c_float), ("eps", C.c_float),
+    ]
+
+
 # every symbol include/vipsy_b200.h declares: name -> (restype, argtypes)
 SYMBOLS = {
     "vipsy_abi_version": (C.c_int, []),
@@ -91,6 +99,9 @@ SYMBOLS = {
     "vipsy_observed_fill": (C.c_int, [_p, C.c_int64, C.c_int32, C.c_int64, _p, _p, _p]),
     "vipsy_cdm_eta_table": (C.c_int, [_p, C.c_int32, C.c_int32, C.c_int32, _p, _p]),
     "vipsy_fill_normal": (C.c_int, [_p, C.c_int32, C.c_int64, C.c_int32, C.c_uint64, C.c_uint64, C.c_int64, _p]),
+    "vipsy_fill_normal_dev": (C.c_int, [_p, C.c_int32, C.c_int64, C.c_int32, C.c_uint64, _p, C.c_int64, _p]),
+    "vipsy_fill_uniform_dev": (C.c_int, [_p, C.c_int32, C.c_int64, C.c_int32, C.c_uint64, _p, C.c_int64, _p]),
+    "vipsy_adam_step": (C.c_int, [C.POINTER(AdamTensor), C.c_int32, _p, C.c_int32, _p]),
     "vipsy_selftest_umma": (C.c_int, [_p, C.c_int32, C.c_int32, _p, C.c_int32, C.c_int32, _p, C.c_int32, C.c_int32,
                                       C.c_int32, _p]),
     "vipsy_fill_uniform": (C.c_int, [_p, C.c_int32, C.c_int64, C.c_int32, C.c_uint64, C.c_uint64, C.c_int64, _p]),

@@ -164,7 +164,8 @@ __global__ void eta_table_kernel(const uint32_t* __restrict__ qmask, int J, int 
 
 template <bool NORMAL>
 __global__ void fill_noise_kernel(float* __restrict__ out, int S, int64_t B, int K, uint64_t seed,
-                                  uint64_t offset, int64_t person_offset) {
+                                  uint64_t offset, int64_t person_offset, const uint64_t* __restrict__ offset_dev) {
+  if (offset_dev) offset += *offset_dev;      // CUDA-graph replays: the call counter lives in device memory
   if (NORMAL && K > 32 && K <= 128) {         // the 32 < K <= 128 layout of noise_coord(): one element per thread
     const int64_t total = (int64_t)S * B * K;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
@@ -199,6 +200,43 @@ __global__ void fill_noise_kernel(float* __restrict__ out, int S, int64_t B, int
         out[(s * B + b) * K + k] = zz[e];
       }
     }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Multi-tensor Adam with the patched SVI.step's extras folded in (vi.py:508-515): the `free` mask multiplies the
+// gradient (vi.py:511-512), torch.optim.Adam's default update follows (no weight decay, no amsgrad:
+// pyro.optim.Adam), the gradient is zeroed (vi.py:515).  One launch for every parameter of the
+// step; the step count and the learning rates may live in device memory so that a CUDA graph of the whole
+// iteration can be replayed.
+// ---------------------------------------------------------------------------
+constexpr int kAdamMaxTensors = 24;
+struct AdamBatch {
+  VipsyAdamTensor t[kAdamMaxTensors];
+  int n;
+};
+
+__global__ void __launch_bounds__(256) adam_kernel(const AdamBatch b, const int64_t* __restrict__ step_dev, int zero_grad) {
+  const VipsyAdamTensor t = b.t[blockIdx.y];
+  const int64_t step = *step_dev - t.step_offset;       // this tensor's own step count, >= 1
+  if (step < 1) return;
+  const float lr = t.lr_dev ? *t.lr_dev : t.lr;
+  // torch.optim.Adam (single-tensor form): step_size = lr / (1 - b1^t); denom = sqrt(v) / sqrt(1 - b2^t) + eps
+  const double bc1 = 1.0 - pow((double)t.beta1, (double)step);
+  const double bc2 = 1.0 - pow((double)t.beta2, (double)step);
+  const float step_size = (float)((double)lr / bc1);
+  const float inv_sqrt_bc2 = (float)(1.0 / sqrt(bc2));
+  const float b1 = t.beta1, b2 = t.beta2, omb1 = 1.f - t.beta1, omb2 = 1.f - t.beta2;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < t.n; i += (int64_t)gridDim.x * blockDim.x) {
+    float g = t.grad[i];
+    if (t.free_mask && !t.free_mask[i]) g = 0.f;
+    const float m = fmaf(b1, t.exp_avg[i], omb1 * g);             // lerp(m, g, 1 - b1)
+    const float v = fmaf(b2, t.exp_avg_sq[i], omb2 * g * g);
+    t.exp_avg[i] = m;
+    t.exp_avg_sq[i] = v;
+    const float denom = sqrtf(v) * inv_sqrt_bc2 + t.eps;
+    t.param[i] -= step_size * (m / denom);
+    if (zero_grad) t.grad[i] = 0.f;
   }
 }
 
@@ -275,16 +313,16 @@ int vipsy_cdm_eta_table(const uint32_t* qmask, int32_t n_items, int32_t n_attrs,
 }
 
 static int fill_noise(bool normal, float* out, int32_t S, int64_t B, int32_t K, uint64_t seed,
-                      uint64_t offset, int64_t person_offset, void* stream) {
+                      uint64_t offset, int64_t person_offset, void* stream, const uint64_t* offset_dev = nullptr) {
   VIPSY_REQUIRE(out && S > 0 && B >= 0 && K > 0, VIPSY_ERR_ARG, "vipsy_fill_*: bad argument");
   if (B == 0) return VIPSY_OK;
   const int64_t total = B * (((int64_t)S * K + 3) / 4);
   int64_t blocks = (total + 255) / 256;
   if (blocks > num_sms() * 8) blocks = num_sms() * 8;
   if (normal)
-    fill_noise_kernel<true><<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(out, S, B, K, seed, offset, person_offset);
+    fill_noise_kernel<true><<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(out, S, B, K, seed, offset, person_offset, offset_dev);
   else
-    fill_noise_kernel<false><<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(out, S, B, K, seed, offset, person_offset);
+    fill_noise_kernel<false><<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(out, S, B, K, seed, offset, person_offset, offset_dev);
   VIPSY_CUDA_CHECK(cudaGetLastError());
   return VIPSY_OK;
 }
@@ -296,6 +334,39 @@ int vipsy_fill_normal(float* out, int32_t S, int64_t B, int32_t K, uint64_t seed
 int vipsy_fill_uniform(float* out, int32_t S, int64_t B, int32_t K, uint64_t seed, uint64_t offset,
                        int64_t person_offset, void* stream) {
   return fill_noise(false, out, S, B, K, seed, offset, person_offset, stream);
+}
+
+int vipsy_fill_normal_dev(float* out, int32_t S, int64_t B, int32_t K, uint64_t seed, const uint64_t* offset_dev,
+                          int64_t person_offset, void* stream) {
+  VIPSY_REQUIRE(offset_dev, VIPSY_ERR_ARG, "vipsy_fill_normal_dev: offset_dev is NULL");
+  return fill_noise(true, out, S, B, K, seed, 0, person_offset, stream, offset_dev);
+}
+int vipsy_fill_uniform_dev(float* out, int32_t S, int64_t B, int32_t K, uint64_t seed, const uint64_t* offset_dev,
+                           int64_t person_offset, void* stream) {
+  VIPSY_REQUIRE(offset_dev, VIPSY_ERR_ARG, "vipsy_fill_uniform_dev: offset_dev is NULL");
+  return fill_noise(false, out, S, B, K, seed, 0, person_offset, stream, offset_dev);
+}
+
+int vipsy_adam_step(const VipsyAdamTensor* tensors, int32_t n_tensors, const int64_t* step_dev, int32_t zero_grad,
+                    void* stream) {
+  VIPSY_REQUIRE(tensors && n_tensors >= 0 && step_dev, VIPSY_ERR_ARG, "vipsy_adam_step: null argument");
+  for (int32_t t0 = 0; t0 < n_tensors; t0 += kAdamMaxTensors) {
+    AdamBatch b;
+    b.n = n_tensors - t0 < kAdamMaxTensors ? n_tensors - t0 : kAdamMaxTensors;
+    int64_t max_n = 0;
+    for (int i = 0; i < b.n; ++i) {
+      b.t[i] = tensors[t0 + i];
+      VIPSY_REQUIRE(b.t[i].param && b.t[i].grad && b.t[i].exp_avg && b.t[i].exp_avg_sq && b.t[i].n >= 0, VIPSY_ERR_ARG,
+                    "vipsy_adam_step: tensor %d has a null pointer", t0 + i);
+      if (b.t[i].n > max_n) max_n = b.t[i].n;
+    }
+    int64_t bx = (max_n + 1023) / 1024;                 // 256 threads x 4 elements per pass
+    if (bx > (int64_t)num_sms() * 4) bx = (int64_t)num_sms() * 4;
+    if (bx < 1) bx = 1;
+    adam_kernel<<<dim3((unsigned)bx, (unsigned)b.n), 256, 0, (cudaStream_t)stream>>>(b, step_dev, zero_grad);
+    VIPSY_CUDA_CHECK(cudaGetLastError());
+  }
+  return VIPSY_OK;
 }
 
 }  // extern "C"

@@ -120,12 +120,73 @@ def param(name: str, init=None, constraint: str = REAL) -> torch.Tensor:
 
 # --------------------------------------------------------------------------- optimisers
 class PyroOptim:
-    """One ``torch.optim`` instance per parameter tensor, created lazily."""
+    """One ``torch.optim`` instance per parameter tensor, created lazily.
+
+    ``fused_step`` is the device-resident form of the same update for ``torch.optim.Adam`` with default
+    options: one multi-tensor kernel (``ops.adam_step``) applies the free mask, the Adam update and the
+    gradient zeroing for every parameter of the step; the step count and the learning rates live in device
+    memory, so the whole SVI iteration can be captured in a CUDA graph.  The per-parameter ``torch.optim``
+    objects still exist (``optim_objs``; schedulers step them), but only as the source of the hyper-parameters."""
 
     def __init__(self, optim_constructor, optim_args: Union[dict, Callable], clip_args=None):
         self.ctor, self.args = optim_constructor, optim_args
         self.optim_objs: Dict[torch.Tensor, torch.optim.Optimizer] = {}
         self._names: Dict[torch.Tensor, str] = {}
+        self._fused: Dict[torch.Tensor, dict] = {}
+        self._step_dev: Optional[torch.Tensor] = None
+        self._steps_host = 0
+
+    # ---- device-resident Adam ------------------------------------------------------------------------------
+    def supports_fused(self) -> bool:
+        return self.ctor is torch.optim.Adam
+
+    def _fused_state(self, name: str, p: torch.Tensor) -> dict:
+        st = self._fused.get(p)
+        if st is None:
+            if p not in self.optim_objs:
+                self.optim_objs[p] = self._make(p, name)
+                self._names[p] = name
+            g = self.optim_objs[p].param_groups[0]
+            if g.get("weight_decay", 0) != 0 or g.get("amsgrad", False) or g.get("maximize", False):
+                raise NotImplementedError("fused Adam covers torch.optim.Adam's default options only")
+            st = dict(param=p.data, exp_avg=torch.zeros_like(p.data), exp_avg_sq=torch.zeros_like(p.data),
+                      lr_dev=torch.full((1,), float(g["lr"]), dtype=torch.float32, device=p.device),
+                      lr=float(g["lr"]), beta1=float(g["betas"][0]), beta2=float(g["betas"][1]), eps=float(g["eps"]),
+                      step_offset=self._steps_host, group=g)
+            self._fused[p] = st
+        return st
+
+    def fused_step(self, sites):
+        """sites: (name, leaf, free mask or None) with ``leaf.grad`` set.  Stream-ordered, no host sync."""
+        from . import ops
+        live = [(n, p, f) for n, p, f in sites if p.grad is not None]
+        if not live:
+            return
+        dev = live[0][1].device
+        if self._step_dev is None:
+            self._step_dev = torch.zeros(1, dtype=torch.int64, device=dev)
+        tensors = []
+        for name, p, free in live:
+            st = dict(self._fused_state(name, p))
+            st["grad"] = p.grad if p.grad.is_contiguous() else p.grad.contiguous()
+            if free is not None:
+                fm = st.get("free_u8")
+                if fm is None:
+                    fm = free.to(device=p.device, dtype=torch.uint8).expand_as(p).contiguous()
+                    self._fused[p]["free_u8"] = fm
+                st["free_mask"] = fm
+            tensors.append(st)
+        self._step_dev.add_(1)
+        self._steps_host += 1          # NOTE: under graph replay the host count is advanced by SVI
+        ops.adam_step(tensors, self._step_dev, zero_grad=False)
+
+    def sync_lr(self):
+        """Copy the (possibly scheduler-modified) learning rates of the torch optimizer objects to the device."""
+        for p, st in self._fused.items():
+            lr = float(st["group"]["lr"])
+            if lr != st["lr"]:
+                st["lr"] = lr
+                st["lr_dev"].fill_(lr)
 
     def _args_for(self, name: str) -> dict:
         if callable(self.args):
@@ -170,8 +231,12 @@ class PyroLRScheduler(PyroOptim):
         return opt
 
     def step(self, *args, **kwargs):
-        for s in self.schedulers.values():
-            s.step(*args, **kwargs)
+        import warnings
+        with warnings.catch_warnings():          # fused mode never calls the torch optimizer's own step()
+            warnings.simplefilter("ignore", UserWarning)
+            for s in self.schedulers.values():
+                s.step(*args, **kwargs)
+        self.sync_lr()
 
 
 class MultiStepLR(PyroLRScheduler):
@@ -205,13 +270,29 @@ class TraceEnum_ELBO(Trace_ELBO):                           # noqa: N801
 # --------------------------------------------------------------------------- SVI
 class SVI:
     """The reference's patched SVI (vi.py:503-516): loss_and_grads, multiply ``param.grad`` by
-    the site's ``free`` mask, optimiser step, zero grads, return the loss as a float."""
+    the site's ``free`` mask, optimiser step, zero grads, return the loss as a float.
 
-    def __init__(self, model, guide, optim: PyroOptim, loss: Trace_ELBO):
+    ``cuda_graph=True``: the whole iteration -- minibatch draw, noise, encoder forward, fused
+    ELBO + gradient kernels, constraint chain rules, encoder backward, free mask, Adam, gradient zeroing --
+    runs on the device with no host round trip and is captured once into a CUDA graph; every later ``step``
+    is one graph launch.  The reference's default usage (subsample_size ~ 100, tens of thousands of
+    iterations) is bound by launch and interpreter overhead, not by arithmetic; this removes it.  Needs
+    ``torch.optim.Adam`` with default options (what ``pyro.optim.Adam`` wraps)."""
+
+    WARMUP = 2          # eager iterations before capture (lazy parameter / optimiser / workspace creation)
+
+    def __init__(self, model, guide, optim: PyroOptim, loss: Trace_ELBO, cuda_graph: bool = False):
         self.model, self.guide, self.optim, self.loss = model, guide, optim, loss
         self.owner = model.__self__
+        self.cuda_graph = bool(cuda_graph)
+        if self.cuda_graph and not optim.supports_fused():
+            raise NotImplementedError("cuda_graph=True needs an Adam optimiser (pyro.optim.Adam / MultiStepLR of Adam)")
+        self._graph = None
+        self._static_loss = None
+        self._eager_steps = 0
 
-    def step(self, *args, **kwargs) -> float:
+    # ---- eager form, torch.optim objects (the reference's order of operations) -------------------------------
+    def _step_eager(self, *args, **kwargs) -> torch.Tensor:
         loss, sites = self.owner.loss_and_grads(self.loss, *args, **kwargs)
         params: List[Tuple[str, torch.Tensor]] = []
         for name, p, free in sites:
@@ -221,7 +302,39 @@ class SVI:
         self.optim(params)
         for _, p in params:                                      # pyro.infer.util.zero_grads
             p.grad = None
-        return float(loss)
+        return loss
+
+    # ---- device-resident form ----------------------------------------------------------------------------------
+    def _step_device(self, *args, **kwargs) -> torch.Tensor:
+        loss, sites = self.owner.loss_and_grads(self.loss, *args, **kwargs)
+        self.optim.fused_step(sites)                             # free mask + Adam in one launch
+        for _, p, _ in sites:
+            p.grad = None
+        return loss
+
+    def step_async(self, *args, **kwargs) -> torch.Tensor:
+        """One iteration; returns the loss as a device tensor without synchronising."""
+        if not self.cuda_graph:
+            return self._step_eager(*args, **kwargs)
+        owner = self.owner
+        owner._device_rng = True                                 # noise / minibatch counters in device memory
+        if self._graph is None:
+            if self._eager_steps < self.WARMUP:
+                self._eager_steps += 1
+                return self._step_device(*args, **kwargs)
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            host_steps = self.optim._steps_host
+            with torch.cuda.graph(g):
+                self._static_loss = self._step_device(*args, **kwargs)
+            self.optim._steps_host = host_steps                  # capture does not execute
+            self._graph = g
+        self._graph.replay()
+        self.optim._steps_host += 1
+        return self._static_loss
+
+    def step(self, *args, **kwargs) -> float:
+        return float(self.step_async(*args, **kwargs))
 
     def evaluate_loss(self, *args, **kwargs) -> float:
         with torch.no_grad():

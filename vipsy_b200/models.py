@@ -117,6 +117,10 @@ class BasePsy(nn.Module):               # vi.py:521-533
         self._sparse = self._n_missing > 0.5 * self._codes.numel()
         self._obs_csr = None          # CSR of the observed cells, built on first use (K = 1, S = 1 path)
         self._seed, self._calls = int(seed), 0
+        # device-resident RNG state (SVI(cuda_graph=True)): the noise call counter is a device scalar and the
+        # minibatch is drawn with graph-safe torch ops, so a captured iteration differs on every replay
+        self._device_rng = False
+        self._calls_dev = None
         # optional person sharding (vipsy_b200.dist.attach): this rank holds rows
         # [person_offset, person_offset + sample_size) of a global_size-person job
         self.global_size = self.sample_size
@@ -136,11 +140,24 @@ class BasePsy(nn.Module):               # vi.py:521-533
         N, B = self.sample_size, min(self.subsample_size, self.sample_size)
         if B >= N:
             return None, N, 1.0
+        if self._device_rng:          # uniform random B-subset in random order, no host sync (graph-safe)
+            return torch.rand(N, device=self.device).topk(B).indices, B, N / B
         return torch.randperm(N, device=self.device)[:B], B, N / B
 
-    def _noise_args(self):
+    def _noise_args(self, kind=None, S=1, B=0, K=1):
+        """Noise arguments of one kernel call.  Default: (seed, offset, person_offset) for the in-kernel Philox
+        generator.  With device-resident RNG state the same generator is run by ``ops.fill_*`` with its call
+        counter read from device memory and the draws are injected (``eps`` / ``u``): identical streams."""
         self._calls += 1
-        return dict(seed=self._seed, offset=self._calls, person_offset=self.person_offset)
+        if not self._device_rng or kind is None:
+            return dict(seed=self._seed, offset=self._calls, person_offset=self.person_offset)
+        if self._calls_dev is None:
+            self._calls_dev = torch.zeros(1, dtype=torch.int64, device=self.device)
+        self._calls_dev.add_(1)
+        fill = ops.fill_normal if kind == "eps" else ops.fill_uniform
+        # the eager counter and the device counter advance together, so switching modes keeps one stream
+        return {kind: fill(S, B, K, self._seed, self._calls_dev, self.person_offset,
+                           device=self.device)}
 
     def _encoder_input(self, idx):
         x = self._data_dev if idx is None else self._data_dev[idx]
@@ -156,16 +173,29 @@ class BasePsy(nn.Module):               # vi.py:521-533
         return name in ("x_local", "x_scale", "attr_p", "theta_local", "theta_scale") and not (
             name == "x_scale" and getattr(self, "share_cov", False) and getattr(self, "x_feature", 1) > 1)
 
+    def _use_graph(self, cuda_graph, optim, S) -> bool:
+        """cuda_graph=None: capture the iteration when it is small enough to be launch-bound."""
+        if cuda_graph is None:
+            B = min(self.subsample_size, self.sample_size)
+            work = B * self.item_size * max(S, 1) * max(getattr(self, "x_feature", 1), 1)
+            cuda_graph = work <= 2_000_000 and self.reducer is None
+        return bool(cuda_graph) and optim.supports_fused()
+
     def _fit_loop(self, svi, optim, max_iter, postfix_fn, evaluate=False):
         it = trange(max_iter) if trange is not None else range(max_iter)
         loss = float("nan")
         for i in it:
-            loss = svi.step(self.data)
+            show = trange is not None and (i % 50 == 0 or i == max_iter - 1)
+            last = i == max_iter - 1
+            # the loss is read back (a device sync) only when it is shown or returned
+            loss_t = svi.step_async(self.data)
             if evaluate:
                 loss = svi.evaluate_loss(self.data)
+            elif show or last:
+                loss = float(loss_t)
             if isinstance(optim, PyroLRScheduler):
                 optim.step()
-            if trange is not None and (i % 50 == 0 or i == max_iter - 1):
+            if show:
                 with torch.no_grad():
                     it.set_postfix(loss="{0:1.2f}".format(loss), **postfix_fn())
         return loss
@@ -239,7 +269,7 @@ class BaseIRT(BasePsy):                 # vi.py:536-656
                                   want_grad=want_grad, sparse=self._sparse and self.x_feature == 1,
                                   n_masked=self._n_missing if idx is None else None,
                                   obs=self._observed_csr() if (self._sparse and self.x_feature == 1 and s == 1) else None,
-                                  **gkw, **self._noise_args())
+                                  **gkw, **self._noise_args("eps", s, Bg, self.x_feature))
             w = 1.0 / len(groups)
             total = r["loss"] * w if total is None else total + r["loss"] * w
             if want_grad:
@@ -260,10 +290,11 @@ class BaseIRT(BasePsy):                 # vi.py:536-656
     def guide(self, data):
         raise RuntimeError("the guide is evaluated by the fused kernel; call fit() or SVI.step()")
 
-    def fit(self, optim=None, loss=None, max_iter=5000, random_instance=None):     # vi.py:627-656
+    def fit(self, optim=None, loss=None, max_iter=5000, random_instance=None, cuda_graph=None):     # vi.py:627-656
         optim = Adam({"lr": 5e-2}) if optim is None else optim
         loss = Trace_ELBO(num_particles=1) if loss is None else loss
-        svi = SVI(self.model, self.guide, optim=optim, loss=loss)
+        svi = SVI(self.model, self.guide, optim=optim, loss=loss,
+                  cuda_graph=self._use_graph(cuda_graph, optim, loss.num_particles))
         st = get_param_store()
 
         def postfix():
@@ -369,7 +400,8 @@ class BaseCDM(BasePsy):                 # vi.py:726-782  (REINFORCE with a Berno
             phi, backward, gsites = self._attr_p(idx)
             r = ops.cdm_score_elbo_grad(self._codes, self._qmask, g, s, phi.detach(), n_attrs=self.attr_size,
                                         n_particles=si, model=self._model, scale=scale, baseline=cfg.baseline,
-                                        idx=idx, want_grad=want_grad, **self._noise_args())
+                                        idx=idx, want_grad=want_grad,
+                                        **self._noise_args("u", si, Bg, self.attr_size))
             w = 1.0 / len(groups)
             total = r["loss"] * w if total is None else total + r["loss"] * w
             if want_grad:
@@ -392,12 +424,14 @@ class BaseCDM(BasePsy):                 # vi.py:726-782  (REINFORCE with a Berno
     def _default_loss(self):
         return Trace_ELBO(num_particles=1)
 
-    def fit(self, optim=None, loss=None, max_iter=5000, random_instance=None, evaluate_loss_each_iter=False):
+    def fit(self, optim=None, loss=None, max_iter=5000, random_instance=None, evaluate_loss_each_iter=False,
+            cuda_graph=None):
         """vi.py:758-782.  The reference re-evaluates the ELBO after every step (vi.py:770) only to
         print it; ``evaluate_loss_each_iter=True`` reproduces that, the default reports the step's loss."""
         optim = Adam({"lr": 1e-3}) if optim is None else optim
         loss = self._default_loss() if loss is None else loss
-        svi = SVI(self.model, self.guide, optim=optim, loss=loss)
+        svi = SVI(self.model, self.guide, optim=optim, loss=loss,
+                  cuda_graph=self._use_graph(cuda_graph, optim, loss.num_particles))
         st = get_param_store()
 
         def postfix():
@@ -463,7 +497,8 @@ class VCCDM(BaseCDM):                   # vi.py:819-863  (exact enumeration of t
             extra, backward, gsites = self._enum_extra(idx, Bg)
             r = ops.cdm_enum_elbo_grad(self._codes, self._qmask, g, s, n_attrs=self.attr_size,
                                        model="dina" if hod else self._model, scale=scale, idx=idx,
-                                       n_particles=si, want_grad=want_grad, **extra, **self._noise_args())
+                                       n_particles=si, want_grad=want_grad, **extra,
+                                       **self._noise_args("eps" if hod else None, si, Bg, 1))
             w = 1.0 / len(groups)
             total = r["loss"] * w if total is None else total + r["loss"] * w
             if want_grad:
@@ -526,10 +561,12 @@ class VCHoDina(VCCDM):                  # vi.py:894-958
         return (dict(lam0=l0_u.detach(), lam1=lam1, mu=mu, sigma=sigma), backward,
                 [("lam0", l0_u, None), ("lam1", l1_u, None)] + tsites)
 
-    def fit(self, optim=None, loss=None, max_iter=50000, random_instance=None, evaluate_loss_each_iter=False):
+    def fit(self, optim=None, loss=None, max_iter=50000, random_instance=None, evaluate_loss_each_iter=False,
+            cuda_graph=None):
         optim = Adam({"lr": 5e-3}) if optim is None else optim                  # vi.py:936
         loss = TraceEnum_ELBO(num_particles=1) if loss is None else loss
-        svi = SVI(self.model, self.guide, optim=optim, loss=loss)
+        svi = SVI(self.model, self.guide, optim=optim, loss=loss,
+                  cuda_graph=self._use_graph(cuda_graph, optim, loss.num_particles))
         st = get_param_store()
 
         def postfix():

@@ -98,16 +98,50 @@ def observed_csr(y: torch.Tensor):
     return row_ptr, entries, nnz
 
 
-def fill_normal(S: int, B: int, K: int, seed: int, offset: int, person_offset: int = 0, device="cuda"):
+def fill_normal(S: int, B: int, K: int, seed: int, offset, person_offset: int = 0, device="cuda"):
+    """S x B x K draws of the in-kernel N(0,1) generator.  ``offset``: the call counter, an int or a one-element
+    int64 CUDA tensor read at execution time (CUDA-graph replays then draw fresh noise)."""
     out = torch.empty((S, B, K), dtype=torch.float32, device=device)
-    N.check(N.lib().vipsy_fill_normal(_ptr(out), S, B, K, seed, offset, person_offset, _stream()))
+    if isinstance(offset, torch.Tensor):
+        N.check(N.lib().vipsy_fill_normal_dev(_ptr(out), S, B, K, seed, _ptr(offset), person_offset, _stream()))
+    else:
+        N.check(N.lib().vipsy_fill_normal(_ptr(out), S, B, K, seed, offset, person_offset, _stream()))
     return out
 
 
-def fill_uniform(S: int, B: int, K: int, seed: int, offset: int, person_offset: int = 0, device="cuda"):
+def fill_uniform(S: int, B: int, K: int, seed: int, offset, person_offset: int = 0, device="cuda"):
     out = torch.empty((S, B, K), dtype=torch.float32, device=device)
-    N.check(N.lib().vipsy_fill_uniform(_ptr(out), S, B, K, seed, offset, person_offset, _stream()))
+    if isinstance(offset, torch.Tensor):
+        N.check(N.lib().vipsy_fill_uniform_dev(_ptr(out), S, B, K, seed, _ptr(offset), person_offset, _stream()))
+    else:
+        N.check(N.lib().vipsy_fill_uniform(_ptr(out), S, B, K, seed, offset, person_offset, _stream()))
     return out
+
+
+def adam_step(tensors, step_dev: torch.Tensor, zero_grad: bool = True):
+    """One launch of the multi-tensor Adam (+ free mask, + zero grad) over ``tensors``: a list of dicts with
+    param, grad, exp_avg, exp_avg_sq (fp32 CUDA, same numel), optional free_mask (uint8), lr_dev, and the
+    scalars lr, beta1, beta2, eps, step_offset.  ``step_dev``: int64 CUDA scalar, the step count after increment."""
+    n = len(tensors)
+    if n == 0:
+        return
+    arr = (N.AdamTensor * n)()
+    for i, t in enumerate(tensors):
+        p = t["param"]
+        for k in ("param", "grad", "exp_avg", "exp_avg_sq"):
+            x = t[k]
+            if not (x.is_cuda and x.dtype == torch.float32 and x.is_contiguous() and x.numel() == p.numel()):
+                raise ValueError(f"adam_step: {k} must be a contiguous fp32 CUDA tensor of the parameter's size")
+        a = arr[i]
+        a.param, a.grad, a.exp_avg, a.exp_avg_sq = p.data_ptr(), t["grad"].data_ptr(), t["exp_avg"].data_ptr(), t["exp_avg_sq"].data_ptr()
+        fm = t.get("free_mask")
+        if fm is not None and not (fm.is_cuda and fm.dtype == torch.uint8 and fm.is_contiguous() and fm.numel() == p.numel()):
+            raise ValueError("adam_step: free_mask must be a contiguous uint8 CUDA tensor of the parameter's size")
+        a.free_mask = _ptr(fm)
+        a.lr_dev = _ptr(t.get("lr_dev"))
+        a.n, a.step_offset = p.numel(), int(t.get("step_offset", 0))
+        a.lr, a.beta1, a.beta2, a.eps = float(t["lr"]), float(t["beta1"]), float(t["beta2"]), float(t["eps"])
+    N.check(N.lib().vipsy_adam_step(arr, n, _ptr(step_dev), int(zero_grad), _stream()))
 
 
 def qmask_from_q(q: torch.Tensor) -> torch.Tensor:
