@@ -130,6 +130,28 @@ def other_configs(dev, peaks, flush, iters=5):
                                          model="irt_2pl", seed=1, offset=nxt()))
     out["c1_lsat_shape_2pl_1000x5_S1"] = {"ms": ms, "evals_per_s": 5000 / ms * 1e3, "bound": "launch latency"}
     del w
+    # c1 as the reference runs it: the WHOLE SVI iteration (ELBO + grads + free mask + Adam + zero grads),
+    # eager (torch.optim objects, Python between launches) vs captured once in a CUDA graph
+    import time as _time
+    import vipsy_b200 as vb
+    from vipsy_b200 import infer
+    yl = (torch.rand(1000, 5, generator=torch.Generator().manual_seed(3)) < 0.7).float()
+    it_us = {}
+    for graph in (False, True):
+        vb.clear_param_store()
+        m = vb.VIRT(data=yl, model="irt_2pl", device=dev)
+        svi = infer.SVI(m.model, m.guide, optim=vb.Adam({"lr": 5e-2}), loss=vb.Trace_ELBO(num_particles=1), cuda_graph=graph)
+        for _ in range(5):
+            svi.step(m.data)
+        torch.cuda.synchronize()
+        n_it = 300 if not graph else 2000
+        t0 = _time.perf_counter()
+        for _ in range(n_it):
+            svi.step_async(m.data)
+        torch.cuda.synchronize()
+        it_us["cuda_graph" if graph else "eager"] = (_time.perf_counter() - t0) / n_it * 1e6
+    vb.clear_param_store()
+    out["c1_full_svi_iteration_us"] = it_us
 
     # c4: 2PL, 2M x 200, 90 % missing, S = 1, observed-cell CSR layout (built once, outside the timing)
     w = workloads.uni_irt(2_000_000, 200, "irt_2pl", missing=0.9, seed=12, device=dev)

@@ -15,6 +15,24 @@
 
 namespace vipsy {
 
+// shared-memory accesses by 32-bit shared-window address: keeps the compiler from re-deriving the window base
+// (S2UR SR_CgaCtaId + 3 uniform ops) in front of every access of the hot loop
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ float2 lds_f2(uint32_t a) {
+  float2 v;
+  asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts_f2(uint32_t a, float2 v) {
+  asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(a), "f"(v.x), "f"(v.y) : "memory");
+}
+__device__ __forceinline__ float lds_f1(uint32_t a) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts_f1(uint32_t a, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory"); }
+
 template <int MODEL, bool FASTPATH>
 __device__ __forceinline__ void csr_cell(const float t, const float dmc, const float base, const bool obs,
                                          float& w, float& a1, float& a2, float& qc) {
@@ -125,12 +143,14 @@ __global__ void __launch_bounds__(kUniThreads) irt_uni_csr_kernel(const IrtUniPa
 
   // one batch: this lane's entry `ent` (valid iff obs) of the person whose latent is x
   float Gi, Lr;
+  const uint32_t tab_s = smem_addr(tabAB), acc_s = smem_addr(acc);
+  const bool want_grad = p.want_grad != 0;
   auto batch = [&](uint32_t ent, bool obs, float x) {
     const int j = (int)(ent & 0x7fffu);
     if constexpr (MODEL <= 2) {
       // lean 1PL / 2PL form: sign flip by XOR, one select puts an idle lane at t = -126 (sp = 1, 1 - sp = 0),
       // the probability clamp is the min at t = 23 (sp = eps) with the gradient switched off beyond it
-      const float2 ab = tabAB[j];
+      const float2 ab = lds_f2(tab_s + 8u * (uint32_t)j);
       const uint32_t flip = (~ent << 16) & 0x80000000u;                  // y == 0: negate
       float t = __uint_as_float(__float_as_uint(fmaf(ab.x, x, ab.y)) ^ flip);
       t = obs ? t : -126.f;
@@ -140,15 +160,16 @@ __global__ void __launch_bounds__(kUniThreads) irt_uni_csr_kernel(const IrtUniPa
       const float ws = __uint_as_float(__float_as_uint(w) ^ flip);
       Gi = fmaf(ab.x, ws, Gi);
       Lr *= sp;
-      if (obs && p.want_grad) {
+      if (obs && want_grad) {
         if constexpr (NQ == 2) {
-          float2* ap = reinterpret_cast<float2*>(acc) + j;
-          float2 v = *ap;
+          const uint32_t ap = acc_s + 8u * (uint32_t)j;
+          float2 v = lds_f2(ap);
           v.x += ws;
           v.y = fmaf(ws, x, v.y);
-          *ap = v;
+          sts_f2(ap, v);
         } else {
-          acc[j] += ws;
+          const uint32_t ap = acc_s + 4u * (uint32_t)j;
+          sts_f1(ap, lds_f1(ap) + ws);
         }
       }
     } else {
@@ -164,7 +185,7 @@ __global__ void __launch_bounds__(kUniThreads) irt_uni_csr_kernel(const IrtUniPa
       const float ws = y1 ? w : -w;
       Gi = fmaf(it2.x, ws, Gi);
       Lr *= qc;
-      if (obs && p.want_grad) {
+      if (obs && want_grad) {
         float4* ap = reinterpret_cast<float4*>(acc) + j;
         float4 v = *ap;
         v.x += ws;
@@ -188,7 +209,7 @@ __global__ void __launch_bounds__(kUniThreads) irt_uni_csr_kernel(const IrtUniPa
     const uint16_t* pe = p.entries + __shfl_sync(0xffffffffu, cur.beg, sub) + sl;
     uint32_t ent[NBP];
 #pragma unroll
-    for (int b = 0; b < NBP; ++b) ent[b] = b * SW + sl < cnt ? (uint32_t)__ldg(pe + b * SW) : 0u;
+    for (int b = 0; b < NBP; ++b) ent[b] = __ldg(b * SW + sl < cnt ? pe + b * SW : p.entries);
 #pragma unroll 1
     for (int r = 0; r < SW; ++r) {
       const int pn = (r + 1 < SW ? (r + 1) * NSUB : 0) + sub;
@@ -197,7 +218,9 @@ __global__ void __launch_bounds__(kUniThreads) irt_uni_csr_kernel(const IrtUniPa
       const uint16_t* pen = p.entries + __shfl_sync(0xffffffffu, cur.beg, pn) + sl;
       uint32_t entn[NBP];
 #pragma unroll
-      for (int b = 0; b < NBP; ++b) entn[b] = b * SW + sl < cntn ? (uint32_t)__ldg(pen + b * SW) : 0u;
+      // unconditional loads (an idle lane re-reads entry 0, a valid entry it then ignores): the loaded register
+      // is not touched until the next round, so the load latency hides behind this round's batches
+      for (int b = 0; b < NBP; ++b) entn[b] = __ldg(b * SW + sl < cntn ? pen + b * SW : p.entries);
 
       int cmax = cnt;                                  // longest row among this round's NSUB persons
 #pragma unroll
