@@ -348,8 +348,9 @@ def run_ours(args, rank, world, local_rank):
                    "power_w_max": ck["power_w_max"]},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": host.h2d_bytes,
                 "d2h_bytes_per_step": host.d2h_bytes, "ms_per_step": e2e_s * 1e3,
-                "how": "vipsy_b200.host_api.IrtHostStep: pinned host y (2-bit transport rows) / mu / sigma -> 4-chunk "
-                       "3-stream pipeline (copy, expand + fused kernel, copy back) -> host per-person and item grads + loss"},
+                "how": "vipsy_irt_host_step (C ABI, host buffers): pinned host y (2-bit transport rows) / mu / sigma -> "
+                       "4-chunk 3-stream pipeline (copy, expand + fused kernel, copy back) -> host per-person and item "
+                       "grads + loss"},
         "gpu_launches": gpu_launches,
         "roofline": {"bound": "hbm", "achieved": achieved_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                      "frac": achieved_gbs / peaks["hbm_gbs"], "traffic": traffic, "peak_source": peaks_src,

@@ -139,6 +139,38 @@ size_t vipsy_irt_workspace_bytes(const VipsyIrtArgs* args);
 int vipsy_irt_elbo_grad(const VipsyIrtArgs* args, void* stream);
 
 /* ------------------------------------------------------------------------
+ * The same evaluation (K == 1) with HOST buffers: what a binding of loss_and_grads(model, guide, data)
+ * (vi.py:507) calls when `data` and the variational parameters live in host memory.  The persons are cut into
+ * n_chunks chunks; copies in, kernels and copies out overlap on the three caller-owned streams; everything is
+ * enqueued before the call returns and the host outputs are valid once `s_out` has been synchronised.  Pinned
+ * host memory is needed for the copies to be asynchronous.  `dev` supplies sizes, model, scalars, flags,
+ * seed / offset / person_offset; its pointer fields are ignored.
+ * ---------------------------------------------------------------------- */
+typedef struct VipsyIrtHostArgs {
+  VipsyIrtArgs dev;
+  const uint8_t* y_host;     /* batch x J codes, or batch x (J+3)/4 rows of the 2-bit transport format */
+  int32_t y_packed2;         /* 1: y_host is in the 2-bit transport format                             */
+  int32_t n_chunks;          /* >= 1                                                                   */
+  const float* mu_host;      /* batch                                                                  */
+  const float* sigma_host;   /* batch                                                                  */
+  const float* a_host;       /* J (2PL+)                                                               */
+  const float* b_host;       /* J                                                                      */
+  const float* c_host;       /* J (3PL+)                                                               */
+  const float* d_host;       /* J (4PL)                                                                */
+  double* loss_host;         /* 1                                                                      */
+  float* d_mu_host;          /* batch, or NULL                                                         */
+  float* d_sigma_host;       /* batch, or NULL (goes with d_mu_host)                                   */
+  float* item_grads_host;    /* [d_b | d_a | d_c | d_d], J x model floats, or NULL                     */
+  void* dev_scratch;         /* device scratch, vipsy_irt_host_scratch_bytes()                         */
+  size_t dev_scratch_bytes;
+  void* s_in;                /* cudaStream_t: host -> device copies                                    */
+  void* s_run;               /* cudaStream_t: kernels                                                  */
+  void* s_out;               /* cudaStream_t: device -> host copies                                    */
+} VipsyIrtHostArgs;
+size_t vipsy_irt_host_scratch_bytes(const VipsyIrtHostArgs* args);
+int vipsy_irt_host_step(const VipsyIrtHostArgs* args);
+
+/* ------------------------------------------------------------------------
  * Enumerated CDMs: TraceEnum_ELBO over VCCDM.model (vi.py:839-857), optionally
  * with the HO-DINA pattern prior and Gaussian guide of VCHoDina (vi.py:897-934).
  *

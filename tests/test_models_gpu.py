@@ -178,6 +178,11 @@ def test_host_step_two_bit_transport_matches_device_call():
         assert torch.equal(got["item_grads"], ref["item_grads"].cpu())
         assert float(got["loss"]) == float(ref["loss"])
     assert host.h2d_bytes == N * (25 + 8) + 4 * J * 4
+    host4 = IrtHostStep(N, J, "irt_4pl", n_chunks=4)          # chunked: per-person outputs identical, item sums to rounding
+    got4 = host4(ops.pack_responses_2bit_host(hy), hp["mu"], hp["sigma"], hp["a"], hp["b"], hp["c"], hp["d"], n_particles=8, seed=9, offset=3)
+    assert torch.equal(got4["d_mu"], ref["d_mu"].cpu())
+    assert_close(got4["item_grads"], ref["item_grads"], 1e-5, 1e-5, "item grads over 4 chunks")
+    assert_close(got4["loss"], ref["loss"], 1e-9, 1e-9, "loss over 4 chunks")
     assert torch.equal(ops.unpack_responses_2bit(ops.pack_responses_2bit_host(hy).cuda(), J).cpu(), hy)
 
 

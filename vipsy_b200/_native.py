@@ -49,6 +49,15 @@ class IrtArgs(C.Structure):
     ]
 
 
+class IrtHostArgs(C.Structure):
+    _fields_ = [
+        ("dev", IrtArgs), ("y_host", _p), ("y_packed2", C.c_int32), ("n_chunks", C.c_int32),
+        ("mu_host", _p), ("sigma_host", _p), ("a_host", _p), ("b_host", _p), ("c_host", _p), ("d_host", _p),
+        ("loss_host", _p), ("d_mu_host", _p), ("d_sigma_host", _p), ("item_grads_host", _p),
+        ("dev_scratch", _p), ("dev_scratch_bytes", C.c_size_t), ("s_in", _p), ("s_run", _p), ("s_out", _p),
+    ]
+
+
 class CdmEnumArgs(C.Structure):
     _fields_ = [
         ("n_rows", C.c_int64), ("batch", C.c_int64),
@@ -88,6 +97,8 @@ SYMBOLS = {
     "vipsy_last_error": (C.c_char_p, []),
     "vipsy_irt_workspace_bytes": (C.c_size_t, [C.POINTER(IrtArgs)]),
     "vipsy_irt_elbo_grad": (C.c_int, [C.POINTER(IrtArgs), _p]),
+    "vipsy_irt_host_scratch_bytes": (C.c_size_t, [C.POINTER(IrtHostArgs)]),
+    "vipsy_irt_host_step": (C.c_int, [C.POINTER(IrtHostArgs)]),
     "vipsy_cdm_enum_workspace_bytes": (C.c_size_t, [C.POINTER(CdmEnumArgs)]),
     "vipsy_cdm_enum_elbo_grad": (C.c_int, [C.POINTER(CdmEnumArgs), _p]),
     "vipsy_cdm_score_workspace_bytes": (C.c_size_t, [C.POINTER(CdmScoreArgs)]),

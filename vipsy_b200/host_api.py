@@ -2,117 +2,90 @@
 ``loss_and_grads(model, guide, data)`` (vi.py:507) calls when the response
 matrix and the variational parameters live in (pinned) host memory.
 
-The response matrix may be handed over in the 2-bit transport format of
-``ops.pack_responses_2bit_host`` (4 cells per byte; packed once when the data are
-loaded): the chunk is expanded to byte codes on the device right after its copy.
-
-The persons are cut into chunks; chunk i+1's host->device copy and chunk i-1's
-device->host copy of the per-person gradients overlap chunk i's kernel on three
-CUDA streams.  Item-level gradients and the loss are accumulated on the device
-and read back once.  Every byte moved is counted (``h2d_bytes`` / ``d2h_bytes``).
+Thin wrapper over ``vipsy_irt_host_step`` (csrc/host_step.cu): the chunked
+copy-in / expand + kernel / copy-out pipeline over three CUDA streams is
+enqueued from C, no interpreter between launches.  The response matrix may be
+handed over in the 2-bit transport format of ``ops.pack_responses_2bit_host``
+(4 cells per byte; packed once when the data are loaded).  Every byte moved is
+counted (``h2d_bytes`` / ``d2h_bytes``).
 """
 from __future__ import annotations
 
-from typing import Dict, Optional
+import ctypes as C
+from typing import Dict
 
 import torch
 
-from . import ops
+from . import _native as N
 
 
 class IrtHostStep:
-    def __init__(self, n_persons: int, n_items: int, model: str = "irt_4pl", n_chunks: int = 8, device="cuda"):
+    def __init__(self, n_persons: int, n_items: int, model: str = "irt_4pl", n_chunks: int = 4, device="cuda"):
         self.N, self.J, self.model = n_persons, n_items, model
         self.dev = torch.device(device)
-        self.n_chunks = max(1, min(n_chunks, n_persons))
-        per = -(-n_persons // self.n_chunks)
-        per = -(-per // 32) * 32                      # whole warps of persons per chunk
-        self.bounds = [(s, min(s + per, n_persons)) for s in range(0, n_persons, per)]
-        d = self.dev
-        self.y = torch.empty((n_persons, n_items), dtype=torch.uint8, device=d)
-        self.y2 = None                                # device staging of 2-bit rows, allocated on first use
-        self.mu = torch.empty((n_persons, 1), dtype=torch.float32, device=d)
-        self.sigma = torch.empty((n_persons, 1), dtype=torch.float32, device=d)
-        self.d_mu = torch.empty((n_persons, 1), dtype=torch.float32, device=d)
-        self.d_sigma = torch.empty((n_persons, 1), dtype=torch.float32, device=d)
-        self.items = torch.empty((4, n_items), dtype=torch.float32, device=d)
+        self.n_chunks = max(1, min(n_chunks, max(n_persons // 32, 1)))
+        self.m = N.IRT_MODEL[model]
         self.h_d_mu = torch.empty((n_persons, 1), dtype=torch.float32, pin_memory=True)
         self.h_d_sigma = torch.empty((n_persons, 1), dtype=torch.float32, pin_memory=True)
-        self.h_items = torch.empty((4, n_items), dtype=torch.float32, pin_memory=True)
-        self.h_item_grads = None
+        self.h_item_grads = torch.empty(self.m * n_items, dtype=torch.float32, pin_memory=True)
         self.h_loss = torch.empty(1, dtype=torch.float64, pin_memory=True)
-        self.s_in, self.s_run, self.s_out = (torch.cuda.Stream(d) for _ in range(3))
+        self.h_items = torch.empty((4, n_items), dtype=torch.float32, pin_memory=True)
+        self.s_in, self.s_run, self.s_out = (torch.cuda.Stream(self.dev) for _ in range(3))
+        self.scratch = None
         self.h2d_bytes = self.d2h_bytes = 0
         self.kernel_launches = 0
 
     def __call__(self, y: torch.Tensor, mu: torch.Tensor, sigma: torch.Tensor, a, b, c=None, d=None, *,
                  n_particles: int = 1, D: float = 1.0, scale: float = 1.0, seed: int = 0, offset: int = 0,
                  person_offset: int = 0, estimator: str = "pathwise", baseline: float = 0.0) -> Dict[str, torch.Tensor]:
-        """All tensor arguments are HOST tensors (pinned for async copies).  y: N x J uint8 codes, or
-        N x ceil(J/4) uint8 rows in the 2-bit transport format."""
-        J = self.J
+        """All tensor arguments are HOST tensors (pinned for asynchronous copies).  y: N x J uint8 codes, or
+        N x ceil(J/4) uint8 rows in the 2-bit transport format.  Returns pinned host tensors."""
+        J, m = self.J, self.m
+        for t, nm in ((y, "y"), (mu, "mu"), (sigma, "sigma")):
+            if t.is_cuda or not t.is_contiguous():
+                raise ValueError(f"{nm} must be a contiguous HOST tensor")
         packed = y.shape[1] != J
-        if packed:
-            if y.shape[1] != (J + 3) // 4:
-                raise ValueError("y must be N x J codes or N x ceil(J/4) 2-bit rows")
-            if self.y2 is None:
-                self.y2 = torch.empty((self.N, (J + 3) // 4), dtype=torch.uint8, device=self.dev)
+        if packed and y.shape[1] != (J + 3) // 4:
+            raise ValueError("y must be N x J codes or N x ceil(J/4) 2-bit rows")
+        if y.dtype != torch.uint8 or mu.dtype != torch.float32 or sigma.dtype != torch.float32:
+            raise ValueError("y must be uint8, mu / sigma float32")
+        h = self.h_items
+        h[0].copy_(b.reshape(-1))
+        if m >= 2:
+            h[1].copy_(a.reshape(-1))
+        if m >= 3:
+            h[2].copy_(c.reshape(-1))
+        if m >= 4:
+            h[3].copy_(d.reshape(-1))
+        args = N.IrtHostArgs()
+        dv = args.dev
+        dv.n_rows, dv.batch, dv.n_items, dv.n_dims, dv.n_particles = self.N, self.N, J, 1, int(n_particles)
+        dv.model, dv.estimator = m, N.EST[estimator]
+        dv.D, dv.scale, dv.baseline = float(D), float(scale), float(baseline)
+        dv.seed, dv.offset, dv.person_offset = seed, offset, person_offset
+        args.y_host, args.y_packed2, args.n_chunks = y.data_ptr(), int(packed), self.n_chunks
+        args.mu_host, args.sigma_host = mu.data_ptr(), sigma.data_ptr()
+        args.b_host = h[0].data_ptr()
+        args.a_host = h[1].data_ptr() if m >= 2 else None
+        args.c_host = h[2].data_ptr() if m >= 3 else None
+        args.d_host = h[3].data_ptr() if m >= 4 else None
+        args.loss_host = self.h_loss.data_ptr()
+        args.d_mu_host, args.d_sigma_host = self.h_d_mu.data_ptr(), self.h_d_sigma.data_ptr()
+        args.item_grads_host = self.h_item_grads.data_ptr()
+        L = N.lib()
+        need = L.vipsy_irt_host_scratch_bytes(C.byref(args))
+        if self.scratch is None or self.scratch.numel() < need:
+            self.scratch = torch.empty(need, dtype=torch.uint8, device=self.dev)
+        args.dev_scratch, args.dev_scratch_bytes = self.scratch.data_ptr(), self.scratch.numel()
         cur = torch.cuda.current_stream(self.dev)
         for s in (self.s_in, self.s_run, self.s_out):
             s.wait_stream(cur)
-        h = self.h_items
-        h[0].copy_(b.reshape(-1)); h[1].copy_((a if a is not None else torch.ones(J)).reshape(-1))
-        h[2].copy_((c if c is not None else torch.zeros(J)).reshape(-1))
-        h[3].copy_((d if d is not None else torch.ones(J)).reshape(-1))
-        h2d = d2h = 0
-        keep = []
-        item_acc = loss_acc = None
-        with torch.cuda.stream(self.s_in):
-            self.items.copy_(h, non_blocking=True)
-            h2d += h.numel() * 4
-        for (s, e) in self.bounds:
-            ev_in, ev_run = torch.cuda.Event(), torch.cuda.Event()
-            with torch.cuda.stream(self.s_in):
-                if packed:
-                    self.y2[s:e].copy_(y[s:e], non_blocking=True)
-                else:
-                    self.y[s:e].copy_(y[s:e], non_blocking=True)
-                self.mu[s:e].copy_(mu[s:e], non_blocking=True)
-                self.sigma[s:e].copy_(sigma[s:e], non_blocking=True)
-                ev_in.record()
-                h2d += (e - s) * (y.shape[1] + 8)
-            with torch.cuda.stream(self.s_run):
-                self.s_run.wait_event(ev_in)
-                if packed:
-                    ops.unpack_responses_2bit(self.y2[s:e], J, out=self.y[s:e])
-                    self.kernel_launches += 1
-                r = ops.irt_elbo_grad(self.y[s:e], self.mu[s:e], sigma=self.sigma[s:e], n_particles=n_particles,
-                                      a=self.items[1], b=self.items[0], c=self.items[2], d=self.items[3],
-                                      model=self.model, D=D, scale=scale, seed=seed, offset=offset,
-                                      person_offset=person_offset + s, estimator=estimator, baseline=baseline,
-                                      d_mu_out=self.d_mu[s:e], d_scale_out=self.d_sigma[s:e])
-                self.kernel_launches += 3
-                if item_acc is None:
-                    item_acc, loss_acc = r["item_grads"], r["loss"]
-                else:
-                    item_acc = item_acc + r["item_grads"]
-                    loss_acc = loss_acc + r["loss"]
-                keep.append(r)
-                ev_run.record()
-            with torch.cuda.stream(self.s_out):
-                self.s_out.wait_event(ev_run)
-                self.h_d_mu[s:e].copy_(self.d_mu[s:e], non_blocking=True)
-                self.h_d_sigma[s:e].copy_(self.d_sigma[s:e], non_blocking=True)
-                d2h += (e - s) * 8
-        with torch.cuda.stream(self.s_out):
-            self.s_out.wait_stream(self.s_run)
-            if self.h_item_grads is None or self.h_item_grads.numel() != item_acc.numel():
-                self.h_item_grads = torch.empty(item_acc.numel(), dtype=torch.float32, pin_memory=True)
-            self.h_item_grads.copy_(item_acc, non_blocking=True)
-            self.h_loss.copy_(loss_acc, non_blocking=True)
-            d2h += item_acc.numel() * 4 + 8
+        args.s_in, args.s_run, args.s_out = self.s_in.cuda_stream, self.s_run.cuda_stream, self.s_out.cuda_stream
+        N.check(L.vipsy_irt_host_step(C.byref(args)))
         self.s_out.synchronize()
-        cur.wait_stream(self.s_out)
-        self.h2d_bytes, self.d2h_bytes = h2d, d2h
-        return {"loss": self.h_loss, "d_mu": self.h_d_mu, "d_sigma": self.h_d_sigma,
-                "item_grads": self.h_item_grads}
+        cur.wait_stream(self.s_run)
+        chunks = self.n_chunks
+        self.kernel_launches += chunks * (3 + int(packed)) + 1
+        self.h2d_bytes = self.N * (y.shape[1] + 8) + m * J * 4
+        self.d2h_bytes = self.N * 8 + m * J * 4 + 8
+        return {"loss": self.h_loss, "d_mu": self.h_d_mu, "d_sigma": self.h_d_sigma, "item_grads": self.h_item_grads}
