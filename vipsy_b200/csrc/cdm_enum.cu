@@ -53,48 +53,57 @@ struct CdmEnumParams {
 
 __device__ __forceinline__ int pad_addr(int c) { return c + ((c >> 7) << 2); }
 
+// The 32 lattice values of a lane live in 16 float2 registers, value t = pair t/2, half t%2, so that four of
+// the five stages of each transform (and the log-sum-exp arithmetic) run as sm_100 packed FADD2 / FFMA2 / FMUL2.
+#define LAT(v, t) (((t) & 1) ? (v)[(t) >> 1].y : (v)[(t) >> 1].x)
+
 // subset-sum over the 5 register-index bits: v[i] += v[i ^ bit] for i with bit set
-__device__ __forceinline__ void zeta_regs(float (&v)[32]) {
+__device__ __forceinline__ void zeta_regs(float2 (&v)[16]) {
 #pragma unroll
-  for (int bit = 1; bit < 32; bit <<= 1) {
+  for (int k = 0; k < 16; ++k) v[k].y += v[k].x;                           // bit 0: inside the pair
 #pragma unroll
-    for (int i = 0; i < 32; ++i)
-      if (i & bit) v[i] += v[i ^ bit];
+  for (int bit = 1; bit < 16; bit <<= 1) {
+#pragma unroll
+    for (int k = 0; k < 16; ++k)
+      if (k & bit) v[k] = __fadd2_rn(v[k], v[k ^ bit]);
   }
 }
 // superset-sum (transpose of the above): v[i] += v[i | bit] for i with bit clear
-__device__ __forceinline__ void zeta_regs_T(float (&v)[32]) {
+__device__ __forceinline__ void zeta_regs_T(float2 (&v)[16]) {
 #pragma unroll
-  for (int bit = 1; bit < 32; bit <<= 1) {
+  for (int k = 0; k < 16; ++k) v[k].x += v[k].y;
 #pragma unroll
-    for (int i = 0; i < 32; ++i)
-      if (!(i & bit)) v[i] += v[i | bit];
+  for (int bit = 1; bit < 16; bit <<= 1) {
+#pragma unroll
+    for (int k = 0; k < 16; ++k)
+      if (!(k & bit)) v[k] = __fadd2_rn(v[k], v[k | bit]);
   }
 }
 
 // registers in layout A (index i = q*4 + e) <-> padded shared memory
-__device__ __forceinline__ void store_A(float* X, const float (&v)[32], int lane) {
+__device__ __forceinline__ void store_A(float* X, const float2 (&v)[16], int lane) {
 #pragma unroll
   for (int q = 0; q < 8; ++q)
-    *reinterpret_cast<float4*>(X + q * 132 + lane * 4) = make_float4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
+    *reinterpret_cast<float4*>(X + q * 132 + lane * 4) = make_float4(v[2 * q].x, v[2 * q].y, v[2 * q + 1].x, v[2 * q + 1].y);
 }
-__device__ __forceinline__ void load_A(const float* X, float (&v)[32], int lane) {
+__device__ __forceinline__ void load_A(const float* X, float2 (&v)[16], int lane) {
 #pragma unroll
   for (int q = 0; q < 8; ++q) {
     const float4 t = *reinterpret_cast<const float4*>(X + q * 132 + lane * 4);
-    v[q * 4] = t.x; v[q * 4 + 1] = t.y; v[q * 4 + 2] = t.z; v[q * 4 + 3] = t.w;
+    v[2 * q] = make_float2(t.x, t.y);
+    v[2 * q + 1] = make_float2(t.z, t.w);
   }
 }
 // registers in layout B (index t) <-> padded shared memory; bank = (hi*4 + t*4 + lo) % 32: conflict-free
-__device__ __forceinline__ void store_B(float* X, const float (&v)[32], int lane) {
+__device__ __forceinline__ void store_B(float* X, const float2 (&v)[16], int lane) {
   const int base = (lane >> 2) * 132 + (lane & 3);
 #pragma unroll
-  for (int t = 0; t < 32; ++t) X[base + t * 4] = v[t];
+  for (int t = 0; t < 32; ++t) X[base + t * 4] = LAT(v, t);
 }
-__device__ __forceinline__ void load_B(const float* X, float (&v)[32], int lane) {
+__device__ __forceinline__ void load_B(const float* X, float2 (&v)[16], int lane) {
   const int base = (lane >> 2) * 132 + (lane & 3);
 #pragma unroll
-  for (int t = 0; t < 32; ++t) v[t] = X[base + t * 4];
+  for (int t = 0; t < 32; ++t) LAT(v, t) = X[base + t * 4];
 }
 
 // Sum 16 per-lane values across the warp with a transposing butterfly (16 shuffles):
@@ -133,7 +142,8 @@ struct ItemConst {      // per item, built once per CTA
   float db1, db0;       // d lb(y|eta=0) / d g   for y = 1, 0
 };
 
-template <bool HODINA>
+// NS: 32-item slots per lane (J <= 32 NS); the per-lane item accumulators are 4 NS registers
+template <bool HODINA, int NS>
 __global__ void __launch_bounds__(kCdmThreads, HODINA ? 2 : 3) cdm_enum_kernel(const CdmEnumParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int J = p.J, K = p.K;
@@ -182,12 +192,12 @@ __global__ void __launch_bounds__(kCdmThreads, HODINA ? 2 : 3) cdm_enum_kernel(c
   for (int i = threadIdx.x; i < kCdmWarps * 2 * kLatPad; i += kCdmThreads) wbuf[i] = 0.f;
   __syncthreads();
   const int max_round = max_round_sm;
-  const int nslots = (J + 31) >> 5;
+  constexpr int nslots = NS;
 
   // per-lane item accumulators: slot k <-> item k*32 + lane
-  float accS1[kMaxSlots], accS0[kMaxSlots], accN1[kMaxSlots], accN0[kMaxSlots];
+  float accS1[NS], accS0[NS], accN1[NS], accN0[NS];
 #pragma unroll
-  for (int k = 0; k < kMaxSlots; ++k) accS1[k] = accS0[k] = accN1[k] = accN0[k] = 0.f;
+  for (int k = 0; k < NS; ++k) accS1[k] = accS0[k] = accN1[k] = accN0[k] = 0.f;
   float accL0 = 0.f, accL1 = 0.f;     // HO-DINA: lane (2k, 2k+1) accumulates d lam0_k, d lam1_k
   double loss_acc = 0.0;
 
@@ -205,10 +215,10 @@ __global__ void __launch_bounds__(kCdmThreads, HODINA ? 2 : 3) cdm_enum_kernel(c
     const int64_t row = p.idx ? p.idx[b] : b;
     const uint8_t* yrow = p.y + row * p.ld_y;
     // ---- responses -> base, sparse f --------------------------------------
-    unsigned codes[kMaxSlots];
+    unsigned codes[NS];
     float base_part = 0.f;
 #pragma unroll
-    for (int k = 0; k < kMaxSlots; ++k) {
+    for (int k = 0; k < NS; ++k) {
       codes[k] = 255u;
       if (k < nslots) {
         const int j = k * 32 + lane;
@@ -217,7 +227,7 @@ __global__ void __launch_bounds__(kCdmThreads, HODINA ? 2 : 3) cdm_enum_kernel(c
     }
     for (int rd = 0; rd <= max_round; ++rd) {
 #pragma unroll
-      for (int k = 0; k < kMaxSlots; ++k) {
+      for (int k = 0; k < NS; ++k) {
         if (k < nslots) {
           const int j = k * 32 + lane;
           if (j < J && codes[k] != 255u) {
@@ -232,11 +242,11 @@ __global__ void __launch_bounds__(kCdmThreads, HODINA ? 2 : 3) cdm_enum_kernel(c
       __syncwarp();
     }
     const float base = warp_sum(base_part);
-    float v[32];
+    float2 v[16];
     load_A(F, v, lane);
     __syncwarp();
 #pragma unroll
-    for (int k = 0; k < kMaxSlots; ++k)        // keep F sparse-zero for the next person
+    for (int k = 0; k < NS; ++k)        // keep F sparse-zero for the next person
       if (k < nslots) {
         const int j = k * 32 + lane;
         if (j < J && codes[k] != 255u) F[pad_addr(imask[j])] = 0.f;
@@ -250,14 +260,13 @@ __global__ void __launch_bounds__(kCdmThreads, HODINA ? 2 : 3) cdm_enum_kernel(c
     __syncwarp();          // X is rewritten below
 
     // ---- posterior over patterns (per particle for HO-DINA) -----------------
-    float post[32];
+    float2 post[16];
 #pragma unroll
-    for (int t = 0; t < 32; ++t) post[t] = 0.f;
+    for (int k = 0; k < 16; ++k) post[k] = make_float2(0.f, 0.f);
     float mu = 0.f, sg = 1.f, se = 0.f, see = 0.f, gth_sum = 0.f, gth_eps = 0.f, marg_sum = 0.f;
     if (HODINA) { mu = p.mu[b]; sg = p.sigma[b]; }
     const int n_part = HODINA ? p.S : 1;
     for (int sidx = 0; sidx < n_part; ++sidx) {
-      float w[32];
       float eps_s = 0.f, theta = 0.f, pik = 0.5f;
       if (HODINA) {
         if (p.eps) eps_s = p.eps[(int64_t)sidx * p.B + b];
@@ -288,48 +297,68 @@ __global__ void __launch_bounds__(kCdmThreads, HODINA ? 2 : 3) cdm_enum_kernel(c
         // lane bits: lo = attrs 0,1; hi = attrs 7,8,9.  register bits t = attrs 2..6
         float lw_lane = ((lane & 1) ? l1[0] : l0[0]) + ((lane & 2) ? l1[1] : l0[1]) +
                         ((lane & 4) ? l1[7] : l0[7]) + ((lane & 8) ? l1[8] : l0[8]) + ((lane & 16) ? l1[9] : l0[9]);
-        float lwr[32];
-        lwr[0] = lw_lane + l0[2] + l0[3] + l0[4] + l0[5] + l0[6];
+        // log prior of the lane's 32 patterns, built by doubling over the register bits (pairs: FADD2)
+        float2 lj[16];
+        lj[0].x = lw_lane + l0[2] + l0[3] + l0[4] + l0[5] + l0[6];
+        lj[0].y = lj[0].x + (l1[2] - l0[2]);
 #pragma unroll
-        for (int bit = 0; bit < 5; ++bit) {
+        for (int bit = 1; bit < 5; ++bit) {
           const float dlt = l1[2 + bit] - l0[2 + bit];
+          const float2 d2 = make_float2(dlt, dlt);
 #pragma unroll
-          for (int t = (1 << bit); t < (2 << bit); ++t) lwr[t] = lwr[t - (1 << bit)] + dlt;
+          for (int k = (1 << (bit - 1)); k < (1 << bit); ++k) lj[k] = __fadd2_rn(lj[k - (1 << (bit - 1))], d2);
         }
-        // Categorical(probs=w): p = w / sum w (= w up to rounding), floor at eps
+        // Categorical(probs=w): p = w / sum w (= w up to rounding), floor at eps;
+        // bit t of `live` = pattern t is not floored
+        uint32_t live = 0u;
+        float m = -3.0e38f;
 #pragma unroll
         for (int t = 0; t < 32; ++t) {
-          const float lwt = lwr[t];
-          const bool floored = (lwt + shift) < kLogEps32;
-          w[t] = floored ? 0.f : 1.f;                      // "not floored" flag, reused below
-          lwr[t] = fminf(fmaxf(lwt, kLogEps32 - shift), -kEps32 - shift);   // log clamp(p, eps, 1-eps)
+          const float lwt = LAT(lj, t);
+          if (!((lwt + shift) < kLogEps32)) live |= 1u << t;
+          const float lc = fminf(fmaxf(lwt, kLogEps32 - shift), -kEps32 - shift);   // log clamp(p, eps, 1-eps)
+          const float joint = LAT(v, t) + lc;
+          LAT(lj, t) = joint;
+          m = fmaxf(m, joint);
         }
-        float m = -3.0e38f;
-        float lj[32];
-#pragma unroll
-        for (int t = 0; t < 32; ++t) { lj[t] = v[t] + lwr[t]; m = fmaxf(m, lj[t]); }
         m = warp_max(m);
-        float ssum = 0.f;
+        const float2 l2e = make_float2(kLog2e, kLog2e), nm = make_float2(-m * kLog2e, -m * kLog2e);
+        float2 ss = make_float2(0.f, 0.f);
 #pragma unroll
-        for (int t = 0; t < 32; ++t) { lj[t] = ex2_approx((lj[t] - m) * kLog2e); ssum += lj[t]; }
-        ssum = warp_sum(ssum);
+        for (int k = 0; k < 16; ++k) {
+          const float2 t2 = __ffma2_rn(lj[k], l2e, nm);
+          lj[k] = make_float2(ex2_approx(t2.x), ex2_approx(t2.y));
+          ss = __fadd2_rn(ss, lj[k]);
+        }
+        const float ssum = warp_sum(ss.x + ss.y);
         const float inv = 1.f / ssum;
         marg_sum += m + logf(ssum) + base;
-        // posterior, attribute marginals of the non-floored mass
+        // posterior; attribute marginals of the non-floored mass by a halving tree over the register bits:
+        // after level b the survivors are sums over bits 0..b, and the odd partner of each pair carries bit b
         float red[16];
 #pragma unroll
         for (int a = 0; a < 16; ++a) red[a] = 0.f;
-        float tot = 0.f;
+        const float2 inv2 = make_float2(inv, inv), invS2 = make_float2(invS, invS);
+        float2 rn[16];
 #pragma unroll
-        for (int t = 0; t < 32; ++t) {
-          const float r = lj[t] * inv;
-          post[t] = fmaf(r, invS, post[t]);
-          const float rn = r * w[t];
-          tot += rn;
-#pragma unroll
-          for (int bit = 0; bit < 5; ++bit)
-            if (t & (1 << bit)) red[2 + bit] += rn;
+        for (int k = 0; k < 16; ++k) {
+          const float2 r = __fmul2_rn(lj[k], inv2);
+          post[k] = __ffma2_rn(r, invS2, post[k]);
+          rn[k] = make_float2((live >> (2 * k)) & 1u ? r.x : 0.f, (live >> (2 * k + 1)) & 1u ? r.y : 0.f);
         }
+        float lvl[16];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) { red[2] += rn[k].y; lvl[k] = rn[k].x + rn[k].y; }      // register bit 0 = attribute 2
+#pragma unroll
+        for (int bit = 1; bit < 5; ++bit) {
+          const int n = 16 >> bit;                                                        // survivors after this level
+#pragma unroll
+          for (int k = 0; k < n; ++k) {
+            red[2 + bit] += lvl[2 * k + 1];
+            lvl[k] = lvl[2 * k] + lvl[2 * k + 1];
+          }
+        }
+        const float tot = lvl[0];
         red[0] = (lane & 1) ? tot : 0.f; red[1] = (lane & 2) ? tot : 0.f;
         red[7] = (lane & 4) ? tot : 0.f; red[8] = (lane & 8) ? tot : 0.f; red[9] = (lane & 16) ? tot : 0.f;
         red[10] = tot;
@@ -346,16 +375,23 @@ __global__ void __launch_bounds__(kCdmThreads, HODINA ? 2 : 3) cdm_enum_kernel(c
         // uniform Categorical(1/C): log prior = -K ln2 per real pattern, exact under embedding
         float m = -3.0e38f;
 #pragma unroll
-        for (int t = 0; t < 32; ++t) m = fmaxf(m, v[t]);
+        for (int k = 0; k < 16; ++k) m = fmaxf(m, fmaxf(v[k].x, v[k].y));
         m = warp_max(m);
-        float ssum = 0.f;
+        // exp(v - m) = 2^(v log2e - m log2e): one packed FFMA per pair, then the two MUFU.EX2
+        const float2 l2e = make_float2(kLog2e, kLog2e), nm = make_float2(-m * kLog2e, -m * kLog2e);
+        float2 ss = make_float2(0.f, 0.f);
 #pragma unroll
-        for (int t = 0; t < 32; ++t) { w[t] = ex2_approx((v[t] - m) * kLog2e); ssum += w[t]; }
-        ssum = warp_sum(ssum);
+        for (int k = 0; k < 16; ++k) {
+          const float2 t2 = __ffma2_rn(v[k], l2e, nm);
+          post[k] = make_float2(ex2_approx(t2.x), ex2_approx(t2.y));
+          ss = __fadd2_rn(ss, post[k]);
+        }
+        const float ssum = warp_sum(ss.x + ss.y);
         const float inv = 1.f / ssum;
         marg_sum += m + logf(ssum) + base - 10.f * kLn2;
+        const float2 inv2 = make_float2(inv, inv);
 #pragma unroll
-        for (int t = 0; t < 32; ++t) post[t] = w[t] * inv;
+        for (int k = 0; k < 16; ++k) post[k] = __fmul2_rn(post[k], inv2);
       }
     }
 
@@ -382,7 +418,7 @@ __global__ void __launch_bounds__(kCdmThreads, HODINA ? 2 : 3) cdm_enum_kernel(c
         int c = (lane >> 2) * 128 + t * 4 + (lane & 3);
         if (c < (1 << K)) {
           if (dino) c = (~c) & ((1 << K) - 1);
-          p.posterior[b * ((int64_t)1 << K) + c] = post[t] * rep;
+          p.posterior[b * ((int64_t)1 << K) + c] = LAT(post, t) * rep;
         }
       }
     }
@@ -398,7 +434,7 @@ __global__ void __launch_bounds__(kCdmThreads, HODINA ? 2 : 3) cdm_enum_kernel(c
       store_A(X, post, lane);
       __syncwarp();
 #pragma unroll
-      for (int k = 0; k < kMaxSlots; ++k) {
+      for (int k = 0; k < NS; ++k) {
         if (k < nslots) {
           const int j = k * 32 + lane;
           if (j < J && codes[k] != 255u) {
@@ -429,7 +465,7 @@ __global__ void __launch_bounds__(kCdmThreads, HODINA ? 2 : 3) cdm_enum_kernel(c
     __syncthreads();
     float* red = wbuf;
 #pragma unroll
-    for (int k = 0; k < kMaxSlots; ++k) {
+    for (int k = 0; k < NS; ++k) {
       if (k < nslots) {
         const int j = k * 32 + lane;
         if (j < J) {
@@ -477,10 +513,13 @@ int cdm_enum_launch(const VipsyCdmEnumArgs* a, cudaStream_t st) {
   p.loss_partial = reinterpret_cast<double*>(a->workspace);
   p.partial = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(a->workspace) + ((rows_max * 8 + 15) & ~size_t(15)));
   const size_t smem = cdm_smem_bytes(p.J);
-  auto kern = a->hodina ? cdm_enum_kernel<true> : cdm_enum_kernel<false>;
-  static int occ[2] = {0, 0};
-  static size_t occ_smem[2] = {0, 0};
-  const int which = a->hodina ? 1 : 0;
+  const int ns = p.J <= 64 ? 2 : (p.J <= 128 ? 4 : 8);
+  void (*kern)(const CdmEnumParams);
+  if (a->hodina) kern = ns == 2 ? cdm_enum_kernel<true, 2> : (ns == 4 ? cdm_enum_kernel<true, 4> : cdm_enum_kernel<true, 8>);
+  else kern = ns == 2 ? cdm_enum_kernel<false, 2> : (ns == 4 ? cdm_enum_kernel<false, 4> : cdm_enum_kernel<false, 8>);
+  static int occ[6] = {0, 0, 0, 0, 0, 0};
+  static size_t occ_smem[6] = {0, 0, 0, 0, 0, 0};
+  const int which = (a->hodina ? 3 : 0) + (ns == 2 ? 0 : (ns == 4 ? 1 : 2));
   if (smem > 48 * 1024) VIPSY_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   if (occ[which] == 0 || occ_smem[which] != smem) {
     VIPSY_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[which], kern, kCdmThreads, smem));
