@@ -200,6 +200,26 @@ __global__ void __launch_bounds__(kCdmThreads, HODINA ? 2 : 3) cdm_enum_kernel(c
   for (int k = 0; k < NS; ++k) accS1[k] = accS0[k] = accN1[k] = accN0[k] = 0.f;
   float accL0 = 0.f, accL1 = 0.f;     // HO-DINA: lane (2k, 2k+1) accumulates d lam0_k, d lam1_k
   double loss_acc = 0.0;
+  // this lane's items (slot k <-> item k*32 + lane), hoisted out of the person loop: lattice address of the
+  // item's mask (-1: no lattice term), duplicate-mask round, flags, and the y = 1 / 0 constants
+  int it_addr[NS], it_round[NS], it_flag[NS];
+  float it_b1[NS], it_b0[NS], it_d1[NS], it_d0[NS];
+#pragma unroll
+  for (int k = 0; k < NS; ++k) {
+    const int j = k * 32 + lane;
+    it_addr[k] = -1; it_round[k] = 0; it_flag[k] = 2;
+    it_b1[k] = it_b0[k] = it_d1[k] = it_d0[k] = 0.f;
+    if (j < J) {
+      const ItemConst c = ic[j];
+      const int fl = iflag[j];
+      it_flag[k] = fl;
+      it_round[k] = iround[j];
+      it_addr[k] = (fl & 2) ? -1 : pad_addr(imask[j]);
+      it_d1[k] = c.delta1; it_d0[k] = c.delta0;
+      it_b1[k] = c.base1 + ((fl & 1) ? -c.delta1 : 0.f);
+      it_b0[k] = c.base0 + ((fl & 1) ? -c.delta0 : 0.f);
+    }
+  }
 
   // HO-DINA per-lane constants: attribute owned by this lane for the logit stage
   const int kk = (lane >> 1) & 15;
@@ -225,20 +245,13 @@ __global__ void __launch_bounds__(kCdmThreads, HODINA ? 2 : 3) cdm_enum_kernel(c
         if (j < J) codes[k] = yrow[j];
       }
     }
-    for (int rd = 0; rd <= max_round; ++rd) {
 #pragma unroll
-      for (int k = 0; k < NS; ++k) {
-        if (k < nslots) {
-          const int j = k * 32 + lane;
-          if (j < J && codes[k] != 255u) {
-            const ItemConst c = ic[j];
-            const bool y1 = codes[k] != 0u;
-            const int fl = iflag[j];
-            if (rd == 0) base_part += (y1 ? c.base1 : c.base0) + ((fl & 1) ? -(y1 ? c.delta1 : c.delta0) : 0.f);
-            if (!(fl & 2) && iround[j] == rd) F[pad_addr(imask[j])] += y1 ? c.delta1 : c.delta0;
-          }
-        }
-      }
+    for (int k = 0; k < NS; ++k)
+      if (codes[k] != 255u) base_part += codes[k] != 0u ? it_b1[k] : it_b0[k];
+    for (int rd = 0; rd <= max_round; ++rd) {          // items sharing a mask take turns (plain read-modify-write)
+#pragma unroll
+      for (int k = 0; k < NS; ++k)
+        if (codes[k] != 255u && it_addr[k] >= 0 && it_round[k] == rd) F[it_addr[k]] += codes[k] != 0u ? it_d1[k] : it_d0[k];
       __syncwarp();
     }
     const float base = warp_sum(base_part);
@@ -247,10 +260,7 @@ __global__ void __launch_bounds__(kCdmThreads, HODINA ? 2 : 3) cdm_enum_kernel(c
     __syncwarp();
 #pragma unroll
     for (int k = 0; k < NS; ++k)        // keep F sparse-zero for the next person
-      if (k < nslots) {
-        const int j = k * 32 + lane;
-        if (j < J && codes[k] != 255u) F[pad_addr(imask[j])] = 0.f;
-      }
+      if (codes[k] != 255u && it_addr[k] >= 0) F[it_addr[k]] = 0.f;
     // ---- forward lattice transform: ll(c) - base ----------------------------
     zeta_regs(v);
     store_A(X, v, lane);
@@ -435,15 +445,11 @@ __global__ void __launch_bounds__(kCdmThreads, HODINA ? 2 : 3) cdm_enum_kernel(c
       __syncwarp();
 #pragma unroll
       for (int k = 0; k < NS; ++k) {
-        if (k < nslots) {
-          const int j = k * 32 + lane;
-          if (j < J && codes[k] != 255u) {
-            const int fl = iflag[j];
-            float R = X[pad_addr(imask[j])];
-            R = (fl & 2) ? 0.f : ((fl & 1) ? 1.f - R : R);     // posterior mass with eta_cj = 1
-            if (codes[k] != 0u) { accS1[k] += R; accN1[k] += 1.f; }
-            else { accS0[k] += R; accN0[k] += 1.f; }
-          }
+        if (codes[k] != 255u) {
+          float R = it_addr[k] >= 0 ? X[it_addr[k]] : 0.f;
+          R = (it_flag[k] & 2) ? 0.f : ((it_flag[k] & 1) ? 1.f - R : R);     // posterior mass with eta_cj = 1
+          if (codes[k] != 0u) { accS1[k] += R; accN1[k] += 1.f; }
+          else { accS0[k] += R; accN0[k] += 1.f; }
         }
       }
       __syncwarp();
