@@ -46,7 +46,25 @@ size_t vipsy_irt_workspace_bytes(const VipsyIrtArgs* a) {
   return mirt_workspace_bytes(a);
 }
 
+// B == 0: nothing to evaluate; the outputs are defined (loss 0, item gradients 0) and no kernel needs a pointer
+static int irt_empty_batch(const VipsyIrtArgs* a, cudaStream_t st) {
+  const size_t J = (size_t)a->n_items, K = (size_t)a->n_dims;
+  VIPSY_REQUIRE(a->loss, VIPSY_ERR_ARG, "vipsy_irt: loss is required");
+  VIPSY_CUDA_CHECK(cudaMemsetAsync(a->loss, 0, 8, st));
+  if (a->d_b) VIPSY_CUDA_CHECK(cudaMemsetAsync(a->d_b, 0, J * 4, st));
+  if (a->d_a && a->model >= VIPSY_IRT_2PL) VIPSY_CUDA_CHECK(cudaMemsetAsync(a->d_a, 0, K * J * 4, st));
+  if (a->d_c && a->model >= VIPSY_IRT_3PL) VIPSY_CUDA_CHECK(cudaMemsetAsync(a->d_c, 0, J * 4, st));
+  if (a->d_d && a->model >= VIPSY_IRT_4PL) VIPSY_CUDA_CHECK(cudaMemsetAsync(a->d_d, 0, J * 4, st));
+  if (a->d_chol && a->cov_mode == VIPSY_COV_SHARED) {
+    const size_t n = a->chol_layout == VIPSY_CHOL_PACKED ? K * (K + 1) / 2 : K * K;
+    VIPSY_CUDA_CHECK(cudaMemsetAsync(a->d_chol, 0, n * 4, st));
+  }
+  return VIPSY_OK;
+}
+
 int vipsy_irt_elbo_grad(const VipsyIrtArgs* a, void* stream) {
+  if (a && a->batch == 0 && a->n_items > 0 && a->n_dims > 0 && a->model >= VIPSY_IRT_1PL && a->model <= VIPSY_IRT_4PL)
+    return irt_empty_batch(a, (cudaStream_t)stream);
   int rc = check_irt(a);
   if (rc != VIPSY_OK) return rc;
   if (a->n_dims == 1) return irt_uni_launch(a, (cudaStream_t)stream);

@@ -503,7 +503,7 @@ constexpr int kCdmMaxCtasPerSM = 8;
 
 size_t cdm_enum_workspace_bytes(const VipsyCdmEnumArgs* a) {
   const size_t rows = (size_t)num_sms() * kCdmMaxCtasPerSM;
-  return ((rows * 8 + 15) & ~size_t(15)) + rows * (2 * (size_t)a->n_items + 2 * (size_t)a->n_attrs) * 4;
+  return (((rows + kMaskRows) * 8 + 15) & ~size_t(15)) + rows * (2 * (size_t)a->n_items + 2 * (size_t)a->n_attrs) * 4;
 }
 
 int cdm_enum_launch(const VipsyCdmEnumArgs* a, cudaStream_t st) {
@@ -517,7 +517,7 @@ int cdm_enum_launch(const VipsyCdmEnumArgs* a, cudaStream_t st) {
   p.want_grad = (a->d_g || a->d_s || a->d_lam0 || a->d_lam1) ? 1 : 0;
   const size_t rows_max = (size_t)num_sms() * kCdmMaxCtasPerSM;
   p.loss_partial = reinterpret_cast<double*>(a->workspace);
-  p.partial = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(a->workspace) + ((rows_max * 8 + 15) & ~size_t(15)));
+  p.partial = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(a->workspace) + (((rows_max + kMaskRows) * 8 + 15) & ~size_t(15)));
   const size_t smem = cdm_smem_bytes(p.J);
   const int ns = p.J <= 64 ? 2 : (p.J <= 128 ? 4 : 8);
   void (*kern)(const CdmEnumParams);
@@ -539,6 +539,14 @@ int cdm_enum_launch(const VipsyCdmEnumArgs* a, cudaStream_t st) {
   if (ctas < 1) ctas = 1;
   kern<<<(int)ctas, kCdmThreads, smem, st>>>(p);
   VIPSY_CUDA_CHECK(cudaGetLastError());
+  // masked cells (VCCDM masks them, vi.py:852-856): log(1 - eps) each in every pattern's log-likelihood, i.e. a
+  // constant of the person's marginal
+  int mask_rows = 0;
+  {
+    int rc = launch_masked_term(a->y, a->y_row_stride, a->idx, a->batch, p.J, a->scale, -1, p.loss_partial + ctas,
+                                &mask_rows, st);
+    if (rc != VIPSY_OK) return rc;
+  }
   FinalizeSegs segs{};
   segs.n = 4;
   segs.out[0] = a->d_g; segs.cols[0] = p.J;
@@ -550,7 +558,7 @@ int cdm_enum_launch(const VipsyCdmEnumArgs* a, cudaStream_t st) {
   // columns are sums over particles: alpha = -scale / S.  Two finalize launches keep it simple.
   if (p.want_grad) {
     FinalizeSegs s1 = segs; s1.out[2] = nullptr; s1.out[3] = nullptr;
-    int rc = launch_finalize(p.partial, (int)ctas, 2 * p.J + 2 * p.K, -a->scale, s1, p.loss_partial, (int)ctas, a->loss, st);
+    int rc = launch_finalize(p.partial, (int)ctas, 2 * p.J + 2 * p.K, -a->scale, s1, p.loss_partial, (int)ctas + mask_rows, a->loss, st);
     if (rc != VIPSY_OK) return rc;
     if (a->hodina && (a->d_lam0 || a->d_lam1)) {
       FinalizeSegs s2 = segs; s2.out[0] = nullptr; s2.out[1] = nullptr;
@@ -558,7 +566,7 @@ int cdm_enum_launch(const VipsyCdmEnumArgs* a, cudaStream_t st) {
     }
     return VIPSY_OK;
   }
-  return launch_finalize(nullptr, 0, 0, alpha, segs, p.loss_partial, (int)ctas, a->loss, st);
+  return launch_finalize(nullptr, 0, 0, alpha, segs, p.loss_partial, (int)ctas + mask_rows, a->loss, st);
 }
 
 }  // namespace vipsy
@@ -579,6 +587,16 @@ int vipsy_cdm_enum_elbo_grad(const VipsyCdmEnumArgs* a, void* stream) {
   VIPSY_REQUIRE(a->batch >= 0 && a->n_items > 0 && a->n_attrs > 0 && a->n_particles > 0, VIPSY_ERR_ARG,
                 "vipsy_cdm_enum: bad sizes B=%lld J=%d K=%d S=%d", (long long)a->batch, a->n_items, a->n_attrs,
                 a->n_particles);
+  if (a->batch == 0) {                       // nothing to evaluate: loss 0, gradients 0
+    VIPSY_REQUIRE(a->loss, VIPSY_ERR_ARG, "vipsy_cdm_enum: loss is required");
+    cudaStream_t st = (cudaStream_t)stream;
+    VIPSY_CUDA_CHECK(cudaMemsetAsync(a->loss, 0, 8, st));
+    if (a->d_g) VIPSY_CUDA_CHECK(cudaMemsetAsync(a->d_g, 0, (size_t)a->n_items * 4, st));
+    if (a->d_s) VIPSY_CUDA_CHECK(cudaMemsetAsync(a->d_s, 0, (size_t)a->n_items * 4, st));
+    if (a->d_lam0) VIPSY_CUDA_CHECK(cudaMemsetAsync(a->d_lam0, 0, (size_t)a->n_attrs * 4, st));
+    if (a->d_lam1) VIPSY_CUDA_CHECK(cudaMemsetAsync(a->d_lam1, 0, (size_t)a->n_attrs * 4, st));
+    return VIPSY_OK;
+  }
   VIPSY_REQUIRE(a->n_attrs <= 10, VIPSY_ERR_UNSUPPORTED,
                 "vipsy_cdm_enum: K=%d attributes (2^K patterns) > 10 is not built", a->n_attrs);
   VIPSY_REQUIRE(a->n_items <= 32 * kMaxSlots, VIPSY_ERR_UNSUPPORTED, "vipsy_cdm_enum: J=%d > %d", a->n_items,

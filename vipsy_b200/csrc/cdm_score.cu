@@ -190,6 +190,14 @@ int vipsy_cdm_score_elbo_grad(const VipsyCdmScoreArgs* a, void* stream) {
                 "vipsy_cdm_score: unknown model %d (CDM_FUN has dina, dino)", a->model);
   VIPSY_REQUIRE(a->batch >= 0 && a->n_items > 0 && a->n_attrs > 0 && a->n_particles > 0, VIPSY_ERR_ARG,
                 "vipsy_cdm_score: bad sizes");
+  if (a->batch == 0) {                       // nothing to evaluate: loss 0, gradients 0
+    VIPSY_REQUIRE(a->loss, VIPSY_ERR_ARG, "vipsy_cdm_score: loss is required");
+    cudaStream_t st = (cudaStream_t)stream;
+    VIPSY_CUDA_CHECK(cudaMemsetAsync(a->loss, 0, 8, st));
+    if (a->d_g) VIPSY_CUDA_CHECK(cudaMemsetAsync(a->d_g, 0, (size_t)a->n_items * 4, st));
+    if (a->d_s) VIPSY_CUDA_CHECK(cudaMemsetAsync(a->d_s, 0, (size_t)a->n_items * 4, st));
+    return VIPSY_OK;
+  }
   VIPSY_REQUIRE(a->n_attrs <= 32 && a->n_items <= 32 * kScSlots, VIPSY_ERR_UNSUPPORTED,
                 "vipsy_cdm_score: K=%d (<=32) J=%d (<=%d)", a->n_attrs, a->n_items, 32 * kScSlots);
   VIPSY_REQUIRE(a->y && a->qmask && a->g && a->s && a->attr_p && a->loss, VIPSY_ERR_ARG,

@@ -189,4 +189,11 @@ struct FinalizeSegs {
 int launch_finalize(const float* partial, int rows, int cols, float alpha, const FinalizeSegs& segs,
                     const double* loss_partial, int loss_rows, double* loss_out, cudaStream_t stream);
 
+
+// -scale * log(1-eps) * (masked cells among the batch rows) as extra fp64 loss partial rows (util.cu);
+// known >= 0: the caller's count is used instead of a pass over y.  Writes *n_rows <= kMaskRows rows.
+constexpr int kMaskRows = 296;
+int launch_masked_term(const uint8_t* y, int64_t ld, const int64_t* idx, int64_t B, int J, float scale, int64_t known,
+                       double* out_rows, int* n_rows, cudaStream_t st);
+
 }  // namespace vipsy

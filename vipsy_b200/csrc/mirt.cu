@@ -466,7 +466,7 @@ static MirtLayout mirt_layout(const VipsyIrtArgs* a) {
   L.item_part = o; o += a16((size_t)kMirtMaxGrid * (K * J + 3 * J) * 4);
   L.chol_part = o; o += a16(a->cov_mode == VIPSY_COV_SHARED ? (size_t)kMirtMaxGrid * tri * 4 : 0);
   L.chol_tmp = o; o += a16(a->cov_mode == VIPSY_COV_SHARED ? tri * 4 : 0);
-  L.loss_part = o; o += a16((size_t)kMirtMaxGrid * 8);
+  L.loss_part = o; o += a16((size_t)(kMirtMaxGrid + kMaskRows) * 8);
   L.total = o;
   return L;
 }
@@ -597,6 +597,14 @@ int mirt_launch(const VipsyIrtArgs* a, cudaStream_t st) {
     mirt_cholgrad_kernel<<<grid3, kCgThreads, smem, st>>>(p);
     VIPSY_CUDA_CHECK(cudaGetLastError());
   }
+  // masked cells: log(1 - eps) each (common.cuh), as extra loss partial rows
+  int mask_rows = 0;
+  {
+    int rc = launch_masked_term(a->y, a->y_row_stride, a->idx, a->batch, J, a->scale,
+                                (a->flags & VIPSY_IRT_FLAG_MASKED_KNOWN) ? a->n_masked_cells : -1,
+                                p.loss_partial + grid3, &mask_rows, st);
+    if (rc != VIPSY_OK) return rc;
+  }
   // (4) fixed-order reductions: item gradients (+ loss), shared-covariance gradient
   {
     FinalizeSegs segs{};
@@ -606,7 +614,7 @@ int mirt_launch(const VipsyIrtArgs* a, cudaStream_t st) {
     segs.out[2] = a->model >= VIPSY_IRT_3PL ? a->d_c : nullptr; segs.cols[2] = J;
     segs.out[3] = a->model >= VIPSY_IRT_4PL ? a->d_d : nullptr; segs.cols[3] = J;
     int rc = launch_finalize(p.item_partial, grid2, K * J + 3 * J, -a->scale / (float)a->n_particles, segs,
-                             p.loss_partial, grid3, a->loss, st);
+                             p.loss_partial, grid3 + mask_rows, a->loss, st);
     if (rc != VIPSY_OK) return rc;
   }
   if (shared_cov && a->d_chol) {

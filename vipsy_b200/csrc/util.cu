@@ -96,6 +96,79 @@ int launch_finalize(const float* partial, int rows, int cols, float alpha, const
 }
 
 // ---------------------------------------------------------------------------
+// Masked cells score log(1 - eps) each (kMaskedLogProb) and nothing else.  The K = 1 particle kernel sits at its
+// register cap (any extra work in it costs 3-5 % through re-planned register allocation, measured) and the
+// K > 1 / enumeration kernels never look at a masked cell at all, so this constant of the batch is produced by a
+// side kernel: CTA b writes -scale * log(1-eps) * (masked cells of its rows) as one more fp64 loss partial;
+// integer counts, fixed order => deterministic.  With the count known to the caller (the response matrix never
+// changes between steps) one thread just writes it.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ int missing_in(const int4& v) {      // codes are 0 / 1 / 255: bit 1 marks a missing cell
+  return __popc((uint32_t)v.x & 0x02020202u) + __popc((uint32_t)v.y & 0x02020202u) +
+         __popc((uint32_t)v.z & 0x02020202u) + __popc((uint32_t)v.w & 0x02020202u);
+}
+__global__ void __launch_bounds__(256) masked_term_kernel(const uint8_t* __restrict__ y, int64_t ld,
+                                                          const int64_t* __restrict__ idx, int64_t B, int J,
+                                                          float scale, int64_t known, double* __restrict__ out) {
+  if (known >= 0) {
+    if (threadIdx.x == 0) out[blockIdx.x] = blockIdx.x == 0 ? -(double)scale * (double)kMaskedLogProb * (double)known : 0.0;
+    return;
+  }
+  __shared__ long long part[8];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  long long n = 0;
+  if (idx == nullptr && ld == J) {
+    // contiguous batch: one flat byte range, 16-byte loads, four in flight per thread
+    const int64_t total = B * (int64_t)J;
+    const uintptr_t base = reinterpret_cast<uintptr_t>(y);
+    int64_t head = (int64_t)((16 - (base & 15)) & 15);
+    if (head > total) head = total;
+    const int64_t nvec = (total - head) >> 4;
+    const int4* v = reinterpret_cast<const int4*>(y + head);
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (int64_t)gridDim.x * blockDim.x;
+    int64_t i = tid;
+    for (; i + 3 * nth < nvec; i += 4 * nth) {
+      const int4 a = __ldg(v + i), b = __ldg(v + i + nth), c = __ldg(v + i + 2 * nth), d = __ldg(v + i + 3 * nth);
+      n += missing_in(a) + missing_in(b) + missing_in(c) + missing_in(d);
+    }
+    for (; i < nvec; i += nth) n += missing_in(__ldg(v + i));
+    if (blockIdx.x == 0) {
+      for (int64_t k = threadIdx.x; k < head; k += blockDim.x) n += y[k] == 255;
+      for (int64_t k = head + (nvec << 4) + threadIdx.x; k < total; k += blockDim.x) n += y[k] == 255;
+    }
+  } else {
+    for (int64_t r = (int64_t)blockIdx.x * 8 + warp; r < B; r += (int64_t)gridDim.x * 8) {
+      const uint8_t* g = y + (idx ? idx[r] : r) * ld;
+      if (((reinterpret_cast<uintptr_t>(g) | (uintptr_t)J) & 3) == 0) {
+        const uint32_t* gw = reinterpret_cast<const uint32_t*>(g);
+        for (int w = lane; w < (J >> 2); w += 32) n += __popc(__ldg(gw + w) & 0x02020202u);
+      } else {
+        for (int j = lane; j < J; j += 32) n += g[j] == 255;
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) n += __shfl_xor_sync(0xffffffffu, n, o);
+  if (lane == 0) part[warp] = n;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    long long t = 0;
+    for (int w = 0; w < 8; ++w) t += part[w];
+    out[blockIdx.x] = -(double)scale * (double)kMaskedLogProb * (double)t;
+  }
+}
+
+int launch_masked_term(const uint8_t* y, int64_t ld, const int64_t* idx, int64_t B, int J, float scale, int64_t known,
+                       double* out_rows, int* n_rows, cudaStream_t st) {
+  int rows = known >= 0 ? 1 : (int)((B + 63) / 64 < kMaskRows ? (B + 63) / 64 : kMaskRows);
+  if (rows < 1) rows = 1;
+  masked_term_kernel<<<rows, 256, 0, st>>>(y, ld, idx, B, J, scale, known, out_rows);
+  VIPSY_CUDA_CHECK(cudaGetLastError());
+  *n_rows = rows;
+  return VIPSY_OK;
+}
+
+// ---------------------------------------------------------------------------
 // float responses with NaN = missing (vi.py:621) -> one byte per cell
 // ---------------------------------------------------------------------------
 __global__ void pack_responses_kernel(const float* __restrict__ y, int64_t n, uint8_t* __restrict__ out) {
