@@ -212,6 +212,12 @@ typedef struct VipsyCdmEnumArgs {
   float* posterior;        /* optional B x C pattern posterior (read-out), or NULL */
   void* workspace;
   size_t workspace_bytes;
+  /* VaeCCDM (vi.py:866-891), ignored with hodina: */
+  const float* log_prior;  /* B x C log Categorical(attr_p).logits of the batch persons, or NULL = uniform prior;
+                              d loss / d log_prior = -scale * posterior                                        */
+  int32_t score_missing;   /* 1: a missing cell is scored as Bernoulli(p).log_prob(-1) = 2 log(1-p) - log p
+                              (the reference substitutes -1 and does not mask, vi.py:881-891); 0: masked     */
+  int32_t reserved2;
 } VipsyCdmEnumArgs;
 
 size_t vipsy_cdm_enum_workspace_bytes(const VipsyCdmEnumArgs* args);

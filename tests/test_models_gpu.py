@@ -156,8 +156,7 @@ def test_vchodina_and_vcdm_steps_run_and_match():
     m2 = vb.VCDM(data=y, q=q, model="dino")
     l0 = m2.fit(max_iter=3)
     assert np.isfinite(l0)
-    with pytest.raises(NotImplementedError):
-        vb.VaeCCDM(data=y, q=q).loss_and_grads(vb.TraceEnum_ELBO(), y)
+
 
 
 def test_host_step_two_bit_transport_matches_device_call():
@@ -306,3 +305,38 @@ def test_cuda_graph_cdm_families(cls):
         svi = infer.SVI(m.model, m.guide, optim=vb.Adam({"lr": 1e-2}), loss=m._default_loss() if hasattr(m, "_default_loss") else vb.TraceEnum_ELBO(), cuda_graph=graph)
         res.append([svi.step(m.data) for _ in range(8)])
     assert np.allclose(res[0], res[1], rtol=1e-4), res
+
+
+def test_vaeccdm_class_matches_oracle_and_trains():
+    """VaeCCDM end to end: the encoder (softmax over the batch axis, sic) receives -scale * posterior through
+    log Categorical(attr_p).logits; first-step loss and g/s gradients equal the oracle's."""
+    import copy
+    g = torch.Generator().manual_seed(5)
+    K, J, N = 3, 18, 120
+    q = (torch.rand(K, J, generator=g) < 0.5).float()
+    q[0, q.sum(0) == 0] = 1.0
+    y = (torch.rand(N, J, generator=g) < 0.5).float()
+    y[torch.rand(N, J, generator=g) < 0.1] = float("nan")
+    torch.manual_seed(1)
+    m = vb.VaeCCDM(data=y, q=q, hidden_dim=8)
+    enc_cpu = copy.deepcopy(m.encoder).cpu()
+    loss, sites = m.loss_and_grads(vb.TraceEnum_ELBO(num_particles=1), y)
+    yin = torch.where(torch.isnan(y), torch.full_like(y, -1.0), y)
+    attr_p = enc_cpu(yin)
+    ref = o.cdm_enum_elbo_grad(y, q, torch.full((1, J), 0.1), torch.full((1, J), 0.1), model="dina",
+                               prior_probs=attr_p.detach(), mask_missing=False)
+    assert_close(loss, ref["loss"], 2e-5, 2e-5, "loss")
+    gr = {n: p.grad for n, p, _ in sites}
+    assert_close(gr["g"], ref["d_g"] * 0.1 * 0.9, 1e-4, 1e-4, "g (unconstrained)")
+    attr_p.backward(ref["d_prior"].float())
+    # fc2.bias has an exactly-zero gradient (a per-pattern shift cancels in the softmax over the batch axis):
+    # compare every tensor on the scale of the largest encoder gradient
+    gmax = max(float(pc.grad.abs().max()) for pc in enc_cpu.parameters())
+    for (n, p), pc in zip(m.encoder.named_parameters(), enc_cpu.parameters()):
+        assert float((p.grad.cpu() - pc.grad).abs().max()) <= 2e-3 * gmax, n
+    vb.clear_param_store()
+    torch.manual_seed(1)
+    m = vb.VaeCCDM(data=y, q=q, hidden_dim=8)
+    first = m.fit(optim=vb.Adam({"lr": 1e-2}), max_iter=1)
+    last = m.fit(optim=vb.Adam({"lr": 1e-2}), max_iter=150)
+    assert last < first

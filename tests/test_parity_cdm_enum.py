@@ -123,3 +123,23 @@ def test_cdm_deterministic_and_idx(ops):
     ref = o.cdm_enum_elbo_grad(y[idx], q, gg, ss, scale=6.0)
     assert_close(sub["loss"], ref["loss"], 1e-5, 1e-5)
     assert_close(sub["d_g"], ref["d_g"], 1e-5, 1e-5)
+
+
+@pytest.mark.parametrize("model", ["dina", "dino"])
+@pytest.mark.parametrize("B,J,K", [(37, 9, 3), (64, 60, 10), (50, 100, 7), (20, 33, 1)])
+def test_vaeccdm_prior_and_scored_missing_cells(ops, model, B, J, K):
+    """VaeCCDM.model (vi.py:872-891): per-person pattern prior through Categorical(probs) (normalise, clamp,
+    log) and missing cells scored as y = -1 instead of masked; d loss / d log_prior = -scale * posterior."""
+    q, y, gg, ss, g = make_cdm(B, J, K, seed=7 * B + K, missing=0.2)
+    C = 2 ** K
+    pp = torch.rand(B, C, generator=g) ** 4 + 1e-9
+    pp[0, 0] = 1e-12                                   # a floored entry
+    ref = o.cdm_enum_elbo_grad(y, q, gg, ss, model=model, scale=2.0, prior_probs=pp, mask_missing=False)
+    prior = (pp.double() / pp.double().sum(-1, keepdim=True)).clamp(min=o.EPS32, max=1 - o.EPS32)
+    got = ops.cdm_enum_elbo_grad(codes_from_float(y).cuda(), q.cuda(), gg.cuda(), ss.cuda(), model=model, scale=2.0,
+                                 log_prior=prior.log().float().cuda(), score_missing=True, want_posterior=True)
+    torch.cuda.synchronize()
+    assert_close(got["loss"], ref["loss"], 1e-5, 1e-5, "loss")
+    assert_close(got["d_g"], ref["d_g"], 1e-5, 1e-5, "d_g")
+    assert_close(got["d_s"], ref["d_s"], 1e-5, 1e-5, "d_s")
+    assert_close(got["posterior"], ref["posterior"], 1e-4, 1e-5, "posterior")

@@ -68,6 +68,7 @@ class CdmEnumArgs(C.Structure):
         ("seed", C.c_uint64), ("offset", C.c_uint64), ("person_offset", C.c_int64),
         ("loss", _p), ("d_g", _p), ("d_s", _p), ("d_lam0", _p), ("d_lam1", _p), ("d_mu", _p), ("d_sigma", _p),
         ("posterior", _p), ("workspace", _p), ("workspace_bytes", C.c_size_t),
+        ("log_prior", _p), ("score_missing", C.c_int32), ("reserved2", C.c_int32),
     ]
 
 

@@ -46,6 +46,8 @@ struct CdmEnumParams {
   uint64_t seed, offset;
   int64_t person_offset;
   float *d_mu, *d_sigma, *posterior;
+  const float* log_prior;   // B x 2^K per-person log pattern prior (VaeCCDM, vi.py:880-886) or null = uniform
+  int score_missing;
   float* partial;        // [grid][2J + 2K]
   double* loss_partial;  // [grid]
   int want_grad;
@@ -140,10 +142,14 @@ struct ItemConst {      // per item, built once per CTA
   float delta1, delta0; // lb(y | eta = 1) - lb(y | eta = 0)
   float da1, da0;       // d lb(y|eta=1) / d s   for y = 1, 0
   float db1, db0;       // d lb(y|eta=0) / d g   for y = 1, 0
+  // VaeCCDM scores a missing cell as Bernoulli(p).log_prob(-1) = 2 log(1-p) - log p (vi.py:881-891: y = -1, no mask)
+  float baseM, deltaM, daM, dbM;
 };
 
 // NS: 32-item slots per lane (J <= 32 NS); the per-lane item accumulators are 4 NS registers
-template <bool HODINA, int NS>
+// SCOREM (the VaeCCDM variant): per-person log prior input and / or missing cells scored as a third response
+// category instead of being skipped.  A separate instantiation: the plain kernel keeps its register budget.
+template <bool HODINA, int NS, bool SCOREM = false>
 __global__ void __launch_bounds__(kCdmThreads, HODINA ? 2 : 3) cdm_enum_kernel(const CdmEnumParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int J = p.J, K = p.K;
@@ -172,10 +178,13 @@ __global__ void __launch_bounds__(kCdmThreads, HODINA ? 2 : 3) cdm_enum_kernel(c
     const float k1 = (p1 == p1c) ? 1.f : 0.f, k0 = (p0 == p0c) ? 1.f : 0.f;   // clamp => zero gradient
     c.da1 = -k1 / p1c; c.da0 = k1 / (1.f - p1c);              // d/ds of log(1-s), log(s)
     c.db1 = k0 / p0c;  c.db0 = -k0 / (1.f - p0c);             // d/dg of log(g), log(1-g)
+    c.baseM = 2.f * b0 - b1; c.deltaM = (2.f * a0 - a1) - (2.f * b0 - b1);
+    c.daM = k1 * (2.f / (1.f - p1c) + 1.f / p1c);             // d/ds of 2 log(s) - log(1-s)
+    c.dbM = k0 * (-2.f / (1.f - p0c) - 1.f / p0c);            // d/dg of 2 log(1-g) - log(g)
     const uint32_t m = p.qmask[j] & (uint32_t)((1u << K) - 1u);
     int flag = 0;                                             // bit0: inverted (DINO), bit1: dead (eta == 0)
     if (dino) flag = (__popc(m) >= 2) ? 1 : 2;
-    if (flag & 1) { c.delta1 = -c.delta1; c.delta0 = -c.delta0; }   // ll = base + delta - delta [q subset ~c]
+    if (flag & 1) { c.delta1 = -c.delta1; c.delta0 = -c.delta0; c.deltaM = -c.deltaM; }   // ll = base + delta - delta [q subset ~c]
     ic[j] = c;
     imask[j] = (int)m;
     iflag[j] = flag;
@@ -195,15 +204,17 @@ __global__ void __launch_bounds__(kCdmThreads, HODINA ? 2 : 3) cdm_enum_kernel(c
   constexpr int nslots = NS;
 
   // per-lane item accumulators: slot k <-> item k*32 + lane
-  float accS1[NS], accS0[NS], accN1[NS], accN0[NS];
+  float accS1[NS], accS0[NS], accN1[NS], accN0[NS], accSM[SCOREM ? NS : 1], accNM[SCOREM ? NS : 1];
 #pragma unroll
   for (int k = 0; k < NS; ++k) accS1[k] = accS0[k] = accN1[k] = accN0[k] = 0.f;
+#pragma unroll
+  for (int k = 0; k < (SCOREM ? NS : 1); ++k) accSM[k] = accNM[k] = 0.f;
   float accL0 = 0.f, accL1 = 0.f;     // HO-DINA: lane (2k, 2k+1) accumulates d lam0_k, d lam1_k
   double loss_acc = 0.0;
   // this lane's items (slot k <-> item k*32 + lane), hoisted out of the person loop: lattice address of the
   // item's mask (-1: no lattice term), duplicate-mask round, flags, and the y = 1 / 0 constants
   int it_addr[NS], it_round[NS], it_flag[NS];
-  float it_b1[NS], it_b0[NS], it_d1[NS], it_d0[NS];
+  float it_b1[NS], it_b0[NS], it_d1[NS], it_d0[NS], it_bM[SCOREM ? NS : 1], it_dM[SCOREM ? NS : 1];
 #pragma unroll
   for (int k = 0; k < NS; ++k) {
     const int j = k * 32 + lane;
@@ -218,6 +229,10 @@ __global__ void __launch_bounds__(kCdmThreads, HODINA ? 2 : 3) cdm_enum_kernel(c
       it_d1[k] = c.delta1; it_d0[k] = c.delta0;
       it_b1[k] = c.base1 + ((fl & 1) ? -c.delta1 : 0.f);
       it_b0[k] = c.base0 + ((fl & 1) ? -c.delta0 : 0.f);
+      if constexpr (SCOREM) {
+        it_dM[k] = c.deltaM;
+        it_bM[k] = c.baseM + ((fl & 1) ? -c.deltaM : 0.f);
+      }
     }
   }
 
@@ -245,13 +260,23 @@ __global__ void __launch_bounds__(kCdmThreads, HODINA ? 2 : 3) cdm_enum_kernel(c
         if (j < J) codes[k] = yrow[j];
       }
     }
+    // SCOREM: a missing cell of a real item becomes code 2 (third category), padding slots stay 255
+    if constexpr (SCOREM) {
+      if (p.score_missing) {
+#pragma unroll
+        for (int k = 0; k < NS; ++k)
+          if (codes[k] == 255u && k * 32 + lane < J) codes[k] = 2u;
+      }
+    }
 #pragma unroll
     for (int k = 0; k < NS; ++k)
-      if (codes[k] != 255u) base_part += codes[k] != 0u ? it_b1[k] : it_b0[k];
+      if (codes[k] != 255u)
+        base_part += (SCOREM && codes[k] == 2u) ? it_bM[SCOREM ? k : 0] : (codes[k] != 0u ? it_b1[k] : it_b0[k]);
     for (int rd = 0; rd <= max_round; ++rd) {          // items sharing a mask take turns (plain read-modify-write)
 #pragma unroll
       for (int k = 0; k < NS; ++k)
-        if (codes[k] != 255u && it_addr[k] >= 0 && it_round[k] == rd) F[it_addr[k]] += codes[k] != 0u ? it_d1[k] : it_d0[k];
+        if (codes[k] != 255u && it_addr[k] >= 0 && it_round[k] == rd)
+          F[it_addr[k]] += (SCOREM && codes[k] == 2u) ? it_dM[SCOREM ? k : 0] : (codes[k] != 0u ? it_d1[k] : it_d0[k]);
       __syncwarp();
     }
     const float base = warp_sum(base_part);
@@ -382,7 +407,30 @@ __global__ void __launch_bounds__(kCdmThreads, HODINA ? 2 : 3) cdm_enum_kernel(c
         gth_eps = fmaf(gth, eps_s, gth_eps);
         if (!(lane & 1)) { accL0 += Mk; accL1 = fmaf(Mk, theta, accL1); }
       } else {
-        // uniform Categorical(1/C): log prior = -K ln2 per real pattern, exact under embedding
+        // uniform Categorical(1/C): log prior = -K ln2 per real pattern, exact under embedding;
+        // or the person's own log prior (VaeCCDM), staged through X so that the global reads are coalesced
+        float prior_const = -10.f * kLn2;
+        if (SCOREM && p.log_prior) {
+          const float* lp = p.log_prior + b * ((int64_t)1 << K);
+          const int cm = (1 << K) - 1;
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            float4 t4;
+            const int c0 = q * 128 + lane * 4;
+            t4.x = lp[(dino ? ~(c0 + 0) : (c0 + 0)) & cm];
+            t4.y = lp[(dino ? ~(c0 + 1) : (c0 + 1)) & cm];
+            t4.z = lp[(dino ? ~(c0 + 2) : (c0 + 2)) & cm];
+            t4.w = lp[(dino ? ~(c0 + 3) : (c0 + 3)) & cm];
+            *reinterpret_cast<float4*>(X + q * 132 + lane * 4) = t4;
+          }
+          __syncwarp();
+          float2 lpv[16];
+          load_B(X, lpv, lane);
+          __syncwarp();
+#pragma unroll
+          for (int k = 0; k < 16; ++k) v[k] = __fadd2_rn(v[k], lpv[k]);
+          prior_const = -shift;                    // each real pattern is replicated 2^(10-K) times
+        }
         float m = -3.0e38f;
 #pragma unroll
         for (int k = 0; k < 16; ++k) m = fmaxf(m, fmaxf(v[k].x, v[k].y));
@@ -398,7 +446,7 @@ __global__ void __launch_bounds__(kCdmThreads, HODINA ? 2 : 3) cdm_enum_kernel(c
         }
         const float ssum = warp_sum(ss.x + ss.y);
         const float inv = 1.f / ssum;
-        marg_sum += m + logf(ssum) + base - 10.f * kLn2;
+        marg_sum += m + logf(ssum) + base + prior_const;
         const float2 inv2 = make_float2(inv, inv);
 #pragma unroll
         for (int k = 0; k < 16; ++k) post[k] = __fmul2_rn(post[k], inv2);
@@ -448,7 +496,8 @@ __global__ void __launch_bounds__(kCdmThreads, HODINA ? 2 : 3) cdm_enum_kernel(c
         if (codes[k] != 255u) {
           float R = it_addr[k] >= 0 ? X[it_addr[k]] : 0.f;
           R = (it_flag[k] & 2) ? 0.f : ((it_flag[k] & 1) ? 1.f - R : R);     // posterior mass with eta_cj = 1
-          if (codes[k] != 0u) { accS1[k] += R; accN1[k] += 1.f; }
+          if (SCOREM && codes[k] == 2u) { accSM[SCOREM ? k : 0] += R; accNM[SCOREM ? k : 0] += 1.f; }
+          else if (codes[k] != 0u) { accS1[k] += R; accN1[k] += 1.f; }
           else { accS0[k] += R; accN0[k] += 1.f; }
         }
       }
@@ -477,8 +526,14 @@ __global__ void __launch_bounds__(kCdmThreads, HODINA ? 2 : 3) cdm_enum_kernel(c
         if (j < J) {
           const ItemConst c = ic[j];
           // d/dg: eta = 0 mass is (n - S);  d/ds: eta = 1 mass is S
-          red[warp * ncol + j] = (accN1[k] - accS1[k]) * c.db1 + (accN0[k] - accS0[k]) * c.db0;
-          red[warp * ncol + J + j] = accS1[k] * c.da1 + accS0[k] * c.da0;
+          float dg = (accN1[k] - accS1[k]) * c.db1 + (accN0[k] - accS0[k]) * c.db0;
+          float ds = accS1[k] * c.da1 + accS0[k] * c.da0;
+          if constexpr (SCOREM) {
+            dg += (accNM[k] - accSM[k]) * c.dbM;
+            ds += accSM[k] * c.daM;
+          }
+          red[warp * ncol + j] = dg;
+          red[warp * ncol + J + j] = ds;
         }
       }
     }
@@ -514,6 +569,9 @@ int cdm_enum_launch(const VipsyCdmEnumArgs* a, cudaStream_t st) {
   p.model = a->hodina ? VIPSY_CDM_DINA : a->model; p.hodina = a->hodina;
   p.scale = a->scale; p.seed = a->seed; p.offset = a->offset; p.person_offset = a->person_offset;
   p.d_mu = a->d_mu; p.d_sigma = a->d_sigma; p.posterior = a->posterior;
+  p.log_prior = a->hodina ? nullptr : a->log_prior;
+  p.score_missing = a->score_missing != 0 && !a->hodina;
+  const bool scorem = (p.score_missing || p.log_prior) && !a->hodina;
   p.want_grad = (a->d_g || a->d_s || a->d_lam0 || a->d_lam1) ? 1 : 0;
   const size_t rows_max = (size_t)num_sms() * kCdmMaxCtasPerSM;
   p.loss_partial = reinterpret_cast<double*>(a->workspace);
@@ -522,10 +580,11 @@ int cdm_enum_launch(const VipsyCdmEnumArgs* a, cudaStream_t st) {
   const int ns = p.J <= 64 ? 2 : (p.J <= 128 ? 4 : 8);
   void (*kern)(const CdmEnumParams);
   if (a->hodina) kern = ns == 2 ? cdm_enum_kernel<true, 2> : (ns == 4 ? cdm_enum_kernel<true, 4> : cdm_enum_kernel<true, 8>);
+  else if (scorem) kern = ns == 2 ? cdm_enum_kernel<false, 2, true> : (ns == 4 ? cdm_enum_kernel<false, 4, true> : cdm_enum_kernel<false, 8, true>);
   else kern = ns == 2 ? cdm_enum_kernel<false, 2> : (ns == 4 ? cdm_enum_kernel<false, 4> : cdm_enum_kernel<false, 8>);
-  static int occ[6] = {0, 0, 0, 0, 0, 0};
-  static size_t occ_smem[6] = {0, 0, 0, 0, 0, 0};
-  const int which = (a->hodina ? 3 : 0) + (ns == 2 ? 0 : (ns == 4 ? 1 : 2));
+  static int occ[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+  static size_t occ_smem[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+  const int which = (a->hodina ? 3 : (scorem ? 6 : 0)) + (ns == 2 ? 0 : (ns == 4 ? 1 : 2));
   if (smem > 48 * 1024) VIPSY_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   if (occ[which] == 0 || occ_smem[which] != smem) {
     VIPSY_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[which], kern, kCdmThreads, smem));
@@ -542,7 +601,7 @@ int cdm_enum_launch(const VipsyCdmEnumArgs* a, cudaStream_t st) {
   // masked cells (VCCDM masks them, vi.py:852-856): log(1 - eps) each in every pattern's log-likelihood, i.e. a
   // constant of the person's marginal
   int mask_rows = 0;
-  {
+  if (!p.score_missing) {
     int rc = launch_masked_term(a->y, a->y_row_stride, a->idx, a->batch, p.J, a->scale, -1, p.loss_partial + ctas,
                                 &mask_rows, st);
     if (rc != VIPSY_OK) return rc;

@@ -517,6 +517,7 @@ class VCCDM(BaseCDM):                   # vi.py:819-863  (exact enumeration of t
         """Per-person posterior over attribute patterns at the current parameters (read-out)."""
         _, _, g, s = self._gs()
         extra, _, _ = self._enum_extra(None, self.sample_size)
+        extra = {k: v for k, v in extra.items() if k != "want_posterior"}
         r = ops.cdm_enum_elbo_grad(self._codes, self._qmask, g, s, n_attrs=self.attr_size, model=self._model,
                                    want_grad=False, want_posterior=True, **extra, **self._noise_args())
         return r["posterior"]
@@ -528,9 +529,20 @@ class VaeCCDM(VCCDM):                   # vi.py:866-891
         self.encoder = SoftmaxEncoder(self.item_size, self.all_attr.size(0), hidden_dim).to(self.device)
 
     def _enum_extra(self, idx, B):
-        raise NotImplementedError(
-            "VaeCCDM needs a per-person pattern prior input to the enumeration kernel; not built yet "
-            "(SURVEY 8a row a12 marks its encoder part out of scope)")
+        """vi.py:878-886: attr_p = encoder(data with NaN -> -1) -- a softmax over the BATCH axis (sic, vi.py:480) --
+        becomes the pattern prior through Categorical(probs=attr_p): normalise over patterns, clamp, log (A.4).
+        The missing cells stay in as y = -1 (no mask, vi.py:887-891): ``score_missing``."""
+        get_param_store().register_module("encoder", self.encoder)
+        attr_p = self.encoder(self._encoder_input(idx))
+        prior = attr_p / attr_p.sum(-1, keepdim=True)
+        eps = torch.finfo(torch.float32).eps
+        log_prior = torch.log(prior.clamp(min=eps, max=1.0 - eps))
+        scale = self.sample_size / B
+
+        def backward(r, w):
+            torch.autograd.backward([log_prior], [r["posterior"] * (-scale * w)])
+        return (dict(log_prior=log_prior.detach(), score_missing=True, want_posterior=True), backward,
+                [(f"encoder$$${n}", p, None) for n, p in self.encoder.named_parameters()])
 
 
 class VCHoDina(VCCDM):                  # vi.py:894-958

@@ -323,9 +323,12 @@ def cdm_enum_elbo_grad(
     eps: Optional[torch.Tensor] = None, n_particles: int = 1,
     seed: int = 0, offset: int = 0, person_offset: int = 0,
     want_grad: bool = True, want_posterior: bool = False,
+    log_prior: Optional[torch.Tensor] = None, score_missing: bool = False,
 ) -> Dict[str, Optional[torch.Tensor]]:
     """TraceEnum_ELBO.loss_and_grads for VCCDM.model (vi.py:839-857) or, when lam0/lam1/mu/sigma
-    are given, VCHoDina (vi.py:897-934): exact marginal over the 2^K attribute patterns."""
+    are given, VCHoDina (vi.py:897-934): exact marginal over the 2^K attribute patterns.
+    ``log_prior`` (B x 2^K) + ``score_missing`` give VaeCCDM.model (vi.py:872-891): per-person pattern prior
+    from the encoder, missing cells scored as y = -1; d loss / d log_prior = -scale * out["posterior"]."""
     if not y.is_cuda or y.dtype != torch.uint8 or y.dim() != 2 or y.stride(1) != 1:
         raise ValueError("y must be a CUDA uint8 code matrix with unit column stride")
     dev = y.device
@@ -382,12 +385,19 @@ def cdm_enum_elbo_grad(
     if want_posterior:
         out["posterior"] = torch.zeros((B, 2 ** K), dtype=torch.float32, device=dev)
         args.posterior = _ptr(out["posterior"])
+    lp_ = None
+    if log_prior is not None:
+        if hod:
+            raise ValueError("log_prior is for the VCCDM / VaeCCDM model, not HO-DINA")
+        lp_ = _f32(log_prior, "log_prior", B * 2 ** K)
+        args.log_prior = _ptr(lp_)
+    args.score_missing = int(bool(score_missing))
     L = N.lib()
     ws = _workspace("cdm_enum", L.vipsy_cdm_enum_workspace_bytes(C.byref(args)), dev)
     args.workspace, args.workspace_bytes = _ptr(ws), ws.numel()
     N.check(L.vipsy_cdm_enum_elbo_grad(C.byref(args), _stream()))
     out["loss"] = loss
-    out["_keepalive"] = (qm, g_, s_, idx_, eps_, ws, args)
+    out["_keepalive"] = (qm, g_, s_, idx_, eps_, ws, args, lp_)
     return out
 
 
