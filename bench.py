@@ -284,7 +284,7 @@ def run_ours(args, rank, world, local_rank):
     kernel_ms = sum(kms) / len(kms)
 
     # ---- e2e: host buffers in, host results out, every step -----------------
-    host = IrtHostStep(N_PERSONS, N_ITEMS, MODEL, n_chunks=4, device=dev)
+    host = IrtHostStep(N_PERSONS, N_ITEMS, MODEL, n_chunks=6, device=dev)
     # responses in the 2-bit host transport format (4 cells per byte, packed once when the data are loaded)
     hy = ops.pack_responses_2bit_host(w["y"].cpu(), pin=True)
     hmu = torch.empty(w["mu"].shape, dtype=torch.float32, pin_memory=True).copy_(w["mu"])
@@ -349,7 +349,7 @@ def run_ours(args, rank, world, local_rank):
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": host.h2d_bytes,
                 "d2h_bytes_per_step": host.d2h_bytes, "ms_per_step": e2e_s * 1e3,
                 "how": "vipsy_irt_host_step (C ABI, host buffers): pinned host y (2-bit transport rows) / mu / sigma -> "
-                       "4-chunk 3-stream pipeline (copy, expand + fused kernel, copy back) -> host per-person and item "
+                       "6-chunk (wave-aligned, small first chunk) 3-stream pipeline (copy, expand + fused kernel, copy back) -> host per-person and item "
                        "grads + loss"},
         "gpu_launches": gpu_launches,
         "roofline": {"bound": "hbm", "achieved": achieved_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",

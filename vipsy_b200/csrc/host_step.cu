@@ -114,12 +114,27 @@ int vipsy_irt_host_step(const VipsyIrtHostArgs* h) {
   if (a.model >= 3) VIPSY_CUDA_CHECK(cudaMemcpyAsync(items + 2 * J, h->c_host, (size_t)J * 4, cudaMemcpyHostToDevice, s_in));
   if (a.model >= 4) VIPSY_CUDA_CHECK(cudaMemcpyAsync(items + 3 * J, h->d_host, (size_t)J * 4, cudaMemcpyHostToDevice, s_in));
 
-  int64_t per = (N + h->n_chunks - 1) / h->n_chunks;
-  per = (per + 31) / 32 * 32;                                   // whole warps of persons per chunk
+  // Chunk schedule: sizes in whole "waves" of the persistent particle kernel (SMs x 4 CTAs x 4 warps x 32
+  // persons per round; a chunk of 3.3 waves costs 4 rounds) when the batch is that large, else whole warps.
+  // The first chunk is a single wave so that the first kernel starts after a ~2 MB copy, not a quarter of
+  // the matrix.
+  const int64_t wave = (int64_t)num_sms() * 4 * 4 * 32;
+  int64_t first = 0, per;
+  if (h->n_chunks >= 3 && N >= 6 * wave) {
+    first = wave;
+    per = (N - first + h->n_chunks - 2) / (h->n_chunks - 1);
+    per = (per + wave - 1) / wave * wave;
+  } else {
+    per = (N + h->n_chunks - 1) / h->n_chunks;
+    if (per >= 2 * wave) per = (per + wave - 1) / wave * wave;
+  }
+  per = (per + 31) / 32 * 32;
   if (per < 32) per = 32;
   int used = 0;
-  for (int64_t s0 = 0; s0 < N; s0 += per, ++used) {
-    const int64_t n = (N - s0 < per) ? N - s0 : per;
+  for (int64_t s0 = 0; s0 < N; ++used) {
+    const int64_t want = (used == 0 && first > 0) ? first : per;
+    const int64_t n = (N - s0 < want) ? N - s0 : want;
+    VIPSY_REQUIRE(used < h->n_chunks, VIPSY_ERR_UNSUPPORTED, "vipsy_irt_host_step: chunk schedule overflow");
     cudaEvent_t ev_in = pool.get(2 * used), ev_run = pool.get(2 * used + 1);
     VIPSY_REQUIRE(ev_in && ev_run, VIPSY_ERR_CUDA, "vipsy_irt_host_step: cudaEventCreate failed");
     uint8_t* y = base + L.y + (size_t)s0 * J;
@@ -167,6 +182,7 @@ int vipsy_irt_host_step(const VipsyIrtHostArgs* h) {
       VIPSY_CUDA_CHECK(cudaMemcpyAsync(h->d_mu_host + s0, dmu, (size_t)n * 4, cudaMemcpyDeviceToHost, s_out));
       VIPSY_CUDA_CHECK(cudaMemcpyAsync(h->d_sigma_host + s0, dsg, (size_t)n * 4, cudaMemcpyDeviceToHost, s_out));
     }
+    s0 += n;
   }
   // chunk sums in chunk order, then the small read-back
   float* gsum = reinterpret_cast<float*>(base + L.gsum);
