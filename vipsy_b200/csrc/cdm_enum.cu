@@ -150,7 +150,7 @@ struct ItemConst {      // per item, built once per CTA
 // SCOREM (the VaeCCDM variant): per-person log prior input and / or missing cells scored as a third response
 // category instead of being skipped.  A separate instantiation: the plain kernel keeps its register budget.
 template <bool HODINA, int NS, bool SCOREM = false>
-__global__ void __launch_bounds__(kCdmThreads, HODINA ? 2 : 3) cdm_enum_kernel(const CdmEnumParams p) {
+__global__ void __launch_bounds__(kCdmThreads, 3) cdm_enum_kernel(const CdmEnumParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int J = p.J, K = p.K;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
