@@ -222,15 +222,34 @@ def run_ours(args, rank, world, local_rank):
     d_mu = torch.empty((N_PERSONS, 1), dtype=torch.float32, device=dev)
     d_sigma = torch.empty((N_PERSONS, 1), dtype=torch.float32, device=dev)
     state = {"offset": 0, "launches": 0}
+    # N > 1: the step's one exchange (packed item gradients + loss) is a single kernel over NVLink peer memory
+    # (vipsy_peer_allreduce); VIPSY_BENCH_NCCL=1 switches to two NCCL all-reduces for comparison
+    par = None
+    if world > 1 and not os.environ.get("VIPSY_BENCH_NCCL"):
+        from vipsy_b200.dist import PeerAllReduce
+        ok = torch.ones(1, device=dev)
+        try:
+            par = PeerAllReduce(n_float=4 * N_ITEMS, n_double=1, device=dev)
+        except Exception as e:                      # no peer mapping on this box: every rank falls back together
+            print(f"[bench] peer memory unavailable on rank {rank} ({e!r}); using NCCL", file=sys.stderr)
+            ok.zero_()
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if float(ok.item()) == 0.0:
+            par = None
     n_masked = int((w["y"] == 255).sum().item())          # constant of the (fixed) response matrix, counted once
 
     def step():
         state["offset"] += 1
+        g_out, l_out = par.slot_views() if par is not None else (None, None)
         r = ops.irt_elbo_grad(w["y"], w["mu"], sigma=w["sigma"], n_particles=N_PARTICLES, a=w["a"], b=w["b"],
                               c=w["c"], d=w["d"], model=MODEL, scale=scale, seed=20261017, offset=state["offset"],
-                              person_offset=person_offset, d_mu_out=d_mu, d_scale_out=d_sigma, n_masked=n_masked)
+                              person_offset=person_offset, d_mu_out=d_mu, d_scale_out=d_sigma, n_masked=n_masked,
+                              item_grads_out=g_out, loss_out=l_out)
         state["launches"] += 3                      # fused kernel + masked-cell constant + fixed-order finalize
-        if world > 1:                               # item gradients + loss: the only exchange
+        if par is not None:                         # item gradients + loss: the only exchange
+            r["item_grads"], r["loss"] = par.reduce()
+            state["launches"] += 1
+        elif world > 1:
             dist.all_reduce(r["item_grads"])
             dist.all_reduce(r["loss"])
         return r
@@ -342,6 +361,8 @@ def run_ours(args, rank, world, local_rank):
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "persons_per_gpu": N_PERSONS, "items": N_ITEMS, "particles": N_PARTICLES,
                    "model": MODEL, "noise": "in-kernel Philox4x32-10", "parallelism": f"person-shard x{world}",
+                   "exchange": ("none" if world == 1 else ("vipsy_peer_allreduce: one kernel over NVLink peer memory"
+                                                           if par is not None else "2 x NCCL all_reduce")),
                    "l2": "flushed between steps (256 MiB memset outside the per-step events)",
                    "timing": "sum of per-step CUDA-event intervals, max over ranks"},
         "clocks": {"sm_mhz": ck["sm_mhz"], "sm_max_mhz": ck["sm_max_mhz"], "reasons": ck["reasons"],

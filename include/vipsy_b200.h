@@ -291,6 +291,19 @@ int vipsy_fill_uniform_dev(float* out, int32_t n_particles, int64_t batch, int32
                            const uint64_t* offset_dev, int64_t person_offset, void* stream);
 
 /* ------------------------------------------------------------------------
+ * The path's one exchange in a person-sharded job (item / shared-factor / encoder gradients + loss, summed over
+ * ranks) as a single kernel over NVLink peer memory instead of a collective-library call.  peer_bufs_dev: device
+ * array of `world` addresses, entry r = base of rank r's symmetric buffer as mapped into THIS process.  Buffer
+ * layout (identical on all ranks): flag_bytes of flags (world uint32, zero before first use), then two slots of
+ * slot_bytes; a slot holds n_float floats, padding to 8 bytes, n_double doubles.  The caller has this rank's
+ * payload written to slot (epoch & 1) by earlier work on `stream`; epochs start at 1 and grow by 1 per call, the
+ * same on every rank.  Sums are taken in rank order: bit-identical on all ranks.
+ * ---------------------------------------------------------------------- */
+int vipsy_peer_allreduce(const uint64_t* peer_bufs_dev, int32_t rank, int32_t world, int64_t flag_bytes,
+                         int64_t slot_bytes, int32_t n_float, int32_t n_double, float* out_float, double* out_double,
+                         uint32_t epoch, void* stream);
+
+/* ------------------------------------------------------------------------
  * The tail of the patched SVI.step (vi.py:508-515) on the device: multiply the gradient by the site's `free`
  * mask (vi.py:511-512), torch.optim.Adam's default update (one state per parameter tensor, as pyro.optim.Adam
  * keeps them), zero the gradient (vi.py:515) -- one launch for all parameter tensors of the step.

@@ -65,3 +65,14 @@ def test_bad_arguments_are_rejected_without_a_gpu(lib):
     assert lib.vipsy_irt_workspace_bytes(C.byref(a)) == 0
     with pytest.raises(N.VipsyError):
         N.check(lib.vipsy_pack_responses(None, 4, None, None))
+
+
+def test_peer_allreduce_rejects_bad_layouts(lib):
+    """vipsy_peer_allreduce argument validation (the kernel itself needs >= 2 GPUs: scripts/test_peer_allreduce.py)."""
+    f = lib.vipsy_peer_allreduce
+    assert f(None, 0, 2, 1024, 512, 4, 1, None, None, 1, None) == N.ERR_ARG            # no pointer table
+    dummy = C.c_uint64(0)
+    assert f(C.byref(dummy), 2, 2, 1024, 512, 4, 1, None, None, 1, None) == N.ERR_ARG  # rank >= world
+    assert f(C.byref(dummy), 0, 2, 4, 512, 4, 1, None, None, 1, None) == N.ERR_ARG     # flag area too small
+    assert f(C.byref(dummy), 0, 2, 1024, 16, 400, 1, None, None, 1, None) == N.ERR_ARG  # slot too small
+    assert b"vipsy_peer_allreduce" in lib.vipsy_last_error()

@@ -113,6 +113,8 @@ SYMBOLS = {
     "vipsy_fill_normal": (C.c_int, [_p, C.c_int32, C.c_int64, C.c_int32, C.c_uint64, C.c_uint64, C.c_int64, _p]),
     "vipsy_fill_normal_dev": (C.c_int, [_p, C.c_int32, C.c_int64, C.c_int32, C.c_uint64, _p, C.c_int64, _p]),
     "vipsy_fill_uniform_dev": (C.c_int, [_p, C.c_int32, C.c_int64, C.c_int32, C.c_uint64, _p, C.c_int64, _p]),
+    "vipsy_peer_allreduce": (C.c_int, [_p, C.c_int32, C.c_int32, C.c_int64, C.c_int64, C.c_int32, C.c_int32, _p, _p,
+                                       C.c_uint32, _p]),
     "vipsy_adam_step": (C.c_int, [C.POINTER(AdamTensor), C.c_int32, _p, C.c_int32, _p]),
     "vipsy_selftest_umma": (C.c_int, [_p, C.c_int32, C.c_int32, _p, C.c_int32, C.c_int32, _p, C.c_int32, C.c_int32,
                                       C.c_int32, _p]),

@@ -313,6 +313,90 @@ __global__ void __launch_bounds__(256) adam_kernel(const AdamBatch b, const int6
   }
 }
 
+// ---------------------------------------------------------------------------
+// One-shot all-reduce over NVLink peer memory for the path's only exchange: the packed item-gradient
+// buffer + the loss, 0.4-200 KB, latency-bound.  Every rank owns a symmetric buffer (same layout on all ranks,
+// mapped into every process): [flags: world x uint32 | pad][slot 0 payload][slot 1 payload]; a payload is
+// n_float floats followed by n_double doubles.  The producer kernels of this rank (finalize_kernel) write the
+// payload of slot epoch & 1 directly; this kernel then
+//   1. publishes: system-scope fence, writes `epoch` into flag[rank] of every peer,
+//   2. waits until all world flags of its own buffer have reached `epoch`,
+//   3. reads every peer's payload over NVLink and sums in RANK ORDER (all ranks get bit-identical results),
+// one launch, no NCCL call, no host round trip.  Slots alternate, so a peer still reading slot e while this rank
+// already produces e + 1 is safe; slot e is rewritten only at e + 2, after the barrier of e + 1.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ float ld_relaxed_sys_f32(const float* p) {
+  float v;
+  asm volatile("ld.relaxed.sys.global.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ double ld_relaxed_sys_f64(const double* p) {
+  double v;
+  asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+  return v;
+}
+
+__device__ __forceinline__ float4 ld_relaxed_sys_f32x4(const float* p) {
+  float4 v;
+  asm volatile("ld.relaxed.sys.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
+  return v;
+}
+
+constexpr int kPeerMaxWorld = 16;      // peers whose loads are kept in flight together
+
+__global__ void __launch_bounds__(256) peer_allreduce_kernel(const uint64_t* __restrict__ peer_bufs, int rank, int world,
+                                                             int64_t flag_bytes, int64_t slot_bytes, int n_float,
+                                                             int n_double, float* __restrict__ out_float,
+                                                             double* __restrict__ out_double, uint32_t epoch) {
+  const int tid = threadIdx.x;
+  if (blockIdx.x == 0) {                 // publish once: everything this rank wrote before is visible system-wide
+    __threadfence_system();
+    if (tid < world) st_release_sys(reinterpret_cast<uint32_t*>(peer_bufs[tid]) + rank, epoch);
+  }
+  if (tid < world) {                     // every CTA waits for every peer's flag in its own buffer
+    const uint32_t* mine = reinterpret_cast<const uint32_t*>(peer_bufs[rank]) + tid;
+    while ((int32_t)(ld_acquire_sys(mine) - epoch) < 0) {}
+  }
+  __syncthreads();
+  const int64_t off = flag_bytes + (int64_t)(epoch & 1u) * slot_bytes;
+  const int64_t doff = off + (((int64_t)n_float * 4 + 7) & ~int64_t(7));
+  // floats, four at a time; all peers' loads of a chunk are issued before the first add (one NVLink round trip)
+  const int nvec = n_float >> 2;
+  for (int i = blockIdx.x * blockDim.x + tid; i < nvec; i += gridDim.x * blockDim.x) {
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int r0 = 0; r0 < world; r0 += kPeerMaxWorld) {
+      float4 v[kPeerMaxWorld];
+#pragma unroll
+      for (int k = 0; k < kPeerMaxWorld; ++k)
+        if (r0 + k < world) v[k] = ld_relaxed_sys_f32x4(reinterpret_cast<const float*>(peer_bufs[r0 + k] + off) + 4 * i);
+#pragma unroll
+      for (int k = 0; k < kPeerMaxWorld; ++k)
+        if (r0 + k < world) { acc.x += v[k].x; acc.y += v[k].y; acc.z += v[k].z; acc.w += v[k].w; }
+    }
+    *reinterpret_cast<float4*>(out_float + 4 * i) = acc;
+  }
+  if (blockIdx.x == 0) {
+    for (int i = (nvec << 2) + tid; i < n_float; i += blockDim.x) {
+      float s = 0.f;
+      for (int r = 0; r < world; ++r) s += ld_relaxed_sys_f32(reinterpret_cast<const float*>(peer_bufs[r] + off) + i);
+      out_float[i] = s;
+    }
+    for (int i = tid; i < n_double; i += blockDim.x) {
+      double s = 0.0;
+      for (int r = 0; r < world; ++r) s += ld_relaxed_sys_f64(reinterpret_cast<const double*>(peer_bufs[r] + doff) + i);
+      out_double[i] = s;
+    }
+  }
+}
+
 }  // namespace vipsy
 
 using namespace vipsy;
@@ -418,6 +502,28 @@ int vipsy_fill_uniform_dev(float* out, int32_t S, int64_t B, int32_t K, uint64_t
                            int64_t person_offset, void* stream) {
   VIPSY_REQUIRE(offset_dev, VIPSY_ERR_ARG, "vipsy_fill_uniform_dev: offset_dev is NULL");
   return fill_noise(false, out, S, B, K, seed, 0, person_offset, stream, offset_dev);
+}
+
+int vipsy_peer_allreduce(const uint64_t* peer_bufs_dev, int32_t rank, int32_t world, int64_t flag_bytes,
+                         int64_t slot_bytes, int32_t n_float, int32_t n_double, float* out_float, double* out_double,
+                         uint32_t epoch, void* stream) {
+  VIPSY_REQUIRE(peer_bufs_dev && world >= 1 && world <= 256 && rank >= 0 && rank < world && n_float >= 0 && n_double >= 0,
+                VIPSY_ERR_ARG, "vipsy_peer_allreduce: bad arguments");
+  VIPSY_REQUIRE(flag_bytes >= (int64_t)world * 4 && (flag_bytes & 7) == 0 && (slot_bytes & 7) == 0 &&
+                    slot_bytes >= (((int64_t)n_float * 4 + 7) & ~int64_t(7)) + (int64_t)n_double * 8,
+                VIPSY_ERR_ARG, "vipsy_peer_allreduce: layout does not fit (flag_bytes %lld, slot_bytes %lld)",
+                (long long)flag_bytes, (long long)slot_bytes);
+  VIPSY_REQUIRE((n_float == 0 || out_float) && (n_double == 0 || out_double), VIPSY_ERR_ARG,
+                "vipsy_peer_allreduce: output pointer is NULL");
+  VIPSY_REQUIRE((reinterpret_cast<uintptr_t>(out_float) & 15) == 0 && (flag_bytes & 15) == 0 && (slot_bytes & 15) == 0,
+                VIPSY_ERR_ARG, "vipsy_peer_allreduce: out_float, flag_bytes and slot_bytes must be 16-byte aligned");
+  int grid = (n_float / 4 + 255) / 256;
+  if (grid < 1) grid = 1;
+  if (grid > 32) grid = 32;
+  peer_allreduce_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(peer_bufs_dev, rank, world, flag_bytes, slot_bytes, n_float,
+                                                             n_double, out_float, out_double, epoch);
+  VIPSY_CUDA_CHECK(cudaGetLastError());
+  return VIPSY_OK;
 }
 
 int vipsy_adam_step(const VipsyAdamTensor* tensors, int32_t n_tensors, const int64_t* step_dev, int32_t zero_grad,

@@ -45,6 +45,62 @@ class GradReducer:
         return flat[0].to(torch.float64) + flat[1].to(torch.float64)
 
 
+class PeerAllReduce:
+    """The step's one exchange as ONE kernel over NVLink peer memory (``vipsy_peer_allreduce``): every rank's
+    producer kernels write their packed item gradients + loss straight into a symmetric buffer
+    (``torch.distributed._symmetric_memory``), the kernel publishes a flag to every peer, waits for theirs and
+    sums all payloads in rank order -- no collective-library call, bit-identical results on all ranks.
+
+        par = PeerAllReduce(n_float=ncol, n_double=1, device=dev)
+        g, l = par.slot_views()                 # where this step's producers must write
+        ops.irt_elbo_grad(..., item_grads_out=g, loss_out=l)
+        grads, loss = par.reduce()              # summed over ranks (fp32 / fp64 device tensors)
+    """
+
+    FLAG_BYTES = 1024
+
+    def __init__(self, n_float: int, n_double: int = 1, device=None, group=None):
+        import torch.distributed._symmetric_memory as symm_mem
+        from . import _native as N
+        self._N = N
+        self.group = group if group is not None else dist.group.WORLD
+        self.rank, self.world = dist.get_rank(self.group), dist.get_world_size(self.group)
+        if self.world * 4 > self.FLAG_BYTES:
+            raise ValueError("PeerAllReduce: world size too large for the flag area")
+        self.n_float, self.n_double = int(n_float), int(n_double)
+        self.slot_bytes = ((self.n_float * 4 + 7) // 8) * 8 + self.n_double * 8
+        self.slot_bytes = ((self.slot_bytes + 255) // 256) * 256
+        total = self.FLAG_BYTES + 2 * self.slot_bytes
+        self.buf = symm_mem.empty(total, dtype=torch.uint8, device=device)
+        self.buf.zero_()
+        self.hdl = symm_mem.rendezvous(self.buf, self.group)
+        ptrs = [int(p) for p in self.hdl.buffer_ptrs]
+        self.peer_ptrs = torch.tensor(ptrs, dtype=torch.int64, device=self.buf.device)
+        self.out_f = torch.empty(max(self.n_float, 1), dtype=torch.float32, device=self.buf.device)
+        self.out_d = torch.empty(max(self.n_double, 1), dtype=torch.float64, device=self.buf.device)
+        self.epoch = 0
+        torch.cuda.synchronize(self.buf.device)
+        self.hdl.barrier()                       # flags are zero everywhere before the first epoch
+        torch.cuda.synchronize(self.buf.device)
+
+    def slot_views(self):
+        """(fp32[n_float], fp64[n_double]) views of the slot the NEXT ``reduce()`` will read."""
+        off = self.FLAG_BYTES + ((self.epoch + 1) & 1) * self.slot_bytes
+        doff = off + ((self.n_float * 4 + 7) // 8) * 8
+        f = self.buf[off:off + self.n_float * 4].view(torch.float32)
+        d = self.buf[doff:doff + self.n_double * 8].view(torch.float64)
+        return f, d
+
+    def reduce(self):
+        self.epoch += 1
+        L = self._N.lib()
+        self._N.check(L.vipsy_peer_allreduce(self.peer_ptrs.data_ptr(), self.rank, self.world, self.FLAG_BYTES,
+                                             self.slot_bytes, self.n_float, self.n_double, self.out_f.data_ptr(),
+                                             self.out_d.data_ptr(), self.epoch & 0xffffffff,
+                                             torch.cuda.current_stream(self.buf.device).cuda_stream))
+        return self.out_f[:self.n_float], self.out_d[:self.n_double]
+
+
 def attach(model, global_size: int, person_offset: int, group=None):
     """Mark an estimator (built on this rank's person block) as one shard of a larger job."""
     model.global_size = int(global_size)

@@ -177,8 +177,12 @@ def irt_elbo_grad(
     want_grad: bool = True, strict: bool = False, tensor_cores: bool = True, sparse: bool = False,
     row_kernel: bool = True, obs=None, n_masked: Optional[int] = None,
     d_mu_out: Optional[torch.Tensor] = None, d_scale_out: Optional[torch.Tensor] = None,
+    item_grads_out: Optional[torch.Tensor] = None, loss_out: Optional[torch.Tensor] = None,
 ) -> Dict[str, Optional[torch.Tensor]]:
     """One fused ELBO + gradient evaluation (Trace_ELBO.loss_and_grads, vi.py:507).
+
+    ``item_grads_out`` (fp32, packed [d_b | d_a | d_c | d_d]) / ``loss_out`` (fp64, 1): optional destinations,
+    e.g. views into a symmetric peer-memory buffer (``dist.PeerAllReduce``).
 
     ``d_mu_out`` / ``d_scale_out``: optional preallocated fp32 CUDA buffers for the
     per-person gradients (d_sigma for K == 1, d_chol otherwise).  ``tensor_cores=False``
@@ -240,7 +244,12 @@ def irt_elbo_grad(
     args.a_free = _ptr(af_)
 
     out: Dict[str, Optional[torch.Tensor]] = {}
-    loss = torch.empty(1, dtype=torch.float64, device=dev)
+    if loss_out is not None:
+        if not (loss_out.is_cuda and loss_out.dtype == torch.float64 and loss_out.numel() == 1):
+            raise ValueError("loss_out must be a one-element fp64 CUDA tensor")
+        loss = loss_out
+    else:
+        loss = torch.empty(1, dtype=torch.float64, device=dev)
     args.loss = _ptr(loss)
     sg_ = ch_ = None
     if K == 1:
@@ -286,7 +295,13 @@ def irt_elbo_grad(
         # item gradients live in one packed fp32 buffer [d_b | d_a | d_c | d_d] so a
         # person-sharded job all-reduces it with a single collective
         ncol = J + (K * J if m >= 2 else 0) + (J if m >= 3 else 0) + (J if m >= 4 else 0)
-        packed = torch.empty(ncol, dtype=torch.float32, device=dev)
+        if item_grads_out is not None:
+            if not (item_grads_out.is_cuda and item_grads_out.dtype == torch.float32 and item_grads_out.is_contiguous()
+                    and item_grads_out.numel() == ncol):
+                raise ValueError(f"item_grads_out must be a contiguous fp32 CUDA tensor of {ncol} elements")
+            packed = item_grads_out.view(-1)
+        else:
+            packed = torch.empty(ncol, dtype=torch.float32, device=dev)
         out["item_grads"] = packed
         o = 0
         out["d_b"] = packed[o:o + J].view(1, J); o += J
