@@ -14,11 +14,12 @@ if __name__ == "__main__":
         off = [0]
         dchol = torch.zeros_like(w["chol_packed_raw"])
         dmu = torch.empty_like(w["mu"])
+        n_miss = int((w["y"] == 255).sum().item())
         def run():
             off[0] += 1
             return ops.irt_elbo_grad(w["y"], w["mu"], chol=w["chol_packed_raw"], chol_packed=True, chol_raw=True,
                                      n_particles=S, a=w["a"], b=w["b"], model="irt_2pl", a_free=w["a_free"],
-                                     seed=1, offset=off[0], d_mu_out=dmu, d_scale_out=dchol)
+                                     seed=1, offset=off[0], d_mu_out=dmu, d_scale_out=dchol, n_masked=n_miss)
         with ClockSampler() as cs:
             ms = timeit(run, it=10)
         tri = K * (K + 1) // 2
