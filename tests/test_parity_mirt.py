@@ -150,3 +150,12 @@ def test_mirt_deterministic(ops):
     r2 = ops.irt_elbo_grad(codes, cs["mu"].to(dev), **kw)
     for k in ("loss", "d_mu", "d_chol", "item_grads"):
         assert torch.equal(r1[k], r2[k]), k
+
+
+@pytest.mark.parametrize("K,S,layout", [(40, 3, "packed"), (40, 4, "dense"), (100, 5, "packed"), (65, 8, "packed"),
+                                        (33, 7, "dense"), (100, 8, "packed")])
+def test_streaming_guide_kernels_more_particles(ops, K, S, layout):
+    """2 < S <= 8 with a per-person factor and K > 32: the multi-pass sampler (pairs of particles per pass over
+    the factor) and the particle-loop guide-gradient stream."""
+    cs = make(B=45, J=70, K=K, S=S, model="irt_2pl", seed=K + S)
+    run(ops, cs, layout=layout, raw=True, scale=2.0)
