@@ -62,8 +62,10 @@ enum { VIPSY_IRT_FLAG_STRICT = 1,
                                           observed cells (same results; pays off below ~50 % density)        */
        VIPSY_IRT_FLAG_NO_ROW = 8,       /* K == 1, S == 1: force the lane-per-person kernels (default: the
                                           warp-per-person row kernels when J % 4 == 0, 64 <= J <= 512)       */
-       VIPSY_IRT_FLAG_MASKED_KNOWN = 16 };/* n_masked_cells is valid: saves one counting pass over the batch rows
+       VIPSY_IRT_FLAG_MASKED_KNOWN = 16,/* n_masked_cells is valid: saves one counting pass over the batch rows
                                           in the K == 1, S > 1 path (the matrix is constant between steps)   */
+       VIPSY_IRT_FLAG_NO_FUSED = 32 };  /* 2 <= K <= 8, per-person factor: force the three-kernel path (sample,
+                                          contraction, guide gradient) instead of the single fused kernel    */
 enum { VIPSY_CHOL_DENSE = 0,  /* row-major K x K, strict upper triangle ignored        */
        VIPSY_CHOL_PACKED = 1 };/* torch.tril_indices row-major order, K(K+1)/2 (vi.py:453) */
 

@@ -159,3 +159,28 @@ def test_streaming_guide_kernels_more_particles(ops, K, S, layout):
     the factor) and the particle-loop guide-gradient stream."""
     cs = make(B=45, J=70, K=K, S=S, model="irt_2pl", seed=K + S)
     run(ops, cs, layout=layout, raw=True, scale=2.0)
+
+
+@pytest.mark.parametrize("K", [2, 3, 4, 5, 6, 7, 8])
+@pytest.mark.parametrize("model,S", [("irt_2pl", 1), ("irt_3pl", 5), ("irt_4pl", 8), ("irt_2pl", 20)])
+def test_fused_small_k_kernel(ops, K, model, S):
+    """2 <= K <= 8, per-person factor: the single fused kernel (lane per person, warp-shuffle reductions),
+    every particle-chunk remainder, packed and dense layouts, injected noise."""
+    cs = make(B=75, J=37, K=K, S=S, model=model, seed=10 * K + S, missing=0.2)
+    run(ops, cs, layout="packed" if K % 2 else "dense", raw=bool(S % 2), scale=2.0, D=1.702 if model == "irt_3pl" else 1.0)
+
+
+def test_fused_small_k_matches_three_kernel_path_on_philox_noise(ops):
+    """Same in-kernel Philox stream in both paths (noise_coord's K <= 32 layout): outputs agree to rounding;
+    the fused kernel is bit-reproducible."""
+    cs = make(B=700, J=60, K=4, S=6, model="irt_2pl", seed=3)
+    dev = "cuda"
+    kw = dict(chol=packed_of(cs["raw"]).to(dev), chol_packed=True, chol_raw=True, n_particles=6, a=cs["a"].to(dev),
+              b=cs["b"].to(dev), model="irt_2pl", a_free=cs["free"].to(dev), seed=11, offset=5, person_offset=9)
+    codes = codes_from_float(cs["y"]).to(dev)
+    f1 = ops.irt_elbo_grad(codes, cs["mu"].to(dev), **kw)
+    f2 = ops.irt_elbo_grad(codes, cs["mu"].to(dev), **kw)
+    u = ops.irt_elbo_grad(codes, cs["mu"].to(dev), fused=False, **kw)
+    for k in ("loss", "d_mu", "d_chol", "d_a", "d_b"):
+        assert torch.equal(f1[k], f2[k]), k
+        assert_close(f1[k], u[k], 2e-5, 2e-5, k)

@@ -23,6 +23,7 @@ IRT_FLAG_NO_TENSOR = 2
 IRT_FLAG_SPARSE = 4
 IRT_FLAG_NO_ROW = 8
 IRT_FLAG_MASKED_KNOWN = 16
+IRT_FLAG_NO_FUSED = 32
 
 _p = C.c_void_p
 

@@ -533,8 +533,18 @@ int mirt_launch(const VipsyIrtArgs* a, cudaStream_t st) {
   }
   const bool shared_cov = a->cov_mode == VIPSY_COV_SHARED;
 
-  const bool stream = mirt_stream_supported(p);
-  const bool small = !stream && mirt_small_supported(p);
+  int grid2 = 0, grid3 = 0;
+  p.n_parts = 1;
+  // K <= 8 with a per-person factor: one fused kernel (warp-shuffle FMAs, nothing staged through HBM)
+  const bool fused = !(a->flags & VIPSY_IRT_FLAG_NO_FUSED) && mirt_fused_supported(p);
+  if (fused) {
+    int rc = launch_mirt_fused(p, kMirtMaxGrid, &grid2, st);
+    if (rc != VIPSY_OK) return rc;
+    grid3 = grid2;
+  }
+  const bool stream = !fused && mirt_stream_supported(p);
+  const bool small = !fused && !stream && mirt_small_supported(p);
+  if (!fused) {
   // (1) sample
   if (small) {
     int rc = launch_sample_small(p, kMirtMaxGrid, st);
@@ -558,8 +568,6 @@ int mirt_launch(const VipsyIrtArgs* a, cudaStream_t st) {
     if (rc != VIPSY_OK) return rc;
   }
   // (2) likelihood + backward contractions: tcgen05 for K >= 8 (2PL), SIMT otherwise
-  int grid2 = 0;
-  p.n_parts = 1;
   const bool want_tc = !(a->flags & VIPSY_IRT_FLAG_NO_TENSOR) && mirt_tc_supported(p);
   if (want_tc) {
     int rc = launch_lik_tc(p, &grid2, &p.n_parts, st);
@@ -580,7 +588,6 @@ int mirt_launch(const VipsyIrtArgs* a, cudaStream_t st) {
     if (rc != VIPSY_OK) return rc;
   }
   // (3) guide gradients + loss partials
-  int grid3;
   if (small) {
     int rc = launch_cholgrad_small(p, kMirtMaxGrid, &grid3, st);
     if (rc != VIPSY_OK) return rc;
@@ -597,6 +604,7 @@ int mirt_launch(const VipsyIrtArgs* a, cudaStream_t st) {
     mirt_cholgrad_kernel<<<grid3, kCgThreads, smem, st>>>(p);
     VIPSY_CUDA_CHECK(cudaGetLastError());
   }
+  }   // !fused
   // masked cells: log(1 - eps) each (common.cuh), as extra loss partial rows
   int mask_rows = 0;
   {

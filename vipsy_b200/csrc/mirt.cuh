@@ -58,6 +58,11 @@ __device__ __forceinline__ void noise_lane4(const MirtParams& p, int s, int64_t 
   }
 }
 
+// K <= 8, per-person factor: the whole evaluation in one kernel (mirt_fused.cu); writes item_partial /
+// loss_partial rows [0, *grid_out), d_mu, d_chol.
+bool mirt_fused_supported(const MirtParams& p);
+int launch_mirt_fused(const MirtParams& p, int max_grid, int* grid_out, cudaStream_t st);
+
 // tcgen05 likelihood contraction (mirt_tc.cu).  rows_out = partial rows written to item_partial,
 // parts_out = number of d x / log-lik partial planes (one per 128-item tile).
 bool mirt_tc_supported(const MirtParams& p);

@@ -175,7 +175,7 @@ def irt_elbo_grad(
     chol_packed: bool = False, chol_raw: bool = False,
     seed: int = 0, offset: int = 0, person_offset: int = 0,
     want_grad: bool = True, strict: bool = False, tensor_cores: bool = True, sparse: bool = False,
-    row_kernel: bool = True, obs=None, n_masked: Optional[int] = None,
+    row_kernel: bool = True, obs=None, n_masked: Optional[int] = None, fused: bool = True,
     d_mu_out: Optional[torch.Tensor] = None, d_scale_out: Optional[torch.Tensor] = None,
     item_grads_out: Optional[torch.Tensor] = None, loss_out: Optional[torch.Tensor] = None,
 ) -> Dict[str, Optional[torch.Tensor]]:
@@ -190,6 +190,7 @@ def irt_elbo_grad(
     tells the kernel most cells are missing: it compacts each person's observed cells first.
     ``obs``: the (row_ptr, entries, nnz) triple of ``observed_csr(y)``; used by the K == 1, S == 1 path.
     ``n_masked``: number of missing cells among the batch rows, if the caller knows it (saves a counting pass).
+    ``fused=False`` (2 <= K <= 8, per-person factor) forces the three-kernel path instead of the fused kernel.
     ``row_kernel=False`` (K == 1, S == 1) forces the lane-per-person kernels instead of the warp-per-person ones."""
     if not y.is_cuda or y.dtype != torch.uint8:
         raise ValueError("y must be a CUDA uint8 code matrix (see pack_responses)")
@@ -215,7 +216,8 @@ def irt_elbo_grad(
     args.model, args.estimator = m, N.EST[estimator]
     args.D, args.scale, args.baseline = float(D), float(scale), float(baseline)
     args.flags = (N.IRT_FLAG_STRICT if strict else 0) | (0 if tensor_cores else N.IRT_FLAG_NO_TENSOR) \
-        | (N.IRT_FLAG_SPARSE if sparse else 0) | (0 if row_kernel else N.IRT_FLAG_NO_ROW)
+        | (N.IRT_FLAG_SPARSE if sparse else 0) | (0 if row_kernel else N.IRT_FLAG_NO_ROW) \
+        | (0 if fused else N.IRT_FLAG_NO_FUSED)
     args.y, args.y_row_stride = _ptr(y), y.stride(0)
     if n_masked is not None:
         args.flags |= N.IRT_FLAG_MASKED_KNOWN
