@@ -184,3 +184,30 @@ def test_fused_small_k_matches_three_kernel_path_on_philox_noise(ops):
     for k in ("loss", "d_mu", "d_chol", "d_a", "d_b"):
         assert torch.equal(f1[k], f2[k]), k
         assert_close(f1[k], u[k], 2e-5, 2e-5, k)
+
+
+@pytest.mark.parametrize("K,model,S", [(2, "irt_2pl", 4), (3, "irt_4pl", 5), (4, "irt_3pl", 8), (6, "irt_2pl", 3), (8, "irt_2pl", 2)])
+@pytest.mark.parametrize("raw,layout", [(True, "packed"), (False, "dense")])
+def test_fused_small_k_score_function_estimator(ops, K, model, S, raw, layout):
+    """REINFORCE for the MultivariateNormal guide (north star (d)): x constant, weights scale (ll + log p - log q)
+    - baseline times the score of q (L^-T eps; tril(L^-T eps eps^T) - diag(1/L_ii)); item gradients unchanged."""
+    cs = make(B=60, J=30, K=K, S=S, model=model, seed=7 * K + S, missing=0.15)
+    m = cs["model"]
+    kw = dict(a=cs["a"], b=cs["b"], c=cs["c"] if m in ("irt_3pl", "irt_4pl") else None, d=cs["d"] if m == "irt_4pl" else None)
+    chol_in = cs["raw"] if raw else o.lower_cholesky(cs["raw"])
+    ref = o.irt_elbo_grad(cs["y"], cs["mu"], chol_in, cs["eps"], kw["a"], kw["b"], kw["c"], kw["d"], model=m, scale=1.5,
+                          a_free=cs["free"], chol_raw=raw, estimator="score", baseline=3.0)
+    dev = "cuda"
+    chol_dev = (packed_of(chol_in) if layout == "packed" else chol_in).to(dev)
+    got = ops.irt_elbo_grad(codes_from_float(cs["y"]).to(dev), cs["mu"].to(dev), chol=chol_dev, eps=cs["eps"].to(dev),
+                            **{k: (v.to(dev) if v is not None else None) for k, v in kw.items()}, model=m, scale=1.5,
+                            a_free=cs["free"].to(dev), chol_packed=(layout == "packed"), chol_raw=raw,
+                            estimator="score", baseline=3.0)
+    tol = 3e-5
+    assert_close(got["loss"], ref["loss"], tol, tol, "loss")
+    assert_close(got["d_mu"], ref["d_mu"], tol, tol, "d_mu")
+    rd = ref["d_scale"].tril()
+    gd = got["d_chol"].cpu()
+    assert_close(gd if layout == "dense" else gd, rd if layout == "dense" else packed_of(rd), tol, tol, "d_chol")
+    assert_close(got["d_a"], ref["d_a"], tol, tol, "d_a")
+    assert_close(got["d_b"], ref["d_b"], tol, tol, "d_b")

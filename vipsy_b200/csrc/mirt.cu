@@ -499,9 +499,11 @@ static int launch_lik(const MirtParams& p, int* grid_out, cudaStream_t st) {
 int mirt_launch(const VipsyIrtArgs* a, cudaStream_t st) {
   const int K = a->n_dims, J = a->n_items, tri = K * (K + 1) / 2;
   VIPSY_REQUIRE(K >= 2 && K <= 128, VIPSY_ERR_UNSUPPORTED, "vipsy_irt_elbo_grad: K=%d outside 2..128", K);
-  VIPSY_REQUIRE(a->estimator == VIPSY_EST_PATHWISE, VIPSY_ERR_UNSUPPORTED,
-                "vipsy_irt_elbo_grad: the score estimator is built for K == 1 only (the reference never "
-                "executes it for MultivariateNormal guides, SURVEY Finding 1)");
+  VIPSY_REQUIRE(a->estimator == VIPSY_EST_PATHWISE ||
+                    (K <= 8 && a->cov_mode == VIPSY_COV_PERSON && !(a->flags & VIPSY_IRT_FLAG_NO_FUSED)),
+                VIPSY_ERR_UNSUPPORTED,
+                "vipsy_irt_elbo_grad: for K > 1 the score estimator is built in the fused kernel only (K <= 8, "
+                "per-person factor); the reference never executes it for MultivariateNormal guides (SURVEY Finding 1)");
   VIPSY_REQUIRE(a->chol, VIPSY_ERR_ARG, "vipsy_irt_elbo_grad: chol is required for K > 1");
   VIPSY_REQUIRE(a->cov_mode == VIPSY_COV_SHARED || a->cov_mode == VIPSY_COV_PERSON, VIPSY_ERR_ARG,
                 "vipsy_irt_elbo_grad: cov_mode must be SHARED or PERSON for K > 1");
@@ -518,6 +520,7 @@ int mirt_launch(const VipsyIrtArgs* a, cudaStream_t st) {
   p.B = a->batch; p.J = J; p.K = K; p.S = a->n_particles; p.model = a->model;
   p.cov_mode = a->cov_mode; p.chol_layout = a->chol_layout; p.chol_raw = a->chol_raw;
   p.D = a->D; p.scale = a->scale;
+  p.score = a->estimator == VIPSY_EST_SCORE ? 1 : 0; p.baseline = a->baseline;
   p.seed = a->seed; p.offset = a->offset; p.person_offset = a->person_offset;
   p.x = reinterpret_cast<float*>(ws + L.x); p.gx = reinterpret_cast<float*>(ws + L.gx);
   p.ell = reinterpret_cast<float*>(ws + L.ell); p.aux = reinterpret_cast<float*>(ws + L.aux);

@@ -13,6 +13,8 @@ struct MirtParams {
   int64_t B;
   int J, K, S, model, cov_mode, chol_layout, chol_raw;
   float D, scale;
+  int score;            // 1: score-function (REINFORCE) estimator for the guide parameters (fused K <= 8 kernel only)
+  float baseline;       // its fixed control variate
   uint64_t seed, offset; int64_t person_offset;
   // workspace
   float* x;        // [S*B][K]

@@ -29,7 +29,10 @@ __host__ __device__ inline size_t fused_smem_bytes(int J, int K, int model) {
   return s;
 }
 
-template <int K, int MODEL>
+// SCORE: REINFORCE estimator for the guide parameters (north star (d); SURVEY A.2 "score mode"): x is a constant,
+// each particle's weight w_s = scale (ll_s + log p(x_s) - log q(x_s)) - baseline multiplies the score of q,
+// grad_mu log q = L^-T eps, grad_L log q = tril(L^-T eps eps^T) - diag(1 / L_ii); item gradients are unchanged.
+template <int K, int MODEL, bool SCORE>
 __global__ void __launch_bounds__(kFuThreads) mirt_fused_kernel(const MirtParams p) {
   constexpr int SC = K <= 2 ? 8 : (K <= 4 ? 4 : 2);                  // particles held in registers at once
   constexpr int NQ = K + 1 + (MODEL >= 3 ? 1 : 0) + (MODEL >= 4 ? 1 : 0);
@@ -112,7 +115,9 @@ __global__ void __launch_bounds__(kFuThreads) mirt_fused_kernel(const MirtParams
     float Lsum = 0.f, quad = 0.f;          // sum of log2 q;  0.5 sum_s (|eps_s|^2 - |x_s|^2)
 
     for (int s0 = 0; s0 < S; s0 += SC) {
-      float eps[SC][K], x[SC][K], G[SC][K];
+      float eps[SC][K], x[SC][K], G[SC][K], ll2[SC];
+#pragma unroll
+      for (int s = 0; s < SC; ++s) ll2[s] = 0.f;
       if constexpr ((SC * K) % 4 == 0) {
         // in-kernel noise: the chunk's SC * K draws are consecutive elements n = s K + k of the person's stream
         // (noise_coord, K <= 32 layout), i.e. whole Philox blocks: one call per four draws
@@ -176,8 +181,12 @@ __global__ void __launch_bounds__(kFuThreads) mirt_fused_kernel(const MirtParams
               const float es = e * sp;
               const float q = MODEL >= 3 ? fmaf(it.z, sp, base) : sp;
               const float qc = fminf(fmaxf(q, kEps32), kOneMinusEps32);
-              prod *= qc;
-              if (SC == 8 && s == 3) { Lsum += lg2_approx(prod); prod = 1.f; }
+              if constexpr (SCORE) {
+                ll2[s] += lg2_approx(qc);                             // per-particle log-likelihood (log2 units)
+              } else {
+                prod *= qc;
+                if (SC == 8 && s == 3) { Lsum += lg2_approx(prod); prod = 1.f; }
+              }
               if (q == qc) {                                          // the clamp blocks the gradient
                 float w, a1 = 0.f, a2 = 0.f;
                 if (MODEL >= 3) {
@@ -192,7 +201,7 @@ __global__ void __launch_bounds__(kFuThreads) mirt_fused_kernel(const MirtParams
                 const float gl = ws * glf;
 #pragma unroll
                 for (int k = 0; k < K; ++k) {
-                  G[s][k] = fmaf(gl, a[k], G[s][k]);
+                  if constexpr (!SCORE) G[s][k] = fmaf(gl, a[k], G[s][k]);
                   v[k] = fmaf(ws, x[s][k], v[k]);
                 }
                 v[K] += ws;
@@ -201,7 +210,7 @@ __global__ void __launch_bounds__(kFuThreads) mirt_fused_kernel(const MirtParams
               }
             }
           }
-          Lsum += lg2_approx(prod);
+          if constexpr (!SCORE) Lsum += lg2_approx(prod);
         }
         // K + 1 (+2) sums over the 32 persons, four quantities per butterfly
 #pragma unroll
@@ -214,16 +223,43 @@ __global__ void __launch_bounds__(kFuThreads) mirt_fused_kernel(const MirtParams
           if (own >= 0 && q0i + own < NQ) acc[(q0i + own) * J + j] += r;
         }
       }
-      // ---- this chunk's share of d mu, d L: g_x = (sum_j d lb/d x) - x ---------------------------------
+      // ---- this chunk's share of d mu, d L ---------------------------------------------------------------
 #pragma unroll
       for (int s = 0; s < SC; ++s) {
         if (s0 + s < S) {
+          if constexpr (SCORE) {
+            float x2 = 0.f, e2 = 0.f, logdet = 0.f;
 #pragma unroll
-          for (int r = 0; r < K; ++r) {
-            const float gk = G[s][r] - x[s][r];
-            dmu[r] += gk;
+            for (int k = 0; k < K; ++k) {
+              x2 = fmaf(x[s][k], x[s][k], x2);
+              e2 = fmaf(eps[s][k], eps[s][k], e2);
+              logdet += __logf(L[k * (k + 1) / 2 + k]);
+            }
+            Lsum += ll2[s];
+            const float wgt = p.scale * (kLn2 * ll2[s] - 0.5f * x2 + 0.5f * e2 + logdet) - p.baseline;
+            float u[K];                                     // L^T u = eps (back substitution)
 #pragma unroll
-            for (int c = 0; c <= r; ++c) dL[r * (r + 1) / 2 + c] = fmaf(gk, eps[s][c], dL[r * (r + 1) / 2 + c]);
+            for (int r = K - 1; r >= 0; --r) {
+              float t = eps[s][r];
+#pragma unroll
+              for (int c = r + 1; c < K; ++c) t = fmaf(-L[c * (c + 1) / 2 + r], u[c], t);
+              u[r] = t / L[r * (r + 1) / 2 + r];
+            }
+#pragma unroll
+            for (int r = 0; r < K; ++r) {
+              dmu[r] = fmaf(wgt, u[r], dmu[r]);
+#pragma unroll
+              for (int c = 0; c <= r; ++c) dL[r * (r + 1) / 2 + c] = fmaf(wgt * u[r], eps[s][c], dL[r * (r + 1) / 2 + c]);
+              dL[r * (r + 1) / 2 + r] -= wgt / L[r * (r + 1) / 2 + r];
+            }
+          } else {
+#pragma unroll
+            for (int r = 0; r < K; ++r) {
+              const float gk = G[s][r] - x[s][r];           // g_x = (sum_j d lb/d x) - x
+              dmu[r] += gk;
+#pragma unroll
+              for (int c = 0; c <= r; ++c) dL[r * (r + 1) / 2 + c] = fmaf(gk, eps[s][c], dL[r * (r + 1) / 2 + c]);
+            }
           }
         }
       }
@@ -236,9 +272,10 @@ __global__ void __launch_bounds__(kFuThreads) mirt_fused_kernel(const MirtParams
 #pragma unroll
       for (int k = 0; k < K; ++k) logdet += __logf(L[k * (k + 1) / 2 + k]);
       loss_acc += (double)(kf * (kLn2 * Lsum + quad + (float)S * logdet));
+      const float gf = SCORE ? -1.f / (float)S : kf;      // score weights already carry the plate scale
       if (p.d_mu) {
 #pragma unroll
-        for (int k = 0; k < K; ++k) p.d_mu[bi * K + k] = kf * dmu[k];
+        for (int k = 0; k < K; ++k) p.d_mu[bi * K + k] = gf * dmu[k];
       }
       if (p.d_chol) {
         float* out = p.d_chol + bi * (packed ? TRI : K * K);
@@ -246,10 +283,11 @@ __global__ void __launch_bounds__(kFuThreads) mirt_fused_kernel(const MirtParams
         for (int r = 0; r < K; ++r)
 #pragma unroll
           for (int c = 0; c <= r; ++c) {
-            float v = kf * dL[r * (r + 1) / 2 + c];
+            float v = gf * dL[r * (r + 1) / 2 + c];
             if (r == c) {
               const float lii = L[r * (r + 1) / 2 + r];
-              v = p.chol_raw ? fmaf(v, lii, -p.scale) : v - p.scale / lii;     // - scale d(sum log L_ii); exp chain rule
+              if constexpr (SCORE) v = p.chol_raw ? v * lii : v;                  // exp chain rule only
+              else v = p.chol_raw ? fmaf(v, lii, -p.scale) : v - p.scale / lii;   // - scale d(sum log L_ii); exp chain rule
             }
             out[packed ? (r * (r + 1) / 2 + c) : (r * K + c)] = v;
           }
@@ -287,9 +325,9 @@ bool mirt_fused_supported(const MirtParams& p) {
          fused_smem_bytes(p.J, p.K, p.model) <= 200 * 1024;
 }
 
-template <int K, int MODEL>
+template <int K, int MODEL, bool SCORE>
 static int launch_fused_one(const MirtParams& p, int max_grid, int* grid_out, cudaStream_t st) {
-  auto kern = mirt_fused_kernel<K, MODEL>;
+  auto kern = mirt_fused_kernel<K, MODEL, SCORE>;
   const size_t smem = fused_smem_bytes(p.J, K, MODEL);
   static int occ = 0;
   static size_t occ_smem = ~size_t(0);
@@ -314,10 +352,17 @@ static int launch_fused_one(const MirtParams& p, int max_grid, int* grid_out, cu
 
 template <int K>
 static int launch_fused_model(const MirtParams& p, int max_grid, int* grid_out, cudaStream_t st) {
+  if (p.score) {
+    switch (p.model) {
+      case VIPSY_IRT_2PL: return launch_fused_one<K, 2, true>(p, max_grid, grid_out, st);
+      case VIPSY_IRT_3PL: return launch_fused_one<K, 3, true>(p, max_grid, grid_out, st);
+      default: return launch_fused_one<K, 4, true>(p, max_grid, grid_out, st);
+    }
+  }
   switch (p.model) {
-    case VIPSY_IRT_2PL: return launch_fused_one<K, 2>(p, max_grid, grid_out, st);
-    case VIPSY_IRT_3PL: return launch_fused_one<K, 3>(p, max_grid, grid_out, st);
-    default: return launch_fused_one<K, 4>(p, max_grid, grid_out, st);
+    case VIPSY_IRT_2PL: return launch_fused_one<K, 2, false>(p, max_grid, grid_out, st);
+    case VIPSY_IRT_3PL: return launch_fused_one<K, 3, false>(p, max_grid, grid_out, st);
+    default: return launch_fused_one<K, 4, false>(p, max_grid, grid_out, st);
   }
 }
 
