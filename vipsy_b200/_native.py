@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.environ.get("VIPSY_B200_LIB") or os.path.join(HERE, "_lib", "libvipsy_b200.so")
+LIB_PATH = os.path.join(HERE, "_lib", "libvipsy_b200.so")
 
 OK, ERR_ARG, ERR_UNSUPPORTED, ERR_WORKSPACE, ERR_CUDA = 0, -1, -2, -3, -4
 Y_MISSING = 255
@@ -136,7 +136,7 @@ def lib():
         for name, (res, args) in SYMBOLS.items():
             fn = getattr(L, name)
             fn.restype, fn.argtypes = res, args
-        if L.vipsy_abi_version() != 2 and not os.environ.get("VIPSY_B200_LIB"):
+        if L.vipsy_abi_version() != 2:
             raise VipsyError(ERR_ARG, "ABI version mismatch")
         _lib = L
     return _lib
