@@ -21,16 +21,42 @@ def shard_bounds(n: int, world: int, rank: int) -> Tuple[int, int]:
 
 
 class GradReducer:
-    """Callable(loss, leaves) -> loss: all-reduce(sum) of [loss_hi, loss_lo, grads...]."""
+    """Callable(loss, leaves) -> loss: all-reduce(sum) of [loss_hi, loss_lo, grads...].
 
-    def __init__(self, group=None):
+    ``peer=True`` (CUDA, one node): the exchange is ``PeerAllReduce`` -- one kernel over NVLink peer memory, the
+    loss travelling as fp64 -- instead of a collective-library call; same sums, taken in rank order."""
+
+    def __init__(self, group=None, peer: bool = False):
         self.group = group
         self.bytes_last = 0
+        self.peer = bool(peer)
+        self._par = None
+
+    def _reduce_peer(self, loss, leaves, grads):
+        n = sum(g.numel() for g in grads)
+        if self._par is None or self._par.n_float != n:
+            self._par = PeerAllReduce(n_float=n, n_double=1, device=loss.device, group=self.group)
+        f, d = self._par.slot_views()
+        o = 0
+        for g in grads:
+            f[o:o + g.numel()].copy_(g.reshape(-1))
+            o += g.numel()
+        d.copy_(loss.detach().to(torch.float64).reshape(1))
+        out_f, out_d = self._par.reduce()
+        self.bytes_last = n * 4 + 8
+        o = 0
+        for p, g in zip(leaves, grads):
+            k = g.numel()
+            p.grad = out_f[o:o + k].view_as(p).to(p.dtype).clone()
+            o += k
+        return out_d[0].clone()
 
     def __call__(self, loss: torch.Tensor, leaves: Sequence[torch.Tensor]) -> torch.Tensor:
         if not dist.is_initialized() or dist.get_world_size(self.group) == 1:
             return loss
         grads = [p.grad if p.grad is not None else torch.zeros_like(p) for p in leaves]
+        if self.peer and loss.is_cuda:
+            return self._reduce_peer(loss, leaves, grads)
         dev = loss.device
         hi = loss.detach().to(torch.float32)
         lo = (loss.detach().to(torch.float64) - hi.to(torch.float64)).to(torch.float32)
@@ -101,11 +127,11 @@ class PeerAllReduce:
         return self.out_f[:self.n_float], self.out_d[:self.n_double]
 
 
-def attach(model, global_size: int, person_offset: int, group=None):
+def attach(model, global_size: int, person_offset: int, group=None, peer: bool = False):
     """Mark an estimator (built on this rank's person block) as one shard of a larger job."""
     model.global_size = int(global_size)
     model.person_offset = int(person_offset)
-    model.reducer = GradReducer(group)
+    model.reducer = GradReducer(group, peer=peer)
     return model
 
 
