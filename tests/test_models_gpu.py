@@ -340,3 +340,25 @@ def test_vaeccdm_class_matches_oracle_and_trains():
     first = m.fit(optim=vb.Adam({"lr": 1e-2}), max_iter=1)
     last = m.fit(optim=vb.Adam({"lr": 1e-2}), max_iter=150)
     assert last < first
+
+
+def test_cuda_graph_minibatch_multi_particle_and_evaluate_loss():
+    """Captured iteration with a fresh minibatch per particle (several kernel calls per step) and the reference's
+    evaluate_loss-after-every-step option (vi.py:770) running eagerly beside the graph."""
+    g = torch.Generator().manual_seed(4)
+    K, J, N = 3, 16, 300
+    q = (torch.rand(K, J, generator=g) < 0.5).float()
+    q[0, q.sum(0) == 0] = 1.0
+    y = (torch.rand(N, J, generator=g) < 0.5).float()
+    torch.manual_seed(0)
+    m = vb.VIRT(data=y, model="irt_2pl", subsample_size=64)
+    l = m.fit(optim=vb.Adam({"lr": 1e-2}), loss=vb.Trace_ELBO(num_particles=3), max_iter=40, cuda_graph=True)
+    assert np.isfinite(l)
+    vb.clear_param_store()
+    m2 = vb.VCCDM(data=y, q=q, subsample_size=100)
+    l2 = m2.fit(optim=vb.Adam({"lr": 1e-2}), max_iter=30, evaluate_loss_each_iter=True, cuda_graph=True)
+    assert np.isfinite(l2)
+    vb.clear_param_store()
+    m3 = vb.VaeIRT(data=y, model="irt_2pl", x_feature=2, subsample_size=50, hidden_dim=8)      # fused K = 2 kernel in the graph
+    l3 = m3.fit(optim=vb.Adam({"lr": 1e-2}), loss=vb.Trace_ELBO(num_particles=2), max_iter=30)
+    assert np.isfinite(l3)
