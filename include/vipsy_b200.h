@@ -61,7 +61,7 @@ enum { VIPSY_IRT_FLAG_STRICT = 1,
        VIPSY_IRT_FLAG_SPARSE = 4,       /* K == 1 hint: most cells are missing -> per-person compaction of the
                                           observed cells (same results; pays off below ~50 % density)        */
        VIPSY_IRT_FLAG_NO_ROW = 8,       /* K == 1, S == 1: force the lane-per-person kernels (default: the
-                                          warp-per-person row kernels when J % 4 == 0, 64 <= J <= 512)       */
+                                          warp-per-person row kernels, J <= 512 (256 for 3PL / 4PL))          */
        VIPSY_IRT_FLAG_MASKED_KNOWN = 16,/* n_masked_cells is valid: saves one counting pass over the batch rows
                                           in the K == 1, S > 1 path (the matrix is constant between steps)   */
        VIPSY_IRT_FLAG_NO_FUSED = 32 };  /* 2 <= K <= 8, per-person factor: force the three-kernel path (sample,

@@ -43,3 +43,8 @@ if __name__ == "__main__":
         case(1_000_000, 100, "irt_4pl", 0.0, False, row)
         case(1_000_000, 100, "irt_2pl", 0.0, False, row)
         case(500_000, 500, "irt_2pl", 0.0, False, row)
+    for row in (False, True):
+        case(2_000_000, 50, "irt_2pl", 0.0, False, row)
+        case(2_000_000, 20, "irt_4pl", 0.0, False, row)
+        case(4_000_000, 6, "irt_2pl", 0.0, False, row)
+        case(1_000_000, 101, "irt_2pl", 0.0, False, row)

@@ -370,3 +370,30 @@ def test_csr_path_idx_gather_deterministic(ops):
     check(r1, ref, "irt_2pl")
     for k in ("loss", "d_mu", "d_sigma", "d_a", "d_b"):
         assert torch.equal(r1[k], r2[k]), k
+
+
+@pytest.mark.parametrize("model", ["irt_1pl", "irt_2pl", "irt_3pl", "irt_4pl"])
+@pytest.mark.parametrize("J", [1, 5, 6, 8, 13, 20, 33, 50, 63, 64])
+def test_row_kernel_short_rows(ops, model, J):
+    """J <= 64: several persons per warp step (WP = 2, 4, 8, 16 words per row), rows of any length / alignment --
+    the reference's own data sets have J = 5 (lsat.dat) and 6 (ex5.2.dat), its article experiment J = 50."""
+    cs = make_case(B=1237, J=J, S=1, model=model, missing=0.15, seed=3 * J + 1)
+    got, ref = run_both(ops, cs, D=1.702, scale=4.0)
+    check(got, ref, model)
+    lane, _ = run_both(ops, cs, D=1.702, scale=4.0)          # deterministic
+    assert torch.equal(lane["d_b"], got["d_b"]) and torch.equal(lane["d_mu"], got["d_mu"])
+
+
+@pytest.mark.parametrize("J,sparse", [(101, False), (203, False), (130, True), (66, True), (67, False), (511, False)])
+def test_row_kernels_unaligned_rows(ops, J, sparse):
+    """J % 4 != 0: every other row starts off a 4-byte boundary (funnel-shifted loads), the last word is partial."""
+    cs = make_case(B=777, J=J, S=1, model="irt_2pl", missing=0.6 if sparse else 0.1, seed=J)
+    got, ref = run_both(ops, cs, scale=2.0, sparse=sparse)
+    check(got, ref, "irt_2pl")
+    g = torch.Generator().manual_seed(1)
+    y_full = (torch.rand(1500, J, generator=g) < 0.5).float()
+    idx = torch.randperm(1500, generator=g)[:777]
+    y_full[idx] = cs["y"]
+    got2, _ = run_both(ops, cs, scale=2.0, idx=idx, y_full=y_full, sparse=sparse)
+    for k in ("loss", "d_mu", "d_a", "d_b"):
+        assert torch.equal(got2[k], got[k]), k

@@ -161,6 +161,44 @@ __device__ __forceinline__ void item_evals(const float dmc, const float base, co
 }
 
 
+// One (person, item) cell, one particle.  t = signed logit in log2 units (see item_evals).
+// Returns w = s(1-s)/q, a1 = sp/q, a2 = (1-sp)/q (all 0 when !obs) and the clamped probability (1 when !obs).
+template <int MODEL, bool FASTPATH>
+__device__ __forceinline__ void cell_eval1(const float t, const float dmc, const float base, const bool obs,
+                                           float& w, float& a1, float& a2, float& qc) {
+  if constexpr (FASTPATH) {
+    const float e = ex2_approx(fminf(t, 60.f));
+    const float ope = e + 1.f;
+    const float num = fmaf(base, e, base + dmc);
+    float R = rcp_approx(num * ope);
+    R = obs ? R : 0.f;
+    const float sp = num * R;
+    const float q = num * sp;
+    a1 = ope * R;
+    a2 = a1 * e;
+    w = e * R;
+    qc = obs ? q : 1.f;
+  } else {
+    const float e = ex2_approx(fminf(t, 126.f));
+    const float sp = rcp_approx(e + 1.f);
+    const float es = e * sp;
+    float q;
+    if constexpr (MODEL >= 3) q = fmaf(dmc, sp, base); else q = sp;
+    const float qcl = vclampp(q);
+    const bool keep = obs && (q == qcl);
+    if constexpr (MODEL >= 3) {
+      const float r = keep ? rcp_approx(qcl) : 0.f;
+      a1 = r * sp;
+      a2 = r * es;
+      w = a1 * es;
+    } else {
+      a1 = 0.f; a2 = 0.f;
+      w = keep ? es : 0.f;
+    }
+    qc = obs ? qcl : 1.f;
+  }
+}
+
 // sparse (compacted) variant, irt_uni_sparse.cu
 size_t irt_uni_sparse_smem_bytes(int J, int NQ);
 int irt_uni_sparse_launch(int model, bool fast, int SC, IrtUniParams& p, cudaStream_t st, int* grid_out);

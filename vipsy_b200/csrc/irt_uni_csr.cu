@@ -33,41 +33,6 @@ __device__ __forceinline__ float lds_f1(uint32_t a) {
 }
 __device__ __forceinline__ void sts_f1(uint32_t a, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory"); }
 
-template <int MODEL, bool FASTPATH>
-__device__ __forceinline__ void csr_cell(const float t, const float dmc, const float base, const bool obs,
-                                         float& w, float& a1, float& a2, float& qc) {
-  if constexpr (FASTPATH) {
-    const float e = ex2_approx(fminf(t, 60.f));
-    const float ope = e + 1.f;
-    const float num = fmaf(base, e, base + dmc);
-    float R = rcp_approx(num * ope);
-    R = obs ? R : 0.f;
-    const float sp = num * R;
-    a1 = ope * R;
-    a2 = a1 * e;
-    w = e * R;
-    qc = obs ? num * sp : 1.f;
-  } else {
-    const float e = ex2_approx(fminf(t, 126.f));
-    const float sp = rcp_approx(e + 1.f);
-    const float es = e * sp;
-    float q;
-    if constexpr (MODEL >= 3) q = fmaf(dmc, sp, base); else q = sp;
-    const float qcl = vclampp(q);
-    const bool keep = obs && (q == qcl);
-    if constexpr (MODEL >= 3) {
-      const float r = keep ? rcp_approx(qcl) : 0.f;
-      a1 = r * sp;
-      a2 = r * es;
-      w = a1 * es;
-    } else {
-      a1 = 0.f; a2 = 0.f;
-      w = keep ? es : 0.f;
-    }
-    qc = obs ? qcl : 1.f;
-  }
-}
-
 // accumulator row of one item: NQ sums padded to 1, 2 or 4 floats so that one LDS/STS moves the row
 __host__ __device__ constexpr int csr_acc_width(int NQ) { return NQ <= 2 ? NQ : 4; }
 // item table: {A', B'} (1PL / 2PL; D a = -A' / log2 e) or {A', B', c, d-c} + {D a (d-c), 1-d}
@@ -180,8 +145,8 @@ __global__ void __launch_bounds__(kUniThreads) irt_uni_csr_kernel(const IrtUniPa
       const float t = y1 ? tt0 : -tt0;
       const float base = y1 ? it.z : it2.y;
       float w, a1, a2, qc;
-      if (FAST && use_fast) csr_cell<MODEL, true>(t, it.w, base, obs, w, a1, a2, qc);
-      else csr_cell<MODEL, false>(t, it.w, base, obs, w, a1, a2, qc);
+      if (FAST && use_fast) cell_eval1<MODEL, true>(t, it.w, base, obs, w, a1, a2, qc);
+      else cell_eval1<MODEL, false>(t, it.w, base, obs, w, a1, a2, qc);
       const float ws = y1 ? w : -w;
       Gi = fmaf(it2.x, ws, Gi);
       Lr *= qc;

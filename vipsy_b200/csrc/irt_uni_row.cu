@@ -27,44 +27,6 @@ namespace vipsy {
 
 constexpr int kRowGroup = 4;          // persons whose d lb / d x sums are reduced together
 
-// One (person, item) cell, one particle.  t = signed logit in log2 units (see item_evals).
-// Returns w = s(1-s)/q, a1 = sp/q, a2 = (1-sp)/q (all 0 when !obs) and the clamped probability (1 when !obs).
-template <int MODEL, bool FASTPATH>
-__device__ __forceinline__ void cell_eval1(const float t, const float dmc, const float base, const bool obs,
-                                           float& w, float& a1, float& a2, float& qc) {
-  if constexpr (FASTPATH) {
-    const float e = ex2_approx(fminf(t, 60.f));
-    const float ope = e + 1.f;
-    const float num = fmaf(base, e, base + dmc);
-    float R = rcp_approx(num * ope);
-    R = obs ? R : 0.f;
-    const float sp = num * R;
-    const float q = num * sp;
-    a1 = ope * R;
-    a2 = a1 * e;
-    w = e * R;
-    qc = obs ? q : 1.f;
-  } else {
-    const float e = ex2_approx(fminf(t, 126.f));
-    const float sp = rcp_approx(e + 1.f);
-    const float es = e * sp;
-    float q;
-    if constexpr (MODEL >= 3) q = fmaf(dmc, sp, base); else q = sp;
-    const float qcl = vclampp(q);
-    const bool keep = obs && (q == qcl);
-    if constexpr (MODEL >= 3) {
-      const float r = keep ? rcp_approx(qcl) : 0.f;
-      a1 = r * sp;
-      a2 = r * es;
-      w = a1 * es;
-    } else {
-      a1 = 0.f; a2 = 0.f;
-      w = keep ? es : 0.f;
-    }
-    qc = obs ? qcl : 1.f;
-  }
-}
-
 // per-person variational inputs of a 32-person tile, one person per lane
 struct RowTileLane {
   float mu, sg, eps, x;
@@ -98,20 +60,58 @@ __device__ __forceinline__ void row_tile_finish(const IrtUniParams& p, const Row
   loss_acc -= (double)(p.scale * fmaf(kLn2, Ltile, prior));
 }
 
-template <int NP>
+// Cells [4w, 4w+4) of a response row as one 32-bit word, whatever the row's byte alignment and length: an
+// unaligned row takes two aligned loads and a funnel shift (the second only if it still holds bytes of this
+// row); cells at or beyond J come back as 0xff = missing.  Requires 4 w < J.
+__device__ __forceinline__ uint32_t row_word(const uint8_t* base, int w, int J) {
+  const int nb = J - 4 * w;                                    // cells of this word inside the row
+  const uintptr_t addr = reinterpret_cast<uintptr_t>(base) + 4 * (uintptr_t)w;
+  const int m = (int)(addr & 3);
+  const uint32_t* ap = reinterpret_cast<const uint32_t*>(addr - m);
+  uint32_t word = __ldg(ap);
+  if (m != 0) {
+    const uint32_t hi = (m + min(nb, 4) > 4) ? __ldg(ap + 1) : 0xffffffffu;
+    word = __funnelshift_r(word, hi, 8 * m);
+  }
+  if (nb < 4) word |= 0xffffffffu << (8 * nb);
+  return word;
+}
+
+// every row of the matrix starts on a 4-byte boundary and holds whole words: plain 32-bit loads
+__host__ __device__ inline bool rows_word_aligned(const IrtUniParams& p) {
+  return ((reinterpret_cast<uintptr_t>(p.y) | (uintptr_t)p.ld_y | (uintptr_t)p.J) & 3) == 0;
+}
+
+template <int NP, bool ALIGNED>
 __device__ __forceinline__ void row_load_group(const IrtUniParams& p, int64_t b_first, int lane, int nwords,
                                                uint32_t (&W)[kRowGroup][NP]) {
+  if constexpr (ALIGNED) {                         // straight-line loads the compiler can hoist
+#pragma unroll
+    for (int i = 0; i < kRowGroup; ++i) {
+      const int64_t b = b_first + i;
+      const bool ok = b < p.B;
+      int64_t row = b;
+      if (ok && p.idx) row = __ldg(p.idx + b);
+      const uint32_t* g = reinterpret_cast<const uint32_t*>(p.y + row * p.ld_y);
+#pragma unroll
+      for (int k = 0; k < NP; ++k) {
+        const int w = lane + 32 * k;
+        W[i][k] = (ok && w < nwords) ? __ldg(g + w) : 0xffffffffu;
+      }
+    }
+    return;
+  }
 #pragma unroll
   for (int i = 0; i < kRowGroup; ++i) {
     const int64_t b = b_first + i;
     const bool ok = b < p.B;
     int64_t row = b;
     if (ok && p.idx) row = __ldg(p.idx + b);
-    const uint32_t* g = reinterpret_cast<const uint32_t*>(p.y + row * p.ld_y);
+    const uint8_t* g = p.y + row * p.ld_y;
 #pragma unroll
     for (int k = 0; k < NP; ++k) {
       const int w = lane + 32 * k;
-      W[i][k] = (ok && w < nwords) ? __ldg(g + w) : 0xffffffffu;
+      W[i][k] = (ok && w < nwords) ? row_word(g, w, p.J) : 0xffffffffu;
     }
   }
 }
@@ -132,13 +132,14 @@ constexpr int row_min_ctas(int MODEL, int NP) {
   if (MODEL > 2) return 1;
   return NP == 1 ? 6 : NP == 2 ? 5 : 3;
 }
-template <int MODEL, int NP, bool FAST>
+// ALIGNED: every row starts on a 4-byte boundary and holds whole words (plain 32-bit loads); otherwise row_word()
+template <int MODEL, int NP, bool FAST, bool ALIGNED>
 __global__ void __launch_bounds__(kUniThreads, row_min_ctas(MODEL, NP)) irt_uni_row_kernel(const IrtUniParams p) {
   constexpr int NQ = MODEL;
   constexpr int JP = NP * 128;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float* acc_sm = reinterpret_cast<float*>(smem_raw);             // [warp][NQ][JP], used after the main loop
-  const int J = p.J, nwords = J >> 2;
+  const int J = p.J, nwords = (J + 3) >> 2;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 
   // item parameters of this lane's 4*NP items
@@ -190,7 +191,7 @@ __global__ void __launch_bounds__(kUniThreads, row_min_ctas(MODEL, NP)) irt_uni_
   const int64_t nwarps = (int64_t)gridDim.x * kUniWarps;
 
   uint32_t Wc[kRowGroup][NP], Wn[kRowGroup][NP];
-  if (gwarp < ntiles) row_load_group<NP>(p, gwarp * 32, lane, nwords, Wc);
+  if (gwarp < ntiles) row_load_group<NP, ALIGNED>(p, gwarp * 32, lane, nwords, Wc);
 
   for (int64_t tile = gwarp; tile < ntiles; tile += nwarps) {
     const int64_t b0 = tile * 32;
@@ -204,7 +205,7 @@ __global__ void __launch_bounds__(kUniThreads, row_min_ctas(MODEL, NP)) irt_uni_
     for (int g = 0; g < 32 / kRowGroup; ++g) {
       // next group's rows (next tile's first group after the last one); out-of-range persons read as missing
       const int64_t nb = g + 1 < 32 / kRowGroup ? b0 + (g + 1) * kRowGroup : (tile + nwarps) * 32;
-      row_load_group<NP>(p, nb, lane, nwords, Wn);
+      row_load_group<NP, ALIGNED>(p, nb, lane, nwords, Wn);
       float Gl[kRowGroup];
 #pragma unroll
       for (int i = 0; i < kRowGroup; ++i) {
@@ -339,6 +340,199 @@ __global__ void __launch_bounds__(kUniThreads, row_min_ctas(MODEL, NP)) irt_uni_
 }
 
 // ---------------------------------------------------------------------------------------------------
+// dense, J <= 64: a row is WP = 2..16 words, so 32 / WP persons share a warp step
+// ---------------------------------------------------------------------------------------------------
+// Same mapping as irt_uni_row_kernel with the lanes split into 32 / WP groups of WP lanes: lane l owns word
+// l % WP (4 items, parameters and gradient sums in registers) and, in step t, works on person t * (32 / WP) +
+// l / WP of the tile.  The per-person sum of d lb / d x needs log2(WP) shuffles inside the group; the item sums
+// of the groups are combined once, at the end of the kernel.  Typical test lengths (J = 20..60; the reference's
+// own data sets have J = 5 and 6) keep all 32 lanes busy this way.
+template <int MODEL, int WP, bool FAST>
+__global__ void __launch_bounds__(kUniThreads) irt_uni_rowsm_kernel(const IrtUniParams p) {
+  constexpr int NQ = MODEL;
+  constexpr int PPS = 32 / WP;          // persons per step
+  constexpr int JP = 4 * WP;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float* acc_sm = reinterpret_cast<float*>(smem_raw);             // [warp][NQ][JP], used after the main loop
+  const int J = p.J, nwords = (J + 3) >> 2;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int wl = lane % WP, grp = lane / WP;
+
+  float Ap[4], Bp[4], Cc[4], Dm[4], Om[4], Gc[4];
+  int ok = 1;
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    const int j = 4 * wl + c;
+    const bool in = j < J;
+    const float aj = (MODEL >= 2 && in) ? p.a[j] : (in ? 1.f : 0.f);
+    const float bj = in ? p.b[j] : 0.f;
+    const float cj = (MODEL >= 3 && in) ? p.c[j] : 0.f;
+    const float dj = (MODEL == 4 && in) ? p.d[j] : 1.f;
+    Ap[c] = -p.D * kLog2e * aj;
+    Bp[c] = -p.D * kLog2e * bj;
+    Cc[c] = cj;
+    Dm[c] = dj - cj;
+    Om[c] = 1.f - dj;
+    Gc[c] = p.D * aj * (dj - cj);
+    if (FAST && in) ok &= (cj >= 1e-3f) && (dj <= 1.f - 1e-3f) && (dj - cj >= 1e-3f);
+  }
+  const bool use_fast = FAST && __all_sync(0xffffffffu, ok);
+  float2 Ah[2], Bh[2], Gh[2], acc2[2][NQ >= 2 ? 2 : 1];
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    Ah[h] = make_float2(0.5f * Ap[2 * h], 0.5f * Ap[2 * h + 1]);
+    Bh[h] = make_float2(0.5f * Bp[2 * h], 0.5f * Bp[2 * h + 1]);
+    Gh[h] = make_float2(0.5f * Gc[2 * h], 0.5f * Gc[2 * h + 1]);
+    acc2[h][0] = make_float2(0.f, 0.f);
+    if constexpr (NQ >= 2) acc2[h][1] = make_float2(0.f, 0.f);
+  }
+  float acc[4][NQ];
+#pragma unroll
+  for (int c = 0; c < 4; ++c)
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) acc[c][q] = 0.f;
+
+  double loss_acc = 0.0;
+  const int64_t ntiles = (p.B + 31) / 32;
+  const int64_t gwarp = (int64_t)blockIdx.x * kUniWarps + warp;
+  const int64_t nwarps = (int64_t)gridDim.x * kUniWarps;
+
+  const bool aligned = rows_word_aligned(p);
+  for (int64_t tile = gwarp; tile < ntiles; tile += nwarps) {
+    const int64_t b0 = tile * 32;
+    const RowTileLane tl = row_tile_lane(p, b0 + lane);
+    const int rows = (int)min((int64_t)32, p.B - b0);
+    uint32_t W[WP];
+#pragma unroll
+    for (int t = 0; t < WP; ++t) {
+      const int64_t b = b0 + t * PPS + grp;
+      const bool okb = b < p.B && wl < nwords;
+      int64_t row = b;
+      if (okb && p.idx) row = __ldg(p.idx + b);
+      const uint8_t* g = p.y + row * p.ld_y;
+      W[t] = !okb ? 0xffffffffu : (aligned ? __ldg(reinterpret_cast<const uint32_t*>(g) + wl) : row_word(g, wl, J));
+    }
+    float Gmine = 0.f, Ltile = 0.f;
+    int n_half = 0;
+#pragma unroll
+    for (int t = 0; t < WP; ++t) {
+      const float x = __shfl_sync(0xffffffffu, tl.x, t * PPS + grp);
+      const uint32_t word = W[t];
+      n_half += __popc(word & 0x02020202u);
+      float Gi = 0.f;
+      if constexpr (MODEL <= 2) {
+        // packed 1PL / 2PL cells, see irt_uni_row_kernel
+        const float2 xx = make_float2(x, x);
+        const uint32_t nw = ~word;
+        const uint32_t T = ((nw << 7) & 0x80808080u) | (nw & 0x40404040u);
+        float2 sg[2], tt[2], sp[2], es[2];
+        sg[0] = make_float2(__uint_as_float(__byte_perm(T, 0u, 0x0444u)), __uint_as_float(__byte_perm(T, 0u, 0x1444u)));
+        sg[1] = make_float2(__uint_as_float(__byte_perm(T, 0u, 0x2444u)), __uint_as_float(__byte_perm(T, 0u, 0x3444u)));
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          tt[h] = __fmul2_rn(sg[h], __ffma2_rn(Ah[h], xx, Bh[h]));
+          const float2 e = make_float2(ex2_approx(fminf(tt[h].x, 23.f)), ex2_approx(fminf(tt[h].y, 23.f)));
+          const float2 ope = __fadd2_rn(e, make_float2(1.f, 1.f));
+          sp[h] = make_float2(rcp_approx(ope.x), rcp_approx(ope.y));
+          es[h] = __fmul2_rn(e, sp[h]);
+        }
+        if (fmaxf(fmaxf(tt[0].x, tt[0].y), fmaxf(tt[1].x, tt[1].y)) >= 23.f) {
+          if (tt[0].x >= 23.f) es[0].x = 0.f;
+          if (tt[0].y >= 23.f) es[0].y = 0.f;
+          if (tt[1].x >= 23.f) es[1].x = 0.f;
+          if (tt[1].y >= 23.f) es[1].y = 0.f;
+        }
+        float2 G2 = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const float2 ws = __fmul2_rn(sg[h], es[h]);
+          G2 = __ffma2_rn(Gh[h], ws, G2);
+          acc2[h][0] = __fadd2_rn(acc2[h][0], ws);
+          if constexpr (NQ >= 2) acc2[h][1] = __ffma2_rn(ws, xx, acc2[h][1]);
+        }
+        const float2 pr = __fmul2_rn(sp[0], sp[1]);
+        Ltile += lg2_approx(pr.x * pr.y);
+        Gi = G2.x + G2.y;
+      } else {
+        float prod = 1.f;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const uint32_t code = (word >> (8 * c)) & 0xffu;
+          const bool obs = code != 255u, y1 = code != 0u;
+          const float t0 = fmaf(Ap[c], x, Bp[c]);
+          const float tv = y1 ? t0 : -t0;
+          const float base = y1 ? Cc[c] : Om[c];
+          float w, a1, a2, qc;
+          if (FAST && use_fast) cell_eval1<MODEL, true>(tv, Dm[c], base, obs, w, a1, a2, qc);
+          else cell_eval1<MODEL, false>(tv, Dm[c], base, obs, w, a1, a2, qc);
+          const float ws = y1 ? w : -w;
+          Gi = fmaf(Gc[c], ws, Gi);
+          acc[c][0] += ws;
+          acc[c][1] = fmaf(ws, x, acc[c][1]);
+          if constexpr (NQ >= 3) acc[c][2] += y1 ? a2 : -a1;
+          if constexpr (NQ >= 4) acc[c][3] += y1 ? a1 : -a2;
+          prod *= qc;
+        }
+        Ltile += lg2_approx(prod);
+      }
+      // the person's sum over its WP lanes, then handed to the lane that owns the person (lane index = slot in tile)
+#pragma unroll
+      for (int o = WP / 2; o > 0; o >>= 1) Gi += __shfl_xor_sync(0xffffffffu, Gi, o);
+      const float v = __shfl_sync(0xffffffffu, Gi, (lane % PPS) * WP);
+      if (lane / PPS == t) Gmine = v;
+    }
+    if constexpr (MODEL <= 2) Ltile += (float)n_half;     // every missing cell put a factor 1/2 into the product
+    row_tile_finish(p, tl, b0 + lane, Gmine, Ltile, n_half + (lane == 0 ? rows * J - 32 * JP : 0), loss_acc);
+  }
+
+  // ---- item sums: groups -> lane group 0, warps -> CTA partial row ----------------------------------------------
+  if constexpr (MODEL <= 2) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h)
+#pragma unroll
+      for (int q = 0; q < NQ; ++q) {
+        acc[2 * h][q] = 0.5f * acc2[h][q].x;
+        acc[2 * h + 1][q] = 0.5f * acc2[h][q].y;
+      }
+  }
+#pragma unroll
+  for (int c = 0; c < 4; ++c)
+#pragma unroll
+    for (int q = 0; q < NQ; ++q)
+#pragma unroll
+      for (int o = WP; o < 32; o <<= 1) acc[c][q] += __shfl_xor_sync(0xffffffffu, acc[c][q], o);
+  __shared__ double loss_sm[kUniWarps];
+  loss_acc = warp_sum(loss_acc);
+  if (lane == 0) loss_sm[warp] = loss_acc;
+  if (p.want_grad && grp == 0) {
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+#pragma unroll
+      for (int q = 0; q < NQ; ++q) acc_sm[((size_t)warp * NQ + q) * JP + 4 * wl + c] = acc[c][q];
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+#pragma unroll
+    for (int w = 0; w < kUniWarps; ++w) t += loss_sm[w];
+    p.loss_partial[blockIdx.x] = t;
+  }
+  if (p.want_grad) {
+    for (int i = threadIdx.x; i < NQ * J; i += kUniThreads) {
+      const int q = i / J, j = i - q * J;
+      float t = 0.f;
+#pragma unroll
+      for (int w = 0; w < kUniWarps; ++w) t += acc_sm[((size_t)w * NQ + q) * JP + j];
+      if (q < 2) {
+        const float cj = MODEL >= 3 ? p.c[j] : 0.f, dj = MODEL == 4 ? p.d[j] : 1.f;
+        t *= p.D * (dj - cj);
+      }
+      p.item_partial[(size_t)blockIdx.x * NQ * J + i] = t;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
 // sparse
 // ---------------------------------------------------------------------------------------------------
 __host__ __device__ inline size_t rowsp_smem_bytes(int J, int NQ) {
@@ -348,11 +542,11 @@ __host__ __device__ inline size_t rowsp_smem_bytes(int J, int NQ) {
   return s;
 }
 
-template <int MODEL, int NP, bool FAST>
+template <int MODEL, int NP, bool FAST, bool ALIGNED>
 __global__ void __launch_bounds__(kUniThreads) irt_uni_rowsp_kernel(const IrtUniParams p) {
   constexpr int NQ = MODEL;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int J = p.J, nwords = J >> 2;
+  const int J = p.J, nwords = (J + 3) >> 2;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   float4* tab = reinterpret_cast<float4*>(smem_raw);                                   // {A', B', c, d-c}
   float2* tab2 = reinterpret_cast<float2*>(smem_raw + (size_t)J * 16);                 // {D a (d-c), 1-d}
@@ -381,7 +575,7 @@ __global__ void __launch_bounds__(kUniThreads) irt_uni_rowsp_kernel(const IrtUni
   const uint32_t lt_mask = (1u << lane) - 1u;
 
   uint32_t Wc[kRowGroup][NP], Wn[kRowGroup][NP];
-  if (gwarp < ntiles) row_load_group<NP>(p, gwarp * 32, lane, nwords, Wc);
+  if (gwarp < ntiles) row_load_group<NP, ALIGNED>(p, gwarp * 32, lane, nwords, Wc);
 
   for (int64_t tile = gwarp; tile < ntiles; tile += nwarps) {
     const int64_t b0 = tile * 32;
@@ -392,7 +586,7 @@ __global__ void __launch_bounds__(kUniThreads) irt_uni_rowsp_kernel(const IrtUni
 #pragma unroll 1
     for (int g = 0; g < 32 / kRowGroup; ++g) {
       const int64_t nb = g + 1 < 32 / kRowGroup ? b0 + (g + 1) * kRowGroup : (tile + nwarps) * 32;
-      row_load_group<NP>(p, nb, lane, nwords, Wn);
+      row_load_group<NP, ALIGNED>(p, nb, lane, nwords, Wn);
       float Gl[kRowGroup];
 #pragma unroll
       for (int i = 0; i < kRowGroup; ++i) {
@@ -502,17 +696,41 @@ static int launch_row_dense(IrtUniParams& p, cudaStream_t st, int* grid) {
   static int occ = 0;
   static size_t occ_smem = ~size_t(0);
   const size_t smem = (size_t)kUniWarps * MODEL * NP * 128 * 4;
-  return launch_row(irt_uni_row_kernel<MODEL, NP, FAST>, p, smem, st, grid, &occ, &occ_smem);
+  static int occ_u = 0;
+  static size_t occ_smem_u = ~size_t(0);
+  if (!rows_word_aligned(p))
+    return launch_row(irt_uni_row_kernel<MODEL, NP, FAST, false>, p, smem, st, grid, &occ_u, &occ_smem_u);
+  return launch_row(irt_uni_row_kernel<MODEL, NP, FAST, true>, p, smem, st, grid, &occ, &occ_smem);
 }
 template <int MODEL, int NP, bool FAST>
 static int launch_row_sparse(IrtUniParams& p, cudaStream_t st, int* grid) {
   static int occ = 0;
   static size_t occ_smem = ~size_t(0);
-  return launch_row(irt_uni_rowsp_kernel<MODEL, NP, FAST>, p, rowsp_smem_bytes(p.J, MODEL), st, grid, &occ, &occ_smem);
+  static int occ_u = 0;
+  static size_t occ_smem_u = ~size_t(0);
+  if (!rows_word_aligned(p))
+    return launch_row(irt_uni_rowsp_kernel<MODEL, NP, FAST, false>, p, rowsp_smem_bytes(p.J, MODEL), st, grid, &occ_u,
+                      &occ_smem_u);
+  return launch_row(irt_uni_rowsp_kernel<MODEL, NP, FAST, true>, p, rowsp_smem_bytes(p.J, MODEL), st, grid, &occ, &occ_smem);
+}
+
+template <int MODEL, int WP, bool FAST>
+static int launch_row_small(IrtUniParams& p, cudaStream_t st, int* grid) {
+  static int occ = 0;
+  static size_t occ_smem = ~size_t(0);
+  const size_t smem = (size_t)kUniWarps * MODEL * 4 * WP * 4;
+  return launch_row(irt_uni_rowsm_kernel<MODEL, WP, FAST>, p, smem, st, grid, &occ, &occ_smem);
 }
 
 template <int MODEL, bool FAST>
 static int launch_row_np(bool sparse, int NP, IrtUniParams& p, cudaStream_t st, int* grid) {
+  if (!sparse && p.J <= 64) {                       // several persons per warp step
+    const int nw = (p.J + 3) >> 2;
+    if (nw <= 2) return launch_row_small<MODEL, 2, FAST>(p, st, grid);
+    if (nw <= 4) return launch_row_small<MODEL, 4, FAST>(p, st, grid);
+    if (nw <= 8) return launch_row_small<MODEL, 8, FAST>(p, st, grid);
+    return launch_row_small<MODEL, 16, FAST>(p, st, grid);
+  }
   if (sparse) {
     switch (NP) {
       case 1: return launch_row_sparse<MODEL, 1, FAST>(p, st, grid);
@@ -533,19 +751,19 @@ static int launch_row_np(bool sparse, int NP, IrtUniParams& p, cudaStream_t st, 
   }
 }
 
-// Does the row mapping cover this call?  S == 1 pathwise, 32-bit aligned rows, enough items to fill a
-// warp's lanes, few enough for the register-resident (dense) / 4-word-prefetch (sparse) layouts.
+// Does the row mapping cover this call?  S == 1 pathwise; any row alignment and length (row_word); few enough items
+// for the register-resident (dense) / 4-word-prefetch (sparse) layouts.  Short rows (J <= 64) take the
+// several-persons-per-step kernel; the compaction form needs rows long enough to be worth compacting.
 bool irt_uni_row_supported(const VipsyIrtArgs* a, bool sparse) {
   if (a->n_particles != 1 || a->estimator != VIPSY_EST_PATHWISE) return false;
   const int J = a->n_items;
-  if ((J & 3) || (a->y_row_stride & 3) || (reinterpret_cast<uintptr_t>(a->y) & 3)) return false;
-  if (J < 64) return false;
-  if (sparse) return J <= 512 && rowsp_smem_bytes(J, a->model) <= 200 * 1024;
+  if (sparse && J > 64) return J <= 512 && rowsp_smem_bytes(J, a->model) <= 200 * 1024;
   return J <= (a->model <= 2 ? 512 : 256);
 }
 
 int irt_uni_row_launch(int model, bool fast, bool sparse, IrtUniParams& p, cudaStream_t st, int* grid_out) {
   const int NP = (p.J + 127) / 128;
+  if (p.J <= 64) sparse = false;
   switch (model) {
     case VIPSY_IRT_1PL: return launch_row_np<1, false>(sparse, NP, p, st, grid_out);
     case VIPSY_IRT_2PL: return launch_row_np<2, false>(sparse, NP, p, st, grid_out);
