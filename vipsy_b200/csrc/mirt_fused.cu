@@ -321,7 +321,10 @@ __global__ void __launch_bounds__(kFuThreads) mirt_fused_kernel(const MirtParams
 
 // ------------------------------------------------------------------------------------------------------------------
 bool mirt_fused_supported(const MirtParams& p) {
-  return p.cov_mode == VIPSY_COV_PERSON && p.K >= 2 && p.K <= 8 && p.model >= VIPSY_IRT_2PL &&
+  // measured (scripts/dev_bench_mirt_fused.py): 2.4-8x faster than the three-kernel path for K = 2..7; at K = 8 the
+  // tcgen05 contraction takes over (0.52 vs 0.68 ms).  The score estimator exists only here, so it keeps K = 8.
+  const int kmax = p.score ? 8 : 7;
+  return p.cov_mode == VIPSY_COV_PERSON && p.K >= 2 && p.K <= kmax && p.model >= VIPSY_IRT_2PL &&
          fused_smem_bytes(p.J, p.K, p.model) <= 200 * 1024;
 }
 
