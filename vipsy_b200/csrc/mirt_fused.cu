@@ -32,9 +32,11 @@ __host__ __device__ inline size_t fused_smem_bytes(int J, int K, int model) {
 // SCORE: REINFORCE estimator for the guide parameters (north star (d); SURVEY A.2 "score mode"): x is a constant,
 // each particle's weight w_s = scale (ll_s + log p(x_s) - log q(x_s)) - baseline multiplies the score of q,
 // grad_mu log q = L^-T eps, grad_L log q = tril(L^-T eps eps^T) - diag(1 / L_ii); item gradients are unchanged.
-template <int K, int MODEL, bool SCORE>
+// SC: particles held in registers at once (fused_sc(): 8 / 4 / 2 by K; 2 when the call has at most two particles)
+__host__ __device__ constexpr int fused_sc(int K) { return K <= 2 ? 8 : (K <= 6 ? 4 : 2); }
+
+template <int K, int MODEL, bool SCORE, int SC>
 __global__ void __launch_bounds__(kFuThreads) mirt_fused_kernel(const MirtParams p) {
-  constexpr int SC = K <= 2 ? 8 : (K <= 4 ? 4 : 2);                  // particles held in registers at once
   constexpr int NQ = K + 1 + (MODEL >= 3 ? 1 : 0) + (MODEL >= 4 ? 1 : 0);
   constexpr int TRI = K * (K + 1) / 2;
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -328,9 +330,9 @@ bool mirt_fused_supported(const MirtParams& p) {
          fused_smem_bytes(p.J, p.K, p.model) <= 200 * 1024;
 }
 
-template <int K, int MODEL, bool SCORE>
-static int launch_fused_one(const MirtParams& p, int max_grid, int* grid_out, cudaStream_t st) {
-  auto kern = mirt_fused_kernel<K, MODEL, SCORE>;
+template <int K, int MODEL, bool SCORE, int SC>
+static int launch_fused_sc(const MirtParams& p, int max_grid, int* grid_out, cudaStream_t st) {
+  auto kern = mirt_fused_kernel<K, MODEL, SCORE, SC>;
   const size_t smem = fused_smem_bytes(p.J, K, MODEL);
   static int occ = 0;
   static size_t occ_smem = ~size_t(0);
@@ -351,6 +353,14 @@ static int launch_fused_one(const MirtParams& p, int max_grid, int* grid_out, cu
   VIPSY_CUDA_CHECK(cudaGetLastError());
   *grid_out = (int)g;
   return VIPSY_OK;
+}
+
+template <int K, int MODEL, bool SCORE>
+static int launch_fused_one(const MirtParams& p, int max_grid, int* grid_out, cudaStream_t st) {
+  // few particles: the wide chunk only costs registers (measured: K = 5, S = 1: 0.39 ms with SC = 2, 0.43 with 4)
+  if constexpr (!SCORE && fused_sc(K) > 2)
+    if (p.S <= 2) return launch_fused_sc<K, MODEL, SCORE, 2>(p, max_grid, grid_out, st);
+  return launch_fused_sc<K, MODEL, SCORE, fused_sc(K)>(p, max_grid, grid_out, st);
 }
 
 template <int K>
