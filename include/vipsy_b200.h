@@ -327,6 +327,50 @@ int vipsy_adam_step(const VipsyAdamTensor* tensors_host, int32_t n_tensors, cons
                     int32_t zero_grad, void* stream);
 
 /* ------------------------------------------------------------------------
+ * Amortised guide of VaeIRT, K = 1: NormEncoder (vi.py:417-435) evaluated on the stored response codes with the
+ * guide's input rule NaN -> -1 (vi.py:679-682):
+ *     hidden = softplus(fc1(x)),  mu = fc21(hidden),  sigma = exp(fc22(hidden)).
+ * forward writes mu, sigma (the kernel inputs of vipsy_irt_elbo_grad) and the fc1 pre-activations; backward
+ * takes the kernel's d_mu / d_sigma and produces the gradients of all six encoder tensors (d x is never
+ * needed), deterministic: per-CTA partial rows summed in a fixed order with fp64 accumulation.  The fp32
+ * response matrix and the hidden activations of the torch formulation are never materialised.
+ * n_hidden <= 64 (the reference's default hidden_dim, vi.py:661); any n_items.
+ * ---------------------------------------------------------------------- */
+typedef struct VipsyNormEncoderArgs {
+  int64_t n_rows;            /* rows of y                                   */
+  int64_t batch;             /* B                                           */
+  int32_t n_items;           /* J                                           */
+  int32_t n_hidden;          /* H <= 64                                     */
+  const uint8_t* y;          /* response codes 0 / 1 / 255, n_rows x y_row_stride */
+  int64_t y_row_stride;
+  const int64_t* idx;        /* [B] or NULL                                 */
+  const float* w1;           /* fc1.weight  [H x J] row-major               */
+  const float* b1;           /* fc1.bias    [H]                             */
+  const float* w21;          /* fc21.weight [H]                             */
+  const float* b21;          /* fc21.bias   [1]                             */
+  const float* w22;          /* fc22.weight [H]                             */
+  const float* b22;          /* fc22.bias   [1]                             */
+  float* mu;                 /* [B]   forward out                           */
+  float* sigma;              /* [B]   forward out, backward in              */
+  float* pre;                /* [B x H] fc1 pre-activations: forward out, backward in */
+  const float* d_mu;         /* [B]   backward in                           */
+  const float* d_sigma;      /* [B]   backward in (w.r.t. sigma, not log sigma) */
+  float grad_scale;          /* multiplies every output gradient (1 / particle groups) */
+  int32_t reserved;
+  float* d_w1;               /* [H x J] backward out (overwritten)          */
+  float* d_b1;               /* [H]                                         */
+  float* d_w21;              /* [H]                                         */
+  float* d_b21;              /* [1]                                         */
+  float* d_w22;              /* [H]                                         */
+  float* d_b22;              /* [1]                                         */
+  void* workspace;           /* backward: vipsy_norm_encoder_workspace_bytes */
+  size_t workspace_bytes;
+} VipsyNormEncoderArgs;
+size_t vipsy_norm_encoder_workspace_bytes(const VipsyNormEncoderArgs* args);
+int vipsy_norm_encoder_forward(const VipsyNormEncoderArgs* args, void* stream);
+int vipsy_norm_encoder_backward(const VipsyNormEncoderArgs* args, void* stream);
+
+/* ------------------------------------------------------------------------
  * Diagnostics: one 128-row tcgen05 tile product per operand orientation of the
  * tensor-core MIRT kernel (fp16 hi/lo split, fp32 accumulation in TMEM).
  *   variant 0: out[128 x c2] = t1[r1 x c1] . t2[r2 x c2]        (c1 == r2)

@@ -173,6 +173,16 @@ def _mask_nan(p, y):
     return p, y, nan
 
 
+def norm_encoder(y, w1, b1, w21, b21, w22, b22, dtype=torch.float64):
+    """``NormEncoder.forward`` (vi.py:417-435) on the guide's input (vi.py:679-682: NaN -> -1):
+    hidden = softplus(fc1(x)); returns (fc21(hidden), exp(fc22(hidden))), each B x 1.  Differentiable in the six
+    weight tensors (pass leaves to get their gradients by autograd)."""
+    x = y.to(dtype)
+    x = torch.where(torch.isnan(x), torch.full_like(x, -1.0), x)
+    hidden = torch.nn.functional.softplus(x @ w1.to(dtype).t() + b1.to(dtype))
+    return hidden @ w21.to(dtype).t() + b21.to(dtype), torch.exp(hidden @ w22.to(dtype).t() + b22.to(dtype))
+
+
 def _leaf(t, dtype):
     return None if t is None else t.detach().to(dtype).clone().requires_grad_(True)
 

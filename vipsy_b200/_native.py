@@ -93,6 +93,18 @@ class AdamTensor(C.Structure):
     ]
 
 
+class NormEncoderArgs(C.Structure):
+    _fields_ = [
+        ("n_rows", C.c_int64), ("batch", C.c_int64), ("n_items", C.c_int32), ("n_hidden", C.c_int32),
+        ("y", _p), ("y_row_stride", C.c_int64), ("idx", _p),
+        ("w1", _p), ("b1", _p), ("w21", _p), ("b21", _p), ("w22", _p), ("b22", _p),
+        ("mu", _p), ("sigma", _p), ("pre", _p), ("d_mu", _p), ("d_sigma", _p),
+        ("grad_scale", C.c_float), ("reserved", C.c_int32),
+        ("d_w1", _p), ("d_b1", _p), ("d_w21", _p), ("d_b21", _p), ("d_w22", _p), ("d_b22", _p),
+        ("workspace", _p), ("workspace_bytes", C.c_size_t),
+    ]
+
+
 # every symbol include/vipsy_b200.h declares: name -> (restype, argtypes)
 SYMBOLS = {
     "vipsy_abi_version": (C.c_int, []),
@@ -116,6 +128,9 @@ SYMBOLS = {
     "vipsy_fill_uniform_dev": (C.c_int, [_p, C.c_int32, C.c_int64, C.c_int32, C.c_uint64, _p, C.c_int64, _p]),
     "vipsy_peer_allreduce": (C.c_int, [_p, C.c_int32, C.c_int32, C.c_int64, C.c_int64, C.c_int32, C.c_int32, _p, _p,
                                        C.c_uint32, _p]),
+    "vipsy_norm_encoder_workspace_bytes": (C.c_size_t, [C.POINTER(NormEncoderArgs)]),
+    "vipsy_norm_encoder_forward": (C.c_int, [C.POINTER(NormEncoderArgs), _p]),
+    "vipsy_norm_encoder_backward": (C.c_int, [C.POINTER(NormEncoderArgs), _p]),
     "vipsy_adam_step": (C.c_int, [C.POINTER(AdamTensor), C.c_int32, _p, C.c_int32, _p]),
     "vipsy_selftest_umma": (C.c_int, [_p, C.c_int32, C.c_int32, _p, C.c_int32, C.c_int32, _p, C.c_int32, C.c_int32,
                                       C.c_int32, _p]),

@@ -351,11 +351,23 @@ class VaeIRT(BaseIRT):                  # vi.py:659-693
         super().__init__(*args, **kwargs)
         enc = NormEncoder if self.x_feature == 1 else MvnEncoder
         self.encoder = enc(self.item_size, self.x_feature, hidden_dim).to(self.device)
+        self.fused_encoder = True       # K = 1: encoder forward / backward as CUDA kernels (False: torch autograd)
 
     def _guide(self, idx, B):
         get_param_store().register_module("encoder", self.encoder)
-        x_loc, x_sc = self.encoder(self._encoder_input(idx))
         sites = [(f"encoder$$${n}", p, None) for n, p in self.encoder.named_parameters()]
+        if self.x_feature == 1 and self.fused_encoder and self.encoder.fc1.out_features <= ops.NORM_ENCODER_MAX_HIDDEN:
+            # NormEncoder evaluated by the CUDA kernels on the response codes (csrc/enc_norm.cu): no fp32 input
+            # matrix, no stored hidden activations, deterministic weight gradients
+            enc = self.encoder
+            mu, sigma, pre = ops.norm_encoder_forward(self._codes, enc, idx)
+
+            def backward(r, w):
+                g = ops.norm_encoder_backward(self._codes, enc, sigma, pre, r["d_mu"], r["d_sigma"], idx, grad_scale=w)
+                for n, p in enc.named_parameters():
+                    _accum(p, g[n])
+            return dict(mu=mu, sigma=sigma), backward, sites
+        x_loc, x_sc = self.encoder(self._encoder_input(idx))
         if self.x_feature == 1:
             def backward(r, w):
                 torch.autograd.backward([x_loc, x_sc], [r["d_mu"] * w, r["d_sigma"] * w])

@@ -466,3 +466,70 @@ def cdm_score_elbo_grad(
     out["loss"] = loss
     out["_keepalive"] = (qm, g_, s_, ap_, u_, idx_, ws)
     return out
+
+
+# --------------------------------------------------------------------------- NormEncoder (vi.py:417-435, 677-684)
+NORM_ENCODER_MAX_HIDDEN = 64
+
+
+def _norm_encoder_args(y, idx, enc):
+    """enc: object with fc1 / fc21 / fc22 ``nn.Linear`` members (fc21, fc22 have one output)."""
+    if not y.is_cuda or y.dtype != torch.uint8 or y.dim() != 2 or y.stride(1) != 1:
+        raise ValueError("y must be a CUDA uint8 code matrix (see pack_responses)")
+    H, J = enc.fc1.weight.shape
+    if J != y.shape[1] or enc.fc21.weight.shape != (1, H) or enc.fc22.weight.shape != (1, H):
+        raise ValueError("encoder shapes do not match the response matrix / K = 1")
+    a = N.NormEncoderArgs()
+    a.n_rows, a.n_items, a.n_hidden = y.shape[0], J, H
+    a.y, a.y_row_stride = _ptr(y), y.stride(0)
+    if idx is not None:
+        if idx.dtype != torch.int64 or not idx.is_cuda:
+            raise ValueError("idx must be a CUDA int64 tensor")
+        idx = idx.contiguous()
+        a.idx, a.batch = _ptr(idx), idx.numel()
+    else:
+        a.batch = y.shape[0]
+    keep = [idx]
+    for name, t in (("w1", enc.fc1.weight), ("b1", enc.fc1.bias), ("w21", enc.fc21.weight), ("b21", enc.fc21.bias),
+                    ("w22", enc.fc22.weight), ("b22", enc.fc22.bias)):
+        t = _f32(t, name)
+        keep.append(t)
+        setattr(a, name, _ptr(t))
+    return a, keep
+
+
+def norm_encoder_forward(y: torch.Tensor, enc, idx: Optional[torch.Tensor] = None):
+    """mu [B], sigma [B], pre [B, H] of the amortised K = 1 guide, straight from the response codes."""
+    a, keep = _norm_encoder_args(y, idx, enc)
+    dev, B, H = y.device, int(a.batch), int(a.n_hidden)
+    mu = torch.empty(B, dtype=torch.float32, device=dev)
+    sigma = torch.empty(B, dtype=torch.float32, device=dev)
+    pre = torch.empty((B, H), dtype=torch.float32, device=dev)
+    a.mu, a.sigma, a.pre = _ptr(mu), _ptr(sigma), _ptr(pre)
+    N.check(N.lib().vipsy_norm_encoder_forward(C.byref(a), _stream()))
+    return mu, sigma, pre
+
+
+def norm_encoder_backward(y: torch.Tensor, enc, sigma: torch.Tensor, pre: torch.Tensor, d_mu: torch.Tensor,
+                          d_sigma: torch.Tensor, idx: Optional[torch.Tensor] = None, grad_scale: float = 1.0):
+    """Gradients of the six encoder tensors given d loss / d mu and d loss / d sigma; returns a dict keyed by the
+    ``named_parameters`` names (fc1.weight, fc1.bias, fc21.weight, ...), shaped like the parameters."""
+    a, keep = _norm_encoder_args(y, idx, enc)
+    dev, B, H, J = y.device, int(a.batch), int(a.n_hidden), int(a.n_items)
+    sigma, pre = _f32(sigma, "sigma", B), _f32(pre, "pre", B * H)
+    d_mu, d_sigma = _f32(d_mu, "d_mu", B), _f32(d_sigma, "d_sigma", B)
+    a.sigma, a.pre, a.d_mu, a.d_sigma, a.grad_scale = _ptr(sigma), _ptr(pre), _ptr(d_mu), _ptr(d_sigma), grad_scale
+    out = {"fc1.weight": torch.empty((H, J), dtype=torch.float32, device=dev),
+           "fc1.bias": torch.empty(H, dtype=torch.float32, device=dev),
+           "fc21.weight": torch.empty((1, H), dtype=torch.float32, device=dev),
+           "fc21.bias": torch.empty(1, dtype=torch.float32, device=dev),
+           "fc22.weight": torch.empty((1, H), dtype=torch.float32, device=dev),
+           "fc22.bias": torch.empty(1, dtype=torch.float32, device=dev)}
+    a.d_w1, a.d_b1 = _ptr(out["fc1.weight"]), _ptr(out["fc1.bias"])
+    a.d_w21, a.d_b21 = _ptr(out["fc21.weight"]), _ptr(out["fc21.bias"])
+    a.d_w22, a.d_b22 = _ptr(out["fc22.weight"]), _ptr(out["fc22.bias"])
+    L = N.lib()
+    ws = _workspace("norm_encoder", L.vipsy_norm_encoder_workspace_bytes(C.byref(a)), dev)
+    a.workspace, a.workspace_bytes = _ptr(ws), ws.numel()
+    N.check(L.vipsy_norm_encoder_backward(C.byref(a), _stream()))
+    return out
