@@ -37,12 +37,20 @@ __device__ __forceinline__ float code_x(uint32_t c) { return c == 255u ? -1.0f :
 constexpr int kEncWords = kEncTB * (kEncJC / 4) / kEncThreads;      // 16
 __device__ __forceinline__ void load_codes(uint32_t (&wd)[kEncWords], const EncParams& P, int64_t tile0, int j0,
                                            bool aligned) {
+  const int w = threadIdx.x & 31, p0 = threadIdx.x >> 5;            // word w of persons p0 + 8 q
+  const int j = j0 + 4 * w;
+  if (aligned && P.idx == nullptr && tile0 + kEncTB <= P.B && (j + 3 < P.J || j >= P.J)) {
+    // interior tile, whole (or absent) word: 16 independent loads, no per-word control flow
+    const uint32_t* g = reinterpret_cast<const uint32_t*>(P.y + (tile0 + p0) * P.ld + j);
+    const int64_t step = 2 * P.ld;                                   // 8 rows, in words
+    const bool live = j < P.J;
+#pragma unroll
+    for (int q = 0; q < kEncWords; ++q) wd[q] = live ? __ldg(g + q * step) : 0u;
+    return;
+  }
 #pragma unroll
   for (int q = 0; q < kEncWords; ++q) {
-    const int e = threadIdx.x + q * kEncThreads;
-    const int p = e >> 5, w = e & 31;
-    const int64_t r = tile0 + p;
-    const int j = j0 + 4 * w;
+    const int64_t r = tile0 + p0 + 8 * q;
     uint32_t word = 0;
     if (r < P.B && j < P.J) {
       const uint8_t* g = P.y + (P.idx ? __ldg(P.idx + r) : r) * P.ld + j;
@@ -233,6 +241,7 @@ __global__ void __launch_bounds__(kEncThreads, 2) enc_norm_bwd_kernel(const EncP
         const int64_t r = tile0 + pq + 4 * i;
         pv[i] = (r < P.B && h < P.H) ? __ldg(P.pre + (size_t)r * P.H + h) : 0.0f;
       }
+      asm volatile("" ::: "memory");                // all 32 loads are issued before the first use
 #pragma unroll
       for (int i = 0; i < kEncTB / 4; ++i) {
         const int p = pq + 4 * i;
