@@ -334,7 +334,8 @@ int vipsy_adam_step(const VipsyAdamTensor* tensors_host, int32_t n_tensors, cons
  * takes the kernel's d_mu / d_sigma and produces the gradients of all six encoder tensors (d x is never
  * needed), deterministic: per-CTA partial rows summed in a fixed order with fp64 accumulation.  The fp32
  * response matrix and the hidden activations of the torch formulation are never materialised.
- * n_hidden <= 64 (the reference's default hidden_dim, vi.py:661); any n_items.
+ * n_hidden <= 64 (the reference's default hidden_dim, vi.py:661); any n_items.  J <= 127: both products run on
+ * the tensor cores (tcgen05, 3-term bf16 split of the fp32 factor, fp32 accumulation in TMEM); else FFMA2 tiles.
  * ---------------------------------------------------------------------- */
 typedef struct VipsyNormEncoderArgs {
   int64_t n_rows;            /* rows of y                                   */
@@ -356,7 +357,7 @@ typedef struct VipsyNormEncoderArgs {
   const float* d_mu;         /* [B]   backward in                           */
   const float* d_sigma;      /* [B]   backward in (w.r.t. sigma, not log sigma) */
   float grad_scale;          /* multiplies every output gradient (1 / particle groups) */
-  int32_t reserved;
+  int32_t flags;             /* bit 0: SIMT kernels only (default: tcgen05 kernels when J <= 127) */
   float* d_w1;               /* [H x J] backward out (overwritten)          */
   float* d_b1;               /* [H]                                         */
   float* d_w21;              /* [H]                                         */

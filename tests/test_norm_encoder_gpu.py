@@ -1,5 +1,6 @@
 """GPU: the NormEncoder kernels (csrc/enc_norm.cu -- vi.py:417-435 with the guide's NaN -> -1 input rule,
-vi.py:679-682) against the fp64 oracle restatement: mu, sigma forward; all six weight gradients backward.
+vi.py:679-682; tcgen05 variant csrc/enc_norm_tc.cu for J <= 127) against the fp64 oracle restatement: mu, sigma
+forward; all six weight gradients backward; both kernel families.
 Floating point: tolerance 2e-5 of the largest magnitude of each tensor (fp32 accumulation over J and B)."""
 import pytest
 import torch
@@ -46,8 +47,11 @@ def _close(got, ref, name, tol=2e-5):
     (2000, 50, 64, 0.1, 333),        # minibatch through idx
     (1, 1, 1, 0.0, None),
     (40000, 64, 64, 0.05, None),     # more tiles than CTAs: persistent loop
+    (5000, 127, 64, 0.1, None),      # widest tensor-core shape (item slot 127 carries the bias column)
+    (3000, 16, 8, 0.1, None),
 ])
-def test_norm_encoder_forward_backward(ops, B, J, H, missing, sub):
+@pytest.mark.parametrize("tc", [True, False])
+def test_norm_encoder_forward_backward(ops, B, J, H, missing, sub, tc):
     g = torch.Generator().manual_seed(B * 31 + J)
     y = (torch.rand(B, J, generator=g) < 0.6).float()
     if missing:
@@ -55,11 +59,11 @@ def test_norm_encoder_forward_backward(ops, B, J, H, missing, sub):
     enc = _encoder(J, H, B + J + H)
     codes = codes_from_float(y).cuda()
     idx = torch.randperm(B, generator=g)[:sub].cuda() if sub else None
-    mu, sigma, pre = ops.norm_encoder_forward(codes, enc, idx)
+    mu, sigma, pre = ops.norm_encoder_forward(codes, enc, idx, tensor_cores=tc)
     Bb = sub or B
     d_mu = torch.randn(Bb, generator=g).cuda()
     d_sigma = torch.randn(Bb, generator=g).cuda()
-    got = ops.norm_encoder_backward(codes, enc, sigma, pre, d_mu, d_sigma, idx, grad_scale=0.5)
+    got = ops.norm_encoder_backward(codes, enc, sigma, pre, d_mu, d_sigma, idx, grad_scale=0.5, tensor_cores=tc)
     torch.cuda.synchronize()
     # oracle, fp64
     leaves = {n: p.detach().cpu().double().requires_grad_(True) for n, p in enc.named_parameters()}

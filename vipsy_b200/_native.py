@@ -99,7 +99,7 @@ class NormEncoderArgs(C.Structure):
         ("y", _p), ("y_row_stride", C.c_int64), ("idx", _p),
         ("w1", _p), ("b1", _p), ("w21", _p), ("b21", _p), ("w22", _p), ("b22", _p),
         ("mu", _p), ("sigma", _p), ("pre", _p), ("d_mu", _p), ("d_sigma", _p),
-        ("grad_scale", C.c_float), ("reserved", C.c_int32),
+        ("grad_scale", C.c_float), ("flags", C.c_int32),
         ("d_w1", _p), ("d_b1", _p), ("d_w21", _p), ("d_b21", _p), ("d_w22", _p), ("d_b22", _p),
         ("workspace", _p), ("workspace_bytes", C.c_size_t),
     ]

@@ -11,7 +11,7 @@
 //   backward: d fc1.weight[h][j] = sum_b dpre[b][h] * x[b][j], thread = 4 hidden units x 8 items held in
 //             registers across all the tiles of a persistent CTA; dpre is rebuilt per tile from `pre`.
 // Cross-CTA sums: one partial row per CTA, folded by finalize_kernel (fixed order, fp64) -> deterministic.
-#include "common.cuh"
+#include "enc_norm.cuh"
 
 namespace vipsy {
 
@@ -20,14 +20,6 @@ constexpr int kEncH = 64;               // hidden slots (weights zero-padded up 
 constexpr int kEncJC = 128;             // item columns per shared-memory chunk
 constexpr int kEncLd = kEncJC + 4;      // xs row pitch (floats): 16-byte aligned rows
 constexpr int kEncThreads = 256;
-
-struct EncParams {
-  const uint8_t* y; int64_t ld; const int64_t* idx; int64_t B; int J, H;
-  const float *w1, *b1, *w21, *b21, *w22, *b22;
-  float *mu, *sigma, *pre;
-  const float *d_mu, *d_sigma; float gscale;
-  float* partial; int cols;             // backward: [gridDim.x x cols]
-};
 
 __device__ __forceinline__ float code_x(uint32_t c) { return c == 255u ? -1.0f : (c ? 1.0f : 0.0f); }
 
@@ -74,16 +66,6 @@ __device__ __forceinline__ void store_x(float* xs, const uint32_t (&wd)[kEncWord
     *reinterpret_cast<float4*>(xs + p * kEncLd + 4 * w) =
         make_float4(code_x(word & 255u), code_x((word >> 8) & 255u), code_x((word >> 16) & 255u), code_x(word >> 24));
   }
-}
-
-// softplus (torch: beta 1, threshold 20) and its derivative from one exponential: three MUFU ops, absolute error
-// ~1e-7 (beyond the threshold log2(1 + e) rounds to 0 and the value is x itself, as in torch)
-__device__ __forceinline__ void softplus_parts(float x, float& sp, float& sg) {
-  const float e = ex2_approx(-fabsf(x) * kLog2e);
-  const float t = 1.0f + e;
-  const float r = rcp_approx(t);
-  sp = fmaf(lg2_approx(t), kLn2, fmaxf(x, 0.0f));
-  sg = x >= 0.0f ? r : e * r;                      // softplus'(x) = sigmoid(x)
 }
 
 // ------------------------------------------------------------------------------------------------ forward
@@ -372,6 +354,7 @@ int vipsy_norm_encoder_forward(const VipsyNormEncoderArgs* a, void* stream) {
     attr = true;
   }
   const EncParams P = enc_params(a);
+  if (enc_tc_supported(P.H, P.J) && !(a->flags & 1)) return enc_tc_fwd_launch(P, (cudaStream_t)stream);
   enc_norm_fwd_kernel<<<enc_grid_x(a->batch), kEncThreads, kEncFwdSmem, (cudaStream_t)stream>>>(P);
   VIPSY_CUDA_CHECK(cudaGetLastError());
   return VIPSY_OK;
@@ -403,9 +386,14 @@ int vipsy_norm_encoder_backward(const VipsyNormEncoderArgs* a, void* stream) {
   EncParams P = enc_params(a);
   P.partial = reinterpret_cast<float*>(a->workspace);
   const int gx = enc_grid_x(a->batch);
-  dim3 grid(gx, (J + kEncJC - 1) / kEncJC);
-  enc_norm_bwd_kernel<<<grid, kEncThreads, kEncBwdSmem, st>>>(P);
-  VIPSY_CUDA_CHECK(cudaGetLastError());
+  if (enc_tc_supported(H, J) && !(a->flags & 1)) {
+    rc = enc_tc_bwd_launch(P, gx, st);
+    if (rc != VIPSY_OK) return rc;
+  } else {
+    dim3 grid(gx, (J + kEncJC - 1) / kEncJC);
+    enc_norm_bwd_kernel<<<grid, kEncThreads, kEncBwdSmem, st>>>(P);
+    VIPSY_CUDA_CHECK(cudaGetLastError());
+  }
   FinalizeSegs segs{};
   segs.n = 6;
   segs.out[0] = a->d_w1;  segs.cols[0] = H * J;

@@ -38,6 +38,11 @@ __host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N, uint32_t a_m
        | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
+// same, bf16 operands (a_format = b_format = 1): fp32 exponent range, 3-term splits carry a full fp32 mantissa
+__host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N, uint32_t a_major, uint32_t b_major) {
+  return make_idesc_f16(M, N, a_major, b_major) | (1u << 7) | (1u << 10);
+}
+
 // D[tmem] (+)= A[smem] * B[smem]; one thread issues on behalf of the CTA.
 __device__ __forceinline__ void mma_f16_ss(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
                                            uint32_t accumulate) {

@@ -472,7 +472,7 @@ def cdm_score_elbo_grad(
 NORM_ENCODER_MAX_HIDDEN = 64
 
 
-def _norm_encoder_args(y, idx, enc):
+def _norm_encoder_args(y, idx, enc, tensor_cores=True):
     """enc: object with fc1 / fc21 / fc22 ``nn.Linear`` members (fc21, fc22 have one output)."""
     if not y.is_cuda or y.dtype != torch.uint8 or y.dim() != 2 or y.stride(1) != 1:
         raise ValueError("y must be a CUDA uint8 code matrix (see pack_responses)")
@@ -482,6 +482,7 @@ def _norm_encoder_args(y, idx, enc):
     a = N.NormEncoderArgs()
     a.n_rows, a.n_items, a.n_hidden = y.shape[0], J, H
     a.y, a.y_row_stride = _ptr(y), y.stride(0)
+    a.flags = 0 if tensor_cores else 1
     if idx is not None:
         if idx.dtype != torch.int64 or not idx.is_cuda:
             raise ValueError("idx must be a CUDA int64 tensor")
@@ -498,9 +499,9 @@ def _norm_encoder_args(y, idx, enc):
     return a, keep
 
 
-def norm_encoder_forward(y: torch.Tensor, enc, idx: Optional[torch.Tensor] = None):
+def norm_encoder_forward(y: torch.Tensor, enc, idx: Optional[torch.Tensor] = None, tensor_cores: bool = True):
     """mu [B], sigma [B], pre [B, H] of the amortised K = 1 guide, straight from the response codes."""
-    a, keep = _norm_encoder_args(y, idx, enc)
+    a, keep = _norm_encoder_args(y, idx, enc, tensor_cores)
     dev, B, H = y.device, int(a.batch), int(a.n_hidden)
     mu = torch.empty(B, dtype=torch.float32, device=dev)
     sigma = torch.empty(B, dtype=torch.float32, device=dev)
@@ -511,10 +512,11 @@ def norm_encoder_forward(y: torch.Tensor, enc, idx: Optional[torch.Tensor] = Non
 
 
 def norm_encoder_backward(y: torch.Tensor, enc, sigma: torch.Tensor, pre: torch.Tensor, d_mu: torch.Tensor,
-                          d_sigma: torch.Tensor, idx: Optional[torch.Tensor] = None, grad_scale: float = 1.0):
+                          d_sigma: torch.Tensor, idx: Optional[torch.Tensor] = None, grad_scale: float = 1.0,
+                          tensor_cores: bool = True):
     """Gradients of the six encoder tensors given d loss / d mu and d loss / d sigma; returns a dict keyed by the
     ``named_parameters`` names (fc1.weight, fc1.bias, fc21.weight, ...), shaped like the parameters."""
-    a, keep = _norm_encoder_args(y, idx, enc)
+    a, keep = _norm_encoder_args(y, idx, enc, tensor_cores)
     dev, B, H, J = y.device, int(a.batch), int(a.n_hidden), int(a.n_items)
     sigma, pre = _f32(sigma, "sigma", B), _f32(pre, "pre", B * H)
     d_mu, d_sigma = _f32(d_mu, "d_mu", B), _f32(d_sigma, "d_sigma", B)
