@@ -24,7 +24,7 @@ constexpr int kH = 64;                    // hidden slots = UMMA N
 constexpr int kThreads = 256;
 constexpr uint32_t kCS = 128;             // bytes between core matrices along the contiguous dimension
 constexpr uint32_t kTmemCols = 64;
-constexpr int kNQ = 8;                    // 16-byte chunks (8 items) per thread and tile: 2 threads per person
+constexpr int kBwdThreads = 512;          // backward: 4 threads per person (16 hidden units each)
 
 bool enc_tc_supported(int H, int J) { return H >= 1 && H <= kH && J >= 1 && J <= 127; }
 
@@ -47,15 +47,18 @@ __device__ __forceinline__ uint32_t codes_bf16x2(uint32_t word, int k) {
 
 // Codes of person (tile0 + p), items [8 j8, 8 j8 + 8) for this thread's chunks j8 = half + 2 q -> registers.
 // `ones_col` >= 0: that item position reads as code 1 for valid persons (the bias column of the backward product).
-__device__ __forceinline__ void tc_load_codes(uint32_t (&wd)[kNQ][2], const EncParams& P, int64_t tile0, int n_chunks,
+// NT threads share a person (16-byte chunks j8 = (threadIdx.x >> 7) + NT q).
+template <int NT>
+__device__ __forceinline__ void tc_load_codes(uint32_t (&wd)[16 / NT][2], const EncParams& P, int64_t tile0, int n_chunks,
                                               bool aligned) {
+  constexpr int kNQ = 16 / NT;
   const int p = threadIdx.x & (kTB - 1), half = threadIdx.x >> 7;
   const int64_t r = tile0 + p;
   const bool ok = r < P.B;
   const uint8_t* g = ok ? P.y + (P.idx ? __ldg(P.idx + r) : r) * P.ld : P.y;
 #pragma unroll
   for (int q = 0; q < kNQ; ++q) {
-    const int j8 = half + 2 * q;
+    const int j8 = half + NT * q;
 #pragma unroll
     for (int k = 0; k < 2; ++k) {
       const int j = 8 * j8 + 4 * k;
@@ -73,12 +76,14 @@ __device__ __forceinline__ void tc_load_codes(uint32_t (&wd)[kNQ][2], const EncP
     }
   }
 }
-__device__ __forceinline__ void tc_store_x(unsigned char* Xt, uint32_t RS, const uint32_t (&wd)[kNQ][2], int n_chunks,
+template <int NT>
+__device__ __forceinline__ void tc_store_x(unsigned char* Xt, uint32_t RS, const uint32_t (&wd)[16 / NT][2], int n_chunks,
                                            int ones_col, bool person_ok) {
+  constexpr int kNQ = 16 / NT;
   const int p = threadIdx.x & (kTB - 1), half = threadIdx.x >> 7;
 #pragma unroll
   for (int q = 0; q < kNQ; ++q) {
-    const int j8 = half + 2 * q;
+    const int j8 = half + NT * q;
     if (j8 < n_chunks) {
       uint4 v = make_uint4(codes_bf16x2(wd[q][0], 0), codes_bf16x2(wd[q][0], 1), codes_bf16x2(wd[q][1], 0),
                            codes_bf16x2(wd[q][1], 1));
@@ -93,7 +98,7 @@ __device__ __forceinline__ void tc_store_x(unsigned char* Xt, uint32_t RS, const
 }
 
 // ------------------------------------------------------------------------------------------------ forward
-__global__ void __launch_bounds__(kThreads) enc_tc_fwd_kernel(const EncParams P, const int JP) {
+__global__ void __launch_bounds__(kThreads, 2) enc_tc_fwd_kernel(const EncParams P, const int JP) {
   extern __shared__ __align__(1024) unsigned char smem[];
   __shared__ uint64_t bar;
   __shared__ uint32_t tmem_base_sm;
@@ -136,12 +141,12 @@ __global__ void __launch_bounds__(kThreads) enc_tc_fwd_kernel(const EncParams P,
   const float b21 = __ldg(P.b21), b22 = __ldg(P.b22);
   const int quad = warp & 3, half = warp >> 2;    // TMEM lane quadrant, column half of this warp
   const int64_t n_tiles = (P.B + kTB - 1) / kTB;
-  uint32_t wd[kNQ][2];
-  if ((int64_t)blockIdx.x < n_tiles) tc_load_codes(wd, P, (int64_t)blockIdx.x * kTB, n_chunks, aligned);
+  uint32_t wd[8][2];
+  if ((int64_t)blockIdx.x < n_tiles) tc_load_codes<2>(wd, P, (int64_t)blockIdx.x * kTB, n_chunks, aligned);
   uint32_t phase = 0;
   for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const int64_t tile0 = tile * kTB;
-    tc_store_x(Xt, RS, wd, n_chunks, -1, true);
+    tc_store_x<2>(Xt, RS, wd, n_chunks, -1, true);
     umma::fence_proxy_async();
     __syncthreads();
     if (t == 0) {
@@ -157,7 +162,7 @@ __global__ void __launch_bounds__(kThreads) enc_tc_fwd_kernel(const EncParams P,
       }
       umma::commit(&bar);
     }
-    if (tile + gridDim.x < n_tiles) tc_load_codes(wd, P, (tile + gridDim.x) * kTB, n_chunks, aligned);
+    if (tile + gridDim.x < n_tiles) tc_load_codes<2>(wd, P, (tile + gridDim.x) * kTB, n_chunks, aligned);
     umma::mbar_wait(&bar, phase);
     phase ^= 1u;
     umma::fence_after_sync();
@@ -204,7 +209,7 @@ __global__ void __launch_bounds__(kThreads) enc_tc_fwd_kernel(const EncParams P,
 }
 
 // ------------------------------------------------------------------------------------------------ backward
-__global__ void __launch_bounds__(kThreads) enc_tc_bwd_kernel(const EncParams P) {
+__global__ void __launch_bounds__(kBwdThreads) enc_tc_bwd_kernel(const EncParams P) {
   extern __shared__ __align__(1024) unsigned char smem[];
   __shared__ uint64_t bar;
   __shared__ uint32_t tmem_base_sm;
@@ -217,7 +222,7 @@ __global__ void __launch_bounds__(kThreads) enc_tc_bwd_kernel(const EncParams P)
   unsigned char* Xt = smem;
   unsigned char* Dt[3] = {Xt + 16 * RSx, Xt + 16 * RSx + 16 * RSd, Xt + 16 * RSx + 32 * RSd};
   const bool aligned = ((reinterpret_cast<uintptr_t>(P.y) | (uintptr_t)P.ld) & 3) == 0;
-  const int p = t & (kTB - 1), hhalf = t >> 7;    // this thread: person p, hidden chunks hc = hhalf + 2 q (8 units each)
+  const int p = t & (kTB - 1), hq = t >> 7;       // this thread: person p, hidden chunks hc = hq + 4 q (8 units each)
 
   if (t < 2 * kH) {
     const int h = t & 63;
@@ -236,14 +241,14 @@ __global__ void __launch_bounds__(kThreads) enc_tc_bwd_kernel(const EncParams P)
   const uint32_t sX = umma::smem_u32(Xt);
   const uint32_t sD[3] = {umma::smem_u32(Dt[0]), umma::smem_u32(Dt[1]), umma::smem_u32(Dt[2])};
 
-  float s21[4][8], s22[4][8];
+  float s21[2][8], s22[2][8];
 #pragma unroll
-  for (int q = 0; q < 4; ++q)
+  for (int q = 0; q < 2; ++q)
 #pragma unroll
     for (int i = 0; i < 8; ++i) s21[q][i] = s22[q][i] = 0.0f;
   float s_gm = 0.0f, s_gl = 0.0f;
   const int64_t n_tiles = (P.B + kTB - 1) / kTB;
-  uint32_t wd[kNQ][2];
+  uint32_t wd[4][2];
   float n_dm = 0.0f, n_ds = 0.0f, n_sg = 0.0f;
   auto load_heads = [&](int64_t tile0) {
     const int64_t r = tile0 + p;
@@ -251,7 +256,7 @@ __global__ void __launch_bounds__(kThreads) enc_tc_bwd_kernel(const EncParams P)
     if (r < P.B) { n_dm = __ldg(P.d_mu + r); n_ds = __ldg(P.d_sigma + r); n_sg = __ldg(P.sigma + r); }
   };
   if ((int64_t)blockIdx.x < n_tiles) {
-    tc_load_codes(wd, P, (int64_t)blockIdx.x * kTB, 16, aligned);
+    tc_load_codes<4>(wd, P, (int64_t)blockIdx.x * kTB, 16, aligned);
     load_heads((int64_t)blockIdx.x * kTB);
   }
   uint32_t phase = 0, acc = 0;
@@ -262,10 +267,10 @@ __global__ void __launch_bounds__(kThreads) enc_tc_bwd_kernel(const EncParams P)
     const bool ok = r < P.B;
     // this person's dpre row from `pre` (global loads first; they fly while the previous tile's MMAs finish)
     const float a = n_dm * P.gscale, b = n_ds * n_sg * P.gscale;       // exp chain rule; 0 beyond B
-    float pv[4][8];
+    float pv[2][8];
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const int h0 = 8 * (hhalf + 2 * q);
+    for (int q = 0; q < 2; ++q) {
+      const int h0 = 8 * (hq + 4 * q);
 #pragma unroll
       for (int i = 0; i < 8; ++i) pv[q][i] = 0.0f;
       if (ok) {
@@ -291,22 +296,22 @@ __global__ void __launch_bounds__(kThreads) enc_tc_bwd_kernel(const EncParams P)
       phase ^= 1u;
       pending = false;
     }
-    tc_store_x(Xt, RSx, wd, 16, P.J, ok);
-    if (hhalf == 0) { s_gm += a; s_gl += b; }
+    tc_store_x<4>(Xt, RSx, wd, 16, P.J, ok);
+    if (hq == 0) { s_gm += a; s_gl += b; }
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
+    for (int q = 0; q < 2; ++q) {
       uint32_t hi[8], mid[8], lo[8];
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         float sp, sg;
         softplus_parts(pv[q][i], sp, sg);
-        const int h = 8 * (hhalf + 2 * q) + i;
+        const int h = 8 * (hq + 4 * q) + i;
         const float dp = fmaf(a, wh[0][h], b * wh[1][h]) * sg;          // 0 beyond H (weights) and beyond B (a, b)
         s21[q][i] = fmaf(a, sp, s21[q][i]);
         s22[q][i] = fmaf(b, sp, s22[q][i]);
         split3(dp, hi[i], mid[i], lo[i]);
       }
-      const uint32_t o = (uint32_t)(p >> 3) * RSd + (uint32_t)(hhalf + 2 * q) * kCS + (uint32_t)(p & 7) * 16u;
+      const uint32_t o = (uint32_t)(p >> 3) * RSd + (uint32_t)(hq + 4 * q) * kCS + (uint32_t)(p & 7) * 16u;
       *reinterpret_cast<uint4*>(Dt[0] + o) =
           make_uint4(hi[0] | hi[1] << 16, hi[2] | hi[3] << 16, hi[4] | hi[5] << 16, hi[6] | hi[7] << 16);
       *reinterpret_cast<uint4*>(Dt[1] + o) =
@@ -330,7 +335,7 @@ __global__ void __launch_bounds__(kThreads) enc_tc_bwd_kernel(const EncParams P)
     }
     pending = true;
     if (tile + gridDim.x < n_tiles) {
-      tc_load_codes(wd, P, (tile + gridDim.x) * kTB, 16, aligned);
+      tc_load_codes<4>(wd, P, (tile + gridDim.x) * kTB, 16, aligned);
       load_heads((tile + gridDim.x) * kTB);
     }
   }
@@ -340,7 +345,7 @@ __global__ void __launch_bounds__(kThreads) enc_tc_bwd_kernel(const EncParams P)
   // [d_w1 (H x J) | d_b1 (H) | d_w21 (H) | d_b21 | d_w22 (H) | d_b22]; slot J is the ones column = d_b1
   float* row = P.partial + (size_t)blockIdx.x * P.cols;
   float* tail = row + (size_t)P.H * P.J;
-  {
+  if (warp < 8) {
     const int quad = warp & 3, half = warp >> 2;
     float v[32];
     umma::tmem_ld32(tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)(half * 32), v);
@@ -354,19 +359,19 @@ __global__ void __launch_bounds__(kThreads) enc_tc_bwd_kernel(const EncParams P)
       }
     }
   }
-  // d fc21.weight / d fc22.weight: sum over the persons (threads of one half) of the register partials
+  // d fc21.weight / d fc22.weight: sum over the persons (the four warps of one quarter) of the register partials
 #pragma unroll
-  for (int q = 0; q < 4; ++q)
+  for (int q = 0; q < 2; ++q)
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       const float x = warp_sum(s21[q][i]), y = warp_sum(s22[q][i]);
       if (lane == 0) {
-        red[0][warp & 3][8 * (hhalf + 2 * q) + i] = x;
-        red[1][warp & 3][8 * (hhalf + 2 * q) + i] = y;
+        red[0][warp & 3][8 * (hq + 4 * q) + i] = x;
+        red[1][warp & 3][8 * (hq + 4 * q) + i] = y;
       }
     }
   s_gm = warp_sum(s_gm); s_gl = warp_sum(s_gl);
-  if (lane == 0 && hhalf == 0) { gm[warp] = s_gm; gl[warp] = s_gl; }
+  if (lane == 0 && hq == 0) { gm[warp] = s_gm; gl[warp] = s_gl; }
   umma::fence_before_sync();
   __syncthreads();
   if (t < P.H) {
@@ -392,7 +397,7 @@ int enc_tc_fwd_launch(const EncParams& P, cudaStream_t st) {
     attr = smem;
   }
   const int64_t tiles = (P.B + kTB - 1) / kTB;
-  const int64_t cap = (smem * 3 <= 220 * 1024 ? 3 : 2) * (int64_t)num_sms();
+  const int64_t cap = 2 * (int64_t)num_sms();
   enc_tc_fwd_kernel<<<(int)(tiles < cap ? tiles : cap), kThreads, smem, st>>>(P, JP);
   VIPSY_CUDA_CHECK(cudaGetLastError());
   return VIPSY_OK;
@@ -405,7 +410,7 @@ int enc_tc_bwd_launch(const EncParams& P, int grid_x, cudaStream_t st) {
                                           (int)kTcBwdSmem));
     attr = true;
   }
-  enc_tc_bwd_kernel<<<grid_x, kThreads, kTcBwdSmem, st>>>(P);
+  enc_tc_bwd_kernel<<<grid_x, kBwdThreads, kTcBwdSmem, st>>>(P);
   VIPSY_CUDA_CHECK(cudaGetLastError());
   return VIPSY_OK;
 }
