@@ -354,7 +354,8 @@ int vipsy_norm_encoder_forward(const VipsyNormEncoderArgs* a, void* stream) {
     attr = true;
   }
   const EncParams P = enc_params(a);
-  if (enc_tc_supported(P.H, P.J) && !(a->flags & 1)) return enc_tc_fwd_launch(P, (cudaStream_t)stream);
+  if (enc_tc_supported(P.H, P.J) && !(a->flags & 1) && (reinterpret_cast<uintptr_t>(a->pre) & 15) == 0)
+    return enc_tc_fwd_launch(P, (cudaStream_t)stream);
   enc_norm_fwd_kernel<<<enc_grid_x(a->batch), kEncThreads, kEncFwdSmem, (cudaStream_t)stream>>>(P);
   VIPSY_CUDA_CHECK(cudaGetLastError());
   return VIPSY_OK;
@@ -386,7 +387,7 @@ int vipsy_norm_encoder_backward(const VipsyNormEncoderArgs* a, void* stream) {
   EncParams P = enc_params(a);
   P.partial = reinterpret_cast<float*>(a->workspace);
   const int gx = enc_grid_x(a->batch);
-  if (enc_tc_supported(H, J) && !(a->flags & 1)) {
+  if (enc_tc_supported(H, J) && !(a->flags & 1) && (reinterpret_cast<uintptr_t>(a->pre) & 15) == 0) {
     rc = enc_tc_bwd_launch(P, gx, st);
     if (rc != VIPSY_OK) return rc;
   } else {

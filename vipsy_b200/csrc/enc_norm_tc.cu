@@ -5,7 +5,7 @@
 // exponent range), so three MMAs per 16-deep k-step reproduce the fp32 product and the fp32 accumulator in TMEM
 // adds them -- same numerics class as the SIMT kernels (enc_norm.cu), a tenth of the issue slots.
 //
-//   forward : pre[128 persons x 64] = X[128 x JP] . W1^T        A = code tile (K-major), B = W1 tiles (K-major),
+//   forward : pre[128 persons x 64] = [X | 1][128 x JP] . [W1 | b1]^T   A = code tile (K-major), B = W1 tiles (K-major),
 //             epilogue TMEM -> registers: bias, store pre, softplus, the two 64 -> 1 heads
 //   backward: D[128 x 64] += X^T[JP128 x 128 persons] . dpre    A = code tile (MN-major, + a ones column -> d b1),
 //             B = dpre tiles (MN-major); D stays in TMEM over every tile of the persistent CTA and is read once
@@ -24,6 +24,7 @@ constexpr int kH = 64;                    // hidden slots = UMMA N
 constexpr int kThreads = 256;
 constexpr uint32_t kCS = 128;             // bytes between core matrices along the contiguous dimension
 constexpr uint32_t kTmemCols = 64;
+constexpr int kPitch = kH + 4;               // fp32 [person][hidden] staging tiles: conflict-free rows
 constexpr int kBwdThreads = 512;          // backward: 4 threads per person (16 hidden units each)
 
 bool enc_tc_supported(int H, int J) { return H >= 1 && H <= kH && J >= 1 && J <= 127; }
@@ -39,60 +40,85 @@ __device__ __forceinline__ void split3(float v, uint32_t& hi, uint32_t& mid, uin
   const float r2 = r1 - __bfloat162float(m);
   hi = __bfloat16_as_ushort(h); mid = __bfloat16_as_ushort(m); lo = bf16_bits(r2);
 }
-// two response codes (0 / 1 / 255) -> two bf16 (0, 1, -1) in one word
-__device__ __forceinline__ uint32_t code_bf16(uint32_t c) { return (c & 1u) * 0x3f80u | (c & 0x80u) << 8; }
-__device__ __forceinline__ uint32_t codes_bf16x2(uint32_t word, int k) {
-  return code_bf16((word >> (16 * k)) & 255u) | code_bf16((word >> (16 * k + 8)) & 255u) << 16;
+// Same split by truncation, two values at a time, integer pipe only: the upper halves of v, v - hi, v - hi - mid
+// are the three bf16 terms (8 + 8 + 8 mantissa bits, every residual exact); packed as (v0 | v1 << 16) per term.
+__device__ __forceinline__ void split3_pair(float v0, float v1, uint32_t& hi, uint32_t& mid, uint32_t& lo) {
+  const uint32_t h0 = __float_as_uint(v0) & 0xffff0000u, h1 = __float_as_uint(v1) & 0xffff0000u;
+  const float r0 = v0 - __uint_as_float(h0), r1 = v1 - __uint_as_float(h1);
+  const uint32_t m0 = __float_as_uint(r0) & 0xffff0000u, m1 = __float_as_uint(r1) & 0xffff0000u;
+  const float q0 = r0 - __uint_as_float(m0), q1 = r1 - __uint_as_float(m1);
+  hi = __byte_perm(h0, h1, 0x7632);
+  mid = __byte_perm(m0, m1, 0x7632);
+  lo = __byte_perm(__float_as_uint(q0), __float_as_uint(q1), 0x7632);
 }
-
-// Codes of person (tile0 + p), items [8 j8, 8 j8 + 8) for this thread's chunks j8 = half + 2 q -> registers.
-// `ones_col` >= 0: that item position reads as code 1 for valid persons (the bias column of the backward product).
-// NT threads share a person (16-byte chunks j8 = (threadIdx.x >> 7) + NT q).
-template <int NT>
-__device__ __forceinline__ void tc_load_codes(uint32_t (&wd)[16 / NT][2], const EncParams& P, int64_t tile0, int n_chunks,
+// four response codes (0 / 1 / 255) -> four bf16 (0, 1, -1) by byte lookup: code & 3 in {0, 1, 3} selects the low
+// byte {00, 80, 80} and the high byte {00, 3f, bf} of the bf16 through one PRMT per pair of codes
+__device__ __forceinline__ void codes_bf16x4(uint32_t word, uint32_t& lo_pair, uint32_t& hi_pair) {
+  const uint32_t m = word & 0x03030303u;
+  const uint32_t s0 = (m & 0xffffu) * 0x11u + 0x4040u, s1 = (m >> 16) * 0x11u + 0x4040u;
+  lo_pair = __byte_perm(0x80008000u, 0xbf003f00u, s0);
+  hi_pair = __byte_perm(0x80008000u, 0xbf003f00u, s1);
+}
+// Response codes of a 128-person tile -> registers -> bf16 operand tile.  A warp instruction covers 8 persons (one
+// row block of core matrices) x 4 consecutive 4-byte words, so a request touches 8 short segments instead of 32
+// rows; warp w owns row blocks w, w + NW, ...; per row block 8 iterations cover 32 words (128 items).
+// `ones_col` >= 0: that item slot reads as 1 for persons below b_ones (bias column of either product).
+template <int NW>
+__device__ __forceinline__ void tc_load_codes(uint32_t (&wd)[16 / NW][8], const EncParams& P, int64_t tile0, int n_words,
                                               bool aligned) {
-  constexpr int kNQ = 16 / NT;
-  const int p = threadIdx.x & (kTB - 1), half = threadIdx.x >> 7;
-  const int64_t r = tile0 + p;
-  const bool ok = r < P.B;
-  const uint8_t* g = ok ? P.y + (P.idx ? __ldg(P.idx + r) : r) * P.ld : P.y;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, pp = lane & 7, w0 = lane >> 3;
+  const int jt = P.J & ~3;                          // start of the one partial word of a row (J % 4 != 0)
 #pragma unroll
-  for (int q = 0; q < kNQ; ++q) {
-    const int j8 = half + NT * q;
+  for (int rbi = 0; rbi < 16 / NW; ++rbi) {
+    const int64_t r = tile0 + (warp + NW * rbi) * 8 + pp;
+    const bool ok = r < P.B;
+    const uint8_t* g = ok ? P.y + (P.idx ? __ldg(P.idx + r) : r) * P.ld : P.y;
+    if (aligned) {
+      uint32_t tail = 0;
+      if ((P.J & 3) && ok && ((jt >> 2) & 3) == w0 && (jt >> 2) < n_words)
+        for (int b = 0; b < (P.J & 3); ++b) tail |= (uint32_t)__ldg(g + jt + b) << (8 * b);
 #pragma unroll
-    for (int k = 0; k < 2; ++k) {
-      const int j = 8 * j8 + 4 * k;
-      uint32_t word = 0;
-      if (ok && j8 < n_chunks && j < P.J) {
-        if (aligned && j + 3 < P.J) {
-          word = __ldg(reinterpret_cast<const uint32_t*>(g + j));
-        } else {
+      for (int it = 0; it < 8; ++it) {
+        const int word = w0 + 4 * it, j = 4 * word;
+        wd[rbi][it] = (ok && word < n_words && j + 3 < P.J) ? __ldg(reinterpret_cast<const uint32_t*>(g + j))
+                                                            : (j == jt ? tail : 0u);
+      }
+    } else {
+#pragma unroll
+      for (int it = 0; it < 8; ++it) {
+        const int word = w0 + 4 * it, j = 4 * word;
+        uint32_t v = 0;
+        if (ok && word < n_words && j < P.J) {
 #pragma unroll
           for (int b = 0; b < 4; ++b)
-            if (j + b < P.J) word |= (uint32_t)__ldg(g + j + b) << (8 * b);
+            if (j + b < P.J) v |= (uint32_t)__ldg(g + j + b) << (8 * b);
         }
+        wd[rbi][it] = v;
       }
-      wd[q][k] = word;
     }
   }
 }
-template <int NT>
-__device__ __forceinline__ void tc_store_x(unsigned char* Xt, uint32_t RS, const uint32_t (&wd)[16 / NT][2], int n_chunks,
-                                           int ones_col, bool person_ok) {
-  constexpr int kNQ = 16 / NT;
-  const int p = threadIdx.x & (kTB - 1), half = threadIdx.x >> 7;
+template <int NW>
+__device__ __forceinline__ void tc_store_x(unsigned char* Xt, uint32_t RS, const uint32_t (&wd)[16 / NW][8], int n_words,
+                                           int ones_col, int64_t tile0, int64_t b_ones) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, pp = lane & 7, w0 = lane >> 3;
 #pragma unroll
-  for (int q = 0; q < kNQ; ++q) {
-    const int j8 = half + NT * q;
-    if (j8 < n_chunks) {
-      uint4 v = make_uint4(codes_bf16x2(wd[q][0], 0), codes_bf16x2(wd[q][0], 1), codes_bf16x2(wd[q][1], 0),
-                           codes_bf16x2(wd[q][1], 1));
-      if (ones_col >= 0 && (ones_col >> 3) == j8 && person_ok) {
-        const uint32_t one = 0x3f80u << (16 * (ones_col & 1));
-        const int wsel = (ones_col & 7) >> 1;
-        if (wsel == 0) v.x |= one; else if (wsel == 1) v.y |= one; else if (wsel == 2) v.z |= one; else v.w |= one;
+  for (int rbi = 0; rbi < 16 / NW; ++rbi) {
+    const int rb = warp + NW * rbi;
+    const bool one_ok = tile0 + rb * 8 + pp < b_ones;
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      const int word = w0 + 4 * it;
+      if (word < n_words) {
+        uint2 v;
+        codes_bf16x4(wd[rbi][it], v.x, v.y);
+        if (ones_col >= 0 && (ones_col >> 2) == word && one_ok) {
+          const uint32_t one = 0x3f80u << (16 * (ones_col & 1));
+          if (ones_col & 2) v.y |= one; else v.x |= one;
+        }
+        *reinterpret_cast<uint2*>(Xt + (uint32_t)rb * RS + (uint32_t)(word >> 1) * kCS + (uint32_t)pp * 16u +
+                                  (uint32_t)(word & 1) * 8u) = v;
       }
-      *reinterpret_cast<uint4*>(Xt + (uint32_t)(p >> 3) * RS + (uint32_t)j8 * kCS + (uint32_t)(p & 7) * 16u) = v;
     }
   }
 }
@@ -109,11 +135,13 @@ __global__ void __launch_bounds__(kThreads, 2) enc_tc_fwd_kernel(const EncParams
   const uint32_t RS = (uint32_t)n_chunks * kCS;   // same pitch for the code tile (16 row blocks) and W tiles (8)
   unsigned char* Xt = smem;
   unsigned char* Wt[3] = {Xt + 16 * RS, Xt + 24 * RS, Xt + 32 * RS};
+  float* ps = reinterpret_cast<float*>(Xt + 40 * RS);     // [128][kPitch] pre tile on its way to global memory
   const bool aligned = ((reinterpret_cast<uintptr_t>(P.y) | (uintptr_t)P.ld) & 3) == 0;
 
   for (int e = t; e < kH * JP; e += kThreads) {   // fc1.weight -> three bf16 operand tiles, once per CTA
     const int h = e / JP, j = e - h * JP;
-    const float v = (h < P.H && j < P.J) ? __ldg(P.w1 + (size_t)h * P.J + j) : 0.0f;
+    float v = 0.0f;                               // item slot J multiplies the ones column: the bias row
+    if (h < P.H) v = j < P.J ? __ldg(P.w1 + (size_t)h * P.J + j) : (j == P.J ? __ldg(P.b1 + h) : 0.0f);
     uint32_t a, b, c;
     split3(v, a, b, c);
     const uint32_t o = umma::tile_off(h, j, RS, kCS);
@@ -141,12 +169,12 @@ __global__ void __launch_bounds__(kThreads, 2) enc_tc_fwd_kernel(const EncParams
   const float b21 = __ldg(P.b21), b22 = __ldg(P.b22);
   const int quad = warp & 3, half = warp >> 2;    // TMEM lane quadrant, column half of this warp
   const int64_t n_tiles = (P.B + kTB - 1) / kTB;
-  uint32_t wd[8][2];
-  if ((int64_t)blockIdx.x < n_tiles) tc_load_codes<2>(wd, P, (int64_t)blockIdx.x * kTB, n_chunks, aligned);
+  uint32_t wd[2][8];
+  if ((int64_t)blockIdx.x < n_tiles) tc_load_codes<8>(wd, P, (int64_t)blockIdx.x * kTB, 2 * n_chunks, aligned);
   uint32_t phase = 0;
   for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const int64_t tile0 = tile * kTB;
-    tc_store_x<2>(Xt, RS, wd, n_chunks, -1, true);
+    tc_store_x<8>(Xt, RS, wd, 2 * n_chunks, P.J, tile0, INT64_MAX);
     umma::fence_proxy_async();
     __syncthreads();
     if (t == 0) {
@@ -162,7 +190,7 @@ __global__ void __launch_bounds__(kThreads, 2) enc_tc_fwd_kernel(const EncParams
       }
       umma::commit(&bar);
     }
-    if (tile + gridDim.x < n_tiles) tc_load_codes<2>(wd, P, (tile + gridDim.x) * kTB, n_chunks, aligned);
+    if (tile + gridDim.x < n_tiles) tc_load_codes<8>(wd, P, (tile + gridDim.x) * kTB, 2 * n_chunks, aligned);
     umma::mbar_wait(&bar, phase);
     phase ^= 1u;
     umma::fence_after_sync();
@@ -170,29 +198,18 @@ __global__ void __launch_bounds__(kThreads, 2) enc_tc_fwd_kernel(const EncParams
       float v[32];
       umma::tmem_ld32(tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)(half * 32), v);
       const int p = quad * 32 + lane;
-      const int64_t r = tile0 + p;
       const int h0 = half * 32;
       float m = 0.0f, l = 0.0f;
 #pragma unroll
       for (int c = 0; c < 32; ++c) {
-        v[c] += hv[h0 + c];
         float sp, sg;
         softplus_parts(v[c], sp, sg);
         m = fmaf(sp, hv[kH + h0 + c], m);           // weights are 0 beyond H
         l = fmaf(sp, hv[2 * kH + h0 + c], l);
       }
-      if (r < P.B) {
-        float* dst = P.pre + (size_t)r * P.H + h0;
-        if ((P.H & 3) == 0) {
 #pragma unroll
-          for (int c = 0; c < 32; c += 4)
-            if (h0 + c < P.H) *reinterpret_cast<float4*>(dst + c) = make_float4(v[c], v[c + 1], v[c + 2], v[c + 3]);
-        } else {
-#pragma unroll
-          for (int c = 0; c < 32; ++c)
-            if (h0 + c < P.H) dst[c] = v[c];
-        }
-      }
+      for (int c = 0; c < 32; c += 4)
+        *reinterpret_cast<float4*>(ps + p * kPitch + h0 + c) = make_float4(v[c], v[c + 1], v[c + 2], v[c + 3]);
       part[half][p] = make_float2(m, l);
     }
     umma::fence_before_sync();
@@ -201,6 +218,21 @@ __global__ void __launch_bounds__(kThreads, 2) enc_tc_fwd_kernel(const EncParams
       const float2 a = part[0][t], b = part[1][t];
       P.mu[tile0 + t] = (a.x + b.x) + b21;
       P.sigma[tile0 + t] = expf((a.y + b.y) + b22);
+    }
+    // pre tile -> global memory, whole rows per warp request (the tile is one contiguous block of `pre`)
+    if ((P.H & 3) == 0) {
+      const int h4 = P.H >> 2;
+      for (int e = t; e < kTB * h4; e += kThreads) {
+        const int row = e / h4, c4 = e - row * h4;
+        if (tile0 + row < P.B)
+          *reinterpret_cast<float4*>(P.pre + (size_t)(tile0 + row) * P.H + 4 * c4) =
+              *reinterpret_cast<const float4*>(ps + row * kPitch + 4 * c4);
+      }
+    } else {
+      for (int e = t; e < kTB * P.H; e += kThreads) {
+        const int row = e / P.H, c = e - row * P.H;
+        if (tile0 + row < P.B) P.pre[(size_t)(tile0 + row) * P.H + c] = ps[row * kPitch + c];
+      }
     }
   }
   umma::fence_before_sync();
@@ -221,6 +253,7 @@ __global__ void __launch_bounds__(kBwdThreads) enc_tc_bwd_kernel(const EncParams
   constexpr uint32_t RSd = (kH / 8) * kCS;        // dpre tiles: 128 persons x 64 hidden
   unsigned char* Xt = smem;
   unsigned char* Dt[3] = {Xt + 16 * RSx, Xt + 16 * RSx + 16 * RSd, Xt + 16 * RSx + 32 * RSd};
+  float* pb = reinterpret_cast<float*>(Xt + 16 * RSx + 48 * RSd);      // [128][kPitch] `pre` rows of the tile
   const bool aligned = ((reinterpret_cast<uintptr_t>(P.y) | (uintptr_t)P.ld) & 3) == 0;
   const int p = t & (kTB - 1), hq = t >> 7;       // this thread: person p, hidden chunks hc = hq + 4 q (8 units each)
 
@@ -228,6 +261,7 @@ __global__ void __launch_bounds__(kBwdThreads) enc_tc_bwd_kernel(const EncParams
     const int h = t & 63;
     wh[t >> 6][h] = h < P.H ? __ldg((t >> 6 ? P.w22 : P.w21) + h) : 0.0f;
   }
+  for (int e = t; e < kTB * kPitch; e += kBwdThreads) pb[e] = 0.0f;     // columns beyond H stay 0
   if (warp == 0) umma::tmem_alloc(&tmem_base_sm, kTmemCols);
   if (t == 0) {
     umma::mbar_init(&bar, 1);
@@ -248,76 +282,83 @@ __global__ void __launch_bounds__(kBwdThreads) enc_tc_bwd_kernel(const EncParams
     for (int i = 0; i < 8; ++i) s21[q][i] = s22[q][i] = 0.0f;
   float s_gm = 0.0f, s_gl = 0.0f;
   const int64_t n_tiles = (P.B + kTB - 1) / kTB;
-  uint32_t wd[4][2];
+  uint32_t wd[1][8];
   float n_dm = 0.0f, n_ds = 0.0f, n_sg = 0.0f;
   auto load_heads = [&](int64_t tile0) {
     const int64_t r = tile0 + p;
     n_dm = n_ds = n_sg = 0.0f;
     if (r < P.B) { n_dm = __ldg(P.d_mu + r); n_ds = __ldg(P.d_sigma + r); n_sg = __ldg(P.sigma + r); }
   };
+  // `pre` rows of a tile -> pb: the tile is one contiguous block of the [B x H] matrix, copied by 16-byte
+  // asynchronous copies (whole rows per warp request); rows beyond B read as 0
+  auto fetch_pre = [&](int64_t tile0) {
+    if ((P.H & 3) == 0) {
+      const int h4 = P.H >> 2;
+      for (int e = t; e < kTB * h4; e += kBwdThreads) {
+        const int row = e / h4, c4 = e - row * h4;
+        float* dst = pb + row * kPitch + 4 * c4;
+        if (tile0 + row < P.B) {
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(umma::smem_u32(dst)),
+                       "l"(P.pre + (size_t)(tile0 + row) * P.H + 4 * c4)
+                       : "memory");
+        } else {
+          *reinterpret_cast<float4*>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      }
+    } else {
+      for (int e = t; e < kTB * P.H; e += kBwdThreads) {
+        const int row = e / P.H, c = e - row * P.H;
+        pb[row * kPitch + c] = tile0 + row < P.B ? __ldg(P.pre + (size_t)(tile0 + row) * P.H + c) : 0.0f;
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
   if ((int64_t)blockIdx.x < n_tiles) {
-    tc_load_codes<4>(wd, P, (int64_t)blockIdx.x * kTB, 16, aligned);
+    tc_load_codes<16>(wd, P, (int64_t)blockIdx.x * kTB, 32, aligned);
+    fetch_pre((int64_t)blockIdx.x * kTB);
     load_heads((int64_t)blockIdx.x * kTB);
   }
   uint32_t phase = 0, acc = 0;
   bool pending = false;
   for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const int64_t tile0 = tile * kTB;
-    const int64_t r = tile0 + p;
-    const bool ok = r < P.B;
-    // this person's dpre row from `pre` (global loads first; they fly while the previous tile's MMAs finish)
     const float a = n_dm * P.gscale, b = n_ds * n_sg * P.gscale;       // exp chain rule; 0 beyond B
-    float pv[2][8];
-#pragma unroll
-    for (int q = 0; q < 2; ++q) {
-      const int h0 = 8 * (hq + 4 * q);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) pv[q][i] = 0.0f;
-      if (ok) {
-        const float* src = P.pre + (size_t)r * P.H + h0;
-        if ((P.H & 3) == 0) {
-          if (h0 < P.H) {
-            const float4 u = __ldg(reinterpret_cast<const float4*>(src));
-            pv[q][0] = u.x; pv[q][1] = u.y; pv[q][2] = u.z; pv[q][3] = u.w;
-          }
-          if (h0 + 4 < P.H) {
-            const float4 u = __ldg(reinterpret_cast<const float4*>(src + 4));
-            pv[q][4] = u.x; pv[q][5] = u.y; pv[q][6] = u.z; pv[q][7] = u.w;
-          }
-        } else {
-#pragma unroll
-          for (int i = 0; i < 8; ++i)
-            if (h0 + i < P.H) pv[q][i] = __ldg(src + i);
-        }
-      }
-    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
     if (pending) {                                  // previous tile's MMAs have read the operand tiles
       umma::mbar_wait(&bar, phase);
       phase ^= 1u;
       pending = false;
     }
-    tc_store_x<4>(Xt, RSx, wd, 16, P.J, ok);
+    __syncthreads();                                // every thread's share of `pre` has landed in pb
+    float pv[2][8];
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      const float* src = pb + p * kPitch + 8 * (hq + 4 * q);
+      const float4 u0 = *reinterpret_cast<const float4*>(src), u1 = *reinterpret_cast<const float4*>(src + 4);
+      pv[q][0] = u0.x; pv[q][1] = u0.y; pv[q][2] = u0.z; pv[q][3] = u0.w;
+      pv[q][4] = u1.x; pv[q][5] = u1.y; pv[q][6] = u1.z; pv[q][7] = u1.w;
+    }
+    tc_store_x<16>(Xt, RSx, wd, 32, P.J, tile0, P.B);
     if (hq == 0) { s_gm += a; s_gl += b; }
 #pragma unroll
     for (int q = 0; q < 2; ++q) {
-      uint32_t hi[8], mid[8], lo[8];
+      uint32_t hi[4], mid[4], lo[4];
+      float dp[8];
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         float sp, sg;
         softplus_parts(pv[q][i], sp, sg);
         const int h = 8 * (hq + 4 * q) + i;
-        const float dp = fmaf(a, wh[0][h], b * wh[1][h]) * sg;          // 0 beyond H (weights) and beyond B (a, b)
+        dp[i] = fmaf(a, wh[0][h], b * wh[1][h]) * sg;                   // 0 beyond H (weights) and beyond B (a, b)
         s21[q][i] = fmaf(a, sp, s21[q][i]);
         s22[q][i] = fmaf(b, sp, s22[q][i]);
-        split3(dp, hi[i], mid[i], lo[i]);
       }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) split3_pair(dp[2 * i], dp[2 * i + 1], hi[i], mid[i], lo[i]);
       const uint32_t o = (uint32_t)(p >> 3) * RSd + (uint32_t)(hq + 4 * q) * kCS + (uint32_t)(p & 7) * 16u;
-      *reinterpret_cast<uint4*>(Dt[0] + o) =
-          make_uint4(hi[0] | hi[1] << 16, hi[2] | hi[3] << 16, hi[4] | hi[5] << 16, hi[6] | hi[7] << 16);
-      *reinterpret_cast<uint4*>(Dt[1] + o) =
-          make_uint4(mid[0] | mid[1] << 16, mid[2] | mid[3] << 16, mid[4] | mid[5] << 16, mid[6] | mid[7] << 16);
-      *reinterpret_cast<uint4*>(Dt[2] + o) =
-          make_uint4(lo[0] | lo[1] << 16, lo[2] | lo[3] << 16, lo[4] | lo[5] << 16, lo[6] | lo[7] << 16);
+      *reinterpret_cast<uint4*>(Dt[0] + o) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+      *reinterpret_cast<uint4*>(Dt[1] + o) = make_uint4(mid[0], mid[1], mid[2], mid[3]);
+      *reinterpret_cast<uint4*>(Dt[2] + o) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
     }
     umma::fence_proxy_async();
     __syncthreads();
@@ -335,7 +376,8 @@ __global__ void __launch_bounds__(kBwdThreads) enc_tc_bwd_kernel(const EncParams
     }
     pending = true;
     if (tile + gridDim.x < n_tiles) {
-      tc_load_codes<4>(wd, P, (tile + gridDim.x) * kTB, 16, aligned);
+      fetch_pre((tile + gridDim.x) * kTB);          // pb was consumed before the barrier above
+      tc_load_codes<16>(wd, P, (tile + gridDim.x) * kTB, 32, aligned);
       load_heads((tile + gridDim.x) * kTB);
     }
   }
@@ -385,11 +427,11 @@ __global__ void __launch_bounds__(kBwdThreads) enc_tc_bwd_kernel(const EncParams
   if (warp == 0) umma::tmem_dealloc(tmem, kTmemCols);
 }
 
-static size_t tc_fwd_smem(int JP) { return (size_t)40 * (JP / 8) * kCS + 1024; }
-constexpr size_t kTcBwdSmem = 16 * (kTB / 8) * kCS + 3 * 16 * (kH / 8) * kCS + 1024;
+static size_t tc_fwd_smem(int JP) { return (size_t)40 * (JP / 8) * kCS + (size_t)kTB * kPitch * 4 + 1024; }
+constexpr size_t kTcBwdSmem = 16 * (kTB / 8) * kCS + 3 * 16 * (kH / 8) * kCS + (size_t)kTB * kPitch * 4 + 1024;
 
 int enc_tc_fwd_launch(const EncParams& P, cudaStream_t st) {
-  const int JP = (P.J + 15) / 16 * 16;
+  const int JP = (P.J + 1 + 15) / 16 * 16;        // + the ones column that carries fc1.bias
   static size_t attr = 0;
   const size_t smem = tc_fwd_smem(JP);
   if (smem > attr) {
