@@ -153,6 +153,29 @@ def other_configs(dev, peaks, flush, iters=5):
     vb.clear_param_store()
     out["c1_full_svi_iteration_us"] = it_us
 
+    # c2 as BASELINE names it (VaeIRT, 4PL, S = 32, full batch): the WHOLE iteration = NormEncoder forward +
+    # ELBO kernel + encoder backward + Adam, CUDA-graph replay; encoder as the tcgen05 kernels vs torch autograd
+    yv = (torch.rand(1_000_000, 100, device=dev, generator=torch.Generator(device=dev).manual_seed(4)) < 0.6).float()
+    it_ms = {}
+    for fused in (True, False):
+        vb.clear_param_store()
+        torch.manual_seed(0)
+        m = vb.VaeIRT(data=yv, model="irt_4pl", device=dev)
+        m.fused_encoder = fused
+        svi = infer.SVI(m.model, m.guide, optim=vb.Adam({"lr": 1e-3}), loss=vb.Trace_ELBO(num_particles=32), cuda_graph=True)
+        for _ in range(4):
+            svi.step(m.data)
+        torch.cuda.synchronize()
+        t0 = _time.perf_counter()
+        for _ in range(20):
+            svi.step_async(m.data)
+        torch.cuda.synchronize()
+        it_ms["encoder_kernels" if fused else "encoder_torch_autograd"] = (_time.perf_counter() - t0) / 20 * 1e3
+        del svi, m
+    del yv
+    vb.clear_param_store()
+    out["c2_vaeirt_4pl_1Mx100_S32_full_svi_iteration_ms"] = it_ms
+
     # c4: 2PL, 2M x 200, 90 % missing, S = 1, observed-cell CSR layout (built once, outside the timing)
     w = workloads.uni_irt(2_000_000, 200, "irt_2pl", missing=0.9, seed=12, device=dev)
     obs = ops.observed_csr(w["y"])

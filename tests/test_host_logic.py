@@ -162,3 +162,23 @@ def test_two_bit_transport_packer_host():
     bad = torch.full((2, 8), 7, dtype=torch.uint8)
     with pytest.raises(Exception):
         ops.pack_responses_2bit_host(bad, pin=False)
+
+
+def test_oracle_norm_encoder_is_the_reference_module():
+    """oracle.norm_encoder restates NormEncoder.forward + the guide's NaN -> -1 rule (vi.py:417-435, 679-682):
+    same numbers as the nn.Module the estimator classes hold, and differentiable in the weights."""
+    import torch
+    from oracle import vipsy_oracle as o
+    from vipsy_b200.models import NormEncoder
+    torch.manual_seed(0)
+    enc = NormEncoder(9, 1, 6).double()
+    y = (torch.rand(20, 9) < 0.5).double()
+    y[torch.rand(20, 9) < 0.2] = float("nan")
+    x = torch.where(torch.isnan(y), torch.full_like(y, -1.0), y)
+    loc, sc = enc(x)
+    p = dict(enc.named_parameters())
+    loc2, sc2 = o.norm_encoder(y, p["fc1.weight"], p["fc1.bias"], p["fc21.weight"], p["fc21.bias"], p["fc22.weight"],
+                               p["fc22.bias"])
+    assert torch.allclose(loc, loc2, atol=1e-12) and torch.allclose(sc, sc2, atol=1e-12)
+    (loc2.sum() + sc2.sum()).backward()
+    assert p["fc1.weight"].grad is not None and float(p["fc1.weight"].grad.abs().sum()) > 0

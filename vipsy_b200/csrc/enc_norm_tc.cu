@@ -78,10 +78,11 @@ __device__ __forceinline__ void tc_load_codes(uint32_t (&wd)[16 / NW][8], const 
       if ((P.J & 3) && ok && ((jt >> 2) & 3) == w0 && (jt >> 2) < n_words)
         for (int b = 0; b < (P.J & 3); ++b) tail |= (uint32_t)__ldg(g + jt + b) << (8 * b);
 #pragma unroll
-      for (int it = 0; it < 8; ++it) {
-        const int word = w0 + 4 * it, j = 4 * word;
-        wd[rbi][it] = (ok && word < n_words && j + 3 < P.J) ? __ldg(reinterpret_cast<const uint32_t*>(g + j))
-                                                            : (j == jt ? tail : 0u);
+      for (int it = 0; it < 8; ++it) {              // n_words is a multiple of 4: `it` alone bounds the word
+        const int j = 4 * (w0 + 4 * it);
+        uint32_t v = j == jt ? tail : 0u;
+        if (4 * it < n_words && ok && j + 3 < P.J) v = __ldg(reinterpret_cast<const uint32_t*>(g + j));
+        wd[rbi][it] = v;
       }
     } else {
 #pragma unroll
@@ -109,7 +110,7 @@ __device__ __forceinline__ void tc_store_x(unsigned char* Xt, uint32_t RS, const
 #pragma unroll
     for (int it = 0; it < 8; ++it) {
       const int word = w0 + 4 * it;
-      if (word < n_words) {
+      if (4 * it < n_words) {                       // uniform: n_words is a multiple of 4
         uint2 v;
         codes_bf16x4(wd[rbi][it], v.x, v.y);
         if (ones_col >= 0 && (ones_col >> 2) == word && one_ok) {
@@ -220,7 +221,16 @@ __global__ void __launch_bounds__(kThreads, 2) enc_tc_fwd_kernel(const EncParams
       P.sigma[tile0 + t] = expf((a.y + b.y) + b22);
     }
     // pre tile -> global memory, whole rows per warp request (the tile is one contiguous block of `pre`)
-    if ((P.H & 3) == 0) {
+    if (P.H == kH) {                                // the tile is 32 KB contiguous: 8 float4 per thread
+      float* dst = P.pre + (size_t)tile0 * kH;
+      const int64_t lim = (P.B - tile0) * (kH / 4);
+#pragma unroll
+      for (int q = 0; q < kTB * (kH / 4) / kThreads; ++q) {
+        const int e = t + q * kThreads;
+        if (e < lim)
+          *reinterpret_cast<float4*>(dst + 4 * e) = *reinterpret_cast<const float4*>(ps + (e >> 4) * kPitch + 4 * (e & 15));
+      }
+    } else if ((P.H & 3) == 0) {
       const int h4 = P.H >> 2;
       for (int e = t; e < kTB * h4; e += kThreads) {
         const int row = e / h4, c4 = e - row * h4;
@@ -292,7 +302,21 @@ __global__ void __launch_bounds__(kBwdThreads) enc_tc_bwd_kernel(const EncParams
   // `pre` rows of a tile -> pb: the tile is one contiguous block of the [B x H] matrix, copied by 16-byte
   // asynchronous copies (whole rows per warp request); rows beyond B read as 0
   auto fetch_pre = [&](int64_t tile0) {
-    if ((P.H & 3) == 0) {
+    if (P.H == kH) {                                // 32 KB contiguous: 4 asynchronous 16-byte copies per thread
+      const float* src = P.pre + (size_t)tile0 * kH;
+      const int64_t lim = (P.B - tile0) * (kH / 4);
+#pragma unroll
+      for (int q = 0; q < kTB * (kH / 4) / kBwdThreads; ++q) {
+        const int e = t + q * kBwdThreads;
+        float* dst = pb + (e >> 4) * kPitch + 4 * (e & 15);
+        if (e < lim) {
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(umma::smem_u32(dst)), "l"(src + 4 * e)
+                       : "memory");
+        } else {
+          *reinterpret_cast<float4*>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      }
+    } else if ((P.H & 3) == 0) {
       const int h4 = P.H >> 2;
       for (int e = t; e < kTB * h4; e += kBwdThreads) {
         const int row = e / h4, c4 = e - row * h4;
