@@ -366,7 +366,16 @@ typedef struct VipsyNormEncoderArgs {
   float* d_b22;              /* [1]                                         */
   void* workspace;           /* backward: vipsy_norm_encoder_workspace_bytes */
   size_t workspace_bytes;
+  const void* x_tiles;       /* optional (idx == NULL, batch == n_rows, J <= 127): the response matrix as resident
+                                bf16 operand tiles from vipsy_norm_encoder_pack_tiles -- fetched with one bulk copy
+                                per 128-person tile instead of being expanded from the codes in every call */
 } VipsyNormEncoderArgs;
+/* bytes of the tile buffer for n_rows persons; 0 if J > 127 */
+size_t vipsy_norm_encoder_tiles_bytes(int64_t n_rows, int32_t n_items);
+/* y (n_rows x y_row_stride codes) -> tiles: per 128 persons one 32 KB block in the shared-memory operand layout
+ * (8 x 8 bf16 core matrices, item slot J = 1 for existing persons).  Done once: the matrix is constant. */
+int vipsy_norm_encoder_pack_tiles(const uint8_t* y, int64_t n_rows, int32_t n_items, int64_t y_row_stride,
+                                  void* tiles, void* stream);
 size_t vipsy_norm_encoder_workspace_bytes(const VipsyNormEncoderArgs* args);
 int vipsy_norm_encoder_forward(const VipsyNormEncoderArgs* args, void* stream);
 int vipsy_norm_encoder_backward(const VipsyNormEncoderArgs* args, void* stream);

@@ -11,12 +11,13 @@ codes = (torch.rand(N, J, generator=g) < 0.6).to(torch.uint8).cuda()
 torch.manual_seed(0)
 enc = NormEncoder(J, 1, H).cuda()
 d = torch.randn(N, generator=g).cuda()
-mu, sigma, pre = ops.norm_encoder_forward(codes, enc)
-ops.norm_encoder_backward(codes, enc, sigma, pre, d, d)
+xt = ops.norm_encoder_pack_tiles(codes) if os.environ.get("RESIDENT", "1") == "1" else None
+mu, sigma, pre = ops.norm_encoder_forward(codes, enc, x_tiles=xt)
+ops.norm_encoder_backward(codes, enc, sigma, pre, d, d, x_tiles=xt)
 torch.cuda.synchronize()
 if os.environ.get("TIME", "1") == "1":
-    for name, fn in (("forward", lambda: ops.norm_encoder_forward(codes, enc)),
-                     ("backward", lambda: ops.norm_encoder_backward(codes, enc, sigma, pre, d, d))):
+    for name, fn in (("forward", lambda: ops.norm_encoder_forward(codes, enc, x_tiles=xt)),
+                     ("backward", lambda: ops.norm_encoder_backward(codes, enc, sigma, pre, d, d, x_tiles=xt))):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         for _ in range(3):
             fn()
@@ -25,4 +26,4 @@ if os.environ.get("TIME", "1") == "1":
             fn()
         e1.record()
         torch.cuda.synchronize()
-        print(f"norm_encoder {name} {N}x{J} H={H}: {e0.elapsed_time(e1) / 20 * 1e3:.1f} us")
+        print(f"norm_encoder {name} {N}x{J} H={H} resident={xt is not None}: {e0.elapsed_time(e1) / 20 * 1e3:.1f} us")

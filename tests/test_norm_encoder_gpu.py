@@ -59,11 +59,14 @@ def test_norm_encoder_forward_backward(ops, B, J, H, missing, sub, tc):
     enc = _encoder(J, H, B + J + H)
     codes = codes_from_float(y).cuda()
     idx = torch.randperm(B, generator=g)[:sub].cuda() if sub else None
-    mu, sigma, pre = ops.norm_encoder_forward(codes, enc, idx, tensor_cores=tc)
+    # tensor cores, full batch: once from the codes, once from the resident operand tiles
+    xt = ops.norm_encoder_pack_tiles(codes) if (tc and idx is None and B > 1) else None
+    mu, sigma, pre = ops.norm_encoder_forward(codes, enc, idx, tensor_cores=tc, x_tiles=xt)
     Bb = sub or B
     d_mu = torch.randn(Bb, generator=g).cuda()
     d_sigma = torch.randn(Bb, generator=g).cuda()
-    got = ops.norm_encoder_backward(codes, enc, sigma, pre, d_mu, d_sigma, idx, grad_scale=0.5, tensor_cores=tc)
+    got = ops.norm_encoder_backward(codes, enc, sigma, pre, d_mu, d_sigma, idx, grad_scale=0.5, tensor_cores=tc,
+                                    x_tiles=xt)
     torch.cuda.synchronize()
     # oracle, fp64
     leaves = {n: p.detach().cpu().double().requires_grad_(True) for n, p in enc.named_parameters()}
@@ -75,6 +78,27 @@ def test_norm_encoder_forward_backward(ops, B, J, H, missing, sub, tc):
     _close(sigma, sc.detach(), "sigma")
     for n, leaf in leaves.items():
         _close(got[n], leaf.grad, n)
+
+
+def test_norm_encoder_resident_tiles_equal_on_the_fly(ops):
+    """The resident operand tiles hold exactly what the kernels expand from the codes: identical results."""
+    g = torch.Generator().manual_seed(11)
+    y = (torch.rand(3001, 100, generator=g) < 0.6).float()
+    y[torch.rand(3001, 100, generator=g) < 0.1] = float("nan")
+    enc = _encoder(100, 64, 2)
+    codes = codes_from_float(y).cuda()
+    xt = ops.norm_encoder_pack_tiles(codes)
+    d = torch.randn(3001, generator=g).cuda()
+    out = []
+    for tiles in (None, xt):
+        mu, sigma, pre = ops.norm_encoder_forward(codes, enc, x_tiles=tiles)
+        gr = ops.norm_encoder_backward(codes, enc, sigma, pre, d, d * 0.5, x_tiles=tiles)
+        out.append((mu, sigma, pre, gr))
+    torch.cuda.synchronize()
+    assert torch.equal(out[0][0], out[1][0]) and torch.equal(out[0][1], out[1][1]) and torch.equal(out[0][2], out[1][2])
+    for n in out[0][3]:
+        assert torch.equal(out[0][3][n], out[1][3][n]), n
+    assert ops.norm_encoder_pack_tiles(torch.zeros((10, 200), dtype=torch.uint8, device="cuda")) is None
 
 
 def test_norm_encoder_deterministic(ops):

@@ -101,7 +101,7 @@ class NormEncoderArgs(C.Structure):
         ("mu", _p), ("sigma", _p), ("pre", _p), ("d_mu", _p), ("d_sigma", _p),
         ("grad_scale", C.c_float), ("flags", C.c_int32),
         ("d_w1", _p), ("d_b1", _p), ("d_w21", _p), ("d_b21", _p), ("d_w22", _p), ("d_b22", _p),
-        ("workspace", _p), ("workspace_bytes", C.c_size_t),
+        ("workspace", _p), ("workspace_bytes", C.c_size_t), ("x_tiles", _p),
     ]
 
 
@@ -129,6 +129,8 @@ SYMBOLS = {
     "vipsy_peer_allreduce": (C.c_int, [_p, C.c_int32, C.c_int32, C.c_int64, C.c_int64, C.c_int32, C.c_int32, _p, _p,
                                        C.c_uint32, _p]),
     "vipsy_norm_encoder_workspace_bytes": (C.c_size_t, [C.POINTER(NormEncoderArgs)]),
+    "vipsy_norm_encoder_tiles_bytes": (C.c_size_t, [C.c_int64, C.c_int32]),
+    "vipsy_norm_encoder_pack_tiles": (C.c_int, [_p, C.c_int64, C.c_int32, C.c_int64, _p, _p]),
     "vipsy_norm_encoder_forward": (C.c_int, [C.POINTER(NormEncoderArgs), _p]),
     "vipsy_norm_encoder_backward": (C.c_int, [C.POINTER(NormEncoderArgs), _p]),
     "vipsy_adam_step": (C.c_int, [C.POINTER(AdamTensor), C.c_int32, _p, C.c_int32, _p]),

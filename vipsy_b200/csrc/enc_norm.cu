@@ -329,6 +329,7 @@ static EncParams enc_params(const VipsyNormEncoderArgs* a) {
   P.w1 = a->w1; P.b1 = a->b1; P.w21 = a->w21; P.b21 = a->b21; P.w22 = a->w22; P.b22 = a->b22;
   P.mu = a->mu; P.sigma = a->sigma; P.pre = a->pre; P.d_mu = a->d_mu; P.d_sigma = a->d_sigma;
   P.gscale = a->grad_scale; P.partial = nullptr; P.cols = enc_cols(a->n_hidden, a->n_items);
+  P.xtiles = (a->x_tiles && !a->idx && a->batch == a->n_rows) ? reinterpret_cast<const unsigned char*>(a->x_tiles) : nullptr;
   return P;
 }
 
@@ -337,6 +338,22 @@ static EncParams enc_params(const VipsyNormEncoderArgs* a) {
 using namespace vipsy;
 
 extern "C" {
+
+size_t vipsy_norm_encoder_tiles_bytes(int64_t n_rows, int32_t n_items) {
+  if (n_rows <= 0 || !enc_tc_supported(1, n_items)) return 0;
+  return (size_t)((n_rows + 127) / 128) * kEncTileBytes;
+}
+
+int vipsy_norm_encoder_pack_tiles(const uint8_t* y, int64_t n_rows, int32_t n_items, int64_t y_row_stride, void* tiles,
+                                  void* stream) {
+  VIPSY_REQUIRE(y && tiles && n_rows > 0 && y_row_stride >= n_items, VIPSY_ERR_ARG,
+                "vipsy_norm_encoder_pack_tiles: bad arguments");
+  VIPSY_REQUIRE(enc_tc_supported(1, n_items), VIPSY_ERR_UNSUPPORTED,
+                "vipsy_norm_encoder_pack_tiles: J = %d > 127 has no tensor-core path", n_items);
+  VIPSY_REQUIRE((reinterpret_cast<uintptr_t>(tiles) & 127) == 0, VIPSY_ERR_ARG,
+                "vipsy_norm_encoder_pack_tiles: tiles must be 128-byte aligned");
+  return enc_tc_pack_launch(y, n_rows, n_items, y_row_stride, tiles, (cudaStream_t)stream);
+}
 
 size_t vipsy_norm_encoder_workspace_bytes(const VipsyNormEncoderArgs* a) {
   if (!a || a->n_items <= 0 || a->n_hidden <= 0 || a->n_hidden > kEncH || a->batch < 0) return 0;

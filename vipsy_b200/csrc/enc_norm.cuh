@@ -10,6 +10,7 @@ struct EncParams {
   float *mu, *sigma, *pre;
   const float *d_mu, *d_sigma; float gscale;
   float* partial; int cols;             // backward: [gridDim.x x cols]
+  const unsigned char* xtiles;          // resident bf16 operand tiles or nullptr
 };
 
 // softplus (torch: beta 1, threshold 20) and its derivative from one exponential: three MUFU ops, absolute error
@@ -26,5 +27,7 @@ __device__ __forceinline__ void softplus_parts(float x, float& sp, float& sg) {
 bool enc_tc_supported(int H, int J);
 int enc_tc_fwd_launch(const EncParams& P, cudaStream_t st);
 int enc_tc_bwd_launch(const EncParams& P, int grid_x, cudaStream_t st);
+int enc_tc_pack_launch(const uint8_t* y, int64_t n_rows, int J, int64_t ld, void* tiles, cudaStream_t st);
+constexpr size_t kEncTileBytes = 32768;
 
 }  // namespace vipsy

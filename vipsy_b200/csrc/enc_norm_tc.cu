@@ -124,19 +124,68 @@ __device__ __forceinline__ void tc_store_x(unsigned char* Xt, uint32_t RS, const
   }
 }
 
+// ---- resident operand tiles ---------------------------------------------------------------------------------
+// The response matrix never changes between SVI steps, so its bf16 operand tiles can live in HBM in exactly the
+// shared-memory layout (per 128 persons: 16 row blocks x 16 chunks x 8 rows x 8 bf16 = 32 KB, item slot J = 1 for
+// existing persons).  A tile then reaches shared memory by ONE bulk asynchronous copy that completes on an mbarrier.
+constexpr uint32_t kTileBytes = (uint32_t)kEncTileBytes;
+constexpr uint32_t kRSTile = (kTB / 8) * kCS;     // 2048: row-block pitch of a resident tile (128 item slots)
+
+__global__ void __launch_bounds__(256) enc_tc_pack_kernel(const uint8_t* __restrict__ y, int64_t n_rows, int J,
+                                                          int64_t ld, unsigned char* __restrict__ tiles) {
+  const int64_t tile0 = (int64_t)blockIdx.x * kTB;
+  unsigned char* out = tiles + (size_t)blockIdx.x * kTileBytes;
+  for (int id = threadIdx.x; id < (int)(kTileBytes / 16); id += 256) {       // 16-byte chunk id = rb*128 + ch*8 + pp
+    const int rb = id >> 7, ch = (id >> 3) & 15, pp = id & 7;
+    const int64_t r = tile0 + rb * 8 + pp;
+    uint32_t w[2] = {0u, 0u};
+    if (r < n_rows) {
+      const uint8_t* g = y + r * ld;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int j = 8 * ch + k;
+        const uint32_t c = j < J ? (uint32_t)g[j] : (j == J ? 1u : 0u);
+        w[k >> 2] |= c << (8 * (k & 3));
+      }
+    }
+    uint4 v;
+    codes_bf16x4(w[0], v.x, v.y);
+    codes_bf16x4(w[1], v.z, v.w);
+    *reinterpret_cast<uint4*>(out + (size_t)id * 16) = v;
+  }
+}
+
+int enc_tc_pack_launch(const uint8_t* y, int64_t n_rows, int J, int64_t ld, void* tiles, cudaStream_t st) {
+  const int64_t n_tiles = (n_rows + kTB - 1) / kTB;
+  enc_tc_pack_kernel<<<(unsigned)n_tiles, 256, 0, st>>>(y, n_rows, J, ld, reinterpret_cast<unsigned char*>(tiles));
+  VIPSY_CUDA_CHECK(cudaGetLastError());
+  return VIPSY_OK;
+}
+
+// one thread: expect `bytes` on the mbarrier and start the bulk copy global -> shared that will deliver them
+__device__ __forceinline__ void bulk_load(unsigned char* dst_smem, const unsigned char* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(umma::smem_u32(bar)), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   umma::smem_u32(dst_smem)),
+               "l"(src), "r"(bytes), "r"(umma::smem_u32(bar))
+               : "memory");
+}
+
 // ------------------------------------------------------------------------------------------------ forward
 __global__ void __launch_bounds__(kThreads, 2) enc_tc_fwd_kernel(const EncParams P, const int JP) {
   extern __shared__ __align__(1024) unsigned char smem[];
-  __shared__ uint64_t bar;
+  __shared__ uint64_t bar, barx;
   __shared__ uint32_t tmem_base_sm;
   __shared__ float hv[3 * kH];                    // b1 | w21 | w22, zero beyond H
   __shared__ float2 part[2][kTB];                 // per column half: partial (mu, log sigma) of each person
   const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
   const int n_chunks = JP >> 3;
-  const uint32_t RS = (uint32_t)n_chunks * kCS;   // same pitch for the code tile (16 row blocks) and W tiles (8)
+  const bool resident = P.xtiles != nullptr;
+  const uint32_t RS = (uint32_t)n_chunks * kCS;   // row-block pitch of the W tiles (8 row blocks each)
+  const uint32_t RSx = resident ? kRSTile : RS;   // ... and of the code tile (16 row blocks)
   unsigned char* Xt = smem;
-  unsigned char* Wt[3] = {Xt + 16 * RS, Xt + 24 * RS, Xt + 32 * RS};
-  float* ps = reinterpret_cast<float*>(Xt + 40 * RS);     // [128][kPitch] pre tile on its way to global memory
+  unsigned char* Wt[3] = {Xt + 16 * RSx, Xt + 16 * RSx + 8 * RS, Xt + 16 * RSx + 16 * RS};
+  float* ps = reinterpret_cast<float*>(Xt + 16 * RSx + 24 * RS);     // [128][kPitch] pre tile on its way to global memory
   const bool aligned = ((reinterpret_cast<uintptr_t>(P.y) | (uintptr_t)P.ld) & 3) == 0;
 
   for (int e = t; e < kH * JP; e += kThreads) {   // fc1.weight -> three bf16 operand tiles, once per CTA
@@ -158,6 +207,7 @@ __global__ void __launch_bounds__(kThreads, 2) enc_tc_fwd_kernel(const EncParams
   if (warp == 0) umma::tmem_alloc(&tmem_base_sm, kTmemCols);
   if (t == 0) {
     umma::mbar_init(&bar, 1);
+    umma::mbar_init(&barx, 1);
     umma::fence_mbar_init();
   }
   umma::fence_before_sync();
@@ -171,18 +221,25 @@ __global__ void __launch_bounds__(kThreads, 2) enc_tc_fwd_kernel(const EncParams
   const int quad = warp & 3, half = warp >> 2;    // TMEM lane quadrant, column half of this warp
   const int64_t n_tiles = (P.B + kTB - 1) / kTB;
   uint32_t wd[2][8];
-  if ((int64_t)blockIdx.x < n_tiles) tc_load_codes<8>(wd, P, (int64_t)blockIdx.x * kTB, 2 * n_chunks, aligned);
+  if (resident) {
+    if (t == 0) bulk_load(Xt, P.xtiles + (size_t)blockIdx.x * kTileBytes, kTileBytes, &barx);
+  } else {
+    tc_load_codes<8>(wd, P, (int64_t)blockIdx.x * kTB, 2 * n_chunks, aligned);
+  }
   uint32_t phase = 0;
   for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const int64_t tile0 = tile * kTB;
-    tc_store_x<8>(Xt, RS, wd, 2 * n_chunks, P.J, tile0, INT64_MAX);
-    umma::fence_proxy_async();
+    if (!resident) {
+      tc_store_x<8>(Xt, RS, wd, 2 * n_chunks, P.J, tile0, INT64_MAX);
+      umma::fence_proxy_async();
+    }
     __syncthreads();
     if (t == 0) {
+      if (resident) umma::mbar_wait(&barx, phase);  // this tile's bulk copy has landed
       umma::fence_after_sync();
       uint32_t acc = 0;
       for (int ks = 0; ks < JP / 16; ++ks) {
-        const uint64_t da = umma::make_desc(sX + ks * 2 * kCS, kCS, RS);
+        const uint64_t da = umma::make_desc(sX + ks * 2 * kCS, kCS, RSx);
 #pragma unroll
         for (int term = 0; term < 3; ++term) {
           umma::mma_f16_ss(tmem, da, umma::make_desc(sW[term] + ks * 2 * kCS, kCS, RS), idesc, acc);
@@ -191,10 +248,13 @@ __global__ void __launch_bounds__(kThreads, 2) enc_tc_fwd_kernel(const EncParams
       }
       umma::commit(&bar);
     }
-    if (tile + gridDim.x < n_tiles) tc_load_codes<8>(wd, P, (tile + gridDim.x) * kTB, 2 * n_chunks, aligned);
+    if (!resident && tile + gridDim.x < n_tiles)
+      tc_load_codes<8>(wd, P, (tile + gridDim.x) * kTB, 2 * n_chunks, aligned);
     umma::mbar_wait(&bar, phase);
     phase ^= 1u;
     umma::fence_after_sync();
+    if (resident && t == 0 && tile + gridDim.x < n_tiles)         // the MMAs are done with the code tile: refill it
+      bulk_load(Xt, P.xtiles + (size_t)(tile + gridDim.x) * kTileBytes, kTileBytes, &barx);
     {
       float v[32];
       umma::tmem_ld32(tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)(half * 32), v);
@@ -253,7 +313,7 @@ __global__ void __launch_bounds__(kThreads, 2) enc_tc_fwd_kernel(const EncParams
 // ------------------------------------------------------------------------------------------------ backward
 __global__ void __launch_bounds__(kBwdThreads) enc_tc_bwd_kernel(const EncParams P) {
   extern __shared__ __align__(1024) unsigned char smem[];
-  __shared__ uint64_t bar;
+  __shared__ uint64_t bar, barx;
   __shared__ uint32_t tmem_base_sm;
   __shared__ float gm[kTB], gl[kTB];              // d loss / d mu, d loss / d log sigma of the tile's persons
   __shared__ float red[2][4][kH];                 // end of kernel: [w21 | w22][warp of the half][h]
@@ -265,6 +325,7 @@ __global__ void __launch_bounds__(kBwdThreads) enc_tc_bwd_kernel(const EncParams
   unsigned char* Dt[3] = {Xt + 16 * RSx, Xt + 16 * RSx + 16 * RSd, Xt + 16 * RSx + 32 * RSd};
   float* pb = reinterpret_cast<float*>(Xt + 16 * RSx + 48 * RSd);      // [128][kPitch] `pre` rows of the tile
   const bool aligned = ((reinterpret_cast<uintptr_t>(P.y) | (uintptr_t)P.ld) & 3) == 0;
+  const bool resident = P.xtiles != nullptr;
   const int p = t & (kTB - 1), hq = t >> 7;       // this thread: person p, hidden chunks hc = hq + 4 q (8 units each)
 
   if (t < 2 * kH) {
@@ -275,6 +336,7 @@ __global__ void __launch_bounds__(kBwdThreads) enc_tc_bwd_kernel(const EncParams
   if (warp == 0) umma::tmem_alloc(&tmem_base_sm, kTmemCols);
   if (t == 0) {
     umma::mbar_init(&bar, 1);
+    umma::mbar_init(&barx, 1);
     umma::fence_mbar_init();
   }
   umma::fence_before_sync();
@@ -338,11 +400,15 @@ __global__ void __launch_bounds__(kBwdThreads) enc_tc_bwd_kernel(const EncParams
     asm volatile("cp.async.commit_group;" ::: "memory");
   };
   if ((int64_t)blockIdx.x < n_tiles) {
-    tc_load_codes<16>(wd, P, (int64_t)blockIdx.x * kTB, 32, aligned);
+    if (resident) {
+      if (t == 0) bulk_load(Xt, P.xtiles + (size_t)blockIdx.x * kTileBytes, kTileBytes, &barx);
+    } else {
+      tc_load_codes<16>(wd, P, (int64_t)blockIdx.x * kTB, 32, aligned);
+    }
     fetch_pre((int64_t)blockIdx.x * kTB);
     load_heads((int64_t)blockIdx.x * kTB);
   }
-  uint32_t phase = 0, acc = 0;
+  uint32_t phase = 0, phx = 0, acc = 0;
   bool pending = false;
   for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const int64_t tile0 = tile * kTB;
@@ -352,6 +418,7 @@ __global__ void __launch_bounds__(kBwdThreads) enc_tc_bwd_kernel(const EncParams
       umma::mbar_wait(&bar, phase);
       phase ^= 1u;
       pending = false;
+      if (resident && t == 0) bulk_load(Xt, P.xtiles + (size_t)tile * kTileBytes, kTileBytes, &barx);
     }
     __syncthreads();                                // every thread's share of `pre` has landed in pb
     float pv[2][8];
@@ -362,7 +429,7 @@ __global__ void __launch_bounds__(kBwdThreads) enc_tc_bwd_kernel(const EncParams
       pv[q][0] = u0.x; pv[q][1] = u0.y; pv[q][2] = u0.z; pv[q][3] = u0.w;
       pv[q][4] = u1.x; pv[q][5] = u1.y; pv[q][6] = u1.z; pv[q][7] = u1.w;
     }
-    tc_store_x<16>(Xt, RSx, wd, 32, P.J, tile0, P.B);
+    if (!resident) tc_store_x<16>(Xt, RSx, wd, 32, P.J, tile0, P.B);
     if (hq == 0) { s_gm += a; s_gl += b; }
 #pragma unroll
     for (int q = 0; q < 2; ++q) {
@@ -387,6 +454,10 @@ __global__ void __launch_bounds__(kBwdThreads) enc_tc_bwd_kernel(const EncParams
     umma::fence_proxy_async();
     __syncthreads();
     if (t == 0) {
+      if (resident) {
+        umma::mbar_wait(&barx, phx);                // this tile's bulk copy has landed
+        phx ^= 1u;
+      }
       umma::fence_after_sync();
       for (int ks = 0; ks < kTB / 16; ++ks) {
         const uint64_t da = umma::make_desc(sX + ks * 2 * RSx, RSx, kCS);
@@ -401,7 +472,7 @@ __global__ void __launch_bounds__(kBwdThreads) enc_tc_bwd_kernel(const EncParams
     pending = true;
     if (tile + gridDim.x < n_tiles) {
       fetch_pre((tile + gridDim.x) * kTB);          // pb was consumed before the barrier above
-      tc_load_codes<16>(wd, P, (tile + gridDim.x) * kTB, 32, aligned);
+      if (!resident) tc_load_codes<16>(wd, P, (tile + gridDim.x) * kTB, 32, aligned);
       load_heads((tile + gridDim.x) * kTB);
     }
   }
@@ -451,13 +522,16 @@ __global__ void __launch_bounds__(kBwdThreads) enc_tc_bwd_kernel(const EncParams
   if (warp == 0) umma::tmem_dealloc(tmem, kTmemCols);
 }
 
-static size_t tc_fwd_smem(int JP) { return (size_t)40 * (JP / 8) * kCS + (size_t)kTB * kPitch * 4 + 1024; }
+static size_t tc_fwd_smem(int JP, bool resident) {
+  const size_t RS = (size_t)(JP / 8) * kCS;
+  return 16 * (resident ? (size_t)kRSTile : RS) + 24 * RS + (size_t)kTB * kPitch * 4 + 1024;
+}
 constexpr size_t kTcBwdSmem = 16 * (kTB / 8) * kCS + 3 * 16 * (kH / 8) * kCS + (size_t)kTB * kPitch * 4 + 1024;
 
 int enc_tc_fwd_launch(const EncParams& P, cudaStream_t st) {
   const int JP = (P.J + 1 + 15) / 16 * 16;        // + the ones column that carries fc1.bias
   static size_t attr = 0;
-  const size_t smem = tc_fwd_smem(JP);
+  const size_t smem = tc_fwd_smem(JP, P.xtiles != nullptr);
   if (smem > attr) {
     VIPSY_CUDA_CHECK(cudaFuncSetAttribute(enc_tc_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr = smem;

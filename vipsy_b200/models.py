@@ -352,6 +352,7 @@ class VaeIRT(BaseIRT):                  # vi.py:659-693
         enc = NormEncoder if self.x_feature == 1 else MvnEncoder
         self.encoder = enc(self.item_size, self.x_feature, hidden_dim).to(self.device)
         self.fused_encoder = True       # K = 1: encoder forward / backward as CUDA kernels (False: torch autograd)
+        self._x_tiles, self._x_tiles_tried = None, False
 
     def _guide(self, idx, B):
         get_param_store().register_module("encoder", self.encoder)
@@ -360,10 +361,15 @@ class VaeIRT(BaseIRT):                  # vi.py:659-693
             # NormEncoder evaluated by the CUDA kernels on the response codes (csrc/enc_norm.cu): no fp32 input
             # matrix, no stored hidden activations, deterministic weight gradients
             enc = self.encoder
-            mu, sigma, pre = ops.norm_encoder_forward(self._codes, enc, idx)
+            if idx is None and self._x_tiles is None and not self._x_tiles_tried:
+                self._x_tiles_tried = True              # full batch: resident operand tiles, built once
+                self._x_tiles = ops.norm_encoder_pack_tiles(self._codes)
+            xt = self._x_tiles if idx is None else None
+            mu, sigma, pre = ops.norm_encoder_forward(self._codes, enc, idx, x_tiles=xt)
 
             def backward(r, w):
-                g = ops.norm_encoder_backward(self._codes, enc, sigma, pre, r["d_mu"], r["d_sigma"], idx, grad_scale=w)
+                g = ops.norm_encoder_backward(self._codes, enc, sigma, pre, r["d_mu"], r["d_sigma"], idx, grad_scale=w,
+                                              x_tiles=xt)
                 for n, p in enc.named_parameters():
                     _accum(p, g[n])
             return dict(mu=mu, sigma=sigma), backward, sites

@@ -472,7 +472,21 @@ def cdm_score_elbo_grad(
 NORM_ENCODER_MAX_HIDDEN = 64
 
 
-def _norm_encoder_args(y, idx, enc, tensor_cores=True):
+def norm_encoder_pack_tiles(y: torch.Tensor) -> Optional[torch.Tensor]:
+    """Resident bf16 operand tiles of the (constant) response matrix for the tensor-core encoder kernels, or None
+    when the shape has no tensor-core path (J > 127).  32 KB per 128 persons; build once."""
+    if not y.is_cuda or y.dtype != torch.uint8 or y.dim() != 2 or y.stride(1) != 1:
+        raise ValueError("y must be a CUDA uint8 code matrix (see pack_responses)")
+    L = N.lib()
+    nbytes = L.vipsy_norm_encoder_tiles_bytes(y.shape[0], y.shape[1])
+    if nbytes == 0:
+        return None
+    tiles = torch.empty(nbytes, dtype=torch.uint8, device=y.device)
+    N.check(L.vipsy_norm_encoder_pack_tiles(_ptr(y), y.shape[0], y.shape[1], y.stride(0), _ptr(tiles), _stream()))
+    return tiles
+
+
+def _norm_encoder_args(y, idx, enc, tensor_cores=True, x_tiles=None):
     """enc: object with fc1 / fc21 / fc22 ``nn.Linear`` members (fc21, fc22 have one output)."""
     if not y.is_cuda or y.dtype != torch.uint8 or y.dim() != 2 or y.stride(1) != 1:
         raise ValueError("y must be a CUDA uint8 code matrix (see pack_responses)")
@@ -483,6 +497,7 @@ def _norm_encoder_args(y, idx, enc, tensor_cores=True):
     a.n_rows, a.n_items, a.n_hidden = y.shape[0], J, H
     a.y, a.y_row_stride = _ptr(y), y.stride(0)
     a.flags = 0 if tensor_cores else 1
+    a.x_tiles = _ptr(x_tiles) if (x_tiles is not None and idx is None) else None
     if idx is not None:
         if idx.dtype != torch.int64 or not idx.is_cuda:
             raise ValueError("idx must be a CUDA int64 tensor")
@@ -499,9 +514,11 @@ def _norm_encoder_args(y, idx, enc, tensor_cores=True):
     return a, keep
 
 
-def norm_encoder_forward(y: torch.Tensor, enc, idx: Optional[torch.Tensor] = None, tensor_cores: bool = True):
-    """mu [B], sigma [B], pre [B, H] of the amortised K = 1 guide, straight from the response codes."""
-    a, keep = _norm_encoder_args(y, idx, enc, tensor_cores)
+def norm_encoder_forward(y: torch.Tensor, enc, idx: Optional[torch.Tensor] = None, tensor_cores: bool = True,
+                         x_tiles: Optional[torch.Tensor] = None):
+    """mu [B], sigma [B], pre [B, H] of the amortised K = 1 guide, straight from the response codes (or, full
+    batch, from the resident operand tiles of ``norm_encoder_pack_tiles``)."""
+    a, keep = _norm_encoder_args(y, idx, enc, tensor_cores, x_tiles)
     dev, B, H = y.device, int(a.batch), int(a.n_hidden)
     mu = torch.empty(B, dtype=torch.float32, device=dev)
     sigma = torch.empty(B, dtype=torch.float32, device=dev)
@@ -513,10 +530,10 @@ def norm_encoder_forward(y: torch.Tensor, enc, idx: Optional[torch.Tensor] = Non
 
 def norm_encoder_backward(y: torch.Tensor, enc, sigma: torch.Tensor, pre: torch.Tensor, d_mu: torch.Tensor,
                           d_sigma: torch.Tensor, idx: Optional[torch.Tensor] = None, grad_scale: float = 1.0,
-                          tensor_cores: bool = True):
+                          tensor_cores: bool = True, x_tiles: Optional[torch.Tensor] = None):
     """Gradients of the six encoder tensors given d loss / d mu and d loss / d sigma; returns a dict keyed by the
     ``named_parameters`` names (fc1.weight, fc1.bias, fc21.weight, ...), shaped like the parameters."""
-    a, keep = _norm_encoder_args(y, idx, enc, tensor_cores)
+    a, keep = _norm_encoder_args(y, idx, enc, tensor_cores, x_tiles)
     dev, B, H, J = y.device, int(a.batch), int(a.n_hidden), int(a.n_items)
     sigma, pre = _f32(sigma, "sigma", B), _f32(pre, "pre", B * H)
     d_mu, d_sigma = _f32(d_mu, "d_mu", B), _f32(d_sigma, "d_sigma", B)
