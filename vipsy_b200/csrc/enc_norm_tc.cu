@@ -323,7 +323,7 @@ __global__ void __launch_bounds__(kBwdThreads) enc_tc_bwd_kernel(const EncParams
   constexpr uint32_t RSd = (kH / 8) * kCS;        // dpre tiles: 128 persons x 64 hidden
   unsigned char* Xt = smem;
   unsigned char* Dt[3] = {Xt + 16 * RSx, Xt + 16 * RSx + 16 * RSd, Xt + 16 * RSx + 32 * RSd};
-  float* pb = reinterpret_cast<float*>(Xt + 16 * RSx + 48 * RSd);      // [128][kPitch] `pre` rows of the tile
+  float* pb0 = reinterpret_cast<float*>(Xt + 16 * RSx + 48 * RSd);     // 2 x [128][kPitch]: `pre` rows, this tile / next
   const bool aligned = ((reinterpret_cast<uintptr_t>(P.y) | (uintptr_t)P.ld) & 3) == 0;
   const bool resident = P.xtiles != nullptr;
   const int p = t & (kTB - 1), hq = t >> 7;       // this thread: person p, hidden chunks hc = hq + 4 q (8 units each)
@@ -332,7 +332,7 @@ __global__ void __launch_bounds__(kBwdThreads) enc_tc_bwd_kernel(const EncParams
     const int h = t & 63;
     wh[t >> 6][h] = h < P.H ? __ldg((t >> 6 ? P.w22 : P.w21) + h) : 0.0f;
   }
-  for (int e = t; e < kTB * kPitch; e += kBwdThreads) pb[e] = 0.0f;     // columns beyond H stay 0
+  for (int e = t; e < 2 * kTB * kPitch; e += kBwdThreads) pb0[e] = 0.0f;        // columns beyond H stay 0
   if (warp == 0) umma::tmem_alloc(&tmem_base_sm, kTmemCols);
   if (t == 0) {
     umma::mbar_init(&bar, 1);
@@ -363,7 +363,8 @@ __global__ void __launch_bounds__(kBwdThreads) enc_tc_bwd_kernel(const EncParams
   };
   // `pre` rows of a tile -> pb: the tile is one contiguous block of the [B x H] matrix, copied by 16-byte
   // asynchronous copies (whole rows per warp request); rows beyond B read as 0
-  auto fetch_pre = [&](int64_t tile0) {
+  auto fetch_pre = [&](int64_t tile0, int buf) {
+    float* pb = pb0 + buf * (kTB * kPitch);
     if (P.H == kH) {                                // 32 KB contiguous: 4 asynchronous 16-byte copies per thread
       const float* src = P.pre + (size_t)tile0 * kH;
       const int64_t lim = (P.B - tile0) * (kH / 4);
@@ -405,15 +406,23 @@ __global__ void __launch_bounds__(kBwdThreads) enc_tc_bwd_kernel(const EncParams
     } else {
       tc_load_codes<16>(wd, P, (int64_t)blockIdx.x * kTB, 32, aligned);
     }
-    fetch_pre((int64_t)blockIdx.x * kTB);
+    fetch_pre((int64_t)blockIdx.x * kTB, 0);
     load_heads((int64_t)blockIdx.x * kTB);
   }
   uint32_t phase = 0, phx = 0, acc = 0;
+  int nb = 0;                                     // `pre` buffer of the current tile
   bool pending = false;
   for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const int64_t tile0 = tile * kTB;
     const float a = n_dm * P.gscale, b = n_ds * n_sg * P.gscale;       // exp chain rule; 0 beyond B
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    const bool has_next = tile + gridDim.x < n_tiles;
+    if (has_next) {                                 // next tile's `pre` rows: a whole iteration ahead
+      fetch_pre((tile + gridDim.x) * kTB, (nb ^ 1));
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+    } else {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }
+    const float* pb = pb0 + nb * (kTB * kPitch);
     if (pending) {                                  // previous tile's MMAs have read the operand tiles
       umma::mbar_wait(&bar, phase);
       phase ^= 1u;
@@ -470,8 +479,8 @@ __global__ void __launch_bounds__(kBwdThreads) enc_tc_bwd_kernel(const EncParams
       umma::commit(&bar);
     }
     pending = true;
-    if (tile + gridDim.x < n_tiles) {
-      fetch_pre((tile + gridDim.x) * kTB);          // pb was consumed before the barrier above
+    nb ^= 1;
+    if (has_next) {
       if (!resident) tc_load_codes<16>(wd, P, (tile + gridDim.x) * kTB, 32, aligned);
       load_heads((tile + gridDim.x) * kTB);
     }
@@ -526,7 +535,7 @@ static size_t tc_fwd_smem(int JP, bool resident) {
   const size_t RS = (size_t)(JP / 8) * kCS;
   return 16 * (resident ? (size_t)kRSTile : RS) + 24 * RS + (size_t)kTB * kPitch * 4 + 1024;
 }
-constexpr size_t kTcBwdSmem = 16 * (kTB / 8) * kCS + 3 * 16 * (kH / 8) * kCS + (size_t)kTB * kPitch * 4 + 1024;
+constexpr size_t kTcBwdSmem = 16 * (kTB / 8) * kCS + 3 * 16 * (kH / 8) * kCS + 2 * (size_t)kTB * kPitch * 4 + 1024;
 
 int enc_tc_fwd_launch(const EncParams& P, cudaStream_t st) {
   const int JP = (P.J + 1 + 15) / 16 * 16;        // + the ones column that carries fc1.bias

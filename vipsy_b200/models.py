@@ -116,6 +116,7 @@ class BasePsy(nn.Module):               # vi.py:521-533
         self._n_missing = int((self._codes == 255).sum().item()) if self._codes.numel() else 0
         self._sparse = self._n_missing > 0.5 * self._codes.numel()
         self._obs_csr = None          # CSR of the observed cells, built on first use (K = 1, S = 1 path)
+        self._enc_x_full = None       # encoder input of the full batch (NaN -> -1), built on first use
         self._seed, self._calls = int(seed), 0
         # device-resident RNG state (SVI(cuda_graph=True)): the noise call counter is a device scalar and the
         # minibatch is drawn with graph-safe torch ops, so a captured iteration differs on every replay
@@ -160,7 +161,12 @@ class BasePsy(nn.Module):               # vi.py:521-533
                            device=self.device)}
 
     def _encoder_input(self, idx):
-        x = self._data_dev if idx is None else self._data_dev[idx]
+        if idx is None:                   # full batch: the matrix is constant, substitute once
+            if self._enc_x_full is None:
+                x = self._data_dev
+                self._enc_x_full = torch.where(torch.isnan(x), torch.full_like(x, -1.0), x)
+            return self._enc_x_full
+        x = self._data_dev[idx]
         return torch.where(torch.isnan(x), torch.full_like(x, -1.0), x)      # vi.py:679-682
 
     def _finish(self, loss: torch.Tensor, sites: List[Site]):
