@@ -403,8 +403,9 @@ int vipsy_norm_encoder_backward(const VipsyNormEncoderArgs* a, void* stream) {
   }
   EncParams P = enc_params(a);
   P.partial = reinterpret_cast<float*>(a->workspace);
-  const int gx = enc_grid_x(a->batch);
+  int gx = enc_grid_x(a->batch);
   if (enc_tc_supported(H, J) && !(a->flags & 1) && (reinterpret_cast<uintptr_t>(a->pre) & 15) == 0) {
+    if (gx > num_sms()) gx = num_sms();             // one 512-thread CTA per SM: a single wave, one TMEM drain each
     rc = enc_tc_bwd_launch(P, gx, st);
     if (rc != VIPSY_OK) return rc;
   } else {
