@@ -141,3 +141,27 @@ def test_vaeirt_fused_encoder_matches_autograd_path(ops):
     assert abs(out[True][0] - out[False][0]) <= 2e-6 * abs(out[False][0])
     for n, gr in out[False][1].items():
         _close(out[True][1][n], gr, n, tol=5e-5)
+
+
+def test_vaechodina_fused_encoder_matches_autograd_path(ops):
+    """VaeCHoDina (vi.py:961-981) holds the same NormEncoder for theta: kernels vs torch autograd, one loss_and_grads."""
+    import vipsy_b200 as vb
+    g = torch.Generator().manual_seed(21)
+    K, J, N = 4, 30, 2000
+    q = (torch.rand(K, J, generator=g) < 0.5).float()
+    q[0, q.sum(0) == 0] = 1.0
+    y = (torch.rand(N, J, generator=g) < 0.55).float()
+    y[torch.rand(N, J, generator=g) < 0.1] = float("nan")
+    out = {}
+    for fused in (True, False):
+        vb.clear_param_store()
+        torch.manual_seed(5)
+        m = vb.VaeCHoDina(data=y, q=q, hidden_dim=32, seed=3)
+        m.fused_encoder = fused
+        loss, sites = m.loss_and_grads(vb.TraceEnum_ELBO(2))
+        torch.cuda.synchronize()
+        out[fused] = (float(loss), {n: p.grad.clone() for n, p, _ in sites})
+    assert abs(out[True][0] - out[False][0]) <= 2e-6 * abs(out[False][0])
+    assert set(out[True][1]) == set(out[False][1])
+    for n, gr in out[False][1].items():
+        _close(out[True][1][n], gr, n, tol=5e-5)

@@ -117,6 +117,7 @@ class BasePsy(nn.Module):               # vi.py:521-533
         self._sparse = self._n_missing > 0.5 * self._codes.numel()
         self._obs_csr = None          # CSR of the observed cells, built on first use (K = 1, S = 1 path)
         self._enc_x_full = None       # encoder input of the full batch (NaN -> -1), built on first use
+        self._x_tiles, self._x_tiles_tried = None, False      # resident operand tiles of the encoder kernels
         self._seed, self._calls = int(seed), 0
         # device-resident RNG state (SVI(cuda_graph=True)): the noise call counter is a device scalar and the
         # minibatch is drawn with graph-safe torch ops, so a captured iteration differs on every replay
@@ -168,6 +169,28 @@ class BasePsy(nn.Module):               # vi.py:521-533
             return self._enc_x_full
         x = self._data_dev[idx]
         return torch.where(torch.isnan(x), torch.full_like(x, -1.0), x)      # vi.py:679-682
+
+    def _norm_encoder_kernels(self, idx):
+        """``NormEncoder`` (vi.py:417-435) on this batch through the CUDA kernels (csrc/enc_norm*.cu): no fp32 input
+        matrix, no stored hidden activations, deterministic weight gradients.  Returns mu [B, 1], sigma [B, 1] and
+        ``backward(d_mu, d_sigma, weight)`` that accumulates the gradients of the six encoder tensors."""
+        enc = self.encoder
+        if idx is None and self._x_tiles is None and not self._x_tiles_tried:
+            self._x_tiles_tried = True                  # full batch: resident operand tiles, built once
+            self._x_tiles = ops.norm_encoder_pack_tiles(self._codes)
+        xt = self._x_tiles if idx is None else None
+        mu, sigma, pre = ops.norm_encoder_forward(self._codes, enc, idx, x_tiles=xt)
+
+        def backward(d_mu, d_sigma, w):
+            g = ops.norm_encoder_backward(self._codes, enc, sigma, pre, d_mu, d_sigma, idx, grad_scale=w, x_tiles=xt)
+            for n, p in enc.named_parameters():
+                _accum(p, g[n])
+        return mu.unsqueeze(1), sigma.unsqueeze(1), backward
+
+    def _norm_encoder_fusable(self) -> bool:
+        return (getattr(self, "fused_encoder", False) and isinstance(self.encoder, NormEncoder)
+                and self.encoder.fc21.out_features == 1
+                and self.encoder.fc1.out_features <= ops.NORM_ENCODER_MAX_HIDDEN)
 
     def _finish(self, loss: torch.Tensor, sites: List[Site]):
         """Person-sharded jobs: all-reduce the loss and every replicated parameter's gradient."""
@@ -358,26 +381,15 @@ class VaeIRT(BaseIRT):                  # vi.py:659-693
         enc = NormEncoder if self.x_feature == 1 else MvnEncoder
         self.encoder = enc(self.item_size, self.x_feature, hidden_dim).to(self.device)
         self.fused_encoder = True       # K = 1: encoder forward / backward as CUDA kernels (False: torch autograd)
-        self._x_tiles, self._x_tiles_tried = None, False
 
     def _guide(self, idx, B):
         get_param_store().register_module("encoder", self.encoder)
         sites = [(f"encoder$$${n}", p, None) for n, p in self.encoder.named_parameters()]
-        if self.x_feature == 1 and self.fused_encoder and self.encoder.fc1.out_features <= ops.NORM_ENCODER_MAX_HIDDEN:
-            # NormEncoder evaluated by the CUDA kernels on the response codes (csrc/enc_norm.cu): no fp32 input
-            # matrix, no stored hidden activations, deterministic weight gradients
-            enc = self.encoder
-            if idx is None and self._x_tiles is None and not self._x_tiles_tried:
-                self._x_tiles_tried = True              # full batch: resident operand tiles, built once
-                self._x_tiles = ops.norm_encoder_pack_tiles(self._codes)
-            xt = self._x_tiles if idx is None else None
-            mu, sigma, pre = ops.norm_encoder_forward(self._codes, enc, idx, x_tiles=xt)
+        if self.x_feature == 1 and self._norm_encoder_fusable():
+            mu, sigma, enc_backward = self._norm_encoder_kernels(idx)
 
             def backward(r, w):
-                g = ops.norm_encoder_backward(self._codes, enc, sigma, pre, r["d_mu"], r["d_sigma"], idx, grad_scale=w,
-                                              x_tiles=xt)
-                for n, p in enc.named_parameters():
-                    _accum(p, g[n])
+                enc_backward(r["d_mu"], r["d_sigma"], w)
             return dict(mu=mu, sigma=sigma), backward, sites
         x_loc, x_sc = self.encoder(self._encoder_input(idx))
         if self.x_feature == 1:
@@ -618,9 +630,14 @@ class VaeCHoDina(VCHoDina):             # vi.py:961-981
     def __init__(self, hidden_dim=64, *args, **kwargs):
         super().__init__(*args, **kwargs)
         self.encoder = NormEncoder(self.item_size, 1, hidden_dim).to(self.device)
+        self.fused_encoder = True       # encoder forward / backward as CUDA kernels (False: torch autograd)
 
     def _theta(self, idx):
         get_param_store().register_module("encoder", self.encoder)
+        sites = [(f"encoder$$${n}", p, None) for n, p in self.encoder.named_parameters()]
+        if self._norm_encoder_fusable():
+            mu, sigma, enc_backward = self._norm_encoder_kernels(idx)
+            return mu, sigma, (lambda r, w: enc_backward(r["d_mu"], r["d_sigma"], w)), sites
         loc, sc = self.encoder(self._encoder_input(idx))
 
         def backward(r, w):
