@@ -120,3 +120,49 @@ def test_vaeccdm_kernel_vs_reference_model(ops, gm):
     gmax = max(float(c.g(f"encoder$$${n}").abs().max()) for n, _ in enc.named_parameters())
     for n, p in enc.named_parameters():
         assert float((p.grad.double() - c.g(f"encoder$$${n}").double()).abs().max()) <= 5e-4 * gmax, n
+
+
+@pytest.mark.parametrize("tc", [True, False])
+def test_vaeirt_k1_encoder_kernels_vs_reference_model(ops, gm, tc):
+    """VaeIRT, K = 1 (vi.py:673-684): NormEncoder kernels -> ELBO kernel -> encoder backward kernels, against the
+    loss and gradients the reference's own guide + model produced (encoder weights included)."""
+    from vipsy_b200.models import NormEncoder
+    key = "vaeirt_irt_3pl_k1_S2"
+    c = Case(gm, key)
+    enc = c.encoder(NormEncoder, c.y.shape[1], 1, 5).cuda()
+    codes = codes_from_float(c.y).cuda()
+    mu, sigma, pre = ops.norm_encoder_forward(codes, enc, tensor_cores=tc)
+    a, b, cc, dd = irt_items(c, "irt_3pl")
+    r = ops.irt_elbo_grad(codes, mu.reshape(-1, 1), sigma=sigma.reshape(-1, 1), eps=cu(c.noise("x")), a=cu(a), b=cu(b),
+                          c=cu(cc), d=cu(dd), model="irt_3pl")
+    close(r["loss"].cpu(), c.loss, f"{key} loss")
+    close(r["d_b"].cpu(), c.g("b"), f"{key} b")
+    close(r["d_a"].cpu(), c.g("a"), f"{key} a")
+    close(r["d_c"].cpu() * cc * (1 - cc), c.g("c"), f"{key} c")
+    g = ops.norm_encoder_backward(codes, enc, sigma, pre, r["d_mu"].reshape(-1), r["d_sigma"].reshape(-1), tensor_cores=tc)
+    for n, _ in enc.named_parameters():
+        close(g[n].cpu(), c.g(f"encoder$$${n}"), f"{key} encoder {n}", 5e-4)
+
+
+def test_vaechodina_encoder_kernels_vs_reference_model(ops, gm):
+    """VaeCHoDina (vi.py:961-981), subsampled: theta encoder kernels (minibatch through idx) around the enumeration
+    kernel, against the reference's own loss and gradients."""
+    from vipsy_b200.models import NormEncoder
+    key = "vaechodina_sub9"
+    c = Case(gm, key)
+    q = T(gm["cdm/q"])
+    enc = c.encoder(NormEncoder, c.y.shape[1], 1, 5).cuda()
+    codes = codes_from_float(c.y).cuda()
+    idx = cu(c.idx)
+    mu, sigma, pre = ops.norm_encoder_forward(codes, enc, idx)
+    gg, s = torch.sigmoid(c.u("g")), torch.sigmoid(c.u("s"))
+    lam1 = c.u("lam1").exp()
+    r = ops.cdm_enum_elbo_grad(codes, q.cuda(), gg.cuda(), s.cuda(), lam0=cu(c.u("lam0")), lam1=cu(lam1),
+                               mu=mu.reshape(-1, 1), sigma=sigma.reshape(-1, 1), eps=cu(c.noise("theta")), idx=idx,
+                               scale=c.scale)
+    close(r["loss"].cpu(), c.loss, f"{key} loss")
+    close(r["d_lam1"].cpu() * lam1, c.g("lam1"), f"{key} lam1")
+    close(r["d_g"].cpu() * gg * (1 - gg), c.g("g"), f"{key} g")
+    g = ops.norm_encoder_backward(codes, enc, sigma, pre, r["d_mu"].reshape(-1), r["d_sigma"].reshape(-1), idx)
+    for n, _ in enc.named_parameters():
+        close(g[n].cpu(), c.g(f"encoder$$${n}"), f"{key} encoder {n}", 5e-4)
