@@ -334,8 +334,9 @@ int vipsy_adam_step(const VipsyAdamTensor* tensors_host, int32_t n_tensors, cons
  * takes the kernel's d_mu / d_sigma and produces the gradients of all six encoder tensors (d x is never
  * needed), deterministic: per-CTA partial rows summed in a fixed order with fp64 accumulation.  The fp32
  * response matrix and the hidden activations of the torch formulation are never materialised.
- * n_hidden <= 64 (the reference's default hidden_dim, vi.py:661); any n_items.  J <= 127: both products run on
- * the tensor cores (tcgen05, 3-term bf16 split of the fp32 factor, fp32 accumulation in TMEM); else FFMA2 tiles.
+ * n_hidden <= 64 (the reference's default hidden_dim, vi.py:661); any n_items.  J <= 127 (J <= 255 with x_tiles):
+ * both products run on the tensor cores (tcgen05, 3-term bf16 split of the fp32 factor, fp32 accumulation in
+ * TMEM); else FFMA2 tiles.
  * ---------------------------------------------------------------------- */
 typedef struct VipsyNormEncoderArgs {
   int64_t n_rows;            /* rows of y                                   */
@@ -366,14 +367,15 @@ typedef struct VipsyNormEncoderArgs {
   float* d_b22;              /* [1]                                         */
   void* workspace;           /* backward: vipsy_norm_encoder_workspace_bytes */
   size_t workspace_bytes;
-  const void* x_tiles;       /* optional (idx == NULL, batch == n_rows, J <= 127): the response matrix as resident
+  const void* x_tiles;       /* optional (idx == NULL, batch == n_rows, J <= 255): the response matrix as resident
                                 bf16 operand tiles from vipsy_norm_encoder_pack_tiles -- fetched with one bulk copy
                                 per 128-person tile instead of being expanded from the codes in every call */
 } VipsyNormEncoderArgs;
-/* bytes of the tile buffer for n_rows persons; 0 if J > 127 */
+/* bytes of the tile buffer for n_rows persons (32 KB per 128 persons, 64 KB when J > 127); 0 if J > 255 */
 size_t vipsy_norm_encoder_tiles_bytes(int64_t n_rows, int32_t n_items);
 /* y (n_rows x y_row_stride codes) -> tiles: per 128 persons one 32 KB block in the shared-memory operand layout
- * (8 x 8 bf16 core matrices, item slot J = 1 for existing persons).  Done once: the matrix is constant. */
+ * (8 x 8 bf16 core matrices, 128 or 256 item slots, slot J = 1 for existing persons).  Done once: the matrix is
+ * constant. */
 int vipsy_norm_encoder_pack_tiles(const uint8_t* y, int64_t n_rows, int32_t n_items, int64_t y_row_stride,
                                   void* tiles, void* stream);
 size_t vipsy_norm_encoder_workspace_bytes(const VipsyNormEncoderArgs* args);

@@ -49,6 +49,9 @@ def _close(got, ref, name, tol=2e-5):
     (40000, 64, 64, 0.05, None),     # more tiles than CTAs: persistent loop
     (5000, 127, 64, 0.1, None),      # widest tensor-core shape (item slot 127 carries the bias column)
     (3000, 16, 8, 0.1, None),
+    (2500, 200, 64, 0.3, None),      # two 128-slot item blocks: tensor cores through the resident tiles only
+    (1111, 255, 48, 0.1, None),      # widest resident shape (slot 255 = bias column)
+    (900, 128, 64, 0.0, None),
 ])
 @pytest.mark.parametrize("tc", [True, False])
 def test_norm_encoder_forward_backward(ops, B, J, H, missing, sub, tc):
@@ -98,7 +101,8 @@ def test_norm_encoder_resident_tiles_equal_on_the_fly(ops):
     assert torch.equal(out[0][0], out[1][0]) and torch.equal(out[0][1], out[1][1]) and torch.equal(out[0][2], out[1][2])
     for n in out[0][3]:
         assert torch.equal(out[0][3][n], out[1][3][n]), n
-    assert ops.norm_encoder_pack_tiles(torch.zeros((10, 200), dtype=torch.uint8, device="cuda")) is None
+    assert ops.norm_encoder_pack_tiles(torch.zeros((10, 256), dtype=torch.uint8, device="cuda")) is None
+    assert ops.norm_encoder_pack_tiles(torch.zeros((300, 200), dtype=torch.uint8, device="cuda")).numel() == 3 * 65536
 
 
 def test_norm_encoder_deterministic(ops):

@@ -340,16 +340,16 @@ using namespace vipsy;
 extern "C" {
 
 size_t vipsy_norm_encoder_tiles_bytes(int64_t n_rows, int32_t n_items) {
-  if (n_rows <= 0 || !enc_tc_supported(1, n_items)) return 0;
-  return (size_t)((n_rows + 127) / 128) * kEncTileBytes;
+  if (n_rows <= 0 || !enc_tc_resident_supported(1, n_items)) return 0;
+  return (size_t)((n_rows + 127) / 128) * enc_tc_tile_bytes(n_items);
 }
 
 int vipsy_norm_encoder_pack_tiles(const uint8_t* y, int64_t n_rows, int32_t n_items, int64_t y_row_stride, void* tiles,
                                   void* stream) {
   VIPSY_REQUIRE(y && tiles && n_rows > 0 && y_row_stride >= n_items, VIPSY_ERR_ARG,
                 "vipsy_norm_encoder_pack_tiles: bad arguments");
-  VIPSY_REQUIRE(enc_tc_supported(1, n_items), VIPSY_ERR_UNSUPPORTED,
-                "vipsy_norm_encoder_pack_tiles: J = %d > 127 has no tensor-core path", n_items);
+  VIPSY_REQUIRE(enc_tc_resident_supported(1, n_items), VIPSY_ERR_UNSUPPORTED,
+                "vipsy_norm_encoder_pack_tiles: J = %d > 255 has no tensor-core path", n_items);
   VIPSY_REQUIRE((reinterpret_cast<uintptr_t>(tiles) & 127) == 0, VIPSY_ERR_ARG,
                 "vipsy_norm_encoder_pack_tiles: tiles must be 128-byte aligned");
   return enc_tc_pack_launch(y, n_rows, n_items, y_row_stride, tiles, (cudaStream_t)stream);
@@ -371,7 +371,8 @@ int vipsy_norm_encoder_forward(const VipsyNormEncoderArgs* a, void* stream) {
     attr = true;
   }
   const EncParams P = enc_params(a);
-  if (enc_tc_supported(P.H, P.J) && !(a->flags & 1) && (reinterpret_cast<uintptr_t>(a->pre) & 15) == 0)
+  if ((P.xtiles ? enc_tc_resident_supported(P.H, P.J) : enc_tc_supported(P.H, P.J)) && !(a->flags & 1) &&
+      (reinterpret_cast<uintptr_t>(a->pre) & 15) == 0)
     return enc_tc_fwd_launch(P, (cudaStream_t)stream);
   enc_norm_fwd_kernel<<<enc_grid_x(a->batch), kEncThreads, kEncFwdSmem, (cudaStream_t)stream>>>(P);
   VIPSY_CUDA_CHECK(cudaGetLastError());
@@ -404,7 +405,8 @@ int vipsy_norm_encoder_backward(const VipsyNormEncoderArgs* a, void* stream) {
   EncParams P = enc_params(a);
   P.partial = reinterpret_cast<float*>(a->workspace);
   int gx = enc_grid_x(a->batch);
-  if (enc_tc_supported(H, J) && !(a->flags & 1) && (reinterpret_cast<uintptr_t>(a->pre) & 15) == 0) {
+  if ((P.xtiles ? enc_tc_resident_supported(H, J) : enc_tc_supported(H, J)) && !(a->flags & 1) &&
+      (reinterpret_cast<uintptr_t>(a->pre) & 15) == 0) {
     if (gx > num_sms()) gx = num_sms();             // one 512-thread CTA per SM: a single wave, one TMEM drain each
     rc = enc_tc_bwd_launch(P, gx, st);
     if (rc != VIPSY_OK) return rc;

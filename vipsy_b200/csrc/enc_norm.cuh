@@ -25,9 +25,10 @@ __device__ __forceinline__ void softplus_parts(float x, float& sp, float& sg) {
 
 // tensor-core variants (enc_norm_tc.cu); the partial-row layout and the finalize step are shared
 bool enc_tc_supported(int H, int J);
+bool enc_tc_resident_supported(int H, int J);
+size_t enc_tc_tile_bytes(int J);
 int enc_tc_fwd_launch(const EncParams& P, cudaStream_t st);
 int enc_tc_bwd_launch(const EncParams& P, int grid_x, cudaStream_t st);
 int enc_tc_pack_launch(const uint8_t* y, int64_t n_rows, int J, int64_t ld, void* tiles, cudaStream_t st);
-constexpr size_t kEncTileBytes = 32768;
 
 }  // namespace vipsy

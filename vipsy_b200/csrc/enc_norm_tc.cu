@@ -28,6 +28,10 @@ constexpr int kPitch = kH + 4;               // fp32 [person][hidden] staging ti
 constexpr int kBwdThreads = 512;          // backward: 4 threads per person (16 hidden units each)
 
 bool enc_tc_supported(int H, int J) { return H >= 1 && H <= kH && J >= 1 && J <= 127; }
+// with resident operand tiles the item axis may span two 128-slot blocks (slot J is the ones column)
+bool enc_tc_resident_supported(int H, int J) { return H >= 1 && H <= kH && J >= 1 && J <= 255; }
+static int enc_tc_slots(int J) { return J <= 127 ? 128 : 256; }
+size_t enc_tc_tile_bytes(int J) { return (size_t)kTB * enc_tc_slots(J) * 2; }
 
 __device__ __forceinline__ uint32_t bf16_bits(float v) {
   return (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(v));
@@ -126,17 +130,14 @@ __device__ __forceinline__ void tc_store_x(unsigned char* Xt, uint32_t RS, const
 
 // ---- resident operand tiles ---------------------------------------------------------------------------------
 // The response matrix never changes between SVI steps, so its bf16 operand tiles can live in HBM in exactly the
-// shared-memory layout (per 128 persons: 16 row blocks x 16 chunks x 8 rows x 8 bf16 = 32 KB, item slot J = 1 for
-// existing persons).  A tile then reaches shared memory by ONE bulk asynchronous copy that completes on an mbarrier.
-constexpr uint32_t kTileBytes = (uint32_t)kEncTileBytes;
-constexpr uint32_t kRSTile = (kTB / 8) * kCS;     // 2048: row-block pitch of a resident tile (128 item slots)
-
+// shared-memory layout (per 128 persons: 16 row blocks x NS/8 chunks x 8 rows x 8 bf16, NS = 128 or 256 item slots = 32 / 64 KB, item
+// slot J = 1 for existing persons).  A tile then reaches shared memory by ONE bulk asynchronous copy that completes on an mbarrier.
 __global__ void __launch_bounds__(256) enc_tc_pack_kernel(const uint8_t* __restrict__ y, int64_t n_rows, int J,
-                                                          int64_t ld, unsigned char* __restrict__ tiles) {
+                                                          int64_t ld, unsigned char* __restrict__ tiles, int NS) {
   const int64_t tile0 = (int64_t)blockIdx.x * kTB;
-  unsigned char* out = tiles + (size_t)blockIdx.x * kTileBytes;
-  for (int id = threadIdx.x; id < (int)(kTileBytes / 16); id += 256) {       // 16-byte chunk id = rb*128 + ch*8 + pp
-    const int rb = id >> 7, ch = (id >> 3) & 15, pp = id & 7;
+  unsigned char* out = tiles + (size_t)blockIdx.x * ((size_t)kTB * NS * 2);
+  for (int id = threadIdx.x; id < 16 * NS; id += 256) {        // 16-byte chunk id = rb * NS + ch * 8 + pp
+    const int rb = id / NS, rem = id - rb * NS, ch = rem >> 3, pp = rem & 7;
     const int64_t r = tile0 + rb * 8 + pp;
     uint32_t w[2] = {0u, 0u};
     if (r < n_rows) {
@@ -157,7 +158,8 @@ __global__ void __launch_bounds__(256) enc_tc_pack_kernel(const uint8_t* __restr
 
 int enc_tc_pack_launch(const uint8_t* y, int64_t n_rows, int J, int64_t ld, void* tiles, cudaStream_t st) {
   const int64_t n_tiles = (n_rows + kTB - 1) / kTB;
-  enc_tc_pack_kernel<<<(unsigned)n_tiles, 256, 0, st>>>(y, n_rows, J, ld, reinterpret_cast<unsigned char*>(tiles));
+  enc_tc_pack_kernel<<<(unsigned)n_tiles, 256, 0, st>>>(y, n_rows, J, ld, reinterpret_cast<unsigned char*>(tiles),
+                                                        enc_tc_slots(J));
   VIPSY_CUDA_CHECK(cudaGetLastError());
   return VIPSY_OK;
 }
@@ -172,7 +174,10 @@ __device__ __forceinline__ void bulk_load(unsigned char* dst_smem, const unsigne
 }
 
 // ------------------------------------------------------------------------------------------------ forward
-__global__ void __launch_bounds__(kThreads, 2) enc_tc_fwd_kernel(const EncParams P, const int JP) {
+template <int NS>
+__global__ void __launch_bounds__(kThreads, NS == 128 ? 2 : 1) enc_tc_fwd_kernel(const EncParams P, const int JP) {
+  constexpr uint32_t kRSTile = (NS / 8) * kCS;    // row-block pitch of a resident tile
+  constexpr uint32_t kTileBytes = kTB * NS * 2;
   extern __shared__ __align__(1024) unsigned char smem[];
   __shared__ uint64_t bar, barx;
   __shared__ uint32_t tmem_base_sm;
@@ -180,7 +185,7 @@ __global__ void __launch_bounds__(kThreads, 2) enc_tc_fwd_kernel(const EncParams
   __shared__ float2 part[2][kTB];                 // per column half: partial (mu, log sigma) of each person
   const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
   const int n_chunks = JP >> 3;
-  const bool resident = P.xtiles != nullptr;
+  const bool resident = NS == 256 || P.xtiles != nullptr;          // two slot blocks exist only as resident tiles
   const uint32_t RS = (uint32_t)n_chunks * kCS;   // row-block pitch of the W tiles (8 row blocks each)
   const uint32_t RSx = resident ? kRSTile : RS;   // ... and of the code tile (16 row blocks)
   unsigned char* Xt = smem;
@@ -224,13 +229,13 @@ __global__ void __launch_bounds__(kThreads, 2) enc_tc_fwd_kernel(const EncParams
   if (resident) {
     if (t == 0) bulk_load(Xt, P.xtiles + (size_t)blockIdx.x * kTileBytes, kTileBytes, &barx);
   } else {
-    tc_load_codes<8>(wd, P, (int64_t)blockIdx.x * kTB, 2 * n_chunks, aligned);
+    if constexpr (NS == 128) tc_load_codes<8>(wd, P, (int64_t)blockIdx.x * kTB, 2 * n_chunks, aligned);
   }
   uint32_t phase = 0;
   for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const int64_t tile0 = tile * kTB;
     if (!resident) {
-      tc_store_x<8>(Xt, RS, wd, 2 * n_chunks, P.J, tile0, INT64_MAX);
+      if constexpr (NS == 128) tc_store_x<8>(Xt, RS, wd, 2 * n_chunks, P.J, tile0, INT64_MAX);
       umma::fence_proxy_async();
     }
     __syncthreads();
@@ -248,8 +253,10 @@ __global__ void __launch_bounds__(kThreads, 2) enc_tc_fwd_kernel(const EncParams
       }
       umma::commit(&bar);
     }
-    if (!resident && tile + gridDim.x < n_tiles)
-      tc_load_codes<8>(wd, P, (tile + gridDim.x) * kTB, 2 * n_chunks, aligned);
+    if constexpr (NS == 128) {
+      if (!resident && tile + gridDim.x < n_tiles)
+        tc_load_codes<8>(wd, P, (tile + gridDim.x) * kTB, 2 * n_chunks, aligned);
+    }
     umma::mbar_wait(&bar, phase);
     phase ^= 1u;
     umma::fence_after_sync();
@@ -311,7 +318,10 @@ __global__ void __launch_bounds__(kThreads, 2) enc_tc_fwd_kernel(const EncParams
 }
 
 // ------------------------------------------------------------------------------------------------ backward
+template <int NS>
 __global__ void __launch_bounds__(kBwdThreads) enc_tc_bwd_kernel(const EncParams P) {
+  constexpr uint32_t kTileBytes = kTB * NS * 2;
+  constexpr int MB = NS / 128;                    // 128-slot blocks of the item axis = accumulators in TMEM
   extern __shared__ __align__(1024) unsigned char smem[];
   __shared__ uint64_t bar, barx;
   __shared__ uint32_t tmem_base_sm;
@@ -319,13 +329,13 @@ __global__ void __launch_bounds__(kBwdThreads) enc_tc_bwd_kernel(const EncParams
   __shared__ float red[2][4][kH];                 // end of kernel: [w21 | w22][warp of the half][h]
   __shared__ float wh[2][kH];                     // fc21.weight | fc22.weight, zero beyond H
   const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
-  constexpr uint32_t RSx = (kTB / 8) * kCS;       // code tile: 128 persons x 128 item slots (item J = ones column)
+  constexpr uint32_t RSx = (NS / 8) * kCS;        // code tile: 128 persons x NS item slots (item J = ones column)
   constexpr uint32_t RSd = (kH / 8) * kCS;        // dpre tiles: 128 persons x 64 hidden
   unsigned char* Xt = smem;
   unsigned char* Dt[3] = {Xt + 16 * RSx, Xt + 16 * RSx + 16 * RSd, Xt + 16 * RSx + 32 * RSd};
   float* pb0 = reinterpret_cast<float*>(Xt + 16 * RSx + 48 * RSd);     // 2 x [128][kPitch]: `pre` rows, this tile / next
   const bool aligned = ((reinterpret_cast<uintptr_t>(P.y) | (uintptr_t)P.ld) & 3) == 0;
-  const bool resident = P.xtiles != nullptr;
+  const bool resident = NS == 256 || P.xtiles != nullptr;
   const int p = t & (kTB - 1), hq = t >> 7;       // this thread: person p, hidden chunks hc = hq + 4 q (8 units each)
 
   if (t < 2 * kH) {
@@ -333,7 +343,7 @@ __global__ void __launch_bounds__(kBwdThreads) enc_tc_bwd_kernel(const EncParams
     wh[t >> 6][h] = h < P.H ? __ldg((t >> 6 ? P.w22 : P.w21) + h) : 0.0f;
   }
   for (int e = t; e < 2 * kTB * kPitch; e += kBwdThreads) pb0[e] = 0.0f;        // columns beyond H stay 0
-  if (warp == 0) umma::tmem_alloc(&tmem_base_sm, kTmemCols);
+  if (warp == 0) umma::tmem_alloc(&tmem_base_sm, MB * kTmemCols);
   if (t == 0) {
     umma::mbar_init(&bar, 1);
     umma::mbar_init(&barx, 1);
@@ -404,7 +414,7 @@ __global__ void __launch_bounds__(kBwdThreads) enc_tc_bwd_kernel(const EncParams
     if (resident) {
       if (t == 0) bulk_load(Xt, P.xtiles + (size_t)blockIdx.x * kTileBytes, kTileBytes, &barx);
     } else {
-      tc_load_codes<16>(wd, P, (int64_t)blockIdx.x * kTB, 32, aligned);
+      if constexpr (NS == 128) tc_load_codes<16>(wd, P, (int64_t)blockIdx.x * kTB, 32, aligned);
     }
     fetch_pre((int64_t)blockIdx.x * kTB, 0);
     load_heads((int64_t)blockIdx.x * kTB);
@@ -438,7 +448,9 @@ __global__ void __launch_bounds__(kBwdThreads) enc_tc_bwd_kernel(const EncParams
       pv[q][0] = u0.x; pv[q][1] = u0.y; pv[q][2] = u0.z; pv[q][3] = u0.w;
       pv[q][4] = u1.x; pv[q][5] = u1.y; pv[q][6] = u1.z; pv[q][7] = u1.w;
     }
-    if (!resident) tc_store_x<16>(Xt, RSx, wd, 32, P.J, tile0, P.B);
+    if constexpr (NS == 128) {
+      if (!resident) tc_store_x<16>(Xt, RSx, wd, 32, P.J, tile0, P.B);
+    }
     if (hq == 0) { s_gm += a; s_gl += b; }
 #pragma unroll
     for (int q = 0; q < 2; ++q) {
@@ -469,19 +481,24 @@ __global__ void __launch_bounds__(kBwdThreads) enc_tc_bwd_kernel(const EncParams
       }
       umma::fence_after_sync();
       for (int ks = 0; ks < kTB / 16; ++ks) {
-        const uint64_t da = umma::make_desc(sX + ks * 2 * RSx, RSx, kCS);
 #pragma unroll
-        for (int term = 0; term < 3; ++term) {
-          umma::mma_f16_ss(tmem, da, umma::make_desc(sD[term] + ks * 2 * RSd, RSd, kCS), idesc, acc);
-          acc = 1;
+        for (int mb = 0; mb < MB; ++mb) {           // item-slot block mb: 16 core-matrix columns further along
+          const uint64_t da = umma::make_desc(sX + ks * 2 * RSx + mb * 16 * kCS, RSx, kCS);
+#pragma unroll
+          for (int term = 0; term < 3; ++term)        // only the very first MMA of an accumulator overwrites it
+            umma::mma_f16_ss(tmem + mb * kTmemCols, da, umma::make_desc(sD[term] + ks * 2 * RSd, RSd, kCS), idesc,
+                             (acc | (uint32_t)ks | (uint32_t)term) != 0u ? 1u : 0u);
         }
       }
+      acc = 1;
       umma::commit(&bar);
     }
     pending = true;
     nb ^= 1;
     if (has_next) {
-      if (!resident) tc_load_codes<16>(wd, P, (tile + gridDim.x) * kTB, 32, aligned);
+      if constexpr (NS == 128) {
+        if (!resident) tc_load_codes<16>(wd, P, (tile + gridDim.x) * kTB, 32, aligned);
+      }
       load_heads((tile + gridDim.x) * kTB);
     }
   }
@@ -493,15 +510,18 @@ __global__ void __launch_bounds__(kBwdThreads) enc_tc_bwd_kernel(const EncParams
   float* tail = row + (size_t)P.H * P.J;
   if (warp < 8) {
     const int quad = warp & 3, half = warp >> 2;
-    float v[32];
-    umma::tmem_ld32(tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)(half * 32), v);
-    const int j = quad * 32 + lane;
 #pragma unroll
-    for (int c = 0; c < 32; ++c) {
-      const int h = half * 32 + c;
-      if (h < P.H) {
-        if (j < P.J) row[(size_t)h * P.J + j] = v[c];
-        else if (j == P.J) tail[h] = v[c];
+    for (int mb = 0; mb < MB; ++mb) {
+      float v[32];
+      umma::tmem_ld32(tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)(mb * kTmemCols + half * 32), v);
+      const int j = mb * 128 + quad * 32 + lane;
+#pragma unroll
+      for (int c = 0; c < 32; ++c) {
+        const int h = half * 32 + c;
+        if (h < P.H) {
+          if (j < P.J) row[(size_t)h * P.J + j] = v[c];
+          else if (j == P.J) tail[h] = v[c];
+        }
       }
     }
   }
@@ -528,38 +548,69 @@ __global__ void __launch_bounds__(kBwdThreads) enc_tc_bwd_kernel(const EncParams
     tail[2 * P.H] = (gm[0] + gm[1]) + (gm[2] + gm[3]);
     tail[3 * P.H + 1] = (gl[0] + gl[1]) + (gl[2] + gl[3]);
   }
-  if (warp == 0) umma::tmem_dealloc(tmem, kTmemCols);
+  if (warp == 0) umma::tmem_dealloc(tmem, MB * kTmemCols);
 }
 
-static size_t tc_fwd_smem(int JP, bool resident) {
+static size_t tc_fwd_smem(int JP, bool resident, int NS) {
   const size_t RS = (size_t)(JP / 8) * kCS;
-  return 16 * (resident ? (size_t)kRSTile : RS) + 24 * RS + (size_t)kTB * kPitch * 4 + 1024;
+  return 16 * (resident ? (size_t)(NS / 8) * kCS : RS) + 24 * RS + (size_t)kTB * kPitch * 4 + 1024;
 }
-constexpr size_t kTcBwdSmem = 16 * (kTB / 8) * kCS + 3 * 16 * (kH / 8) * kCS + 2 * (size_t)kTB * kPitch * 4 + 1024;
+static size_t tc_bwd_smem(int NS) {
+  return 16 * (size_t)(NS / 8) * kCS + 3 * 16 * (kH / 8) * kCS + 2 * (size_t)kTB * kPitch * 4 + 1024;
+}
 
 int enc_tc_fwd_launch(const EncParams& P, cudaStream_t st) {
   const int JP = (P.J + 1 + 15) / 16 * 16;        // + the ones column that carries fc1.bias
-  static size_t attr = 0;
-  const size_t smem = tc_fwd_smem(JP, P.xtiles != nullptr);
-  if (smem > attr) {
-    VIPSY_CUDA_CHECK(cudaFuncSetAttribute(enc_tc_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr = smem;
+  const int NS = enc_tc_slots(P.J);
+  const bool resident = P.xtiles != nullptr;
+  if (NS == 256 && !resident) {
+    set_error("enc_tc_fwd_launch: J > 127 needs resident operand tiles");
+    return VIPSY_ERR_UNSUPPORTED;
   }
+  const size_t smem = tc_fwd_smem(JP, resident, NS);
+  static size_t attr[2] = {0, 0};
   const int64_t tiles = (P.B + kTB - 1) / kTB;
-  const int64_t cap = 2 * (int64_t)num_sms();
-  enc_tc_fwd_kernel<<<(int)(tiles < cap ? tiles : cap), kThreads, smem, st>>>(P, JP);
+  if (NS == 128) {
+    if (smem > attr[0]) {
+      VIPSY_CUDA_CHECK(cudaFuncSetAttribute(enc_tc_fwd_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      attr[0] = smem;
+    }
+    const int64_t cap = 2 * (int64_t)num_sms();
+    enc_tc_fwd_kernel<128><<<(int)(tiles < cap ? tiles : cap), kThreads, smem, st>>>(P, JP);
+  } else {
+    if (smem > attr[1]) {
+      VIPSY_CUDA_CHECK(cudaFuncSetAttribute(enc_tc_fwd_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      attr[1] = smem;
+    }
+    const int64_t cap = (int64_t)num_sms();        // one CTA per SM: 64 KB code tile + up to 96 KB of W tiles
+    enc_tc_fwd_kernel<256><<<(int)(tiles < cap ? tiles : cap), kThreads, smem, st>>>(P, JP);
+  }
   VIPSY_CUDA_CHECK(cudaGetLastError());
   return VIPSY_OK;
 }
 
 int enc_tc_bwd_launch(const EncParams& P, int grid_x, cudaStream_t st) {
-  static bool attr = false;
-  if (!attr) {
-    VIPSY_CUDA_CHECK(cudaFuncSetAttribute(enc_tc_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          (int)kTcBwdSmem));
-    attr = true;
+  const int NS = enc_tc_slots(P.J);
+  if (NS == 256 && P.xtiles == nullptr) {
+    set_error("enc_tc_bwd_launch: J > 127 needs resident operand tiles");
+    return VIPSY_ERR_UNSUPPORTED;
   }
-  enc_tc_bwd_kernel<<<grid_x, kBwdThreads, kTcBwdSmem, st>>>(P);
+  static bool attr[2] = {false, false};
+  if (NS == 128) {
+    if (!attr[0]) {
+      VIPSY_CUDA_CHECK(cudaFuncSetAttribute(enc_tc_bwd_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            (int)tc_bwd_smem(128)));
+      attr[0] = true;
+    }
+    enc_tc_bwd_kernel<128><<<grid_x, kBwdThreads, tc_bwd_smem(128), st>>>(P);
+  } else {
+    if (!attr[1]) {
+      VIPSY_CUDA_CHECK(cudaFuncSetAttribute(enc_tc_bwd_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            (int)tc_bwd_smem(256)));
+      attr[1] = true;
+    }
+    enc_tc_bwd_kernel<256><<<grid_x, kBwdThreads, tc_bwd_smem(256), st>>>(P);
+  }
   VIPSY_CUDA_CHECK(cudaGetLastError());
   return VIPSY_OK;
 }

@@ -474,7 +474,7 @@ NORM_ENCODER_MAX_HIDDEN = 64
 
 def norm_encoder_pack_tiles(y: torch.Tensor) -> Optional[torch.Tensor]:
     """Resident bf16 operand tiles of the (constant) response matrix for the tensor-core encoder kernels, or None
-    when the shape has no tensor-core path (J > 127).  32 KB per 128 persons; build once."""
+    when the shape has no tensor-core path (J > 255).  32 KB per 128 persons (64 KB when J > 127); build once."""
     if not y.is_cuda or y.dtype != torch.uint8 or y.dim() != 2 or y.stride(1) != 1:
         raise ValueError("y must be a CUDA uint8 code matrix (see pack_responses)")
     L = N.lib()
