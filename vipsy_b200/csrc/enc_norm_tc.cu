@@ -193,16 +193,29 @@ __global__ void __launch_bounds__(kThreads, NS == 128 ? 2 : 1) enc_tc_fwd_kernel
   float* ps = reinterpret_cast<float*>(Xt + 16 * RSx + 24 * RS);     // [128][kPitch] pre tile on its way to global memory
   const bool aligned = ((reinterpret_cast<uintptr_t>(P.y) | (uintptr_t)P.ld) & 3) == 0;
 
-  for (int e = t; e < kH * JP; e += kThreads) {   // fc1.weight -> three bf16 operand tiles, once per CTA
-    const int h = e / JP, j = e - h * JP;
-    float v = 0.0f;                               // item slot J multiplies the ones column: the bias row
-    if (h < P.H) v = j < P.J ? __ldg(P.w1 + (size_t)h * P.J + j) : (j == P.J ? __ldg(P.b1 + h) : 0.0f);
-    uint32_t a, b, c;
-    split3(v, a, b, c);
-    const uint32_t o = umma::tile_off(h, j, RS, kCS);
-    *reinterpret_cast<uint16_t*>(Wt[0] + o) = (uint16_t)a;
-    *reinterpret_cast<uint16_t*>(Wt[1] + o) = (uint16_t)b;
-    *reinterpret_cast<uint16_t*>(Wt[2] + o) = (uint16_t)c;
+  // fc1.weight -> three bf16 operand tiles, once per CTA; eight loads in flight per thread (the CTA's first
+  // MMA waits for this, and a one-tile minibatch launch is nothing but this prologue)
+  for (int e0 = t; e0 < kH * JP; e0 += 8 * kThreads) {
+    float v[8];
+    uint32_t o[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int e = e0 + u * kThreads;
+      const int h = e / JP, j = e - h * JP;
+      v[u] = 0.0f;                                  // item slot J multiplies the ones column: the bias row
+      if (e < kH * JP && h < P.H) v[u] = j < P.J ? __ldg(P.w1 + (size_t)h * P.J + j) : (j == P.J ? __ldg(P.b1 + h) : 0.0f);
+      o[u] = umma::tile_off(h, j, RS, kCS);
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      if (e0 + u * kThreads < kH * JP) {
+        uint32_t a, b, c;
+        split3(v[u], a, b, c);
+        *reinterpret_cast<uint16_t*>(Wt[0] + o[u]) = (uint16_t)a;
+        *reinterpret_cast<uint16_t*>(Wt[1] + o[u]) = (uint16_t)b;
+        *reinterpret_cast<uint16_t*>(Wt[2] + o[u]) = (uint16_t)c;
+      }
+    }
   }
   if (t < 3 * kH) {
     const int h = t & 63, which = t >> 6;
