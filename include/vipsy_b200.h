@@ -326,6 +326,14 @@ typedef struct VipsyAdamTensor {
 int vipsy_adam_step(const VipsyAdamTensor* tensors_host, int32_t n_tensors, const int64_t* step_dev,
                     int32_t zero_grad, void* stream);
 
+/* pyro.plate('data', N, subsample_size=B) (idx = randperm(N)[:B]): B distinct row indices of
+ * [0, n_rows), uniformly distributed over the ordered B-subsets, in ONE launch with the call counter in device
+ * memory (*counter_dev is read, then incremented, by the kernel) -- graph-safe, so a captured SVI iteration draws a
+ * fresh minibatch on every replay.  Deterministic in (seed, counter).  batch <= VIPSY_SAMPLE_MAX_BATCH. */
+enum { VIPSY_SAMPLE_MAX_BATCH = 2048 };
+int vipsy_sample_indices_dev(int64_t* idx_out, int32_t batch, int64_t n_rows, uint64_t seed, uint64_t* counter_dev,
+                             void* stream);
+
 /* ------------------------------------------------------------------------
  * Amortised guide of VaeIRT, K = 1: NormEncoder (vi.py:417-435) evaluated on the stored response codes with the
  * guide's input rule NaN -> -1 (vi.py:679-682):

@@ -128,6 +128,7 @@ SYMBOLS = {
     "vipsy_fill_uniform_dev": (C.c_int, [_p, C.c_int32, C.c_int64, C.c_int32, C.c_uint64, _p, C.c_int64, _p]),
     "vipsy_peer_allreduce": (C.c_int, [_p, C.c_int32, C.c_int32, C.c_int64, C.c_int64, C.c_int32, C.c_int32, _p, _p,
                                        C.c_uint32, _p]),
+    "vipsy_sample_indices_dev": (C.c_int, [_p, C.c_int32, C.c_int64, C.c_uint64, _p, _p]),
     "vipsy_norm_encoder_workspace_bytes": (C.c_size_t, [C.POINTER(NormEncoderArgs)]),
     "vipsy_norm_encoder_tiles_bytes": (C.c_size_t, [C.c_int64, C.c_int32]),
     "vipsy_norm_encoder_pack_tiles": (C.c_int, [_p, C.c_int64, C.c_int32, C.c_int64, _p, _p]),

@@ -401,6 +401,58 @@ __global__ void __launch_bounds__(256) peer_allreduce_kernel(const uint64_t* __r
 
 using namespace vipsy;
 
+// ---------------------------------------------------------------------------
+// Minibatch draw of the `data` plate: B distinct indices of [0, N), one CTA.  Every position owns a Philox stream
+// (position, round); a position whose value already occurs at a LOWER position redraws in the next round, until
+// all are distinct.  The result is invariant under relabelling of the values, hence uniform over ordered
+// B-subsets (what randperm(N)[:B] gives); fixed priority => deterministic.  B <= 2048: the scan is O(B^2 / 1024).
+// ---------------------------------------------------------------------------
+constexpr int kSampleThreads = 1024;
+__global__ void __launch_bounds__(kSampleThreads) sample_indices_kernel(int64_t* __restrict__ out, int B, int64_t N,
+                                                                        uint64_t seed, uint64_t* counter) {
+  __shared__ int64_t cand[VIPSY_SAMPLE_MAX_BATCH];
+  const uint64_t off = *counter;
+  const int t = threadIdx.x;
+  bool redraw[2] = {true, true};
+  for (uint32_t round = 0;; ++round) {
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      const int i = t + q * kSampleThreads;
+      if (i < B && redraw[q]) {
+        const uint4 r = philox_draw(seed ^ 0x9E3779B97F4A7C15ull, off, (uint64_t)i, round);
+        const uint64_t u = ((uint64_t)r.x << 32) | r.y;
+        cand[i] = (int64_t)__umul64hi(u, (uint64_t)N);               // floor(u N / 2^64)
+      }
+    }
+    __syncthreads();
+    int any = 0;
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      const int i = t + q * kSampleThreads;
+      redraw[q] = false;
+      if (i < B) {
+        const int64_t v = cand[i];
+        for (int j = 0; j < i; ++j)
+          if (cand[j] == v) { redraw[q] = true; break; }
+        any |= redraw[q];
+      }
+    }
+    if (!__syncthreads_or(any)) break;                               // also orders the scan before the next draws
+  }
+#pragma unroll
+  for (int q = 0; q < 2; ++q) {
+    const int i = t + q * kSampleThreads;
+    if (i < B) out[i] = cand[i];
+  }
+  if (t == 0) *counter = off + 1;
+}
+static int launch_sample_indices(int64_t* out, int B, int64_t N, uint64_t seed, uint64_t* counter, cudaStream_t st) {
+  if (B == 0) return VIPSY_OK;
+  sample_indices_kernel<<<1, kSampleThreads, 0, st>>>(out, B, N, seed, counter);
+  VIPSY_CUDA_CHECK(cudaGetLastError());
+  return VIPSY_OK;
+}
+
 extern "C" {
 
 int vipsy_abi_version(void) { return VIPSY_ABI_VERSION; }
@@ -502,6 +554,15 @@ int vipsy_fill_uniform_dev(float* out, int32_t S, int64_t B, int32_t K, uint64_t
                            int64_t person_offset, void* stream) {
   VIPSY_REQUIRE(offset_dev, VIPSY_ERR_ARG, "vipsy_fill_uniform_dev: offset_dev is NULL");
   return fill_noise(false, out, S, B, K, seed, 0, person_offset, stream, offset_dev);
+}
+
+int vipsy_sample_indices_dev(int64_t* idx_out, int32_t batch, int64_t n_rows, uint64_t seed, uint64_t* counter_dev,
+                             void* stream) {
+  VIPSY_REQUIRE(idx_out && counter_dev && batch >= 0 && n_rows > 0 && batch <= n_rows, VIPSY_ERR_ARG,
+                "vipsy_sample_indices_dev: bad arguments (batch %d, rows %lld)", batch, (long long)n_rows);
+  VIPSY_REQUIRE(batch <= VIPSY_SAMPLE_MAX_BATCH, VIPSY_ERR_UNSUPPORTED, "vipsy_sample_indices_dev: batch %d > %d", batch,
+                (int)VIPSY_SAMPLE_MAX_BATCH);
+  return launch_sample_indices(idx_out, batch, n_rows, seed, counter_dev, (cudaStream_t)stream);
 }
 
 int vipsy_peer_allreduce(const uint64_t* peer_bufs_dev, int32_t rank, int32_t world, int64_t flag_bytes,

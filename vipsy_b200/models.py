@@ -123,6 +123,7 @@ class BasePsy(nn.Module):               # vi.py:521-533
         # minibatch is drawn with graph-safe torch ops, so a captured iteration differs on every replay
         self._device_rng = False
         self._calls_dev = None
+        self._plate_calls_dev = None  # minibatch-draw counter (ops.sample_indices)
         # optional person sharding (vipsy_b200.dist.attach): this rank holds rows
         # [person_offset, person_offset + sample_size) of a global_size-person job
         self.global_size = self.sample_size
@@ -143,6 +144,10 @@ class BasePsy(nn.Module):               # vi.py:521-533
         if B >= N:
             return None, N, 1.0
         if self._device_rng:          # uniform random B-subset in random order, no host sync (graph-safe)
+            if B <= ops.SAMPLE_MAX_BATCH:         # one launch, counter in device memory
+                if self._plate_calls_dev is None:
+                    self._plate_calls_dev = torch.zeros(1, dtype=torch.int64, device=self.device)
+                return ops.sample_indices(N, B, self._seed ^ (self.person_offset * 0x9E3779B1), self._plate_calls_dev), B, N / B
             return torch.rand(N, device=self.device).topk(B).indices, B, N / B
         return torch.randperm(N, device=self.device)[:B], B, N / B
 

@@ -468,6 +468,19 @@ def cdm_score_elbo_grad(
     return out
 
 
+SAMPLE_MAX_BATCH = 2048
+
+
+def sample_indices(n_rows: int, batch: int, seed: int, counter_dev: torch.Tensor) -> torch.Tensor:
+    """``randperm(n_rows)[:batch]`` in one stream-ordered launch: ``batch`` distinct row indices, uniform over ordered
+    subsets, keyed by (seed, *counter_dev); the kernel increments the device counter (graph-safe)."""
+    if not counter_dev.is_cuda or counter_dev.dtype != torch.int64 or counter_dev.numel() != 1:
+        raise ValueError("counter_dev must be a one-element CUDA int64 tensor")
+    out = torch.empty(batch, dtype=torch.int64, device=counter_dev.device)
+    N.check(N.lib().vipsy_sample_indices_dev(_ptr(out), batch, n_rows, seed & (2 ** 64 - 1), _ptr(counter_dev), _stream()))
+    return out
+
+
 # --------------------------------------------------------------------------- NormEncoder (vi.py:417-435, 677-684)
 NORM_ENCODER_MAX_HIDDEN = 64
 
