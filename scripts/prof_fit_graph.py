@@ -9,8 +9,9 @@ g = torch.Generator().manual_seed(0)
 y = (torch.rand(100_000, 100, generator=g) < 0.6).float()
 m = (vb.VIRT if which == "virt" else vb.VaeIRT)(data=y, model="irt_2pl", subsample_size=100)
 svi = infer.SVI(m.model, m.guide, optim=vb.Adam({"lr": 1e-2}), loss=vb.Trace_ELBO(1), cuda_graph=False)
+m._device_rng = True                      # the stream-ordered form that SVI(cuda_graph=True) captures
 for _ in range(3):
-    svi.step(m.data)
+    svi._step_device(m.data)
 torch.cuda.synchronize()
 torch.cuda.profiler.start()
 svi._step_device(m.data)
