@@ -38,7 +38,8 @@ def test_every_declared_symbol_is_exported(lib):
 
 def test_struct_layout_matches_header():
     structs = {"VipsyIrtArgs": N.IrtArgs, "VipsyCdmEnumArgs": N.CdmEnumArgs, "VipsyCdmScoreArgs": N.CdmScoreArgs,
-               "VipsyIrtHostArgs": N.IrtHostArgs, "VipsyAdamTensor": N.AdamTensor}
+               "VipsyIrtHostArgs": N.IrtHostArgs, "VipsyAdamTensor": N.AdamTensor,
+               "VipsyNormEncoderArgs": N.NormEncoderArgs}
     lines = ['#include <stdio.h>', '#include <stddef.h>', f'#include "{HEADER}"', "int main(void){"]
     for cname, st in structs.items():
         lines.append(f'printf("{cname} %zu\\n", sizeof({cname}));')
