@@ -143,11 +143,11 @@ class BasePsy(nn.Module):               # vi.py:521-533
         N, B = self.sample_size, min(self.subsample_size, self.sample_size)
         if B >= N:
             return None, N, 1.0
+        if B <= ops.SAMPLE_MAX_BATCH:             # one launch, counter in device memory: the same index stream in
+            if self._plate_calls_dev is None:     # eager and captured iterations (graph-safe, no host sync)
+                self._plate_calls_dev = torch.zeros(1, dtype=torch.int64, device=self.device)
+            return ops.sample_indices(N, B, self._seed ^ (self.person_offset * 0x9E3779B1), self._plate_calls_dev), B, N / B
         if self._device_rng:          # uniform random B-subset in random order, no host sync (graph-safe)
-            if B <= ops.SAMPLE_MAX_BATCH:         # one launch, counter in device memory
-                if self._plate_calls_dev is None:
-                    self._plate_calls_dev = torch.zeros(1, dtype=torch.int64, device=self.device)
-                return ops.sample_indices(N, B, self._seed ^ (self.person_offset * 0x9E3779B1), self._plate_calls_dev), B, N / B
             return torch.rand(N, device=self.device).topk(B).indices, B, N / B
         return torch.randperm(N, device=self.device)[:B], B, N / B
 
