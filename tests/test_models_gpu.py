@@ -251,6 +251,19 @@ def test_cuda_graph_step_equals_eager_virt_4pl():
     assert lg[-1] < lg[0]
 
 
+def test_cuda_graph_step_equals_eager_minibatch_vaeirt():
+    """Subsampled fit: both modes draw the minibatch with the same kernel and device counter (and the same noise
+    streams), so the captured iteration reproduces the eager one loss by loss."""
+    g = torch.Generator().manual_seed(1)
+    y = (torch.rand(900, 20, generator=g) < 0.6).float()
+    y[torch.rand(900, 20, generator=g) < 0.1] = float("nan")
+    (le, pe), (lg, pg) = _fit_pair(lambda: vb.VaeIRT(data=y, model="irt_2pl", subsample_size=64, hidden_dim=16, seed=2), 10,
+                                   optim=lambda: vb.Adam({"lr": 1e-2}), loss=vb.Trace_ELBO(num_particles=2))
+    assert np.allclose(le, lg, rtol=2e-5), (le, lg)
+    for n in pe:
+        assert_close(pg[n], pe[n], 1e-4, 1e-4, n)
+
+
 def test_cuda_graph_step_equals_eager_vaeirt_mirt_with_scheduler():
     """Encoder forward + backward inside the captured graph, staircase free mask, MultiStepLR through lr_dev."""
     g = torch.Generator().manual_seed(1)
