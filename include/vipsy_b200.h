@@ -161,13 +161,14 @@ typedef struct VipsyIrtHostArgs {
   const float* d_host;       /* J (4PL)                                                                */
   double* loss_host;         /* 1                                                                      */
   float* d_mu_host;          /* batch, or NULL                                                         */
-  float* d_sigma_host;       /* batch, or NULL (goes with d_mu_host)                                   */
+  float* d_sigma_host;       /* batch; NULL exactly when d_mu_host is NULL                             */
   float* item_grads_host;    /* [d_b | d_a | d_c | d_d], J x model floats, or NULL                     */
   void* dev_scratch;         /* device scratch, vipsy_irt_host_scratch_bytes()                         */
   size_t dev_scratch_bytes;
   void* s_in;                /* cudaStream_t: host -> device copies                                    */
   void* s_run;               /* cudaStream_t: kernels                                                  */
   void* s_out;               /* cudaStream_t: device -> host copies                                    */
+  const uint8_t* a_free_host; /* J 0/1 bytes: the `free` mask of site 'a' (vi.py:511-512) applied to d_a, or NULL */
 } VipsyIrtHostArgs;
 size_t vipsy_irt_host_scratch_bytes(const VipsyIrtHostArgs* args);
 int vipsy_irt_host_step(const VipsyIrtHostArgs* args);

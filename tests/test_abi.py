@@ -77,3 +77,17 @@ def test_peer_allreduce_rejects_bad_layouts(lib):
     assert f(C.byref(dummy), 0, 2, 4, 512, 4, 1, None, None, 1, None) == N.ERR_ARG     # flag area too small
     assert f(C.byref(dummy), 0, 2, 1024, 16, 400, 1, None, None, 1, None) == N.ERR_ARG  # slot too small
     assert b"vipsy_peer_allreduce" in lib.vipsy_last_error()
+
+
+def test_host_step_rejects_half_a_gradient_pair(lib):
+    """d_mu_host without d_sigma_host (or the reverse) is an argument error, not a write through NULL."""
+    import torch
+    a = N.IrtHostArgs()
+    a.dev.n_rows = a.dev.batch = 64
+    a.dev.n_items, a.dev.n_dims, a.dev.n_particles, a.dev.model = 4, 1, 1, 2
+    keep = [torch.zeros(64 * 4, dtype=torch.uint8), torch.zeros(64), torch.ones(64), torch.ones(4), torch.zeros(4),
+            torch.zeros(1, dtype=torch.float64), torch.zeros(64)]
+    a.y_host, a.mu_host, a.sigma_host, a.a_host, a.b_host, a.loss_host, a.d_mu_host = (t.data_ptr() for t in keep)
+    a.n_chunks = 1
+    assert N.lib().vipsy_irt_host_step(C.byref(a)) == N.ERR_ARG
+    assert b"go together" in N.lib().vipsy_last_error()

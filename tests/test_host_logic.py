@@ -89,6 +89,78 @@ def test_svi_step_order_free_mask_and_zero_grads():
     assert svi.evaluate_loss(None) == 1.25
 
 
+def test_supports_fused_checks_the_resolved_optimiser_arguments():
+    """The device-resident Adam covers torch.optim.Adam's default options only: anything else must be reported by
+    supports_fused (so fit() can fall back to the eager torch.optim path) instead of failing on the first step."""
+    assert infer.Adam({"lr": 1e-2}).supports_fused()
+    assert infer.Adam({"lr": 1e-2, "betas": (0.8, 0.99)}).supports_fused()
+    assert not infer.Adam({"lr": 1e-2, "weight_decay": 1e-4}).supports_fused()
+    assert not infer.Adam({"lr": 1e-2, "amsgrad": True}).supports_fused()
+    assert not infer.Adam({"lr": 1e-2, "maximize": True}).supports_fused()
+    assert not infer.Adam({"lr": 1e-2}, clip_args={"clip_norm": 1.0}).supports_fused()
+    assert not infer.PyroOptim(torch.optim.SGD, {"lr": 1e-2}).supports_fused()
+
+    def per_param(module_name, param_name):
+        return {"lr": 1e-2, "weight_decay": 1e-3} if param_name == "b" else {"lr": 1e-2}
+    opt = infer.Adam(per_param)
+    assert opt.supports_fused(["a", "encoder$$$fc1.weight"]) and not opt.supports_fused(["a", "b"])
+    sched = infer.MultiStepLR({"optimizer": torch.optim.Adam, "optim_args": {"lr": 0.1, "amsgrad": True},
+                               "milestones": [2], "gamma": 0.1})
+    assert not sched.supports_fused()
+
+
+def test_svi_auto_mode_falls_back_to_eager_and_strict_mode_raises():
+    class Owner:
+        _calls = 0
+
+        def __init__(self):
+            self.b = torch.zeros(3, requires_grad=True)
+
+        def model(self, data):
+            pass
+        guide = model
+
+        def loss_and_grads(self, cfg, data):
+            self.b.grad = torch.ones(3)
+            return torch.tensor(2.0), [("b", self.b, None)]
+
+    def per_param(module_name, param_name):
+        return {"lr": 0.5, "weight_decay": 0.1}
+    ow = Owner()
+    svi = infer.SVI(ow.model, ow.guide, infer.Adam(per_param), infer.Trace_ELBO(), cuda_graph=None)
+    assert svi.cuda_graph                                   # callable arguments: undecided until the names are known
+    assert svi.step(None) == 2.0 and not svi.cuda_graph     # decided on the first step: eager torch.optim.Adam
+    assert float(ow.b[0]) == pytest.approx(-0.5) and ow.b.grad is None
+    assert svi.step(None) == 2.0
+    with pytest.raises(NotImplementedError):
+        infer.SVI(ow.model, ow.guide, infer.Adam({"lr": 0.5, "amsgrad": True}), infer.Trace_ELBO(), cuda_graph=True)
+    strict = infer.SVI(ow.model, ow.guide, infer.Adam(per_param), infer.Trace_ELBO(), cuda_graph=True)
+    with pytest.raises(NotImplementedError):
+        strict.step(None)
+    auto = infer.SVI(ow.model, ow.guide, infer.Adam({"lr": 0.5}, clip_args={"clip_value": 0.1}), infer.Trace_ELBO(),
+                     cuda_graph=None)
+    assert not auto.cuda_graph
+
+
+def test_clip_args_are_applied_per_parameter_before_the_step():
+    """pyro.optim clip_args: {'clip_norm': x} / {'clip_value': y}, dict or callable, per parameter tensor."""
+    p = torch.zeros(4, requires_grad=True)
+    q = torch.zeros(4, requires_grad=True)
+    opt = infer.PyroOptim(torch.optim.SGD, {"lr": 1.0}, clip_args={"clip_norm": 1.0})
+    p.grad, q.grad = torch.full((4,), 3.0), torch.full((4,), 0.1)
+    opt([("p", p), ("q", q)])
+    assert torch.allclose(p.detach(), torch.full((4,), -0.5), atol=1e-5)      # norm 6 -> 1
+    assert torch.allclose(q.detach(), torch.full((4,), -0.1), atol=1e-6)      # norm 0.2: untouched
+    r = torch.zeros(2, requires_grad=True)
+    optv = infer.PyroOptim(torch.optim.SGD, {"lr": 1.0},
+                           clip_args=lambda m, n: {"clip_value": 0.25} if n == "r" else {})
+    r.grad = torch.tensor([2.0, -0.1])
+    optv([("r", r)])
+    assert torch.allclose(r.detach(), torch.tensor([-0.25, 0.1]))
+    with pytest.raises(ValueError):
+        infer.PyroOptim(torch.optim.SGD, {"lr": 1.0}, clip_args={"clip": 1.0})([("p", p)])
+
+
 def test_shard_bounds_cover_everything():
     for n in (0, 1, 7, 1000, 1_000_003):
         for world in (1, 2, 3, 8):

@@ -173,6 +173,7 @@ def test_host_step_two_bit_transport_matches_device_call():
     hy = w["y"].cpu()
     for y_in in (hy, ops.pack_responses_2bit_host(hy)):
         got = host(y_in, hp["mu"], hp["sigma"], hp["a"], hp["b"], hp["c"], hp["d"], n_particles=8, seed=9, offset=3)
+        got = {k: v.clone() for k, v in got.items()}
         assert torch.equal(got["d_mu"], ref["d_mu"].cpu()) and torch.equal(got["d_sigma"], ref["d_sigma"].cpu())
         assert torch.equal(got["item_grads"], ref["item_grads"].cpu())
         assert float(got["loss"]) == float(ref["loss"])
@@ -183,6 +184,11 @@ def test_host_step_two_bit_transport_matches_device_call():
     assert_close(got4["item_grads"], ref["item_grads"], 1e-5, 1e-5, "item grads over 4 chunks")
     assert_close(got4["loss"], ref["loss"], 1e-9, 1e-9, "loss over 4 chunks")
     assert torch.equal(ops.unpack_responses_2bit(ops.pack_responses_2bit_host(hy).cuda(), J).cpu(), hy)
+    # the `free` mask of site 'a' (vi.py:511-512) travels with the host call: frozen entries come back exactly 0
+    free = torch.rand(J) < 0.5
+    gotf = host(hy, hp["mu"], hp["sigma"], hp["a"], hp["b"], hp["c"], hp["d"], n_particles=8, seed=9, offset=3, a_free=free)
+    ig, igf = got["item_grads"].clone().reshape(4, J), gotf["item_grads"].reshape(4, J)
+    assert torch.equal(igf[1], ig[1] * free) and torch.equal(igf[[0, 2, 3]], ig[[0, 2, 3]])
 
 
 # ---- device-resident iteration: fused Adam, device RNG counters, CUDA graph ----------------
@@ -375,3 +381,57 @@ def test_cuda_graph_minibatch_multi_particle_and_evaluate_loss():
     m3 = vb.VaeIRT(data=y, model="irt_2pl", x_feature=2, subsample_size=50, hidden_dim=8)      # fused K = 2 kernel in the graph
     l3 = m3.fit(optim=vb.Adam({"lr": 1e-2}), loss=vb.Trace_ELBO(num_particles=2), max_iter=30)
     assert np.isfinite(l3)
+
+
+def test_default_fit_falls_back_to_eager_for_adam_options_the_device_step_does_not_cover():
+    """fit() captures a CUDA graph by default; a valid Adam configuration outside the device-resident step's
+    coverage (weight decay from a per-parameter callable, gradient clipping) must run through the eager
+    torch.optim path and give the same result as an explicit cuda_graph=False, not fail on the first step."""
+    g = torch.Generator().manual_seed(1)
+    y = (torch.rand(400, 12, generator=g) < 0.6).float()
+
+    def per_param(module_name, param_name):
+        return {"lr": 2e-2, "weight_decay": 1e-2} if param_name == "a" else {"lr": 2e-2}
+    res = []
+    for graph in (None, False):
+        vb.clear_param_store()
+        m = vb.VIRT(data=y, model="irt_2pl", seed=2)
+        m._device_rng = True
+        loss = m.fit(optim=vb.Adam(per_param, clip_args={"clip_norm": 50.0}), max_iter=6, cuda_graph=graph)
+        res.append((loss, vb.get_param_store().get("a").clone(), vb.get_param_store().get("b").clone()))
+    assert res[0][0] == res[1][0] and torch.equal(res[0][1], res[1][1]) and torch.equal(res[0][2], res[1][2])
+    vb.clear_param_store()
+    with pytest.raises(NotImplementedError):
+        vb.VIRT(data=y, model="irt_2pl").fit(optim=vb.Adam(per_param), max_iter=2, cuda_graph=True)
+
+
+def test_noise_counters_stay_in_step_across_eager_captured_and_readout_calls():
+    """The host and device call counters advance together in every mode, so no (seed, offset) Philox stream is
+    used twice: eager evaluations before a captured fit, the replays, and read-outs after it."""
+    torch.manual_seed(0)
+    q = (torch.rand(3, 10) < 0.5).float()
+    q[:, q.sum(0) == 0] = 1.0
+    y = (torch.rand(300, 10) < 0.5).float()
+    m = vb.VCHoDina(data=y, q=q, seed=5)
+    cfg = vb.TraceEnum_ELBO(num_particles=1)
+    m.loss(cfg)
+    m.loss(cfg)                                             # two eager calls first: host count 2, no device counter
+    assert m._calls == 2 and m._calls_dev is None
+    m.fit(max_iter=7, cuda_graph=True)
+    assert int(m._calls_dev) == m._calls == 2 + 7
+    m.posterior()                                           # kind=None call: still advances both
+    assert int(m._calls_dev) == m._calls == 10
+
+
+def test_vchodina_posterior_uses_the_model_the_fit_uses():
+    """VCHoDina ignores `model=` (always DINA, vi.py:905): the read-out must score with the same link."""
+    torch.manual_seed(1)
+    q = (torch.rand(3, 12) < 0.5).float()
+    q[:, q.sum(0) == 0] = 1.0
+    y = (torch.rand(200, 12) < 0.5).float()
+    post = []
+    for model in ("dina", "dino"):
+        vb.clear_param_store()
+        m = vb.VCHoDina(data=y, q=q, model=model, seed=3)
+        post.append(m.posterior())
+    assert torch.equal(post[0], post[1])

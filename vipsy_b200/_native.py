@@ -56,6 +56,7 @@ class IrtHostArgs(C.Structure):
         ("mu_host", _p), ("sigma_host", _p), ("a_host", _p), ("b_host", _p), ("c_host", _p), ("d_host", _p),
         ("loss_host", _p), ("d_mu_host", _p), ("d_sigma_host", _p), ("item_grads_host", _p),
         ("dev_scratch", _p), ("dev_scratch_bytes", C.c_size_t), ("s_in", _p), ("s_run", _p), ("s_out", _p),
+        ("a_free_host", _p),
     ]
 
 

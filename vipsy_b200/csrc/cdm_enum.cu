@@ -582,18 +582,13 @@ int cdm_enum_launch(const VipsyCdmEnumArgs* a, cudaStream_t st) {
   if (a->hodina) kern = ns == 2 ? cdm_enum_kernel<true, 2> : (ns == 4 ? cdm_enum_kernel<true, 4> : cdm_enum_kernel<true, 8>);
   else if (scorem) kern = ns == 2 ? cdm_enum_kernel<false, 2, true> : (ns == 4 ? cdm_enum_kernel<false, 4, true> : cdm_enum_kernel<false, 8, true>);
   else kern = ns == 2 ? cdm_enum_kernel<false, 2> : (ns == 4 ? cdm_enum_kernel<false, 4> : cdm_enum_kernel<false, 8>);
-  static int occ[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-  static size_t occ_smem[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+  static OccCache occ_cache[9];
+  int occ = 0;
   const int which = (a->hodina ? 3 : (scorem ? 6 : 0)) + (ns == 2 ? 0 : (ns == 4 ? 1 : 2));
   if (smem > 48 * 1024) VIPSY_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  if (occ[which] == 0 || occ_smem[which] != smem) {
-    VIPSY_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[which], kern, kCdmThreads, smem));
-    occ_smem[which] = smem;
-    if (occ[which] < 1) occ[which] = 1;
-    if (occ[which] > kCdmMaxCtasPerSM) occ[which] = kCdmMaxCtasPerSM;
-  }
+  VIPSY_CUDA_CHECK(cached_occupancy(occ_cache[which], kern, kCdmThreads, smem, kCdmMaxCtasPerSM, &occ));
   int64_t ctas = (a->batch + kCdmWarps - 1) / kCdmWarps;
-  const int64_t cap = (int64_t)num_sms() * occ[which];
+  const int64_t cap = (int64_t)num_sms() * occ;
   if (ctas > cap) ctas = cap;
   if (ctas < 1) ctas = 1;
   kern<<<(int)ctas, kCdmThreads, smem, st>>>(p);

@@ -1,6 +1,8 @@
 // Shared device helpers for the vipsy_b200 kernels (sm_100a).
 #pragma once
 #include <cuda_runtime.h>
+
+#include <atomic>
 #include <stdint.h>
 #include <stdio.h>
 
@@ -175,6 +177,28 @@ inline int num_sms() {
       n = kNumSMs;
   }
   return n;
+}
+
+// Resident CTAs per SM of one kernel instantiation at one dynamic shared-memory size, cached per call site in
+// one atomic word {smem + 1 : 40 bits | occupancy : 24 bits}.  Lock-free and device-agnostic: racing threads and
+// other devices of the box (one GPU model) compute the same value.
+struct OccCache {
+  std::atomic<uint64_t> w{0};
+};
+template <class Kern>
+inline cudaError_t cached_occupancy(OccCache& c, Kern k, int threads, size_t smem, int hi, int* out) {
+  uint64_t w = c.w.load(std::memory_order_relaxed);
+  if ((w >> 24) != (uint64_t)smem + 1) {
+    int occ = 0;
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, threads, smem);
+    if (e != cudaSuccess) return e;
+    if (occ < 1) occ = 1;
+    if (occ > hi) occ = hi;
+    w = (((uint64_t)smem + 1) << 24) | (uint64_t)occ;
+    c.w.store(w, std::memory_order_relaxed);
+  }
+  *out = (int)(w & 0xffffffu);
+  return cudaSuccess;
 }
 
 // Column sums of a row-major [rows x cols] fp32 partial matrix in a fixed order

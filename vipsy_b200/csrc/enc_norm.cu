@@ -364,12 +364,9 @@ int vipsy_norm_encoder_forward(const VipsyNormEncoderArgs* a, void* stream) {
   int rc = check_enc(a, false);
   if (rc != VIPSY_OK) return rc;
   if (a->batch == 0) return VIPSY_OK;
-  static bool attr = false;
-  if (!attr) {
-    VIPSY_CUDA_CHECK(cudaFuncSetAttribute(enc_norm_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          (int)kEncFwdSmem));
-    attr = true;
-  }
+  // the attribute is per device: set on every launch (cheap), never cached process-wide
+  VIPSY_CUDA_CHECK(cudaFuncSetAttribute(enc_norm_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (int)kEncFwdSmem));
   const EncParams P = enc_params(a);
   if ((P.xtiles ? enc_tc_resident_supported(P.H, P.J) : enc_tc_supported(P.H, P.J)) && !(a->flags & 1) &&
       (reinterpret_cast<uintptr_t>(a->pre) & 15) == 0)
@@ -396,12 +393,8 @@ int vipsy_norm_encoder_backward(const VipsyNormEncoderArgs* a, void* stream) {
   VIPSY_REQUIRE(a->workspace && a->workspace_bytes >= vipsy_norm_encoder_workspace_bytes(a), VIPSY_ERR_ARG,
                 "vipsy_norm_encoder_backward: workspace too small (%zu < %zu)", a->workspace_bytes,
                 vipsy_norm_encoder_workspace_bytes(a));
-  static bool attr = false;
-  if (!attr) {
-    VIPSY_CUDA_CHECK(cudaFuncSetAttribute(enc_norm_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          (int)kEncBwdSmem));
-    attr = true;
-  }
+  VIPSY_CUDA_CHECK(cudaFuncSetAttribute(enc_norm_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (int)kEncBwdSmem));
   EncParams P = enc_params(a);
   P.partial = reinterpret_cast<float*>(a->workspace);
   int gx = enc_grid_x(a->batch);

@@ -581,20 +581,14 @@ int enc_tc_fwd_launch(const EncParams& P, cudaStream_t st) {
     return VIPSY_ERR_UNSUPPORTED;
   }
   const size_t smem = tc_fwd_smem(JP, resident, NS);
-  static size_t attr[2] = {0, 0};
   const int64_t tiles = (P.B + kTB - 1) / kTB;
   if (NS == 128) {
-    if (smem > attr[0]) {
-      VIPSY_CUDA_CHECK(cudaFuncSetAttribute(enc_tc_fwd_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      attr[0] = smem;
-    }
+    // per-device attribute: set on every launch, no process-wide cache
+    VIPSY_CUDA_CHECK(cudaFuncSetAttribute(enc_tc_fwd_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int64_t cap = 2 * (int64_t)num_sms();
     enc_tc_fwd_kernel<128><<<(int)(tiles < cap ? tiles : cap), kThreads, smem, st>>>(P, JP);
   } else {
-    if (smem > attr[1]) {
-      VIPSY_CUDA_CHECK(cudaFuncSetAttribute(enc_tc_fwd_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      attr[1] = smem;
-    }
+    VIPSY_CUDA_CHECK(cudaFuncSetAttribute(enc_tc_fwd_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int64_t cap = (int64_t)num_sms();        // one CTA per SM: 64 KB code tile + up to 96 KB of W tiles
     enc_tc_fwd_kernel<256><<<(int)(tiles < cap ? tiles : cap), kThreads, smem, st>>>(P, JP);
   }
@@ -608,20 +602,13 @@ int enc_tc_bwd_launch(const EncParams& P, int grid_x, cudaStream_t st) {
     set_error("enc_tc_bwd_launch: J > 127 needs resident operand tiles");
     return VIPSY_ERR_UNSUPPORTED;
   }
-  static bool attr[2] = {false, false};
   if (NS == 128) {
-    if (!attr[0]) {
-      VIPSY_CUDA_CHECK(cudaFuncSetAttribute(enc_tc_bwd_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                            (int)tc_bwd_smem(128)));
-      attr[0] = true;
-    }
+    VIPSY_CUDA_CHECK(cudaFuncSetAttribute(enc_tc_bwd_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)tc_bwd_smem(128)));
     enc_tc_bwd_kernel<128><<<grid_x, kBwdThreads, tc_bwd_smem(128), st>>>(P);
   } else {
-    if (!attr[1]) {
-      VIPSY_CUDA_CHECK(cudaFuncSetAttribute(enc_tc_bwd_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                            (int)tc_bwd_smem(256)));
-      attr[1] = true;
-    }
+    VIPSY_CUDA_CHECK(cudaFuncSetAttribute(enc_tc_bwd_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)tc_bwd_smem(256)));
     enc_tc_bwd_kernel<256><<<grid_x, kBwdThreads, tc_bwd_smem(256), st>>>(P);
   }
   VIPSY_CUDA_CHECK(cudaGetLastError());

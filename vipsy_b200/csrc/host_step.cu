@@ -15,7 +15,7 @@ namespace vipsy {
 static inline size_t al256(size_t x) { return (x + 255) & ~size_t(255); }
 
 struct HostLayout {
-  size_t y, y2, mu, sigma, d_mu, d_sigma, items, grads, loss, gsum, lsum, ws, total;
+  size_t y, y2, mu, sigma, d_mu, d_sigma, items, a_free, grads, loss, gsum, lsum, ws, total;
   size_t ws_bytes;
   int ncol;
 };
@@ -35,6 +35,7 @@ static HostLayout host_layout(const VipsyIrtHostArgs* h) {
   L.d_mu = o; o += al256(N * 4);
   L.d_sigma = o; o += al256(N * 4);
   L.items = o; o += al256(4 * J * 4);
+  L.a_free = o; o += h->a_free_host ? al256(J) : 0;
   L.grads = o; o += al256((size_t)h->n_chunks * L.ncol * 4);
   L.loss = o; o += al256((size_t)h->n_chunks * 8);
   L.gsum = o; o += al256((size_t)L.ncol * 4);
@@ -96,6 +97,8 @@ int vipsy_irt_host_step(const VipsyIrtHostArgs* h) {
   VIPSY_REQUIRE(a.model < 2 || h->a_host, VIPSY_ERR_ARG, "vipsy_irt_host_step: a is required for 2PL+");
   VIPSY_REQUIRE(a.model < 3 || h->c_host, VIPSY_ERR_ARG, "vipsy_irt_host_step: c is required for 3PL+");
   VIPSY_REQUIRE(a.model < 4 || h->d_host, VIPSY_ERR_ARG, "vipsy_irt_host_step: d is required for 4PL");
+  VIPSY_REQUIRE((h->d_mu_host == nullptr) == (h->d_sigma_host == nullptr), VIPSY_ERR_ARG,
+                "vipsy_irt_host_step: d_mu_host and d_sigma_host go together (both or neither)");
   VIPSY_REQUIRE(h->s_in && h->s_run && h->s_out, VIPSY_ERR_ARG, "vipsy_irt_host_step: three streams are required");
   const HostLayout L = host_layout(h);
   VIPSY_REQUIRE(h->dev_scratch && h->dev_scratch_bytes >= L.total, VIPSY_ERR_WORKSPACE,
@@ -113,6 +116,12 @@ int vipsy_irt_host_step(const VipsyIrtHostArgs* h) {
   if (a.model >= 2) VIPSY_CUDA_CHECK(cudaMemcpyAsync(items + J, h->a_host, (size_t)J * 4, cudaMemcpyHostToDevice, s_in));
   if (a.model >= 3) VIPSY_CUDA_CHECK(cudaMemcpyAsync(items + 2 * J, h->c_host, (size_t)J * 4, cudaMemcpyHostToDevice, s_in));
   if (a.model >= 4) VIPSY_CUDA_CHECK(cudaMemcpyAsync(items + 3 * J, h->d_host, (size_t)J * 4, cudaMemcpyHostToDevice, s_in));
+  // the `free` mask of site 'a' (vi.py:511-512): applied to d_a per chunk by the kernel path, as on the device entry
+  uint8_t* a_free_dev = nullptr;
+  if (h->a_free_host && a.model >= 2) {
+    a_free_dev = base + L.a_free;
+    VIPSY_CUDA_CHECK(cudaMemcpyAsync(a_free_dev, h->a_free_host, (size_t)J, cudaMemcpyHostToDevice, s_in));
+  }
 
   // Chunk schedule: sizes in whole "waves" of the persistent particle kernel (SMs x 4 CTAs x 4 warps x 32
   // persons per round; a chunk of 3.3 waves costs 4 rounds) when the batch is that large, else whole warps.
@@ -162,7 +171,7 @@ int vipsy_irt_host_step(const VipsyIrtHostArgs* h) {
     c.person_offset = a.person_offset + s0;
     c.b = items; c.a = a.model >= 2 ? items + J : nullptr; c.c = a.model >= 3 ? items + 2 * J : nullptr;
     c.d = a.model >= 4 ? items + 3 * J : nullptr;
-    c.a_free = nullptr;
+    c.a_free = a_free_dev;
     c.loss = reinterpret_cast<double*>(base + L.loss) + used;
     float* g = reinterpret_cast<float*>(base + L.grads) + (size_t)used * L.ncol;
     c.d_mu = want_grad ? dmu : nullptr; c.d_sigma = want_grad ? dsg : nullptr; c.d_chol = nullptr;

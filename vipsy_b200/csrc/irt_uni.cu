@@ -256,15 +256,10 @@ constexpr int kUniMaxCtasPerSM = 8;
 template <int MODEL, bool SCORE, int SC, bool FAST>
 static int launch_one(IrtUniParams& p, size_t smem, cudaStream_t st, int* grid_out) {
   auto k = irt_uni_kernel<MODEL, SCORE, SC, FAST>;
-  static int occ = 0;   // per instantiation
-  static size_t occ_smem = ~size_t(0);
+  static OccCache occ_cache;   // per instantiation
+  int occ = 0;
   if (smem > 48 * 1024) VIPSY_CUDA_CHECK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  if (occ == 0 || occ_smem != smem) {
-    VIPSY_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, kUniThreads, smem));
-    occ_smem = smem;
-    if (occ < 1) occ = 1;
-    if (occ > kUniMaxCtasPerSM) occ = kUniMaxCtasPerSM;
-  }
+  VIPSY_CUDA_CHECK(cached_occupancy(occ_cache, k, kUniThreads, smem, kUniMaxCtasPerSM, &occ));
   const int64_t ntiles = (p.B + 31) / 32;
   int64_t ctas = (ntiles + kUniWarps - 1) / kUniWarps;
   const int64_t cap = (int64_t)num_sms() * occ;

@@ -254,16 +254,11 @@ __global__ void __launch_bounds__(kUniThreads) irt_uni_csr_kernel(const IrtUniPa
 template <int MODEL, int SW, bool FAST>
 static int launch_csr_one(IrtUniParams& p, cudaStream_t st, int* grid_out) {
   auto k = irt_uni_csr_kernel<MODEL, SW, FAST>;
-  static int occ = 0;
-  static size_t occ_smem = ~size_t(0);
+  static OccCache occ_cache;   // per instantiation
+  int occ = 0;
   const size_t smem = csr_smem_bytes(p.J, MODEL, SW);
   if (smem > 48 * 1024) VIPSY_CUDA_CHECK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  if (occ == 0 || occ_smem != smem) {
-    VIPSY_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, kUniThreads, smem));
-    occ_smem = smem;
-    if (occ < 1) occ = 1;
-    if (occ > 8) occ = 8;
-  }
+  VIPSY_CUDA_CHECK(cached_occupancy(occ_cache, k, kUniThreads, smem, 8, &occ));
   const int64_t ntiles = (p.B + 31) / 32;
   int64_t ctas = (ntiles + kUniWarps - 1) / kUniWarps;
   const int64_t cap = (int64_t)num_sms() * occ;

@@ -669,20 +669,13 @@ __global__ void __launch_bounds__(kUniThreads) irt_uni_rowsp_kernel(const IrtUni
 
 // ---------------------------------------------------------------------------------------------------
 template <typename Kern>
-static int launch_row(Kern k, IrtUniParams& p, size_t smem, cudaStream_t st, int* grid_out, int* occ_cache,
-                      size_t* occ_smem) {
+static int launch_row(Kern k, IrtUniParams& p, size_t smem, cudaStream_t st, int* grid_out, OccCache* occ_cache) {
   if (smem > 48 * 1024) VIPSY_CUDA_CHECK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  if (*occ_cache == 0 || *occ_smem != smem) {
-    int occ = 0;
-    VIPSY_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, kUniThreads, smem));
-    if (occ < 1) occ = 1;
-    if (occ > 8) occ = 8;               // workspace rows: num_sms * 8 (irt_uni_workspace_bytes)
-    *occ_cache = occ;
-    *occ_smem = smem;
-  }
+  int occ = 0;                          // capped at 8: workspace rows = num_sms * 8 (irt_uni_workspace_bytes)
+  VIPSY_CUDA_CHECK(cached_occupancy(*occ_cache, k, kUniThreads, smem, 8, &occ));
   const int64_t ntiles = (p.B + 31) / 32;
   int64_t ctas = (ntiles + kUniWarps - 1) / kUniWarps;
-  const int64_t cap = (int64_t)num_sms() * *occ_cache;
+  const int64_t cap = (int64_t)num_sms() * occ;
   if (ctas > cap) ctas = cap;
   if (ctas < 1) ctas = 1;
   *grid_out = (int)ctas;
@@ -693,33 +686,25 @@ static int launch_row(Kern k, IrtUniParams& p, size_t smem, cudaStream_t st, int
 
 template <int MODEL, int NP, bool FAST>
 static int launch_row_dense(IrtUniParams& p, cudaStream_t st, int* grid) {
-  static int occ = 0;
-  static size_t occ_smem = ~size_t(0);
+  static OccCache occ, occ_u;
   const size_t smem = (size_t)kUniWarps * MODEL * NP * 128 * 4;
-  static int occ_u = 0;
-  static size_t occ_smem_u = ~size_t(0);
   if (!rows_word_aligned(p))
-    return launch_row(irt_uni_row_kernel<MODEL, NP, FAST, false>, p, smem, st, grid, &occ_u, &occ_smem_u);
-  return launch_row(irt_uni_row_kernel<MODEL, NP, FAST, true>, p, smem, st, grid, &occ, &occ_smem);
+    return launch_row(irt_uni_row_kernel<MODEL, NP, FAST, false>, p, smem, st, grid, &occ_u);
+  return launch_row(irt_uni_row_kernel<MODEL, NP, FAST, true>, p, smem, st, grid, &occ);
 }
 template <int MODEL, int NP, bool FAST>
 static int launch_row_sparse(IrtUniParams& p, cudaStream_t st, int* grid) {
-  static int occ = 0;
-  static size_t occ_smem = ~size_t(0);
-  static int occ_u = 0;
-  static size_t occ_smem_u = ~size_t(0);
+  static OccCache occ, occ_u;
   if (!rows_word_aligned(p))
-    return launch_row(irt_uni_rowsp_kernel<MODEL, NP, FAST, false>, p, rowsp_smem_bytes(p.J, MODEL), st, grid, &occ_u,
-                      &occ_smem_u);
-  return launch_row(irt_uni_rowsp_kernel<MODEL, NP, FAST, true>, p, rowsp_smem_bytes(p.J, MODEL), st, grid, &occ, &occ_smem);
+    return launch_row(irt_uni_rowsp_kernel<MODEL, NP, FAST, false>, p, rowsp_smem_bytes(p.J, MODEL), st, grid, &occ_u);
+  return launch_row(irt_uni_rowsp_kernel<MODEL, NP, FAST, true>, p, rowsp_smem_bytes(p.J, MODEL), st, grid, &occ);
 }
 
 template <int MODEL, int WP, bool FAST>
 static int launch_row_small(IrtUniParams& p, cudaStream_t st, int* grid) {
-  static int occ = 0;
-  static size_t occ_smem = ~size_t(0);
+  static OccCache occ;
   const size_t smem = (size_t)kUniWarps * MODEL * 4 * WP * 4;
-  return launch_row(irt_uni_rowsm_kernel<MODEL, WP, FAST>, p, smem, st, grid, &occ, &occ_smem);
+  return launch_row(irt_uni_rowsm_kernel<MODEL, WP, FAST>, p, smem, st, grid, &occ);
 }
 
 template <int MODEL, bool FAST>

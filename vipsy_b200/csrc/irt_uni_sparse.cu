@@ -275,15 +275,10 @@ __global__ void __launch_bounds__(kUniThreads, 3) irt_uni_sparse_kernel(const Ir
 template <int MODEL, int SC, bool FAST>
 static int launch_sparse_one(IrtUniParams& p, size_t smem, cudaStream_t st, int* grid_out) {
   auto k = irt_uni_sparse_kernel<MODEL, SC, FAST>;
-  static int occ = 0;
-  static size_t occ_smem = ~size_t(0);
+  static OccCache occ_cache;   // per instantiation
+  int occ = 0;
   if (smem > 48 * 1024) VIPSY_CUDA_CHECK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  if (occ == 0 || occ_smem != smem) {
-    VIPSY_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, kUniThreads, smem));
-    occ_smem = smem;
-    if (occ < 1) occ = 1;
-    if (occ > 8) occ = 8;
-  }
+  VIPSY_CUDA_CHECK(cached_occupancy(occ_cache, k, kUniThreads, smem, 8, &occ));
   const int64_t ntiles = (p.B + 31) / 32;
   int64_t ctas = (ntiles + kUniWarps - 1) / kUniWarps;
   const int64_t cap = (int64_t)num_sms() * occ;

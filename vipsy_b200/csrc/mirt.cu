@@ -477,14 +477,10 @@ template <int KI>
 static int launch_lik(const MirtParams& p, int* grid_out, cudaStream_t st) {
   auto k = mirt_lik_kernel<KI>;
   const size_t smem = lik_smem_floats(p.K) * 4;
-  static int occ = 0;
-  static size_t occ_smem = 0;
+  static OccCache occ_cache;   // per instantiation
+  int occ = 0;
   if (smem > 48 * 1024) VIPSY_CUDA_CHECK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  if (occ == 0 || occ_smem != smem) {
-    VIPSY_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, kLikThreads, smem));
-    occ_smem = smem;
-    if (occ < 1) occ = 1;
-  }
+  VIPSY_CUDA_CHECK(cached_occupancy(occ_cache, k, kLikThreads, smem, 64, &occ));
   const int64_t ntile = ((int64_t)p.S * p.B + kTM - 1) / kTM;
   int64_t g = (int64_t)num_sms() * occ;
   if (g > kMirtMaxGrid) g = kMirtMaxGrid;

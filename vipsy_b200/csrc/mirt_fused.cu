@@ -334,15 +334,10 @@ template <int K, int MODEL, bool SCORE, int SC>
 static int launch_fused_sc(const MirtParams& p, int max_grid, int* grid_out, cudaStream_t st) {
   auto kern = mirt_fused_kernel<K, MODEL, SCORE, SC>;
   const size_t smem = fused_smem_bytes(p.J, K, MODEL);
-  static int occ = 0;
-  static size_t occ_smem = ~size_t(0);
+  static OccCache occ_cache;   // per instantiation
+  int occ = 0;
   if (smem > 48 * 1024) VIPSY_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  if (occ == 0 || occ_smem != smem) {
-    VIPSY_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kFuThreads, smem));
-    occ_smem = smem;
-    if (occ < 1) occ = 1;
-    if (occ > 8) occ = 8;
-  }
+  VIPSY_CUDA_CHECK(cached_occupancy(occ_cache, kern, kFuThreads, smem, 8, &occ));
   const int64_t ntiles = (p.B + 31) / 32;
   int64_t g = (ntiles + kFuWarps - 1) / kFuWarps;
   const int64_t cap = (int64_t)num_sms() * occ;

@@ -37,9 +37,12 @@ class IrtHostStep:
 
     def __call__(self, y: torch.Tensor, mu: torch.Tensor, sigma: torch.Tensor, a, b, c=None, d=None, *,
                  n_particles: int = 1, D: float = 1.0, scale: float = 1.0, seed: int = 0, offset: int = 0,
-                 person_offset: int = 0, estimator: str = "pathwise", baseline: float = 0.0) -> Dict[str, torch.Tensor]:
+                 person_offset: int = 0, estimator: str = "pathwise", baseline: float = 0.0,
+                 a_free=None) -> Dict[str, torch.Tensor]:
         """All tensor arguments are HOST tensors (pinned for asynchronous copies).  y: N x J uint8 codes, or
-        N x ceil(J/4) uint8 rows in the 2-bit transport format.  Returns pinned host tensors."""
+        N x ceil(J/4) uint8 rows in the 2-bit transport format.  ``a_free``: optional J-element 0/1 host mask of
+        site 'a' (vi.py:511-512); d_a of frozen entries comes back 0, as on the device entry.  Returns pinned
+        host tensors."""
         J, m = self.J, self.m
         for t, nm in ((y, "y"), (mu, "mu"), (sigma, "sigma")):
             if t.is_cuda or not t.is_contiguous():
@@ -72,6 +75,11 @@ class IrtHostStep:
         args.loss_host = self.h_loss.data_ptr()
         args.d_mu_host, args.d_sigma_host = self.h_d_mu.data_ptr(), self.h_d_sigma.data_ptr()
         args.item_grads_host = self.h_item_grads.data_ptr()
+        if a_free is not None and m >= 2:
+            self._a_free = a_free.reshape(-1).to(torch.uint8).contiguous()        # kept alive until the sync below
+            if self._a_free.numel() != J or self._a_free.is_cuda:
+                raise ValueError("a_free must be a host tensor with J elements")
+            args.a_free_host = self._a_free.data_ptr()
         L = N.lib()
         need = L.vipsy_irt_host_scratch_bytes(C.byref(args))
         if self.scratch is None or self.scratch.numel() < need:
@@ -86,6 +94,6 @@ class IrtHostStep:
         cur.wait_stream(self.s_run)
         chunks = self.n_chunks
         self.kernel_launches += chunks * (3 + int(packed)) + 1
-        self.h2d_bytes = self.N * (y.shape[1] + 8) + m * J * 4
+        self.h2d_bytes = self.N * (y.shape[1] + 8) + m * J * 4 + (J if args.a_free_host else 0)
         self.d2h_bytes = self.N * 8 + m * J * 4 + 8
         return {"loss": self.h_loss, "d_mu": self.h_d_mu, "d_sigma": self.h_d_sigma, "item_grads": self.h_item_grads}

@@ -130,6 +130,9 @@ class PyroOptim:
 
     def __init__(self, optim_constructor, optim_args: Union[dict, Callable], clip_args=None):
         self.ctor, self.args = optim_constructor, optim_args
+        # pyro.optim.PyroOptim: {'clip_norm': x} and / or {'clip_value': y}, a dict or a callable
+        # (module_name, param_name) -> dict; applied per parameter tensor right before its optimiser step
+        self.clip_args = clip_args
         self.optim_objs: Dict[torch.Tensor, torch.optim.Optimizer] = {}
         self._names: Dict[torch.Tensor, str] = {}
         self._fused: Dict[torch.Tensor, dict] = {}
@@ -137,8 +140,21 @@ class PyroOptim:
         self._steps_host = 0
 
     # ---- device-resident Adam ------------------------------------------------------------------------------
-    def supports_fused(self) -> bool:
-        return self.ctor is torch.optim.Adam
+    _FUSED_DEFAULTS = (("weight_decay", 0), ("amsgrad", False), ("maximize", False))
+
+    @classmethod
+    def _fusable_args(cls, a: dict) -> bool:
+        return all(a.get(k, dflt) == dflt for k, dflt in cls._FUSED_DEFAULTS)
+
+    def supports_fused(self, names: Optional[Iterable[str]] = None) -> bool:
+        """Can ``fused_step`` reproduce this optimiser?  torch.optim.Adam with default options (no weight decay,
+        amsgrad or maximize) and no gradient clipping.  Per-parameter callable arguments can only be resolved once
+        the parameter names are known: pass ``names`` (SVI does, on its first step)."""
+        if self.ctor is not torch.optim.Adam or self.clip_args is not None:
+            return False
+        if not callable(self.args):
+            return self._fusable_args(self.args)
+        return all(self._fusable_args(self._args_for(n)) for n in (names or ()))
 
     def _fused_state(self, name: str, p: torch.Tensor) -> dict:
         st = self._fused.get(p)
@@ -198,12 +214,28 @@ class PyroOptim:
     def _make(self, p, name):
         return self.ctor([p], **self._args_for(name))
 
+    def _clip(self, name: str, p: torch.Tensor):
+        if self.clip_args is None:
+            return
+        if callable(self.clip_args):
+            ca = dict(self.clip_args(name.split("$$$")[0], name.split("$$$")[-1]))
+        else:
+            ca = dict(self.clip_args)
+        unknown = set(ca) - {"clip_norm", "clip_value"}
+        if unknown:
+            raise ValueError(f"clip_args: unknown keys {sorted(unknown)} (clip_norm, clip_value)")
+        if ca.get("clip_norm") is not None:
+            torch.nn.utils.clip_grad_norm_([p], ca["clip_norm"])
+        if ca.get("clip_value") is not None:
+            torch.nn.utils.clip_grad_value_([p], ca["clip_value"])
+
     def __call__(self, params: Iterable[Tuple[str, torch.Tensor]]):
         for name, p in params:
             if p not in self.optim_objs:
                 self.optim_objs[p] = self._make(p, name)
                 self._names[p] = name
             if p.grad is not None:
+                self._clip(name, p)
                 self.optim_objs[p].step()
 
 
@@ -281,19 +313,29 @@ class SVI:
 
     WARMUP = 2          # eager iterations before capture (lazy parameter / optimiser / workspace creation)
 
-    def __init__(self, model, guide, optim: PyroOptim, loss: Trace_ELBO, cuda_graph: bool = False):
+    _NEEDS = ("the device-resident iteration needs torch.optim.Adam with default options (no weight_decay / amsgrad "
+              "/ maximize) and no clip_args; pass cuda_graph=False for the eager torch.optim path")
+
+    def __init__(self, model, guide, optim: PyroOptim, loss: Trace_ELBO, cuda_graph: Optional[bool] = False):
+        """cuda_graph: True = device-resident captured iteration or an error; False = eager torch.optim objects;
+        None = captured when the optimiser allows it, else eager (decided at the latest on the first step, when
+        per-parameter callable optimiser arguments can be resolved)."""
         self.model, self.guide, self.optim, self.loss = model, guide, optim, loss
         self.owner = model.__self__
-        self.cuda_graph = bool(cuda_graph)
-        if self.cuda_graph and not optim.supports_fused():
-            raise NotImplementedError("cuda_graph=True needs an Adam optimiser (pyro.optim.Adam / MultiStepLR of Adam)")
+        self._strict = cuda_graph is True
+        self.cuda_graph = (cuda_graph is None or bool(cuda_graph)) and (optim.supports_fused() or callable(optim.args))
+        if self._strict and not self.cuda_graph:
+            raise NotImplementedError(self._NEEDS)
+        self._fused_checked = False
         self._graph = None
         self._static_loss = None
         self._eager_steps = 0
 
     # ---- eager form, torch.optim objects (the reference's order of operations) -------------------------------
     def _step_eager(self, *args, **kwargs) -> torch.Tensor:
-        loss, sites = self.owner.loss_and_grads(self.loss, *args, **kwargs)
+        return self._finish_eager(*self.owner.loss_and_grads(self.loss, *args, **kwargs))
+
+    def _finish_eager(self, loss, sites) -> torch.Tensor:
         params: List[Tuple[str, torch.Tensor]] = []
         for name, p, free in sites:
             if free is not None and p.grad is not None:
@@ -307,6 +349,13 @@ class SVI:
     # ---- device-resident form ----------------------------------------------------------------------------------
     def _step_device(self, *args, **kwargs) -> torch.Tensor:
         loss, sites = self.owner.loss_and_grads(self.loss, *args, **kwargs)
+        if not self._fused_checked:                              # first (eager warm-up) step: names are known now
+            self._fused_checked = True
+            if not self.optim.supports_fused([n for n, _, _ in sites]):
+                if self._strict:
+                    raise NotImplementedError(self._NEEDS)
+                self.cuda_graph = False                          # auto mode: this and every later step run eagerly
+                return self._finish_eager(loss, sites)
         self.optim.fused_step(sites)                             # free mask + Adam in one launch
         for _, p, _ in sites:
             p.grad = None
@@ -324,13 +373,15 @@ class SVI:
                 return self._step_device(*args, **kwargs)
             torch.cuda.synchronize()
             g = torch.cuda.CUDAGraph()
-            host_steps = self.optim._steps_host
+            host_steps, calls0 = self.optim._steps_host, owner._calls
             with torch.cuda.graph(g):
                 self._static_loss = self._step_device(*args, **kwargs)
             self.optim._steps_host = host_steps                  # capture does not execute
+            self._calls_per_iter, owner._calls = owner._calls - calls0, calls0
             self._graph = g
         self._graph.replay()
         self.optim._steps_host += 1
+        owner._calls += self._calls_per_iter                     # the noise calls the replay just made on the device
         return self._static_loss
 
     def step(self, *args, **kwargs) -> float:

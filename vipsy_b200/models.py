@@ -157,12 +157,15 @@ class BasePsy(nn.Module):               # vi.py:521-533
         counter read from device memory and the draws are injected (``eps`` / ``u``): identical streams."""
         self._calls += 1
         if not self._device_rng or kind is None:
+            if self._calls_dev is not None:       # both counters advance on every call: one stream across modes
+                self._calls_dev.add_(1)
             return dict(seed=self._seed, offset=self._calls, person_offset=self.person_offset)
-        if self._calls_dev is None:
-            self._calls_dev = torch.zeros(1, dtype=torch.int64, device=self.device)
+        if self._calls_dev is None:   # starts at the host count: eager evaluations before a captured fit are not replayed
+            self._calls_dev = torch.full((1,), self._calls - 1, dtype=torch.int64, device=self.device)
         self._calls_dev.add_(1)
         fill = ops.fill_normal if kind == "eps" else ops.fill_uniform
-        # the eager counter and the device counter advance together, so switching modes keeps one stream
+        # the host counter and the device counter advance together (SVI adds the replayed calls to the host
+        # count), so switching between eager, captured and read-out calls never reuses a (seed, offset) stream
         return {kind: fill(S, B, K, self._seed, self._calls_dev, self.person_offset,
                            device=self.device)}
 
@@ -212,8 +215,8 @@ class BasePsy(nn.Module):               # vi.py:521-533
         iterations are launch- and interpreter-bound (c1: 570 -> 29 us); large ones still shed the ~0.5 ms of host
         glue per step.  Pass cuda_graph=False for the eager form (torch.optim objects between launches)."""
         if cuda_graph is None:
-            cuda_graph = self.reducer is None
-        return bool(cuda_graph) and optim.supports_fused()
+            return None if self.reducer is None else False     # None: SVI captures when the optimiser allows it
+        return bool(cuda_graph)
 
     def _fit_loop(self, svi, optim, max_iter, postfix_fn, evaluate=False):
         it = trange(max_iter) if trange is not None else range(max_iter)
@@ -559,7 +562,8 @@ class VCCDM(BaseCDM):                   # vi.py:819-863  (exact enumeration of t
         _, _, g, s = self._gs()
         extra, _, _ = self._enum_extra(None, self.sample_size)
         extra = {k: v for k, v in extra.items() if k != "want_posterior"}
-        r = ops.cdm_enum_elbo_grad(self._codes, self._qmask, g, s, n_attrs=self.attr_size, model=self._model,
+        r = ops.cdm_enum_elbo_grad(self._codes, self._qmask, g, s, n_attrs=self.attr_size,
+                                   model="dina" if isinstance(self, VCHoDina) else self._model,     # vi.py:905
                                    want_grad=False, want_posterior=True, **extra, **self._noise_args())
         return r["posterior"]
 
