@@ -174,6 +174,45 @@ size_t vipsy_irt_host_scratch_bytes(const VipsyIrtHostArgs* args);
 int vipsy_irt_host_step(const VipsyIrtHostArgs* args);
 
 /* ------------------------------------------------------------------------
+ * Amortised multivariate-normal guide: VaeIRT.guide for K > 1 (vi.py:685-693) with the tail of MvnEncoder
+ * (vi.py:438-455) fused in.  The reference computes, per step and for the B batch rows,
+ *     hidden = softplus(fc1(x));  loc = fc21(hidden);  raw = fc22(hidden)            (vi.py:446-451)
+ *     L = tril(scatter(raw), -1) + diag(exp(diag))   (vi.py:452-454 + LowerCholeskyTransform, vi.py:693)
+ *     x = loc + L eps  ~  MultivariateNormal(loc, scale_tril = L)                    (vi.py:693, rsample)
+ * and backpropagates through all of it.  raw is B x K(K+1)/2 floats (4 GB for 200 000 persons at K = 100) that
+ * are written once and read once, and so is its gradient.  This entry takes `hidden` and `loc` (B x H and
+ * B x K -- the caller keeps fc1 / fc21 in its framework, as north_star asks for the encoder MLP) and evaluates
+ * fc22 on the tensor cores inside the sampler: factor rows are consumed straight from tensor memory, then the
+ * likelihood contraction of vipsy_irt_elbo_grad runs, and the backward pass forms d fc22.weight, d fc22.bias
+ * and d hidden from the outer products (d loss / d x)(eps)^T on chip.  Neither raw nor its gradient ever
+ * exists in HBM.  Packed order of raw: torch.tril_indices(K, K), row-major (vi.py:453).
+ *
+ * `irt` supplies sizes, data, item parameters, mu (= loc), noise, the loss and d_mu / item-gradient outputs exactly
+ * as for vipsy_irt_elbo_grad; its sigma / chol / d_sigma / d_chol / workspace fields are ignored
+ * (cov_mode PERSON, pathwise estimator, K >= 2).  H <= 64.
+ * ---------------------------------------------------------------------- */
+typedef struct VipsyMvnEncoderIrtArgs {
+  VipsyIrtArgs irt;
+  int32_t n_hidden;        /* H                                                                         */
+  int32_t reserved;
+  const float* hidden;     /* B x H   softplus(fc1(x)) of the batch rows (in batch order)                */
+  const float* w22;        /* K(K+1)/2 x H   fc22.weight                                                 */
+  const float* b22;        /* K(K+1)/2       fc22.bias                                                   */
+  float* d_hidden;         /* B x H   d loss / d hidden through fc22 (fc21's share follows from d_mu)    */
+  float* d_w22;            /* K(K+1)/2 x H                                                               */
+  float* d_b22;            /* K(K+1)/2                                                                   */
+  void* workspace;
+  size_t workspace_bytes;  /* >= vipsy_irt_mvn_encoder_workspace_bytes()                                 */
+} VipsyMvnEncoderIrtArgs;
+size_t vipsy_irt_mvn_encoder_workspace_bytes(const VipsyMvnEncoderIrtArgs* args);
+/* loss + every gradient (NULL gradient pointers: the value only, evaluate_loss) */
+int vipsy_irt_mvn_encoder_elbo_grad(const VipsyMvnEncoderIrtArgs* args, void* stream);
+/* The guide's sample site alone (vi.py:693): x [S][B][K] = loc + L eps, the draws eps [S][B][K], diag L [B][K]
+ * and logdet [B] = sum_i log L_ii.  Any output may be NULL.  Uses args->workspace like the full entry. */
+int vipsy_mvn_encoder_sample(const VipsyMvnEncoderIrtArgs* args, float* x, float* eps_out, float* diag, float* logdet,
+                             void* stream);
+
+/* ------------------------------------------------------------------------
  * Enumerated CDMs: TraceEnum_ELBO over VCCDM.model (vi.py:839-857), optionally
  * with the HO-DINA pattern prior and Gaussian guide of VCHoDina (vi.py:897-934).
  *

@@ -60,6 +60,14 @@ class IrtHostArgs(C.Structure):
     ]
 
 
+class MvnEncoderIrtArgs(C.Structure):
+    _fields_ = [
+        ("irt", IrtArgs), ("n_hidden", C.c_int32), ("reserved", C.c_int32),
+        ("hidden", _p), ("w22", _p), ("b22", _p), ("d_hidden", _p), ("d_w22", _p), ("d_b22", _p),
+        ("workspace", _p), ("workspace_bytes", C.c_size_t),
+    ]
+
+
 class CdmEnumArgs(C.Structure):
     _fields_ = [
         ("n_rows", C.c_int64), ("batch", C.c_int64),
@@ -114,6 +122,7 @@ SYMBOLS = {
     "vipsy_irt_elbo_grad": (C.c_int, [C.POINTER(IrtArgs), _p]),
     "vipsy_irt_host_scratch_bytes": (C.c_size_t, [C.POINTER(IrtHostArgs)]),
     "vipsy_irt_host_step": (C.c_int, [C.POINTER(IrtHostArgs)]),
+    "vipsy_mvn_encoder_sample": (C.c_int, [C.POINTER(MvnEncoderIrtArgs), _p, _p, _p, _p, _p]),
     "vipsy_cdm_enum_workspace_bytes": (C.c_size_t, [C.POINTER(CdmEnumArgs)]),
     "vipsy_cdm_enum_elbo_grad": (C.c_int, [C.POINTER(CdmEnumArgs), _p]),
     "vipsy_cdm_score_workspace_bytes": (C.c_size_t, [C.POINTER(CdmScoreArgs)]),

@@ -327,6 +327,49 @@ def irt_elbo_grad(
     return out
 
 
+MVN_ENCODER_MAX_HIDDEN = 64
+
+
+def _mvn_workspace_bytes(K: int, H: int) -> int:
+    """Bytes of the fc22 operand image (csrc/enc_mvn.cuh: mv_chunks x mv_chunk_bytes, rounded to 256)."""
+    nb = (K + 7) // 8
+    pp = 32 * nb * (nb + 1)
+    kh = (H + 1 + 15) // 16 * 16
+    return ((pp + 127) // 128 * (2 * 128 * kh * 2) + 255) & ~255
+
+
+def mvn_encoder_sample(mu: torch.Tensor, hidden: torch.Tensor, w22: torch.Tensor, b22: torch.Tensor, *,
+                       eps: Optional[torch.Tensor] = None, n_particles: int = 1, seed: int = 0, offset: int = 0,
+                       person_offset: int = 0) -> Dict[str, torch.Tensor]:
+    """The sample site of VaeIRT's amortised MVN guide (vi.py:693) with MvnEncoder's fc22 fused in:
+    x [S, B, K] = mu + L eps with L = tril(raw, -1) + diag(exp(raw_ii)), raw = fc22(hidden) evaluated on the
+    tensor cores and consumed on chip.  Also returns the draws, diag L and sum_i log L_ii."""
+    mu_, h_, w_, b_ = _f32(mu, "mu"), _f32(hidden, "hidden"), _f32(w22, "w22"), _f32(b22, "b22")
+    B, K = mu_.shape
+    H = h_.shape[1]
+    if h_.shape[0] != B or w_.shape != (K * (K + 1) // 2, H) or b_.numel() != K * (K + 1) // 2:
+        raise ValueError("hidden must be B x H, w22 K(K+1)/2 x H, b22 K(K+1)/2")
+    eps_ = _f32(eps, "eps", None)
+    S = int(n_particles) if eps_ is None else eps_.numel() // max(B * K, 1)
+    dev = mu_.device
+    a = N.MvnEncoderIrtArgs()
+    a.irt.batch = a.irt.n_rows = B
+    a.irt.n_dims, a.irt.n_particles, a.irt.n_items = K, S, 1
+    a.irt.mu, a.irt.eps = _ptr(mu_), _ptr(eps_)
+    a.irt.seed, a.irt.offset, a.irt.person_offset = seed, offset, person_offset
+    a.n_hidden, a.hidden, a.w22, a.b22 = H, _ptr(h_), _ptr(w_), _ptr(b_)
+    ws = _workspace("mvn_sample", _mvn_workspace_bytes(K, H), dev)
+    a.workspace, a.workspace_bytes = _ptr(ws), ws.numel()
+    out = {"x": torch.empty((S, B, K), dtype=torch.float32, device=dev),
+           "eps": torch.empty((S, B, K), dtype=torch.float32, device=dev),
+           "diag": torch.empty((B, K), dtype=torch.float32, device=dev),
+           "logdet": torch.empty(B, dtype=torch.float32, device=dev)}
+    N.check(N.lib().vipsy_mvn_encoder_sample(C.byref(a), _ptr(out["x"]), _ptr(out["eps"]), _ptr(out["diag"]),
+                                             _ptr(out["logdet"]), _stream()))
+    out["_keepalive"] = (mu_, h_, w_, b_, eps_, ws)
+    return out
+
+
 def cdm_enum_elbo_grad(
     y: torch.Tensor,                     # n_rows x J uint8 codes
     q: torch.Tensor,                     # K x J 0/1 Q-matrix (or J int32 masks from qmask_from_q)
