@@ -122,6 +122,8 @@ SYMBOLS = {
     "vipsy_irt_elbo_grad": (C.c_int, [C.POINTER(IrtArgs), _p]),
     "vipsy_irt_host_scratch_bytes": (C.c_size_t, [C.POINTER(IrtHostArgs)]),
     "vipsy_irt_host_step": (C.c_int, [C.POINTER(IrtHostArgs)]),
+    "vipsy_irt_mvn_encoder_workspace_bytes": (C.c_size_t, [C.POINTER(MvnEncoderIrtArgs)]),
+    "vipsy_irt_mvn_encoder_elbo_grad": (C.c_int, [C.POINTER(MvnEncoderIrtArgs), _p]),
     "vipsy_mvn_encoder_sample": (C.c_int, [C.POINTER(MvnEncoderIrtArgs), _p, _p, _p, _p, _p]),
     "vipsy_cdm_enum_workspace_bytes": (C.c_size_t, [C.POINTER(CdmEnumArgs)]),
     "vipsy_cdm_enum_elbo_grad": (C.c_int, [C.POINTER(CdmEnumArgs), _p]),

@@ -5,14 +5,14 @@ namespace vipsy {
 size_t irt_uni_workspace_bytes(const VipsyIrtArgs* a);
 int irt_uni_launch(const VipsyIrtArgs* a, cudaStream_t st);
 size_t mirt_workspace_bytes(const VipsyIrtArgs* a);
-int mirt_launch(const VipsyIrtArgs* a, cudaStream_t st);
+struct MvnEncParams;
+int mirt_launch(const VipsyIrtArgs* a, cudaStream_t st, MvnEncParams* enc);
 int umma_selftest_launch(const float* t1, int R1, int C1, const float* t2, int R2, int C2, float* out, int variant,
                          int swap, int n_split, cudaStream_t st);
 }  // namespace vipsy
 
-using namespace vipsy;
-
-static int check_irt(const VipsyIrtArgs* a) {
+namespace vipsy {
+int check_irt(const VipsyIrtArgs* a) {
   VIPSY_REQUIRE(a != nullptr, VIPSY_ERR_ARG, "vipsy_irt: args is NULL");
   VIPSY_REQUIRE(a->model >= VIPSY_IRT_1PL && a->model <= VIPSY_IRT_4PL, VIPSY_ERR_ARG,
                 "vipsy_irt: unknown model %d (IRT_FUN has irt_1pl..irt_4pl)", a->model);
@@ -36,6 +36,9 @@ static int check_irt(const VipsyIrtArgs* a) {
   }
   return VIPSY_OK;
 }
+}  // namespace vipsy
+
+using namespace vipsy;
 
 extern "C" {
 
@@ -70,7 +73,7 @@ int vipsy_irt_elbo_grad(const VipsyIrtArgs* a, void* stream) {
   if (a->n_dims == 1) return irt_uni_launch(a, (cudaStream_t)stream);
   VIPSY_REQUIRE(a->model != VIPSY_IRT_1PL, VIPSY_ERR_ARG,
                 "vipsy_irt_elbo_grad: irt_1pl is D*(x+b) (vi.py:29): defined for K == 1 only");
-  return mirt_launch(a, (cudaStream_t)stream);
+  return mirt_launch(a, (cudaStream_t)stream, nullptr);
 }
 
 int vipsy_selftest_umma(const float* t1, int32_t r1, int32_t c1, const float* t2, int32_t r2, int32_t c2, float* out,

@@ -21,6 +21,7 @@ constexpr float kLn2 = 0.6931471805599453f;
 constexpr int kNumSMs = 148;
 
 void set_error(const char* fmt, ...);
+int check_irt(const VipsyIrtArgs* a);      // argument validation shared by the IRT entry points (api.cu)
 
 #define VIPSY_CUDA_CHECK(expr)                                                       \
   do {                                                                               \

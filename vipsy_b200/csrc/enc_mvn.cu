@@ -56,12 +56,14 @@ __device__ __forceinline__ void mv_row_of(int pc, int& i, int& j) {
   j = 8 * Jc + (pc & 7);
 }
 
+// img  (forward):  chunks of 128 padded columns x KH = [hidden | 1 | 0], hi tile then lo tile, rows = columns of L
+// imgb (backward): units of 64 padded columns x NH hidden units (no bias column), hi tile then lo tile
 __global__ void mvn_prep_kernel(const float* __restrict__ w22, const float* __restrict__ b22, int K, int H, int KH,
-                                int n_chunks, unsigned char* __restrict__ img) {
+                                int NH, int n_chunks, unsigned char* __restrict__ img, unsigned char* __restrict__ imgb) {
   const int n_oct = KH / 8;
   const int total = n_chunks * kMvCN * n_oct;
-  const uint32_t RS = (uint32_t)n_oct * kCSb;
-  const size_t tile_bytes = (size_t)kMvCN * KH * 2;
+  const uint32_t RS = (uint32_t)n_oct * kCSb, RSb = (uint32_t)(NH / 8) * kCSb;
+  const size_t tile_bytes = (size_t)kMvCN * KH * 2, tileb_bytes = (size_t)64 * NH * 2;
   for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
     const int pc = e / n_oct, o = e - pc * n_oct;
     int i, j;
@@ -84,6 +86,18 @@ __global__ void mvn_prep_kernel(const float* __restrict__ w22, const float* __re
     unsigned char* base = img + (size_t)c * 2 * tile_bytes + (size_t)(r >> 3) * RS + (size_t)o * kCSb + (r & 7) * 16;
     *reinterpret_cast<uint4*>(base) = hi;
     *reinterpret_cast<uint4*>(base + tile_bytes) = lo;
+    if (imgb && o * 8 < NH) {
+      if (o * 8 + 8 > H) {                      // the octet that holds the bias column forward: weights only here
+#pragma unroll
+        for (int t = 0; t < 8; ++t)
+          if (o * 8 + t >= H) v[t] = 0.f;
+        split8(v, hi, lo);
+      }
+      const int u = pc >> 6, ru = pc & 63;
+      unsigned char* bb = imgb + (size_t)u * 2 * tileb_bytes + (size_t)(ru >> 3) * RSb + (size_t)o * kCSb + (ru & 7) * 16;
+      *reinterpret_cast<uint4*>(bb) = hi;
+      *reinterpret_cast<uint4*>(bb + tileb_bytes) = lo;
+    }
   }
 }
 
@@ -299,23 +313,43 @@ __global__ void __launch_bounds__(kFwThreads, 1) mvn_fwd_kernel(const MvnEncPara
               }
               if (Jc == I) {                                      // diagonal block: rows 8I .. 8I+7 are complete
                 const float ev[8] = {e0.x, e0.y, e0.z, e0.w, e1.x, e1.y, e1.z, e1.w};
+                float xo[8], lo8[8];
 #pragma unroll
                 for (int r = 0; r < 8; ++r) {
                   const int i = 8 * I + r;
+                  const float dv = v[9 * r];                     // 64 raw_ii
+                  const float dr = dv * inv_scale;
+                  const float lii = __expf(dr);
+                  const float xv = mu_r[r] + fmaf(lii * kMvWScale - dv, ev[r], acc[r]);    // exp(raw_ii) eps_i for raw_ii eps_i
+                  xo[r] = xv; lo8[r] = lii;
                   if (i < K) {
-                    const float dv = v[9 * r];                   // 64 raw_ii
-                    const float dr = dv * inv_scale;
-                    const float lii = __expf(dr);
-                    const float xv = mu_r[r] + fmaf(lii * kMvWScale - dv, ev[r], acc[r]);  // exp(raw_ii) eps_i for raw_ii eps_i
-                    if (live) {
-                      if (xr) xr[i] = xv;
-                      if (s == 0 && m.diagL) m.diagL[b * K + i] = lii;
-                    }
                     auxp = fmaf(-0.5f * xv, xv, auxp);
                     if (s == 0) logdet += dr;
                   }
                   acc[r] = 0.f;
                   mu_r[r] = i + 8 < K ? mur[i + 8] : 0.f;
+                }
+                if (live) {                                       // 32-byte pieces of the person's rows: whole sectors
+                  const int i0 = 8 * I;
+                  const bool wd = s == 0 && m.diagL != nullptr;
+                  if ((K & 3) == 0) {
+                    if (xr) {
+                      *reinterpret_cast<float4*>(xr + i0) = make_float4(xo[0], xo[1], xo[2], xo[3]);
+                      if (i0 + 4 < K) *reinterpret_cast<float4*>(xr + i0 + 4) = make_float4(xo[4], xo[5], xo[6], xo[7]);
+                    }
+                    if (wd) {
+                      float* dg = m.diagL + b * K + i0;
+                      *reinterpret_cast<float4*>(dg) = make_float4(lo8[0], lo8[1], lo8[2], lo8[3]);
+                      if (i0 + 4 < K) *reinterpret_cast<float4*>(dg + 4) = make_float4(lo8[4], lo8[5], lo8[6], lo8[7]);
+                    }
+                  } else {
+#pragma unroll
+                    for (int r = 0; r < 8; ++r)
+                      if (i0 + r < K) {
+                        if (xr) xr[i0 + r] = xo[r];
+                        if (wd) m.diagL[b * K + i0 + r] = lo8[r];
+                      }
+                  }
                 }
                 ++I; Jc = 0;
               } else {
@@ -337,12 +371,530 @@ __global__ void __launch_bounds__(kFwThreads, 1) mvn_fwd_kernel(const MvnEncPara
   if (warp == kFwEpiWarps + 1) umma::tmem_dealloc(tmem, 512);
 }
 
+
+// ------------------------------------------------------------------------------------------------ tail of the likelihood
+// G = -(scale / S) (sum over item tiles of d lb / d x  -  x)  (the prior's share is -x), written over plane 0 of gx;
+// d_mu = sum_s G (the pathwise gradient of the location is the gradient of x); loss partial per CTA from the
+// log-likelihood rows and the forward kernel's aux word.  What mirt_cholgrad_* does, minus the factor gradient.
+constexpr int kTailThreads = 256;
+__global__ void __launch_bounds__(kTailThreads) mvn_tail_kernel(const MirtParams p, float* __restrict__ gmax) {
+  __shared__ double red[kTailThreads / 32];
+  const int K = p.K, S = p.S;
+  const int64_t BK = p.B * K, R = (int64_t)S * p.B;
+  const float kf = -p.scale / (float)S;
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (int64_t)gridDim.x * blockDim.x;
+  if (p.d_mu) {
+    float gm = 0.f;
+    for (int64_t e = tid; e < BK; e += nth) {
+      float t = 0.f;
+      for (int s = 0; s < S; ++s) {
+        const int64_t at = (int64_t)s * BK + e;
+        float g = -p.x[at];
+        for (int part = 0; part < p.n_parts; ++part) g += p.gx[(int64_t)part * R * K + at];
+        g *= kf;
+        p.gx[at] = g;
+        gm = fmaxf(gm, fabsf(g));
+        t += g;
+      }
+      p.d_mu[e] = t;
+    }
+    gm = warp_max(gm);                                  // a maximum: independent of the order, hence deterministic
+    if ((threadIdx.x & 31) == 0 && gm > 0.f) atomicMax(reinterpret_cast<int*>(gmax), __float_as_int(gm));
+  }
+  double acc = 0.0;
+  for (int64_t b = tid; b < p.B; b += nth) {
+    float ell = 0.f;
+    for (int s = 0; s < S; ++s)
+      for (int part = 0; part < p.n_parts; ++part) ell += p.ell[(int64_t)part * R + (int64_t)s * p.B + b];
+    const float4 ax = *reinterpret_cast<const float4*>(p.aux + 4 * b);
+    acc += (double)(kf * (ell + ((ax.x + ax.y) + (ax.z + ax.w))));
+  }
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < kTailThreads / 32; ++w) t += red[w];
+    p.loss_partial[blockIdx.x] = t;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ backward
+constexpr int kBwGenWarps = 16;                        // warps 0-15 generate V: thread = (person, pair of rows of a unit)
+constexpr int kBwGen = kBwGenWarps * 32;
+constexpr int kBwThreads = kBwGen + 64;                // + warp 16: bulk-copy producer, warp 17: MMA issuer
+
+__device__ __forceinline__ void gen_bar() { asm volatile("bar.sync 1, %0;" ::"n"(kBwGen) : "memory"); }
+
+__device__ __forceinline__ void unit_to_block(int u, int& I, int& Jc) {
+  I = 0;
+  while ((I + 1) * (I + 2) / 2 <= u) ++I;
+  Jc = u - I * (I + 1) / 2;
+}
+
+// The draws of 128 persons (one particle) -> shared memory rows er[person][0..K), read back coalesced.
+__device__ __forceinline__ void load_eps_tile(const float* __restrict__ src /* [B][K] of this particle */, int64_t b0,
+                                              int64_t B, int K, float* eps_s, int ES, int warp, int lane) {
+  constexpr int PW = kMvTP / kBwGenWarps;               // persons per warp
+  for (int pp = 0; pp < PW; ++pp) {
+    const int t = warp * PW + pp;
+    const int64_t b = b0 + t;
+    float* er = eps_s + (size_t)t * ES;
+    for (int k = lane; k < K; k += 32) er[k] = b < B ? src[b * K + k] : 0.f;
+  }
+}
+
+// One 64-column unit (block row I, block column Jc) of V = d loss / d raw for the thread's person, rows 2 sub and
+// 2 sub + 1 of the unit: V[(i, j)] = G_i eps_j; on the diagonal the exp chain rule and the entropy term:
+// d raw_ii = (G_i eps_i) L_ii - scale (mirt_cholgrad_kernel's rule for chol_raw).  fp16 hi / lo 16-byte pieces go to
+// the operand tile T[r = person][c = column] (K-major for V W, MN-major for V^T [hidden | 1]).
+__device__ __forceinline__ void gen_unit(unsigned char* Vh, unsigned char* Vl, uint32_t RS, int col0, const float* er,
+                                         int t, int sub, int I, int Jc, const float (&gI)[2], const float (&lI)[2],
+                                         const float (&dadd)[2]) {
+  const float4 e0 = *reinterpret_cast<const float4*>(er + 8 * Jc);
+  const float4 e1 = *reinterpret_cast<const float4*>(er + 8 * Jc + 4);
+  const float ev[8] = {e0.x, e0.y, e0.z, e0.w, e1.x, e1.y, e1.z, e1.w};
+#pragma unroll
+  for (int rr = 0; rr < 2; ++rr) {
+    const int r = 2 * sub + rr;
+    float v[8];
+#pragma unroll
+    for (int jj = 0; jj < 8; ++jj) v[jj] = gI[rr] * ev[jj];
+    if (Jc == I) {
+#pragma unroll
+      for (int jj = 0; jj < 8; ++jj) v[jj] = jj == r ? fmaf(v[jj], lI[rr], dadd[rr]) : (jj > r ? 0.f : v[jj]);
+    }
+    uint4 hi, lo;
+    split8(v, hi, lo);
+    const uint32_t off = (uint32_t)(t >> 3) * RS + (uint32_t)((col0 >> 3) + r) * kCSb + (uint32_t)(t & 7) * 16u;
+    *reinterpret_cast<uint4*>(Vh + off) = hi;
+    *reinterpret_cast<uint4*>(Vl + off) = lo;
+  }
+}
+
+// G rows 8I + 2 sub + {0, 1} of the thread's person (0 beyond K / B), the diagonal of L for them and the entropy term
+__device__ __forceinline__ void load_g(const MirtParams& m, int s, int64_t b, bool live, int I, int sub, float ginv,
+                                       float (&gI)[2], float (&lI)[2], float (&dadd)[2]) {
+#pragma unroll
+  for (int rr = 0; rr < 2; ++rr) {
+    const int i = 8 * I + 2 * sub + rr;
+    const bool ok = live && i < m.K;
+    gI[rr] = ok ? ginv * m.gx[((int64_t)s * m.B + b) * m.K + i] : 0.f;
+    lI[rr] = ok ? m.diagL[b * m.K + i] : 0.f;
+    dadd[rr] = (ok && s == 0) ? -m.scale * ginv : 0.f;
+  }
+}
+
+// ---- d hidden[person][h] = (1 / 64) sum_p V[person][p] (64 W22)[p][h]: CTAs own person tiles, every unit of V ------
+struct DhSmem {
+  uint32_t offEps, offV, offW, total, v_bytes, w_bytes;
+  int ES, nst;
+};
+__host__ __device__ inline DhSmem dh_smem(int K, int H) {
+  DhSmem s;
+  s.ES = (K + 7) / 8 * 8 + 4;
+  s.v_bytes = 2u * kMvTP * 64 * 2;                      // hi + lo, 128 persons x 64 columns
+  s.w_bytes = 2u * 64 * (uint32_t)mv_nh(H) * 2;         // hi + lo, 64 columns x NH
+  s.nst = 3;
+  uint32_t o = 0;
+  s.offEps = o; o += (uint32_t)kMvTP * s.ES * 4;
+  s.offV = o; o += 2 * s.v_bytes;
+  s.offW = o; o += (uint32_t)s.nst * s.w_bytes;
+  s.total = o;
+  return s;
+}
+
+__global__ void __launch_bounds__(kBwThreads, 1) mvn_bwd_dh_kernel(const MvnEncParams P) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  __shared__ uint64_t bar_vfull[2], bar_vfree[2], bar_wfull[3], bar_wempty[3], bar_dfull, bar_dfree;
+  __shared__ uint32_t tmem_base_sm;
+  const MirtParams& m = P.m;
+  const int K = m.K, S = m.S, H = P.H, NH = mv_nh(H), NB = mv_nb(K), NU = NB * (NB + 1) / 2;
+  const DhSmem L = dh_smem(K, H);
+  const int ES = L.ES;
+  float* eps_s = reinterpret_cast<float*>(smem + L.offEps);
+  unsigned char* Vb = smem + L.offV;
+  unsigned char* Wb = smem + L.offW;
+  const uint32_t RSV = (64 / 8) * kCSb, RSW = (uint32_t)(NH / 8) * kCSb;
+  // The tensor core adds into its fp32 accumulator with truncation: a long chain of accumulating MMAs drifts by
+  // ~2^-24 of the running sum per instruction (measured: 2e-5 relative over the 1092 MMAs of a K = 100 tile).
+  // The units therefore go round-robin into NACC independent accumulators, summed (round-to-nearest) at the drain.
+  const uint32_t NACC = 512u / (uint32_t)NH < 8u ? 512u / (uint32_t)NH : 8u;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int64_t n_tiles = (m.B + kMvTP - 1) / kMvTP;
+  const float* eps_src = m.eps ? m.eps : P.eps_out;
+  // V is an fp16 hi/lo operand: G is scaled by a power of two so that max |G'| <= 16 (exact; undone at the drain)
+  int gexp;
+  frexpf(fmaxf(*P.gmax, m.scale), &gexp);
+  const float ginv = ldexpf(1.f, 4 - gexp), gfix = ldexpf(1.f, gexp - 4);
+
+  if (tid == 0) {
+    for (int i = 0; i < 2; ++i) { umma::mbar_init(&bar_vfull[i], kBwGen); umma::mbar_init(&bar_vfree[i], 1); }
+    for (int i = 0; i < 3; ++i) { umma::mbar_init(&bar_wfull[i], 1); umma::mbar_init(&bar_wempty[i], 1); }
+    umma::mbar_init(&bar_dfull, 1);
+    umma::mbar_init(&bar_dfree, 128);
+    umma::fence_mbar_init();
+  }
+  if (warp == kBwGenWarps + 1) umma::tmem_alloc(&tmem_base_sm, 512);
+  umma::fence_before_sync();
+  __syncthreads();
+  umma::fence_after_sync();
+  const uint32_t tmem = tmem_base_sm;
+
+  if (warp == kBwGenWarps) {
+    if (lane == 0) {                                   // bulk-copy producer: the units of the backward image
+      uint32_t it = 0;
+      for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x)
+        for (int s = 0; s < S; ++s)
+          for (int u = 0; u < NU; ++u, ++it) {
+            const uint32_t st = it % 3, round = it / 3;
+            umma::mbar_wait(&bar_wempty[st], (round & 1) ^ 1);
+            umma::bulk_load(Wb + (size_t)st * L.w_bytes, P.wimg_b + (size_t)u * L.w_bytes, L.w_bytes, &bar_wfull[st]);
+          }
+    }
+  } else if (warp == kBwGenWarps + 1) {
+    if (lane == 0) {                                   // MMA issuer
+      const uint32_t idesc = umma::make_idesc_f16(kMvTP, NH, umma::kMajorK, umma::kMajorMN);
+      uint32_t it = 0, ntile = 0;
+      for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++ntile) {
+        umma::mbar_wait(&bar_dfree, (ntile & 1) ^ 1);
+        umma::fence_after_sync();
+        uint32_t nu = 0;
+        for (int s = 0; s < S; ++s)
+          for (int u = 0; u < NU; ++u, ++it, ++nu) {
+            const uint32_t vb = it & 1, st = it % 3;
+            const uint32_t ai = nu % NACC;               // round-robin over the accumulators (see NACC)
+            uint32_t acc = nu < NACC ? 0u : 1u;
+            umma::mbar_wait(&bar_vfull[vb], (it >> 1) & 1);
+            umma::mbar_wait(&bar_wfull[st], (it / 3) & 1);
+            umma::fence_after_sync();
+            const uint32_t sVh = umma::smem_u32(Vb + (size_t)vb * L.v_bytes), sVl = sVh + L.v_bytes / 2;
+            const uint32_t sWh = umma::smem_u32(Wb + (size_t)st * L.w_bytes), sWl = sWh + L.w_bytes / 2;
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) {
+#pragma unroll
+              for (int term = 0; term < 3; ++term) {
+                const uint64_t da = umma::make_desc((term == 2 ? sVl : sVh) + ks * 2 * kCSb, kCSb, RSV);
+                const uint64_t db = umma::make_desc((term == 1 ? sWl : sWh) + ks * 2 * RSW, RSW, kCSb);
+                umma::mma_f16_ss(tmem + ai * NH, da, db, idesc, acc);
+                acc = 1;
+              }
+            }
+            umma::commit(&bar_vfree[vb]);
+            umma::commit(&bar_wempty[st]);
+          }
+        umma::commit(&bar_dfull);
+      }
+    }
+  } else {
+    const int t = tid & 127, sub = tid >> 7;
+    float* er = eps_s + (size_t)t * ES;
+    if (sub == 0)
+      for (int k = K; k < ES; ++k) er[k] = 0.f;
+    uint32_t it = 0, ntile = 0;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++ntile) {
+      const int64_t b = tile * kMvTP + t;
+      const bool live = b < m.B;
+      for (int s = 0; s < S; ++s) {
+        gen_bar();                                     // everyone has finished with the previous draws
+        load_eps_tile(eps_src + (int64_t)s * m.B * K, tile * kMvTP, m.B, K, eps_s, ES, warp, lane);
+        gen_bar();
+        int I = 0, Jc = 0;
+        float gI[2], lI[2], dadd[2];
+        load_g(m, s, b, live, 0, sub, ginv, gI, lI, dadd);
+        for (int u = 0; u < NU; ++u, ++it) {
+          const uint32_t vb = it & 1;
+          umma::mbar_wait(&bar_vfree[vb], ((it >> 1) & 1) ^ 1);
+          unsigned char* Vh = Vb + (size_t)vb * L.v_bytes;
+          gen_unit(Vh, Vh + L.v_bytes / 2, RSV, 0, er, t, sub, I, Jc, gI, lI, dadd);
+          umma::fence_proxy_async();
+          umma::mbar_arrive(&bar_vfull[vb]);
+          if (Jc == I) { ++I; Jc = 0; if (I < NB) load_g(m, s, b, live, I, sub, ginv, gI, lI, dadd); }
+          else ++Jc;
+        }
+      }
+      if (warp < 4) {                                  // drain d hidden of this tile: thread = person = TMEM lane
+        umma::mbar_wait(&bar_dfull, ntile & 1);
+        umma::fence_after_sync();
+        const uint32_t tl = tmem + ((uint32_t)(warp * 32) << 16);
+        const float dfix = gfix / kMvWScale;
+        const uint32_t n_used = (uint32_t)(S * NU) < NACC ? (uint32_t)(S * NU) : NACC;
+        for (int c0 = 0; c0 < NH; c0 += 16) {
+          float v[16];
+          umma::tmem_ld16(tl + c0, v);
+          for (uint32_t ai = 1; ai < n_used; ++ai) {
+            float w[16];
+            umma::tmem_ld16(tl + ai * NH + c0, w);
+#pragma unroll
+            for (int q = 0; q < 16; ++q) v[q] += w[q];
+          }
+          if (live && P.d_hidden) {
+            float* dst = P.d_hidden + b * H + c0;
+            if ((H & 3) == 0 && c0 + 16 <= H) {
+#pragma unroll
+              for (int q = 0; q < 4; ++q)
+                *reinterpret_cast<float4*>(dst + 4 * q) = make_float4(v[4 * q] * dfix, v[4 * q + 1] * dfix,
+                                                                      v[4 * q + 2] * dfix, v[4 * q + 3] * dfix);
+            } else {
+#pragma unroll
+              for (int q = 0; q < 16; ++q)
+                if (c0 + q < H) dst[q] = v[q] * dfix;
+            }
+          }
+        }
+        umma::fence_before_sync();
+        umma::mbar_arrive(&bar_dfree);
+      }
+    }
+  }
+  umma::fence_before_sync();
+  __syncthreads();
+  umma::fence_after_sync();
+  if (warp == kBwGenWarps + 1) umma::tmem_dealloc(tmem, 512);
+}
+
+// ---- d [W22 | b22][(i,j)][h] = sum over persons of V[person][(i,j)] [hidden | 1][person][h] -------------------------
+// CTA (pg, qg): chunks [pg * CPB, ..) of the factor columns x person tiles qg, qg + n_qg, ..; the accumulators of the
+// slab stay in tensor memory over every tile; partial results [qg] are summed in a fixed order by mvn_dw_finalize.
+struct DwSmem {
+  uint32_t offEps, offV, offH, total, v_bytes, h_bytes;
+  int ES, nvb;
+};
+__host__ __device__ inline DwSmem dw_smem(int K, int H) {
+  DwSmem s;
+  s.ES = (K + 7) / 8 * 8 + 4;
+  s.v_bytes = 2u * kMvTP * kMvCN * 2;                   // hi + lo, 128 persons x 128 columns
+  s.h_bytes = 2u * kMvTP * (uint32_t)mv_kh(H) * 2;      // hi + lo, 128 persons x KH
+  uint32_t o = 0;
+  s.offEps = o; o += (uint32_t)kMvTP * s.ES * 4;
+  s.nvb = (o + 2 * s.v_bytes + s.h_bytes <= 227u * 1024u) ? 2 : 1;      // K > 112: one V buffer
+  s.offV = o; o += (uint32_t)s.nvb * s.v_bytes;
+  s.offH = o; o += s.h_bytes;
+  s.total = o;
+  return s;
+}
+__host__ __device__ inline int dw_cpb(int H) { return 512 / mv_kh(H) < 8 ? 512 / mv_kh(H) : 8; }   // chunks per CTA slab
+
+__global__ void __launch_bounds__(kBwThreads, 1) mvn_bwd_dw_kernel(const MvnEncParams P, const int n_pg, const int n_qg) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  __shared__ uint64_t bar_vfull[2], bar_vfree[2], bar_hfree, bar_done;
+  __shared__ uint32_t tmem_base_sm;
+  const MirtParams& m = P.m;
+  const int K = m.K, S = m.S, H = P.H, KH = mv_kh(H), NB = mv_nb(K), NU = NB * (NB + 1) / 2;
+  const DwSmem L = dw_smem(K, H);
+  const int ES = L.ES, CPB = dw_cpb(H), n_chunks = mv_chunks(K);
+  const uint32_t NVB = (uint32_t)L.nvb;
+  float* eps_s = reinterpret_cast<float*>(smem + L.offEps);
+  unsigned char* Vb = smem + L.offV;
+  unsigned char* Hh = smem + L.offH;
+  unsigned char* Hl = Hh + L.h_bytes / 2;
+  const uint32_t RSV = (kMvCN / 8) * kCSb, RSH = (uint32_t)(KH / 8) * kCSb;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int pg = blockIdx.x % n_pg, qg = blockIdx.x / n_pg;
+  const int c0 = pg * CPB, c1 = min(c0 + CPB, n_chunks), nblk = c1 - c0;
+  const int64_t n_tiles = (m.B + kMvTP - 1) / kMvTP;
+  const float* eps_src = m.eps ? m.eps : P.eps_out;
+  // V is an fp16 hi/lo operand: G is scaled by a power of two so that max |G'| <= 16 (exact; undone at the drain)
+  int gexp;
+  frexpf(fmaxf(*P.gmax, m.scale), &gexp);
+  const float ginv = ldexpf(1.f, 4 - gexp), gfix = ldexpf(1.f, gexp - 4);
+
+  if (tid == 0) {
+    for (int i = 0; i < 2; ++i) { umma::mbar_init(&bar_vfull[i], kBwGen); umma::mbar_init(&bar_vfree[i], 1); }
+    umma::mbar_init(&bar_hfree, 1);
+    umma::mbar_init(&bar_done, 1);
+    umma::fence_mbar_init();
+  }
+  if (warp == kBwGenWarps + 1) umma::tmem_alloc(&tmem_base_sm, 512);
+  umma::fence_before_sync();
+  __syncthreads();
+  umma::fence_after_sync();
+  const uint32_t tmem = tmem_base_sm;
+
+  if (warp == kBwGenWarps + 1) {
+    if (lane == 0) {                                   // MMA issuer
+      const uint32_t idesc = umma::make_idesc_f16(kMvCN, KH, umma::kMajorMN, umma::kMajorMN);
+      const uint32_t sHh = umma::smem_u32(Hh), sHl = umma::smem_u32(Hl);
+      uint32_t it = 0;
+      bool first = true;
+      for (int64_t tile = qg; tile < n_tiles; tile += n_qg) {
+        for (int s = 0; s < S; ++s)
+          for (int k = 0; k < nblk; ++k, ++it) {
+            const uint32_t vb = it % NVB;
+            umma::mbar_wait(&bar_vfull[vb], (it / NVB) & 1);         // V chunk (and, first of the tile, the H tile) staged
+            umma::fence_after_sync();
+            const uint32_t sVh = umma::smem_u32(Vb + (size_t)vb * L.v_bytes), sVl = sVh + L.v_bytes / 2;
+            uint32_t acc = (first && s == 0) ? 0u : 1u;
+#pragma unroll 1
+            for (int ks = 0; ks < kMvTP / 16; ++ks) {
+#pragma unroll
+              for (int term = 0; term < 3; ++term) {
+                const uint64_t da = umma::make_desc((term == 2 ? sVl : sVh) + ks * 2 * RSV, RSV, kCSb);
+                const uint64_t db = umma::make_desc((term == 1 ? sHl : sHh) + ks * 2 * RSH, RSH, kCSb);
+                umma::mma_f16_ss(tmem + k * KH, da, db, idesc, acc);
+                acc = 1;
+              }
+            }
+            umma::commit(&bar_vfree[vb]);
+          }
+        first = false;
+        umma::commit(&bar_hfree);                      // every MMA that reads this tile's H tile has completed
+      }
+      umma::commit(&bar_done);
+    }
+  } else if (warp < kBwGenWarps) {
+    const int t = tid & 127, sub = tid >> 7;
+    float* er = eps_s + (size_t)t * ES;
+    if (sub == 0)
+      for (int k = K; k < ES; ++k) er[k] = 0.f;
+    uint32_t it = 0, ntile = 0;
+    for (int64_t tile = qg; tile < n_tiles; tile += n_qg, ++ntile) {
+      const int64_t b = tile * kMvTP + t;
+      const bool live = b < m.B;
+      for (int s = 0; s < S; ++s) {
+        gen_bar();
+        load_eps_tile(eps_src + (int64_t)s * m.B * K, tile * kMvTP, m.B, K, eps_s, ES, warp, lane);
+        if (s == 0) {
+          // [hidden | 1 | 0] tile (MN-major B operand: T[r = person][c = h]); the previous tile's MMAs are done with it
+          umma::mbar_wait(&bar_hfree, (ntile & 1) ^ 1);
+          const float* hr = P.hidden + (live ? b : 0) * H;
+          for (int o = sub; o < KH / 8; o += kBwGen / 128) {
+            float v[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              const int k = o * 8 + q;
+              v[q] = !live ? 0.f : (k < H ? hr[k] : (k == H ? 1.f : 0.f));
+            }
+            uint4 hi, lo;
+            split8(v, hi, lo);
+            const uint32_t off = (uint32_t)(t >> 3) * RSH + (uint32_t)o * kCSb + (uint32_t)(t & 7) * 16u;
+            *reinterpret_cast<uint4*>(Hh + off) = hi;
+            *reinterpret_cast<uint4*>(Hl + off) = lo;
+          }
+        }
+        gen_bar();
+        for (int k = 0; k < nblk; ++k, ++it) {
+          const uint32_t vb = it % NVB;
+          umma::mbar_wait(&bar_vfree[vb], ((it / NVB) & 1) ^ 1);
+          unsigned char* Vh = Vb + (size_t)vb * L.v_bytes;
+#pragma unroll 1
+          for (int half = 0; half < 2; ++half) {
+            const int u = 2 * (c0 + k) + half;
+            int I, Jc;
+            unit_to_block(u, I, Jc);
+            float gI[2], lI[2], dadd[2];
+            load_g(m, s, b, live && u < NU, I, sub, ginv, gI, lI, dadd);
+            gen_unit(Vh, Vh + L.v_bytes / 2, RSV, 64 * half, er, t, sub, I < NB ? I : 0, I < NB ? Jc : 1, gI, lI, dadd);
+          }
+          umma::fence_proxy_async();
+          umma::mbar_arrive(&bar_vfull[vb]);
+        }
+      }
+    }
+    if (warp < 4) {                                    // drain: thread = factor column of the chunk = TMEM lane
+      umma::mbar_wait(&bar_done, 0);
+      umma::fence_after_sync();
+      const uint32_t tl = tmem + ((uint32_t)(warp * 32) << 16);
+      for (int k = 0; k < nblk; ++k) {
+        float* dst = P.dw_part + ((size_t)qg * n_chunks * kMvCN + (size_t)(c0 + k) * kMvCN + t) * KH;
+        for (int q0 = 0; q0 < KH; q0 += 16) {
+          float v[16];
+          umma::tmem_ld16(tl + k * KH + q0, v);
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            *reinterpret_cast<float4*>(dst + q0 + 4 * q) = make_float4(v[4 * q] * gfix, v[4 * q + 1] * gfix, v[4 * q + 2] * gfix, v[4 * q + 3] * gfix);
+        }
+      }
+      umma::fence_before_sync();
+    }
+  }
+  umma::fence_before_sync();
+  __syncthreads();
+  umma::fence_after_sync();
+  if (warp == kBwGenWarps + 1) umma::tmem_dealloc(tmem, 512);
+}
+
+// d_w22[p][h], d_b22[p] = sum over the person groups, in order, of the partial rows of padded column mv_col(i, j)
+__global__ void mvn_dw_finalize_kernel(const float* __restrict__ part, int n_qg, int n_cols, int K, int H, int KH,
+                                       float* __restrict__ d_w22, float* __restrict__ d_b22) {
+  const int P = K * (K + 1) / 2;
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < P * (H + 1); e += gridDim.x * blockDim.x) {
+    const int p = e / (H + 1), h = e - p * (H + 1);
+    int i = (int)((sqrtf(8.f * (float)p + 1.f) - 1.f) * 0.5f);
+    while (tri_off(i + 1) <= p) ++i;
+    while (tri_off(i) > p) --i;
+    const int j = p - tri_off(i);
+    const size_t pc = (size_t)mv_col(i, j);
+    float t = 0.f;
+    for (int q = 0; q < n_qg; ++q) t += part[((size_t)q * n_cols + pc) * KH + h];
+    if (h < H) { if (d_w22) d_w22[(size_t)p * H + h] = t; }
+    else if (d_b22) d_b22[p] = t;
+  }
+}
+
 }  // namespace
+
+
+size_t mvn_wimg_bytes(int K, int H) { return ((size_t)mv_chunks(K) * mv_chunk_bytes(H) + 255) & ~size_t(255); }
+size_t mvn_wimgb_bytes(int K, int H) {
+  return ((size_t)2 * mv_chunks(K) * (2 * 64 * mv_nh(H) * 2) + 255) & ~size_t(255);
+}
+static void dw_grid(int K, int H, int* n_pg, int* n_qg) {
+  const int cpb = dw_cpb(H), n_chunks = mv_chunks(K);
+  *n_pg = (n_chunks + cpb - 1) / cpb;
+  int q = num_sms() / *n_pg;
+  *n_qg = q < 1 ? 1 : q;
+}
+size_t mvn_dwpart_bytes(int K, int H) {
+  int n_pg, n_qg;
+  dw_grid(K, H, &n_pg, &n_qg);
+  return ((size_t)n_qg * mv_chunks(K) * kMvCN * mv_kh(H) * 4 + 255) & ~size_t(255);
+}
+
+int launch_mvn_tail(const MvnEncParams& P, int* loss_rows, cudaStream_t st) {
+  int64_t g = (P.m.B * P.m.K + kTailThreads * 4 - 1) / (kTailThreads * 4);
+  const int64_t cap = (int64_t)num_sms() * 8;
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  VIPSY_CUDA_CHECK(cudaMemsetAsync(P.gmax, 0, 4, st));
+  mvn_tail_kernel<<<(int)g, kTailThreads, 0, st>>>(P.m, P.gmax);
+  VIPSY_CUDA_CHECK(cudaGetLastError());
+  *loss_rows = (int)g;
+  return VIPSY_OK;
+}
+
+int launch_mvn_bwd(const MvnEncParams& P, cudaStream_t st) {
+  const int K = P.m.K, H = P.H;
+  const int64_t n_tiles = (P.m.B + kMvTP - 1) / kMvTP;
+  if (P.d_hidden) {
+    const DhSmem L = dh_smem(K, H);
+    VIPSY_CUDA_CHECK(cudaFuncSetAttribute(mvn_bwd_dh_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
+    int64_t g = num_sms();
+    if (g > n_tiles) g = n_tiles;
+    mvn_bwd_dh_kernel<<<(int)g, kBwThreads, L.total, st>>>(P);
+    VIPSY_CUDA_CHECK(cudaGetLastError());
+  }
+  if (P.d_w22 || P.d_b22) {
+    const DwSmem L = dw_smem(K, H);
+    VIPSY_REQUIRE(L.total <= 227 * 1024, VIPSY_ERR_UNSUPPORTED, "mvn encoder backward: K=%d H=%d does not fit shared memory", K, H);
+    VIPSY_CUDA_CHECK(cudaFuncSetAttribute(mvn_bwd_dw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
+    int n_pg, n_qg;
+    dw_grid(K, H, &n_pg, &n_qg);
+    if (n_qg > n_tiles) n_qg = (int)n_tiles;
+    mvn_bwd_dw_kernel<<<n_pg * n_qg, kBwThreads, L.total, st>>>(P, n_pg, n_qg);
+    VIPSY_CUDA_CHECK(cudaGetLastError());
+    const int total = K * (K + 1) / 2 * (H + 1);
+    mvn_dw_finalize_kernel<<<(total + 255) / 256, 256, 0, st>>>(P.dw_part, n_qg, mv_chunks(K) * kMvCN, K, H, mv_kh(H),
+                                                                P.d_w22, P.d_b22);
+    VIPSY_CUDA_CHECK(cudaGetLastError());
+  }
+  return VIPSY_OK;
+}
 
 int launch_mvn_prep(const MvnEncParams& P, cudaStream_t st) {
   const int KH = mv_kh(P.H), n_chunks = mv_chunks(P.m.K);
   const int total = n_chunks * kMvCN * (KH / 8);
-  mvn_prep_kernel<<<(total + 255) / 256, 256, 0, st>>>(P.w22, P.b22, P.m.K, P.H, KH, n_chunks, P.wimg);
+  mvn_prep_kernel<<<(total + 255) / 256, 256, 0, st>>>(P.w22, P.b22, P.m.K, P.H, KH, mv_nh(P.H), n_chunks, P.wimg, P.wimg_b);
   VIPSY_CUDA_CHECK(cudaGetLastError());
   return VIPSY_OK;
 }
@@ -383,13 +935,72 @@ static MvnEncParams mvn_params(const VipsyMvnEncoderIrtArgs* a) {
   return P;
 }
 
-size_t mvn_wimg_bytes(int K, int H) { return ((size_t)mv_chunks(K) * mv_chunk_bytes(H) + 255) & ~size_t(255); }
-
 }  // namespace vipsy
 
 using namespace vipsy;
 
 extern "C" {
+
+// workspace: [ mirt_layout of irt | fc22 operand images | the draws | partial d [W22 | b22] ]
+struct MvnLayout { size_t mirt, wimg, wimgb, eps, dwpart, gmax, total; };
+static MvnLayout mvn_layout(const VipsyMvnEncoderIrtArgs* a) {
+  const VipsyIrtArgs& r = a->irt;
+  MvnLayout L;
+  size_t o = 0;
+  L.mirt = o; o += (mirt_workspace_bytes(&r) + 255) & ~size_t(255);
+  L.wimg = o; o += mvn_wimg_bytes(r.n_dims, a->n_hidden);
+  L.wimgb = o; o += mvn_wimgb_bytes(r.n_dims, a->n_hidden);
+  L.eps = o; o += r.eps ? 0 : (((size_t)r.n_particles * r.batch * r.n_dims * 4 + 255) & ~size_t(255));
+  L.dwpart = o; o += mvn_dwpart_bytes(r.n_dims, a->n_hidden);
+  L.gmax = o; o += 256;
+  L.total = o;
+  return L;
+}
+
+size_t vipsy_irt_mvn_encoder_workspace_bytes(const VipsyMvnEncoderIrtArgs* a) {
+  if (!a || a->irt.batch < 0 || a->irt.n_dims < 2 || a->irt.n_dims > 128 || a->irt.n_items <= 0 || a->irt.n_particles <= 0 ||
+      a->n_hidden < 1 || a->n_hidden > kMvMaxH)
+    return 0;
+  VipsyMvnEncoderIrtArgs t = *a;
+  t.irt.cov_mode = VIPSY_COV_PERSON;
+  return mvn_layout(&t).total;
+}
+
+int vipsy_irt_mvn_encoder_elbo_grad(const VipsyMvnEncoderIrtArgs* a, void* stream) {
+  int rc = check_mvn(a, "vipsy_irt_mvn_encoder_elbo_grad");
+  if (rc != VIPSY_OK) return rc;
+  VipsyIrtArgs r = a->irt;
+  r.cov_mode = VIPSY_COV_PERSON; r.chol = nullptr; r.d_chol = nullptr; r.sigma = nullptr; r.d_sigma = nullptr;
+  r.chol_layout = VIPSY_CHOL_PACKED; r.chol_raw = 1;
+  rc = check_irt(&r);
+  if (rc != VIPSY_OK) return rc;
+  VIPSY_REQUIRE(r.model != VIPSY_IRT_1PL, VIPSY_ERR_ARG, "vipsy_irt_mvn_encoder_elbo_grad: irt_1pl is defined for K == 1 only");
+  VIPSY_REQUIRE(r.estimator == VIPSY_EST_PATHWISE, VIPSY_ERR_UNSUPPORTED,
+                "vipsy_irt_mvn_encoder_elbo_grad: the reference runs MultivariateNormal guides pathwise (SURVEY Finding 1)");
+  VIPSY_REQUIRE((r.d_mu != nullptr) || (!a->d_hidden && !a->d_w22 && !a->d_b22), VIPSY_ERR_ARG,
+                "vipsy_irt_mvn_encoder_elbo_grad: encoder gradients need irt.d_mu as well");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (r.batch == 0) {
+    VIPSY_CUDA_CHECK(cudaMemsetAsync(r.loss, 0, 8, st));
+    return VIPSY_OK;
+  }
+  VipsyMvnEncoderIrtArgs t = *a;
+  t.irt = r;
+  const MvnLayout L = mvn_layout(&t);
+  VIPSY_REQUIRE(a->workspace && a->workspace_bytes >= L.total, VIPSY_ERR_WORKSPACE,
+                "vipsy_irt_mvn_encoder_elbo_grad: workspace %zu B < required %zu B", a->workspace_bytes, L.total);
+  unsigned char* ws = reinterpret_cast<unsigned char*>(a->workspace);
+  r.workspace = ws + L.mirt;
+  r.workspace_bytes = L.wimg - L.mirt;
+  MvnEncParams P = mvn_params(a);
+  P.wimg = ws + L.wimg;
+  P.wimg_b = ws + L.wimgb;
+  P.eps_out = r.eps ? nullptr : reinterpret_cast<float*>(ws + L.eps);
+  P.dw_part = reinterpret_cast<float*>(ws + L.dwpart);
+  P.gmax = reinterpret_cast<float*>(ws + L.gmax);
+  P.logdet_out = nullptr;
+  return mirt_launch(&r, st, &P);
+}
 
 int vipsy_mvn_encoder_sample(const VipsyMvnEncoderIrtArgs* a, float* x, float* eps_out, float* diag, float* logdet,
                              void* stream) {
@@ -401,6 +1012,7 @@ int vipsy_mvn_encoder_sample(const VipsyMvnEncoderIrtArgs* a, float* x, float* e
                 "vipsy_mvn_encoder_sample: workspace %zu B < required %zu B", a->workspace_bytes, need);
   MvnEncParams P = mvn_params(a);
   P.wimg = reinterpret_cast<unsigned char*>(a->workspace);
+  P.wimg_b = nullptr;
   P.m.x = x; P.eps_out = eps_out; P.m.diagL = diag; P.logdet_out = logdet; P.m.aux = nullptr;
   cudaStream_t st = (cudaStream_t)stream;
   rc = launch_mvn_prep(P, st);

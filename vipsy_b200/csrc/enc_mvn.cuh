@@ -37,10 +37,11 @@ struct MvnEncParams {
   const float* b22;          // [P]
   int H;
   unsigned char* wimg;       // [chunks][hi | lo] operand image of 64 * [fc22.weight | fc22.bias | 0]
+  unsigned char* wimg_b;     // [units][hi | lo] 64 padded columns x NH of 64 * fc22.weight (backward: d hidden), or null
   float* eps_out;            // [S*B][K] the draws (for the backward pass and for parity tests), or null
   float* logdet_out;         // [B] sum_i log L_ii, or null
-  float* dh_part;            // [n_pg][B][H]
   float* dw_part;            // [n_qg][PP][KH]
+  float* gmax;               // device scalar: max |G| of the step (power-of-two normalisation of the fp16 operand V)
   float* d_hidden;           // outputs
   float* d_w22;
   float* d_b22;
@@ -49,6 +50,10 @@ struct MvnEncParams {
 size_t mvn_enc_extra_bytes(const VipsyMvnEncoderIrtArgs* a);
 int launch_mvn_prep(const MvnEncParams& P, cudaStream_t st);
 int launch_mvn_fwd(const MvnEncParams& P, cudaStream_t st);
-int launch_mvn_bwd(const MvnEncParams& P, int* loss_rows, cudaStream_t st);
+int launch_mvn_tail(const MvnEncParams& P, int* loss_rows, cudaStream_t st);
+int launch_mvn_bwd(const MvnEncParams& P, cudaStream_t st);
+size_t mvn_wimg_bytes(int K, int H);
+size_t mvn_wimgb_bytes(int K, int H);
+size_t mvn_dwpart_bytes(int K, int H);
 
 }  // namespace vipsy

@@ -15,6 +15,7 @@
 #include <stdlib.h>
 
 #include "mirt.cuh"
+#include "enc_mvn.cuh"
 
 namespace vipsy {
 
@@ -492,7 +493,7 @@ static int launch_lik(const MirtParams& p, int* grid_out, cudaStream_t st) {
   return VIPSY_OK;
 }
 
-int mirt_launch(const VipsyIrtArgs* a, cudaStream_t st) {
+int mirt_launch(const VipsyIrtArgs* a, cudaStream_t st, MvnEncParams* enc) {
   const int K = a->n_dims, J = a->n_items, tri = K * (K + 1) / 2;
   VIPSY_REQUIRE(K >= 2 && K <= 128, VIPSY_ERR_UNSUPPORTED, "vipsy_irt_elbo_grad: K=%d outside 2..128", K);
   VIPSY_REQUIRE(a->estimator == VIPSY_EST_PATHWISE ||
@@ -500,9 +501,11 @@ int mirt_launch(const VipsyIrtArgs* a, cudaStream_t st) {
                 VIPSY_ERR_UNSUPPORTED,
                 "vipsy_irt_elbo_grad: for K > 1 the score estimator is built in the fused kernel only (K <= 8, "
                 "per-person factor); the reference never executes it for MultivariateNormal guides (SURVEY Finding 1)");
-  VIPSY_REQUIRE(a->chol, VIPSY_ERR_ARG, "vipsy_irt_elbo_grad: chol is required for K > 1");
+  VIPSY_REQUIRE(a->chol || enc, VIPSY_ERR_ARG, "vipsy_irt_elbo_grad: chol is required for K > 1");
   VIPSY_REQUIRE(a->cov_mode == VIPSY_COV_SHARED || a->cov_mode == VIPSY_COV_PERSON, VIPSY_ERR_ARG,
                 "vipsy_irt_elbo_grad: cov_mode must be SHARED or PERSON for K > 1");
+  VIPSY_REQUIRE(!enc || (a->cov_mode == VIPSY_COV_PERSON && a->estimator == VIPSY_EST_PATHWISE), VIPSY_ERR_UNSUPPORTED,
+                "vipsy_irt_mvn_encoder_elbo_grad: per-person factor, pathwise estimator");
   VIPSY_REQUIRE((size_t)a->n_particles * K * 8 + (size_t)tri * 4 <= 200 * 1024, VIPSY_ERR_UNSUPPORTED,
                 "vipsy_irt_elbo_grad: S*K too large for the guide-gradient kernel (S=%d K=%d)", a->n_particles, K);
   const MirtLayout L = mirt_layout(a);
@@ -535,17 +538,23 @@ int mirt_launch(const VipsyIrtArgs* a, cudaStream_t st) {
   int grid2 = 0, grid3 = 0;
   p.n_parts = 1;
   // K <= 8 with a per-person factor: one fused kernel (warp-shuffle FMAs, nothing staged through HBM)
-  const bool fused = !(a->flags & VIPSY_IRT_FLAG_NO_FUSED) && mirt_fused_supported(p);
+  const bool fused = !enc && !(a->flags & VIPSY_IRT_FLAG_NO_FUSED) && mirt_fused_supported(p);
   if (fused) {
     int rc = launch_mirt_fused(p, kMirtMaxGrid, &grid2, st);
     if (rc != VIPSY_OK) return rc;
     grid3 = grid2;
   }
-  const bool stream = !fused && mirt_stream_supported(p);
-  const bool small = !fused && !stream && mirt_small_supported(p);
+  const bool stream = !enc && !fused && mirt_stream_supported(p);
+  const bool small = !enc && !fused && !stream && mirt_small_supported(p);
   if (!fused) {
   // (1) sample
-  if (small) {
+  if (enc) {              // amortised guide: fc22 on the tensor cores inside the sampler (enc_mvn.cu)
+    enc->m = p;
+    int rc = launch_mvn_prep(*enc, st);
+    if (rc != VIPSY_OK) return rc;
+    rc = launch_mvn_fwd(*enc, st);
+    if (rc != VIPSY_OK) return rc;
+  } else if (small) {
     int rc = launch_sample_small(p, kMirtMaxGrid, st);
     if (rc != VIPSY_OK) return rc;
   } else if (stream) {
@@ -587,7 +596,15 @@ int mirt_launch(const VipsyIrtArgs* a, cudaStream_t st) {
     if (rc != VIPSY_OK) return rc;
   }
   // (3) guide gradients + loss partials
-  if (small) {
+  if (enc) {              // d mu + loss here; d fc22.weight / bias and d hidden from on-chip outer products
+    enc->m = p;           // n_parts is known now
+    int rc = launch_mvn_tail(*enc, &grid3, st);
+    if (rc != VIPSY_OK) return rc;
+    if (a->d_mu) {
+      rc = launch_mvn_bwd(*enc, st);
+      if (rc != VIPSY_OK) return rc;
+    }
+  } else if (small) {
     int rc = launch_cholgrad_small(p, kMirtMaxGrid, &grid3, st);
     if (rc != VIPSY_OK) return rc;
   } else if (stream) {

@@ -77,6 +77,12 @@ bool mirt_stream_supported(const MirtParams& p);
 int launch_sample_stream(const MirtParams& p, int max_grid, cudaStream_t st);
 int launch_cholgrad_stream(const MirtParams& p, int max_grid, int* grid_out, cudaStream_t st);
 
+// The whole K > 1 evaluation (mirt.cu).  enc != null: the guide is the amortised one of enc_mvn.cuh -- the sampler
+// and the guide-gradient kernels are replaced by the fused fc22 kernels, a->chol / d_chol are not used.
+struct MvnEncParams;
+size_t mirt_workspace_bytes(const VipsyIrtArgs* a);
+int mirt_launch(const VipsyIrtArgs* a, cudaStream_t st, MvnEncParams* enc);
+
 // thread-per-(person, particle) / thread-per-element kernels for K <= 32, any S (mirt_small.cu)
 bool mirt_small_supported(const MirtParams& p);
 int launch_sample_small(const MirtParams& p, int max_grid, cudaStream_t st);

@@ -178,8 +178,15 @@ def irt_elbo_grad(
     row_kernel: bool = True, obs=None, n_masked: Optional[int] = None, fused: bool = True,
     d_mu_out: Optional[torch.Tensor] = None, d_scale_out: Optional[torch.Tensor] = None,
     item_grads_out: Optional[torch.Tensor] = None, loss_out: Optional[torch.Tensor] = None,
+    mvn_encoder=None,
 ) -> Dict[str, Optional[torch.Tensor]]:
     """One fused ELBO + gradient evaluation (Trace_ELBO.loss_and_grads, vi.py:507).
+
+    ``mvn_encoder=(hidden, fc22_weight, fc22_bias)`` (K > 1, instead of ``chol``): the amortised guide of
+    VaeIRT (vi.py:685-693).  ``mu`` is fc21's output, ``hidden`` = softplus(fc1(x)) for the batch rows; fc22, the
+    tril scatter and LowerCholeskyTransform are evaluated inside the sampler on the tensor cores and the B x K(K+1)/2
+    factor matrix never exists in HBM.  Returns ``d_hidden`` (through fc22 only), ``d_w22``, ``d_b22`` instead of
+    ``d_chol``.
 
     ``item_grads_out`` (fp32, packed [d_b | d_a | d_c | d_d]) / ``loss_out`` (fp64, 1): optional destinations,
     e.g. views into a symmetric peer-memory buffer (``dist.PeerAllReduce``).
@@ -254,7 +261,19 @@ def irt_elbo_grad(
         loss = torch.empty(1, dtype=torch.float64, device=dev)
     args.loss = _ptr(loss)
     sg_ = ch_ = None
-    if K == 1:
+    enc_ = None
+    if mvn_encoder is not None:
+        if K < 2:
+            raise ValueError("mvn_encoder is the K > 1 guide")
+        tri = K * (K + 1) // 2
+        enc_ = tuple(_f32(t, n) for t, n in zip(mvn_encoder, ("hidden", "fc22.weight", "fc22.bias")))
+        H = enc_[0].shape[1]
+        if enc_[0].shape[0] != B or tuple(enc_[1].shape) != (tri, H) or enc_[2].numel() != tri:
+            raise ValueError("mvn_encoder: hidden B x H, fc22.weight K(K+1)/2 x H, fc22.bias K(K+1)/2")
+        if H > MVN_ENCODER_MAX_HIDDEN:
+            raise ValueError(f"mvn_encoder: hidden_dim {H} > {MVN_ENCODER_MAX_HIDDEN}")
+        args.cov_mode = N.COV_PERSON
+    elif K == 1:
         sg_ = _f32(sigma, "sigma", B)
         args.sigma, args.cov_mode = _ptr(sg_), N.COV_DIAG1
     else:
@@ -290,6 +309,10 @@ def irt_elbo_grad(
             d_sigma = _out(d_scale_out, (B, 1))
             args.d_sigma = _ptr(d_sigma)
             out["d_sigma"] = d_sigma
+        elif enc_ is not None:
+            out["d_hidden"] = torch.empty_like(enc_[0])
+            out["d_w22"] = torch.empty_like(enc_[1])
+            out["d_b22"] = torch.empty(enc_[2].numel(), dtype=torch.float32, device=dev)
         else:
             d_chol = _out(d_scale_out, tuple(ch_.shape), zero=d_scale_out is None)
             args.d_chol = _ptr(d_chol)
@@ -318,12 +341,23 @@ def irt_elbo_grad(
             out["d_d"] = packed[o:o + J].view(1, J); o += J
             args.d_d = out["d_d"].data_ptr()
     L = N.lib()
-    nbytes = L.vipsy_irt_workspace_bytes(C.byref(args))
-    ws = _workspace("irt", nbytes, dev)
-    args.workspace, args.workspace_bytes = _ptr(ws), ws.numel()
-    N.check(L.vipsy_irt_elbo_grad(C.byref(args), _stream()))
+    if enc_ is not None:
+        ea = N.MvnEncoderIrtArgs()
+        ea.irt = args
+        ea.n_hidden, ea.hidden, ea.w22, ea.b22 = enc_[0].shape[1], _ptr(enc_[0]), _ptr(enc_[1]), _ptr(enc_[2])
+        if want_grad:
+            ea.d_hidden, ea.d_w22, ea.d_b22 = _ptr(out["d_hidden"]), _ptr(out["d_w22"]), _ptr(out["d_b22"])
+        nbytes = L.vipsy_irt_mvn_encoder_workspace_bytes(C.byref(ea))
+        ws = _workspace("irt_mvn", nbytes, dev)
+        ea.workspace, ea.workspace_bytes = _ptr(ws), ws.numel()
+        N.check(L.vipsy_irt_mvn_encoder_elbo_grad(C.byref(ea), _stream()))
+    else:
+        nbytes = L.vipsy_irt_workspace_bytes(C.byref(args))
+        ws = _workspace("irt", nbytes, dev)
+        args.workspace, args.workspace_bytes = _ptr(ws), ws.numel()
+        N.check(L.vipsy_irt_elbo_grad(C.byref(args), _stream()))
     out["loss"] = loss
-    out["_keepalive"] = (mu_, sg_, ch_, eps_, a_, b_, c_, d_, af_, idx_, ws, obs)
+    out["_keepalive"] = (mu_, sg_, ch_, eps_, a_, b_, c_, d_, af_, idx_, ws, obs, enc_)
     return out
 
 
