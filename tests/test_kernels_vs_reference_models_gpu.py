@@ -166,3 +166,29 @@ def test_vaechodina_encoder_kernels_vs_reference_model(ops, gm):
     g = ops.norm_encoder_backward(codes, enc, sigma, pre, r["d_mu"].reshape(-1), r["d_sigma"].reshape(-1), idx)
     for n, _ in enc.named_parameters():
         close(g[n].cpu(), c.g(f"encoder$$${n}"), f"{key} encoder {n}", 5e-4)
+
+
+def test_vaeirt_k3_fused_mvn_encoder_vs_reference_model(ops, gm):
+    """VaeIRT, K = 3, subsampled (vi.py:685-693): fc1 / fc21 in torch, fc22 + tril scatter + LowerCholeskyTransform +
+    rsample fused into the CUDA path, against the loss and every gradient (fc22's weights included) that the
+    reference's own guide + model produced."""
+    from vipsy_b200.models import MvnEncoder
+    key = "vaeirt_irt_2pl_k3_sub12"
+    c = Case(gm, key)
+    enc = c.encoder(MvnEncoder, c.y.shape[1], 3, 5).cuda()
+    yb = c.y[c.idx].cuda()
+    hidden = enc.softplus(enc.fc1(torch.where(torch.isnan(yb), torch.full_like(yb, -1.0), yb)))
+    loc = enc.fc21(hidden)
+    a, b, _, _ = irt_items(c, "irt_2pl")
+    free = T(gm[f"{key}/a_free"]).bool()
+    r = ops.irt_elbo_grad(codes_from_float(c.y).cuda(), loc.detach(),
+                          mvn_encoder=(hidden.detach(), enc.fc22.weight.detach(), enc.fc22.bias.detach()),
+                          eps=cu(c.noise("x")), a=cu(a), b=cu(b), model="irt_2pl", scale=c.scale, idx=cu(c.idx),
+                          a_free=cu(free))
+    close(r["loss"].cpu(), c.loss, f"{key} loss")
+    close(r["d_a"].cpu(), c.g("a"), f"{key} a")
+    close(r["d_b"].cpu(), c.g("b"), f"{key} b")
+    torch.autograd.backward([hidden, loc], [r["d_hidden"], r["d_mu"]])
+    enc.fc22.weight.grad, enc.fc22.bias.grad = r["d_w22"], r["d_b22"]
+    for n, p in enc.named_parameters():
+        close(p.grad.cpu(), c.g(f"encoder$$${n}"), f"{key} encoder {n}", 5e-4)

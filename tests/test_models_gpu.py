@@ -435,3 +435,25 @@ def test_vchodina_posterior_uses_the_model_the_fit_uses():
         m = vb.VCHoDina(data=y, q=q, model=model, seed=3)
         post.append(m.posterior())
     assert torch.equal(post[0], post[1])
+
+
+def test_vaeirt_mirt_fused_encoder_tail_equals_torch_autograd():
+    """VaeIRT, K > 1: the default path (fc22 + sampler fused, csrc/enc_mvn.cu) against fused_encoder=False (MvnEncoder
+    and its backward in torch, the factor matrix in HBM): same noise stream, same losses and parameters."""
+    g = torch.Generator().manual_seed(4)
+    y = (torch.rand(500, 30, generator=g) < 0.55).float()
+    y[torch.rand(500, 30, generator=g) < 0.05] = float("nan")
+    out = []
+    for fused in (True, False):
+        vb.clear_param_store()
+        torch.manual_seed(7)
+        m = vb.VaeIRT(data=y, model="irt_2pl", x_feature=4, hidden_dim=16, seed=9)
+        m.fused_encoder = fused
+        svi = infer.SVI(m.model, m.guide, optim=vb.Adam({"lr": 1e-2}), loss=vb.Trace_ELBO(num_particles=2), cuda_graph=False)
+        losses = [svi.step(m.data) for _ in range(6)]
+        out.append((losses, {n: vb.get_param_store().get(n).clone() for n in vb.get_param_store().names()}))
+    (lf, pf), (lt, pt) = out
+    assert np.allclose(lf, lt, rtol=2e-5), (lf, lt)
+    for n in pf:
+        assert_close(pf[n], pt[n], 2e-4, 2e-4, n)
+    assert lf[-1] < lf[0]

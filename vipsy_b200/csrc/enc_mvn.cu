@@ -673,11 +673,12 @@ __host__ __device__ inline DwSmem dw_smem(int K, int H) {
   s.total = o;
   return s;
 }
+constexpr int kDwFlushTiles = 8;
 __host__ __device__ inline int dw_cpb(int H) { return 512 / mv_kh(H) < 8 ? 512 / mv_kh(H) : 8; }   // chunks per CTA slab
 
 __global__ void __launch_bounds__(kBwThreads, 1) mvn_bwd_dw_kernel(const MvnEncParams P, const int n_pg, const int n_qg) {
   extern __shared__ __align__(128) unsigned char smem[];
-  __shared__ uint64_t bar_vfull[2], bar_vfree[2], bar_hfree, bar_done;
+  __shared__ uint64_t bar_vfull[2], bar_vfree[2], bar_hfree, bar_done, bar_drained;
   __shared__ uint32_t tmem_base_sm;
   const MirtParams& m = P.m;
   const int K = m.K, S = m.S, H = P.H, KH = mv_kh(H), NB = mv_nb(K), NU = NB * (NB + 1) / 2;
@@ -703,6 +704,7 @@ __global__ void __launch_bounds__(kBwThreads, 1) mvn_bwd_dw_kernel(const MvnEncP
     for (int i = 0; i < 2; ++i) { umma::mbar_init(&bar_vfull[i], kBwGen); umma::mbar_init(&bar_vfree[i], 1); }
     umma::mbar_init(&bar_hfree, 1);
     umma::mbar_init(&bar_done, 1);
+    umma::mbar_init(&bar_drained, 128);
     umma::fence_mbar_init();
   }
   if (warp == kBwGenWarps + 1) umma::tmem_alloc(&tmem_base_sm, 512);
@@ -715,9 +717,9 @@ __global__ void __launch_bounds__(kBwThreads, 1) mvn_bwd_dw_kernel(const MvnEncP
     if (lane == 0) {                                   // MMA issuer
       const uint32_t idesc = umma::make_idesc_f16(kMvCN, KH, umma::kMajorMN, umma::kMajorMN);
       const uint32_t sHh = umma::smem_u32(Hh), sHl = umma::smem_u32(Hl);
-      uint32_t it = 0;
+      uint32_t it = 0, ntile = 0, nflush = 0;
       bool first = true;
-      for (int64_t tile = qg; tile < n_tiles; tile += n_qg) {
+      for (int64_t tile = qg; tile < n_tiles; tile += n_qg, ++ntile) {
         for (int s = 0; s < S; ++s)
           for (int k = 0; k < nblk; ++k, ++it) {
             const uint32_t vb = it % NVB;
@@ -739,15 +741,21 @@ __global__ void __launch_bounds__(kBwThreads, 1) mvn_bwd_dw_kernel(const MvnEncP
           }
         first = false;
         umma::commit(&bar_hfree);                      // every MMA that reads this tile's H tile has completed
+        if ((ntile + 1) % kDwFlushTiles == 0 || tile + n_qg >= n_tiles) {
+          umma::commit(&bar_done);                     // flush: the drain warps add the accumulators to the partial rows
+          umma::mbar_wait(&bar_drained, nflush & 1);
+          umma::fence_after_sync();
+          first = true;
+          ++nflush;
+        }
       }
-      umma::commit(&bar_done);
     }
   } else if (warp < kBwGenWarps) {
     const int t = tid & 127, sub = tid >> 7;
     float* er = eps_s + (size_t)t * ES;
     if (sub == 0)
       for (int k = K; k < ES; ++k) er[k] = 0.f;
-    uint32_t it = 0, ntile = 0;
+    uint32_t it = 0, ntile = 0, nflush = 0;
     for (int64_t tile = qg; tile < n_tiles; tile += n_qg, ++ntile) {
       const int64_t b = tile * kMvTP + t;
       const bool live = b < m.B;
@@ -790,22 +798,35 @@ __global__ void __launch_bounds__(kBwThreads, 1) mvn_bwd_dw_kernel(const MvnEncP
           umma::mbar_arrive(&bar_vfull[vb]);
         }
       }
-    }
-    if (warp < 4) {                                    // drain: thread = factor column of the chunk = TMEM lane
-      umma::mbar_wait(&bar_done, 0);
-      umma::fence_after_sync();
-      const uint32_t tl = tmem + ((uint32_t)(warp * 32) << 16);
-      for (int k = 0; k < nblk; ++k) {
-        float* dst = P.dw_part + ((size_t)qg * n_chunks * kMvCN + (size_t)(c0 + k) * kMvCN + t) * KH;
-        for (int q0 = 0; q0 < KH; q0 += 16) {
-          float v[16];
-          umma::tmem_ld16(tl + k * KH + q0, v);
+      // Flush every kDwFlushTiles tiles: the accumulators are added (round-to-nearest, fixed order) to this CTA's
+      // partial rows, which bounds the chain of truncating tensor-core accumulations (see mvn_bwd_dh_kernel).
+      if ((ntile + 1) % kDwFlushTiles == 0 || tile + n_qg >= n_tiles) {
+        if (warp < 4) {                                // thread = factor column of the chunk = TMEM lane
+          umma::mbar_wait(&bar_done, nflush & 1);
+          umma::fence_after_sync();
+          const uint32_t tl = tmem + ((uint32_t)(warp * 32) << 16);
+          for (int k = 0; k < nblk; ++k) {
+            float* dst = P.dw_part + ((size_t)qg * n_chunks * kMvCN + (size_t)(c0 + k) * kMvCN + t) * KH;
+            for (int q0 = 0; q0 < KH; q0 += 16) {
+              float v[16];
+              umma::tmem_ld16(tl + k * KH + q0, v);
 #pragma unroll
-          for (int q = 0; q < 4; ++q)
-            *reinterpret_cast<float4*>(dst + q0 + 4 * q) = make_float4(v[4 * q] * gfix, v[4 * q + 1] * gfix, v[4 * q + 2] * gfix, v[4 * q + 3] * gfix);
+              for (int q = 0; q < 4; ++q) {
+                float4 o = make_float4(v[4 * q] * gfix, v[4 * q + 1] * gfix, v[4 * q + 2] * gfix, v[4 * q + 3] * gfix);
+                float4* dp = reinterpret_cast<float4*>(dst + q0 + 4 * q);
+                if (nflush > 0) {
+                  const float4 old = *dp;
+                  o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
+                }
+                *dp = o;
+              }
+            }
+          }
+          umma::fence_before_sync();
+          umma::mbar_arrive(&bar_drained);
         }
+        ++nflush;
       }
-      umma::fence_before_sync();
     }
   }
   umma::fence_before_sync();

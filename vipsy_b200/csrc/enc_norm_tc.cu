@@ -356,7 +356,11 @@ __global__ void __launch_bounds__(kBwdThreads) enc_tc_bwd_kernel(const EncParams
     wh[t >> 6][h] = h < P.H ? __ldg((t >> 6 ? P.w22 : P.w21) + h) : 0.0f;
   }
   for (int e = t; e < 2 * kTB * kPitch; e += kBwdThreads) pb0[e] = 0.0f;        // columns beyond H stay 0
-  if (warp == 0) umma::tmem_alloc(&tmem_base_sm, MB * kTmemCols);
+  // The tensor core adds into its fp32 accumulator with truncation: a chain of accumulating MMAs drifts by about
+  // 2^-24 of the running sum per instruction (measured at 1M persons: d fc1.weight off by 1.6e-5 after 1272 MMAs).
+  // The CTA's tiles therefore go round-robin into NACC independent accumulator sets, summed at the drain.
+  constexpr uint32_t NACC = 512 / (MB * kTmemCols);
+  if (warp == 0) umma::tmem_alloc(&tmem_base_sm, 512);
   if (t == 0) {
     umma::mbar_init(&bar, 1);
     umma::mbar_init(&barx, 1);
@@ -432,7 +436,7 @@ __global__ void __launch_bounds__(kBwdThreads) enc_tc_bwd_kernel(const EncParams
     fetch_pre((int64_t)blockIdx.x * kTB, 0);
     load_heads((int64_t)blockIdx.x * kTB);
   }
-  uint32_t phase = 0, phx = 0, acc = 0;
+  uint32_t phase = 0, phx = 0, nt = 0;           // nt: tiles this CTA has issued
   int nb = 0;                                     // `pre` buffer of the current tile
   bool pending = false;
   for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
@@ -499,13 +503,14 @@ __global__ void __launch_bounds__(kBwdThreads) enc_tc_bwd_kernel(const EncParams
           const uint64_t da = umma::make_desc(sX + ks * 2 * RSx + mb * 16 * kCS, RSx, kCS);
 #pragma unroll
           for (int term = 0; term < 3; ++term)        // only the very first MMA of an accumulator overwrites it
-            umma::mma_f16_ss(tmem + mb * kTmemCols, da, umma::make_desc(sD[term] + ks * 2 * RSd, RSd, kCS), idesc,
-                             (acc | (uint32_t)ks | (uint32_t)term) != 0u ? 1u : 0u);
+            umma::mma_f16_ss(tmem + ((nt % NACC) * MB + mb) * kTmemCols, da,
+                             umma::make_desc(sD[term] + ks * 2 * RSd, RSd, kCS), idesc,
+                             ((nt >= NACC ? 1u : 0u) | (uint32_t)ks | (uint32_t)term) != 0u ? 1u : 0u);
         }
       }
-      acc = 1;
       umma::commit(&bar);
     }
+    ++nt;
     pending = true;
     nb ^= 1;
     if (has_next) {
@@ -527,6 +532,12 @@ __global__ void __launch_bounds__(kBwdThreads) enc_tc_bwd_kernel(const EncParams
     for (int mb = 0; mb < MB; ++mb) {
       float v[32];
       umma::tmem_ld32(tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)(mb * kTmemCols + half * 32), v);
+      for (uint32_t s = 1; s < (nt < NACC ? nt : NACC); ++s) {       // the other accumulator sets, in order
+        float w[32];
+        umma::tmem_ld32(tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)((s * MB + mb) * kTmemCols + half * 32), w);
+#pragma unroll
+        for (int c = 0; c < 32; ++c) v[c] += w[c];
+      }
       const int j = mb * 128 + quad * 32 + lane;
 #pragma unroll
       for (int c = 0; c < 32; ++c) {
@@ -561,7 +572,7 @@ __global__ void __launch_bounds__(kBwdThreads) enc_tc_bwd_kernel(const EncParams
     tail[2 * P.H] = (gm[0] + gm[1]) + (gm[2] + gm[3]);
     tail[3 * P.H + 1] = (gl[0] + gl[1]) + (gl[2] + gl[3]);
   }
-  if (warp == 0) umma::tmem_dealloc(tmem, MB * kTmemCols);
+  if (warp == 0) umma::tmem_dealloc(tmem, 512);
 }
 
 static size_t tc_fwd_smem(int JP, bool resident, int NS) {

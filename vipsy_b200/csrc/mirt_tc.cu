@@ -37,7 +37,12 @@ constexpr int kTcTN = 128;                 // items per CTA (UMMA N of the forwa
 constexpr int kTcYStride = kTcTN + 4;      // response tile row stride (bank-conflict-free row reads)
 constexpr uint32_t kCS = 128;              // byte stride between core matrices along the contiguous dim
 constexpr uint32_t kTmemCols = 512;
-constexpr uint32_t kColLogit = 0, kColDx = 128, kColDa = 256;
+constexpr uint32_t kColLogit = 0, kColDx = 128, kColDa = 256;   // + a second d a accumulator at kColDa + 128
+// The tensor core adds into its fp32 accumulator with truncation, so a chain of accumulating MMAs drifts by about
+// 2^-24 of the running sum per instruction (measured at 200 000 persons: d a off by 1.7e-5 after 1008 MMAs into
+// one accumulator).  d a therefore accumulates in TMEM for kTcFlushTiles row tiles only; the epilogue adds each
+// finished group to the CTA's partial row (round-to-nearest) while the next group builds up in the other accumulator.
+constexpr int kTcFlushTiles = 8;
 
 __host__ __device__ inline int tc_kp(int K) { return ((K + 1 + 15) / 16) * 16; }   // + ones column, k-step 16
 
@@ -397,14 +402,15 @@ __global__ void __launch_bounds__(kTcThreads, 1) mirt_tc_lik_kernel(const MirtPa
             acc = 1;
           }
         }
-        acc = n > 0 ? 1u : 0u;
+        acc = (n % kTcFlushTiles) != 0 ? 1u : 0u;          // a new group starts a fresh accumulator
+        const uint32_t col_da = kColDa + (uint32_t)((n / kTcFlushTiles) & 1) * 128u;
         if (!(p.dbg & 8))
         for (int ks = 0; ks < kTcTM / 16; ++ks) {
 #pragma unroll
           for (int term = 0; term < 3; ++term) {
             const uint64_t da = umma::make_desc((term == 2 ? sXl : sXh) + ks * 2 * L.rsX, L.rsX, kCS);
             const uint64_t db = umma::make_desc((term == 1 ? sGl : sGh) + ks * 2 * L.rsG, L.rsG, kCS);
-            umma::mma_f16_ss(tmem + kColDa, da, db, idesc_da, acc);
+            umma::mma_f16_ss(tmem + col_da, da, db, idesc_da, acc);
             acc = 1;
           }
         }
@@ -420,6 +426,24 @@ __global__ void __launch_bounds__(kTcThreads, 1) mirt_tc_lik_kernel(const MirtPa
     const int pr = quad * 32 + lane;                         // this thread's tile row
     const float negDl2e = -p.D * kLog2e;
     float cs_acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};   // lane (l & 15): column l & 15 of chunk cc: d_c | d_d
+    // d a / d b of one finished group of row tiles -> this CTA's partial row (group 0 stores, later groups add)
+    auto flush_da = [&](uint32_t taddr, int64_t grp) {
+      const int k = quad * 32 + lane;
+      float* part = p.item_partial + (size_t)g * ((size_t)K * J + 3 * (size_t)J);
+      umma::fence_after_sync();
+      for (int cc = 0; cc < 4; ++cc) {
+        const int c0 = half * 64 + cc * 16;
+        float v[16];
+        umma::tmem_ld16(taddr + c0, v);
+        if (k <= K) {
+          float* dst = part + (size_t)k * J + j0 + c0;        // k == K lands on the d_b segment (offset K*J)
+#pragma unroll
+          for (int i = 0; i < 16; ++i)
+            if (j0 + c0 + i < J) dst[i] = grp > 0 ? dst[i] + v[i] : v[i];
+        }
+      }
+      umma::fence_before_sync();
+    };
     int64_t n = 0;
     for (int64_t tm = g; tm < ntile_m; tm += G, ++n) {
       const int64_t r0 = tm * kTcTM;
@@ -496,6 +520,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) mirt_tc_lik_kernel(const MirtPa
       mbar_arrive(&bars[kBarGFull]);
       mbar_arrive(&bars[kBarYFree0 + (n & 1)]);
       if (tid == 0) TC_STAMP(2, 1);
+      // first tile of a new group: the previous group's d a is complete (the logits of this tile were committed after
+      // every earlier MMA) and nothing writes that accumulator before the group after next -> add it to the partial row
+      if (n > 0 && n % kTcFlushTiles == 0) {
+        flush_da(tmem_row + kColDa + (uint32_t)(((n / kTcFlushTiles) - 1) & 1) * 128u, n / kTcFlushTiles - 1);
+      }
       // per-row log-likelihood partial of this item tile: column half 1 hands its sum to half 0
       float* llsm = llsm_all + (n & 1) * kTcTM;
       if (half == 1) llsm[pr] = ll;
@@ -507,21 +536,17 @@ __global__ void __launch_bounds__(kTcThreads, 1) mirt_tc_lik_kernel(const MirtPa
     if (n > 0) umma::mbar_wait(&bars[kBarDxFull], (uint32_t)((n - 1) & 1));
     umma::fence_after_sync();
 
-    // ---- flush d a (rows k < K) and d b (row K) of this CTA's item tile: the last kBarDxFull wait above
-    //      covers every MMA of the CTA ------------------------------------------------------------------
+    // ---- flush the last group of d a (rows k < K) and d b (row K) of this CTA's item tile: the last kBarDxFull
+    //      wait above covers every MMA of the CTA ------------------------------------------------------------
     {
-      const int k = quad * 32 + lane;
       float* part = p.item_partial + (size_t)g * ((size_t)K * J + 3 * (size_t)J);
-      for (int cc = 0; cc < 4; ++cc) {
-        const int c0 = half * 64 + cc * 16;
-        float v[16];
-        umma::tmem_ld16(tmem_row + kColDa + c0, v);
-        if (k <= K) {
-          float* dst = part + (size_t)k * J + j0 + c0;        // k == K lands on the d_b segment (offset K*J)
-#pragma unroll
-          for (int i = 0; i < 16; ++i)
-            if (j0 + c0 + i < J) dst[i] = v[i];
-        }
+      if (n > 0) {
+        const int64_t grp = (n - 1) / kTcFlushTiles;
+        flush_da(tmem_row + kColDa + (uint32_t)(grp & 1) * 128u, grp);
+      } else {
+        const int k = quad * 32 + lane;
+        for (int c = half * 64; c < half * 64 + 64; ++c)
+          if (k <= K && j0 + c < J) part[(size_t)k * J + j0 + c] = 0.f;
       }
       if (MODEL >= VIPSY_IRT_3PL) {                           // d_c, d_d: combine the four row quadrants in order
         float* cs = reinterpret_cast<float*>(smem + L.offCs);

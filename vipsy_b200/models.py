@@ -200,6 +200,10 @@ class BasePsy(nn.Module):               # vi.py:521-533
                 and self.encoder.fc21.out_features == 1
                 and self.encoder.fc1.out_features <= ops.NORM_ENCODER_MAX_HIDDEN)
 
+    def _mvn_encoder_fusable(self) -> bool:
+        return (getattr(self, "fused_encoder", False) and isinstance(self.encoder, MvnEncoder)
+                and self.encoder.fc1.out_features <= ops.MVN_ENCODER_MAX_HIDDEN and 2 <= self.x_feature <= 128)
+
     def _finish(self, loss: torch.Tensor, sites: List[Site]):
         """Person-sharded jobs: all-reduce the loss and every replicated parameter's gradient."""
         if self.reducer is not None:
@@ -299,6 +303,7 @@ class BaseIRT(BasePsy):                 # vi.py:536-656
         for _, s in groups:
             idx, Bg, scale = self._plate()
             gkw, backward, gsites = self._guide(idx, Bg)
+            noise = self._noise_args("eps", s, Bg, self.x_feature)
             r = ops.irt_elbo_grad(self._codes, model=self._model, D=float(self.D), scale=scale, n_particles=s,
                                   a=items["a"][1] if "a" in items else None, b=items["b"][1],
                                   c=items["c"][1] if "c" in items else None, d=items["d"][1] if "d" in items else None,
@@ -306,7 +311,7 @@ class BaseIRT(BasePsy):                 # vi.py:536-656
                                   want_grad=want_grad, sparse=self._sparse and self.x_feature == 1,
                                   n_masked=self._n_missing if idx is None else None,
                                   obs=self._observed_csr() if (self._sparse and self.x_feature == 1 and s == 1) else None,
-                                  **gkw, **self._noise_args("eps", s, Bg, self.x_feature))
+                                  **gkw, **noise)
             w = 1.0 / len(groups)
             total = r["loss"] * w if total is None else total + r["loss"] * w
             if want_grad:
@@ -388,7 +393,10 @@ class VaeIRT(BaseIRT):                  # vi.py:659-693
         super().__init__(*args, **kwargs)
         enc = NormEncoder if self.x_feature == 1 else MvnEncoder
         self.encoder = enc(self.item_size, self.x_feature, hidden_dim).to(self.device)
-        self.fused_encoder = True       # K = 1: encoder forward / backward as CUDA kernels (False: torch autograd)
+        # encoder inside the CUDA path (False: torch autograd end to end).  K = 1: NormEncoder forward / backward
+        # kernels (csrc/enc_norm*.cu).  K > 1: MvnEncoder's fc22 + tril scatter + LowerCholeskyTransform fused into
+        # the sampler and its backward (csrc/enc_mvn.cu); fc1 / fc21 stay in torch.
+        self.fused_encoder = True
 
     def _guide(self, idx, B):
         get_param_store().register_module("encoder", self.encoder)
@@ -399,6 +407,17 @@ class VaeIRT(BaseIRT):                  # vi.py:659-693
             def backward(r, w):
                 enc_backward(r["d_mu"], r["d_sigma"], w)
             return dict(mu=mu, sigma=sigma), backward, sites
+        if self.x_feature > 1 and self._mvn_encoder_fusable():
+            enc = self.encoder
+            hidden = enc.softplus(enc.fc1(self._encoder_input(idx)))
+            x_loc = enc.fc21(hidden)
+
+            def backward(r, w):
+                _accum(enc.fc22.weight, r["d_w22"] * w)
+                _accum(enc.fc22.bias, r["d_b22"] * w)
+                torch.autograd.backward([hidden, x_loc], [r["d_hidden"] * w, r["d_mu"] * w])
+            return (dict(mu=x_loc.detach(), mvn_encoder=(hidden.detach(), enc.fc22.weight.detach(), enc.fc22.bias.detach())),
+                    backward, sites)
         x_loc, x_sc = self.encoder(self._encoder_input(idx))
         if self.x_feature == 1:
             def backward(r, w):
