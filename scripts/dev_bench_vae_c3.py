@@ -8,10 +8,11 @@ from vipsy_b200 import infer
 
 N = int(os.environ.get("N", 200_000))
 y = (torch.rand(N, 500, device="cuda", generator=torch.Generator(device="cuda").manual_seed(0)) < 0.6).float()
-for graph in (False, True):
+for fused, graph in ((False, False), (False, True), (True, False), (True, True)):
     vb.clear_param_store()
     torch.manual_seed(0)
     m = vb.VaeIRT(data=y, model="irt_2pl", x_feature=100)
+    m.fused_encoder = fused
     svi = infer.SVI(m.model, m.guide, optim=vb.Adam({"lr": 1e-3}), loss=vb.Trace_ELBO(1), cuda_graph=graph)
     for _ in range(3):
         svi.step(m.data)
@@ -20,9 +21,9 @@ for graph in (False, True):
     for _ in range(10):
         svi.step_async(m.data)
     torch.cuda.synchronize()
-    print(f"VaeIRT irt_2pl K=100 {N}x500 S=1 full batch: {'graph' if graph else 'eager'} "
+    print(f"VaeIRT irt_2pl K=100 {N}x500 S=1 full batch, fc22 {'fused into the guide kernels' if fused else 'in torch'}: {'graph' if graph else 'eager'} "
           f"{(time.perf_counter() - t0) / 10 * 1e3:.3f} ms/iteration", flush=True)
-    if graph is False:
+    if graph is False and not fused:
         # encoder alone (forward + backward through fc22), same tensors
         enc = m.encoder
         x = m._encoder_input(None)

@@ -27,6 +27,13 @@ constexpr int kFwEpiWarps = 4;                 // warps 0-3: epilogue (TMEM lane
 constexpr int kFwThreads = (kFwEpiWarps + 2) * 32;   // + warp 4: bulk-copy producer, warp 5: MMA issuer
 constexpr int kFwTmemBufs = 4;                 // 4 x 128 accumulator columns
 
+// One arrival per warp: every lane has finished (and fenced) its part, lane 0 signals.  512 separate arrivals on one
+// mbarrier serialise on the shared-memory atomic unit (measured: ~2000 cycles per phase).
+__device__ __forceinline__ void warp_arrive(uint64_t* bar, int lane) {
+  __syncwarp();
+  if (lane == 0) umma::mbar_arrive(bar);
+}
+
 __device__ __forceinline__ uint32_t pk_half2(float a, float b) {
   __half2 h = __floats2half2_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&h);
@@ -180,8 +187,8 @@ __global__ void __launch_bounds__(kFwThreads, 1) mvn_fwd_kernel(const MvnEncPara
 
   if (tid == 0) {
     for (int i = 0; i < 4; ++i) { umma::mbar_init(&bar_wfull[i], 1); umma::mbar_init(&bar_wempty[i], 1); }
-    for (int i = 0; i < kFwTmemBufs; ++i) { umma::mbar_init(&bar_tfull[i], 1); umma::mbar_init(&bar_tempty[i], kFwEpiWarps * 32); }
-    umma::mbar_init(&bar_hfull, kFwEpiWarps * 32);
+    for (int i = 0; i < kFwTmemBufs; ++i) { umma::mbar_init(&bar_tfull[i], 1); umma::mbar_init(&bar_tempty[i], kFwEpiWarps); }
+    umma::mbar_init(&bar_hfull, kFwEpiWarps);
     umma::fence_mbar_init();
   }
   if (warp == kFwEpiWarps + 1) umma::tmem_alloc(&tmem_base_sm, 512);
@@ -270,7 +277,7 @@ __global__ void __launch_bounds__(kFwThreads, 1) mvn_fwd_kernel(const MvnEncPara
           *reinterpret_cast<uint4*>(Hl + off) = lo;
         }
         umma::fence_proxy_async();
-        umma::mbar_arrive(&bar_hfull);
+        warp_arrive(&bar_hfull, lane);
       }
       float logdet = 0.f, auxp = 0.f;
       for (int s = 0; s < S; ++s) {
@@ -358,7 +365,7 @@ __global__ void __launch_bounds__(kFwThreads, 1) mvn_fwd_kernel(const MvnEncPara
             }
           }
           umma::fence_before_sync();
-          umma::mbar_arrive(&bar_tempty[buf]);
+          warp_arrive(&bar_tempty[buf], lane);
         }
       }
       if (live && m.aux) *reinterpret_cast<float4*>(m.aux + 4 * b) = make_float4(auxp + (float)S * logdet, 0.f, 0.f, 0.f);
@@ -529,10 +536,10 @@ __global__ void __launch_bounds__(kBwThreads, 1) mvn_bwd_dh_kernel(const MvnEncP
   const float ginv = ldexpf(1.f, 4 - gexp), gfix = ldexpf(1.f, gexp - 4);
 
   if (tid == 0) {
-    for (int i = 0; i < 2; ++i) { umma::mbar_init(&bar_vfull[i], kBwGen); umma::mbar_init(&bar_vfree[i], 1); }
+    for (int i = 0; i < 2; ++i) { umma::mbar_init(&bar_vfull[i], kBwGenWarps); umma::mbar_init(&bar_vfree[i], 1); }
     for (int i = 0; i < 3; ++i) { umma::mbar_init(&bar_wfull[i], 1); umma::mbar_init(&bar_wempty[i], 1); }
     umma::mbar_init(&bar_dfull, 1);
-    umma::mbar_init(&bar_dfree, 128);
+    umma::mbar_init(&bar_dfree, 4);
     umma::fence_mbar_init();
   }
   if (warp == kBwGenWarps + 1) umma::tmem_alloc(&tmem_base_sm, 512);
@@ -608,7 +615,7 @@ __global__ void __launch_bounds__(kBwThreads, 1) mvn_bwd_dh_kernel(const MvnEncP
           unsigned char* Vh = Vb + (size_t)vb * L.v_bytes;
           gen_unit(Vh, Vh + L.v_bytes / 2, RSV, 0, er, t, sub, I, Jc, gI, lI, dadd);
           umma::fence_proxy_async();
-          umma::mbar_arrive(&bar_vfull[vb]);
+          warp_arrive(&bar_vfull[vb], lane);
           if (Jc == I) { ++I; Jc = 0; if (I < NB) load_g(m, s, b, live, I, sub, ginv, gI, lI, dadd); }
           else ++Jc;
         }
@@ -643,7 +650,7 @@ __global__ void __launch_bounds__(kBwThreads, 1) mvn_bwd_dh_kernel(const MvnEncP
           }
         }
         umma::fence_before_sync();
-        umma::mbar_arrive(&bar_dfree);
+        warp_arrive(&bar_dfree, lane);
       }
     }
   }
@@ -654,46 +661,89 @@ __global__ void __launch_bounds__(kBwThreads, 1) mvn_bwd_dh_kernel(const MvnEncP
 }
 
 // ---- d [W22 | b22][(i,j)][h] = sum over persons of V[person][(i,j)] [hidden | 1][person][h] -------------------------
-// CTA (pg, qg): chunks [pg * CPB, ..) of the factor columns x person tiles qg, qg + n_qg, ..; the accumulators of the
-// slab stay in tensor memory over every tile; partial results [qg] are summed in a fixed order by mvn_dw_finalize.
+// CTA (pg, qg): chunks [pg * CPB, ..) of the factor columns x 64-person tiles qg, qg + n_qg, ..; the accumulators of
+// the slab stay in tensor memory; partial results [qg] are summed in a fixed order by mvn_dw_finalize.  A CTA has
+// only CPB chunks of work per tile, so nothing per tile may sit on the critical path: the noise rows and the
+// [hidden | 1] operand tile (pre-split once per step, mvn_himg_kernel) arrive by bulk copies one tile ahead, the
+// handful of G / diag L values a thread needs by 4-byte cp.async one tile ahead, the (I, Jc) of the slab's units from
+// a table built once.
+constexpr int kDwTP = 64;                  // persons per tile (UMMA K extent: 4 k-steps)
+constexpr int kDwFlushTiles = 16;          // accumulate in TMEM for at most 16 tiles = 192 MMAs per accumulator
+constexpr int kDwMaxRows = 6;              // block rows of L that a slab of <= 8 chunks (16 units) can touch
+__host__ __device__ inline int dw_cpb(int H) { return 512 / mv_kh(H) < 8 ? 512 / mv_kh(H) : 8; }   // chunks per CTA slab
+__host__ __device__ inline size_t mv_himg_tile_bytes(int H) { return (size_t)2 * kDwTP * mv_kh(H) * 2; }
+
 struct DwSmem {
-  uint32_t offEps, offV, offH, total, v_bytes, h_bytes;
-  int ES, nvb;
+  uint32_t offEps, offH, offV, offG, offL, total, eps_bytes, h_bytes, v_bytes;
+  int ES;
 };
-__host__ __device__ inline DwSmem dw_smem(int K, int H) {
+__host__ __device__ inline DwSmem dw_smem(int K, int H, bool bulk) {
   DwSmem s;
-  s.ES = (K + 7) / 8 * 8 + 4;
-  s.v_bytes = 2u * kMvTP * kMvCN * 2;                   // hi + lo, 128 persons x 128 columns
-  s.h_bytes = 2u * kMvTP * (uint32_t)mv_kh(H) * 2;      // hi + lo, 128 persons x KH
+  s.ES = bulk ? K : (K + 7) / 8 * 8 + 4;               // bulk: rows as they lie in global memory (K % 4 == 0)
+  s.eps_bytes = ((uint32_t)kDwTP * s.ES * 4 + 64 + 127) & ~127u;
+  s.h_bytes = (uint32_t)mv_himg_tile_bytes(H);
+  s.v_bytes = 2u * kDwTP * kMvCN * 2;
   uint32_t o = 0;
-  s.offEps = o; o += (uint32_t)kMvTP * s.ES * 4;
-  s.nvb = (o + 2 * s.v_bytes + s.h_bytes <= 227u * 1024u) ? 2 : 1;      // K > 112: one V buffer
-  s.offV = o; o += (uint32_t)s.nvb * s.v_bytes;
-  s.offH = o; o += s.h_bytes;
+  s.offEps = o; o += 2 * s.eps_bytes;
+  s.offH = o; o += 2 * s.h_bytes;
+  s.offV = o; o += 2 * s.v_bytes;
+  s.offG = o; o += 2u * kDwMaxRows * 8 * kDwTP * 4;
+  s.offL = o; o += 2u * kDwMaxRows * 8 * kDwTP * 4;
   s.total = o;
   return s;
 }
-constexpr int kDwFlushTiles = 8;
-__host__ __device__ inline int dw_cpb(int H) { return 512 / mv_kh(H) < 8 ? 512 / mv_kh(H) : 8; }   // chunks per CTA slab
 
-__global__ void __launch_bounds__(kBwThreads, 1) mvn_bwd_dw_kernel(const MvnEncParams P, const int n_pg, const int n_qg) {
+// [hidden | 1 | 0] of 64 persons as fp16 hi / lo operand tiles T[r = person][c = h], one 2 x 64 x KH x 2 byte image per tile
+__global__ void mvn_himg_kernel(const float* __restrict__ hidden, int64_t B, int H, int KH, unsigned char* __restrict__ img) {
+  const int n_oct = KH / 8;
+  const int64_t n_rows = (B + kDwTP - 1) / kDwTP * kDwTP;
+  const uint32_t RSH = (uint32_t)n_oct * kCSb;
+  const size_t tile_bytes = (size_t)kDwTP * KH * 2;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n_rows * n_oct; e += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t b = e / n_oct;
+    const int o = (int)(e - b * n_oct);
+    float v[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const int k = o * 8 + q;
+      v[q] = b >= B ? 0.f : (k < H ? hidden[b * H + k] : (k == H ? 1.f : 0.f));
+    }
+    uint4 hi, lo;
+    split8(v, hi, lo);
+    const int r = (int)(b % kDwTP);
+    unsigned char* base = img + (size_t)(b / kDwTP) * 2 * tile_bytes + (size_t)(r >> 3) * RSH + (size_t)o * kCSb + (r & 7) * 16;
+    *reinterpret_cast<uint4*>(base) = hi;
+    *reinterpret_cast<uint4*>(base + tile_bytes) = lo;
+  }
+}
+
+__device__ __forceinline__ void cp_async4(void* dst_smem, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(umma::smem_u32(dst_smem)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+__global__ void __launch_bounds__(kBwThreads, 1) mvn_bwd_dw_kernel(const MvnEncParams P, const int n_pg, const int n_qg,
+                                                                    const int bulk) {
   extern __shared__ __align__(128) unsigned char smem[];
-  __shared__ uint64_t bar_vfull[2], bar_vfree[2], bar_hfree, bar_done, bar_drained;
+  __shared__ uint64_t bar_efull[2], bar_tfree[2], bar_vfull[2], bar_vfree[2], bar_done, bar_drained;
   __shared__ uint32_t tmem_base_sm;
+  __shared__ int utab[16][2];                         // (I, Jc) of the slab's units; I >= NB: beyond the factor
   const MirtParams& m = P.m;
   const int K = m.K, S = m.S, H = P.H, KH = mv_kh(H), NB = mv_nb(K), NU = NB * (NB + 1) / 2;
-  const DwSmem L = dw_smem(K, H);
+  const DwSmem L = dw_smem(K, H, bulk != 0);
   const int ES = L.ES, CPB = dw_cpb(H), n_chunks = mv_chunks(K);
-  const uint32_t NVB = (uint32_t)L.nvb;
-  float* eps_s = reinterpret_cast<float*>(smem + L.offEps);
+  unsigned char* Hb = smem + L.offH;
   unsigned char* Vb = smem + L.offV;
-  unsigned char* Hh = smem + L.offH;
-  unsigned char* Hl = Hh + L.h_bytes / 2;
+  float* gsm = reinterpret_cast<float*>(smem + L.offG);
+  float* lsm = reinterpret_cast<float*>(smem + L.offL);
   const uint32_t RSV = (kMvCN / 8) * kCSb, RSH = (uint32_t)(KH / 8) * kCSb;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int pg = blockIdx.x % n_pg, qg = blockIdx.x / n_pg;
   const int c0 = pg * CPB, c1 = min(c0 + CPB, n_chunks), nblk = c1 - c0;
-  const int64_t n_tiles = (m.B + kMvTP - 1) / kMvTP;
+  const int64_t n_tiles = (m.B + kDwTP - 1) / kDwTP;
+  const int64_t my_tiles = qg < n_tiles ? (n_tiles - qg + n_qg - 1) / n_qg : 0;       // tiles qg, qg + n_qg, ..
+  const int64_t n_steps = my_tiles * S;                                              // (tile, particle) pairs
   const float* eps_src = m.eps ? m.eps : P.eps_out;
   // V is an fp16 hi/lo operand: G is scaled by a power of two so that max |G'| <= 16 (exact; undone at the drain)
   int gexp;
@@ -701,107 +751,168 @@ __global__ void __launch_bounds__(kBwThreads, 1) mvn_bwd_dw_kernel(const MvnEncP
   const float ginv = ldexpf(1.f, 4 - gexp), gfix = ldexpf(1.f, gexp - 4);
 
   if (tid == 0) {
-    for (int i = 0; i < 2; ++i) { umma::mbar_init(&bar_vfull[i], kBwGen); umma::mbar_init(&bar_vfree[i], 1); }
-    umma::mbar_init(&bar_hfree, 1);
+    for (int i = 0; i < 2; ++i) {
+      umma::mbar_init(&bar_efull[i], bulk ? 2 : 1);
+      umma::mbar_init(&bar_tfree[i], kBwGenWarps + 1);
+      umma::mbar_init(&bar_vfull[i], kBwGenWarps);
+      umma::mbar_init(&bar_vfree[i], 1);
+    }
     umma::mbar_init(&bar_done, 1);
-    umma::mbar_init(&bar_drained, 128);
+    umma::mbar_init(&bar_drained, 4);
     umma::fence_mbar_init();
+  }
+  if (tid < 2 * nblk) {
+    int I, Jc;
+    unit_to_block(2 * c0 + tid, I, Jc);
+    utab[tid][0] = 2 * c0 + tid < NU ? I : NB;
+    utab[tid][1] = Jc;
   }
   if (warp == kBwGenWarps + 1) umma::tmem_alloc(&tmem_base_sm, 512);
   umma::fence_before_sync();
   __syncthreads();
   umma::fence_after_sync();
   const uint32_t tmem = tmem_base_sm;
+  const int I_first = utab[0][0];
 
-  if (warp == kBwGenWarps + 1) {
+  if (warp == kBwGenWarps) {
+    if (lane == 0) {                                   // bulk-copy producer: [hidden | 1] tile (+ noise rows) of step n
+      for (int64_t n = 0; n < n_steps; ++n) {
+        const uint32_t buf = (uint32_t)(n & 1);
+        const int64_t tile = qg + (n / S) * n_qg;
+        const int s = (int)(n % S);
+        umma::mbar_wait(&bar_tfree[buf], (uint32_t)(((n >> 1) & 1) ^ 1));
+        umma::bulk_load(Hb + (size_t)buf * L.h_bytes, P.himg + (size_t)tile * L.h_bytes, L.h_bytes, &bar_efull[buf]);
+        if (bulk)
+          umma::bulk_load(smem + L.offEps + (size_t)buf * L.eps_bytes, eps_src + ((int64_t)s * m.B + tile * kDwTP) * K,
+                          (uint32_t)kDwTP * K * 4, &bar_efull[buf]);
+      }
+    }
+  } else if (warp == kBwGenWarps + 1) {
     if (lane == 0) {                                   // MMA issuer
       const uint32_t idesc = umma::make_idesc_f16(kMvCN, KH, umma::kMajorMN, umma::kMajorMN);
-      const uint32_t sHh = umma::smem_u32(Hh), sHl = umma::smem_u32(Hl);
-      uint32_t it = 0, ntile = 0, nflush = 0;
-      bool first = true;
-      for (int64_t tile = qg; tile < n_tiles; tile += n_qg, ++ntile) {
-        for (int s = 0; s < S; ++s)
-          for (int k = 0; k < nblk; ++k, ++it) {
-            const uint32_t vb = it % NVB;
-            umma::mbar_wait(&bar_vfull[vb], (it / NVB) & 1);         // V chunk (and, first of the tile, the H tile) staged
-            umma::fence_after_sync();
-            const uint32_t sVh = umma::smem_u32(Vb + (size_t)vb * L.v_bytes), sVl = sVh + L.v_bytes / 2;
-            uint32_t acc = (first && s == 0) ? 0u : 1u;
-#pragma unroll 1
-            for (int ks = 0; ks < kMvTP / 16; ++ks) {
+      uint32_t it = 0, nflush = 0;
+      bool fresh = true;                               // the accumulators hold nothing yet (start, or just flushed)
+      for (int64_t n = 0; n < n_steps; ++n) {
+        const uint32_t buf = (uint32_t)(n & 1);
+        umma::mbar_wait(&bar_efull[buf], (uint32_t)((n >> 1) & 1));
+        const uint32_t sHh = umma::smem_u32(Hb + (size_t)buf * L.h_bytes), sHl = sHh + L.h_bytes / 2;
+        for (int k = 0; k < nblk; ++k, ++it) {
+          const uint32_t vb = it & 1;
+          umma::mbar_wait(&bar_vfull[vb], (it >> 1) & 1);
+          umma::fence_after_sync();
+          const uint32_t sVh = umma::smem_u32(Vb + (size_t)vb * L.v_bytes), sVl = sVh + L.v_bytes / 2;
+          uint32_t acc = fresh ? 0u : 1u;
 #pragma unroll
-              for (int term = 0; term < 3; ++term) {
-                const uint64_t da = umma::make_desc((term == 2 ? sVl : sVh) + ks * 2 * RSV, RSV, kCSb);
-                const uint64_t db = umma::make_desc((term == 1 ? sHl : sHh) + ks * 2 * RSH, RSH, kCSb);
-                umma::mma_f16_ss(tmem + k * KH, da, db, idesc, acc);
-                acc = 1;
-              }
+          for (int ks = 0; ks < kDwTP / 16; ++ks) {
+#pragma unroll
+            for (int term = 0; term < 3; ++term) {
+              const uint64_t da = umma::make_desc((term == 2 ? sVl : sVh) + ks * 2 * RSV, RSV, kCSb);
+              const uint64_t db = umma::make_desc((term == 1 ? sHl : sHh) + ks * 2 * RSH, RSH, kCSb);
+              umma::mma_f16_ss(tmem + k * KH, da, db, idesc, acc);
+              acc = 1;
             }
-            umma::commit(&bar_vfree[vb]);
           }
-        first = false;
-        umma::commit(&bar_hfree);                      // every MMA that reads this tile's H tile has completed
-        if ((ntile + 1) % kDwFlushTiles == 0 || tile + n_qg >= n_tiles) {
+          umma::commit(&bar_vfree[vb]);
+        }
+        fresh = false;
+        umma::commit(&bar_tfree[buf]);                 // every MMA that reads this step's H tile has completed
+        if ((n + 1) % kDwFlushTiles == 0 || n + 1 == n_steps) {
           umma::commit(&bar_done);                     // flush: the drain warps add the accumulators to the partial rows
           umma::mbar_wait(&bar_drained, nflush & 1);
           umma::fence_after_sync();
-          first = true;
+          fresh = true;
           ++nflush;
         }
       }
     }
-  } else if (warp < kBwGenWarps) {
-    const int t = tid & 127, sub = tid >> 7;
-    float* er = eps_s + (size_t)t * ES;
-    if (sub == 0)
-      for (int k = K; k < ES; ++k) er[k] = 0.f;
-    uint32_t it = 0, ntile = 0, nflush = 0;
-    for (int64_t tile = qg; tile < n_tiles; tile += n_qg, ++ntile) {
-      const int64_t b = tile * kMvTP + t;
-      const bool live = b < m.B;
-      for (int s = 0; s < S; ++s) {
-        gen_bar();
-        load_eps_tile(eps_src + (int64_t)s * m.B * K, tile * kMvTP, m.B, K, eps_s, ES, warp, lane);
-        if (s == 0) {
-          // [hidden | 1 | 0] tile (MN-major B operand: T[r = person][c = h]); the previous tile's MMAs are done with it
-          umma::mbar_wait(&bar_hfree, (ntile & 1) ^ 1);
-          const float* hr = P.hidden + (live ? b : 0) * H;
-          for (int o = sub; o < KH / 8; o += kBwGen / 128) {
-            float v[8];
-#pragma unroll
-            for (int q = 0; q < 8; ++q) {
-              const int k = o * 8 + q;
-              v[q] = !live ? 0.f : (k < H ? hr[k] : (k == H ? 1.f : 0.f));
-            }
-            uint4 hi, lo;
-            split8(v, hi, lo);
-            const uint32_t off = (uint32_t)(t >> 3) * RSH + (uint32_t)o * kCSb + (uint32_t)(t & 7) * 16u;
-            *reinterpret_cast<uint4*>(Hh + off) = hi;
-            *reinterpret_cast<uint4*>(Hl + off) = lo;
-          }
-        }
-        gen_bar();
-        for (int k = 0; k < nblk; ++k, ++it) {
-          const uint32_t vb = it % NVB;
-          umma::mbar_wait(&bar_vfree[vb], ((it / NVB) & 1) ^ 1);
-          unsigned char* Vh = Vb + (size_t)vb * L.v_bytes;
-#pragma unroll 1
-          for (int half = 0; half < 2; ++half) {
-            const int u = 2 * (c0 + k) + half;
-            int I, Jc;
-            unit_to_block(u, I, Jc);
-            float gI[2], lI[2], dadd[2];
-            load_g(m, s, b, live && u < NU, I, sub, ginv, gI, lI, dadd);
-            gen_unit(Vh, Vh + L.v_bytes / 2, RSV, 64 * half, er, t, sub, I < NB ? I : 0, I < NB ? Jc : 1, gI, lI, dadd);
-          }
-          umma::fence_proxy_async();
-          umma::mbar_arrive(&bar_vfull[vb]);
+  } else {
+    const int person = tid & (kDwTP - 1), sub = tid >> 6;            // sub = row of the unit this thread generates
+    uint32_t it = 0, nflush = 0;
+    // G and diag L of the thread's rows (8 I + sub for the slab's block rows) of step n -> buffer n & 1, asynchronously
+    auto prefetch_g = [&](int64_t n) {
+      const uint32_t buf = (uint32_t)(n & 1);
+      const int64_t b = (qg + (n / S) * n_qg) * kDwTP + person;
+      const int s = (int)(n % S);
+      for (int o = 0; o < kDwMaxRows; ++o) {
+        const int i = 8 * (I_first + o) + sub;
+        float* gd = gsm + ((size_t)(buf * kDwMaxRows + o) * 8 + sub) * kDwTP + person;
+        float* ld = lsm + ((size_t)(buf * kDwMaxRows + o) * 8 + sub) * kDwTP + person;
+        if (b < m.B && i < K) {
+          cp_async4(gd, m.gx + ((int64_t)s * m.B + b) * K + i);
+          cp_async4(ld, m.diagL + b * K + i);
+        } else {
+          *gd = 0.f;
+          *ld = 0.f;
         }
       }
-      // Flush every kDwFlushTiles tiles: the accumulators are added (round-to-nearest, fixed order) to this CTA's
+      cp_async_commit();
+    };
+    if (n_steps > 0) prefetch_g(0);
+    for (int64_t n = 0; n < n_steps; ++n) {
+      const uint32_t buf = (uint32_t)(n & 1);
+      const int64_t tile = qg + (n / S) * n_qg;
+      const int s = (int)(n % S);
+      const int64_t b = tile * kDwTP + person;
+      const bool live = b < m.B;
+      float* eps_t = reinterpret_cast<float*>(smem + L.offEps + (size_t)buf * L.eps_bytes);
+      if (!bulk) {                                     // injected noise / K % 4 != 0: rows loaded here, padded pitch
+        const float* src = eps_src + (int64_t)s * m.B * K;
+        for (int pp = warp * (kDwTP / kBwGenWarps); pp < (warp + 1) * (kDwTP / kBwGenWarps); ++pp) {
+          const int64_t bb = tile * kDwTP + pp;
+          for (int k = lane; k < ES; k += 32) eps_t[(size_t)pp * ES + k] = (bb < m.B && k < K) ? src[bb * K + k] : 0.f;
+        }
+        gen_bar();
+      } else {
+        umma::mbar_wait(&bar_efull[buf], (uint32_t)((n >> 1) & 1));
+      }
+      cp_async_wait_all();                             // this step's G / diag L (own entries only: no barrier needed)
+      if (n + 1 < n_steps) prefetch_g(n + 1);
+      const float* er = eps_t + (size_t)person * ES;
+      for (int k = 0; k < nblk; ++k, ++it) {
+        const uint32_t vb = it & 1;
+        umma::mbar_wait(&bar_vfree[vb], ((it >> 1) & 1) ^ 1);
+        unsigned char* Vh = Vb + (size_t)vb * L.v_bytes;
+        unsigned char* Vl = Vh + L.v_bytes / 2;
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          const int I = utab[2 * k + half][0], Jc = utab[2 * k + half][1];
+          float v[8];
+          if (I < NB) {
+            const int o = I - I_first;
+            const float g = ginv * gsm[((size_t)(buf * kDwMaxRows + o) * 8 + sub) * kDwTP + person];
+            const float4 e0 = *reinterpret_cast<const float4*>(er + 8 * Jc);
+            const float4 e1 = *reinterpret_cast<const float4*>(er + 8 * Jc + 4);
+            v[0] = g * e0.x; v[1] = g * e0.y; v[2] = g * e0.z; v[3] = g * e0.w;
+            v[4] = g * e1.x; v[5] = g * e1.y; v[6] = g * e1.z; v[7] = g * e1.w;
+            if (Jc == I) {                             // diagonal block: exp chain rule + entropy term, zero above it
+              const float lii = lsm[((size_t)(buf * kDwMaxRows + o) * 8 + sub) * kDwTP + person];
+              const float dadd = (live && 8 * I + sub < K && s == 0) ? -m.scale * ginv : 0.f;
+#pragma unroll
+              for (int jj = 0; jj < 8; ++jj) v[jj] = jj == sub ? fmaf(v[jj], lii, dadd) : (jj > sub ? 0.f : v[jj]);
+            }
+            if (!live) {                               // rows beyond B: the bulk copy brought whatever lies there
+#pragma unroll
+              for (int jj = 0; jj < 8; ++jj) v[jj] = 0.f;
+            }
+          } else {
+#pragma unroll
+            for (int jj = 0; jj < 8; ++jj) v[jj] = 0.f;
+          }
+          uint4 hi, lo;
+          split8(v, hi, lo);
+          const uint32_t off = (uint32_t)(person >> 3) * RSV + (uint32_t)(8 * half + sub) * kCSb + (uint32_t)(person & 7) * 16u;
+          *reinterpret_cast<uint4*>(Vh + off) = hi;
+          *reinterpret_cast<uint4*>(Vl + off) = lo;
+        }
+        umma::fence_proxy_async();
+        warp_arrive(&bar_vfull[vb], lane);
+      }
+      warp_arrive(&bar_tfree[buf], lane);              // done with this step's noise rows
+      // Flush every kDwFlushTiles steps: the accumulators are added (round-to-nearest, fixed order) to this CTA's
       // partial rows, which bounds the chain of truncating tensor-core accumulations (see mvn_bwd_dh_kernel).
-      if ((ntile + 1) % kDwFlushTiles == 0 || tile + n_qg >= n_tiles) {
+      if ((n + 1) % kDwFlushTiles == 0 || n + 1 == n_steps) {
         if (warp < 4) {                                // thread = factor column of the chunk = TMEM lane
+          const int t = tid;
           umma::mbar_wait(&bar_done, nflush & 1);
           umma::fence_after_sync();
           const uint32_t tl = tmem + ((uint32_t)(warp * 32) << 16);
@@ -823,9 +934,15 @@ __global__ void __launch_bounds__(kBwThreads, 1) mvn_bwd_dw_kernel(const MvnEncP
             }
           }
           umma::fence_before_sync();
-          umma::mbar_arrive(&bar_drained);
+          warp_arrive(&bar_drained, lane);
         }
         ++nflush;
+      }
+    }
+    if (n_steps == 0 && warp < 4) {                    // a CTA without persons still owns its partial rows
+      for (int k = 0; k < nblk; ++k) {
+        float* dst = P.dw_part + ((size_t)qg * n_chunks * kMvCN + (size_t)(c0 + k) * kMvCN + tid) * KH;
+        for (int q = 0; q < KH; ++q) dst[q] = 0.f;
       }
     }
   }
@@ -866,6 +983,12 @@ static void dw_grid(int K, int H, int* n_pg, int* n_qg) {
   int q = num_sms() / *n_pg;
   *n_qg = q < 1 ? 1 : q;
 }
+size_t mvn_himg_bytes(int64_t B, int H) {
+  return ((size_t)((B + kDwTP - 1) / kDwTP) * mv_himg_tile_bytes(H) + 255) & ~size_t(255);
+}
+size_t mvn_eps_bytes(int64_t B, int K, int S) {       // the draws + one tile of zero padding (bulk copies of the last tile)
+  return (((size_t)S * B + kDwTP) * K * 4 + 64 + 255) & ~size_t(255);
+}
 size_t mvn_dwpart_bytes(int K, int H) {
   int n_pg, n_qg;
   dw_grid(K, H, &n_pg, &n_qg);
@@ -896,13 +1019,25 @@ int launch_mvn_bwd(const MvnEncParams& P, cudaStream_t st) {
     VIPSY_CUDA_CHECK(cudaGetLastError());
   }
   if (P.d_w22 || P.d_b22) {
-    const DwSmem L = dw_smem(K, H);
+    // noise rows by bulk copy when they lie in our own (padded) buffer and a row is a whole number of 16-byte pieces
+    const int bulk = (P.m.eps == nullptr && (K & 3) == 0) ? 1 : 0;
+    const DwSmem L = dw_smem(K, H, bulk != 0);
     VIPSY_REQUIRE(L.total <= 227 * 1024, VIPSY_ERR_UNSUPPORTED, "mvn encoder backward: K=%d H=%d does not fit shared memory", K, H);
     VIPSY_CUDA_CHECK(cudaFuncSetAttribute(mvn_bwd_dw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
+    const int64_t n_tiles64 = (P.m.B + kDwTP - 1) / kDwTP;
+    {
+      const int64_t total = n_tiles64 * kDwTP * (mv_kh(H) / 8);
+      int64_t g = (total + 255) / 256;
+      if (g > (int64_t)num_sms() * 16) g = (int64_t)num_sms() * 16;
+      mvn_himg_kernel<<<(int)g, 256, 0, st>>>(P.hidden, P.m.B, H, mv_kh(H), P.himg);
+      VIPSY_CUDA_CHECK(cudaGetLastError());
+    }
+    if (bulk)     // the last tile's copy runs past the last person's row: finite (zero) padding behind the draws
+      VIPSY_CUDA_CHECK(cudaMemsetAsync(P.eps_out + (size_t)P.m.S * P.m.B * K, 0, (size_t)kDwTP * K * 4 + 64, st));
     int n_pg, n_qg;
     dw_grid(K, H, &n_pg, &n_qg);
-    if (n_qg > n_tiles) n_qg = (int)n_tiles;
-    mvn_bwd_dw_kernel<<<n_pg * n_qg, kBwThreads, L.total, st>>>(P, n_pg, n_qg);
+    if (n_qg > n_tiles64) n_qg = (int)n_tiles64;
+    mvn_bwd_dw_kernel<<<n_pg * n_qg, kBwThreads, L.total, st>>>(P, n_pg, n_qg, bulk);
     VIPSY_CUDA_CHECK(cudaGetLastError());
     const int total = K * (K + 1) / 2 * (H + 1);
     mvn_dw_finalize_kernel<<<(total + 255) / 256, 256, 0, st>>>(P.dw_part, n_qg, mv_chunks(K) * kMvCN, K, H, mv_kh(H),
@@ -963,7 +1098,7 @@ using namespace vipsy;
 extern "C" {
 
 // workspace: [ mirt_layout of irt | fc22 operand images | the draws | partial d [W22 | b22] ]
-struct MvnLayout { size_t mirt, wimg, wimgb, eps, dwpart, gmax, total; };
+struct MvnLayout { size_t mirt, wimg, wimgb, himg, eps, dwpart, gmax, total; };
 static MvnLayout mvn_layout(const VipsyMvnEncoderIrtArgs* a) {
   const VipsyIrtArgs& r = a->irt;
   MvnLayout L;
@@ -971,7 +1106,8 @@ static MvnLayout mvn_layout(const VipsyMvnEncoderIrtArgs* a) {
   L.mirt = o; o += (mirt_workspace_bytes(&r) + 255) & ~size_t(255);
   L.wimg = o; o += mvn_wimg_bytes(r.n_dims, a->n_hidden);
   L.wimgb = o; o += mvn_wimgb_bytes(r.n_dims, a->n_hidden);
-  L.eps = o; o += r.eps ? 0 : (((size_t)r.n_particles * r.batch * r.n_dims * 4 + 255) & ~size_t(255));
+  L.himg = o; o += mvn_himg_bytes(r.batch, a->n_hidden);
+  L.eps = o; o += r.eps ? 0 : mvn_eps_bytes(r.batch, r.n_dims, r.n_particles);
   L.dwpart = o; o += mvn_dwpart_bytes(r.n_dims, a->n_hidden);
   L.gmax = o; o += 256;
   L.total = o;
@@ -1016,6 +1152,7 @@ int vipsy_irt_mvn_encoder_elbo_grad(const VipsyMvnEncoderIrtArgs* a, void* strea
   MvnEncParams P = mvn_params(a);
   P.wimg = ws + L.wimg;
   P.wimg_b = ws + L.wimgb;
+  P.himg = ws + L.himg;
   P.eps_out = r.eps ? nullptr : reinterpret_cast<float*>(ws + L.eps);
   P.dw_part = reinterpret_cast<float*>(ws + L.dwpart);
   P.gmax = reinterpret_cast<float*>(ws + L.gmax);

@@ -38,6 +38,7 @@ struct MvnEncParams {
   int H;
   unsigned char* wimg;       // [chunks][hi | lo] operand image of 64 * [fc22.weight | fc22.bias | 0]
   unsigned char* wimg_b;     // [units][hi | lo] 64 padded columns x NH of 64 * fc22.weight (backward: d hidden), or null
+  unsigned char* himg;       // [ceil(B / 64)][hi | lo] 64 persons x KH of [hidden | 1 | 0] (backward: d fc22), or null
   float* eps_out;            // [S*B][K] the draws (for the backward pass and for parity tests), or null
   float* logdet_out;         // [B] sum_i log L_ii, or null
   float* dw_part;            // [n_qg][PP][KH]
@@ -55,5 +56,7 @@ int launch_mvn_bwd(const MvnEncParams& P, cudaStream_t st);
 size_t mvn_wimg_bytes(int K, int H);
 size_t mvn_wimgb_bytes(int K, int H);
 size_t mvn_dwpart_bytes(int K, int H);
+size_t mvn_himg_bytes(int64_t B, int H);
+size_t mvn_eps_bytes(int64_t B, int K, int S);
 
 }  // namespace vipsy
