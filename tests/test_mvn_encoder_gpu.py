@@ -94,14 +94,20 @@ def test_fused_guide_matches_oracle(ops, B, J, K, H, S, model):
     assert not r["d_a"].cpu()[~free].any()
 
 
-def test_fused_guide_equals_materialised_factor_k100(ops):
-    """K = 100, the BASELINE c3 shape scaled down: the fused path against the three-kernel path fed with the factor
-    matrix fc22 would have written to HBM (fp64 fc22 and fp64 backward through it as the arbiter of the encoder side)."""
-    B, J, K, H = 1000, 100, 100, 64
-    d = make(B, J, K, H, 1, seed=5)
+@pytest.mark.parametrize("B,J,K,H,S", [(1000, 100, 100, 64, 1), (500, 30, 4, 16, 2), (333, 20, 12, 8, 3),
+                                       (200, 25, 6, 16, 2), (129, 40, 32, 64, 1), (1, 7, 8, 3, 1)])
+def test_fused_guide_equals_materialised_factor_k100(ops, B, J, K, H, S):
+    """The library's own noise stream (K % 4 == 0: the draws travel to the backward kernels as pre-split fp16 pair
+    words by bulk copy; otherwise as fp32 rows).  K = 100 is the BASELINE c3 shape scaled down: the fused path against
+    the three-kernel path fed with the factor matrix fc22 would have written to HBM (fp64 fc22 and fp64 backward
+    through it as the arbiter of the encoder side)."""
+    d = make(B, J, K, H, S, seed=5)
     cu = {k: v.cuda() for k, v in d.items()}
     codes = ops.pack_responses(cu["y"])
-    kw = dict(a=cu["a"], b=cu["b"], model="irt_2pl", scale=200.0, seed=3, offset=9)
+    # poison what the allocator hands out next: the kernels must not depend on stale workspace / shared-memory contents
+    junk = torch.full((1 << 22,), float("nan"), device="cuda")
+    del junk
+    kw = dict(a=cu["a"], b=cu["b"], model="irt_2pl", scale=200.0, seed=3, offset=9, n_particles=S)
     r = ops.irt_elbo_grad(codes, cu["mu"], mvn_encoder=(cu["hidden"], cu["w22"], cu["b22"]), **kw)
     hd, wd, bd = (cu[n].double().requires_grad_(True) for n in ("hidden", "w22", "b22"))
     packed = hd @ wd.T + bd

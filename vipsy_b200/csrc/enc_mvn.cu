@@ -52,6 +52,61 @@ __device__ __forceinline__ void split8(const float (&v)[8], uint4& hi, uint4& lo
   lo = make_uint4(l[0], l[1], l[2], l[3]);
 }
 
+// The draws in "split" form: a row of K words, word 2m = half2(hi_2m, hi_2m+1), word 2m+1 = half2(lo_2m, lo_2m+1)
+// with z = hi + lo to 2^-22: eight consecutive draws are 32 bytes {H01, L01, H23, L23, H45, L45, H67, L67}.
+__device__ __forceinline__ void split_pair(float z0, float z1, uint32_t& H, uint32_t& L) {
+  const __half2 h = __floats2half2_rn(z0, z1);
+  const float2 hf = __half22float2(h);
+  H = *reinterpret_cast<const uint32_t*>(&h);
+  L = pk_half2(z0 - hf.x, z1 - hf.y);
+}
+__device__ __forceinline__ __half2 as_h2(uint32_t w) { return *reinterpret_cast<const __half2*>(&w); }
+__device__ __forceinline__ uint32_t h2_bits(__half2 h) { return *reinterpret_cast<const uint32_t*>(&h); }
+
+// One row-octet of V = g * eps straight into fp16 hi / lo operand pieces, in packed half arithmetic: with g = gh + gl
+// and eps = eh + el,  hi = fl16(gh eh),  lo = fl16(gl eh + fl16(gh el + (gh eh - hi)))  -- the residual of the first
+// product is exact (one fused rounding), the dropped gl el term and the roundings of lo are 2^-22 of V.  16 HFMA2-class
+// instructions per 8 elements instead of 8 FMUL + 4 + 16 + 4 conversions.
+__device__ __forceinline__ void gen_octet(float g, const uint4& w0, const uint4& w1, uint4& hi, uint4& lo) {
+  const __half2 gh = __float2half2_rn(g);
+  const __half2 gl = __float2half2_rn(g - __low2float(gh));
+  auto one = [&](uint32_t Hw, uint32_t Lw, uint32_t& oh, uint32_t& ol) {
+    const __half2 eh = as_h2(Hw), el = as_h2(Lw);
+    const __half2 h = __hmul2(gh, eh);
+    __half2 r = __hfma2(gh, eh, __hneg2(h));
+    r = __hfma2(gh, el, r);
+    r = __hfma2(gl, eh, r);
+    oh = h2_bits(h);
+    ol = h2_bits(r);
+  };
+  one(w0.x, w0.y, hi.x, lo.x);
+  one(w0.z, w0.w, hi.y, lo.y);
+  one(w1.x, w1.y, hi.z, lo.z);
+  one(w1.z, w1.w, hi.w, lo.w);
+}
+// Diagonal block, row r of the unit: element r becomes (g eps_r) L_rr + dadd (exp chain rule + entropy term, in
+// fp32), the elements above the diagonal are padding -> 0.
+__device__ __forceinline__ void fix_diag(float g, float lii, float dadd, const uint32_t* ep, int r, uint4& hi, uint4& lo) {
+  const uint32_t Hw = ep[(r >> 1) * 2], Lw = ep[(r >> 1) * 2 + 1];
+  const float er = (r & 1) ? __high2float(as_h2(Hw)) + __high2float(as_h2(Lw)) : __low2float(as_h2(Hw)) + __low2float(as_h2(Lw));
+  const float vd = fmaf(g * er, lii, dadd);
+  const __half hd = __float2half_rn(vd);
+  const __half ld = __float2half_rn(vd - __half2float(hd));
+  const uint32_t hb = (uint32_t)__half_as_ushort(hd), lb = (uint32_t)__half_as_ushort(ld);
+  uint32_t* hw = reinterpret_cast<uint32_t*>(&hi);
+  uint32_t* lw = reinterpret_cast<uint32_t*>(&lo);
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    // keep positions < r, replace position r, clear positions > r  (position 2q = low half, 2q + 1 = high half)
+    const uint32_t keep = (2 * q + 1 < r) ? 0xffffffffu : ((2 * q + 1 == r || 2 * q == r) ? 0x0000ffffu : 0u);
+    uint32_t h = hw[q] & keep, l = lw[q] & keep;
+    if (2 * q + 1 == r) { h |= hb << 16; l |= lb << 16; }
+    if (2 * q == r) { h = hb; l = lb; }
+    hw[q] = h;
+    lw[q] = l;
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ operand image
 // Padded column pc of the factor -> (row i, column j) (j > i or i >= K: padding, weight 0).
 __device__ __forceinline__ void mv_row_of(int pc, int& i, int& j) {
@@ -292,6 +347,20 @@ __global__ void __launch_bounds__(kFwThreads, 1) mvn_fwd_kernel(const MvnEncPara
           }
           __syncwarp();
         }
+        if (P.eps_split) {                    // the same rows as fp16 (hi, lo) pair words for the backward kernels
+          __syncwarp();
+          const int64_t b0 = tile * kMvTP + warp * 32;
+          const float* e0 = eps_s + (size_t)(warp * 32) * ES;
+          for (int pp = 0; pp < 32 && b0 + pp < m.B; ++pp) {
+            uint2* dst = reinterpret_cast<uint2*>(P.eps_split + ((int64_t)s * m.B + b0 + pp) * K);
+            for (int mm = lane; mm < K / 2; mm += 32) {
+              uint2 w;
+              split_pair(e0[(size_t)pp * ES + 2 * mm] * kMvWScale, e0[(size_t)pp * ES + 2 * mm + 1] * kMvWScale, w.x, w.y);
+              dst[mm] = w;
+            }
+          }
+          __syncwarp();
+        }
         auxp = fmaf(0.5f, ss, auxp);
         const float* mur = m.mu + (live ? b : 0) * K;
         float* xr = m.x ? m.x + ((int64_t)s * m.B + (live ? b : 0)) * K : nullptr;
@@ -427,9 +496,9 @@ __global__ void __launch_bounds__(kTailThreads) mvn_tail_kernel(const MirtParams
 }
 
 // ------------------------------------------------------------------------------------------------ backward
-constexpr int kBwGenWarps = 16;                        // warps 0-15 generate V: thread = (person, pair of rows of a unit)
+constexpr int kBwGenWarps = 8;                         // warps 0-7 generate V: thread = (person, 2 or 4 rows of a unit)
 constexpr int kBwGen = kBwGenWarps * 32;
-constexpr int kBwThreads = kBwGen + 64;                // + warp 16: bulk-copy producer, warp 17: MMA issuer
+constexpr int kBwThreads = kBwGen + 64;                // + a bulk-copy producer warp and an MMA issuer warp
 
 __device__ __forceinline__ void gen_bar() { asm volatile("bar.sync 1, %0;" ::"n"(kBwGen) : "memory"); }
 
@@ -439,52 +508,13 @@ __device__ __forceinline__ void unit_to_block(int u, int& I, int& Jc) {
   Jc = u - I * (I + 1) / 2;
 }
 
-// The draws of 128 persons (one particle) -> shared memory rows er[person][0..K), read back coalesced.
-__device__ __forceinline__ void load_eps_tile(const float* __restrict__ src /* [B][K] of this particle */, int64_t b0,
-                                              int64_t B, int K, float* eps_s, int ES, int warp, int lane) {
-  constexpr int PW = kMvTP / kBwGenWarps;               // persons per warp
-  for (int pp = 0; pp < PW; ++pp) {
-    const int t = warp * PW + pp;
-    const int64_t b = b0 + t;
-    float* er = eps_s + (size_t)t * ES;
-    for (int k = lane; k < K; k += 32) er[k] = b < B ? src[b * K + k] : 0.f;
-  }
-}
-
-// One 64-column unit (block row I, block column Jc) of V = d loss / d raw for the thread's person, rows 2 sub and
-// 2 sub + 1 of the unit: V[(i, j)] = G_i eps_j; on the diagonal the exp chain rule and the entropy term:
-// d raw_ii = (G_i eps_i) L_ii - scale (mirt_cholgrad_kernel's rule for chol_raw).  fp16 hi / lo 16-byte pieces go to
-// the operand tile T[r = person][c = column] (K-major for V W, MN-major for V^T [hidden | 1]).
-__device__ __forceinline__ void gen_unit(unsigned char* Vh, unsigned char* Vl, uint32_t RS, int col0, const float* er,
-                                         int t, int sub, int I, int Jc, const float (&gI)[2], const float (&lI)[2],
-                                         const float (&dadd)[2]) {
-  const float4 e0 = *reinterpret_cast<const float4*>(er + 8 * Jc);
-  const float4 e1 = *reinterpret_cast<const float4*>(er + 8 * Jc + 4);
-  const float ev[8] = {e0.x, e0.y, e0.z, e0.w, e1.x, e1.y, e1.z, e1.w};
-#pragma unroll
-  for (int rr = 0; rr < 2; ++rr) {
-    const int r = 2 * sub + rr;
-    float v[8];
-#pragma unroll
-    for (int jj = 0; jj < 8; ++jj) v[jj] = gI[rr] * ev[jj];
-    if (Jc == I) {
-#pragma unroll
-      for (int jj = 0; jj < 8; ++jj) v[jj] = jj == r ? fmaf(v[jj], lI[rr], dadd[rr]) : (jj > r ? 0.f : v[jj]);
-    }
-    uint4 hi, lo;
-    split8(v, hi, lo);
-    const uint32_t off = (uint32_t)(t >> 3) * RS + (uint32_t)((col0 >> 3) + r) * kCSb + (uint32_t)(t & 7) * 16u;
-    *reinterpret_cast<uint4*>(Vh + off) = hi;
-    *reinterpret_cast<uint4*>(Vl + off) = lo;
-  }
-}
-
-// G rows 8I + 2 sub + {0, 1} of the thread's person (0 beyond K / B), the diagonal of L for them and the entropy term
+// G rows 8I + NR sub + {0 .. NR-1} of the thread's person (0 beyond K / B), the diagonal of L for them and the entropy term
+template <int NR>
 __device__ __forceinline__ void load_g(const MirtParams& m, int s, int64_t b, bool live, int I, int sub, float ginv,
-                                       float (&gI)[2], float (&lI)[2], float (&dadd)[2]) {
+                                       float (&gI)[NR], float (&lI)[NR], float (&dadd)[NR]) {
 #pragma unroll
-  for (int rr = 0; rr < 2; ++rr) {
-    const int i = 8 * I + 2 * sub + rr;
+  for (int rr = 0; rr < NR; ++rr) {
+    const int i = 8 * I + NR * sub + rr;
     const bool ok = live && i < m.K;
     gI[rr] = ok ? ginv * m.gx[((int64_t)s * m.B + b) * m.K + i] : 0.f;
     lI[rr] = ok ? m.diagL[b * m.K + i] : 0.f;
@@ -493,33 +523,39 @@ __device__ __forceinline__ void load_g(const MirtParams& m, int s, int64_t b, bo
 }
 
 // ---- d hidden[person][h] = (1 / 64) sum_p V[person][p] (64 W22)[p][h]: CTAs own person tiles, every unit of V ------
+constexpr int kDhMaxStages = 8;
 struct DhSmem {
-  uint32_t offEps, offV, offW, total, v_bytes, w_bytes;
-  int ES, nst;
+  uint32_t offEps, offV, offW, total, v_bytes, w_bytes, eps_bytes;
+  int ES, nst, neb;
 };
-__host__ __device__ inline DhSmem dh_smem(int K, int H) {
+__host__ __device__ inline DhSmem dh_smem(int K, int H, bool bulk) {
   DhSmem s;
-  s.ES = (K + 7) / 8 * 8 + 4;
+  s.ES = bulk ? K : (K + 7) / 8 * 8 + 4;               // words per row of the split draws
+  s.eps_bytes = ((uint32_t)kMvTP * s.ES * 4 + 64 + 127) & ~127u;
   s.v_bytes = 2u * kMvTP * 64 * 2;                      // hi + lo, 128 persons x 64 columns
   s.w_bytes = 2u * 64 * (uint32_t)mv_nh(H) * 2;         // hi + lo, 64 columns x NH
-  s.nst = 3;
+  // A bulk copy of a unit takes ~1.2 us from L2: the stream of units needs depth, the draws (one copy per tile)
+  // do not -- so the draws get one buffer and the units every stage that fits (measured: 3 -> 6 stages).
+  s.neb = 1;
+  int nst = (int)((226u * 1024u - s.eps_bytes - 2 * s.v_bytes) / s.w_bytes);
+  s.nst = nst > kDhMaxStages ? kDhMaxStages : nst;
   uint32_t o = 0;
-  s.offEps = o; o += (uint32_t)kMvTP * s.ES * 4;
+  s.offEps = o; o += (uint32_t)s.neb * s.eps_bytes;
   s.offV = o; o += 2 * s.v_bytes;
   s.offW = o; o += (uint32_t)s.nst * s.w_bytes;
   s.total = o;
   return s;
 }
 
-__global__ void __launch_bounds__(kBwThreads, 1) mvn_bwd_dh_kernel(const MvnEncParams P) {
+__global__ void __launch_bounds__(kBwThreads, 1) mvn_bwd_dh_kernel(const MvnEncParams P, const int bulk) {
   extern __shared__ __align__(128) unsigned char smem[];
-  __shared__ uint64_t bar_vfull[2], bar_vfree[2], bar_wfull[3], bar_wempty[3], bar_dfull, bar_dfree;
+  __shared__ uint64_t bar_vfull[2], bar_vfree[2], bar_wfull[kDhMaxStages], bar_wempty[kDhMaxStages], bar_efull[2], bar_efree[2], bar_dfull, bar_dfree;
   __shared__ uint32_t tmem_base_sm;
   const MirtParams& m = P.m;
   const int K = m.K, S = m.S, H = P.H, NH = mv_nh(H), NB = mv_nb(K), NU = NB * (NB + 1) / 2;
-  const DhSmem L = dh_smem(K, H);
-  const int ES = L.ES;
-  float* eps_s = reinterpret_cast<float*>(smem + L.offEps);
+  const DhSmem L = dh_smem(K, H, bulk != 0);
+  const int ES = L.ES, NEB = L.neb;
+  const uint32_t NST = (uint32_t)L.nst;
   unsigned char* Vb = smem + L.offV;
   unsigned char* Wb = smem + L.offW;
   const uint32_t RSV = (64 / 8) * kCSb, RSW = (uint32_t)(NH / 8) * kCSb;
@@ -529,6 +565,8 @@ __global__ void __launch_bounds__(kBwThreads, 1) mvn_bwd_dh_kernel(const MvnEncP
   const uint32_t NACC = 512u / (uint32_t)NH < 8u ? 512u / (uint32_t)NH : 8u;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int64_t n_tiles = (m.B + kMvTP - 1) / kMvTP;
+  const int64_t my_tiles = blockIdx.x < n_tiles ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  const int64_t n_steps = my_tiles * S;                // (tile, particle) pairs of this CTA
   const float* eps_src = m.eps ? m.eps : P.eps_out;
   // V is an fp16 hi/lo operand: G is scaled by a power of two so that max |G'| <= 16 (exact; undone at the drain)
   int gexp;
@@ -536,12 +574,22 @@ __global__ void __launch_bounds__(kBwThreads, 1) mvn_bwd_dh_kernel(const MvnEncP
   const float ginv = ldexpf(1.f, 4 - gexp), gfix = ldexpf(1.f, gexp - 4);
 
   if (tid == 0) {
-    for (int i = 0; i < 2; ++i) { umma::mbar_init(&bar_vfull[i], kBwGenWarps); umma::mbar_init(&bar_vfree[i], 1); }
-    for (int i = 0; i < 3; ++i) { umma::mbar_init(&bar_wfull[i], 1); umma::mbar_init(&bar_wempty[i], 1); }
+    for (int i = 0; i < 2; ++i) {
+      umma::mbar_init(&bar_vfull[i], kBwGenWarps);
+      umma::mbar_init(&bar_vfree[i], 1);
+      umma::mbar_init(&bar_efull[i], 1);
+      umma::mbar_init(&bar_efree[i], kBwGenWarps);
+    }
+    for (int i = 0; i < kDhMaxStages; ++i) { umma::mbar_init(&bar_wfull[i], 1); umma::mbar_init(&bar_wempty[i], 1); }
     umma::mbar_init(&bar_dfull, 1);
     umma::mbar_init(&bar_dfree, 4);
     umma::fence_mbar_init();
   }
+  // The last row-octet of the last person of a tile reaches past the rows a bulk copy brings in (its products meet
+  // zero weights, so the values only have to be finite): clear that tail once.
+  for (int e = 0; e < NEB; ++e)
+    for (uint32_t o = (uint32_t)kMvTP * ES * 4 + 4 * tid; o < L.eps_bytes; o += 4 * kBwThreads)
+      *reinterpret_cast<uint32_t*>(smem + L.offEps + (size_t)e * L.eps_bytes + o) = 0u;
   if (warp == kBwGenWarps + 1) umma::tmem_alloc(&tmem_base_sm, 512);
   umma::fence_before_sync();
   __syncthreads();
@@ -549,19 +597,31 @@ __global__ void __launch_bounds__(kBwThreads, 1) mvn_bwd_dh_kernel(const MvnEncP
   const uint32_t tmem = tmem_base_sm;
 
   if (warp == kBwGenWarps) {
-    if (lane == 0) {                                   // bulk-copy producer: the units of the backward image
+    if (lane == 0) {                                   // bulk-copy producer: the units of the backward image, the draws
+      auto issue_eps = [&](int64_t e) {                // split draws of step e -> buffer e % NEB
+        const uint32_t eb = (uint32_t)(e % NEB);
+        const int64_t tile = blockIdx.x + (e / S) * gridDim.x;
+        umma::mbar_wait(&bar_efree[eb], (uint32_t)((((e / NEB) & 1)) ^ 1));
+        umma::bulk_load(smem + L.offEps + (size_t)eb * L.eps_bytes,
+                        P.eps_split + ((int64_t)(e % S) * m.B + tile * kMvTP) * K, (uint32_t)kMvTP * K * 4, &bar_efull[eb]);
+      };
       uint32_t it = 0;
-      for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x)
-        for (int s = 0; s < S; ++s)
-          for (int u = 0; u < NU; ++u, ++it) {
-            const uint32_t st = it % 3, round = it / 3;
-            umma::mbar_wait(&bar_wempty[st], (round & 1) ^ 1);
-            umma::bulk_load(Wb + (size_t)st * L.w_bytes, P.wimg_b + (size_t)u * L.w_bytes, L.w_bytes, &bar_wfull[st]);
-          }
+      if (bulk && n_steps > 0) issue_eps(0);
+      for (int64_t n = 0; n < n_steps; ++n) {
+        if (bulk && NEB == 2 && n + 1 < n_steps) issue_eps(n + 1);
+        for (int u = 0; u < NU; ++u, ++it) {
+          const uint32_t st = it % NST, round = it / NST;
+          umma::mbar_wait(&bar_wempty[st], (round & 1) ^ 1);
+          umma::bulk_load(Wb + (size_t)st * L.w_bytes, P.wimg_b + (size_t)u * L.w_bytes, L.w_bytes, &bar_wfull[st]);
+        }
+        if (bulk && NEB == 1 && n + 1 < n_steps) issue_eps(n + 1);
+      }
     }
   } else if (warp == kBwGenWarps + 1) {
     if (lane == 0) {                                   // MMA issuer
       const uint32_t idesc = umma::make_idesc_f16(kMvTP, NH, umma::kMajorK, umma::kMajorMN);
+      const uint64_t dV0 = umma::make_desc(umma::smem_u32(Vb), kCSb, RSV);     // V: K-major A
+      const uint64_t dW0 = umma::make_desc(umma::smem_u32(Wb), RSW, kCSb);     // 64 W22 unit: MN-major B
       uint32_t it = 0, ntile = 0;
       for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++ntile) {
         umma::mbar_wait(&bar_dfree, (ntile & 1) ^ 1);
@@ -569,23 +629,23 @@ __global__ void __launch_bounds__(kBwThreads, 1) mvn_bwd_dh_kernel(const MvnEncP
         uint32_t nu = 0;
         for (int s = 0; s < S; ++s)
           for (int u = 0; u < NU; ++u, ++it, ++nu) {
-            const uint32_t vb = it & 1, st = it % 3;
+            const uint32_t vb = it & 1, st = it % NST;
             const uint32_t ai = nu % NACC;               // round-robin over the accumulators (see NACC)
             uint32_t acc = nu < NACC ? 0u : 1u;
             umma::mbar_wait(&bar_vfull[vb], (it >> 1) & 1);
-            umma::mbar_wait(&bar_wfull[st], (it / 3) & 1);
+            umma::mbar_wait(&bar_wfull[st], (it / NST) & 1);
             umma::fence_after_sync();
-            const uint32_t sVh = umma::smem_u32(Vb + (size_t)vb * L.v_bytes), sVl = sVh + L.v_bytes / 2;
-            const uint32_t sWh = umma::smem_u32(Wb + (size_t)st * L.w_bytes), sWl = sWh + L.w_bytes / 2;
+            // descriptors: one base per tile, the k-step only moves the 14-bit start-address field (units of 16 bytes)
+            const uint64_t dVh = dV0 + (uint64_t)((vb * L.v_bytes) >> 4), dVl = dVh + (uint64_t)(L.v_bytes >> 5);
+            const uint64_t dWh = dW0 + (uint64_t)((st * L.w_bytes) >> 4), dWl = dWh + (uint64_t)(L.w_bytes >> 5);
+            const uint32_t td = tmem + ai * NH;
 #pragma unroll
             for (int ks = 0; ks < 4; ++ks) {
-#pragma unroll
-              for (int term = 0; term < 3; ++term) {
-                const uint64_t da = umma::make_desc((term == 2 ? sVl : sVh) + ks * 2 * kCSb, kCSb, RSV);
-                const uint64_t db = umma::make_desc((term == 1 ? sWl : sWh) + ks * 2 * RSW, RSW, kCSb);
-                umma::mma_f16_ss(tmem + ai * NH, da, db, idesc, acc);
-                acc = 1;
-              }
+              const uint64_t ka = (uint64_t)(ks * ((2 * kCSb) >> 4)), kb = (uint64_t)ks * (uint64_t)((2 * RSW) >> 4);
+              umma::mma_f16_ss(td, dVh + ka, dWh + kb, idesc, acc);        // hi * hi
+              umma::mma_f16_ss(td, dVh + ka, dWl + kb, idesc, 1u);         // hi * lo
+              umma::mma_f16_ss(td, dVl + ka, dWh + kb, idesc, 1u);         // lo * hi
+              acc = 1;
             }
             umma::commit(&bar_vfree[vb]);
             umma::commit(&bar_wempty[st]);
@@ -594,33 +654,64 @@ __global__ void __launch_bounds__(kBwThreads, 1) mvn_bwd_dh_kernel(const MvnEncP
       }
     }
   } else {
-    const int t = tid & 127, sub = tid >> 7;
-    float* er = eps_s + (size_t)t * ES;
-    if (sub == 0)
-      for (int k = K; k < ES; ++k) er[k] = 0.f;
-    uint32_t it = 0, ntile = 0;
-    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++ntile) {
+    const int t = tid & 127, sub = tid >> 7;           // thread = (person, rows 4 sub .. 4 sub + 3 of every unit)
+    const uint32_t voff = (uint32_t)(t >> 3) * RSV + (uint32_t)(4 * sub) * kCSb + (uint32_t)(t & 7) * 16u;
+    uint32_t it = 0;
+    for (int64_t n = 0; n < n_steps; ++n) {
+      const uint32_t eb = (uint32_t)(n % NEB);
+      const int64_t tile = blockIdx.x + (n / S) * gridDim.x;
+      const int s = (int)(n % S);
       const int64_t b = tile * kMvTP + t;
       const bool live = b < m.B;
-      for (int s = 0; s < S; ++s) {
+      uint32_t* eps_t = reinterpret_cast<uint32_t*>(smem + L.offEps + (size_t)eb * L.eps_bytes);
+      if (!bulk) {                                     // injected noise / K % 4 != 0: rows split here, padded pitch
         gen_bar();                                     // everyone has finished with the previous draws
-        load_eps_tile(eps_src + (int64_t)s * m.B * K, tile * kMvTP, m.B, K, eps_s, ES, warp, lane);
+        const float* src = eps_src + (int64_t)s * m.B * K;
+        for (int pp = warp * (kMvTP / kBwGenWarps); pp < (warp + 1) * (kMvTP / kBwGenWarps); ++pp) {
+          const int64_t bb = tile * kMvTP + pp;
+          for (int mm = lane; mm < ES / 2; mm += 32) {
+            const float z0 = (bb < m.B && 2 * mm < K) ? src[bb * K + 2 * mm] : 0.f;
+            const float z1 = (bb < m.B && 2 * mm + 1 < K) ? src[bb * K + 2 * mm + 1] : 0.f;
+            split_pair(z0, z1, eps_t[(size_t)pp * ES + 2 * mm], eps_t[(size_t)pp * ES + 2 * mm + 1]);
+          }
+        }
         gen_bar();
-        int I = 0, Jc = 0;
-        float gI[2], lI[2], dadd[2];
-        load_g(m, s, b, live, 0, sub, ginv, gI, lI, dadd);
-        for (int u = 0; u < NU; ++u, ++it) {
-          const uint32_t vb = it & 1;
-          umma::mbar_wait(&bar_vfree[vb], ((it >> 1) & 1) ^ 1);
-          unsigned char* Vh = Vb + (size_t)vb * L.v_bytes;
-          gen_unit(Vh, Vh + L.v_bytes / 2, RSV, 0, er, t, sub, I, Jc, gI, lI, dadd);
-          umma::fence_proxy_async();
-          warp_arrive(&bar_vfull[vb], lane);
-          if (Jc == I) { ++I; Jc = 0; if (I < NB) load_g(m, s, b, live, I, sub, ginv, gI, lI, dadd); }
-          else ++Jc;
+      } else {
+        umma::mbar_wait(&bar_efull[eb], (uint32_t)((n / NEB) & 1));
+      }
+      const uint32_t* er = eps_t + (size_t)t * ES;
+      int I = 0, Jc = 0;
+      float gI[4], lI[4], dadd[4], gN[4], lN[4], dN[4];      // this block row / the next one, fetched a block row ahead
+      load_g<4>(m, s, b, live, 0, sub, ginv, gI, lI, dadd);
+      load_g<4>(m, s, b, live && NB > 1, 1, sub, ginv, gN, lN, dN);
+      for (int u = 0; u < NU; ++u, ++it) {
+        const uint32_t vb = it & 1;
+        umma::mbar_wait(&bar_vfree[vb], ((it >> 1) & 1) ^ 1);
+        unsigned char* Vh = Vb + (size_t)vb * L.v_bytes + voff;
+        unsigned char* Vl = Vh + L.v_bytes / 2;
+        const uint4 w0 = *reinterpret_cast<const uint4*>(er + 8 * Jc), w1 = *reinterpret_cast<const uint4*>(er + 8 * Jc + 4);
+#pragma unroll
+        for (int rr = 0; rr < 4; ++rr) {
+          uint4 hi, lo;
+          gen_octet(gI[rr], w0, w1, hi, lo);
+          if (Jc == I) fix_diag(gI[rr], lI[rr], dadd[rr], er + 8 * Jc, 4 * sub + rr, hi, lo);
+          *reinterpret_cast<uint4*>(Vh + rr * kCSb) = hi;
+          *reinterpret_cast<uint4*>(Vl + rr * kCSb) = lo;
+        }
+        umma::fence_proxy_async();
+        warp_arrive(&bar_vfull[vb], lane);
+        if (Jc == I) {
+          ++I; Jc = 0;
+#pragma unroll
+          for (int rr = 0; rr < 4; ++rr) { gI[rr] = gN[rr]; lI[rr] = lN[rr]; dadd[rr] = dN[rr]; }
+          load_g<4>(m, s, b, live && I + 1 < NB, I + 1, sub, ginv, gN, lN, dN);
+        } else {
+          ++Jc;
         }
       }
-      if (warp < 4) {                                  // drain d hidden of this tile: thread = person = TMEM lane
+      if (bulk) warp_arrive(&bar_efree[eb], lane);     // done with this step's draws
+      if (s == S - 1 && warp < 4) {                    // drain d hidden of this tile: thread = person = TMEM lane
+        const uint32_t ntile = (uint32_t)(n / S);
         umma::mbar_wait(&bar_dfull, ntile & 1);
         umma::fence_after_sync();
         const uint32_t tl = tmem + ((uint32_t)(warp * 32) << 16);
@@ -767,6 +858,9 @@ __global__ void __launch_bounds__(kBwThreads, 1) mvn_bwd_dw_kernel(const MvnEncP
     utab[tid][0] = 2 * c0 + tid < NU ? I : NB;
     utab[tid][1] = Jc;
   }
+  for (int e = 0; e < 2; ++e)                          // finite values behind the rows of a tile (see mvn_bwd_dh_kernel)
+    for (uint32_t o = (uint32_t)kDwTP * ES * 4 + 4 * tid; o < L.eps_bytes; o += 4 * kBwThreads)
+      *reinterpret_cast<uint32_t*>(smem + L.offEps + (size_t)e * L.eps_bytes + o) = 0u;
   if (warp == kBwGenWarps + 1) umma::tmem_alloc(&tmem_base_sm, 512);
   umma::fence_before_sync();
   __syncthreads();
@@ -783,34 +877,35 @@ __global__ void __launch_bounds__(kBwThreads, 1) mvn_bwd_dw_kernel(const MvnEncP
         umma::mbar_wait(&bar_tfree[buf], (uint32_t)(((n >> 1) & 1) ^ 1));
         umma::bulk_load(Hb + (size_t)buf * L.h_bytes, P.himg + (size_t)tile * L.h_bytes, L.h_bytes, &bar_efull[buf]);
         if (bulk)
-          umma::bulk_load(smem + L.offEps + (size_t)buf * L.eps_bytes, eps_src + ((int64_t)s * m.B + tile * kDwTP) * K,
+          umma::bulk_load(smem + L.offEps + (size_t)buf * L.eps_bytes, P.eps_split + ((int64_t)s * m.B + tile * kDwTP) * K,
                           (uint32_t)kDwTP * K * 4, &bar_efull[buf]);
       }
     }
   } else if (warp == kBwGenWarps + 1) {
     if (lane == 0) {                                   // MMA issuer
       const uint32_t idesc = umma::make_idesc_f16(kMvCN, KH, umma::kMajorMN, umma::kMajorMN);
+      const uint64_t dV0 = umma::make_desc(umma::smem_u32(Vb), RSV, kCSb);     // V^T: MN-major A
+      const uint64_t dH0 = umma::make_desc(umma::smem_u32(Hb), RSH, kCSb);     // [hidden | 1]: MN-major B
       uint32_t it = 0, nflush = 0;
       bool fresh = true;                               // the accumulators hold nothing yet (start, or just flushed)
       for (int64_t n = 0; n < n_steps; ++n) {
         const uint32_t buf = (uint32_t)(n & 1);
         umma::mbar_wait(&bar_efull[buf], (uint32_t)((n >> 1) & 1));
-        const uint32_t sHh = umma::smem_u32(Hb + (size_t)buf * L.h_bytes), sHl = sHh + L.h_bytes / 2;
+        const uint64_t dHh = dH0 + (uint64_t)((buf * L.h_bytes) >> 4), dHl = dHh + (uint64_t)(L.h_bytes >> 5);
         for (int k = 0; k < nblk; ++k, ++it) {
           const uint32_t vb = it & 1;
           umma::mbar_wait(&bar_vfull[vb], (it >> 1) & 1);
           umma::fence_after_sync();
-          const uint32_t sVh = umma::smem_u32(Vb + (size_t)vb * L.v_bytes), sVl = sVh + L.v_bytes / 2;
+          const uint64_t dVh = dV0 + (uint64_t)((vb * L.v_bytes) >> 4), dVl = dVh + (uint64_t)(L.v_bytes >> 5);
+          const uint32_t td = tmem + k * KH;
           uint32_t acc = fresh ? 0u : 1u;
 #pragma unroll
           for (int ks = 0; ks < kDwTP / 16; ++ks) {
-#pragma unroll
-            for (int term = 0; term < 3; ++term) {
-              const uint64_t da = umma::make_desc((term == 2 ? sVl : sVh) + ks * 2 * RSV, RSV, kCSb);
-              const uint64_t db = umma::make_desc((term == 1 ? sHl : sHh) + ks * 2 * RSH, RSH, kCSb);
-              umma::mma_f16_ss(tmem + k * KH, da, db, idesc, acc);
-              acc = 1;
-            }
+            const uint64_t ka = (uint64_t)(ks * ((2 * RSV) >> 4)), kb = (uint64_t)ks * (uint64_t)((2 * RSH) >> 4);
+            umma::mma_f16_ss(td, dVh + ka, dHh + kb, idesc, acc);          // hi * hi
+            umma::mma_f16_ss(td, dVh + ka, dHl + kb, idesc, 1u);           // hi * lo
+            umma::mma_f16_ss(td, dVl + ka, dHh + kb, idesc, 1u);           // lo * hi
+            acc = 1;
           }
           umma::commit(&bar_vfree[vb]);
         }
@@ -826,23 +921,29 @@ __global__ void __launch_bounds__(kBwThreads, 1) mvn_bwd_dw_kernel(const MvnEncP
       }
     }
   } else {
-    const int person = tid & (kDwTP - 1), sub = tid >> 6;            // sub = row of the unit this thread generates
+    const int person = tid & (kDwTP - 1), sub = tid >> 6;            // rows 2 sub, 2 sub + 1 of every unit
+    const int n_rows = utab[2 * nblk - 1][0] < NB ? utab[2 * nblk - 1][0] - I_first + 1 : NB - I_first;   // block rows of the slab
     uint32_t it = 0, nflush = 0;
     // G and diag L of the thread's rows (8 I + sub for the slab's block rows) of step n -> buffer n & 1, asynchronously
     auto prefetch_g = [&](int64_t n) {
       const uint32_t buf = (uint32_t)(n & 1);
       const int64_t b = (qg + (n / S) * n_qg) * kDwTP + person;
       const int s = (int)(n % S);
-      for (int o = 0; o < kDwMaxRows; ++o) {
-        const int i = 8 * (I_first + o) + sub;
-        float* gd = gsm + ((size_t)(buf * kDwMaxRows + o) * 8 + sub) * kDwTP + person;
-        float* ld = lsm + ((size_t)(buf * kDwMaxRows + o) * 8 + sub) * kDwTP + person;
-        if (b < m.B && i < K) {
-          cp_async4(gd, m.gx + ((int64_t)s * m.B + b) * K + i);
-          cp_async4(ld, m.diagL + b * K + i);
-        } else {
-          *gd = 0.f;
-          *ld = 0.f;
+      const float* gsrc = m.gx + ((int64_t)s * m.B + b) * K;
+      const float* lsrc = m.diagL + b * K;
+      for (int o = 0; o < n_rows; ++o) {
+#pragma unroll
+        for (int rr = 0; rr < 2; ++rr) {
+          const int i = 8 * (I_first + o) + 2 * sub + rr;
+          float* gd = gsm + ((size_t)(buf * kDwMaxRows + o) * 8 + 2 * sub + rr) * kDwTP + person;
+          float* ld = lsm + ((size_t)(buf * kDwMaxRows + o) * 8 + 2 * sub + rr) * kDwTP + person;
+          if (b < m.B && i < K) {
+            cp_async4(gd, gsrc + i);
+            cp_async4(ld, lsrc + i);
+          } else {
+            *gd = 0.f;
+            *ld = 0.f;
+          }
         }
       }
       cp_async_commit();
@@ -854,12 +955,16 @@ __global__ void __launch_bounds__(kBwThreads, 1) mvn_bwd_dw_kernel(const MvnEncP
       const int s = (int)(n % S);
       const int64_t b = tile * kDwTP + person;
       const bool live = b < m.B;
-      float* eps_t = reinterpret_cast<float*>(smem + L.offEps + (size_t)buf * L.eps_bytes);
-      if (!bulk) {                                     // injected noise / K % 4 != 0: rows loaded here, padded pitch
+      uint32_t* eps_t = reinterpret_cast<uint32_t*>(smem + L.offEps + (size_t)buf * L.eps_bytes);
+      if (!bulk) {                                     // injected noise / K % 4 != 0: rows split here, padded pitch
         const float* src = eps_src + (int64_t)s * m.B * K;
         for (int pp = warp * (kDwTP / kBwGenWarps); pp < (warp + 1) * (kDwTP / kBwGenWarps); ++pp) {
           const int64_t bb = tile * kDwTP + pp;
-          for (int k = lane; k < ES; k += 32) eps_t[(size_t)pp * ES + k] = (bb < m.B && k < K) ? src[bb * K + k] : 0.f;
+          for (int mm = lane; mm < ES / 2; mm += 32) {
+            const float z0 = (bb < m.B && 2 * mm < K) ? src[bb * K + 2 * mm] : 0.f;
+            const float z1 = (bb < m.B && 2 * mm + 1 < K) ? src[bb * K + 2 * mm + 1] : 0.f;
+            split_pair(z0, z1, eps_t[(size_t)pp * ES + 2 * mm], eps_t[(size_t)pp * ES + 2 * mm + 1]);
+          }
         }
         gen_bar();
       } else {
@@ -867,42 +972,33 @@ __global__ void __launch_bounds__(kBwThreads, 1) mvn_bwd_dw_kernel(const MvnEncP
       }
       cp_async_wait_all();                             // this step's G / diag L (own entries only: no barrier needed)
       if (n + 1 < n_steps) prefetch_g(n + 1);
-      const float* er = eps_t + (size_t)person * ES;
+      const uint32_t* er = eps_t + (size_t)person * ES;
+      const float* gp = gsm + ((size_t)buf * kDwMaxRows * 8 + 2 * sub) * kDwTP + person;    // + (o * 8 + rr) * kDwTP
+      const float* lp = lsm + ((size_t)buf * kDwMaxRows * 8 + 2 * sub) * kDwTP + person;
+      const float dadd_t = (live && s == 0) ? -m.scale * ginv : 0.f;
+      const uint32_t voff = (uint32_t)(person >> 3) * RSV + (uint32_t)(2 * sub) * kCSb + (uint32_t)(person & 7) * 16u;
       for (int k = 0; k < nblk; ++k, ++it) {
         const uint32_t vb = it & 1;
         umma::mbar_wait(&bar_vfree[vb], ((it >> 1) & 1) ^ 1);
-        unsigned char* Vh = Vb + (size_t)vb * L.v_bytes;
+        unsigned char* Vh = Vb + (size_t)vb * L.v_bytes + voff;
         unsigned char* Vl = Vh + L.v_bytes / 2;
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
           const int I = utab[2 * k + half][0], Jc = utab[2 * k + half][1];
-          float v[8];
-          if (I < NB) {
-            const int o = I - I_first;
-            const float g = ginv * gsm[((size_t)(buf * kDwMaxRows + o) * 8 + sub) * kDwTP + person];
-            const float4 e0 = *reinterpret_cast<const float4*>(er + 8 * Jc);
-            const float4 e1 = *reinterpret_cast<const float4*>(er + 8 * Jc + 4);
-            v[0] = g * e0.x; v[1] = g * e0.y; v[2] = g * e0.z; v[3] = g * e0.w;
-            v[4] = g * e1.x; v[5] = g * e1.y; v[6] = g * e1.z; v[7] = g * e1.w;
-            if (Jc == I) {                             // diagonal block: exp chain rule + entropy term, zero above it
-              const float lii = lsm[((size_t)(buf * kDwMaxRows + o) * 8 + sub) * kDwTP + person];
-              const float dadd = (live && 8 * I + sub < K && s == 0) ? -m.scale * ginv : 0.f;
+          const bool in = I < NB;                      // units beyond the factor (tail of the last chunk): zeros
+          const int o = in ? I - I_first : 0, jo = in ? 8 * Jc : 0;
+          const uint4 w0 = *reinterpret_cast<const uint4*>(er + jo), w1 = *reinterpret_cast<const uint4*>(er + jo + 4);
 #pragma unroll
-              for (int jj = 0; jj < 8; ++jj) v[jj] = jj == sub ? fmaf(v[jj], lii, dadd) : (jj > sub ? 0.f : v[jj]);
-            }
-            if (!live) {                               // rows beyond B: the bulk copy brought whatever lies there
-#pragma unroll
-              for (int jj = 0; jj < 8; ++jj) v[jj] = 0.f;
-            }
-          } else {
-#pragma unroll
-            for (int jj = 0; jj < 8; ++jj) v[jj] = 0.f;
+          for (int rr = 0; rr < 2; ++rr) {
+            // dead persons / rows beyond K hold g = 0 (prefetch_g), so whatever the bulk copy brought there gives 0
+            const float g = in ? ginv * gp[(size_t)(o * 8 + rr) * kDwTP] : 0.f;
+            uint4 hi, lo;
+            gen_octet(g, w0, w1, hi, lo);
+            if (in && Jc == I)                         // diagonal block: exp chain rule + entropy term, zero above it
+              fix_diag(g, lp[(size_t)(o * 8 + rr) * kDwTP], 8 * I + 2 * sub + rr < K ? dadd_t : 0.f, er + jo, 2 * sub + rr, hi, lo);
+            *reinterpret_cast<uint4*>(Vh + (half * 8 + rr) * kCSb) = hi;
+            *reinterpret_cast<uint4*>(Vl + (half * 8 + rr) * kCSb) = lo;
           }
-          uint4 hi, lo;
-          split8(v, hi, lo);
-          const uint32_t off = (uint32_t)(person >> 3) * RSV + (uint32_t)(8 * half + sub) * kCSb + (uint32_t)(person & 7) * 16u;
-          *reinterpret_cast<uint4*>(Vh + off) = hi;
-          *reinterpret_cast<uint4*>(Vl + off) = lo;
         }
         umma::fence_proxy_async();
         warp_arrive(&bar_vfull[vb], lane);
@@ -987,7 +1083,7 @@ size_t mvn_himg_bytes(int64_t B, int H) {
   return ((size_t)((B + kDwTP - 1) / kDwTP) * mv_himg_tile_bytes(H) + 255) & ~size_t(255);
 }
 size_t mvn_eps_bytes(int64_t B, int K, int S) {       // the draws + one tile of zero padding (bulk copies of the last tile)
-  return (((size_t)S * B + kDwTP) * K * 4 + 64 + 255) & ~size_t(255);
+  return (((size_t)S * B + kMvTP) * K * 4 + 64 + 255) & ~size_t(255);
 }
 size_t mvn_dwpart_bytes(int K, int H) {
   int n_pg, n_qg;
@@ -1010,17 +1106,20 @@ int launch_mvn_tail(const MvnEncParams& P, int* loss_rows, cudaStream_t st) {
 int launch_mvn_bwd(const MvnEncParams& P, cudaStream_t st) {
   const int K = P.m.K, H = P.H;
   const int64_t n_tiles = (P.m.B + kMvTP - 1) / kMvTP;
+  // the draws by bulk copy when they lie in our own (padded, pre-split) buffer: rows are whole 16-byte pieces
+  const int bulk = P.eps_split != nullptr ? 1 : 0;
+  if (bulk)       // the last tile's copy runs past the last person's row: finite (zero) padding behind the draws
+    VIPSY_CUDA_CHECK(cudaMemsetAsync(P.eps_split + (size_t)P.m.S * P.m.B * K, 0, (size_t)kMvTP * K * 4 + 64, st));
   if (P.d_hidden) {
-    const DhSmem L = dh_smem(K, H);
+    const DhSmem L = dh_smem(K, H, bulk != 0);
+    VIPSY_REQUIRE(L.total <= 227 * 1024, VIPSY_ERR_UNSUPPORTED, "mvn encoder backward: K=%d H=%d does not fit shared memory", K, H);
     VIPSY_CUDA_CHECK(cudaFuncSetAttribute(mvn_bwd_dh_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
     int64_t g = num_sms();
     if (g > n_tiles) g = n_tiles;
-    mvn_bwd_dh_kernel<<<(int)g, kBwThreads, L.total, st>>>(P);
+    mvn_bwd_dh_kernel<<<(int)g, kBwThreads, L.total, st>>>(P, bulk);
     VIPSY_CUDA_CHECK(cudaGetLastError());
   }
   if (P.d_w22 || P.d_b22) {
-    // noise rows by bulk copy when they lie in our own (padded) buffer and a row is a whole number of 16-byte pieces
-    const int bulk = (P.m.eps == nullptr && (K & 3) == 0) ? 1 : 0;
     const DwSmem L = dw_smem(K, H, bulk != 0);
     VIPSY_REQUIRE(L.total <= 227 * 1024, VIPSY_ERR_UNSUPPORTED, "mvn encoder backward: K=%d H=%d does not fit shared memory", K, H);
     VIPSY_CUDA_CHECK(cudaFuncSetAttribute(mvn_bwd_dw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
@@ -1032,8 +1131,6 @@ int launch_mvn_bwd(const MvnEncParams& P, cudaStream_t st) {
       mvn_himg_kernel<<<(int)g, 256, 0, st>>>(P.hidden, P.m.B, H, mv_kh(H), P.himg);
       VIPSY_CUDA_CHECK(cudaGetLastError());
     }
-    if (bulk)     // the last tile's copy runs past the last person's row: finite (zero) padding behind the draws
-      VIPSY_CUDA_CHECK(cudaMemsetAsync(P.eps_out + (size_t)P.m.S * P.m.B * K, 0, (size_t)kDwTP * K * 4 + 64, st));
     int n_pg, n_qg;
     dw_grid(K, H, &n_pg, &n_qg);
     if (n_qg > n_tiles64) n_qg = (int)n_tiles64;
@@ -1153,7 +1250,9 @@ int vipsy_irt_mvn_encoder_elbo_grad(const VipsyMvnEncoderIrtArgs* a, void* strea
   P.wimg = ws + L.wimg;
   P.wimg_b = ws + L.wimgb;
   P.himg = ws + L.himg;
-  P.eps_out = r.eps ? nullptr : reinterpret_cast<float*>(ws + L.eps);
+  // our own draws: pre-split fp16 pair words when a row is a whole number of 16-byte pieces (bulk copies), else fp32
+  P.eps_out = (r.eps || (r.n_dims & 3) == 0) ? nullptr : reinterpret_cast<float*>(ws + L.eps);
+  P.eps_split = (r.eps || (r.n_dims & 3) != 0) ? nullptr : reinterpret_cast<uint32_t*>(ws + L.eps);
   P.dw_part = reinterpret_cast<float*>(ws + L.dwpart);
   P.gmax = reinterpret_cast<float*>(ws + L.gmax);
   P.logdet_out = nullptr;
