@@ -436,6 +436,7 @@ int vipsy_norm_encoder_backward(const VipsyNormEncoderArgs* args, void* stream);
  *   variant 0: out[128 x c2] = t1[r1 x c1] . t2[r2 x c2]        (c1 == r2)
  *   variant 1: out[128 x r2] = t1[r1 x c1] . t2[r2 x c2]^T      (c1 == c2)
  *   variant 2: out[128 x c2] = t1[r1 x c1]^T . t2[r2 x c2]      (r1 == r2; rows >= c1 of out undefined)
+ *   variant 3 / 4: as 0 / 1 with the A operand in tensor memory (tcgen05.st, then tcgen05.mma [d], [a], b-desc)
  * n_split = 1 (hi*hi only) .. 3 (+ hi*lo + lo*hi).  Used by tests/test_umma_selftest.py.
  * ---------------------------------------------------------------------- */
 int vipsy_selftest_umma(const float* t1, int32_t r1, int32_t c1, const float* t2, int32_t r2, int32_t c2,

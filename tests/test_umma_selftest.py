@@ -11,7 +11,7 @@ pytestmark = pytest.mark.gpu
 
 def run(variant, t1, t2, swap=0, n_split=3):
     L = N.lib()
-    n = t2.shape[0] if variant == 1 else t2.shape[1]
+    n = t2.shape[0] if variant in (1, 4) else t2.shape[1]
     out = torch.full((128, n), float("nan"), device="cuda")
     N.check(L.vipsy_selftest_umma(t1.data_ptr(), t1.shape[0], t1.shape[1], t2.data_ptr(), t2.shape[0], t2.shape[1],
                                   out.data_ptr(), variant, swap, n_split, None))
@@ -19,15 +19,16 @@ def run(variant, t1, t2, swap=0, n_split=3):
     return out
 
 
-CASES = {0: ((128, 112), (112, 128)), 1: ((128, 128), (112, 128)), 2: ((128, 112), (128, 128))}
+CASES = {0: ((128, 112), (112, 128)), 1: ((128, 128), (112, 128)), 2: ((128, 112), (128, 128)),
+         3: ((128, 112), (112, 64)), 4: ((128, 80), (128, 80))}       # 3, 4: A in tensor memory
 
 
 def expect(variant, t1, t2):
     a, b = t1.double(), t2.double()
-    return a @ b if variant == 0 else (a @ b.T if variant == 1 else a.T @ b)
+    return a @ b if variant in (0, 3) else (a @ b.T if variant in (1, 4) else a.T @ b)
 
 
-@pytest.mark.parametrize("variant", [0, 1, 2])
+@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4])
 def test_tile_product_matches_float64(variant):
     g = torch.Generator(device="cuda").manual_seed(variant)
     s1, s2 = CASES[variant]

@@ -461,18 +461,46 @@ __global__ void __launch_bounds__(kTailThreads) mvn_tail_kernel(const MirtParams
   const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (int64_t)gridDim.x * blockDim.x;
   if (p.d_mu) {
     float gm = 0.f;
-    for (int64_t e = tid; e < BK; e += nth) {
-      float t = 0.f;
-      for (int s = 0; s < S; ++s) {
-        const int64_t at = (int64_t)s * BK + e;
-        float g = -p.x[at];
-        for (int part = 0; part < p.n_parts; ++part) g += p.gx[(int64_t)part * R * K + at];
-        g *= kf;
-        p.gx[at] = g;
-        gm = fmaxf(gm, fabsf(g));
-        t += g;
+    if ((BK & 3) == 0 && (reinterpret_cast<uintptr_t>(p.d_mu) & 15) == 0) {      // 16-byte pieces, every load of a piece in flight before the first use
+      const int np = p.n_parts;
+      for (int64_t e4 = tid; e4 < (BK >> 2); e4 += nth) {
+        float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int s = 0; s < S; ++s) {
+          const int64_t at = (int64_t)s * BK + 4 * e4;
+          const float4 xv = __ldcs(reinterpret_cast<const float4*>(p.x + at));
+          float4 v[4];
+#pragma unroll
+          for (int part = 0; part < 4; ++part)
+            v[part] = part < np ? __ldcs(reinterpret_cast<const float4*>(p.gx + (int64_t)part * R * K + at))
+                                : make_float4(0.f, 0.f, 0.f, 0.f);
+          float4 g = make_float4(v[0].x - xv.x, v[0].y - xv.y, v[0].z - xv.z, v[0].w - xv.w);
+#pragma unroll
+          for (int part = 1; part < 4; ++part) { g.x += v[part].x; g.y += v[part].y; g.z += v[part].z; g.w += v[part].w; }
+          for (int part = 4; part < np; ++part) {
+            const float4 w = __ldcs(reinterpret_cast<const float4*>(p.gx + (int64_t)part * R * K + at));
+            g.x += w.x; g.y += w.y; g.z += w.z; g.w += w.w;
+          }
+          g.x *= kf; g.y *= kf; g.z *= kf; g.w *= kf;
+          *reinterpret_cast<float4*>(p.gx + at) = g;
+          gm = fmaxf(fmaxf(gm, fmaxf(fabsf(g.x), fabsf(g.y))), fmaxf(fabsf(g.z), fabsf(g.w)));
+          t.x += g.x; t.y += g.y; t.z += g.z; t.w += g.w;
+        }
+        __stcs(reinterpret_cast<float4*>(p.d_mu + 4 * e4), t);
       }
-      p.d_mu[e] = t;
+    } else {
+      for (int64_t e = tid; e < BK; e += nth) {
+        float t = 0.f;
+        for (int s = 0; s < S; ++s) {
+          const int64_t at = (int64_t)s * BK + e;
+          float g = -p.x[at];
+          for (int part = 0; part < p.n_parts; ++part) g += p.gx[(int64_t)part * R * K + at];
+          g *= kf;
+          p.gx[at] = g;
+          gm = fmaxf(gm, fabsf(g));
+          t += g;
+        }
+        p.d_mu[e] = t;
+      }
     }
     gm = warp_max(gm);                                  // a maximum: independent of the order, hence deterministic
     if ((threadIdx.x & 31) == 0 && gm > 0.f) atomicMax(reinterpret_cast<int*>(gmax), __float_as_int(gm));

@@ -3,6 +3,8 @@
 //   variant 0  D[m][n] = sum_k T1[m][k] T2[k][n]   A K-major,  B MN-major   (logits = x a)
 //   variant 1  D[m][n] = sum_k T1[m][k] T2[n][k]   A K-major,  B K-major    (d x = G a^T)
 //   variant 2  D[m][n] = sum_k T1[k][m] T2[k][n]   A MN-major, B MN-major   (d a = x^T G)
+//   variant 3  as 0, variant 4 as 1, with A in tensor memory (tcgen05.st by the thread that owns the row): the
+//              operand path of the amortised-guide kernels (enc_mvn.cu)
 // T1 is R1 x C1, T2 is R2 x C2 (fp32, row-major, dimensions multiples of 8 / 16 as the MMA needs).
 #include "common.cuh"
 #include "umma.cuh"
@@ -43,7 +45,7 @@ __global__ void __launch_bounds__(kStThreads) umma_selftest_kernel(const float* 
     *reinterpret_cast<__half*>(t2h + o) = hi;
     *reinterpret_cast<__half*>(t2l + o) = lo;
   }
-  if (warp == 0) umma::tmem_alloc(&tmem_base_sm, 128);
+  if (warp == 0) umma::tmem_alloc(&tmem_base_sm, 256);
   if (tid == 0) {
     umma::mbar_init(&bar, 1);
     umma::fence_mbar_init();
@@ -53,11 +55,34 @@ __global__ void __launch_bounds__(kStThreads) umma_selftest_kernel(const float* 
   __syncthreads();
   umma::fence_after_sync();
   const uint32_t tmem = tmem_base_sm;
+  const bool a_tmem = variant >= 3;
+  if (a_tmem) variant -= 3;
 
   int N, ksteps;
   if (variant == 0) { N = C2; ksteps = C1 / 16; }
   else if (variant == 1) { N = R2; ksteps = C1 / 16; }
   else { N = C2; ksteps = R1 / 16; }
+
+  if (a_tmem) {                                          // row tid of T1 -> lane tid: hi words at column 128, lo at 192
+    const uint32_t tl = tmem + ((uint32_t)(warp * 32) << 16);
+    for (int c0 = 0; c0 < C1; c0 += 16) {
+      uint32_t h[8], l[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        __half h0, l0, h1, l1;
+        umma::split_f16(tid < R1 ? T1[(size_t)tid * C1 + c0 + 2 * q] : 0.f, h0, l0);
+        umma::split_f16(tid < R1 ? T1[(size_t)tid * C1 + c0 + 2 * q + 1] : 0.f, h1, l1);
+        h[q] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
+        l[q] = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
+      }
+      umma::tmem_st8(tl + 128 + c0 / 2, h);
+      umma::tmem_st8(tl + 192 + c0 / 2, l);
+    }
+    umma::tmem_st_wait();
+    umma::fence_before_sync();
+    __syncthreads();
+    umma::fence_after_sync();
+  }
 
   if (tid == 0) {
     const uint32_t a_major = variant == 2 ? umma::kMajorMN : umma::kMajorK;
@@ -81,7 +106,8 @@ __global__ void __launch_bounds__(kStThreads) umma_selftest_kernel(const float* 
           const uint32_t lbo = swap ? CS : RS2, sbo = swap ? RS2 : CS;
           db = umma::make_desc(umma::smem_u32(tb) + ks * 2 * RS2, lbo, sbo);
         }
-        umma::mma_f16_ss(tmem, da, db, idesc, acc);
+        if (a_tmem) umma::mma_f16_ts(tmem, tmem + (term == 2 ? 192 : 128) + ks * 8, db, idesc, acc);
+        else umma::mma_f16_ss(tmem, da, db, idesc, acc);
         acc = 1;
       }
     }
@@ -98,14 +124,14 @@ __global__ void __launch_bounds__(kStThreads) umma_selftest_kernel(const float* 
   }
   umma::fence_before_sync();
   __syncthreads();
-  if (warp == 0) umma::tmem_dealloc(tmem, 128);
+  if (warp == 0) umma::tmem_dealloc(tmem, 256);
 }
 
 int umma_selftest_launch(const float* t1, int R1, int C1, const float* t2, int R2, int C2, float* out, int variant,
                          int swap, int n_split, cudaStream_t st) {
   VIPSY_REQUIRE(t1 && t2 && out, VIPSY_ERR_ARG, "vipsy_selftest_umma: null pointer");
-  VIPSY_REQUIRE(variant >= 0 && variant <= 2 && n_split >= 1 && n_split <= 3, VIPSY_ERR_ARG,
-                "vipsy_selftest_umma: variant in 0..2, n_split in 1..3");
+  VIPSY_REQUIRE(variant >= 0 && variant <= 4 && n_split >= 1 && n_split <= 3, VIPSY_ERR_ARG,
+                "vipsy_selftest_umma: variant in 0..4, n_split in 1..3");
   VIPSY_REQUIRE(R1 % 8 == 0 && C1 % 8 == 0 && R2 % 8 == 0 && C2 % 8 == 0 && R1 <= 128 && C1 <= 128 && R2 <= 128 &&
                     C2 <= 128,
                 VIPSY_ERR_ARG, "vipsy_selftest_umma: tile dimensions must be multiples of 8, at most 128");
