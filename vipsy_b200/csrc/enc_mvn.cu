@@ -25,7 +25,8 @@ namespace {
 constexpr uint32_t kCSb = 128;                 // byte stride between core matrices along the contiguous dimension
 constexpr int kFwEpiWarps = 4;                 // warps 0-3: epilogue (TMEM lane quadrant = warp)
 constexpr int kFwThreads = (kFwEpiWarps + 2) * 32;   // + warp 4: bulk-copy producer, warp 5: MMA issuer
-constexpr int kFwTmemBufs = 4;                 // 4 x 128 accumulator columns
+constexpr int kFwTmemBufs = 3;                 // 3 x 128 accumulator columns; columns 384.. : the [hidden | 1] operand
+constexpr uint32_t kFwACol = 384;              // A operand in tensor memory: KH / 2 words of fp16 hi pairs, then KH / 2 of lo
 
 // One arrival per warp: every lane has finished (and fenced) its part, lane 0 signals.  512 separate arrivals on one
 // mbarrier serialise on the shared-memory atomic unit (measured: ~2000 cycles per phase).
@@ -165,25 +166,21 @@ __global__ void mvn_prep_kernel(const float* __restrict__ w22, const float* __re
 
 // ------------------------------------------------------------------------------------------------ forward
 struct FwSmem {
-  uint32_t offW, offHh, offHl, offEps, total;
-  uint32_t chunk_bytes, tile_h_bytes;
+  uint32_t offW, offEps, total;
+  uint32_t chunk_bytes;
   int nst, ES;
 };
 __host__ __device__ inline FwSmem fw_smem(int K, int H) {
   FwSmem s;
-  const int KH = mv_kh(H);
   s.chunk_bytes = (uint32_t)mv_chunk_bytes(H);
-  s.tile_h_bytes = (uint32_t)kMvTP * KH * 2;
   s.ES = (K + 7) / 8 * 8 + 4;
-  const uint32_t fixed = 2 * s.tile_h_bytes + (uint32_t)kMvTP * s.ES * 4;
+  const uint32_t fixed = (uint32_t)kMvTP * s.ES * 4;
   const uint32_t cap = 227 * 1024 - 1024;
   int nst = (int)((cap - fixed) / s.chunk_bytes);
   if (nst > 4) nst = 4;
   s.nst = nst;
   uint32_t o = 0;
   s.offW = o; o += (uint32_t)(nst > 0 ? nst : 0) * s.chunk_bytes;
-  s.offHh = o; o += s.tile_h_bytes;
-  s.offHl = o; o += s.tile_h_bytes;
   s.offEps = o; o += (uint32_t)kMvTP * s.ES * 4;
   s.total = o;
   return s;
@@ -234,8 +231,6 @@ __global__ void __launch_bounds__(kFwThreads, 1) mvn_fwd_kernel(const MvnEncPara
   const int n_chunks = mv_chunks(K), NB = mv_nb(K);
   const uint32_t RS = (uint32_t)(KH / 8) * kCSb;
   unsigned char* Wst = smem + L.offW;
-  unsigned char* Hh = smem + L.offHh;
-  unsigned char* Hl = smem + L.offHl;
   float* eps_s = reinterpret_cast<float*>(smem + L.offEps);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int64_t n_tiles = (m.B + kMvTP - 1) / kMvTP;
@@ -252,50 +247,53 @@ __global__ void __launch_bounds__(kFwThreads, 1) mvn_fwd_kernel(const MvnEncPara
   umma::fence_after_sync();
   const uint32_t tmem = tmem_base_sm;
 
+  // Producer and MMA warp: whole-warp loops, only the issuing instructions under elect_one() (see umma::elect_one).
+  // The [hidden | 1] tile is the A operand in TENSOR memory (written by the epilogue threads, lane = person): an
+  // SS-mode 128 x 128 x 16 MMA needs 8 KB of shared-memory reads per 64 cycles -- the whole port.
   if (warp == kFwEpiWarps) {
     // =========================== bulk-copy producer: the operand image, chunk by chunk ========================
-    if (lane == 0) {
-      uint32_t it = 0;
-      for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x)
-        for (int s = 0; s < S; ++s)
-          for (int c = 0; c < n_chunks; ++c, ++it) {
-            const uint32_t st = it % NST, round = it / NST;
-            umma::mbar_wait(&bar_wempty[st], (round & 1) ^ 1);
+    uint32_t it = 0;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x)
+      for (int s = 0; s < S; ++s)
+        for (int c = 0; c < n_chunks; ++c, ++it) {
+          const uint32_t st = it % NST, round = it / NST;
+          umma::mbar_wait(&bar_wempty[st], (round & 1) ^ 1);
+          if (umma::elect_one())
             umma::bulk_load(Wst + (size_t)st * L.chunk_bytes, P.wimg + (size_t)c * L.chunk_bytes, L.chunk_bytes,
                             &bar_wfull[st]);
-          }
-    }
+          __syncwarp();
+        }
   } else if (warp == kFwEpiWarps + 1) {
     // =========================== MMA issuer ====================================================================
-    if (lane == 0) {
-      const uint32_t idesc = umma::make_idesc_f16(kMvTP, kMvCN, umma::kMajorK, umma::kMajorK);
-      const uint32_t sHh = umma::smem_u32(Hh), sHl = umma::smem_u32(Hl);
-      uint32_t it = 0, ntile = 0;
-      for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++ntile) {
-        umma::mbar_wait(&bar_hfull, ntile & 1);
-        umma::fence_after_sync();
-        for (int s = 0; s < S; ++s)
-          for (int c = 0; c < n_chunks; ++c, ++it) {
-            const uint32_t st = it % NST, round = it / NST;
-            const uint32_t buf = it % kFwTmemBufs, tround = it / kFwTmemBufs;
-            umma::mbar_wait(&bar_wfull[st], round & 1);
-            umma::mbar_wait(&bar_tempty[buf], (tround & 1) ^ 1);
-            umma::fence_after_sync();
+    const uint32_t idesc = umma::make_idesc_f16(kMvTP, kMvCN, umma::kMajorK, umma::kMajorK);
+    const uint32_t aH = tmem + kFwACol, aL = aH + (uint32_t)(KH / 2);
+    uint32_t it = 0, ntile = 0;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++ntile) {
+      umma::mbar_wait(&bar_hfull, ntile & 1);
+      umma::fence_after_sync();
+      for (int s = 0; s < S; ++s)
+        for (int c = 0; c < n_chunks; ++c, ++it) {
+          const uint32_t st = it % NST, round = it / NST;
+          const uint32_t buf = it % kFwTmemBufs, tround = it / kFwTmemBufs;
+          umma::mbar_wait(&bar_wfull[st], round & 1);
+          umma::mbar_wait(&bar_tempty[buf], (tround & 1) ^ 1);
+          umma::fence_after_sync();
+          if (umma::elect_one()) {
             const uint32_t sWh = umma::smem_u32(Wst + (size_t)st * L.chunk_bytes), sWl = sWh + L.chunk_bytes / 2;
             uint32_t acc = 0;
             for (int ks = 0; ks < KH / 16; ++ks) {
 #pragma unroll
               for (int term = 0; term < 3; ++term) {            // hi*hi, hi*lo, lo*hi
-                const uint64_t da = umma::make_desc((term == 2 ? sHl : sHh) + ks * 2 * kCSb, kCSb, RS);
                 const uint64_t db = umma::make_desc((term == 1 ? sWl : sWh) + ks * 2 * kCSb, kCSb, RS);
-                umma::mma_f16_ss(tmem + buf * kMvCN, da, db, idesc, acc);
+                umma::mma_f16_ts(tmem + buf * kMvCN, (term == 2 ? aL : aH) + 8 * ks, db, idesc, acc);
                 acc = 1;
               }
             }
             umma::commit(&bar_wempty[st]);
             umma::commit(&bar_tfull[buf]);
           }
-      }
+          __syncwarp();
+        }
     }
   } else {
     // =========================== epilogue: thread = person = TMEM lane =========================================
@@ -308,30 +306,38 @@ __global__ void __launch_bounds__(kFwThreads, 1) mvn_fwd_kernel(const MvnEncPara
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
       const int64_t b = tile * kMvTP + t;
       const bool live = b < m.B;
-      // ---- [hidden | 1 | 0] row of this person -> fp16 hi / lo operand tiles (K-major) -------------------------
+      // ---- [hidden | 1 | 0] row of this person -> fp16 hi / lo words of the A operand in tensor memory ------------
+      // (every MMA of the previous tile has completed: this thread has consumed its last accumulator)
       {
         const float* hr = P.hidden + (live ? b : 0) * H;
         const bool vec = (H & 3) == 0;
-        for (int o = 0; o < KH / 8; ++o) {
-          float v[8];
-          if (vec && live && o * 8 + 8 <= H) {
-            const float4 a0 = *reinterpret_cast<const float4*>(hr + o * 8);
-            const float4 a1 = *reinterpret_cast<const float4*>(hr + o * 8 + 4);
-            v[0] = a0.x; v[1] = a0.y; v[2] = a0.z; v[3] = a0.w; v[4] = a1.x; v[5] = a1.y; v[6] = a1.z; v[7] = a1.w;
-          } else {
+        for (int o2 = 0; o2 < KH / 16; ++o2) {           // a k-step: 16 elements = 8 words
+          uint32_t h8[8], l8[8];
 #pragma unroll
-            for (int q = 0; q < 8; ++q) {
-              const int k = o * 8 + q;
-              v[q] = !live ? 0.f : (k < H ? hr[k] : (k == H ? 1.f : 0.f));
+          for (int half = 0; half < 2; ++half) {
+            const int o = 2 * o2 + half;
+            float v[8];
+            if (vec && live && o * 8 + 8 <= H) {
+              const float4 a0 = *reinterpret_cast<const float4*>(hr + o * 8);
+              const float4 a1 = *reinterpret_cast<const float4*>(hr + o * 8 + 4);
+              v[0] = a0.x; v[1] = a0.y; v[2] = a0.z; v[3] = a0.w; v[4] = a1.x; v[5] = a1.y; v[6] = a1.z; v[7] = a1.w;
+            } else {
+#pragma unroll
+              for (int q = 0; q < 8; ++q) {
+                const int k = o * 8 + q;
+                v[q] = !live ? 0.f : (k < H ? hr[k] : (k == H ? 1.f : 0.f));
+              }
             }
+            uint4 hi, lo;
+            split8(v, hi, lo);
+            h8[4 * half] = hi.x; h8[4 * half + 1] = hi.y; h8[4 * half + 2] = hi.z; h8[4 * half + 3] = hi.w;
+            l8[4 * half] = lo.x; l8[4 * half + 1] = lo.y; l8[4 * half + 2] = lo.z; l8[4 * half + 3] = lo.w;
           }
-          uint4 hi, lo;
-          split8(v, hi, lo);
-          const uint32_t off = (uint32_t)(t >> 3) * RS + (uint32_t)o * kCSb + (uint32_t)(t & 7) * 16u;
-          *reinterpret_cast<uint4*>(Hh + off) = hi;
-          *reinterpret_cast<uint4*>(Hl + off) = lo;
+          umma::tmem_st8(tlane + kFwACol + 8 * o2, h8);
+          umma::tmem_st8(tlane + kFwACol + (uint32_t)(KH / 2) + 8 * o2, l8);
         }
-        umma::fence_proxy_async();
+        umma::tmem_st_wait();
+        umma::fence_before_sync();
         warp_arrive(&bar_hfull, lane);
       }
       float logdet = 0.f, auxp = 0.f;
@@ -552,24 +558,23 @@ __device__ __forceinline__ void load_g(const MirtParams& m, int s, int64_t b, bo
 
 // ---- d hidden[person][h] = (1 / 64) sum_p V[person][p] (64 W22)[p][h]: CTAs own person tiles, every unit of V ------
 constexpr int kDhMaxStages = 8;
+constexpr int kDhAStages = 4;                          // V units in tensor memory: 4 x (32 hi + 32 lo) columns
 struct DhSmem {
-  uint32_t offEps, offV, offW, total, v_bytes, w_bytes, eps_bytes;
+  uint32_t offEps, offW, total, w_bytes, eps_bytes;
   int ES, nst, neb;
 };
 __host__ __device__ inline DhSmem dh_smem(int K, int H, bool bulk) {
   DhSmem s;
   s.ES = bulk ? K : (K + 7) / 8 * 8 + 4;               // words per row of the split draws
   s.eps_bytes = ((uint32_t)kMvTP * s.ES * 4 + 64 + 127) & ~127u;
-  s.v_bytes = 2u * kMvTP * 64 * 2;                      // hi + lo, 128 persons x 64 columns
   s.w_bytes = 2u * 64 * (uint32_t)mv_nh(H) * 2;         // hi + lo, 64 columns x NH
   // A bulk copy of a unit takes ~1.2 us from L2: the stream of units needs depth, the draws (one copy per tile)
   // do not -- so the draws get one buffer and the units every stage that fits (measured: 3 -> 6 stages).
   s.neb = 1;
-  int nst = (int)((226u * 1024u - s.eps_bytes - 2 * s.v_bytes) / s.w_bytes);
+  int nst = (int)((226u * 1024u - s.eps_bytes) / s.w_bytes);
   s.nst = nst > kDhMaxStages ? kDhMaxStages : nst;
   uint32_t o = 0;
   s.offEps = o; o += (uint32_t)s.neb * s.eps_bytes;
-  s.offV = o; o += 2 * s.v_bytes;
   s.offW = o; o += (uint32_t)s.nst * s.w_bytes;
   s.total = o;
   return s;
@@ -577,20 +582,24 @@ __host__ __device__ inline DhSmem dh_smem(int K, int H, bool bulk) {
 
 __global__ void __launch_bounds__(kBwThreads, 1) mvn_bwd_dh_kernel(const MvnEncParams P, const int bulk) {
   extern __shared__ __align__(128) unsigned char smem[];
-  __shared__ uint64_t bar_vfull[2], bar_vfree[2], bar_wfull[kDhMaxStages], bar_wempty[kDhMaxStages], bar_efull[2], bar_efree[2], bar_dfull, bar_dfree;
+  __shared__ uint64_t bar_vfull[kDhAStages], bar_vfree[kDhAStages], bar_wfull[kDhMaxStages], bar_wempty[kDhMaxStages], bar_efull[2], bar_efree[2], bar_dfull, bar_dfree;
   __shared__ uint32_t tmem_base_sm;
   const MirtParams& m = P.m;
   const int K = m.K, S = m.S, H = P.H, NH = mv_nh(H), NB = mv_nb(K), NU = NB * (NB + 1) / 2;
   const DhSmem L = dh_smem(K, H, bulk != 0);
   const int ES = L.ES, NEB = L.neb;
   const uint32_t NST = (uint32_t)L.nst;
-  unsigned char* Vb = smem + L.offV;
   unsigned char* Wb = smem + L.offW;
-  const uint32_t RSV = (64 / 8) * kCSb, RSW = (uint32_t)(NH / 8) * kCSb;
+  const uint32_t RSW = (uint32_t)(NH / 8) * kCSb;
+  // V = g eps^T is the A operand and lives in TENSOR memory (lane = person, a unit of 64 columns = 32 + 32 words of
+  // fp16 hi / lo pairs, written by the generating threads with tcgen05.st): it never crosses shared memory, whose
+  // read port an SS-mode 128 x 64 x 16 MMA would saturate (6 KB per 32 cycles).  Columns [0, 256): accumulators,
+  // [256, 512): kDhAStages units of V.
   // The tensor core adds into its fp32 accumulator with truncation: a long chain of accumulating MMAs drifts by
   // ~2^-24 of the running sum per instruction (measured: 2e-5 relative over the 1092 MMAs of a K = 100 tile).
   // The units therefore go round-robin into NACC independent accumulators, summed (round-to-nearest) at the drain.
-  const uint32_t NACC = 512u / (uint32_t)NH < 8u ? 512u / (uint32_t)NH : 8u;
+  const uint32_t NACC = 256u / (uint32_t)NH < 8u ? 256u / (uint32_t)NH : 8u;
+  constexpr uint32_t kACol = 256;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int64_t n_tiles = (m.B + kMvTP - 1) / kMvTP;
   const int64_t my_tiles = blockIdx.x < n_tiles ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
@@ -602,9 +611,11 @@ __global__ void __launch_bounds__(kBwThreads, 1) mvn_bwd_dh_kernel(const MvnEncP
   const float ginv = ldexpf(1.f, 4 - gexp), gfix = ldexpf(1.f, gexp - 4);
 
   if (tid == 0) {
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < kDhAStages; ++i) {
       umma::mbar_init(&bar_vfull[i], kBwGenWarps);
       umma::mbar_init(&bar_vfree[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
       umma::mbar_init(&bar_efull[i], 1);
       umma::mbar_init(&bar_efree[i], kBwGenWarps);
     }
@@ -624,14 +635,19 @@ __global__ void __launch_bounds__(kBwThreads, 1) mvn_bwd_dh_kernel(const MvnEncP
   umma::fence_after_sync();
   const uint32_t tmem = tmem_base_sm;
 
+  // The producer and the MMA warp walk their loops as whole warps (waits by every lane) and put only the issuing
+  // instructions under elect_one(): see umma::elect_one -- behind `if (lane == 0)` one MMA costs ~115 cycles to
+  // issue, more than three times what a 128 x 64 x 16 MMA takes to execute.
   if (warp == kBwGenWarps) {
-    if (lane == 0) {                                   // bulk-copy producer: the units of the backward image, the draws
+    {                                                  // bulk-copy producer: the units of the backward image, the draws
       auto issue_eps = [&](int64_t e) {                // split draws of step e -> buffer e % NEB
         const uint32_t eb = (uint32_t)(e % NEB);
         const int64_t tile = blockIdx.x + (e / S) * gridDim.x;
         umma::mbar_wait(&bar_efree[eb], (uint32_t)((((e / NEB) & 1)) ^ 1));
-        umma::bulk_load(smem + L.offEps + (size_t)eb * L.eps_bytes,
-                        P.eps_split + ((int64_t)(e % S) * m.B + tile * kMvTP) * K, (uint32_t)kMvTP * K * 4, &bar_efull[eb]);
+        if (umma::elect_one())
+          umma::bulk_load(smem + L.offEps + (size_t)eb * L.eps_bytes,
+                          P.eps_split + ((int64_t)(e % S) * m.B + tile * kMvTP) * K, (uint32_t)kMvTP * K * 4, &bar_efull[eb]);
+        __syncwarp();
       };
       uint32_t it = 0;
       if (bulk && n_steps > 0) issue_eps(0);
@@ -640,15 +656,16 @@ __global__ void __launch_bounds__(kBwThreads, 1) mvn_bwd_dh_kernel(const MvnEncP
         for (int u = 0; u < NU; ++u, ++it) {
           const uint32_t st = it % NST, round = it / NST;
           umma::mbar_wait(&bar_wempty[st], (round & 1) ^ 1);
-          umma::bulk_load(Wb + (size_t)st * L.w_bytes, P.wimg_b + (size_t)u * L.w_bytes, L.w_bytes, &bar_wfull[st]);
+          if (umma::elect_one())
+            umma::bulk_load(Wb + (size_t)st * L.w_bytes, P.wimg_b + (size_t)u * L.w_bytes, L.w_bytes, &bar_wfull[st]);
+          __syncwarp();
         }
         if (bulk && NEB == 1 && n + 1 < n_steps) issue_eps(n + 1);
       }
     }
   } else if (warp == kBwGenWarps + 1) {
-    if (lane == 0) {                                   // MMA issuer
+    {                                                  // MMA issuer
       const uint32_t idesc = umma::make_idesc_f16(kMvTP, NH, umma::kMajorK, umma::kMajorMN);
-      const uint64_t dV0 = umma::make_desc(umma::smem_u32(Vb), kCSb, RSV);     // V: K-major A
       const uint64_t dW0 = umma::make_desc(umma::smem_u32(Wb), RSW, kCSb);     // 64 W22 unit: MN-major B
       uint32_t it = 0, ntile = 0;
       for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++ntile) {
@@ -657,33 +674,38 @@ __global__ void __launch_bounds__(kBwThreads, 1) mvn_bwd_dh_kernel(const MvnEncP
         uint32_t nu = 0;
         for (int s = 0; s < S; ++s)
           for (int u = 0; u < NU; ++u, ++it, ++nu) {
-            const uint32_t vb = it & 1, st = it % NST;
+            const uint32_t vb = it % kDhAStages, st = it % NST;
             const uint32_t ai = nu % NACC;               // round-robin over the accumulators (see NACC)
-            uint32_t acc = nu < NACC ? 0u : 1u;
-            umma::mbar_wait(&bar_vfull[vb], (it >> 1) & 1);
+            umma::mbar_wait(&bar_vfull[vb], (it / kDhAStages) & 1);
             umma::mbar_wait(&bar_wfull[st], (it / NST) & 1);
             umma::fence_after_sync();
-            // descriptors: one base per tile, the k-step only moves the 14-bit start-address field (units of 16 bytes)
-            const uint64_t dVh = dV0 + (uint64_t)((vb * L.v_bytes) >> 4), dVl = dVh + (uint64_t)(L.v_bytes >> 5);
-            const uint64_t dWh = dW0 + (uint64_t)((st * L.w_bytes) >> 4), dWl = dWh + (uint64_t)(L.w_bytes >> 5);
-            const uint32_t td = tmem + ai * NH;
+            if (umma::elect_one()) {
+              uint32_t acc = nu < NACC ? 0u : 1u;
+              // B descriptors: one base per tile, the k-step only moves the 14-bit start-address field (units of 16 bytes)
+              const uint64_t dWh = dW0 + (uint64_t)((st * L.w_bytes) >> 4), dWl = dWh + (uint64_t)(L.w_bytes >> 5);
+              const uint32_t aH = tmem + kACol + vb * 64, aL = aH + 32;      // a k-step = 16 columns of V = 8 words
+              const uint32_t td = tmem + ai * NH;
 #pragma unroll
-            for (int ks = 0; ks < 4; ++ks) {
-              const uint64_t ka = (uint64_t)(ks * ((2 * kCSb) >> 4)), kb = (uint64_t)ks * (uint64_t)((2 * RSW) >> 4);
-              umma::mma_f16_ss(td, dVh + ka, dWh + kb, idesc, acc);        // hi * hi
-              umma::mma_f16_ss(td, dVh + ka, dWl + kb, idesc, 1u);         // hi * lo
-              umma::mma_f16_ss(td, dVl + ka, dWh + kb, idesc, 1u);         // lo * hi
-              acc = 1;
+              for (int ks = 0; ks < 4; ++ks) {
+                const uint64_t kb = (uint64_t)ks * (uint64_t)((2 * RSW) >> 4);
+                umma::mma_f16_ts(td, aH + 8 * ks, dWh + kb, idesc, acc);       // hi * hi
+                umma::mma_f16_ts(td, aH + 8 * ks, dWl + kb, idesc, 1u);        // hi * lo
+                umma::mma_f16_ts(td, aL + 8 * ks, dWh + kb, idesc, 1u);        // lo * hi
+                acc = 1;
+              }
+              umma::commit(&bar_vfree[vb]);
+              umma::commit(&bar_wempty[st]);
             }
-            umma::commit(&bar_vfree[vb]);
-            umma::commit(&bar_wempty[st]);
+            __syncwarp();
           }
-        umma::commit(&bar_dfull);
+        if (umma::elect_one()) umma::commit(&bar_dfull);
+        __syncwarp();
       }
     }
   } else {
     const int t = tid & 127, sub = tid >> 7;           // thread = (person, rows 4 sub .. 4 sub + 3 of every unit)
-    const uint32_t voff = (uint32_t)(t >> 3) * RSV + (uint32_t)(4 * sub) * kCSb + (uint32_t)(t & 7) * 16u;
+    // TMEM lane = person (warp w reaches lanes 32 (w % 4) ..: t >> 5 == warp % 4); row r of a unit = words 4 r .. 4 r + 3
+    const uint32_t ta = tmem + ((uint32_t)((warp & 3) * 32) << 16) + kACol + 16u * (uint32_t)sub;
     uint32_t it = 0;
     for (int64_t n = 0; n < n_steps; ++n) {
       const uint32_t eb = (uint32_t)(n % NEB);
@@ -713,20 +735,23 @@ __global__ void __launch_bounds__(kBwThreads, 1) mvn_bwd_dh_kernel(const MvnEncP
       load_g<4>(m, s, b, live, 0, sub, ginv, gI, lI, dadd);
       load_g<4>(m, s, b, live && NB > 1, 1, sub, ginv, gN, lN, dN);
       for (int u = 0; u < NU; ++u, ++it) {
-        const uint32_t vb = it & 1;
-        umma::mbar_wait(&bar_vfree[vb], ((it >> 1) & 1) ^ 1);
-        unsigned char* Vh = Vb + (size_t)vb * L.v_bytes + voff;
-        unsigned char* Vl = Vh + L.v_bytes / 2;
+        const uint32_t vb = it % kDhAStages;
         const uint4 w0 = *reinterpret_cast<const uint4*>(er + 8 * Jc), w1 = *reinterpret_cast<const uint4*>(er + 8 * Jc + 4);
+        uint32_t vh[16], vl[16];
 #pragma unroll
         for (int rr = 0; rr < 4; ++rr) {
           uint4 hi, lo;
           gen_octet(gI[rr], w0, w1, hi, lo);
           if (Jc == I) fix_diag(gI[rr], lI[rr], dadd[rr], er + 8 * Jc, 4 * sub + rr, hi, lo);
-          *reinterpret_cast<uint4*>(Vh + rr * kCSb) = hi;
-          *reinterpret_cast<uint4*>(Vl + rr * kCSb) = lo;
+          vh[4 * rr] = hi.x; vh[4 * rr + 1] = hi.y; vh[4 * rr + 2] = hi.z; vh[4 * rr + 3] = hi.w;
+          vl[4 * rr] = lo.x; vl[4 * rr + 1] = lo.y; vl[4 * rr + 2] = lo.z; vl[4 * rr + 3] = lo.w;
         }
-        umma::fence_proxy_async();
+        umma::mbar_wait(&bar_vfree[vb], ((it / kDhAStages) & 1) ^ 1);
+        umma::fence_after_sync();
+        umma::tmem_st16(ta + vb * 64, vh);
+        umma::tmem_st16(ta + vb * 64 + 32, vl);
+        umma::tmem_st_wait();
+        umma::fence_before_sync();
         warp_arrive(&bar_vfull[vb], lane);
         if (Jc == I) {
           ++I; Jc = 0;
@@ -897,20 +922,23 @@ __global__ void __launch_bounds__(kBwThreads, 1) mvn_bwd_dw_kernel(const MvnEncP
   const int I_first = utab[0][0];
 
   if (warp == kBwGenWarps) {
-    if (lane == 0) {                                   // bulk-copy producer: [hidden | 1] tile (+ noise rows) of step n
+    {                                                  // bulk-copy producer: [hidden | 1] tile (+ noise rows) of step n
       for (int64_t n = 0; n < n_steps; ++n) {
         const uint32_t buf = (uint32_t)(n & 1);
         const int64_t tile = qg + (n / S) * n_qg;
         const int s = (int)(n % S);
         umma::mbar_wait(&bar_tfree[buf], (uint32_t)(((n >> 1) & 1) ^ 1));
-        umma::bulk_load(Hb + (size_t)buf * L.h_bytes, P.himg + (size_t)tile * L.h_bytes, L.h_bytes, &bar_efull[buf]);
-        if (bulk)
-          umma::bulk_load(smem + L.offEps + (size_t)buf * L.eps_bytes, P.eps_split + ((int64_t)s * m.B + tile * kDwTP) * K,
-                          (uint32_t)kDwTP * K * 4, &bar_efull[buf]);
+        if (umma::elect_one()) {
+          umma::bulk_load(Hb + (size_t)buf * L.h_bytes, P.himg + (size_t)tile * L.h_bytes, L.h_bytes, &bar_efull[buf]);
+          if (bulk)
+            umma::bulk_load(smem + L.offEps + (size_t)buf * L.eps_bytes, P.eps_split + ((int64_t)s * m.B + tile * kDwTP) * K,
+                            (uint32_t)kDwTP * K * 4, &bar_efull[buf]);
+        }
+        __syncwarp();
       }
     }
   } else if (warp == kBwGenWarps + 1) {
-    if (lane == 0) {                                   // MMA issuer
+    {                                                  // MMA issuer: a whole-warp loop, issue under elect_one()
       const uint32_t idesc = umma::make_idesc_f16(kMvCN, KH, umma::kMajorMN, umma::kMajorMN);
       const uint64_t dV0 = umma::make_desc(umma::smem_u32(Vb), RSV, kCSb);     // V^T: MN-major A
       const uint64_t dH0 = umma::make_desc(umma::smem_u32(Hb), RSH, kCSb);     // [hidden | 1]: MN-major B
@@ -924,23 +952,30 @@ __global__ void __launch_bounds__(kBwThreads, 1) mvn_bwd_dw_kernel(const MvnEncP
           const uint32_t vb = it & 1;
           umma::mbar_wait(&bar_vfull[vb], (it >> 1) & 1);
           umma::fence_after_sync();
-          const uint64_t dVh = dV0 + (uint64_t)((vb * L.v_bytes) >> 4), dVl = dVh + (uint64_t)(L.v_bytes >> 5);
-          const uint32_t td = tmem + k * KH;
-          uint32_t acc = fresh ? 0u : 1u;
+          if (umma::elect_one()) {
+            const uint64_t dVh = dV0 + (uint64_t)((vb * L.v_bytes) >> 4), dVl = dVh + (uint64_t)(L.v_bytes >> 5);
+            const uint32_t td = tmem + k * KH;
+            uint32_t acc = fresh ? 0u : 1u;
 #pragma unroll
-          for (int ks = 0; ks < kDwTP / 16; ++ks) {
-            const uint64_t ka = (uint64_t)(ks * ((2 * RSV) >> 4)), kb = (uint64_t)ks * (uint64_t)((2 * RSH) >> 4);
-            umma::mma_f16_ss(td, dVh + ka, dHh + kb, idesc, acc);          // hi * hi
-            umma::mma_f16_ss(td, dVh + ka, dHl + kb, idesc, 1u);           // hi * lo
-            umma::mma_f16_ss(td, dVl + ka, dHh + kb, idesc, 1u);           // lo * hi
-            acc = 1;
+            for (int ks = 0; ks < kDwTP / 16; ++ks) {
+              const uint64_t ka = (uint64_t)(ks * ((2 * RSV) >> 4)), kb = (uint64_t)ks * (uint64_t)((2 * RSH) >> 4);
+              umma::mma_f16_ss(td, dVh + ka, dHh + kb, idesc, acc);          // hi * hi
+              umma::mma_f16_ss(td, dVh + ka, dHl + kb, idesc, 1u);           // hi * lo
+              umma::mma_f16_ss(td, dVl + ka, dHh + kb, idesc, 1u);           // lo * hi
+              acc = 1;
+            }
+            umma::commit(&bar_vfree[vb]);
           }
-          umma::commit(&bar_vfree[vb]);
+          __syncwarp();
         }
         fresh = false;
-        umma::commit(&bar_tfree[buf]);                 // every MMA that reads this step's H tile has completed
-        if ((n + 1) % kDwFlushTiles == 0 || n + 1 == n_steps) {
-          umma::commit(&bar_done);                     // flush: the drain warps add the accumulators to the partial rows
+        const bool flush = (n + 1) % kDwFlushTiles == 0 || n + 1 == n_steps;
+        if (umma::elect_one()) {
+          umma::commit(&bar_tfree[buf]);               // every MMA that reads this step's H tile has completed
+          if (flush) umma::commit(&bar_done);          // flush: the drain warps add the accumulators to the partial rows
+        }
+        __syncwarp();
+        if (flush) {
           umma::mbar_wait(&bar_drained, nflush & 1);
           umma::fence_after_sync();
           fresh = true;

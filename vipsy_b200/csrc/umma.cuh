@@ -67,6 +67,21 @@ __device__ __forceinline__ void mma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uin
       "}\n" ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// One lane of a converged warp.  An issue loop should be walked by the WHOLE warp with only the tcgen05.mma / commit /
+// bulk-copy instructions under this predicate: the loop then stays warp-uniform and its descriptors live in uniform
+// registers.  Behind `if (lane == 0)` every operand of every MMA is moved register -> uniform register first, which
+// costs ~100 cycles per MMA (scripts/ubench/mma_rate.cu) -- more than a 128 x 64 x 16 or 128 x 128 x 16 MMA takes.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
 // all previously issued MMAs of this thread arrive on the mbarrier when complete
 __device__ __forceinline__ void commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
