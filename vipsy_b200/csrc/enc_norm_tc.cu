@@ -252,19 +252,22 @@ __global__ void __launch_bounds__(kThreads, NS == 128 ? 2 : 1) enc_tc_fwd_kernel
       umma::fence_proxy_async();
     }
     __syncthreads();
-    if (t == 0) {
+    if (warp == 0) {                                // the warp waits, one elected lane issues (see umma::elect_one)
       if (resident) umma::mbar_wait(&barx, phase);  // this tile's bulk copy has landed
       umma::fence_after_sync();
-      uint32_t acc = 0;
-      for (int ks = 0; ks < JP / 16; ++ks) {
-        const uint64_t da = umma::make_desc(sX + ks * 2 * kCS, kCS, RSx);
+      if (umma::elect_one()) {
+        uint32_t acc = 0;
+        for (int ks = 0; ks < JP / 16; ++ks) {
+          const uint64_t da = umma::make_desc(sX + ks * 2 * kCS, kCS, RSx);
 #pragma unroll
-        for (int term = 0; term < 3; ++term) {
-          umma::mma_f16_ss(tmem, da, umma::make_desc(sW[term] + ks * 2 * kCS, kCS, RS), idesc, acc);
-          acc = 1;
+          for (int term = 0; term < 3; ++term) {
+            umma::mma_f16_ss(tmem, da, umma::make_desc(sW[term] + ks * 2 * kCS, kCS, RS), idesc, acc);
+            acc = 1;
+          }
         }
+        umma::commit(&bar);
       }
-      umma::commit(&bar);
+      __syncwarp();
     }
     if constexpr (NS == 128) {
       if (!resident && tile + gridDim.x < n_tiles)
@@ -491,25 +494,26 @@ __global__ void __launch_bounds__(kBwdThreads) enc_tc_bwd_kernel(const EncParams
     }
     umma::fence_proxy_async();
     __syncthreads();
-    if (t == 0) {
-      if (resident) {
-        umma::mbar_wait(&barx, phx);                // this tile's bulk copy has landed
-        phx ^= 1u;
-      }
+    if (warp == 0) {                                // the warp waits, one elected lane issues (see umma::elect_one)
+      if (resident) umma::mbar_wait(&barx, phx);    // this tile's bulk copy has landed
       umma::fence_after_sync();
-      for (int ks = 0; ks < kTB / 16; ++ks) {
+      if (umma::elect_one()) {
+        for (int ks = 0; ks < kTB / 16; ++ks) {
 #pragma unroll
-        for (int mb = 0; mb < MB; ++mb) {           // item-slot block mb: 16 core-matrix columns further along
-          const uint64_t da = umma::make_desc(sX + ks * 2 * RSx + mb * 16 * kCS, RSx, kCS);
+          for (int mb = 0; mb < MB; ++mb) {           // item-slot block mb: 16 core-matrix columns further along
+            const uint64_t da = umma::make_desc(sX + ks * 2 * RSx + mb * 16 * kCS, RSx, kCS);
 #pragma unroll
-          for (int term = 0; term < 3; ++term)        // only the very first MMA of an accumulator overwrites it
-            umma::mma_f16_ss(tmem + ((nt % NACC) * MB + mb) * kTmemCols, da,
-                             umma::make_desc(sD[term] + ks * 2 * RSd, RSd, kCS), idesc,
-                             ((nt >= NACC ? 1u : 0u) | (uint32_t)ks | (uint32_t)term) != 0u ? 1u : 0u);
+            for (int term = 0; term < 3; ++term)        // only the very first MMA of an accumulator overwrites it
+              umma::mma_f16_ss(tmem + ((nt % NACC) * MB + mb) * kTmemCols, da,
+                               umma::make_desc(sD[term] + ks * 2 * RSd, RSd, kCS), idesc,
+                               ((nt >= NACC ? 1u : 0u) | (uint32_t)ks | (uint32_t)term) != 0u ? 1u : 0u);
+          }
         }
+        umma::commit(&bar);
       }
-      umma::commit(&bar);
+      __syncwarp();
     }
+    if (resident) phx ^= 1u;
     ++nt;
     pending = true;
     nb ^= 1;

@@ -360,8 +360,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) mirt_tc_lik_kernel(const MirtPa
       mbar_arrive(&bars[kBarYFull0 + buf]);
     }
   } else if (warp == kTcMmaWarp) {
-    // =========================== MMA ISSUER (one thread) =============================================
-    if (lane == 0) {
+    // =========================== MMA ISSUER ===========================================================
+    // the whole warp walks the loop (every lane waits), one elected lane issues: see umma::elect_one
+    {
       const uint32_t idesc_fwd = umma::make_idesc_f16(kTcTM, kTcTN, umma::kMajorK, umma::kMajorMN);
       const uint32_t idesc_dx = umma::make_idesc_f16(kTcTM, KP, umma::kMajorK, umma::kMajorK);
       const uint32_t idesc_da = umma::make_idesc_f16(128, kTcTN, umma::kMajorMN, umma::kMajorMN);
@@ -373,8 +374,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) mirt_tc_lik_kernel(const MirtPa
         // forward: logits = [x|1] [a;b]  (A operand K-major from the x tile, B MN-major from the a tile)
         umma::mbar_wait(&bars[kBarXFull], par);
         umma::fence_after_sync();
-        TC_STAMP(1, 0);
         uint32_t acc = 0;
+        if (umma::elect_one()) {
+        TC_STAMP(1, 0);
         for (int ks = 0; ks < KP / 16; ++ks) {
 #pragma unroll
           for (int term = 0; term < 3; ++term) {             // hi*hi, hi*lo, lo*hi
@@ -386,10 +388,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) mirt_tc_lik_kernel(const MirtPa
         }
         umma::commit(&bars[kBarLFull]);
         TC_STAMP(1, 1);
+        }
+        __syncwarp();
         // backward: d x = G a^T (cols kColDx..), d a += x^T G (cols kColDa.., lives across row tiles)
         umma::mbar_wait(&bars[kBarGFull], par);
         if (n > 0) umma::mbar_wait(&bars[kBarDxFree], (uint32_t)((n - 1) & 1));
         umma::fence_after_sync();
+        if (umma::elect_one()) {
         TC_STAMP(1, 2);
         acc = 0;
         if (!(p.dbg & 8))
@@ -417,6 +422,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) mirt_tc_lik_kernel(const MirtPa
         umma::commit(&bars[kBarXFree]);
         umma::commit(&bars[kBarDxFull]);
         TC_STAMP(1, 3);
+        }
+        __syncwarp();
       }
     }
   } else {
