@@ -806,34 +806,41 @@ __global__ void __launch_bounds__(kBwThreads, 1) mvn_bwd_dh_kernel(const MvnEncP
 
 // ---- d [W22 | b22][(i,j)][h] = sum over persons of V[person][(i,j)] [hidden | 1][person][h] -------------------------
 // CTA (pg, qg): chunks [pg * CPB, ..) of the factor columns x 64-person tiles qg, qg + n_qg, ..; the accumulators of
-// the slab stay in tensor memory; partial results [qg] are summed in a fixed order by mvn_dw_finalize.  A CTA has
-// only CPB chunks of work per tile, so nothing per tile may sit on the critical path: the noise rows and the
-// [hidden | 1] operand tile (pre-split once per step, mvn_himg_kernel) arrive by bulk copies one tile ahead, the
-// handful of G / diag L values a thread needs by 4-byte cp.async one tile ahead, the (I, Jc) of the slab's units from
-// a table built once.
+// the slab stay in tensor memory; partial results [qg] are summed in a fixed order by mvn_dw_finalize.
+//
+// V^T is the A operand (M = factor column, K = person) and lives in TENSOR memory: a generating thread owns one factor
+// column (i, j) = its TMEM lane and forms g_i[b] eps_j[b] for 32 persons in packed half arithmetic from two rows of
+// person-contiguous, pre-split fp16 pairs -- rows that mvn_dwprep_kernel lays out once per step (transposed tiles of
+// G, of the draws and of the diagonal terms).  Nothing is transposed, split or converted in this kernel, V never
+// crosses shared memory (whose read port an SS-mode MMA would saturate), and a chunk costs ~90 instructions per
+// thread instead of ~290.
 constexpr int kDwTP = 64;                  // persons per tile (UMMA K extent: 4 k-steps)
 constexpr int kDwFlushTiles = 16;          // accumulate in TMEM for at most 16 tiles = 192 MMAs per accumulator
-constexpr int kDwMaxRows = 6;              // block rows of L that a slab of <= 8 chunks (16 units) can touch
-__host__ __device__ inline int dw_cpb(int H) { return 512 / mv_kh(H) < 8 ? 512 / mv_kh(H) : 8; }   // chunks per CTA slab
+constexpr int kDwMaxRows = 4;              // block rows of L that a slab of <= 4 chunks (8 consecutive units) can touch
+constexpr int kDwAStages = 3;              // V^T chunks in tensor memory: 3 x (32 hi + 32 lo) columns at 320..511
+constexpr uint32_t kDwACol = 512 - 64 * kDwAStages;
+constexpr uint32_t kDwGRec = 512;          // per row i of a tile: [g hi | g lo | diag hi | diag lo], 64 persons x fp16 each
+constexpr uint32_t kDwERec = 272;          // per column j of a tile: [eps hi | eps lo | 16 B pad] (pad: 8 columns -> 32 banks)
+__host__ __device__ inline int dw_cpb(int H) {                                     // chunks per CTA slab
+  const int c = (int)kDwACol / mv_kh(H);
+  return c < 4 ? c : 4;
+}
 __host__ __device__ inline size_t mv_himg_tile_bytes(int H) { return (size_t)2 * kDwTP * mv_kh(H) * 2; }
+__host__ __device__ inline size_t mv_vimg_tile_bytes(int K) { return (size_t)8 * mv_nb(K) * (kDwGRec + kDwERec); }
 
 struct DwSmem {
-  uint32_t offEps, offH, offV, offG, offL, total, eps_bytes, h_bytes, v_bytes;
-  int ES;
+  uint32_t offH, offE, offG, buf_bytes, total, h_bytes, e_bytes, g_bytes;
 };
-__host__ __device__ inline DwSmem dw_smem(int K, int H, bool bulk) {
+__host__ __device__ inline DwSmem dw_smem(int K, int H) {
   DwSmem s;
-  s.ES = bulk ? K : (K + 7) / 8 * 8 + 4;               // bulk: rows as they lie in global memory (K % 4 == 0)
-  s.eps_bytes = ((uint32_t)kDwTP * s.ES * 4 + 64 + 127) & ~127u;
   s.h_bytes = (uint32_t)mv_himg_tile_bytes(H);
-  s.v_bytes = 2u * kDwTP * kMvCN * 2;
-  uint32_t o = 0;
-  s.offEps = o; o += 2 * s.eps_bytes;
-  s.offH = o; o += 2 * s.h_bytes;
-  s.offV = o; o += 2 * s.v_bytes;
-  s.offG = o; o += 2u * kDwMaxRows * 8 * kDwTP * 4;
-  s.offL = o; o += 2u * kDwMaxRows * 8 * kDwTP * 4;
-  s.total = o;
+  s.e_bytes = (uint32_t)(8 * mv_nb(K)) * kDwERec;
+  s.g_bytes = (uint32_t)kDwMaxRows * 8 * kDwGRec;
+  s.offH = 0;
+  s.offE = s.h_bytes;
+  s.offG = s.offE + s.e_bytes;
+  s.buf_bytes = (s.offG + s.g_bytes + 127) & ~127u;
+  s.total = 2 * s.buf_bytes;
   return s;
 }
 
@@ -861,43 +868,101 @@ __global__ void mvn_himg_kernel(const float* __restrict__ hidden, int64_t B, int
   }
 }
 
-__device__ __forceinline__ void cp_async4(void* dst_smem, const void* src) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(umma::smem_u32(dst_smem)), "l"(src) : "memory");
+// The generator's operands, once per step: for every (particle, 64-person tile) a block of person-contiguous rows
+//   row i   : g_i[b] hi | g_i[b] lo | v_ii[b] hi | v_ii[b] lo      v_ii = g_i eps_i L_ii - scale [s == 0]   (diagonal of V)
+//   column j: eps_j[b] hi | eps_j[b] lo
+// with g = G * 2^-e such that max |g| <= 16 (exact; undone by the drain), zeros for dead persons and rows beyond K.
+__global__ void __launch_bounds__(256) mvn_dwprep_kernel(const MvnEncParams P, const float* __restrict__ eps_f32,
+                                                          unsigned char* __restrict__ vimg) {
+  const MirtParams& m = P.m;
+  const int K = m.K, K8 = 8 * mv_nb(K);
+  const int64_t n_tiles = (m.B + kDwTP - 1) / kDwTP;
+  int gexp;
+  frexpf(fmaxf(*P.gmax, m.scale), &gexp);
+  const float ginv = ldexpf(1.f, 4 - gexp);
+  const int bp = threadIdx.x & 31, i0 = threadIdx.x >> 5;
+  for (int64_t step = blockIdx.x; step < n_tiles * m.S; step += gridDim.x) {
+    const int s = (int)(step / n_tiles);
+    const int64_t tile = step - (int64_t)s * n_tiles;
+    unsigned char* grec = vimg + (size_t)step * mv_vimg_tile_bytes(K);
+    unsigned char* erec = grec + (size_t)K8 * kDwGRec;
+    for (int i = i0; i < K8; i += 8) {
+      float g[2], e[2], vd[2];
+      __half eh[2], el[2];
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        const int64_t b = tile * kDwTP + 2 * bp + q;
+        const bool live = b < m.B && i < K;
+        const int64_t row = ((int64_t)s * m.B + b) * K;
+        g[q] = live ? ginv * m.gx[row + i] : 0.f;
+        if (P.eps_split) {
+          const uint32_t Hw = live ? P.eps_split[row + 2 * (i >> 1)] : 0u, Lw = live ? P.eps_split[row + 2 * (i >> 1) + 1] : 0u;
+          eh[q] = __ushort_as_half((unsigned short)((i & 1) ? Hw >> 16 : Hw & 0xffffu));
+          el[q] = __ushort_as_half((unsigned short)((i & 1) ? Lw >> 16 : Lw & 0xffffu));
+          e[q] = __half2float(eh[q]) + __half2float(el[q]);
+        } else {
+          e[q] = live ? eps_f32[row + i] : 0.f;
+          umma::split_f16(e[q], eh[q], el[q]);
+        }
+        const float lii = live ? m.diagL[b * K + i] : 0.f;
+        vd[q] = fmaf(g[q] * e[q], lii, (live && s == 0) ? -m.scale * ginv : 0.f);
+      }
+      uint32_t w[6];
+      split_pair(g[0], g[1], w[0], w[1]);
+      split_pair(vd[0], vd[1], w[2], w[3]);
+      w[4] = (uint32_t)__half_as_ushort(eh[0]) | ((uint32_t)__half_as_ushort(eh[1]) << 16);
+      w[5] = (uint32_t)__half_as_ushort(el[0]) | ((uint32_t)__half_as_ushort(el[1]) << 16);
+      uint32_t* gr = reinterpret_cast<uint32_t*>(grec + (size_t)i * kDwGRec) + bp;
+      gr[0] = w[0]; gr[32] = w[1]; gr[64] = w[2]; gr[96] = w[3];
+      uint32_t* er = reinterpret_cast<uint32_t*>(erec + (size_t)i * kDwERec) + bp;
+      er[0] = w[4]; er[32] = w[5];
+    }
+  }
 }
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
-__global__ void __launch_bounds__(kBwThreads, 1) mvn_bwd_dw_kernel(const MvnEncParams P, const int n_pg, const int n_qg,
-                                                                    const int bulk) {
+__device__ __forceinline__ void gen_pairs(const uint4& gh, const uint4& gl, const uint4& eh, const uint4& el, uint32_t* vh,
+                                          uint32_t* vl) {
+  auto one = [&](uint32_t a, uint32_t al, uint32_t e, uint32_t e_l, uint32_t& oh, uint32_t& ol) {
+    const __half2 h = __hmul2(as_h2(a), as_h2(e));
+    __half2 r = __hfma2(as_h2(a), as_h2(e), __hneg2(h));
+    r = __hfma2(as_h2(a), as_h2(e_l), r);
+    r = __hfma2(as_h2(al), as_h2(e), r);
+    oh = h2_bits(h);
+    ol = h2_bits(r);
+  };
+  one(gh.x, gl.x, eh.x, el.x, vh[0], vl[0]);
+  one(gh.y, gl.y, eh.y, el.y, vh[1], vl[1]);
+  one(gh.z, gl.z, eh.z, el.z, vh[2], vl[2]);
+  one(gh.w, gl.w, eh.w, el.w, vh[3], vl[3]);
+}
+
+__global__ void __launch_bounds__(kBwThreads, 1) mvn_bwd_dw_kernel(const MvnEncParams P, const unsigned char* __restrict__ vimg,
+                                                                    const int n_pg, const int n_qg) {
   extern __shared__ __align__(128) unsigned char smem[];
-  __shared__ uint64_t bar_efull[2], bar_tfree[2], bar_vfull[2], bar_vfree[2], bar_done, bar_drained;
+  __shared__ uint64_t bar_efull[2], bar_tfree[2], bar_vfull[kDwAStages], bar_vfree[kDwAStages], bar_done, bar_drained;
   __shared__ uint32_t tmem_base_sm;
-  __shared__ int utab[16][2];                         // (I, Jc) of the slab's units; I >= NB: beyond the factor
+  __shared__ int utab[8][2];                          // (I, Jc) of the slab's units; I >= NB: beyond the factor
   const MirtParams& m = P.m;
   const int K = m.K, S = m.S, H = P.H, KH = mv_kh(H), NB = mv_nb(K), NU = NB * (NB + 1) / 2;
-  const DwSmem L = dw_smem(K, H, bulk != 0);
-  const int ES = L.ES, CPB = dw_cpb(H), n_chunks = mv_chunks(K);
-  unsigned char* Hb = smem + L.offH;
-  unsigned char* Vb = smem + L.offV;
-  float* gsm = reinterpret_cast<float*>(smem + L.offG);
-  float* lsm = reinterpret_cast<float*>(smem + L.offL);
-  const uint32_t RSV = (kMvCN / 8) * kCSb, RSH = (uint32_t)(KH / 8) * kCSb;
+  const DwSmem L = dw_smem(K, H);
+  const int CPB = dw_cpb(H), n_chunks = mv_chunks(K);
+  const uint32_t RSH = (uint32_t)(KH / 8) * kCSb;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int pg = blockIdx.x % n_pg, qg = blockIdx.x / n_pg;
   const int c0 = pg * CPB, c1 = min(c0 + CPB, n_chunks), nblk = c1 - c0;
   const int64_t n_tiles = (m.B + kDwTP - 1) / kDwTP;
   const int64_t my_tiles = qg < n_tiles ? (n_tiles - qg + n_qg - 1) / n_qg : 0;       // tiles qg, qg + n_qg, ..
   const int64_t n_steps = my_tiles * S;                                              // (tile, particle) pairs
-  const float* eps_src = m.eps ? m.eps : P.eps_out;
-  // V is an fp16 hi/lo operand: G is scaled by a power of two so that max |G'| <= 16 (exact; undone at the drain)
   int gexp;
   frexpf(fmaxf(*P.gmax, m.scale), &gexp);
-  const float ginv = ldexpf(1.f, 4 - gexp), gfix = ldexpf(1.f, gexp - 4);
+  const float gfix = ldexpf(1.f, gexp - 4);
 
   if (tid == 0) {
     for (int i = 0; i < 2; ++i) {
-      umma::mbar_init(&bar_efull[i], bulk ? 2 : 1);
+      umma::mbar_init(&bar_efull[i], 3);               // three bulk copies per step: [hidden | 1], draws, G rows
       umma::mbar_init(&bar_tfree[i], kBwGenWarps + 1);
+    }
+    for (int i = 0; i < kDwAStages; ++i) {
       umma::mbar_init(&bar_vfull[i], kBwGenWarps);
       umma::mbar_init(&bar_vfree[i], 1);
     }
@@ -911,162 +976,130 @@ __global__ void __launch_bounds__(kBwThreads, 1) mvn_bwd_dw_kernel(const MvnEncP
     utab[tid][0] = 2 * c0 + tid < NU ? I : NB;
     utab[tid][1] = Jc;
   }
-  for (int e = 0; e < 2; ++e)                          // finite values behind the rows of a tile (see mvn_bwd_dh_kernel)
-    for (uint32_t o = (uint32_t)kDwTP * ES * 4 + 4 * tid; o < L.eps_bytes; o += 4 * kBwThreads)
-      *reinterpret_cast<uint32_t*>(smem + L.offEps + (size_t)e * L.eps_bytes + o) = 0u;
   if (warp == kBwGenWarps + 1) umma::tmem_alloc(&tmem_base_sm, 512);
   umma::fence_before_sync();
   __syncthreads();
   umma::fence_after_sync();
   const uint32_t tmem = tmem_base_sm;
   const int I_first = utab[0][0];
+  const int I_last = utab[2 * nblk - 1][0] < NB ? utab[2 * nblk - 1][0] : NB - 1;
+  const int n_rows = I_last - I_first + 1;             // block rows of the slab (<= kDwMaxRows)
+  const uint32_t e_copy = (uint32_t)(8 * (I_last + 1)) * kDwERec, g_copy = (uint32_t)(8 * n_rows) * kDwGRec;
 
   if (warp == kBwGenWarps) {
-    {                                                  // bulk-copy producer: [hidden | 1] tile (+ noise rows) of step n
-      for (int64_t n = 0; n < n_steps; ++n) {
-        const uint32_t buf = (uint32_t)(n & 1);
-        const int64_t tile = qg + (n / S) * n_qg;
-        const int s = (int)(n % S);
-        umma::mbar_wait(&bar_tfree[buf], (uint32_t)(((n >> 1) & 1) ^ 1));
-        if (umma::elect_one()) {
-          umma::bulk_load(Hb + (size_t)buf * L.h_bytes, P.himg + (size_t)tile * L.h_bytes, L.h_bytes, &bar_efull[buf]);
-          if (bulk)
-            umma::bulk_load(smem + L.offEps + (size_t)buf * L.eps_bytes, P.eps_split + ((int64_t)s * m.B + tile * kDwTP) * K,
-                            (uint32_t)kDwTP * K * 4, &bar_efull[buf]);
-        }
-        __syncwarp();
-      }
-    }
-  } else if (warp == kBwGenWarps + 1) {
-    {                                                  // MMA issuer: a whole-warp loop, issue under elect_one()
-      const uint32_t idesc = umma::make_idesc_f16(kMvCN, KH, umma::kMajorMN, umma::kMajorMN);
-      const uint64_t dV0 = umma::make_desc(umma::smem_u32(Vb), RSV, kCSb);     // V^T: MN-major A
-      const uint64_t dH0 = umma::make_desc(umma::smem_u32(Hb), RSH, kCSb);     // [hidden | 1]: MN-major B
-      uint32_t it = 0, nflush = 0;
-      bool fresh = true;                               // the accumulators hold nothing yet (start, or just flushed)
-      for (int64_t n = 0; n < n_steps; ++n) {
-        const uint32_t buf = (uint32_t)(n & 1);
-        umma::mbar_wait(&bar_efull[buf], (uint32_t)((n >> 1) & 1));
-        const uint64_t dHh = dH0 + (uint64_t)((buf * L.h_bytes) >> 4), dHl = dHh + (uint64_t)(L.h_bytes >> 5);
-        for (int k = 0; k < nblk; ++k, ++it) {
-          const uint32_t vb = it & 1;
-          umma::mbar_wait(&bar_vfull[vb], (it >> 1) & 1);
-          umma::fence_after_sync();
-          if (umma::elect_one()) {
-            const uint64_t dVh = dV0 + (uint64_t)((vb * L.v_bytes) >> 4), dVl = dVh + (uint64_t)(L.v_bytes >> 5);
-            const uint32_t td = tmem + k * KH;
-            uint32_t acc = fresh ? 0u : 1u;
-#pragma unroll
-            for (int ks = 0; ks < kDwTP / 16; ++ks) {
-              const uint64_t ka = (uint64_t)(ks * ((2 * RSV) >> 4)), kb = (uint64_t)ks * (uint64_t)((2 * RSH) >> 4);
-              umma::mma_f16_ss(td, dVh + ka, dHh + kb, idesc, acc);          // hi * hi
-              umma::mma_f16_ss(td, dVh + ka, dHl + kb, idesc, 1u);           // hi * lo
-              umma::mma_f16_ss(td, dVl + ka, dHh + kb, idesc, 1u);           // lo * hi
-              acc = 1;
-            }
-            umma::commit(&bar_vfree[vb]);
-          }
-          __syncwarp();
-        }
-        fresh = false;
-        const bool flush = (n + 1) % kDwFlushTiles == 0 || n + 1 == n_steps;
-        if (umma::elect_one()) {
-          umma::commit(&bar_tfree[buf]);               // every MMA that reads this step's H tile has completed
-          if (flush) umma::commit(&bar_done);          // flush: the drain warps add the accumulators to the partial rows
-        }
-        __syncwarp();
-        if (flush) {
-          umma::mbar_wait(&bar_drained, nflush & 1);
-          umma::fence_after_sync();
-          fresh = true;
-          ++nflush;
-        }
-      }
-    }
-  } else {
-    const int person = tid & (kDwTP - 1), sub = tid >> 6;            // rows 2 sub, 2 sub + 1 of every unit
-    const int n_rows = utab[2 * nblk - 1][0] < NB ? utab[2 * nblk - 1][0] - I_first + 1 : NB - I_first;   // block rows of the slab
-    uint32_t it = 0, nflush = 0;
-    // G and diag L of the thread's rows (8 I + sub for the slab's block rows) of step n -> buffer n & 1, asynchronously
-    auto prefetch_g = [&](int64_t n) {
-      const uint32_t buf = (uint32_t)(n & 1);
-      const int64_t b = (qg + (n / S) * n_qg) * kDwTP + person;
-      const int s = (int)(n % S);
-      const float* gsrc = m.gx + ((int64_t)s * m.B + b) * K;
-      const float* lsrc = m.diagL + b * K;
-      for (int o = 0; o < n_rows; ++o) {
-#pragma unroll
-        for (int rr = 0; rr < 2; ++rr) {
-          const int i = 8 * (I_first + o) + 2 * sub + rr;
-          float* gd = gsm + ((size_t)(buf * kDwMaxRows + o) * 8 + 2 * sub + rr) * kDwTP + person;
-          float* ld = lsm + ((size_t)(buf * kDwMaxRows + o) * 8 + 2 * sub + rr) * kDwTP + person;
-          if (b < m.B && i < K) {
-            cp_async4(gd, gsrc + i);
-            cp_async4(ld, lsrc + i);
-          } else {
-            *gd = 0.f;
-            *ld = 0.f;
-          }
-        }
-      }
-      cp_async_commit();
-    };
-    if (n_steps > 0) prefetch_g(0);
+    // bulk-copy producer: [hidden | 1] tile, the columns of the draws and the rows of G this slab needs, of step n
     for (int64_t n = 0; n < n_steps; ++n) {
       const uint32_t buf = (uint32_t)(n & 1);
       const int64_t tile = qg + (n / S) * n_qg;
       const int s = (int)(n % S);
-      const int64_t b = tile * kDwTP + person;
-      const bool live = b < m.B;
-      uint32_t* eps_t = reinterpret_cast<uint32_t*>(smem + L.offEps + (size_t)buf * L.eps_bytes);
-      if (!bulk) {                                     // injected noise / K % 4 != 0: rows split here, padded pitch
-        const float* src = eps_src + (int64_t)s * m.B * K;
-        for (int pp = warp * (kDwTP / kBwGenWarps); pp < (warp + 1) * (kDwTP / kBwGenWarps); ++pp) {
-          const int64_t bb = tile * kDwTP + pp;
-          for (int mm = lane; mm < ES / 2; mm += 32) {
-            const float z0 = (bb < m.B && 2 * mm < K) ? src[bb * K + 2 * mm] : 0.f;
-            const float z1 = (bb < m.B && 2 * mm + 1 < K) ? src[bb * K + 2 * mm + 1] : 0.f;
-            split_pair(z0, z1, eps_t[(size_t)pp * ES + 2 * mm], eps_t[(size_t)pp * ES + 2 * mm + 1]);
-          }
-        }
-        gen_bar();
-      } else {
-        umma::mbar_wait(&bar_efull[buf], (uint32_t)((n >> 1) & 1));
+      umma::mbar_wait(&bar_tfree[buf], (uint32_t)(((n >> 1) & 1) ^ 1));
+      if (umma::elect_one()) {
+        unsigned char* dst = smem + (size_t)buf * L.buf_bytes;
+        const unsigned char* src = vimg + (size_t)((int64_t)s * n_tiles + tile) * mv_vimg_tile_bytes(K);
+        umma::bulk_load(dst + L.offH, P.himg + (size_t)tile * L.h_bytes, L.h_bytes, &bar_efull[buf]);
+        umma::bulk_load(dst + L.offE, src + (size_t)(8 * NB) * kDwGRec, e_copy, &bar_efull[buf]);
+        umma::bulk_load(dst + L.offG, src + (size_t)(8 * I_first) * kDwGRec, g_copy, &bar_efull[buf]);
       }
-      cp_async_wait_all();                             // this step's G / diag L (own entries only: no barrier needed)
-      if (n + 1 < n_steps) prefetch_g(n + 1);
-      const uint32_t* er = eps_t + (size_t)person * ES;
-      const float* gp = gsm + ((size_t)buf * kDwMaxRows * 8 + 2 * sub) * kDwTP + person;    // + (o * 8 + rr) * kDwTP
-      const float* lp = lsm + ((size_t)buf * kDwMaxRows * 8 + 2 * sub) * kDwTP + person;
-      const float dadd_t = (live && s == 0) ? -m.scale * ginv : 0.f;
-      const uint32_t voff = (uint32_t)(person >> 3) * RSV + (uint32_t)(2 * sub) * kCSb + (uint32_t)(person & 7) * 16u;
+      __syncwarp();
+    }
+  } else if (warp == kBwGenWarps + 1) {
+    // MMA issuer: a whole-warp loop, issue under elect_one()
+    const uint32_t idesc = umma::make_idesc_f16(kMvCN, KH, umma::kMajorK, umma::kMajorMN);
+    const uint64_t dH0 = umma::make_desc(umma::smem_u32(smem + L.offH), RSH, kCSb);     // [hidden | 1]: MN-major B
+    uint32_t it = 0, nflush = 0;
+    bool fresh = true;                                 // the accumulators hold nothing yet (start, or just flushed)
+    for (int64_t n = 0; n < n_steps; ++n) {
+      const uint32_t buf = (uint32_t)(n & 1);
+      umma::mbar_wait(&bar_efull[buf], (uint32_t)((n >> 1) & 1));
       for (int k = 0; k < nblk; ++k, ++it) {
-        const uint32_t vb = it & 1;
-        umma::mbar_wait(&bar_vfree[vb], ((it >> 1) & 1) ^ 1);
-        unsigned char* Vh = Vb + (size_t)vb * L.v_bytes + voff;
-        unsigned char* Vl = Vh + L.v_bytes / 2;
+        const uint32_t vb = it % kDwAStages;
+        umma::mbar_wait(&bar_vfull[vb], (it / kDwAStages) & 1);
+        umma::fence_after_sync();
+        if (umma::elect_one()) {
+          const uint64_t dHh = dH0 + (uint64_t)((buf * L.buf_bytes) >> 4), dHl = dHh + (uint64_t)(L.h_bytes >> 5);
+          const uint32_t aH = tmem + kDwACol + vb * 64, aL = aH + 32;      // a k-step = 16 persons = 8 words
+          const uint32_t td = tmem + k * KH;
+          uint32_t acc = fresh ? 0u : 1u;
 #pragma unroll
-        for (int half = 0; half < 2; ++half) {
-          const int I = utab[2 * k + half][0], Jc = utab[2 * k + half][1];
-          const bool in = I < NB;                      // units beyond the factor (tail of the last chunk): zeros
-          const int o = in ? I - I_first : 0, jo = in ? 8 * Jc : 0;
-          const uint4 w0 = *reinterpret_cast<const uint4*>(er + jo), w1 = *reinterpret_cast<const uint4*>(er + jo + 4);
-#pragma unroll
-          for (int rr = 0; rr < 2; ++rr) {
-            // dead persons / rows beyond K hold g = 0 (prefetch_g), so whatever the bulk copy brought there gives 0
-            const float g = in ? ginv * gp[(size_t)(o * 8 + rr) * kDwTP] : 0.f;
-            uint4 hi, lo;
-            gen_octet(g, w0, w1, hi, lo);
-            if (in && Jc == I)                         // diagonal block: exp chain rule + entropy term, zero above it
-              fix_diag(g, lp[(size_t)(o * 8 + rr) * kDwTP], 8 * I + 2 * sub + rr < K ? dadd_t : 0.f, er + jo, 2 * sub + rr, hi, lo);
-            *reinterpret_cast<uint4*>(Vh + (half * 8 + rr) * kCSb) = hi;
-            *reinterpret_cast<uint4*>(Vl + (half * 8 + rr) * kCSb) = lo;
+          for (int ks = 0; ks < kDwTP / 16; ++ks) {
+            const uint64_t kb = (uint64_t)ks * (uint64_t)((2 * RSH) >> 4);
+            umma::mma_f16_ts(td, aH + 8 * ks, dHh + kb, idesc, acc);         // hi * hi
+            umma::mma_f16_ts(td, aH + 8 * ks, dHl + kb, idesc, 1u);          // hi * lo
+            umma::mma_f16_ts(td, aL + 8 * ks, dHh + kb, idesc, 1u);          // lo * hi
+            acc = 1;
           }
+          umma::commit(&bar_vfree[vb]);
         }
-        umma::fence_proxy_async();
+        __syncwarp();
+      }
+      fresh = false;
+      const bool flush = (n + 1) % kDwFlushTiles == 0 || n + 1 == n_steps;
+      if (umma::elect_one()) {
+        umma::commit(&bar_tfree[buf]);                 // every MMA that reads this step's H tile has completed
+        if (flush) umma::commit(&bar_done);            // flush: the drain warps add the accumulators to the partial rows
+      }
+      __syncwarp();
+      if (flush) {
+        umma::mbar_wait(&bar_drained, nflush & 1);
+        umma::fence_after_sync();
+        fresh = true;
+        ++nflush;
+      }
+    }
+  } else {
+    // generators: thread = factor column c of the chunk (its TMEM lane) x half of the tile's persons
+    const int q4 = warp & 3, hp = warp >> 2;
+    const int half = q4 >> 1, r = 4 * (q4 & 1) + (lane >> 3), jj = lane & 7;
+    const uint32_t ta = tmem + ((uint32_t)(32 * q4) << 16) + kDwACol + 16u * (uint32_t)hp;
+    uint32_t it = 0, nflush = 0;
+    for (int64_t n = 0; n < n_steps; ++n) {
+      const uint32_t buf = (uint32_t)(n & 1);
+      const unsigned char* Eb = smem + (size_t)buf * L.buf_bytes + L.offE + 64 * hp;
+      const unsigned char* Gb = smem + (size_t)buf * L.buf_bytes + L.offG + 64 * hp;
+      umma::mbar_wait(&bar_efull[buf], (uint32_t)((n >> 1) & 1));
+      for (int k = 0; k < nblk; ++k, ++it) {
+        const uint32_t vb = it % kDwAStages;
+        const int I = utab[2 * k + half][0], Jc = utab[2 * k + half][1];
+        uint32_t vh[16], vl[16];
+        if (I < NB) {                                  // warp-uniform
+          const unsigned char* grow = Gb + (size_t)((I - I_first) * 8 + r) * kDwGRec;
+          const unsigned char* erow = Eb + (size_t)(8 * Jc + jj) * kDwERec;
+          if (Jc == I && jj >= r) {                    // diagonal block: v_ii from the prepared row, zero above it
+            if (jj == r) {
+#pragma unroll
+              for (int p8 = 0; p8 < 4; ++p8) {
+                const uint4 a = *reinterpret_cast<const uint4*>(grow + 256 + 16 * p8);
+                const uint4 b = *reinterpret_cast<const uint4*>(grow + 384 + 16 * p8);
+                vh[4 * p8] = a.x; vh[4 * p8 + 1] = a.y; vh[4 * p8 + 2] = a.z; vh[4 * p8 + 3] = a.w;
+                vl[4 * p8] = b.x; vl[4 * p8 + 1] = b.y; vl[4 * p8 + 2] = b.z; vl[4 * p8 + 3] = b.w;
+              }
+            } else {
+#pragma unroll
+              for (int q = 0; q < 16; ++q) { vh[q] = 0u; vl[q] = 0u; }
+            }
+          } else {
+#pragma unroll
+            for (int p8 = 0; p8 < 4; ++p8) {
+              const uint4 gh = *reinterpret_cast<const uint4*>(grow + 16 * p8);
+              const uint4 gl = *reinterpret_cast<const uint4*>(grow + 128 + 16 * p8);
+              const uint4 eh = *reinterpret_cast<const uint4*>(erow + 16 * p8);
+              const uint4 el = *reinterpret_cast<const uint4*>(erow + 128 + 16 * p8);
+              gen_pairs(gh, gl, eh, el, vh + 4 * p8, vl + 4 * p8);
+            }
+          }
+        } else {                                       // units beyond the factor (tail of the last chunk): zeros
+#pragma unroll
+          for (int q = 0; q < 16; ++q) { vh[q] = 0u; vl[q] = 0u; }
+        }
+        umma::mbar_wait(&bar_vfree[vb], ((it / kDwAStages) & 1) ^ 1);
+        umma::fence_after_sync();
+        umma::tmem_st16(ta + vb * 64, vh);
+        umma::tmem_st16(ta + vb * 64 + 32, vl);
+        umma::tmem_st_wait();
+        umma::fence_before_sync();
         warp_arrive(&bar_vfull[vb], lane);
       }
-      warp_arrive(&bar_tfree[buf], lane);              // done with this step's noise rows
+      warp_arrive(&bar_tfree[buf], lane);              // done with this step's rows
       // Flush every kDwFlushTiles steps: the accumulators are added (round-to-nearest, fixed order) to this CTA's
       // partial rows, which bounds the chain of truncating tensor-core accumulations (see mvn_bwd_dh_kernel).
       if ((n + 1) % kDwFlushTiles == 0 || n + 1 == n_steps) {
@@ -1153,6 +1186,9 @@ size_t mvn_dwpart_bytes(int K, int H) {
   dw_grid(K, H, &n_pg, &n_qg);
   return ((size_t)n_qg * mv_chunks(K) * kMvCN * mv_kh(H) * 4 + 255) & ~size_t(255);
 }
+size_t mvn_vimg_bytes(int64_t B, int K, int S) {       // the generator's operand rows (mvn_dwprep_kernel)
+  return ((size_t)((B + kDwTP - 1) / kDwTP) * S * mv_vimg_tile_bytes(K) + 255) & ~size_t(255);
+}
 
 int launch_mvn_tail(const MvnEncParams& P, int* loss_rows, cudaStream_t st) {
   int64_t g = (P.m.B * P.m.K + kTailThreads * 4 - 1) / (kTailThreads * 4);
@@ -1183,7 +1219,7 @@ int launch_mvn_bwd(const MvnEncParams& P, cudaStream_t st) {
     VIPSY_CUDA_CHECK(cudaGetLastError());
   }
   if (P.d_w22 || P.d_b22) {
-    const DwSmem L = dw_smem(K, H, bulk != 0);
+    const DwSmem L = dw_smem(K, H);
     VIPSY_REQUIRE(L.total <= 227 * 1024, VIPSY_ERR_UNSUPPORTED, "mvn encoder backward: K=%d H=%d does not fit shared memory", K, H);
     VIPSY_CUDA_CHECK(cudaFuncSetAttribute(mvn_bwd_dw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
     const int64_t n_tiles64 = (P.m.B + kDwTP - 1) / kDwTP;
@@ -1193,11 +1229,15 @@ int launch_mvn_bwd(const MvnEncParams& P, cudaStream_t st) {
       if (g > (int64_t)num_sms() * 16) g = (int64_t)num_sms() * 16;
       mvn_himg_kernel<<<(int)g, 256, 0, st>>>(P.hidden, P.m.B, H, mv_kh(H), P.himg);
       VIPSY_CUDA_CHECK(cudaGetLastError());
+      int64_t gp = n_tiles64 * P.m.S;
+      if (gp > (int64_t)num_sms() * 8) gp = (int64_t)num_sms() * 8;
+      mvn_dwprep_kernel<<<(int)gp, 256, 0, st>>>(P, P.m.eps ? P.m.eps : P.eps_out, P.vimg);
+      VIPSY_CUDA_CHECK(cudaGetLastError());
     }
     int n_pg, n_qg;
     dw_grid(K, H, &n_pg, &n_qg);
     if (n_qg > n_tiles64) n_qg = (int)n_tiles64;
-    mvn_bwd_dw_kernel<<<n_pg * n_qg, kBwThreads, L.total, st>>>(P, n_pg, n_qg, bulk);
+    mvn_bwd_dw_kernel<<<n_pg * n_qg, kBwThreads, L.total, st>>>(P, P.vimg, n_pg, n_qg);
     VIPSY_CUDA_CHECK(cudaGetLastError());
     const int total = K * (K + 1) / 2 * (H + 1);
     mvn_dw_finalize_kernel<<<(total + 255) / 256, 256, 0, st>>>(P.dw_part, n_qg, mv_chunks(K) * kMvCN, K, H, mv_kh(H),
@@ -1258,7 +1298,7 @@ using namespace vipsy;
 extern "C" {
 
 // workspace: [ mirt_layout of irt | fc22 operand images | the draws | partial d [W22 | b22] ]
-struct MvnLayout { size_t mirt, wimg, wimgb, himg, eps, dwpart, gmax, total; };
+struct MvnLayout { size_t mirt, wimg, wimgb, himg, vimg, eps, dwpart, gmax, total; };
 static MvnLayout mvn_layout(const VipsyMvnEncoderIrtArgs* a) {
   const VipsyIrtArgs& r = a->irt;
   MvnLayout L;
@@ -1267,6 +1307,7 @@ static MvnLayout mvn_layout(const VipsyMvnEncoderIrtArgs* a) {
   L.wimg = o; o += mvn_wimg_bytes(r.n_dims, a->n_hidden);
   L.wimgb = o; o += mvn_wimgb_bytes(r.n_dims, a->n_hidden);
   L.himg = o; o += mvn_himg_bytes(r.batch, a->n_hidden);
+  L.vimg = o; o += mvn_vimg_bytes(r.batch, r.n_dims, r.n_particles);
   L.eps = o; o += r.eps ? 0 : mvn_eps_bytes(r.batch, r.n_dims, r.n_particles);
   L.dwpart = o; o += mvn_dwpart_bytes(r.n_dims, a->n_hidden);
   L.gmax = o; o += 256;
@@ -1313,6 +1354,7 @@ int vipsy_irt_mvn_encoder_elbo_grad(const VipsyMvnEncoderIrtArgs* a, void* strea
   P.wimg = ws + L.wimg;
   P.wimg_b = ws + L.wimgb;
   P.himg = ws + L.himg;
+  P.vimg = ws + L.vimg;
   // our own draws: pre-split fp16 pair words when a row is a whole number of 16-byte pieces (bulk copies), else fp32
   P.eps_out = (r.eps || (r.n_dims & 3) == 0) ? nullptr : reinterpret_cast<float*>(ws + L.eps);
   P.eps_split = (r.eps || (r.n_dims & 3) != 0) ? nullptr : reinterpret_cast<uint32_t*>(ws + L.eps);

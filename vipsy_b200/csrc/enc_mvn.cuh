@@ -39,6 +39,7 @@ struct MvnEncParams {
   unsigned char* wimg;       // [chunks][hi | lo] operand image of 64 * [fc22.weight | fc22.bias | 0]
   unsigned char* wimg_b;     // [units][hi | lo] 64 padded columns x NH of 64 * fc22.weight (backward: d hidden), or null
   unsigned char* himg;       // [ceil(B / 64)][hi | lo] 64 persons x KH of [hidden | 1 | 0] (backward: d fc22), or null
+  unsigned char* vimg;       // [S][ceil(B / 64)] operand rows of the d fc22 generator (mvn_dwprep_kernel), or null
   uint32_t* eps_split;       // [S*B + pad][K] the draws as fp16 (hi, lo) pair words (K % 4 == 0; see split_pair), or null
   float* eps_out;            // [S*B][K] the draws (for the backward pass and for parity tests), or null
   float* logdet_out;         // [B] sum_i log L_ii, or null
@@ -58,6 +59,7 @@ size_t mvn_wimg_bytes(int K, int H);
 size_t mvn_wimgb_bytes(int K, int H);
 size_t mvn_dwpart_bytes(int K, int H);
 size_t mvn_himg_bytes(int64_t B, int H);
+size_t mvn_vimg_bytes(int64_t B, int K, int S);
 size_t mvn_eps_bytes(int64_t B, int K, int S);
 
 }  // namespace vipsy
