@@ -820,6 +820,11 @@ constexpr int kDwMaxRows = 4;              // block rows of L that a slab of <= 
 constexpr int kDwAStages = 3;              // V^T chunks in tensor memory: 3 x (32 hi + 32 lo) columns at 320..511
 constexpr uint32_t kDwACol = 512 - 64 * kDwAStages;
 constexpr uint32_t kDwGRec = 512;          // per row i of a tile: [g hi | g lo | diag hi | diag lo], 64 persons x fp16 each
+constexpr int kDwGenWarps = 16;            // generator warps: 4 per TMEM lane quadrant, 16 persons of the tile each
+constexpr int kDwThreads = kDwGenWarps * 32 + 64;    // + bulk-copy producer warp + MMA warp
+constexpr int kDwPH = kDwGenWarps / 4;     // person groups per tile
+constexpr int kDwPPT = kDwTP / kDwPH;      // persons per generator thread
+constexpr int kDwFG = (5 + kDwPH - 1) / kDwPH;       // groups of 16 accumulator columns per warp in a flush (KH <= 80)
 constexpr uint32_t kDwERec = 272;          // per column j of a tile: [eps hi | eps lo | 16 B pad] (pad: 8 columns -> 32 banks)
 __host__ __device__ inline int dw_cpb(int H) {                                     // chunks per CTA slab
   const int c = (int)kDwACol / mv_kh(H);
@@ -828,8 +833,10 @@ __host__ __device__ inline int dw_cpb(int H) {                                  
 __host__ __device__ inline size_t mv_himg_tile_bytes(int H) { return (size_t)2 * kDwTP * mv_kh(H) * 2; }
 __host__ __device__ inline size_t mv_vimg_tile_bytes(int K) { return (size_t)8 * mv_nb(K) * (kDwGRec + kDwERec); }
 
+constexpr int kDwBufs = 3;                 // step buffers ([hidden | 1] tile, draws, G rows): copies run two steps ahead
 struct DwSmem {
-  uint32_t offH, offE, offG, buf_bytes, total, h_bytes, e_bytes, g_bytes;
+  uint32_t offH, offE, offG, buf_bytes, offConst, total, h_bytes, e_bytes, g_bytes;
+  int nbuf;
 };
 __host__ __device__ inline DwSmem dw_smem(int K, int H) {
   DwSmem s;
@@ -840,7 +847,9 @@ __host__ __device__ inline DwSmem dw_smem(int K, int H) {
   s.offE = s.h_bytes;
   s.offG = s.offE + s.e_bytes;
   s.buf_bytes = (s.offG + s.g_bytes + 127) & ~127u;
-  s.total = 2 * s.buf_bytes;
+  s.nbuf = (227u * 1024u - 1024u) / s.buf_bytes >= (uint32_t)kDwBufs ? kDwBufs : 2;
+  s.offConst = (uint32_t)s.nbuf * s.buf_bytes;        // 512 B: a row of ones | zeros (fp16), then 256 B of zeros
+  s.total = s.offConst + 512;
   return s;
 }
 
@@ -875,47 +884,78 @@ __global__ void mvn_himg_kernel(const float* __restrict__ hidden, int64_t B, int
 __global__ void __launch_bounds__(256) mvn_dwprep_kernel(const MvnEncParams P, const float* __restrict__ eps_f32,
                                                           unsigned char* __restrict__ vimg) {
   const MirtParams& m = P.m;
-  const int K = m.K, K8 = 8 * mv_nb(K);
+  const int K = m.K, NB = mv_nb(K), K8 = 8 * NB;
   const int64_t n_tiles = (m.B + kDwTP - 1) / kDwTP;
   int gexp;
   frexpf(fmaxf(*P.gmax, m.scale), &gexp);
   const float ginv = ldexpf(1.f, 4 - gexp);
-  const int bp = threadIdx.x & 31, i0 = threadIdx.x >> 5;
+  // a warp = eight rows i (a block row of L), a lane = two persons: 32-byte pieces of their G / draw / diag L rows in,
+  // 128-byte row segments out
+  const int bp = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const bool vec = P.eps_split != nullptr;               // K % 4 == 0: whole 16-byte pieces
   for (int64_t step = blockIdx.x; step < n_tiles * m.S; step += gridDim.x) {
     const int s = (int)(step / n_tiles);
     const int64_t tile = step - (int64_t)s * n_tiles;
     unsigned char* grec = vimg + (size_t)step * mv_vimg_tile_bytes(K);
     unsigned char* erec = grec + (size_t)K8 * kDwGRec;
-    for (int i = i0; i < K8; i += 8) {
-      float g[2], e[2], vd[2];
-      __half eh[2], el[2];
+    for (int o = w; o < NB; o += 8) {
+      float g[2][8], e[2][8], l[2][8];
+      uint32_t ehw[2][4], elw[2][4];                       // the draws as fp16 pairs along i (hi / lo)
 #pragma unroll
       for (int q = 0; q < 2; ++q) {
         const int64_t b = tile * kDwTP + 2 * bp + q;
-        const bool live = b < m.B && i < K;
-        const int64_t row = ((int64_t)s * m.B + b) * K;
-        g[q] = live ? ginv * m.gx[row + i] : 0.f;
-        if (P.eps_split) {
-          const uint32_t Hw = live ? P.eps_split[row + 2 * (i >> 1)] : 0u, Lw = live ? P.eps_split[row + 2 * (i >> 1) + 1] : 0u;
-          eh[q] = __ushort_as_half((unsigned short)((i & 1) ? Hw >> 16 : Hw & 0xffffu));
-          el[q] = __ushort_as_half((unsigned short)((i & 1) ? Lw >> 16 : Lw & 0xffffu));
-          e[q] = __half2float(eh[q]) + __half2float(el[q]);
+        const int64_t row = ((int64_t)s * m.B + b) * K + 8 * o;
+        if (vec) {
+#pragma unroll
+          for (int h4 = 0; h4 < 2; ++h4) {
+            const bool ok = b < m.B && 8 * o + 4 * h4 < K;
+            const float4 gv = ok ? *reinterpret_cast<const float4*>(m.gx + row + 4 * h4) : make_float4(0.f, 0.f, 0.f, 0.f);
+            const float4 lv = ok ? *reinterpret_cast<const float4*>(m.diagL + b * K + 8 * o + 4 * h4) : make_float4(0.f, 0.f, 0.f, 0.f);
+            const uint4 ev = ok ? *reinterpret_cast<const uint4*>(P.eps_split + row + 4 * h4) : make_uint4(0u, 0u, 0u, 0u);
+            g[q][4 * h4] = gv.x; g[q][4 * h4 + 1] = gv.y; g[q][4 * h4 + 2] = gv.z; g[q][4 * h4 + 3] = gv.w;
+            l[q][4 * h4] = lv.x; l[q][4 * h4 + 1] = lv.y; l[q][4 * h4 + 2] = lv.z; l[q][4 * h4 + 3] = lv.w;
+            ehw[q][2 * h4] = ev.x; elw[q][2 * h4] = ev.y; ehw[q][2 * h4 + 1] = ev.z; elw[q][2 * h4 + 1] = ev.w;
+          }
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
+            const float2 hf = __half22float2(as_h2(ehw[q][t])), lf = __half22float2(as_h2(elw[q][t]));
+            e[q][2 * t] = hf.x + lf.x;
+            e[q][2 * t + 1] = hf.y + lf.y;
+          }
         } else {
-          e[q] = live ? eps_f32[row + i] : 0.f;
-          umma::split_f16(e[q], eh[q], el[q]);
+#pragma unroll
+          for (int t = 0; t < 8; ++t) {
+            const bool ok = b < m.B && 8 * o + t < K;
+            g[q][t] = ok ? m.gx[row + t] : 0.f;
+            l[q][t] = ok ? m.diagL[b * K + 8 * o + t] : 0.f;
+            e[q][t] = ok ? eps_f32[row + t] : 0.f;
+          }
+#pragma unroll
+          for (int t = 0; t < 4; ++t) split_pair(e[q][2 * t], e[q][2 * t + 1], ehw[q][t], elw[q][t]);
         }
-        const float lii = live ? m.diagL[b * K + i] : 0.f;
-        vd[q] = fmaf(g[q] * e[q], lii, (live && s == 0) ? -m.scale * ginv : 0.f);
       }
-      uint32_t w[6];
-      split_pair(g[0], g[1], w[0], w[1]);
-      split_pair(vd[0], vd[1], w[2], w[3]);
-      w[4] = (uint32_t)__half_as_ushort(eh[0]) | ((uint32_t)__half_as_ushort(eh[1]) << 16);
-      w[5] = (uint32_t)__half_as_ushort(el[0]) | ((uint32_t)__half_as_ushort(el[1]) << 16);
-      uint32_t* gr = reinterpret_cast<uint32_t*>(grec + (size_t)i * kDwGRec) + bp;
-      gr[0] = w[0]; gr[32] = w[1]; gr[64] = w[2]; gr[96] = w[3];
-      uint32_t* er = reinterpret_cast<uint32_t*>(erec + (size_t)i * kDwERec) + bp;
-      er[0] = w[4]; er[32] = w[5];
+#pragma unroll
+      for (int t = 0; t < 8; ++t) {
+        const int i = 8 * o + t;
+        float gg[2], vd[2];
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          const bool live = tile * kDwTP + 2 * bp + q < m.B && i < K;
+          gg[q] = ginv * g[q][t];
+          vd[q] = fmaf(gg[q] * e[q][t], l[q][t], (live && s == 0) ? -m.scale * ginv : 0.f);
+        }
+        uint32_t wv[4];
+        split_pair(gg[0], gg[1], wv[0], wv[1]);
+        split_pair(vd[0], vd[1], wv[2], wv[3]);
+        // the two persons' halves of element t: low / high half of word t >> 1
+        const uint32_t sh = (t & 1) ? 16u : 0u;
+        const uint32_t eh = ((ehw[0][t >> 1] >> sh) & 0xffffu) | (((ehw[1][t >> 1] >> sh) & 0xffffu) << 16);
+        const uint32_t el = ((elw[0][t >> 1] >> sh) & 0xffffu) | (((elw[1][t >> 1] >> sh) & 0xffffu) << 16);
+        uint32_t* gr = reinterpret_cast<uint32_t*>(grec + (size_t)i * kDwGRec) + bp;
+        gr[0] = wv[0]; gr[32] = wv[1]; gr[64] = wv[2]; gr[96] = wv[3];
+        uint32_t* er = reinterpret_cast<uint32_t*>(erec + (size_t)i * kDwERec) + bp;
+        er[0] = eh; er[32] = el;
+      }
     }
   }
 }
@@ -936,10 +976,10 @@ __device__ __forceinline__ void gen_pairs(const uint4& gh, const uint4& gl, cons
   one(gh.w, gl.w, eh.w, el.w, vh[3], vl[3]);
 }
 
-__global__ void __launch_bounds__(kBwThreads, 1) mvn_bwd_dw_kernel(const MvnEncParams P, const unsigned char* __restrict__ vimg,
+__global__ void __launch_bounds__(kDwThreads, 1) mvn_bwd_dw_kernel(const MvnEncParams P, const unsigned char* __restrict__ vimg,
                                                                     const int n_pg, const int n_qg) {
   extern __shared__ __align__(128) unsigned char smem[];
-  __shared__ uint64_t bar_efull[2], bar_tfree[2], bar_vfull[kDwAStages], bar_vfree[kDwAStages], bar_done, bar_drained;
+  __shared__ uint64_t bar_efull[kDwBufs], bar_tfree[kDwBufs], bar_vfull[kDwAStages], bar_vfree[kDwAStages], bar_done, bar_drained;
   __shared__ uint32_t tmem_base_sm;
   __shared__ int utab[8][2];                          // (I, Jc) of the slab's units; I >= NB: beyond the factor
   const MirtParams& m = P.m;
@@ -958,17 +998,21 @@ __global__ void __launch_bounds__(kBwThreads, 1) mvn_bwd_dw_kernel(const MvnEncP
   const float gfix = ldexpf(1.f, gexp - 4);
 
   if (tid == 0) {
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < kDwBufs; ++i) {
       umma::mbar_init(&bar_efull[i], 3);               // three bulk copies per step: [hidden | 1], draws, G rows
-      umma::mbar_init(&bar_tfree[i], kBwGenWarps + 1);
+      umma::mbar_init(&bar_tfree[i], kDwGenWarps + 1);
     }
     for (int i = 0; i < kDwAStages; ++i) {
-      umma::mbar_init(&bar_vfull[i], kBwGenWarps);
+      umma::mbar_init(&bar_vfull[i], kDwGenWarps);
       umma::mbar_init(&bar_vfree[i], 1);
     }
     umma::mbar_init(&bar_done, 1);
-    umma::mbar_init(&bar_drained, 4);
+    umma::mbar_init(&bar_drained, kDwGenWarps);
     umma::fence_mbar_init();
+  }
+  if (tid < 128) {                                     // constant rows: 64 x 1.0 | 64 x 0 (fp16), then 256 B of zeros
+    uint32_t* cr = reinterpret_cast<uint32_t*>(smem + L.offConst);
+    cr[tid] = tid < 32 ? 0x3c003c00u : 0u;
   }
   if (tid < 2 * nblk) {
     int I, Jc;
@@ -976,7 +1020,7 @@ __global__ void __launch_bounds__(kBwThreads, 1) mvn_bwd_dw_kernel(const MvnEncP
     utab[tid][0] = 2 * c0 + tid < NU ? I : NB;
     utab[tid][1] = Jc;
   }
-  if (warp == kBwGenWarps + 1) umma::tmem_alloc(&tmem_base_sm, 512);
+  if (warp == kDwGenWarps + 1) umma::tmem_alloc(&tmem_base_sm, 512);
   umma::fence_before_sync();
   __syncthreads();
   umma::fence_after_sync();
@@ -985,14 +1029,15 @@ __global__ void __launch_bounds__(kBwThreads, 1) mvn_bwd_dw_kernel(const MvnEncP
   const int I_last = utab[2 * nblk - 1][0] < NB ? utab[2 * nblk - 1][0] : NB - 1;
   const int n_rows = I_last - I_first + 1;             // block rows of the slab (<= kDwMaxRows)
   const uint32_t e_copy = (uint32_t)(8 * (I_last + 1)) * kDwERec, g_copy = (uint32_t)(8 * n_rows) * kDwGRec;
+  const int64_t NBUF = L.nbuf;
 
-  if (warp == kBwGenWarps) {
+  if (warp == kDwGenWarps) {
     // bulk-copy producer: [hidden | 1] tile, the columns of the draws and the rows of G this slab needs, of step n
     for (int64_t n = 0; n < n_steps; ++n) {
-      const uint32_t buf = (uint32_t)(n & 1);
+      const uint32_t buf = (uint32_t)(n % NBUF);
       const int64_t tile = qg + (n / S) * n_qg;
       const int s = (int)(n % S);
-      umma::mbar_wait(&bar_tfree[buf], (uint32_t)(((n >> 1) & 1) ^ 1));
+      umma::mbar_wait(&bar_tfree[buf], (uint32_t)(((n / NBUF) & 1) ^ 1));
       if (umma::elect_one()) {
         unsigned char* dst = smem + (size_t)buf * L.buf_bytes;
         const unsigned char* src = vimg + (size_t)((int64_t)s * n_tiles + tile) * mv_vimg_tile_bytes(K);
@@ -1002,15 +1047,15 @@ __global__ void __launch_bounds__(kBwThreads, 1) mvn_bwd_dw_kernel(const MvnEncP
       }
       __syncwarp();
     }
-  } else if (warp == kBwGenWarps + 1) {
+  } else if (warp == kDwGenWarps + 1) {
     // MMA issuer: a whole-warp loop, issue under elect_one()
     const uint32_t idesc = umma::make_idesc_f16(kMvCN, KH, umma::kMajorK, umma::kMajorMN);
     const uint64_t dH0 = umma::make_desc(umma::smem_u32(smem + L.offH), RSH, kCSb);     // [hidden | 1]: MN-major B
     uint32_t it = 0, nflush = 0;
     bool fresh = true;                                 // the accumulators hold nothing yet (start, or just flushed)
     for (int64_t n = 0; n < n_steps; ++n) {
-      const uint32_t buf = (uint32_t)(n & 1);
-      umma::mbar_wait(&bar_efull[buf], (uint32_t)((n >> 1) & 1));
+      const uint32_t buf = (uint32_t)(n % NBUF);
+      umma::mbar_wait(&bar_efull[buf], (uint32_t)((n / NBUF) & 1));
       for (int k = 0; k < nblk; ++k, ++it) {
         const uint32_t vb = it % kDwAStages;
         umma::mbar_wait(&bar_vfull[vb], (it / kDwAStages) & 1);
@@ -1047,101 +1092,114 @@ __global__ void __launch_bounds__(kBwThreads, 1) mvn_bwd_dw_kernel(const MvnEncP
       }
     }
   } else {
-    // generators: thread = factor column c of the chunk (its TMEM lane) x half of the tile's persons
-    const int q4 = warp & 3, hp = warp >> 2;
+    // generators: thread = factor column c of the chunk (its TMEM lane) x half of the tile's persons.  The slab is
+    // fixed, so the rows a thread multiplies are fixed offsets into the step buffer, found once: its G row (or, on
+    // the diagonal of L, the prepared v_ii row against a row of ones; above the diagonal and beyond the factor a
+    // row of zeros) and its column of the draws -- the loop itself has no branches.
+    const int q4 = warp & 3, hp = warp >> 2;           // lane quadrant; persons kDwPPT hp .. of the tile
     const int half = q4 >> 1, r = 4 * (q4 & 1) + (lane >> 3), jj = lane & 7;
-    const uint32_t ta = tmem + ((uint32_t)(32 * q4) << 16) + kDwACol + 16u * (uint32_t)hp;
+    const uint32_t ta = tmem + ((uint32_t)(32 * q4) << 16) + kDwACol + (uint32_t)(kDwPPT / 2 * hp);
+    const uint32_t sbase = umma::smem_u32(smem);
+    uint32_t goff[4], eoff[4];                         // byte offsets; >= offConst: constant rows (not per buffer)
+    const uint32_t kConst = 0x80000000u;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int I = k < nblk ? utab[2 * k + half][0] : NB, Jc = k < nblk ? utab[2 * k + half][1] : 0;
+      uint32_t go = kConst | (L.offConst + 256u), eo = kConst | L.offConst;          // zeros
+      if (I < NB) {
+        const uint32_t grow = L.offG + (uint32_t)((I - I_first) * 8 + r) * kDwGRec + (uint32_t)(2 * kDwPPT * hp);
+        const uint32_t erow = L.offE + (uint32_t)(8 * Jc + jj) * kDwERec + (uint32_t)(2 * kDwPPT * hp);
+        if (Jc != I || jj < r) { go = grow; eo = erow; }
+        else if (jj == r) { go = grow + 256u; eo = kConst | L.offConst; }
+      }
+      goff[k] = go; eoff[k] = eo;
+    }
+    auto lds128 = [](uint32_t a) {
+      uint4 v;
+      asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+      return v;
+    };
     uint32_t it = 0, nflush = 0;
     for (int64_t n = 0; n < n_steps; ++n) {
-      const uint32_t buf = (uint32_t)(n & 1);
-      const unsigned char* Eb = smem + (size_t)buf * L.buf_bytes + L.offE + 64 * hp;
-      const unsigned char* Gb = smem + (size_t)buf * L.buf_bytes + L.offG + 64 * hp;
-      umma::mbar_wait(&bar_efull[buf], (uint32_t)((n >> 1) & 1));
-      for (int k = 0; k < nblk; ++k, ++it) {
-        const uint32_t vb = it % kDwAStages;
-        const int I = utab[2 * k + half][0], Jc = utab[2 * k + half][1];
-        uint32_t vh[16], vl[16];
-        if (I < NB) {                                  // warp-uniform
-          const unsigned char* grow = Gb + (size_t)((I - I_first) * 8 + r) * kDwGRec;
-          const unsigned char* erow = Eb + (size_t)(8 * Jc + jj) * kDwERec;
-          if (Jc == I && jj >= r) {                    // diagonal block: v_ii from the prepared row, zero above it
-            if (jj == r) {
+      const uint32_t buf = (uint32_t)(n % NBUF);
+      const uint32_t bb = sbase + buf * L.buf_bytes;
+      umma::mbar_wait(&bar_efull[buf], (uint32_t)((n / NBUF) & 1));
 #pragma unroll
-              for (int p8 = 0; p8 < 4; ++p8) {
-                const uint4 a = *reinterpret_cast<const uint4*>(grow + 256 + 16 * p8);
-                const uint4 b = *reinterpret_cast<const uint4*>(grow + 384 + 16 * p8);
-                vh[4 * p8] = a.x; vh[4 * p8 + 1] = a.y; vh[4 * p8 + 2] = a.z; vh[4 * p8 + 3] = a.w;
-                vl[4 * p8] = b.x; vl[4 * p8 + 1] = b.y; vl[4 * p8 + 2] = b.z; vl[4 * p8 + 3] = b.w;
-              }
-            } else {
+      for (int k = 0; k < 4; ++k) {
+        if (k < nblk) {
+          const uint32_t vb = it % kDwAStages;
+          const uint32_t ga = (goff[k] & kConst) ? sbase + (goff[k] & ~kConst) : bb + goff[k];
+          const uint32_t ea = (eoff[k] & kConst) ? sbase + (eoff[k] & ~kConst) : bb + eoff[k];
+          uint32_t vh[kDwPPT / 2], vl[kDwPPT / 2];
 #pragma unroll
-              for (int q = 0; q < 16; ++q) { vh[q] = 0u; vl[q] = 0u; }
-            }
-          } else {
-#pragma unroll
-            for (int p8 = 0; p8 < 4; ++p8) {
-              const uint4 gh = *reinterpret_cast<const uint4*>(grow + 16 * p8);
-              const uint4 gl = *reinterpret_cast<const uint4*>(grow + 128 + 16 * p8);
-              const uint4 eh = *reinterpret_cast<const uint4*>(erow + 16 * p8);
-              const uint4 el = *reinterpret_cast<const uint4*>(erow + 128 + 16 * p8);
-              gen_pairs(gh, gl, eh, el, vh + 4 * p8, vl + 4 * p8);
-            }
+          for (int p8 = 0; p8 < kDwPPT / 8; ++p8) {
+            // the constant rows are 128 B of one value: any 16-byte piece will do, so no person offset there
+            const uint32_t po = 16u * p8;
+            const uint4 gh = lds128(ga + ((goff[k] & kConst) ? 0u : po)), gl = lds128(ga + 128u + ((goff[k] & kConst) ? 0u : po));
+            const uint4 eh = lds128(ea + ((eoff[k] & kConst) ? 0u : po)), el = lds128(ea + 128u + ((eoff[k] & kConst) ? 0u : po));
+            gen_pairs(gh, gl, eh, el, vh + 4 * p8, vl + 4 * p8);
           }
-        } else {                                       // units beyond the factor (tail of the last chunk): zeros
-#pragma unroll
-          for (int q = 0; q < 16; ++q) { vh[q] = 0u; vl[q] = 0u; }
+          umma::mbar_wait(&bar_vfree[vb], ((it / kDwAStages) & 1) ^ 1);
+          umma::fence_after_sync();
+          umma::tmem_st8(ta + vb * 64, vh);
+          umma::tmem_st8(ta + vb * 64 + 32, vl);
+          umma::tmem_st_wait();
+          umma::fence_before_sync();
+          warp_arrive(&bar_vfull[vb], lane);
+          ++it;
         }
-        umma::mbar_wait(&bar_vfree[vb], ((it / kDwAStages) & 1) ^ 1);
-        umma::fence_after_sync();
-        umma::tmem_st16(ta + vb * 64, vh);
-        umma::tmem_st16(ta + vb * 64 + 32, vl);
-        umma::tmem_st_wait();
-        umma::fence_before_sync();
-        warp_arrive(&bar_vfull[vb], lane);
       }
       warp_arrive(&bar_tfree[buf], lane);              // done with this step's rows
       // Flush every kDwFlushTiles steps: the accumulators are added (round-to-nearest, fixed order) to this CTA's
       // partial rows, which bounds the chain of truncating tensor-core accumulations (see mvn_bwd_dh_kernel).
+      // Thread = factor column of the chunk = TMEM lane; the two warps of a lane quadrant take alternate groups of
+      // 16 columns, and the old partial sums are on their way before the accumulators are waited for.
       if ((n + 1) % kDwFlushTiles == 0 || n + 1 == n_steps) {
-        if (warp < 4) {                                // thread = factor column of the chunk = TMEM lane
-          const int t = tid;
-          umma::mbar_wait(&bar_done, nflush & 1);
-          umma::fence_after_sync();
-          const uint32_t tl = tmem + ((uint32_t)(warp * 32) << 16);
-          for (int k = 0; k < nblk; ++k) {
-            float* dst = P.dw_part + ((size_t)qg * n_chunks * kMvCN + (size_t)(c0 + k) * kMvCN + t) * KH;
-            for (int q0 = 0; q0 < KH; q0 += 16) {
+        const int t = 32 * q4 + lane;
+        const uint32_t tl = tmem + ((uint32_t)(q4 * 32) << 16);
+        bool waited = false;
+        for (int k = 0; k < nblk; ++k) {
+          // partial rows [qg][chunk][h][column]: for one h the warp's 32 columns are 128 contiguous bytes
+          float* dst = P.dw_part + ((size_t)qg * n_chunks + (size_t)(c0 + k)) * KH * kMvCN + t;
+          float old[kDwFG][16];
+#pragma unroll
+          for (int gi = 0; gi < kDwFG; ++gi) {
+            const int q0 = 16 * (kDwPH * gi + hp);
+#pragma unroll
+            for (int q = 0; q < 16; ++q) old[gi][q] = (nflush > 0 && q0 < KH) ? dst[(size_t)(q0 + q) * kMvCN] : 0.f;
+          }
+          if (!waited) {
+            umma::mbar_wait(&bar_done, nflush & 1);
+            umma::fence_after_sync();
+            waited = true;
+          }
+#pragma unroll
+          for (int gi = 0; gi < kDwFG; ++gi) {
+            const int q0 = 16 * (kDwPH * gi + hp);
+            if (q0 < KH) {
               float v[16];
               umma::tmem_ld16(tl + k * KH + q0, v);
 #pragma unroll
-              for (int q = 0; q < 4; ++q) {
-                float4 o = make_float4(v[4 * q] * gfix, v[4 * q + 1] * gfix, v[4 * q + 2] * gfix, v[4 * q + 3] * gfix);
-                float4* dp = reinterpret_cast<float4*>(dst + q0 + 4 * q);
-                if (nflush > 0) {
-                  const float4 old = *dp;
-                  o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
-                }
-                *dp = o;
-              }
+              for (int q = 0; q < 16; ++q) dst[(size_t)(q0 + q) * kMvCN] = fmaf(v[q], gfix, old[gi][q]);
             }
           }
-          umma::fence_before_sync();
-          warp_arrive(&bar_drained, lane);
         }
+        umma::fence_before_sync();
+        warp_arrive(&bar_drained, lane);
         ++nflush;
       }
     }
     if (n_steps == 0 && warp < 4) {                    // a CTA without persons still owns its partial rows
       for (int k = 0; k < nblk; ++k) {
-        float* dst = P.dw_part + ((size_t)qg * n_chunks * kMvCN + (size_t)(c0 + k) * kMvCN + tid) * KH;
-        for (int q = 0; q < KH; ++q) dst[q] = 0.f;
+        float* dst = P.dw_part + ((size_t)qg * n_chunks + (size_t)(c0 + k)) * KH * kMvCN + tid;
+        for (int q = 0; q < KH; ++q) dst[(size_t)q * kMvCN] = 0.f;
       }
     }
   }
   umma::fence_before_sync();
   __syncthreads();
   umma::fence_after_sync();
-  if (warp == kBwGenWarps + 1) umma::tmem_dealloc(tmem, 512);
+  if (warp == kDwGenWarps + 1) umma::tmem_dealloc(tmem, 512);
 }
 
 // d_w22[p][h], d_b22[p] = sum over the person groups, in order, of the partial rows of padded column mv_col(i, j)
@@ -1156,7 +1214,7 @@ __global__ void mvn_dw_finalize_kernel(const float* __restrict__ part, int n_qg,
     const int j = p - tri_off(i);
     const size_t pc = (size_t)mv_col(i, j);
     float t = 0.f;
-    for (int q = 0; q < n_qg; ++q) t += part[((size_t)q * n_cols + pc) * KH + h];
+    for (int q = 0; q < n_qg; ++q) t += part[((size_t)q * n_cols + (pc & ~size_t(kMvCN - 1))) * KH + (size_t)h * kMvCN + (pc & (kMvCN - 1))];
     if (h < H) { if (d_w22) d_w22[(size_t)p * H + h] = t; }
     else if (d_b22) d_b22[p] = t;
   }
@@ -1237,7 +1295,7 @@ int launch_mvn_bwd(const MvnEncParams& P, cudaStream_t st) {
     int n_pg, n_qg;
     dw_grid(K, H, &n_pg, &n_qg);
     if (n_qg > n_tiles64) n_qg = (int)n_tiles64;
-    mvn_bwd_dw_kernel<<<n_pg * n_qg, kBwThreads, L.total, st>>>(P, P.vimg, n_pg, n_qg);
+    mvn_bwd_dw_kernel<<<n_pg * n_qg, kDwThreads, L.total, st>>>(P, P.vimg, n_pg, n_qg);
     VIPSY_CUDA_CHECK(cudaGetLastError());
     const int total = K * (K + 1) / 2 * (H + 1);
     mvn_dw_finalize_kernel<<<(total + 255) / 256, 256, 0, st>>>(P.dw_part, n_qg, mv_chunks(K) * kMvCN, K, H, mv_kh(H),

@@ -43,7 +43,7 @@ struct MvnEncParams {
   uint32_t* eps_split;       // [S*B + pad][K] the draws as fp16 (hi, lo) pair words (K % 4 == 0; see split_pair), or null
   float* eps_out;            // [S*B][K] the draws (for the backward pass and for parity tests), or null
   float* logdet_out;         // [B] sum_i log L_ii, or null
-  float* dw_part;            // [n_qg][PP][KH]
+  float* dw_part;            // [n_qg][chunk][KH][128 columns of the chunk]
   float* gmax;               // device scalar: max |G| of the step (power-of-two normalisation of the fp16 operand V)
   float* d_hidden;           // outputs
   float* d_w22;
