@@ -208,7 +208,8 @@ size_t vipsy_irt_mvn_encoder_workspace_bytes(const VipsyMvnEncoderIrtArgs* args)
 /* loss + every gradient (NULL gradient pointers: the value only, evaluate_loss) */
 int vipsy_irt_mvn_encoder_elbo_grad(const VipsyMvnEncoderIrtArgs* args, void* stream);
 /* The guide's sample site alone (vi.py:693): x [S][B][K] = loc + L eps, the draws eps [S][B][K], diag L [B][K]
- * and logdet [B] = sum_i log L_ii.  Any output may be NULL.  Uses args->workspace like the full entry. */
+ * and logdet [B] = sum_i log L_ii.  x, diag and logdet may be NULL; eps_out only with injected noise (the library's own
+ * draws need a home).  Uses args->workspace like the full entry. */
 int vipsy_mvn_encoder_sample(const VipsyMvnEncoderIrtArgs* args, float* x, float* eps_out, float* diag, float* logdet,
                              void* stream);
 

@@ -23,7 +23,7 @@ namespace vipsy {
 namespace {
 
 constexpr uint32_t kCSb = 128;                 // byte stride between core matrices along the contiguous dimension
-constexpr int kFwEpiWarps = 4;                 // warps 0-3: epilogue (TMEM lane quadrant = warp)
+constexpr int kFwEpiWarps = 8;                 // warps 0-7: epilogue, two per TMEM lane quadrant (warp & 3), one unit of a chunk each
 constexpr int kFwThreads = (kFwEpiWarps + 2) * 32;   // + warp 4: bulk-copy producer, warp 5: MMA issuer
 constexpr int kFwTmemBufs = 3;                 // 3 x 128 accumulator columns; columns 384.. : the [hidden | 1] operand
 constexpr uint32_t kFwACol = 384;              // A operand in tensor memory: KH / 2 words of fp16 hi pairs, then KH / 2 of lo
@@ -165,8 +165,9 @@ __global__ void mvn_prep_kernel(const float* __restrict__ w22, const float* __re
 }
 
 // ------------------------------------------------------------------------------------------------ forward
+constexpr uint32_t kFwXchBytes = (2 * 8 + 1) * kMvTP * 4;     // partial row sums [parity][r][person] + log det [person]
 struct FwSmem {
-  uint32_t offW, offEps, total;
+  uint32_t offW, offEps, offX, total;
   uint32_t chunk_bytes;
   int nst, ES;
 };
@@ -174,7 +175,7 @@ __host__ __device__ inline FwSmem fw_smem(int K, int H) {
   FwSmem s;
   s.chunk_bytes = (uint32_t)mv_chunk_bytes(H);
   s.ES = (K + 7) / 8 * 8 + 4;
-  const uint32_t fixed = (uint32_t)kMvTP * s.ES * 4;
+  const uint32_t fixed = (uint32_t)kMvTP * s.ES * 4 + kFwXchBytes;
   const uint32_t cap = 227 * 1024 - 1024;
   int nst = (int)((cap - fixed) / s.chunk_bytes);
   if (nst > 4) nst = 4;
@@ -182,6 +183,7 @@ __host__ __device__ inline FwSmem fw_smem(int K, int H) {
   uint32_t o = 0;
   s.offW = o; o += (uint32_t)(nst > 0 ? nst : 0) * s.chunk_bytes;
   s.offEps = o; o += (uint32_t)kMvTP * s.ES * 4;
+  s.offX = o; o += kFwXchBytes;
   s.total = o;
   return s;
 }
@@ -218,6 +220,45 @@ __device__ __forceinline__ float fill_noise_row(const MirtParams& m, int s, int6
     }
   }
   return ss;
+}
+
+// The draws of the step, once, ahead of the forward kernel (the library's Philox stream: same coordinates as every
+// other kernel): [S*B][K] fp32 (eps_out) or fp16 (hi, lo) pair words (eps_split, K % 4 == 0).  A thread fills the
+// row of its person in shared memory, a warp writes its 32 rows with whole-line stores.  Inside the forward kernel
+// this work (~1600 instructions per person) sat in front of every tile's first MMA.
+constexpr int kNzThreads = 128;
+__global__ void __launch_bounds__(kNzThreads) mvn_noise_kernel(const MvnEncParams P) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  const MirtParams& m = P.m;
+  const int K = m.K, ES = K + 1;                       // odd pitch: the transposed reads below are conflict-free
+  float* rows = reinterpret_cast<float*>(smem);
+  const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+  const int64_t n_tiles = (m.B + kNzThreads - 1) / kNzThreads;
+  for (int64_t step = blockIdx.x; step < n_tiles * m.S; step += gridDim.x) {
+    const int s = (int)(step / n_tiles);
+    const int64_t tile = step - (int64_t)s * n_tiles;
+    const int64_t b = tile * kNzThreads + t;
+    fill_noise_row(m, s, b < m.B ? b : 0, rows + (size_t)t * ES, 1.f);
+    __syncwarp();
+    const int64_t b0 = tile * kNzThreads + warp * 32;
+    const float* e0 = rows + (size_t)(warp * 32) * ES;
+    if (P.eps_split) {
+      for (int pp = 0; pp < 32 && b0 + pp < m.B; ++pp) {
+        uint2* dst = reinterpret_cast<uint2*>(P.eps_split + ((int64_t)s * m.B + b0 + pp) * K);
+        for (int mm = lane; mm < K / 2; mm += 32) {
+          uint2 w;
+          split_pair(e0[(size_t)pp * ES + 2 * mm], e0[(size_t)pp * ES + 2 * mm + 1], w.x, w.y);
+          dst[mm] = w;
+        }
+      }
+    } else {
+      for (int pp = 0; pp < 32 && b0 + pp < m.B; ++pp) {
+        float* dst = P.eps_out + ((int64_t)s * m.B + b0 + pp) * K;
+        for (int k = lane; k < K; k += 32) dst[k] = e0[(size_t)pp * ES + k];
+      }
+    }
+    __syncwarp();
+  }
 }
 
 __global__ void __launch_bounds__(kFwThreads, 1) mvn_fwd_kernel(const MvnEncParams P) {
@@ -284,6 +325,7 @@ __global__ void __launch_bounds__(kFwThreads, 1) mvn_fwd_kernel(const MvnEncPara
             for (int ks = 0; ks < KH / 16; ++ks) {
 #pragma unroll
               for (int term = 0; term < 3; ++term) {            // hi*hi, hi*lo, lo*hi
+                if (term == 2 && 16 * ks >= H) continue;        // only the ones column and padding: the lo part is 0
                 const uint64_t db = umma::make_desc((term == 1 ? sWl : sWh) + ks * 2 * kCSb, kCSb, RS);
                 umma::mma_f16_ts(tmem + buf * kMvCN, (term == 2 ? aL : aH) + 8 * ks, db, idesc, acc);
                 acc = 1;
@@ -297,44 +339,62 @@ __global__ void __launch_bounds__(kFwThreads, 1) mvn_fwd_kernel(const MvnEncPara
     }
   } else {
     // =========================== epilogue: thread = person = TMEM lane =========================================
-    const int t = tid;                                   // 0..127
+    // Two warps per lane quadrant (a lone warp per scheduler issues at a quarter of the rate): warp `half` takes unit
+    // `half` of every chunk.  A block row of L ends with its diagonal unit; the warp that holds that unit finishes
+    // the row, the other one hands over its partial sums through shared memory right after the unit before it.
+    const int quad = warp & 3, half = warp >> 2;
+    const int t = quad * 32 + lane;                      // person of the tile = TMEM lane
     float* er = eps_s + (size_t)t * ES;
-    const uint32_t tlane = tmem + ((uint32_t)(warp * 32) << 16);
+    float* xch = reinterpret_cast<float*>(smem + L.offX);
+    const uint32_t tlane = tmem + ((uint32_t)(quad * 32) << 16);
     const float inv_scale = 1.0f / kMvWScale;
+    auto pair_sync = [&]() { asm volatile("bar.sync %0, 64;" ::"r"(1 + quad) : "memory"); };
     uint32_t it = 0;
-    for (int k = K; k < ES; ++k) er[k] = 0.f;            // padding columns of a row's last group: finite, weight 0
+    if (half == 0)
+      for (int k = K; k < ES; ++k) er[k] = 0.f;          // padding columns of a row's last group: finite, weight 0
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
       const int64_t b = tile * kMvTP + t;
       const bool live = b < m.B;
       // ---- [hidden | 1 | 0] row of this person -> fp16 hi / lo words of the A operand in tensor memory ------------
-      // (every MMA of the previous tile has completed: this thread has consumed its last accumulator)
+      // (every MMA of the previous tile has completed: both warps have consumed their last accumulator)
       {
         const float* hr = P.hidden + (live ? b : 0) * H;
         const bool vec = (H & 3) == 0;
-        for (int o2 = 0; o2 < KH / 16; ++o2) {           // a k-step: 16 elements = 8 words
-          uint32_t h8[8], l8[8];
+        float hv[3][16];                                 // this warp's k-steps (at most 3 of 5), every load in flight first
 #pragma unroll
-          for (int half = 0; half < 2; ++half) {
-            const int o = 2 * o2 + half;
-            float v[8];
-            if (vec && live && o * 8 + 8 <= H) {
-              const float4 a0 = *reinterpret_cast<const float4*>(hr + o * 8);
-              const float4 a1 = *reinterpret_cast<const float4*>(hr + o * 8 + 4);
-              v[0] = a0.x; v[1] = a0.y; v[2] = a0.z; v[3] = a0.w; v[4] = a1.x; v[5] = a1.y; v[6] = a1.z; v[7] = a1.w;
+        for (int q2 = 0; q2 < 3; ++q2) {
+          const int o2 = half + 2 * q2;
+#pragma unroll
+          for (int q = 0; q < 16; q += 4) {
+            const int k = 16 * o2 + q;
+            if (o2 < KH / 16 && vec && live && k + 4 <= H) {
+              const float4 a0 = *reinterpret_cast<const float4*>(hr + k);
+              hv[q2][q] = a0.x; hv[q2][q + 1] = a0.y; hv[q2][q + 2] = a0.z; hv[q2][q + 3] = a0.w;
             } else {
 #pragma unroll
-              for (int q = 0; q < 8; ++q) {
-                const int k = o * 8 + q;
-                v[q] = !live ? 0.f : (k < H ? hr[k] : (k == H ? 1.f : 0.f));
-              }
+              for (int e = 0; e < 4; ++e)
+                hv[q2][q + e] = (o2 >= KH / 16 || !live) ? 0.f : (k + e < H ? hr[k + e] : (k + e == H ? 1.f : 0.f));
             }
-            uint4 hi, lo;
-            split8(v, hi, lo);
-            h8[4 * half] = hi.x; h8[4 * half + 1] = hi.y; h8[4 * half + 2] = hi.z; h8[4 * half + 3] = hi.w;
-            l8[4 * half] = lo.x; l8[4 * half + 1] = lo.y; l8[4 * half + 2] = lo.z; l8[4 * half + 3] = lo.w;
           }
-          umma::tmem_st8(tlane + kFwACol + 8 * o2, h8);
-          umma::tmem_st8(tlane + kFwACol + (uint32_t)(KH / 2) + 8 * o2, l8);
+        }
+#pragma unroll
+        for (int q2 = 0; q2 < 3; ++q2) {
+          const int o2 = half + 2 * q2;                  // a k-step: 16 elements = 8 words
+          if (o2 < KH / 16) {
+            uint32_t h8[8], l8[8];
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {
+              float v[8];
+#pragma unroll
+              for (int q = 0; q < 8; ++q) v[q] = hv[q2][8 * hh + q];
+              uint4 hi, lo;
+              split8(v, hi, lo);
+              h8[4 * hh] = hi.x; h8[4 * hh + 1] = hi.y; h8[4 * hh + 2] = hi.z; h8[4 * hh + 3] = hi.w;
+              l8[4 * hh] = lo.x; l8[4 * hh + 1] = lo.y; l8[4 * hh + 2] = lo.z; l8[4 * hh + 3] = lo.w;
+            }
+            umma::tmem_st8(tlane + kFwACol + 8 * o2, h8);
+            umma::tmem_st8(tlane + kFwACol + (uint32_t)(KH / 2) + 8 * o2, l8);
+          }
         }
         umma::tmem_st_wait();
         umma::fence_before_sync();
@@ -342,109 +402,140 @@ __global__ void __launch_bounds__(kFwThreads, 1) mvn_fwd_kernel(const MvnEncPara
       }
       float logdet = 0.f, auxp = 0.f;
       for (int s = 0; s < S; ++s) {
-        const float ss = fill_noise_row(m, s, live ? b : 0, er, inv_scale);
-        if (P.eps_out) {                      // the warp's 32 rows leave through coalesced stores
-          __syncwarp();
-          const int64_t b0 = tile * kMvTP + warp * 32;
-          const float* e0 = eps_s + (size_t)(warp * 32) * ES;
-          for (int pp = 0; pp < 32 && b0 + pp < m.B; ++pp) {
-            float* dst = P.eps_out + ((int64_t)s * m.B + b0 + pp) * K;
-            for (int k = lane; k < K; k += 32) dst[k] = e0[(size_t)pp * ES + k] * kMvWScale;
-          }
-          __syncwarp();
-        }
-        if (P.eps_split) {                    // the same rows as fp16 (hi, lo) pair words for the backward kernels
-          __syncwarp();
-          const int64_t b0 = tile * kMvTP + warp * 32;
-          const float* e0 = eps_s + (size_t)(warp * 32) * ES;
-          for (int pp = 0; pp < 32 && b0 + pp < m.B; ++pp) {
-            uint2* dst = reinterpret_cast<uint2*>(P.eps_split + ((int64_t)s * m.B + b0 + pp) * K);
-            for (int mm = lane; mm < K / 2; mm += 32) {
-              uint2 w;
-              split_pair(e0[(size_t)pp * ES + 2 * mm] * kMvWScale, e0[(size_t)pp * ES + 2 * mm + 1] * kMvWScale, w.x, w.y);
-              dst[mm] = w;
+        pair_sync();                                     // the partner has finished with the previous draws
+        // the person's draws (mvn_noise_kernel, or injected) -> its row in shared memory, prescaled; half a row per warp
+        float ss = 0.f;
+        {
+          const int64_t row = ((int64_t)s * m.B + (live ? b : 0)) * K;
+          const int kh = (K / 2 + 3) & ~3;               // split point: a multiple of 4
+          const int k0 = half ? kh : 0, k1 = half ? K : (kh < K ? kh : K);
+          if (P.eps_split && !m.eps) {                   // K % 4 == 0: whole 16-byte pieces = 4 draws
+            for (int kk = k0; kk < k1; kk += 32) {       // eight pieces in flight before the first one is used
+              uint4 w[8];
+#pragma unroll
+              for (int q = 0; q < 8; ++q)
+                w[q] = kk + 4 * q < k1 ? *reinterpret_cast<const uint4*>(P.eps_split + row + kk + 4 * q) : make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+              for (int q = 0; q < 8; ++q) {
+                if (kk + 4 * q < k1) {
+                  const float2 h0 = __half22float2(as_h2(w[q].x)), l0 = __half22float2(as_h2(w[q].y));
+                  const float2 h1 = __half22float2(as_h2(w[q].z)), l1 = __half22float2(as_h2(w[q].w));
+                  const float z0 = h0.x + l0.x, z1 = h0.y + l0.y, z2 = h1.x + l1.x, z3 = h1.y + l1.y;
+                  ss = fmaf(z0, z0, fmaf(z1, z1, fmaf(z2, z2, fmaf(z3, z3, ss))));
+                  *reinterpret_cast<float4*>(er + kk + 4 * q) = make_float4(z0 * inv_scale, z1 * inv_scale, z2 * inv_scale, z3 * inv_scale);
+                }
+              }
+            }
+          } else {
+            const float* src = (m.eps ? m.eps : P.eps_out) + row;
+            for (int k = k0; k < k1; ++k) {
+              const float z = src[k];
+              ss = fmaf(z, z, ss);
+              er[k] = z * inv_scale;
             }
           }
-          __syncwarp();
         }
+        pair_sync();                                     // both halves of the row are in place
         auxp = fmaf(0.5f, ss, auxp);
         const float* mur = m.mu + (live ? b : 0) * K;
         float* xr = m.x ? m.x + ((int64_t)s * m.B + (live ? b : 0)) * K : nullptr;
-        int I = 0, Jc = 0;
-        float acc[8], mu_r[8];                                   // mu of the current block row, fetched a block row ahead
+        int I = half, Jc = 0;                            // unit `half` of chunk 0: (0, 0) or (1, 0)
+        int ug = half;                                   // its index in the order of the units
+        float acc[8];
 #pragma unroll
-        for (int r = 0; r < 8; ++r) { acc[r] = 0.f; mu_r[r] = r < K ? mur[r] : 0.f; }
+        for (int r = 0; r < 8; ++r) acc[r] = 0.f;
         for (int c = 0; c < n_chunks; ++c, ++it) {
           const uint32_t buf = it % kFwTmemBufs, tround = it / kFwTmemBufs;
           umma::mbar_wait(&bar_tfull[buf], tround & 1);
           umma::fence_after_sync();
-#pragma unroll 1
-          for (int u = 0; u < kMvCN / 64; ++u) {
-            if (I < NB) {                                        // warp-uniform
-              float v[64];
-              umma::tmem_ld64(tlane + buf * kMvCN + u * 64, v);
-              const float4 e0 = *reinterpret_cast<const float4*>(er + 8 * Jc);
-              const float4 e1 = *reinterpret_cast<const float4*>(er + 8 * Jc + 4);
+          if (I < NB) {                                          // warp-uniform
+            const bool diag = Jc == I;
+            float mu_r[8];
+            if (diag) {
+#pragma unroll
+              for (int r = 0; r < 8; ++r) mu_r[r] = 8 * I + r < K ? mur[8 * I + r] : 0.f;
+            }
+            float v[64];
+            umma::tmem_ld64(tlane + buf * kMvCN + half * 64, v);
+            const float4 e0v = *reinterpret_cast<const float4*>(er + 8 * Jc);
+            const float4 e1v = *reinterpret_cast<const float4*>(er + 8 * Jc + 4);
+#pragma unroll
+            for (int r = 0; r < 8; ++r) {
+              float d0 = v[8 * r] * e0v.x, d1 = v[8 * r + 4] * e1v.x;
+              d0 = fmaf(v[8 * r + 1], e0v.y, d0); d1 = fmaf(v[8 * r + 5], e1v.y, d1);
+              d0 = fmaf(v[8 * r + 2], e0v.z, d0); d1 = fmaf(v[8 * r + 6], e1v.z, d1);
+              d0 = fmaf(v[8 * r + 3], e0v.w, d0); d1 = fmaf(v[8 * r + 7], e1v.w, d1);
+              acc[r] += d0 + d1;
+            }
+            float* xs = xch + (size_t)((I & 1) * 8) * kMvTP + t;
+            if (diag) {                                         // rows 8I .. 8I+7 are complete once the partner's share is in
+              if (I > 0) {
+                pair_sync();
+#pragma unroll
+                for (int r = 0; r < 8; ++r) acc[r] += xs[r * kMvTP];
+              }
+              const float ev[8] = {e0v.x, e0v.y, e0v.z, e0v.w, e1v.x, e1v.y, e1v.z, e1v.w};
+              float xo[8], lo8[8];
 #pragma unroll
               for (int r = 0; r < 8; ++r) {
-                float d0 = v[8 * r] * e0.x, d1 = v[8 * r + 4] * e1.x;
-                d0 = fmaf(v[8 * r + 1], e0.y, d0); d1 = fmaf(v[8 * r + 5], e1.y, d1);
-                d0 = fmaf(v[8 * r + 2], e0.z, d0); d1 = fmaf(v[8 * r + 6], e1.z, d1);
-                d0 = fmaf(v[8 * r + 3], e0.w, d0); d1 = fmaf(v[8 * r + 7], e1.w, d1);
-                acc[r] += d0 + d1;
-              }
-              if (Jc == I) {                                      // diagonal block: rows 8I .. 8I+7 are complete
-                const float ev[8] = {e0.x, e0.y, e0.z, e0.w, e1.x, e1.y, e1.z, e1.w};
-                float xo[8], lo8[8];
-#pragma unroll
-                for (int r = 0; r < 8; ++r) {
-                  const int i = 8 * I + r;
-                  const float dv = v[9 * r];                     // 64 raw_ii
-                  const float dr = dv * inv_scale;
-                  const float lii = __expf(dr);
-                  const float xv = mu_r[r] + fmaf(lii * kMvWScale - dv, ev[r], acc[r]);    // exp(raw_ii) eps_i for raw_ii eps_i
-                  xo[r] = xv; lo8[r] = lii;
-                  if (i < K) {
-                    auxp = fmaf(-0.5f * xv, xv, auxp);
-                    if (s == 0) logdet += dr;
-                  }
-                  acc[r] = 0.f;
-                  mu_r[r] = i + 8 < K ? mur[i + 8] : 0.f;
+                const int i = 8 * I + r;
+                const float dv = v[9 * r];                     // 64 raw_ii
+                const float dr = dv * inv_scale;
+                const float lii = __expf(dr);
+                const float xv = mu_r[r] + fmaf(lii * kMvWScale - dv, ev[r], acc[r]);    // exp(raw_ii) eps_i for raw_ii eps_i
+                xo[r] = xv; lo8[r] = lii;
+                if (i < K) {
+                  auxp = fmaf(-0.5f * xv, xv, auxp);
+                  if (s == 0) logdet += dr;
                 }
-                if (live) {                                       // 32-byte pieces of the person's rows: whole sectors
-                  const int i0 = 8 * I;
-                  const bool wd = s == 0 && m.diagL != nullptr;
-                  if ((K & 3) == 0) {
-                    if (xr) {
-                      *reinterpret_cast<float4*>(xr + i0) = make_float4(xo[0], xo[1], xo[2], xo[3]);
-                      if (i0 + 4 < K) *reinterpret_cast<float4*>(xr + i0 + 4) = make_float4(xo[4], xo[5], xo[6], xo[7]);
-                    }
-                    if (wd) {
-                      float* dg = m.diagL + b * K + i0;
-                      *reinterpret_cast<float4*>(dg) = make_float4(lo8[0], lo8[1], lo8[2], lo8[3]);
-                      if (i0 + 4 < K) *reinterpret_cast<float4*>(dg + 4) = make_float4(lo8[4], lo8[5], lo8[6], lo8[7]);
-                    }
-                  } else {
-#pragma unroll
-                    for (int r = 0; r < 8; ++r)
-                      if (i0 + r < K) {
-                        if (xr) xr[i0 + r] = xo[r];
-                        if (wd) m.diagL[b * K + i0 + r] = lo8[r];
-                      }
-                  }
-                }
-                ++I; Jc = 0;
-              } else {
-                ++Jc;
+                acc[r] = 0.f;
               }
+              if (live) {                                       // 32-byte pieces of the person's rows: whole sectors
+                const int i0 = 8 * I;
+                const bool wd = s == 0 && m.diagL != nullptr;
+                if ((K & 3) == 0) {
+                  if (xr) {
+                    *reinterpret_cast<float4*>(xr + i0) = make_float4(xo[0], xo[1], xo[2], xo[3]);
+                    if (i0 + 4 < K) *reinterpret_cast<float4*>(xr + i0 + 4) = make_float4(xo[4], xo[5], xo[6], xo[7]);
+                  }
+                  if (wd) {
+                    float* dg = m.diagL + b * K + i0;
+                    *reinterpret_cast<float4*>(dg) = make_float4(lo8[0], lo8[1], lo8[2], lo8[3]);
+                    if (i0 + 4 < K) *reinterpret_cast<float4*>(dg + 4) = make_float4(lo8[4], lo8[5], lo8[6], lo8[7]);
+                  }
+                } else {
+#pragma unroll
+                  for (int r = 0; r < 8; ++r)
+                    if (i0 + r < K) {
+                      if (xr) xr[i0 + r] = xo[r];
+                      if (wd) m.diagL[b * K + i0 + r] = lo8[r];
+                    }
+                }
+              }
+            } else if (Jc == I - 1) {                           // the unit before the diagonal one: hand the row over
+#pragma unroll
+              for (int r = 0; r < 8; ++r) { xs[r * kMvTP] = acc[r]; acc[r] = 0.f; }
+              pair_sync();
             }
           }
           umma::fence_before_sync();
           warp_arrive(&bar_tempty[buf], lane);
+#pragma unroll
+          for (int st = 0; st < 2; ++st) {                      // two units on: this warp's unit of the next chunk
+            if (Jc == I) { ++I; Jc = 0; } else ++Jc;
+          }
+          ug += 2;
         }
       }
-      if (live && m.aux) *reinterpret_cast<float4*>(m.aux + 4 * b) = make_float4(auxp + (float)S * logdet, 0.f, 0.f, 0.f);
-      if (live && P.logdet_out) P.logdet_out[b] = logdet;
+      // loss pieces of the person: the tail sums the four words
+      if (live && m.aux) *reinterpret_cast<float2*>(m.aux + 4 * b + 2 * half) = make_float2(auxp + (float)S * logdet, 0.f);
+      if (P.logdet_out) {
+        float* ls = xch + (size_t)16 * kMvTP + t;
+        if (half == 1) *ls = logdet;
+        pair_sync();
+        if (half == 0 && live) P.logdet_out[b] = logdet + *ls;
+        pair_sync();
+      }
     }
   }
   umma::fence_before_sync();
@@ -1314,6 +1405,15 @@ int launch_mvn_prep(const MvnEncParams& P, cudaStream_t st) {
 }
 
 int launch_mvn_fwd(const MvnEncParams& P, cudaStream_t st) {
+  if (!P.m.eps) {                                      // the step's draws -> eps_split / eps_out
+    VIPSY_REQUIRE(P.eps_split || P.eps_out, VIPSY_ERR_ARG, "mvn encoder: no buffer for the draws");
+    const size_t smem = (size_t)kNzThreads * (P.m.K + 1) * 4;
+    VIPSY_CUDA_CHECK(cudaFuncSetAttribute(mvn_noise_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int64_t g = (P.m.B + kNzThreads - 1) / kNzThreads * P.m.S;
+    if (g > (int64_t)num_sms() * 4) g = (int64_t)num_sms() * 4;
+    mvn_noise_kernel<<<(int)g, kNzThreads, smem, st>>>(P);
+    VIPSY_CUDA_CHECK(cudaGetLastError());
+  }
   const FwSmem L = fw_smem(P.m.K, P.H);
   VIPSY_REQUIRE(L.nst >= 2, VIPSY_ERR_UNSUPPORTED, "mvn encoder: K=%d H=%d does not fit shared memory", P.m.K, P.H);
   VIPSY_CUDA_CHECK(cudaFuncSetAttribute(mvn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
@@ -1435,6 +1535,11 @@ int vipsy_mvn_encoder_sample(const VipsyMvnEncoderIrtArgs* a, float* x, float* e
   P.wimg_b = nullptr;
   P.m.x = x; P.eps_out = eps_out; P.m.diagL = diag; P.logdet_out = logdet; P.m.aux = nullptr;
   cudaStream_t st = (cudaStream_t)stream;
+  VIPSY_REQUIRE(a->irt.eps || eps_out, VIPSY_ERR_ARG,
+                "vipsy_mvn_encoder_sample: eps_out may be NULL only with injected noise (args->irt.eps)");
+  if (a->irt.eps && eps_out)
+    VIPSY_CUDA_CHECK(cudaMemcpyAsync(eps_out, a->irt.eps, (size_t)a->irt.n_particles * a->irt.batch * a->irt.n_dims * 4,
+                                     cudaMemcpyDeviceToDevice, st));
   rc = launch_mvn_prep(P, st);
   if (rc != VIPSY_OK) return rc;
   return launch_mvn_fwd(P, st);
