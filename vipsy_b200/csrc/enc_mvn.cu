@@ -68,9 +68,11 @@ __device__ __forceinline__ uint32_t h2_bits(__half2 h) { return *reinterpret_cas
 // and eps = eh + el,  hi = fl16(gh eh),  lo = fl16(gl eh + fl16(gh el + (gh eh - hi)))  -- the residual of the first
 // product is exact (one fused rounding), the dropped gl el term and the roundings of lo are 2^-22 of V.  16 HFMA2-class
 // instructions per 8 elements instead of 8 FMUL + 4 + 16 + 4 conversions.
-__device__ __forceinline__ void gen_octet(float g, const uint4& w0, const uint4& w1, uint4& hi, uint4& lo) {
-  const __half2 gh = __float2half2_rn(g);
-  const __half2 gl = __float2half2_rn(g - __low2float(gh));
+__device__ __forceinline__ void split_g(float g, __half2& gh, __half2& gl) {
+  gh = __float2half2_rn(g);
+  gl = __float2half2_rn(g - __low2float(gh));
+}
+__device__ __forceinline__ void gen_octet(const __half2 gh, const __half2 gl, const uint4& w0, const uint4& w1, uint4& hi, uint4& lo) {
   auto one = [&](uint32_t Hw, uint32_t Lw, uint32_t& oh, uint32_t& ol) {
     const __half2 eh = as_h2(Hw), el = as_h2(Lw);
     const __half2 h = __hmul2(gh, eh);
@@ -821,37 +823,45 @@ __global__ void __launch_bounds__(kBwThreads, 1) mvn_bwd_dh_kernel(const MvnEncP
         umma::mbar_wait(&bar_efull[eb], (uint32_t)((n / NEB) & 1));
       }
       const uint32_t* er = eps_t + (size_t)t * ES;
-      int I = 0, Jc = 0;
       float gI[4], lI[4], dadd[4], gN[4], lN[4], dN[4];      // this block row / the next one, fetched a block row ahead
       load_g<4>(m, s, b, live, 0, sub, ginv, gI, lI, dadd);
-      load_g<4>(m, s, b, live && NB > 1, 1, sub, ginv, gN, lN, dN);
-      for (int u = 0; u < NU; ++u, ++it) {
-        const uint32_t vb = it % kDhAStages;
-        const uint4 w0 = *reinterpret_cast<const uint4*>(er + 8 * Jc), w1 = *reinterpret_cast<const uint4*>(er + 8 * Jc + 4);
-        uint32_t vh[16], vl[16];
+      for (int I = 0; I < NB; ++I) {
+        load_g<4>(m, s, b, live && I + 1 < NB, I + 1, sub, ginv, gN, lN, dN);
+        __half2 gh[4], gl[4];                                // the row factors, split once per block row
 #pragma unroll
-        for (int rr = 0; rr < 4; ++rr) {
-          uint4 hi, lo;
-          gen_octet(gI[rr], w0, w1, hi, lo);
-          if (Jc == I) fix_diag(gI[rr], lI[rr], dadd[rr], er + 8 * Jc, 4 * sub + rr, hi, lo);
-          vh[4 * rr] = hi.x; vh[4 * rr + 1] = hi.y; vh[4 * rr + 2] = hi.z; vh[4 * rr + 3] = hi.w;
-          vl[4 * rr] = lo.x; vl[4 * rr + 1] = lo.y; vl[4 * rr + 2] = lo.z; vl[4 * rr + 3] = lo.w;
-        }
-        umma::mbar_wait(&bar_vfree[vb], ((it / kDhAStages) & 1) ^ 1);
-        umma::fence_after_sync();
-        umma::tmem_st16(ta + vb * 64, vh);
-        umma::tmem_st16(ta + vb * 64 + 32, vl);
-        umma::tmem_st_wait();
-        umma::fence_before_sync();
-        warp_arrive(&bar_vfull[vb], lane);
-        if (Jc == I) {
-          ++I; Jc = 0;
+        for (int rr = 0; rr < 4; ++rr) split_g(gI[rr], gh[rr], gl[rr]);
+        for (int Jc = 0; Jc <= I; ++Jc, ++it) {
+          const uint32_t vb = it % kDhAStages;
+          const uint4 w0 = *reinterpret_cast<const uint4*>(er + 8 * Jc), w1 = *reinterpret_cast<const uint4*>(er + 8 * Jc + 4);
+          uint32_t vh[16], vl[16];
+          if (Jc < I) {                                      // CTA-uniform: the plain units carry no diagonal code
 #pragma unroll
-          for (int rr = 0; rr < 4; ++rr) { gI[rr] = gN[rr]; lI[rr] = lN[rr]; dadd[rr] = dN[rr]; }
-          load_g<4>(m, s, b, live && I + 1 < NB, I + 1, sub, ginv, gN, lN, dN);
-        } else {
-          ++Jc;
+            for (int rr = 0; rr < 4; ++rr) {
+              uint4 hi, lo;
+              gen_octet(gh[rr], gl[rr], w0, w1, hi, lo);
+              vh[4 * rr] = hi.x; vh[4 * rr + 1] = hi.y; vh[4 * rr + 2] = hi.z; vh[4 * rr + 3] = hi.w;
+              vl[4 * rr] = lo.x; vl[4 * rr + 1] = lo.y; vl[4 * rr + 2] = lo.z; vl[4 * rr + 3] = lo.w;
+            }
+          } else {
+#pragma unroll
+            for (int rr = 0; rr < 4; ++rr) {
+              uint4 hi, lo;
+              gen_octet(gh[rr], gl[rr], w0, w1, hi, lo);
+              fix_diag(gI[rr], lI[rr], dadd[rr], er + 8 * Jc, 4 * sub + rr, hi, lo);
+              vh[4 * rr] = hi.x; vh[4 * rr + 1] = hi.y; vh[4 * rr + 2] = hi.z; vh[4 * rr + 3] = hi.w;
+              vl[4 * rr] = lo.x; vl[4 * rr + 1] = lo.y; vl[4 * rr + 2] = lo.z; vl[4 * rr + 3] = lo.w;
+            }
+          }
+          umma::mbar_wait(&bar_vfree[vb], ((it / kDhAStages) & 1) ^ 1);
+          umma::fence_after_sync();
+          umma::tmem_st16(ta + vb * 64, vh);
+          umma::tmem_st16(ta + vb * 64 + 32, vl);
+          umma::tmem_st_wait();
+          umma::fence_before_sync();
+          warp_arrive(&bar_vfull[vb], lane);
         }
+#pragma unroll
+        for (int rr = 0; rr < 4; ++rr) { gI[rr] = gN[rr]; lI[rr] = lN[rr]; dadd[rr] = dN[rr]; }
       }
       if (bulk) warp_arrive(&bar_efree[eb], lane);     // done with this step's draws
       if (s == S - 1 && warp < 4) {                    // drain d hidden of this tile: thread = person = TMEM lane
