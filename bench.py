@@ -217,6 +217,55 @@ def other_configs(dev, peaks, flush, iters=5):
         "ms": ms, "evals_per_s": n3 * 500 / ms * 1e3, "algorithmic_bytes": algo,
         "roofline": {"bound": "hbm", "achieved": algo / ms / 1e6, "peak": hbm, "unit": "GB/s",
                      "frac": algo / ms / 1e6 / hbm}}
+    del w, dchol, dmu
+
+    # c3 as BASELINE names it (amortised: MvnEncoder, vi.py:438-455): fc22 + tril scatter + LowerCholeskyTransform +
+    # rsample + likelihood + every gradient back to [hidden | fc22] in ONE C-ABI call (vipsy_irt_mvn_encoder_elbo_grad);
+    # the B x 5050 factor matrix and its gradient (2 x 4 GB) never exist in HBM.  Tensor-pipe bound (3-term fp16 split).
+    w = workloads.mirt(n3, 500, 100, seed=14, device=dev)
+    K3, H3, J3 = 100, 64, 500
+    P3 = K3 * (K3 + 1) // 2
+    g3 = torch.Generator(device=dev).manual_seed(15)
+    hidden = torch.nn.functional.softplus(torch.randn(n3, H3, device=dev, generator=g3))
+    w22 = (torch.rand(P3, H3, device=dev, generator=g3) - 0.5) * 0.02
+    b22 = torch.zeros(P3, device=dev)
+    ms = timed(lambda: ops.irt_elbo_grad(w["y"], w["mu"], mvn_encoder=(hidden, w22, b22), a=w["a"], b=w["b"], model="irt_2pl",
+                                         a_free=w["a_free"], seed=1, offset=nxt(), n_masked=n_miss3))
+    # fp32-equivalent work of the reference formulation per person: fc22 forward + its two backward products
+    # (3 x 2 H P), L eps and d L (2 x 2 P), logits + d x + d a (6 K J); executed on the tensor cores as 3 fp16 terms
+    flop_algo = n3 * (6.0 * H3 * P3 + 4.0 * P3 + 6.0 * K3 * J3)
+    tens = peaks.get("bf16_tflops_sustained") or peaks.get("bf16_tflops")
+    out["c3_amortised_fused_guide_2pl_K100_200kx500_S1"] = {
+        "ms": ms, "evals_per_s": n3 * J3 / ms * 1e3, "algorithmic_flop_fp32": flop_algo,
+        "hbm_bytes_avoided": 2 * 4 * n3 * P3,
+        "roofline": {"bound": "tensor", "achieved": 3 * flop_algo / ms / 1e9, "peak": tens, "unit": "TFLOP/s",
+                     "frac": 3 * flop_algo / ms / 1e9 / tens,
+                     "note": "3 fp16 MMA terms per fp32 product (hi*hi + hi*lo + lo*hi), padding of the 8x8-blocked "
+                             "triangle (5824 of 5050 columns) not counted; peak = measured cuBLAS bf16, sustained"}}
+    del w, hidden, w22, b22
+    # the whole c3 VaeIRT iteration (torch fc1 / fc21 + the call above + Adam), CUDA-graph replay, vs fc22 in torch
+    y3 = (torch.rand(n3, 500, device=dev, generator=torch.Generator(device=dev).manual_seed(16)) < 0.6).float()
+    it3 = {}
+    for fused in (True, False):
+        vb.clear_param_store()
+        torch.manual_seed(0)
+        m = vb.VaeIRT(data=y3, model="irt_2pl", x_feature=100, device=dev)
+        m.fused_encoder = fused
+        svi = infer.SVI(m.model, m.guide, optim=vb.Adam({"lr": 1e-3}), loss=vb.Trace_ELBO(num_particles=1), cuda_graph=True)
+        for _ in range(3):
+            svi.step(m.data)
+        torch.cuda.synchronize()
+        n_it = 10 if fused else 3
+        t0 = _time.perf_counter()
+        for _ in range(n_it):
+            svi.step_async(m.data)
+        torch.cuda.synchronize()
+        it3["fc22_fused_into_guide_kernels" if fused else "fc22_in_torch"] = (_time.perf_counter() - t0) / n_it * 1e3
+        del svi, m
+        torch.cuda.empty_cache()
+    del y3
+    vb.clear_param_store()
+    out["c3_vaeirt_2pl_K100_200kx500_S1_full_svi_iteration_ms"] = it3
     return out
 
 
