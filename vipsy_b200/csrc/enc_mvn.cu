@@ -263,6 +263,40 @@ __global__ void __launch_bounds__(kNzThreads) mvn_noise_kernel(const MvnEncParam
   }
 }
 
+// 32 < K <= 128 (the library's stream gives lane l of a person the draws l, l + 32, l + 64, l + 96 from one Philox
+// call): a warp per person, nothing staged -- neighbouring lanes exchange their values to form the fp16 pair words.
+__global__ void __launch_bounds__(256) mvn_noise_mid_kernel(const MvnEncParams P) {
+  const MirtParams& m = P.m;
+  const int K = m.K;
+  const int lane = threadIdx.x & 31;
+  const int64_t n_rows = (int64_t)m.S * m.B;
+  for (int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5); row < n_rows; row += (int64_t)gridDim.x * 8) {
+    const int s = (int)(row / m.B);
+    const int64_t b = row - (int64_t)s * m.B;
+    const float4 z = normal4(m.seed, m.offset, (uint64_t)(m.person_offset + b), (uint32_t)s * 32u + (uint32_t)lane);
+    const float zz[4] = {z.x, z.y, z.z, z.w};
+    if (P.eps_split) {
+      uint2* dst = reinterpret_cast<uint2*>(P.eps_split + row * K);
+      const bool odd = lane & 1;
+#pragma unroll
+      for (int seg = 0; seg < 4; ++seg) {
+        const float other = __shfl_xor_sync(0xffffffffu, zz[seg], 1);
+        const int k = 32 * seg + (lane & ~1);                      // the even draw of the pair
+        if ((seg >> 1) == (int)odd && k < K) {                    // even lanes write segments 0, 1; odd lanes 2, 3
+          uint2 w;
+          split_pair(odd ? other : zz[seg], odd ? zz[seg] : other, w.x, w.y);
+          dst[k >> 1] = w;
+        }
+      }
+    } else {
+      float* dst = P.eps_out + row * K;
+#pragma unroll
+      for (int seg = 0; seg < 4; ++seg)
+        if (32 * seg + lane < K) dst[32 * seg + lane] = zz[seg];
+    }
+  }
+}
+
 __global__ void __launch_bounds__(kFwThreads, 1) mvn_fwd_kernel(const MvnEncParams P) {
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ uint64_t bar_wfull[4], bar_wempty[4], bar_tfull[kFwTmemBufs], bar_tempty[kFwTmemBufs], bar_hfull;
@@ -1417,11 +1451,17 @@ int launch_mvn_prep(const MvnEncParams& P, cudaStream_t st) {
 int launch_mvn_fwd(const MvnEncParams& P, cudaStream_t st) {
   if (!P.m.eps) {                                      // the step's draws -> eps_split / eps_out
     VIPSY_REQUIRE(P.eps_split || P.eps_out, VIPSY_ERR_ARG, "mvn encoder: no buffer for the draws");
-    const size_t smem = (size_t)kNzThreads * (P.m.K + 1) * 4;
-    VIPSY_CUDA_CHECK(cudaFuncSetAttribute(mvn_noise_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int64_t g = (P.m.B + kNzThreads - 1) / kNzThreads * P.m.S;
-    if (g > (int64_t)num_sms() * 4) g = (int64_t)num_sms() * 4;
-    mvn_noise_kernel<<<(int)g, kNzThreads, smem, st>>>(P);
+    if (P.m.K > 32) {
+      int64_t g = ((int64_t)P.m.S * P.m.B + 7) / 8;
+      if (g > (int64_t)num_sms() * 32) g = (int64_t)num_sms() * 32;
+      mvn_noise_mid_kernel<<<(int)g, 256, 0, st>>>(P);
+    } else {
+      const size_t smem = (size_t)kNzThreads * (P.m.K + 1) * 4;
+      VIPSY_CUDA_CHECK(cudaFuncSetAttribute(mvn_noise_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      int64_t g = (P.m.B + kNzThreads - 1) / kNzThreads * P.m.S;
+      if (g > (int64_t)num_sms() * 4) g = (int64_t)num_sms() * 4;
+      mvn_noise_kernel<<<(int)g, kNzThreads, smem, st>>>(P);
+    }
     VIPSY_CUDA_CHECK(cudaGetLastError());
   }
   const FwSmem L = fw_smem(P.m.K, P.H);
