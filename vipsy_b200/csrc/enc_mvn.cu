@@ -956,7 +956,8 @@ constexpr int kDwAStages = 3;              // V^T chunks in tensor memory: 3 x (
 constexpr uint32_t kDwACol = 512 - 64 * kDwAStages;
 constexpr uint32_t kDwGRec = 512;          // per row i of a tile: [g hi | g lo | diag hi | diag lo], 64 persons x fp16 each
 constexpr int kDwGenWarps = 16;            // generator warps: 4 per TMEM lane quadrant, 16 persons of the tile each
-constexpr int kDwThreads = kDwGenWarps * 32 + 64;    // + bulk-copy producer warp + MMA warp
+constexpr int kDwMmaWarps = 2;             // MMA-issuing warps (alternate chunks)
+constexpr int kDwThreads = (kDwGenWarps + 1 + kDwMmaWarps) * 32;    // + bulk-copy producer warp + MMA warps
 constexpr int kDwPH = kDwGenWarps / 4;     // person groups per tile
 constexpr int kDwPPT = kDwTP / kDwPH;      // persons per generator thread
 constexpr int kDwFG = (5 + kDwPH - 1) / kDwPH;       // groups of 16 accumulator columns per warp in a flush (KH <= 80)
@@ -1135,13 +1136,13 @@ __global__ void __launch_bounds__(kDwThreads, 1) mvn_bwd_dw_kernel(const MvnEncP
   if (tid == 0) {
     for (int i = 0; i < kDwBufs; ++i) {
       umma::mbar_init(&bar_efull[i], 3);               // three bulk copies per step: [hidden | 1], draws, G rows
-      umma::mbar_init(&bar_tfree[i], kDwGenWarps + 1);
+      umma::mbar_init(&bar_tfree[i], kDwGenWarps + kDwMmaWarps);
     }
     for (int i = 0; i < kDwAStages; ++i) {
       umma::mbar_init(&bar_vfull[i], kDwGenWarps);
       umma::mbar_init(&bar_vfree[i], 1);
     }
-    umma::mbar_init(&bar_done, 1);
+    umma::mbar_init(&bar_done, kDwMmaWarps);
     umma::mbar_init(&bar_drained, kDwGenWarps);
     umma::fence_mbar_init();
   }
@@ -1182,8 +1183,12 @@ __global__ void __launch_bounds__(kDwThreads, 1) mvn_bwd_dw_kernel(const MvnEncP
       }
       __syncwarp();
     }
-  } else if (warp == kDwGenWarps + 1) {
-    // MMA issuer: a whole-warp loop, issue under elect_one()
+  } else if (warp > kDwGenWarps) {
+    // MMA issuers: whole-warp loops, issue under elect_one().  TWO warps take alternate chunks: a wait / commit pair
+    // around a group of MMAs costs the issuing warp ~350 cycles in which it feeds nothing to the tensor pipe -- with two
+    // issuers one warp's round trip hides under the other's MMAs (the chunks go to different accumulators; commits
+    // track the MMAs of the committing thread).
+    const uint32_t mw = (uint32_t)(warp - (kDwGenWarps + 1));
     const uint32_t idesc = umma::make_idesc_f16(kMvCN, KH, umma::kMajorK, umma::kMajorMN);
     const uint64_t dH0 = umma::make_desc(umma::smem_u32(smem + L.offH), RSH, kCSb);     // [hidden | 1]: MN-major B
     uint32_t it = 0, nflush = 0;
@@ -1192,6 +1197,7 @@ __global__ void __launch_bounds__(kDwThreads, 1) mvn_bwd_dw_kernel(const MvnEncP
       const uint32_t buf = (uint32_t)(n % NBUF);
       umma::mbar_wait(&bar_efull[buf], (uint32_t)((n / NBUF) & 1));
       for (int k = 0; k < nblk; ++k, ++it) {
+        if ((it % kDwMmaWarps) != mw) continue;
         const uint32_t vb = it % kDwAStages;
         umma::mbar_wait(&bar_vfull[vb], (it / kDwAStages) & 1);
         umma::fence_after_sync();
@@ -1215,7 +1221,7 @@ __global__ void __launch_bounds__(kDwThreads, 1) mvn_bwd_dw_kernel(const MvnEncP
       fresh = false;
       const bool flush = (n + 1) % kDwFlushTiles == 0 || n + 1 == n_steps;
       if (umma::elect_one()) {
-        umma::commit(&bar_tfree[buf]);                 // every MMA that reads this step's H tile has completed
+        umma::commit(&bar_tfree[buf]);                 // every MMA of this warp that reads this step's H tile has completed
         if (flush) umma::commit(&bar_done);            // flush: the drain warps add the accumulators to the partial rows
       }
       __syncwarp();
