@@ -93,6 +93,19 @@ __device__ __forceinline__ void split_store8(const float (&v)[8], unsigned char*
   *reinterpret_cast<uint4*>(lo_dst) = make_uint4(l[0], l[1], l[2], l[3]);
 }
 
+__device__ __forceinline__ void split8_regs(const float (&v)[8], uint4& hi, uint4& lo) {
+  uint32_t h[4], l[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    __half2 hh = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
+    const float2 hf = __half22float2(hh);
+    h[i] = *reinterpret_cast<uint32_t*>(&hh);
+    l[i] = pack_half2(v[2 * i] - hf.x, v[2 * i + 1] - hf.y);
+  }
+  hi = make_uint4(h[0], h[1], h[2], h[3]);
+  lo = make_uint4(l[0], l[1], l[2], l[3]);
+}
+
 // mbarrier slots of the pipeline (one completion per row tile each; the response ring has one pair per buffer)
 enum { kBarXFull = 0,   // x producers -> MMA: x tile staged                                    (256 arrivals)
        kBarXFree,       // MMA commit -> x producers: backward MMAs done, x and G tiles reusable
@@ -211,8 +224,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) mirt_tc_lik_kernel(const MirtPa
     constexpr int kPre = 8;                                  // 32-byte chunks per thread (16 x 128 / 256)
     const bool xvec = (K & 3) == 0;
 
+    // chunk e of the tile = (row e % 128, 8 columns e / 128): consecutive lanes take consecutive ROWS, so that their
+    // 16-byte pieces of the operand tile are contiguous (8 lanes = one 128-byte core matrix; with consecutive
+    // columns per lane the pieces lie 128 B apart -- an 8-way bank conflict on every store)
     auto load_chunk = [&](int e, int64_t r0, float (&v)[8]) {
-      const int pr = e / nck, c8 = e - pr * nck;
+      const int pr = e & (kTcTM - 1), c8 = e >> 7;
       const int64_t r = r0 + pr;
       if (e < kTcTM * nck && r < R && !(p.dbg & 4)) {
         const float* src = p.x + r * K + c8 * 8;
@@ -221,6 +237,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) mirt_tc_lik_kernel(const MirtPa
           const float4 u1 = *reinterpret_cast<const float4*>(src + 4);
           v[0] = u0.x; v[1] = u0.y; v[2] = u0.z; v[3] = u0.w;
           v[4] = u1.x; v[5] = u1.y; v[6] = u1.z; v[7] = u1.w;
+        } else if (xvec && c8 * 8 + 4 == K) {                 // the chunk that holds the last 4 columns and the ones column
+          const float4 u0 = *reinterpret_cast<const float4*>(src);
+          v[0] = u0.x; v[1] = u0.y; v[2] = u0.z; v[3] = u0.w;
+          v[4] = 1.f; v[5] = 0.f; v[6] = 0.f; v[7] = 0.f;
+        } else if (c8 * 8 > K) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) v[i] = 0.f;
         } else {
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
@@ -260,9 +283,16 @@ __global__ void __launch_bounds__(kTcThreads, 1) mirt_tc_lik_kernel(const MirtPa
     for (int64_t tm = g; tm < ntile_m; tm += G, ++n) {
       const int64_t r0 = tm * kTcTM;
       if (ptid == 0) TC_STAMP(0, 0);
-      float xv[kPre][8];
+      // loaded AND split into the fp16 hi / lo pieces before the buffer is waited for: what is left on the critical
+      // path between "x buffer free" and "x tile staged" are the 16 stores (the split is ~200 instructions per thread).
+      // (Issuing these loads a stage earlier, before the d x drain, needs 64 more live registers: spills at 672 threads.)
+      uint4 xh[kPre], xl[kPre];
 #pragma unroll
-      for (int u = 0; u < kPre; ++u) load_chunk(ptid + u * kTcXThreads, r0, xv[u]);
+      for (int u = 0; u < kPre; ++u) {
+        float xv[8];
+        load_chunk(ptid + u * kTcXThreads, r0, xv);
+        split8_regs(xv, xh[u], xl[u]);
+      }
       if (ptid == 0) TC_STAMP(0, 1);
       // ---- the single x buffer is free once the backward MMAs of tile n-1 have completed ---------------
       if (n > 0) umma::mbar_wait(&bars[kBarXFree], (uint32_t)((n - 1) & 1));
@@ -271,9 +301,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) mirt_tc_lik_kernel(const MirtPa
       for (int u = 0; u < kPre; ++u) {
         const int e = ptid + u * kTcXThreads;
         if (e < kTcTM * nck) {
-          const int pr = e / nck, c8 = e - pr * nck;
+          const int pr = e & (kTcTM - 1), c8 = e >> 7;
           const uint32_t o = umma::tile_off(pr, c8 * 8, L.rsX, kCS);
-          split_store8(xv[u], Xh + o, Xl + o);
+          *reinterpret_cast<uint4*>(Xh + o) = xh[u];
+          *reinterpret_cast<uint4*>(Xl + o) = xl[u];
         }
       }
       umma::fence_proxy_async();                            // generic-proxy writes -> visible to the tensor core
