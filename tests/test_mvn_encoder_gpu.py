@@ -95,7 +95,8 @@ def test_fused_guide_matches_oracle(ops, B, J, K, H, S, model):
 
 
 @pytest.mark.parametrize("B,J,K,H,S", [(1000, 100, 100, 64, 1), (500, 30, 4, 16, 2), (333, 20, 12, 8, 3),
-                                       (200, 25, 6, 16, 2), (129, 40, 32, 64, 1), (1, 7, 8, 3, 1)])
+                                       (200, 25, 6, 16, 2), (129, 40, 32, 64, 1), (1, 7, 8, 3, 1),
+                                       (150, 30, 37, 20, 2), (300, 60, 50, 64, 1), (260, 20, 128, 64, 1)])
 def test_fused_guide_equals_materialised_factor_k100(ops, B, J, K, H, S):
     """The library's own noise stream (K % 4 == 0: the draws travel to the backward kernels as pre-split fp16 pair
     words by bulk copy; otherwise as fp32 rows).  K = 100 is the BASELINE c3 shape scaled down: the fused path against

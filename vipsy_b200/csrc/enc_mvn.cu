@@ -24,7 +24,8 @@ namespace {
 
 constexpr uint32_t kCSb = 128;                 // byte stride between core matrices along the contiguous dimension
 constexpr int kFwEpiWarps = 8;                 // warps 0-7: epilogue, two per TMEM lane quadrant (warp & 3), one unit of a chunk each
-constexpr int kFwThreads = (kFwEpiWarps + 2) * 32;   // + warp 4: bulk-copy producer, warp 5: MMA issuer
+constexpr int kFwMmaWarps = 2;                 // MMA-issuing warps (alternate chunks)
+constexpr int kFwThreads = (kFwEpiWarps + 1 + kFwMmaWarps) * 32;   // + a bulk-copy producer warp + the MMA warps
 constexpr int kFwTmemBufs = 3;                 // 3 x 128 accumulator columns; columns 384.. : the [hidden | 1] operand
 constexpr uint32_t kFwACol = 384;              // A operand in tensor memory: KH / 2 words of fp16 hi pairs, then KH / 2 of lo
 
@@ -340,8 +341,9 @@ __global__ void __launch_bounds__(kFwThreads, 1) mvn_fwd_kernel(const MvnEncPara
                             &bar_wfull[st]);
           __syncwarp();
         }
-  } else if (warp == kFwEpiWarps + 1) {
-    // =========================== MMA issuer ====================================================================
+  } else if (warp > kFwEpiWarps) {
+    // =========================== MMA issuers: two warps on alternate chunks (see mvn_bwd_dw_kernel) ===========
+    const uint32_t mw = (uint32_t)(warp - (kFwEpiWarps + 1));
     const uint32_t idesc = umma::make_idesc_f16(kMvTP, kMvCN, umma::kMajorK, umma::kMajorK);
     const uint32_t aH = tmem + kFwACol, aL = aH + (uint32_t)(KH / 2);
     uint32_t it = 0, ntile = 0;
@@ -350,6 +352,7 @@ __global__ void __launch_bounds__(kFwThreads, 1) mvn_fwd_kernel(const MvnEncPara
       umma::fence_after_sync();
       for (int s = 0; s < S; ++s)
         for (int c = 0; c < n_chunks; ++c, ++it) {
+          if ((it % kFwMmaWarps) != mw) continue;
           const uint32_t st = it % NST, round = it / NST;
           const uint32_t buf = it % kFwTmemBufs, tround = it / kFwTmemBufs;
           umma::mbar_wait(&bar_wfull[st], round & 1);
@@ -685,6 +688,8 @@ __device__ __forceinline__ void load_g(const MirtParams& m, int s, int64_t b, bo
 
 // ---- d hidden[person][h] = (1 / 64) sum_p V[person][p] (64 W22)[p][h]: CTAs own person tiles, every unit of V ------
 constexpr int kDhMaxStages = 8;
+constexpr int kDhMmaWarps = 2;                        // MMA-issuing warps (alternate units)
+constexpr int kDhThreads = kBwGen + 32 + 32 * kDhMmaWarps;
 constexpr int kDhAStages = 4;                          // V units in tensor memory: 4 x (32 hi + 32 lo) columns
 struct DhSmem {
   uint32_t offEps, offW, total, w_bytes, eps_bytes;
@@ -707,7 +712,7 @@ __host__ __device__ inline DhSmem dh_smem(int K, int H, bool bulk) {
   return s;
 }
 
-__global__ void __launch_bounds__(kBwThreads, 1) mvn_bwd_dh_kernel(const MvnEncParams P, const int bulk) {
+__global__ void __launch_bounds__(kDhThreads, 1) mvn_bwd_dh_kernel(const MvnEncParams P, const int bulk) {
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ uint64_t bar_vfull[kDhAStages], bar_vfree[kDhAStages], bar_wfull[kDhMaxStages], bar_wempty[kDhMaxStages], bar_efull[2], bar_efree[2], bar_dfull, bar_dfree;
   __shared__ uint32_t tmem_base_sm;
@@ -725,7 +730,9 @@ __global__ void __launch_bounds__(kBwThreads, 1) mvn_bwd_dh_kernel(const MvnEncP
   // The tensor core adds into its fp32 accumulator with truncation: a long chain of accumulating MMAs drifts by
   // ~2^-24 of the running sum per instruction (measured: 2e-5 relative over the 1092 MMAs of a K = 100 tile).
   // The units therefore go round-robin into NACC independent accumulators, summed (round-to-nearest) at the drain.
-  const uint32_t NACC = 256u / (uint32_t)NH < 8u ? 256u / (uint32_t)NH : 8u;
+  // (an even number: the two issuing warps take alternate units and must never share an accumulator -- the order of
+  //  two warps' MMAs is not fixed, and the results are promised bit-identical run to run)
+  const uint32_t NACC = (256u / (uint32_t)NH < 8u ? 256u / (uint32_t)NH : 8u) & ~1u;
   constexpr uint32_t kACol = 256;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int64_t n_tiles = (m.B + kMvTP - 1) / kMvTP;
@@ -747,14 +754,14 @@ __global__ void __launch_bounds__(kBwThreads, 1) mvn_bwd_dh_kernel(const MvnEncP
       umma::mbar_init(&bar_efree[i], kBwGenWarps);
     }
     for (int i = 0; i < kDhMaxStages; ++i) { umma::mbar_init(&bar_wfull[i], 1); umma::mbar_init(&bar_wempty[i], 1); }
-    umma::mbar_init(&bar_dfull, 1);
+    umma::mbar_init(&bar_dfull, kDhMmaWarps);
     umma::mbar_init(&bar_dfree, 4);
     umma::fence_mbar_init();
   }
   // The last row-octet of the last person of a tile reaches past the rows a bulk copy brings in (its products meet
   // zero weights, so the values only have to be finite): clear that tail once.
   for (int e = 0; e < NEB; ++e)
-    for (uint32_t o = (uint32_t)kMvTP * ES * 4 + 4 * tid; o < L.eps_bytes; o += 4 * kBwThreads)
+    for (uint32_t o = (uint32_t)kMvTP * ES * 4 + 4 * tid; o < L.eps_bytes; o += 4 * kDhThreads)
       *reinterpret_cast<uint32_t*>(smem + L.offEps + (size_t)e * L.eps_bytes + o) = 0u;
   if (warp == kBwGenWarps + 1) umma::tmem_alloc(&tmem_base_sm, 512);
   umma::fence_before_sync();
@@ -790,8 +797,9 @@ __global__ void __launch_bounds__(kBwThreads, 1) mvn_bwd_dh_kernel(const MvnEncP
         if (bulk && NEB == 1 && n + 1 < n_steps) issue_eps(n + 1);
       }
     }
-  } else if (warp == kBwGenWarps + 1) {
-    {                                                  // MMA issuer
+  } else if (warp > kBwGenWarps) {
+    {                                                  // MMA issuers: two warps on alternate units (see mvn_bwd_dw_kernel)
+      const uint32_t mw = (uint32_t)(warp - (kBwGenWarps + 1));
       const uint32_t idesc = umma::make_idesc_f16(kMvTP, NH, umma::kMajorK, umma::kMajorMN);
       const uint64_t dW0 = umma::make_desc(umma::smem_u32(Wb), RSW, kCSb);     // 64 W22 unit: MN-major B
       uint32_t it = 0, ntile = 0;
@@ -801,6 +809,7 @@ __global__ void __launch_bounds__(kBwThreads, 1) mvn_bwd_dh_kernel(const MvnEncP
         uint32_t nu = 0;
         for (int s = 0; s < S; ++s)
           for (int u = 0; u < NU; ++u, ++it, ++nu) {
+            if ((it % kDhMmaWarps) != mw) continue;
             const uint32_t vb = it % kDhAStages, st = it % NST;
             const uint32_t ai = nu % NACC;               // round-robin over the accumulators (see NACC)
             umma::mbar_wait(&bar_vfull[vb], (it / kDhAStages) & 1);
@@ -1414,7 +1423,7 @@ int launch_mvn_bwd(const MvnEncParams& P, cudaStream_t st) {
     VIPSY_CUDA_CHECK(cudaFuncSetAttribute(mvn_bwd_dh_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
     int64_t g = num_sms();
     if (g > n_tiles) g = n_tiles;
-    mvn_bwd_dh_kernel<<<(int)g, kBwThreads, L.total, st>>>(P, bulk);
+    mvn_bwd_dh_kernel<<<(int)g, kDhThreads, L.total, st>>>(P, bulk);
     VIPSY_CUDA_CHECK(cudaGetLastError());
   }
   if (P.d_w22 || P.d_b22) {
