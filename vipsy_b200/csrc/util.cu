@@ -39,7 +39,15 @@ __global__ void __launch_bounds__(kFinWarps * 32) finalize_kernel(const Finalize
   const int col = blockIdx.x * 32 + lane;
   if (blockIdx.x * 32 < a.cols) {
     double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-    if (col < a.cols) {
+    bool wanted = false;                               // columns of a segment without an output are never written
+    {                                                  // by the producers either: do not read them
+      int c = col;
+      for (int i = 0; i < a.segs.n && col < a.cols; ++i) {
+        if (c < a.segs.cols[i]) { wanted = a.segs.out[i] != nullptr; break; }
+        c -= a.segs.cols[i];
+      }
+    }
+    if (col < a.cols && wanted) {
       int r = warp;
       for (; r + 3 * kFinWarps < a.rows; r += 4 * kFinWarps) {
         const float v0 = a.partial[(size_t)r * a.cols + col];
