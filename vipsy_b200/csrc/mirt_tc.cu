@@ -472,9 +472,19 @@ __global__ void __launch_bounds__(kTcThreads, 1) mirt_tc_lik_kernel(const MirtPa
       for (int cc = 0; cc < 4; ++cc) {
         const int c0 = half * 64 + cc * 16;
         float v[16];
+        float* dst = part + (size_t)(k <= K ? k : 0) * J + j0 + c0;        // k == K lands on the d_b segment (offset K*J)
+        const bool vec = (J & 3) == 0 && j0 + c0 + 16 <= J && k <= K;      // 16-byte pieces: 4 requests instead of 16
+        float4 old[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q)                            // the old partial sums are on their way before TMEM is read
+          old[q] = (vec && grp > 0) ? *reinterpret_cast<const float4*>(dst + 4 * q) : make_float4(0.f, 0.f, 0.f, 0.f);
         umma::tmem_ld16(taddr + c0, v);
-        if (k <= K) {
-          float* dst = part + (size_t)k * J + j0 + c0;        // k == K lands on the d_b segment (offset K*J)
+        if (vec) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            *reinterpret_cast<float4*>(dst + 4 * q) = make_float4(old[q].x + v[4 * q], old[q].y + v[4 * q + 1],
+                                                                  old[q].z + v[4 * q + 2], old[q].w + v[4 * q + 3]);
+        } else if (k <= K) {
 #pragma unroll
           for (int i = 0; i < 16; ++i)
             if (j0 + c0 + i < J) dst[i] = grp > 0 ? dst[i] + v[i] : v[i];
