@@ -107,18 +107,22 @@ __device__ __forceinline__ void split8_regs(const float (&v)[8], uint4& hi, uint
 }
 
 // mbarrier slots of the pipeline (one completion per row tile each; the response ring has one pair per buffer)
-enum { kBarXFull = 0,   // x producers -> MMA: x tile staged                                    (256 arrivals)
+enum { kBarXFull = 0,   // x producers -> MMA: x tile staged                                    (8 arrivals)  
        kBarXFree,       // MMA commit -> x producers: backward MMAs done, x and G tiles reusable
        kBarLFull,       // MMA commit -> epilogue: logits in TMEM
-       kBarGFull,       // epilogue -> MMA: G tile written, logits consumed                     (256 arrivals)
+       kBarGFull,       // epilogue -> MMA: G tile written, logits consumed                     (8 arrivals)  
        kBarDxFull,      // MMA commit -> x producers (+ epilogue at the end): d x / d a in TMEM
-       kBarDxFree,      // x producers -> MMA: d x drained to global memory                     (256 arrivals)
-       kBarYFull0, kBarYFull1,   // y producers -> epilogue: response buffer b staged           (128 arrivals)
-       kBarYFree0, kBarYFree1,   // epilogue -> y producers: response buffer b consumed         (256 arrivals)
+       kBarDxFree,      // x producers -> MMA: d x drained to global memory                     (8 arrivals)  
+       kBarYFull0, kBarYFull1,   // y producers -> epilogue: response buffer b staged           (4 arrivals)  
+       kBarYFree0, kBarYFree1,   // epilogue -> y producers: response buffer b consumed         (8 arrivals)  
        kNumBars };
 
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(umma::smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void warp_arrive(uint64_t* bar, int lane) {
+  __syncwarp();
+  if (lane == 0) mbar_arrive(bar);
 }
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
@@ -195,16 +199,18 @@ __global__ void __launch_bounds__(kTcThreads, 1) mirt_tc_lik_kernel(const MirtPa
   }
   if (warp == kTcMmaWarp) umma::tmem_alloc(&tmem_base_sm, kTmemCols);
   if (tid == 0) {
-    umma::mbar_init(&bars[kBarXFull], kTcXThreads);
-    umma::mbar_init(&bars[kBarYFull0], kTcYThreads);
-    umma::mbar_init(&bars[kBarYFull1], kTcYThreads);
-    umma::mbar_init(&bars[kBarYFree0], kTcEpiThreads);
-    umma::mbar_init(&bars[kBarYFree1], kTcEpiThreads);
+    // one arrival per WARP everywhere (all lanes fence, lane 0 signals): hundreds of separate arrivals on one mbarrier
+    // serialise on the shared-memory atomic unit -- 256 of them cost 1-2 k cycles per phase
+    umma::mbar_init(&bars[kBarXFull], kTcXThreads / 32);
+    umma::mbar_init(&bars[kBarYFull0], kTcYThreads / 32);
+    umma::mbar_init(&bars[kBarYFull1], kTcYThreads / 32);
+    umma::mbar_init(&bars[kBarYFree0], kTcEpiThreads / 32);
+    umma::mbar_init(&bars[kBarYFree1], kTcEpiThreads / 32);
     umma::mbar_init(&bars[kBarXFree], 1);
     umma::mbar_init(&bars[kBarLFull], 1);
-    umma::mbar_init(&bars[kBarGFull], kTcEpiThreads);
+    umma::mbar_init(&bars[kBarGFull], kTcEpiThreads / 32);
     umma::mbar_init(&bars[kBarDxFull], 1);
-    umma::mbar_init(&bars[kBarDxFree], kTcXThreads);
+    umma::mbar_init(&bars[kBarDxFree], kTcXThreads / 32);
     umma::fence_mbar_init();
   }
   umma::fence_proxy_async();
@@ -285,7 +291,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) mirt_tc_lik_kernel(const MirtPa
         }
       }
       umma::fence_before_sync();
-      mbar_arrive(&bars[kBarDxFree]);
+      warp_arrive(&bars[kBarDxFree], lane);
     };
 
     int64_t n = 0, r0_prev = 0;
@@ -319,7 +325,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) mirt_tc_lik_kernel(const MirtPa
         }
       }
       umma::fence_proxy_async();                            // generic-proxy writes -> visible to the tensor core
-      mbar_arrive(&bars[kBarXFull]);
+      warp_arrive(&bars[kBarXFull], lane);
       if (ptid == 0) TC_STAMP(0, 3);
       // ---- d x of tile n-1 (kBarXFree and kBarDxFull complete together) --------------------------------
       if (n > 0) {
@@ -399,7 +405,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) mirt_tc_lik_kernel(const MirtPa
           ytile[pr * kTcYStride + jj] = code;
         }
       }
-      mbar_arrive(&bars[kBarYFull0 + buf]);
+      warp_arrive(&bars[kBarYFull0 + buf], lane);
     }
   } else if (warp == kTcMmaWarp) {
     // =========================== MMA ISSUER ===========================================================
@@ -522,6 +528,56 @@ __global__ void __launch_bounds__(kTcThreads, 1) mirt_tc_lik_kernel(const MirtPa
 #pragma unroll
         for (int i = 0; i < 4; ++i) yw[i] = *reinterpret_cast<const uint32_t*>(ytile + pr * kTcYStride + c0 + i * 4);
         float csc[16], csd[16];                              // 3PL / 4PL: this row's d lb/dc, d lb/dd per column
+        if constexpr (MODEL == VIPSY_IRT_2PL) {
+          // 2PL: no per-cell selects (the technique of the K = 1 row kernels, irt_uni_row.cu).  sg = +2 (y = 1),
+          // -2 (y = 0), 0 (missing) is assembled from the response byte with integer ops (top byte of the float
+          // 0x40 / 0xc0 / 0x00); t = (sg D / 2)(-log2e l) is the logit signed by the response and 0 for a missing
+          // cell, whose sp = 1/2 multiplies the likelihood product by exactly 2^-1 (added back through n_half) while
+          // its gradient (sg D / 2) e sp vanishes by itself.  The probability clamp (sp < eps <=> t >= 23) comes from
+          // the min on t; the gradient of a clamped cell is switched off in a rare branch, one test per word.
+          // 16 instructions per cell instead of 29: the epilogue is bound by issue slots (8 warps, 64 cells a thread).
+          const float halfD = 0.5f * p.D;
+          int n_half = 0;
+          float gl16[16];
+#pragma unroll
+          for (int w = 0; w < 4; ++w) {
+            const uint32_t word = yw[w];
+            n_half += __popc(word & 0x02020202u);
+            const uint32_t nw = ~word;
+            const uint32_t T = ((nw << 7) & 0x80808080u) | (nw & 0x40404040u);
+            float sgD[4], tt[4], es[4];
+            sgD[0] = halfD * __uint_as_float(__byte_perm(T, 0u, 0x0444u));
+            sgD[1] = halfD * __uint_as_float(__byte_perm(T, 0u, 0x1444u));
+            sgD[2] = halfD * __uint_as_float(__byte_perm(T, 0u, 0x2444u));
+            sgD[3] = halfD * __uint_as_float(__byte_perm(T, 0u, 0x3444u));
+            float prod = 1.f;                                // one lg2 per 4 cells: each factor >= 1.19e-7
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              tt[i] = sgD[i] * (-kLog2e * v[4 * w + i]);
+              const float e = ex2_approx(fminf(tt[i], 23.f));
+              const float sp = rcp_approx(1.f + e);           // s (y=1) | 1-s (y=0) | 1/2 (missing)
+              es[i] = e * sp;
+              prod *= sp;
+            }
+            if (fmaxf(fmaxf(tt[0], tt[1]), fmaxf(tt[2], tt[3])) >= 23.f) {
+#pragma unroll
+              for (int i = 0; i < 4; ++i)
+                if (tt[i] >= 23.f) es[i] = 0.f;
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) gl16[4 * w + i] = sgD[i] * es[i];
+            ll = fmaf(kLn2, lg2_approx(prod), ll);
+          }
+          ll = fmaf(kLn2, (float)n_half, ll);
+#pragma unroll
+          for (int c8 = 0; c8 < 2; ++c8) {
+            float gl8[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) gl8[i] = gl16[8 * c8 + i];
+            const uint32_t o = umma::tile_off(pr, c0 + c8 * 8, L.rsG, kCS);
+            split_store8(gl8, Gh + o, Gl + o);
+          }
+        } else
 #pragma unroll
         for (int c8 = 0; c8 < 2; ++c8) {
           float gl8[8];
@@ -576,8 +632,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) mirt_tc_lik_kernel(const MirtPa
       }
       umma::fence_before_sync();
       umma::fence_proxy_async();
-      mbar_arrive(&bars[kBarGFull]);
-      mbar_arrive(&bars[kBarYFree0 + (n & 1)]);
+      warp_arrive(&bars[kBarGFull], lane);
+      warp_arrive(&bars[kBarYFree0 + (n & 1)], lane);
       if (tid == 0) TC_STAMP(2, 1);
       // first tile of a new group: the previous group's d a is complete (the logits of this tile were committed after
       // every earlier MMA) and nothing writes that accumulator before the group after next -> add it to the partial row
