@@ -203,6 +203,15 @@ typedef struct VipsyMvnEncoderIrtArgs {
   float* d_b22;            /* K(K+1)/2                                                                   */
   void* workspace;
   size_t workspace_bytes;  /* >= vipsy_irt_mvn_encoder_workspace_bytes()                                 */
+  /* Optional: the location head fc21 as well (vi.py:443, 450: loc = fc21(hidden)).  With w21 != NULL the call
+   * computes loc itself (irt.mu is ignored and may be NULL) -- each row of fc21 rides in a padding slot of the
+   * diagonal 8 x 8 block of its factor row, as one more column against a constant draw of 1 -- and returns
+   * d fc21.weight / d fc21.bias; d_hidden then holds the gradient through BOTH heads.  irt.d_mu (= d loc) is
+   * still written when non-NULL. */
+  const float* w21;        /* K x H   fc21.weight, or NULL                                               */
+  const float* b21;        /* K       fc21.bias (required with w21)                                      */
+  float* d_w21;            /* K x H, or NULL                                                             */
+  float* d_b21;            /* K, or NULL                                                                 */
 } VipsyMvnEncoderIrtArgs;
 size_t vipsy_irt_mvn_encoder_workspace_bytes(const VipsyMvnEncoderIrtArgs* args);
 /* loss + every gradient (NULL gradient pointers: the value only, evaluate_loss) */

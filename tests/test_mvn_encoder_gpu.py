@@ -125,6 +125,43 @@ def test_fused_guide_equals_materialised_factor_k100(ops, B, J, K, H, S):
         assert torch.equal(r[n], again[n]), f"{n} is not bit-identical run to run"
 
 
+@pytest.mark.parametrize("B,J,K,H,S,model", [(300, 40, 10, 16, 1, "irt_2pl"), (257, 33, 37, 20, 2, "irt_2pl"), (500, 12, 3, 8, 1, "irt_2pl"),
+                                             (130, 70, 9, 64, 1, "irt_4pl"), (260, 30, 100, 64, 1, "irt_2pl"), (64, 20, 128, 33, 1, "irt_2pl")])
+def test_fused_location_head_matches_oracle(ops, B, J, K, H, S, model):
+    """fc21 inside the call as well (mvn_encoder with five entries): the location rides in the padding slots of the
+    diagonal units.  fp64 side: loc = fc21(hidden), raw = fc22(hidden), oracle ELBO, autograd back through both heads."""
+    d = make(B, J, K, H, S, seed=3 * J + K, model=model)
+    g = torch.Generator().manual_seed(K)
+    d["w21"] = (torch.rand(K, H, generator=g) - 0.5) * 0.3
+    d["b21"] = (torch.rand(K, generator=g) - 0.5) * 0.3
+    hd, wd, bd, w1, b1 = (d[n].double().requires_grad_(True) for n in ("hidden", "w22", "b22", "w21", "b21"))
+    packed, loc = hd @ wd.T + bd, hd @ w1.T + b1
+    ref = o.irt_elbo_grad(d["y"], loc.detach(), o.tril_from_packed(packed, K).detach(), d["eps"], d["a"], d["b"], d.get("c"),
+                          d.get("d"), model=model, scale=1.3, chol_raw=True)
+    ti = torch.tril_indices(K, K)
+    torch.autograd.backward([packed, loc], [ref["d_scale"][:, ti[0], ti[1]].double(), ref["d_mu"].double()])
+    cu = {k: v.cuda() for k, v in d.items()}
+    r = ops.irt_elbo_grad(ops.pack_responses(cu["y"]), None,
+                          mvn_encoder=(cu["hidden"], cu["w22"], cu["b22"], cu["w21"], cu["b21"]),
+                          eps=cu["eps"], a=cu["a"], b=cu["b"], c=cu.get("c"), d=cu.get("d"), model=model, scale=1.3)
+    assert_close(r["loss"], ref["loss"], TOL, TOL, "loss")
+    for n in ("d_mu", "d_a", "d_b"):
+        assert_close(r[n], ref[n], TOL, TOL, n)
+    for n, t in (("d_hidden", hd), ("d_w22", wd), ("d_b22", bd), ("d_w21", w1), ("d_b21", b1)):
+        assert_close(r[n], t.grad, TOL, TOL, n)
+    # the library's noise stream: same call twice bit-identical, and equal to the three-entry form fed with loc
+    kw = dict(a=cu["a"], b=cu["b"], c=cu.get("c"), d=cu.get("d"), model=model, scale=1.3, seed=5, offset=2, n_particles=S)
+    codes = ops.pack_responses(cu["y"])
+    r1 = ops.irt_elbo_grad(codes, None, mvn_encoder=(cu["hidden"], cu["w22"], cu["b22"], cu["w21"], cu["b21"]), **kw)
+    r2 = ops.irt_elbo_grad(codes, None, mvn_encoder=(cu["hidden"], cu["w22"], cu["b22"], cu["w21"], cu["b21"]), **kw)
+    r3 = ops.irt_elbo_grad(codes, loc.detach().float().cuda(), mvn_encoder=(cu["hidden"], cu["w22"], cu["b22"]), **kw)
+    for n in ("loss", "d_mu", "d_hidden", "d_w21", "d_b21", "d_w22"):
+        assert torch.equal(r1[n], r2[n]), n
+    assert_close(r1["loss"], r3["loss"], TOL, TOL, "loss (five vs three entries)")
+    assert_close(r1["d_mu"], r3["d_mu"], TOL, TOL, "d_mu (five vs three entries)")
+    assert_close(r1["d_w22"], r3["d_w22"], TOL, TOL, "d_w22 (five vs three entries)")
+
+
 def test_value_only_and_minibatch(ops):
     """evaluate_loss (no gradient pointers) gives the same loss; a minibatch through idx reads the right rows."""
     B, J, K, H, N = 96, 30, 6, 16, 400

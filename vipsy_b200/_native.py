@@ -65,6 +65,7 @@ class MvnEncoderIrtArgs(C.Structure):
         ("irt", IrtArgs), ("n_hidden", C.c_int32), ("reserved", C.c_int32),
         ("hidden", _p), ("w22", _p), ("b22", _p), ("d_hidden", _p), ("d_w22", _p), ("d_b22", _p),
         ("workspace", _p), ("workspace_bytes", C.c_size_t),
+        ("w21", _p), ("b21", _p), ("d_w21", _p), ("d_b21", _p),
     ]
 
 

@@ -111,6 +111,17 @@ __device__ __forceinline__ void fix_diag(float g, float lii, float dadd, const u
   }
 }
 
+// element c (0..7) of an octet := val (fp16 hi / lo pair)
+__device__ __forceinline__ void put_elem(uint4& hi, uint4& lo, int c, float val) {
+  const __half hd = __float2half_rn(val);
+  const __half ld = __float2half_rn(val - __half2float(hd));
+  const uint32_t sh = (c & 1) ? 16u : 0u, keep = ~(0xffffu << sh);
+  uint32_t* hw = reinterpret_cast<uint32_t*>(&hi);
+  uint32_t* lw = reinterpret_cast<uint32_t*>(&lo);
+  hw[c >> 1] = (hw[c >> 1] & keep) | ((uint32_t)__half_as_ushort(hd) << sh);
+  lw[c >> 1] = (lw[c >> 1] & keep) | ((uint32_t)__half_as_ushort(ld) << sh);
+}
+
 // ------------------------------------------------------------------------------------------------ operand image
 // Padded column pc of the factor -> (row i, column j) (j > i or i >= K: padding, weight 0).
 __device__ __forceinline__ void mv_row_of(int pc, int& i, int& j) {
@@ -124,7 +135,8 @@ __device__ __forceinline__ void mv_row_of(int pc, int& i, int& j) {
 
 // img  (forward):  chunks of 128 padded columns x KH = [hidden | 1 | 0], hi tile then lo tile, rows = columns of L
 // imgb (backward): units of 64 padded columns x NH hidden units (no bias column), hi tile then lo tile
-__global__ void mvn_prep_kernel(const float* __restrict__ w22, const float* __restrict__ b22, int K, int H, int KH,
+__global__ void mvn_prep_kernel(const float* __restrict__ w22, const float* __restrict__ b22, const float* __restrict__ w21,
+                                const float* __restrict__ b21, int K, int H, int KH,
                                 int NH, int n_chunks, unsigned char* __restrict__ img, unsigned char* __restrict__ imgb) {
   const int n_oct = KH / 8;
   const int total = n_chunks * kMvCN * n_oct;
@@ -144,6 +156,16 @@ __global__ void mvn_prep_kernel(const float* __restrict__ w22, const float* __re
         const int k = o * 8 + t;
         if (k < H) v[t] = kMvWScale * w22[p * H + k];
         else if (k == H) v[t] = kMvWScale * b22[p];
+      }
+    } else if (w21 && (i >> 3) == (j >> 3)) {         // padding of a diagonal unit: a row of fc21 in its slot
+      const int r = mv_loc_row_of_slot(pc & 63), il = 8 * (i >> 3) + r;
+      if (r >= 0 && il < K) {
+#pragma unroll
+        for (int t = 0; t < 8; ++t) {
+          const int k = o * 8 + t;
+          if (k < H) v[t] = kMvWScale * w21[(size_t)il * H + k];
+          else if (k == H) v[t] = kMvWScale * b21[il];
+        }
       }
     }
     uint4 hi, lo;
@@ -387,6 +409,7 @@ __global__ void __launch_bounds__(kFwThreads, 1) mvn_fwd_kernel(const MvnEncPara
     float* xch = reinterpret_cast<float*>(smem + L.offX);
     const uint32_t tlane = tmem + ((uint32_t)(quad * 32) << 16);
     const float inv_scale = 1.0f / kMvWScale;
+    const bool has_loc = P.w21 != nullptr;               // fc21 fused: the location comes out of the same product
     auto pair_sync = [&]() { asm volatile("bar.sync %0, 64;" ::"r"(1 + quad) : "memory"); };
     uint32_t it = 0;
     if (half == 0)
@@ -490,7 +513,7 @@ __global__ void __launch_bounds__(kFwThreads, 1) mvn_fwd_kernel(const MvnEncPara
           if (I < NB) {                                          // warp-uniform
             const bool diag = Jc == I;
             float mu_r[8];
-            if (diag) {
+            if (diag && !has_loc) {
 #pragma unroll
               for (int r = 0; r < 8; ++r) mu_r[r] = 8 * I + r < K ? mur[8 * I + r] : 0.f;
             }
@@ -498,13 +521,27 @@ __global__ void __launch_bounds__(kFwThreads, 1) mvn_fwd_kernel(const MvnEncPara
             umma::tmem_ld64(tlane + buf * kMvCN + half * 64, v);
             const float4 e0v = *reinterpret_cast<const float4*>(er + 8 * Jc);
             const float4 e1v = *reinterpret_cast<const float4*>(er + 8 * Jc + 4);
+            if (diag && has_loc) {
+              // the padding above the diagonal carries fc21's rows (mv_loc_slot): only columns j <= i meet the draws,
+              // the location of row r is read from its slot
+              const float ev[8] = {e0v.x, e0v.y, e0v.z, e0v.w, e1v.x, e1v.y, e1v.z, e1v.w};
 #pragma unroll
-            for (int r = 0; r < 8; ++r) {
-              float d0 = v[8 * r] * e0v.x, d1 = v[8 * r + 4] * e1v.x;
-              d0 = fmaf(v[8 * r + 1], e0v.y, d0); d1 = fmaf(v[8 * r + 5], e1v.y, d1);
-              d0 = fmaf(v[8 * r + 2], e0v.z, d0); d1 = fmaf(v[8 * r + 6], e1v.z, d1);
-              d0 = fmaf(v[8 * r + 3], e0v.w, d0); d1 = fmaf(v[8 * r + 7], e1v.w, d1);
-              acc[r] += d0 + d1;
+              for (int r = 0; r < 8; ++r) {
+                float d = 0.f;
+#pragma unroll
+                for (int jj = 0; jj <= r; ++jj) d = fmaf(v[8 * r + jj], ev[jj], d);
+                acc[r] += d;
+                mu_r[r] = v[mv_loc_slot(r)] * inv_scale;
+              }
+            } else {
+#pragma unroll
+              for (int r = 0; r < 8; ++r) {
+                float d0 = v[8 * r] * e0v.x, d1 = v[8 * r + 4] * e1v.x;
+                d0 = fmaf(v[8 * r + 1], e0v.y, d0); d1 = fmaf(v[8 * r + 5], e1v.y, d1);
+                d0 = fmaf(v[8 * r + 2], e0v.z, d0); d1 = fmaf(v[8 * r + 6], e1v.z, d1);
+                d0 = fmaf(v[8 * r + 3], e0v.w, d0); d1 = fmaf(v[8 * r + 7], e1v.w, d1);
+                acc[r] += d0 + d1;
+              }
             }
             float* xs = xch + (size_t)((I & 1) * 8) * kMvTP + t;
             if (diag) {                                         // rows 8I .. 8I+7 are complete once the partner's share is in
@@ -840,6 +877,7 @@ __global__ void __launch_bounds__(kDhThreads, 1) mvn_bwd_dh_kernel(const MvnEncP
     }
   } else {
     const int t = tid & 127, sub = tid >> 7;           // thread = (person, rows 4 sub .. 4 sub + 3 of every unit)
+    const bool has_loc = P.w21 != nullptr;
     // TMEM lane = person (warp w reaches lanes 32 (w % 4) ..: t >> 5 == warp % 4); row r of a unit = words 4 r .. 4 r + 3
     const uint32_t ta = tmem + ((uint32_t)((warp & 3) * 32) << 16) + kACol + 16u * (uint32_t)sub;
     uint32_t it = 0;
@@ -886,11 +924,30 @@ __global__ void __launch_bounds__(kDhThreads, 1) mvn_bwd_dh_kernel(const MvnEncP
               vl[4 * rr] = lo.x; vl[4 * rr + 1] = lo.y; vl[4 * rr + 2] = lo.z; vl[4 * rr + 3] = lo.w;
             }
           } else {
+            // fc21 fused: the slots above the diagonal hold V = G_r x 1 for the location rows (mv_loc_slot): rows 0 and 1
+            // of the unit, i.e. the sub == 0 thread, which fetches the block row's other four G values for it
+            float gloc[8];
+            if (has_loc && sub == 0) {
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                const int i = 8 * I + 4 + q;
+                gloc[q] = gI[q];
+                gloc[4 + q] = (live && i < K) ? ginv * m.gx[((int64_t)s * m.B + b) * K + i] : 0.f;
+              }
+            }
 #pragma unroll
             for (int rr = 0; rr < 4; ++rr) {
               uint4 hi, lo;
               gen_octet(gh[rr], gl[rr], w0, w1, hi, lo);
               fix_diag(gI[rr], lI[rr], dadd[rr], er + 8 * Jc, 4 * sub + rr, hi, lo);
+              if (has_loc && sub == 0) {
+                if (rr == 0) {
+#pragma unroll
+                  for (int c = 1; c < 8; ++c) put_elem(hi, lo, c, gloc[c]);
+                } else if (rr == 1) {
+                  put_elem(hi, lo, 2, gloc[0]);
+                }
+              }
               vh[4 * rr] = hi.x; vh[4 * rr + 1] = hi.y; vh[4 * rr + 2] = hi.z; vh[4 * rr + 3] = hi.w;
               vl[4 * rr] = lo.x; vl[4 * rr + 1] = lo.y; vl[4 * rr + 2] = lo.z; vl[4 * rr + 3] = lo.w;
             }
@@ -1261,6 +1318,13 @@ __global__ void __launch_bounds__(kDwThreads, 1) mvn_bwd_dw_kernel(const MvnEncP
         const uint32_t erow = L.offE + (uint32_t)(8 * Jc + jj) * kDwERec + (uint32_t)(2 * kDwPPT * hp);
         if (Jc != I || jj < r) { go = grow; eo = erow; }
         else if (jj == r) { go = grow + 256u; eo = kConst | L.offConst; }
+        else if (P.w21) {                              // fc21 fused: a location slot is G of its row against the row of ones
+          const int rl = mv_loc_row_of_slot(8 * r + jj);
+          if (rl >= 0) {
+            go = L.offG + (uint32_t)((I - I_first) * 8 + rl) * kDwGRec + (uint32_t)(2 * kDwPPT * hp);
+            eo = kConst | L.offConst;
+          }
+        }
       }
       goff[k] = go; eoff[k] = eo;
     }
@@ -1354,8 +1418,19 @@ __global__ void __launch_bounds__(kDwThreads, 1) mvn_bwd_dw_kernel(const MvnEncP
 
 // d_w22[p][h], d_b22[p] = sum over the person groups, in order, of the partial rows of padded column mv_col(i, j)
 __global__ void mvn_dw_finalize_kernel(const float* __restrict__ part, int n_qg, int n_cols, int K, int H, int KH,
-                                       float* __restrict__ d_w22, float* __restrict__ d_b22) {
+                                       float* __restrict__ d_w22, float* __restrict__ d_b22, float* __restrict__ d_w21,
+                                       float* __restrict__ d_b21) {
   const int P = K * (K + 1) / 2;
+  // d fc21: location row i sits at slot mv_loc_slot(i % 8) of the diagonal unit of block row i / 8
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < K * (H + 1) && (d_w21 || d_b21); e += gridDim.x * blockDim.x) {
+    const int i = e / (H + 1), h = e - i * (H + 1);
+    const int I = i >> 3;
+    const size_t pc = (size_t)64 * (I * (I + 1) / 2 + I) + mv_loc_slot(i & 7);
+    float t = 0.f;
+    for (int q = 0; q < n_qg; ++q) t += part[((size_t)q * n_cols + (pc & ~size_t(kMvCN - 1))) * KH + (size_t)h * kMvCN + (pc & (kMvCN - 1))];
+    if (h < H) { if (d_w21) d_w21[(size_t)i * H + h] = t; }
+    else if (d_b21) d_b21[i] = t;
+  }
   for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < P * (H + 1); e += gridDim.x * blockDim.x) {
     const int p = e / (H + 1), h = e - p * (H + 1);
     int i = (int)((sqrtf(8.f * (float)p + 1.f) - 1.f) * 0.5f);
@@ -1426,7 +1501,7 @@ int launch_mvn_bwd(const MvnEncParams& P, cudaStream_t st) {
     mvn_bwd_dh_kernel<<<(int)g, kDhThreads, L.total, st>>>(P, bulk);
     VIPSY_CUDA_CHECK(cudaGetLastError());
   }
-  if (P.d_w22 || P.d_b22) {
+  if (P.d_w22 || P.d_b22 || P.d_w21 || P.d_b21) {
     const DwSmem L = dw_smem(K, H);
     VIPSY_REQUIRE(L.total <= 227 * 1024, VIPSY_ERR_UNSUPPORTED, "mvn encoder backward: K=%d H=%d does not fit shared memory", K, H);
     VIPSY_CUDA_CHECK(cudaFuncSetAttribute(mvn_bwd_dw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
@@ -1449,7 +1524,7 @@ int launch_mvn_bwd(const MvnEncParams& P, cudaStream_t st) {
     VIPSY_CUDA_CHECK(cudaGetLastError());
     const int total = K * (K + 1) / 2 * (H + 1);
     mvn_dw_finalize_kernel<<<(total + 255) / 256, 256, 0, st>>>(P.dw_part, n_qg, mv_chunks(K) * kMvCN, K, H, mv_kh(H),
-                                                                P.d_w22, P.d_b22);
+                                                                P.d_w22, P.d_b22, P.d_w21, P.d_b21);
     VIPSY_CUDA_CHECK(cudaGetLastError());
   }
   return VIPSY_OK;
@@ -1458,7 +1533,8 @@ int launch_mvn_bwd(const MvnEncParams& P, cudaStream_t st) {
 int launch_mvn_prep(const MvnEncParams& P, cudaStream_t st) {
   const int KH = mv_kh(P.H), n_chunks = mv_chunks(P.m.K);
   const int total = n_chunks * kMvCN * (KH / 8);
-  mvn_prep_kernel<<<(total + 255) / 256, 256, 0, st>>>(P.w22, P.b22, P.m.K, P.H, KH, mv_nh(P.H), n_chunks, P.wimg, P.wimg_b);
+  mvn_prep_kernel<<<(total + 255) / 256, 256, 0, st>>>(P.w22, P.b22, P.w21, P.b21, P.m.K, P.H, KH, mv_nh(P.H), n_chunks, P.wimg,
+                                                       P.wimg_b);
   VIPSY_CUDA_CHECK(cudaGetLastError());
   return VIPSY_OK;
 }
@@ -1498,7 +1574,10 @@ static int check_mvn(const VipsyMvnEncoderIrtArgs* a, const char* who) {
                 "%s: bad sizes B=%lld K=%d S=%d (K in 2..128)", who, (long long)r.batch, r.n_dims, r.n_particles);
   VIPSY_REQUIRE(a->n_hidden >= 1 && a->n_hidden <= kMvMaxH, VIPSY_ERR_UNSUPPORTED,
                 "%s: hidden_dim %d outside 1..%d", who, a->n_hidden, kMvMaxH);
-  VIPSY_REQUIRE(a->hidden && a->w22 && a->b22 && r.mu, VIPSY_ERR_ARG, "%s: hidden, w22, b22 and irt.mu are required", who);
+  VIPSY_REQUIRE(a->hidden && a->w22 && a->b22 && (r.mu || a->w21), VIPSY_ERR_ARG,
+                "%s: hidden, w22, b22 and irt.mu (or w21) are required", who);
+  VIPSY_REQUIRE(!a->w21 || a->b21, VIPSY_ERR_ARG, "%s: w21 needs b21", who);
+  VIPSY_REQUIRE(a->w21 || (!a->d_w21 && !a->d_b21), VIPSY_ERR_ARG, "%s: d_w21 / d_b21 need w21", who);
   VIPSY_REQUIRE((reinterpret_cast<uintptr_t>(a->workspace) & 127) == 0, VIPSY_ERR_ARG, "%s: workspace must be 128-byte aligned", who);
   return VIPSY_OK;
 }
@@ -1510,7 +1589,8 @@ static MvnEncParams mvn_params(const VipsyMvnEncoderIrtArgs* a) {
   P.m.mu = r.mu; P.m.eps = r.eps; P.m.seed = r.seed; P.m.offset = r.offset; P.m.person_offset = r.person_offset;
   P.m.scale = r.scale;
   P.hidden = a->hidden; P.w22 = a->w22; P.b22 = a->b22; P.H = a->n_hidden;
-  P.d_hidden = a->d_hidden; P.d_w22 = a->d_w22; P.d_b22 = a->d_b22;
+  P.w21 = a->w21; P.b21 = a->b21;
+  P.d_hidden = a->d_hidden; P.d_w22 = a->d_w22; P.d_b22 = a->d_b22; P.d_w21 = a->d_w21; P.d_b21 = a->d_b21;
   return P;
 }
 
@@ -1553,6 +1633,7 @@ int vipsy_irt_mvn_encoder_elbo_grad(const VipsyMvnEncoderIrtArgs* a, void* strea
   VipsyIrtArgs r = a->irt;
   r.cov_mode = VIPSY_COV_PERSON; r.chol = nullptr; r.d_chol = nullptr; r.sigma = nullptr; r.d_sigma = nullptr;
   r.chol_layout = VIPSY_CHOL_PACKED; r.chol_raw = 1;
+  if (!r.mu && a->w21) r.mu = a->hidden;                 // fc21 fused: the location is computed here, irt.mu is never read
   rc = check_irt(&r);
   if (rc != VIPSY_OK) return rc;
   VIPSY_REQUIRE(r.model != VIPSY_IRT_1PL, VIPSY_ERR_ARG, "vipsy_irt_mvn_encoder_elbo_grad: irt_1pl is defined for K == 1 only");

@@ -24,6 +24,11 @@ __host__ __device__ inline int mv_col(int i, int j) {
   const int I = i >> 3, Jc = j >> 3;
   return 64 * (I * (I + 1) / 2 + Jc) + 8 * (i & 7) + (j & 7);
 }
+// fc21 (the location head) rides in the padding above the diagonal of the diagonal units: row r of block row I
+// (location 8 I + r) sits at local column mv_loc_slot(r) of unit (I, I) -- (0, r) for r >= 1, (1, 2) for r = 0 --
+// as a factor column that meets a constant draw of 1.
+__host__ __device__ inline int mv_loc_slot(int r) { return r == 0 ? 10 : r; }
+__host__ __device__ inline int mv_loc_row_of_slot(int idx) { return idx == 10 ? 0 : (idx >= 1 && idx <= 7 ? idx : -1); }
 __host__ __device__ inline int mv_kh(int H) { return (H + 1 + 15) / 16 * 16; }   // + the ones column (fc22.bias)
 __host__ __device__ inline int mv_nh(int H) { return (H + 15) / 16 * 16; }
 __host__ __device__ inline int mv_chunks(int K) { return (mv_pp(K) + kMvCN - 1) / kMvCN; }
@@ -35,6 +40,8 @@ struct MvnEncParams {
   const float* hidden;       // [B][H]
   const float* w22;          // [P][H]
   const float* b22;          // [P]
+  const float* w21;          // [K][H] fc21.weight, or null: the location comes in as m.mu
+  const float* b21;          // [K]
   int H;
   unsigned char* wimg;       // [chunks][hi | lo] operand image of 64 * [fc22.weight | fc22.bias | 0]
   unsigned char* wimg_b;     // [units][hi | lo] 64 padded columns x NH of 64 * fc22.weight (backward: d hidden), or null
@@ -48,6 +55,8 @@ struct MvnEncParams {
   float* d_hidden;           // outputs
   float* d_w22;
   float* d_b22;
+  float* d_w21;              // [K][H], or null
+  float* d_b21;              // [K], or null
 };
 
 size_t mvn_enc_extra_bytes(const VipsyMvnEncoderIrtArgs* a);

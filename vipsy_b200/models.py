@@ -395,7 +395,7 @@ class VaeIRT(BaseIRT):                  # vi.py:659-693
         self.encoder = enc(self.item_size, self.x_feature, hidden_dim).to(self.device)
         # encoder inside the CUDA path (False: torch autograd end to end).  K = 1: NormEncoder forward / backward
         # kernels (csrc/enc_norm*.cu).  K > 1: MvnEncoder's fc22 + tril scatter + LowerCholeskyTransform fused into
-        # the sampler and its backward (csrc/enc_mvn.cu); fc1 / fc21 stay in torch.
+        # the sampler and its backward (csrc/enc_mvn.cu), fc21 with it; fc1 stays in torch.
         self.fused_encoder = True
 
     def _guide(self, idx, B):
@@ -408,15 +408,18 @@ class VaeIRT(BaseIRT):                  # vi.py:659-693
                 enc_backward(r["d_mu"], r["d_sigma"], w)
             return dict(mu=mu, sigma=sigma), backward, sites
         if self.x_feature > 1 and self._mvn_encoder_fusable():
+            # both heads of MvnEncoder (fc21: location, fc22: factor) are evaluated inside the call; torch keeps fc1
             enc = self.encoder
             hidden = enc.softplus(enc.fc1(self._encoder_input(idx)))
-            x_loc = enc.fc21(hidden)
 
             def backward(r, w):
                 _accum(enc.fc22.weight, r["d_w22"] * w)
                 _accum(enc.fc22.bias, r["d_b22"] * w)
-                torch.autograd.backward([hidden, x_loc], [r["d_hidden"] * w, r["d_mu"] * w])
-            return (dict(mu=x_loc.detach(), mvn_encoder=(hidden.detach(), enc.fc22.weight.detach(), enc.fc22.bias.detach())),
+                _accum(enc.fc21.weight, r["d_w21"] * w)
+                _accum(enc.fc21.bias, r["d_b21"] * w)
+                torch.autograd.backward([hidden], [r["d_hidden"] * w])
+            return (dict(mu=None, mvn_encoder=(hidden.detach(), enc.fc22.weight.detach(), enc.fc22.bias.detach(),
+                                               enc.fc21.weight.detach(), enc.fc21.bias.detach())),
                     backward, sites)
         x_loc, x_sc = self.encoder(self._encoder_input(idx))
         if self.x_feature == 1:

@@ -186,7 +186,9 @@ def irt_elbo_grad(
     VaeIRT (vi.py:685-693).  ``mu`` is fc21's output, ``hidden`` = softplus(fc1(x)) for the batch rows; fc22, the
     tril scatter and LowerCholeskyTransform are evaluated inside the sampler on the tensor cores and the B x K(K+1)/2
     factor matrix never exists in HBM.  Returns ``d_hidden`` (through fc22 only), ``d_w22``, ``d_b22`` instead of
-    ``d_chol``.
+    ``d_chol``.  With five entries ``(hidden, fc22.weight, fc22.bias, fc21.weight, fc21.bias)`` the location head is
+    evaluated inside the call as well (``mu`` may be None): ``d_w21`` / ``d_b21`` are returned too and ``d_hidden``
+    holds the gradient through both heads.
 
     ``item_grads_out`` (fp32, packed [d_b | d_a | d_c | d_d]) / ``loss_out`` (fp64, 1): optional destinations,
     e.g. views into a symmetric peer-memory buffer (``dist.PeerAllReduce``).
@@ -205,7 +207,11 @@ def irt_elbo_grad(
         raise ValueError("y must be 2-D with unit column stride")
     dev = y.device
     n_rows, J = y.shape
-    mu_ = _f32(mu, "mu")
+    if mu is None and mvn_encoder is not None and len(mvn_encoder) == 5:
+        # fc21 fused as well: the location is computed inside the call; a placeholder carries the shape only
+        mu_ = torch.empty((mvn_encoder[0].shape[0], mvn_encoder[3].shape[0]), dtype=torch.float32, device=y.device)
+    else:
+        mu_ = _f32(mu, "mu")
     if mu_.dim() == 1:
         mu_ = mu_.unsqueeze(1)
     B, K = mu_.shape
@@ -266,10 +272,12 @@ def irt_elbo_grad(
         if K < 2:
             raise ValueError("mvn_encoder is the K > 1 guide")
         tri = K * (K + 1) // 2
-        enc_ = tuple(_f32(t, n) for t, n in zip(mvn_encoder, ("hidden", "fc22.weight", "fc22.bias")))
+        enc_ = tuple(_f32(t, n) for t, n in zip(mvn_encoder, ("hidden", "fc22.weight", "fc22.bias", "fc21.weight", "fc21.bias")))
         H = enc_[0].shape[1]
         if enc_[0].shape[0] != B or tuple(enc_[1].shape) != (tri, H) or enc_[2].numel() != tri:
             raise ValueError("mvn_encoder: hidden B x H, fc22.weight K(K+1)/2 x H, fc22.bias K(K+1)/2")
+        if len(enc_) not in (3, 5) or (len(enc_) == 5 and (tuple(enc_[3].shape) != (K, H) or enc_[4].numel() != K)):
+            raise ValueError("mvn_encoder: (hidden, fc22.weight, fc22.bias[, fc21.weight K x H, fc21.bias K])")
         if H > MVN_ENCODER_MAX_HIDDEN:
             raise ValueError(f"mvn_encoder: hidden_dim {H} > {MVN_ENCODER_MAX_HIDDEN}")
         args.cov_mode = N.COV_PERSON
@@ -312,6 +320,9 @@ def irt_elbo_grad(
         elif enc_ is not None:
             out["d_hidden"] = torch.empty_like(enc_[0])
             out["d_w22"] = torch.empty_like(enc_[1])
+            if len(enc_) == 5:
+                out["d_w21"] = torch.empty_like(enc_[3])
+                out["d_b21"] = torch.empty_like(enc_[4])
             out["d_b22"] = torch.empty(enc_[2].numel(), dtype=torch.float32, device=dev)
         else:
             d_chol = _out(d_scale_out, tuple(ch_.shape), zero=d_scale_out is None)
@@ -345,8 +356,12 @@ def irt_elbo_grad(
         ea = N.MvnEncoderIrtArgs()
         ea.irt = args
         ea.n_hidden, ea.hidden, ea.w22, ea.b22 = enc_[0].shape[1], _ptr(enc_[0]), _ptr(enc_[1]), _ptr(enc_[2])
+        if len(enc_) == 5:
+            ea.w21, ea.b21 = _ptr(enc_[3]), _ptr(enc_[4])
         if want_grad:
             ea.d_hidden, ea.d_w22, ea.d_b22 = _ptr(out["d_hidden"]), _ptr(out["d_w22"]), _ptr(out["d_b22"])
+            if len(enc_) == 5:
+                ea.d_w21, ea.d_b21 = _ptr(out["d_w21"]), _ptr(out["d_b21"])
         nbytes = L.vipsy_irt_mvn_encoder_workspace_bytes(C.byref(ea))
         ws = _workspace("irt_mvn", nbytes, dev)
         ea.workspace, ea.workspace_bytes = _ptr(ws), ws.numel()
