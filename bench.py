@@ -219,7 +219,7 @@ def other_configs(dev, peaks, flush, iters=5):
                      "frac": algo / ms / 1e6 / hbm}}
     del w, dchol, dmu
 
-    # c3 as BASELINE names it (amortised: MvnEncoder, vi.py:438-455): fc22 + tril scatter + LowerCholeskyTransform +
+    # c3 as BASELINE names it (amortised: MvnEncoder, vi.py:438-455): fc21 + fc22 + tril scatter + LowerCholeskyTransform +
     # rsample + likelihood + every gradient back to [hidden | fc22] in ONE C-ABI call (vipsy_irt_mvn_encoder_elbo_grad);
     # the B x 5050 factor matrix and its gradient (2 x 4 GB) never exist in HBM.  Tensor-pipe bound (3-term fp16 split).
     w = workloads.mirt(n3, 500, 100, seed=14, device=dev)
@@ -229,11 +229,13 @@ def other_configs(dev, peaks, flush, iters=5):
     hidden = torch.nn.functional.softplus(torch.randn(n3, H3, device=dev, generator=g3))
     w22 = (torch.rand(P3, H3, device=dev, generator=g3) - 0.5) * 0.02
     b22 = torch.zeros(P3, device=dev)
-    ms = timed(lambda: ops.irt_elbo_grad(w["y"], w["mu"], mvn_encoder=(hidden, w22, b22), a=w["a"], b=w["b"], model="irt_2pl",
-                                         a_free=w["a_free"], seed=1, offset=nxt(), n_masked=n_miss3))
-    # fp32-equivalent work of the reference formulation per person: fc22 forward + its two backward products
-    # (3 x 2 H P), L eps and d L (2 x 2 P), logits + d x + d a (6 K J); executed on the tensor cores as 3 fp16 terms
-    flop_algo = n3 * (6.0 * H3 * P3 + 4.0 * P3 + 6.0 * K3 * J3)
+    w21 = (torch.rand(K3, H3, device=dev, generator=g3) - 0.5) * 0.2
+    b21 = torch.zeros(K3, device=dev)
+    ms = timed(lambda: ops.irt_elbo_grad(w["y"], None, mvn_encoder=(hidden, w22, b22, w21, b21), a=w["a"], b=w["b"],
+                                         model="irt_2pl", a_free=w["a_free"], seed=1, offset=nxt(), n_masked=n_miss3))
+    # fp32-equivalent work of the reference formulation per person: fc22 and fc21 forward + their two backward products
+    # (3 x 2 H (P + K)), L eps and d L (2 x 2 P), logits + d x + d a (6 K J); executed on the tensor cores as 3 fp16 terms
+    flop_algo = n3 * (6.0 * H3 * (P3 + K3) + 4.0 * P3 + 6.0 * K3 * J3)
     tens = peaks.get("bf16_tflops_sustained") or peaks.get("bf16_tflops")
     out["c3_amortised_fused_guide_2pl_K100_200kx500_S1"] = {
         "ms": ms, "evals_per_s": n3 * J3 / ms * 1e3, "algorithmic_flop_fp32": flop_algo,
@@ -242,8 +244,8 @@ def other_configs(dev, peaks, flush, iters=5):
                      "frac": 3 * flop_algo / ms / 1e9 / tens,
                      "note": "3 fp16 MMA terms per fp32 product (hi*hi + hi*lo + lo*hi), padding of the 8x8-blocked "
                              "triangle (5824 of 5050 columns) not counted; peak = measured cuBLAS bf16, sustained"}}
-    del w, hidden, w22, b22
-    # the whole c3 VaeIRT iteration (torch fc1 / fc21 + the call above + Adam), CUDA-graph replay, vs fc22 in torch
+    del w, hidden, w22, b22, w21, b21
+    # the whole c3 VaeIRT iteration (torch fc1 + the call above + Adam), CUDA-graph replay, vs the whole encoder in torch
     y3 = (torch.rand(n3, 500, device=dev, generator=torch.Generator(device=dev).manual_seed(16)) < 0.6).float()
     it3 = {}
     for fused in (True, False):

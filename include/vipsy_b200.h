@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define VIPSY_ABI_VERSION 2
+#define VIPSY_ABI_VERSION 3
 
 enum {
   VIPSY_OK = 0,
@@ -181,7 +181,8 @@ int vipsy_irt_host_step(const VipsyIrtHostArgs* args);
  *     x = loc + L eps  ~  MultivariateNormal(loc, scale_tril = L)                    (vi.py:693, rsample)
  * and backpropagates through all of it.  raw is B x K(K+1)/2 floats (4 GB for 200 000 persons at K = 100) that
  * are written once and read once, and so is its gradient.  This entry takes `hidden` and `loc` (B x H and
- * B x K -- the caller keeps fc1 / fc21 in its framework, as north_star asks for the encoder MLP) and evaluates
+ * B x K -- the caller keeps fc1 / fc21 in its framework, as north_star asks for the encoder MLP; or hands fc21 over
+ * as well, see w21 below) and evaluates
  * fc22 on the tensor cores inside the sampler: factor rows are consumed straight from tensor memory, then the
  * likelihood contraction of vipsy_irt_elbo_grad runs, and the backward pass forms d fc22.weight, d fc22.bias
  * and d hidden from the outer products (d loss / d x)(eps)^T on chip.  Neither raw nor its gradient ever

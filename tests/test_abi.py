@@ -33,13 +33,13 @@ def test_every_declared_symbol_is_exported(lib):
     for n in names:
         assert n in N.SYMBOLS, f"{n} declared in the header but not bound"
         assert getattr(lib, n) is not None
-    assert lib.vipsy_abi_version() == 2
+    assert lib.vipsy_abi_version() == 3
 
 
 def test_struct_layout_matches_header():
     structs = {"VipsyIrtArgs": N.IrtArgs, "VipsyCdmEnumArgs": N.CdmEnumArgs, "VipsyCdmScoreArgs": N.CdmScoreArgs,
                "VipsyIrtHostArgs": N.IrtHostArgs, "VipsyAdamTensor": N.AdamTensor,
-               "VipsyNormEncoderArgs": N.NormEncoderArgs}
+               "VipsyNormEncoderArgs": N.NormEncoderArgs, "VipsyMvnEncoderIrtArgs": N.MvnEncoderIrtArgs}
     lines = ['#include <stdio.h>', '#include <stddef.h>', f'#include "{HEADER}"', "int main(void){"]
     for cname, st in structs.items():
         lines.append(f'printf("{cname} %zu\\n", sizeof({cname}));')

@@ -167,7 +167,7 @@ def lib():
         for name, (res, args) in SYMBOLS.items():
             fn = getattr(L, name)
             fn.restype, fn.argtypes = res, args
-        if L.vipsy_abi_version() != 2:
+        if L.vipsy_abi_version() != 3:
             raise VipsyError(ERR_ARG, "ABI version mismatch")
         _lib = L
     return _lib
