@@ -246,20 +246,31 @@ __global__ void __launch_bounds__(kCdmThreads, 3) cdm_enum_kernel(const CdmEnumP
   const int64_t gwarp = (int64_t)blockIdx.x * kCdmWarps + warp;
   const int64_t nwarps = (int64_t)gridDim.x * kCdmWarps;
 
+  // the response codes of a person are fetched one person ahead: ~10 % of the stall samples sat on their first use
+  auto load_codes = [&](int64_t b, unsigned (&cd)[NS]) {
+#pragma unroll
+    for (int k = 0; k < NS; ++k) cd[k] = 255u;
+    if (b < p.B) {
+      const int64_t row = p.idx ? p.idx[b] : b;
+      const uint8_t* yrow = p.y + row * p.ld_y;
+#pragma unroll
+      for (int k = 0; k < NS; ++k) {
+        if (k < nslots) {
+          const int j = k * 32 + lane;
+          if (j < J) cd[k] = yrow[j];
+        }
+      }
+    }
+  };
+  unsigned codes_next[NS];
+  load_codes(gwarp, codes_next);
   for (int64_t b = gwarp; b < p.B; b += nwarps) {
-    const int64_t row = p.idx ? p.idx[b] : b;
-    const uint8_t* yrow = p.y + row * p.ld_y;
     // ---- responses -> base, sparse f --------------------------------------
     unsigned codes[NS];
     float base_part = 0.f;
 #pragma unroll
-    for (int k = 0; k < NS; ++k) {
-      codes[k] = 255u;
-      if (k < nslots) {
-        const int j = k * 32 + lane;
-        if (j < J) codes[k] = yrow[j];
-      }
-    }
+    for (int k = 0; k < NS; ++k) codes[k] = codes_next[k];
+    load_codes(b + nwarps, codes_next);
     // SCOREM: a missing cell of a real item becomes code 2 (third category), padding slots stay 255
     if constexpr (SCOREM) {
       if (p.score_missing) {
