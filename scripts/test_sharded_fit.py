@@ -45,6 +45,30 @@ for name, r in (("nccl", nccl), ("peer", peer)):
         t0 = t.clone()
         dist.broadcast(t0, 0)
         ok &= bool(torch.equal(t0, t))
+
+
+# the amortised K > 1 guide (fused fc21 / fc22, csrc/enc_mvn.cu): encoder weights are replicated, their gradients -- among
+# them d fc21 / d fc22 from the fused call -- are summed across the shards together with the item gradients
+def run_vae(sharded, steps=5):
+    vb.clear_param_store()
+    torch.manual_seed(11)
+    data = y[lo:hi] if sharded else y
+    m = vb.VaeIRT(data=data, model="irt_2pl", x_feature=4, hidden_dim=16, seed=7, device=dev)
+    if sharded:
+        attach(m, N, lo, peer=False)
+    svi = infer.SVI(m.model, m.guide, optim=vb.Adam({"lr": 1e-2}), loss=vb.Trace_ELBO(num_particles=1), cuda_graph=False)
+    losses = [svi.step(m.data) for _ in range(steps)]
+    return losses, vb.param("a").clone(), {n: p.detach().clone() for n, p in m.encoder.named_parameters()}
+
+
+vref, vsh = run_vae(False), run_vae(True)
+ok_vae = all(abs(a - b) <= 5e-5 * abs(b) for a, b in zip(vsh[0], vref[0])) and bool(torch.allclose(vsh[1], vref[1], rtol=5e-4, atol=5e-5))
+for n in vref[2]:
+    ok_vae &= bool(torch.allclose(vsh[2][n], vref[2][n], rtol=5e-4, atol=5e-5))
+ok &= ok_vae
+if rank == 0:
+    print(f"world={world}: sharded VaeIRT K=4 (fused MVN guide) == unsharded: {ok_vae}; losses {vref[0][0]:.3f} -> {vref[0][-1]:.3f} "
+          f"vs {vsh[0][0]:.3f} -> {vsh[0][-1]:.3f}", flush=True)
 flag = torch.tensor([int(ok)], device=dev)
 dist.all_reduce(flag, op=dist.ReduceOp.MIN)
 if rank == 0:
