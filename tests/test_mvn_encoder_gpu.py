@@ -74,6 +74,22 @@ def test_sample_site_matches_fp64(ops, B, K, H, S, inject):
     assert_close(r["logdet"], torch.diagonal(raw, dim1=1, dim2=2).sum(1), TOL, TOL, "log det")
 
 
+def test_sample_site_with_location_head(ops):
+    """fc21 inside vipsy_mvn_encoder_sample: the same draws, x shifted by fc21(hidden) instead of a given mu."""
+    B, K, H = 300, 21, 24
+    d = make(B, 4, K, H, 2, seed=77)
+    g = torch.Generator().manual_seed(3)
+    w21, b21 = (torch.rand(K, H, generator=g) - 0.5) * 0.4, torch.randn(K, generator=g)
+    loc = d["hidden"].double() @ w21.double().T + b21.double()
+    cu = {k: v.cuda() for k, v in d.items()}
+    r = ops.mvn_encoder_sample(None, cu["hidden"], cu["w22"], cu["b22"], w21=w21.cuda(), b21=b21.cuda(), n_particles=2, seed=4, offset=1)
+    r0 = ops.mvn_encoder_sample(loc.float().cuda(), cu["hidden"], cu["w22"], cu["b22"], n_particles=2, seed=4, offset=1)
+    assert torch.equal(r["eps"], r0["eps"]) and torch.equal(r["diag"], r0["diag"])
+    raw = o.tril_from_packed(d["hidden"].double() @ d["w22"].double().T + d["b22"].double(), K)
+    x = loc.unsqueeze(0) + torch.einsum("bij,sbj->sbi", o.lower_cholesky(raw), r["eps"].cpu().double())
+    assert_close(r["x"], x, TOL, TOL, "x")
+
+
 @pytest.mark.parametrize("B,J,K,H,S,model", [(300, 40, 10, 16, 1, "irt_2pl"), (128, 20, 8, 64, 1, "irt_2pl"),
                                              (257, 33, 37, 20, 2, "irt_2pl"), (500, 12, 3, 8, 1, "irt_2pl"),
                                              (200, 40, 12, 32, 3, "irt_3pl"), (130, 70, 9, 64, 1, "irt_4pl"),

@@ -387,15 +387,26 @@ def _mvn_workspace_bytes(K: int, H: int) -> int:
     return ((pp + 127) // 128 * (2 * 128 * kh * 2) + 255) & ~255
 
 
-def mvn_encoder_sample(mu: torch.Tensor, hidden: torch.Tensor, w22: torch.Tensor, b22: torch.Tensor, *,
+def mvn_encoder_sample(mu: Optional[torch.Tensor], hidden: torch.Tensor, w22: torch.Tensor, b22: torch.Tensor, *,
+                       w21: Optional[torch.Tensor] = None, b21: Optional[torch.Tensor] = None,
                        eps: Optional[torch.Tensor] = None, n_particles: int = 1, seed: int = 0, offset: int = 0,
                        person_offset: int = 0) -> Dict[str, torch.Tensor]:
     """The sample site of VaeIRT's amortised MVN guide (vi.py:693) with MvnEncoder's fc22 fused in:
     x [S, B, K] = mu + L eps with L = tril(raw, -1) + diag(exp(raw_ii)), raw = fc22(hidden) evaluated on the
-    tensor cores and consumed on chip.  Also returns the draws, diag L and sum_i log L_ii."""
-    mu_, h_, w_, b_ = _f32(mu, "mu"), _f32(hidden, "hidden"), _f32(w22, "w22"), _f32(b22, "b22")
+    tensor cores and consumed on chip.  Also returns the draws, diag L and sum_i log L_ii.  With ``w21`` / ``b21``
+    (fc21) the location is computed inside the call too and ``mu`` may be None."""
+    h_, w_, b_ = _f32(hidden, "hidden"), _f32(w22, "w22"), _f32(b22, "b22")
+    w21_, b21_ = _f32(w21, "w21", None), _f32(b21, "b21", None)
+    if mu is None:
+        if w21_ is None or b21_ is None:
+            raise ValueError("mvn_encoder_sample: mu or (w21, b21) is required")
+        mu_ = torch.empty((h_.shape[0], w21_.shape[0]), dtype=torch.float32, device=h_.device)   # shape only
+    else:
+        mu_ = _f32(mu, "mu")
     B, K = mu_.shape
     H = h_.shape[1]
+    if w21_ is not None and (tuple(w21_.shape) != (K, H) or b21_ is None or b21_.numel() != K):
+        raise ValueError("w21 must be K x H with b21 of K entries")
     if h_.shape[0] != B or w_.shape != (K * (K + 1) // 2, H) or b_.numel() != K * (K + 1) // 2:
         raise ValueError("hidden must be B x H, w22 K(K+1)/2 x H, b22 K(K+1)/2")
     eps_ = _f32(eps, "eps", None)
@@ -407,6 +418,8 @@ def mvn_encoder_sample(mu: torch.Tensor, hidden: torch.Tensor, w22: torch.Tensor
     a.irt.mu, a.irt.eps = _ptr(mu_), _ptr(eps_)
     a.irt.seed, a.irt.offset, a.irt.person_offset = seed, offset, person_offset
     a.n_hidden, a.hidden, a.w22, a.b22 = H, _ptr(h_), _ptr(w_), _ptr(b_)
+    if w21_ is not None:
+        a.w21, a.b21 = _ptr(w21_), _ptr(b21_)
     ws = _workspace("mvn_sample", _mvn_workspace_bytes(K, H), dev)
     a.workspace, a.workspace_bytes = _ptr(ws), ws.numel()
     out = {"x": torch.empty((S, B, K), dtype=torch.float32, device=dev),
@@ -415,7 +428,7 @@ def mvn_encoder_sample(mu: torch.Tensor, hidden: torch.Tensor, w22: torch.Tensor
            "logdet": torch.empty(B, dtype=torch.float32, device=dev)}
     N.check(N.lib().vipsy_mvn_encoder_sample(C.byref(a), _ptr(out["x"]), _ptr(out["eps"]), _ptr(out["diag"]),
                                              _ptr(out["logdet"]), _stream()))
-    out["_keepalive"] = (mu_, h_, w_, b_, eps_, ws)
+    out["_keepalive"] = (mu_, h_, w_, b_, eps_, ws, w21_, b21_)
     return out
 
 
