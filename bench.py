@@ -75,17 +75,34 @@ def time_oracle(n_persons, steps, warmup):
     return dt, torch.get_num_threads()
 
 
+REF_SAMPLE_PERSONS = 20_000
+
+
+def config_dict(world):
+    """`config` of the JSON line -- the same dict, key for key, in both arms (the driver compares them)."""
+    return {
+        "workload": WORKLOAD, "persons_per_gpu": N_PERSONS, "items": N_ITEMS, "particles": N_PARTICLES,
+        "model": MODEL, "parallelism": f"person-shard x{world}",
+        "exchange": "none" if world == 1 else "one packed sum of item gradients + loss per step",
+        "noise": "gpu arm: in-kernel Philox4x32-10; reference arm: injected torch.randn",
+        "l2": "gpu arm: flushed between steps (256 MiB memset outside the per-step events); reference arm: CPU",
+        "timing": "gpu arm: sum of per-step CUDA-event intervals, max over ranks; reference arm: perf_counter "
+                  "around the steps on rank 0",
+        "reference_arm_sample": f"{REF_SAMPLE_PERSONS} persons x {N_ITEMS} items x S={N_PARTICLES} per step",
+    }
+
+
 def run_reference(args, rank, world):
     if rank != 0:
         return
-    n = 20_000
+    n = REF_SAMPLE_PERSONS
     dt, threads = time_oracle(n, args.steps, args.warmup)
     value = n * N_ITEMS * N_PARTICLES / dt
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "sample": f"{n} persons x {N_ITEMS} items x S={N_PARTICLES} per step"},
+        "config": config_dict(world),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
                          "sample": f"{n} persons x {N_ITEMS} items x S={N_PARTICLES}, torch-CPU oracle "
                                    "(restated Pyro Trace_ELBO, no Pyro overhead), fp32"},
@@ -434,12 +451,9 @@ def run_ours(args, rank, world, local_rank):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "persons_per_gpu": N_PERSONS, "items": N_ITEMS, "particles": N_PARTICLES,
-                   "model": MODEL, "noise": "in-kernel Philox4x32-10", "parallelism": f"person-shard x{world}",
-                   "exchange": ("none" if world == 1 else ("vipsy_peer_allreduce: one kernel over NVLink peer memory"
-                                                           if par is not None else "2 x NCCL all_reduce")),
-                   "l2": "flushed between steps (256 MiB memset outside the per-step events)",
-                   "timing": "sum of per-step CUDA-event intervals, max over ranks"},
+        "config": config_dict(world),
+        "exchange_impl": ("none" if world == 1 else ("vipsy_peer_allreduce: one kernel over NVLink peer memory"
+                                                     if par is not None else "2 x NCCL all_reduce")),
         "clocks": {"sm_mhz": ck["sm_mhz"], "sm_max_mhz": ck["sm_max_mhz"], "reasons": ck["reasons"],
                    "power_w_max": ck["power_w_max"]},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": host.h2d_bytes,

@@ -23,12 +23,122 @@
 
 namespace vipsy {
 
+// Item loop of the pathwise estimator as ONE basic block per item (PIPE instantiation of the kernel below).
+// The lane-per-person loop used to spend a quarter of each item in a serial chain that feeds nothing to the
+// MUFU pipe: response byte -> vote -> branch -> table loads -> evaluations -> six dependent shuffles ->
+// shared-memory add.  Here (i) the cross-warp reduction of item j-1 is issued inside the evaluations of item j
+// (the sums wait in registers; the first round adds zeros to row 0), (ii) missing cells are evaluated like
+// y = 1 and masked by selects instead of a divergent branch, (iii) the response byte is fetched one item
+// ahead, and (iv) the rational-form / clamp choice is made per tile outside the loop (MODE), so nothing splits
+// the block and the scheduler interleaves the shuffle chain with the MUFU stream.
+// MODE 0: probability-clamp form; 1: rational form, exponent clamped; 2: rational form, exponent bounded
+// by the caller (no FMNMX).  Same sums in the same order as the branchy loop: bit-identical results.
+template <int MODEL, int SC, int MODE>
+struct UniItem {
+  static constexpr int NQ = MODEL;
+  // evaluates item j for the lane's person; v[] = the lane's terms of the item-gradient sums (masked)
+  static __device__ __forceinline__ void eval(const int j, const unsigned code, const float4* __restrict__ tab,
+                                              const float2* __restrict__ tab2, const float mu, const float sg,
+                                              const typename NoiseVec<SC>::type (&eps)[SC / NoiseVec<SC>::W],
+                                              float (&v)[NQ], float& Lsum, float& G1, float& G2) {
+    const bool obs = code != 255u;
+    const float4 it = tab[j];
+    const float2 it2 = tab2[j];
+    const bool y1 = code != 0u;                                     // a missing cell runs as y = 1 and is masked below
+    const float A = y1 ? it.x : -it.x, Bc = y1 ? it.y : -it.y;
+    const float T0 = fmaf(A, mu, Bc), T1 = A * sg;
+    const float base = MODEL >= 3 ? (y1 ? it.z : it2.y) : 0.f;
+    float W1, W2, A1, A2, Lj = 0.f;
+    float dummy[1];
+    if constexpr (MODE == 0) item_evals<MODEL, false, SC, false>(it.w, base, T0, T1, eps, dummy, W1, W2, A1, A2, Lj);
+    else if constexpr (MODE == 1) item_evals<MODEL, false, SC, true, true>(it.w, base, T0, T1, eps, dummy, W1, W2, A1, A2, Lj);
+    else item_evals<MODEL, false, SC, true, false>(it.w, base, T0, T1, eps, dummy, W1, W2, A1, A2, Lj);
+    const float sgn = obs ? (y1 ? 1.f : -1.f) : 0.f;
+    W1 *= sgn; W2 *= sgn;
+    Lsum += obs ? Lj : 0.f;
+    G1 = fmaf(it2.x, W1, G1);
+    G2 = fmaf(it2.x, W2, G2);
+    v[0] = W1;
+    if constexpr (NQ >= 2) v[1] = fmaf(sg, W2, mu * W1);
+    if constexpr (NQ >= 3) v[2] = obs ? (y1 ? A2 : -A1) : 0.f;
+    if constexpr (NQ >= 4) v[3] = obs ? (y1 ? A1 : -A2) : 0.f;
+  }
+};
+
+template <int MODEL, int SC, int MODE, int UNR>
+__device__ __forceinline__ void uni_item_loop(const int J, const float4* __restrict__ tab, const float2* __restrict__ tab2,
+                                              const unsigned char* __restrict__ yrow, const bool valid, const int lane,
+                                              float* __restrict__ acc, const float mu, const float sg,
+                                              const typename NoiseVec<SC>::type (&eps)[SC / NoiseVec<SC>::W],
+                                              float& Lsum, float& G1, float& G2) {
+  constexpr int NQ = MODEL;
+  using It = UniItem<MODEL, SC, MODE>;
+  const int own = warp_sum_multi_owner<NQ>(lane);
+  float vp[UNR][NQ];
+  int jp[UNR];
+#pragma unroll
+  for (int u = 0; u < UNR; ++u) {
+    jp[u] = 0;
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) vp[u][q] = 0.f;
+  }
+  // response bytes one step ahead; reads past the row stay inside the warp's tile buffer (16 bytes of slack)
+  unsigned next[UNR];
+#pragma unroll
+  for (int u = 0; u < UNR; ++u) next[u] = yrow[u < J ? u : 0];
+  int j = 0;
+  for (; j + UNR <= J; j += UNR) {
+    unsigned code[UNR];
+    bool any_obs = false;
+#pragma unroll
+    for (int u = 0; u < UNR; ++u) {
+      code[u] = valid ? next[u] : 255u;
+      any_obs |= code[u] != 255u;
+    }
+#pragma unroll
+    for (int u = 0; u < UNR; ++u) next[u] = yrow[(j + UNR + u < J ? j + UNR + u : j)];
+    if (!__any_sync(0xffffffffu, any_obs)) continue;
+    // the previous step's items cross the warp while this step's are evaluated
+    float v[UNR][NQ];
+#pragma unroll
+    for (int u = 0; u < UNR; ++u) It::eval(j + u, code[u], tab, tab2, mu, sg, eps, v[u], Lsum, G1, G2);
+#pragma unroll
+    for (int u = 0; u < UNR; ++u) {
+      const float r = warp_sum_multi<NQ>(vp[u], lane);
+      if (own >= 0) acc[own * J + jp[u]] += r;
+    }
+#pragma unroll
+    for (int u = 0; u < UNR; ++u) {
+      jp[u] = j + u;
+#pragma unroll
+      for (int q = 0; q < NQ; ++q) vp[u][q] = v[u][q];
+    }
+  }
+#pragma unroll
+  for (int u = 0; u < UNR; ++u) {
+    const float r = warp_sum_multi<NQ>(vp[u], lane);
+    if (own >= 0) acc[own * J + jp[u]] += r;
+  }
+  if constexpr (UNR > 1) {
+    for (; j < J; ++j) {                                            // J % UNR items, unpipelined
+      const unsigned code = valid ? (unsigned)yrow[j] : 255u;
+      if (!__any_sync(0xffffffffu, code != 255u)) continue;
+      float v[NQ];
+      It::eval(j, code, tab, tab2, mu, sg, eps, v, Lsum, G1, G2);
+      const float r = warp_sum_multi<NQ>(v, lane);
+      if (own >= 0) acc[own * J + j] += r;
+    }
+  }
+}
+
 // MODEL: 1..4 (number of item parameters).  SCORE: REINFORCE estimator for the
 // guide parameters.  SC: particles kept in registers at once (S % SC == 0).
 // FAST (4PL only): compile in the rational-form path; each CTA checks the item
 // table once and uses it only if no item can reach the probability clamp.
-template <int MODEL, bool SCORE, int SC, bool FAST>
+// PIPE (pathwise only): the item loop is uni_item_loop above.
+template <int MODEL, bool SCORE, int SC, bool FAST, bool PIPE, int kUniUnroll = 1>
 __global__ void __launch_bounds__(kUniThreads, 4) irt_uni_kernel(const IrtUniParams p) {
+  static_assert(!(PIPE && SCORE), "the pipelined item loop serves the pathwise estimator");
   constexpr int NQ = MODEL;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int J = p.J;
@@ -51,6 +161,7 @@ __global__ void __launch_bounds__(kUniThreads, 4) irt_uni_kernel(const IrtUniPar
   }
   for (int i = threadIdx.x; i < kUniWarps * NQ * J; i += kUniThreads) acc_all[i] = 0.f;
   bool use_fast = false;
+  float amax = 0.f, bmax = 0.f;   // max |A'_j|, |B'_j| over the item table (PIPE && FAST: exponent bound per tile)
   if (FAST) {   // every item bounded away from the clamp => rational form is safe
     int ok = 1;
     for (int j = threadIdx.x; j < J; j += kUniThreads) {
@@ -58,6 +169,17 @@ __global__ void __launch_bounds__(kUniThreads, 4) irt_uni_kernel(const IrtUniPar
       ok &= (cj >= 1e-3f) && (dj <= 1.f - 1e-3f) && (dj - cj >= 1e-3f);
     }
     use_fast = __syncthreads_and(ok) != 0;
+    if (PIPE) {
+      for (int j = lane; j < J; j += 32) {
+        amax = fmaxf(amax, fabsf(tab[j].x));
+        bmax = fmaxf(bmax, fabsf(tab[j].y));
+      }
+#pragma unroll
+      for (int o = 16; o; o >>= 1) {
+        amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+        bmax = fmaxf(bmax, __shfl_xor_sync(0xffffffffu, bmax, o));
+      }
+    }
   } else {
     __syncthreads();
   }
@@ -151,6 +273,27 @@ __global__ void __launch_bounds__(kUniThreads, 4) irt_uni_kernel(const IrtUniPar
       }
 
       // ---- items ----------------------------------------------------------
+      if constexpr (PIPE) {
+#define UNI_LOOP(MODE) \
+  uni_item_loop<MODEL, SC, MODE, kUniUnroll>(J, tab, tab2, yrow, valid, lane, acc, mu, sg, eps, Lsum, G1, G2)
+        if (FAST && use_fast) {
+          // |tt| <= max|A'| (|mu| + sigma max|eps|) + max|B'| for every item and particle of the person
+          float emax = 0.f;
+#pragma unroll
+          for (int i = 0; i < SC / VW; ++i) {
+            if constexpr (VW == 2) emax = fmaxf(emax, fmaxf(fabsf(eps[i].x), fabsf(eps[i].y)));
+            else emax = fmaxf(emax, fabsf(eps[i]));
+          }
+          const float bound = fmaf(amax, fmaf(fabsf(sg), emax, fabsf(mu)), bmax);
+          if (__all_sync(0xffffffffu, bound < 60.f))      // false for NaN / inf inputs as well
+            UNI_LOOP(2);
+          else
+            UNI_LOOP(1);
+        } else {
+          UNI_LOOP(0);
+        }
+#undef UNI_LOOP
+      } else
       for (int j = 0; j < J; ++j) {
         const unsigned code = valid ? (unsigned)yrow[j] : 255u;
         const bool obs = code != 255u;
@@ -253,9 +396,9 @@ __global__ void __launch_bounds__(kUniThreads, 4) irt_uni_kernel(const IrtUniPar
 // ---------------------------------------------------------------------------
 constexpr int kUniMaxCtasPerSM = 8;
 
-template <int MODEL, bool SCORE, int SC, bool FAST>
-static int launch_one(IrtUniParams& p, size_t smem, cudaStream_t st, int* grid_out) {
-  auto k = irt_uni_kernel<MODEL, SCORE, SC, FAST>;
+template <int MODEL, bool SCORE, int SC, bool FAST, bool PIPE, int UNR = 1>
+static int launch_one_k(IrtUniParams& p, size_t smem, cudaStream_t st, int* grid_out) {
+  auto k = irt_uni_kernel<MODEL, SCORE, SC, FAST, PIPE, UNR>;
   static OccCache occ_cache;   // per instantiation
   int occ = 0;
   if (smem > 48 * 1024) VIPSY_CUDA_CHECK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -269,6 +412,16 @@ static int launch_one(IrtUniParams& p, size_t smem, cudaStream_t st, int* grid_o
   k<<<(int)ctas, kUniThreads, smem, st>>>(p);
   VIPSY_CUDA_CHECK(cudaGetLastError());
   return VIPSY_OK;
+}
+
+// Pathwise estimator: pipelined item loop, two items per block when at most 8 particles sit in registers
+// (measured, 1M x 100 4PL: S=32 2.105 -> 2.015 ms with one item per block, 2.047 with two; S=8 0.742 -> 0.700 /
+// 0.635 ms; S=4 0.510 -> 0.489 / 0.449 ms; profiles/r02_uni_pipelined_ab.txt).  The REINFORCE estimator keeps
+// the branchy loop.
+template <int MODEL, bool SCORE, int SC, bool FAST>
+static int launch_one(IrtUniParams& p, size_t smem, cudaStream_t st, int* grid_out) {
+  if constexpr (SCORE) return launch_one_k<MODEL, SCORE, SC, FAST, false>(p, smem, st, grid_out);
+  else return launch_one_k<MODEL, SCORE, SC, FAST, true, (SC <= 8 ? 2 : 1)>(p, smem, st, grid_out);
 }
 
 template <int MODEL, bool SCORE, bool FAST>

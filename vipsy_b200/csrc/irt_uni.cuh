@@ -91,11 +91,19 @@ template <> struct NoiseVec<1> { using type = float; static constexpr int W = 1;
 // unreachable): q = (base e' + base + (d-c)) / (1+e') =: num/ope, and the single
 // reciprocal R = 1/(num ope) yields sp = num R, sp/q = ope R, w = e' R:
 // 2.125 MUFU per evaluation instead of 3.25.
-template <int MODEL, bool SCORE, int SC, bool FASTPATH>
-__device__ __forceinline__ void item_evals(const float dmc, const float base, const float T0, const float T1,
-                                           const typename NoiseVec<SC>::type (&eps)[SC / NoiseVec<SC>::W],
-                                           float (&lls)[SCORE ? SC : 1], float& W1o, float& W2o, float& A1o,
-                                           float& A2o, float& Lj) {
+//
+// CLAMP = false (FASTPATH only): the caller has bounded tt below 60 for every particle, so the two FMNMX per
+// pair are dropped.  Sums start from the first pair's terms instead of 0 / 1 (the compiler does not fold
+// packed operations on constants).
+// item_evals_v leaves the sums as pairs and the last group's probability product unlogged; item_evals is the
+// complete form.
+template <int MODEL, bool SCORE, int SC, bool FASTPATH, bool CLAMP = true>
+__device__ __forceinline__ void item_evals_v(const float dmc, const float base, const float T0, const float T1,
+                                             const typename NoiseVec<SC>::type (&eps)[SC / NoiseVec<SC>::W],
+                                             float (&lls)[SCORE ? SC : 1], typename NoiseVec<SC>::type& W1o,
+                                             typename NoiseVec<SC>::type& W2o, typename NoiseVec<SC>::type& A1o,
+                                             typename NoiseVec<SC>::type& A2o, typename NoiseVec<SC>::type& prodo,
+                                             float& Lj) {
   using V = typename NoiseVec<SC>::type;
   constexpr int W = NoiseVec<SC>::W;
   constexpr int NV = SC / W;
@@ -106,7 +114,8 @@ __device__ __forceinline__ void item_evals(const float dmc, const float base, co
     const V basev = vbcast<V>(base), bdv = vbcast<V>(base + dmc);
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
-      const V tt = vmin(vfma(T1v, eps[i], T0v), 60.f);
+      V tt = vfma(T1v, eps[i], T0v);
+      if constexpr (CLAMP) tt = vmin(tt, 60.f);
       const V e = vex2(tt);
       const V ope = vadd(e, one);
       const V num = vfma(basev, e, bdv);
@@ -115,15 +124,19 @@ __device__ __forceinline__ void item_evals(const float dmc, const float base, co
       const V q = vmul(num, sp);
       const V us = vmul(ope, R);                                 // sp / q = 1 / num
       const V w = vmul(e, R);                                    // sp (1-sp) / q
-      A1 = vadd(A1, us);
-      A2 = vfma(us, e, A2);                                      // (1-sp) / q = e' / num
-      W1 = vadd(W1, w);
-      W2 = vfma(w, eps[i], W2);
+      if (i == 0) {
+        A1 = us; A2 = vmul(us, e); W1 = w; W2 = vmul(w, eps[i]);
+      } else {
+        A1 = vadd(A1, us);
+        A2 = vfma(us, e, A2);                                    // (1-sp) / q = e' / num
+        W1 = vadd(W1, w);
+        W2 = vfma(w, eps[i], W2);
+      }
       if constexpr (SCORE) {
         vlg2_add(q, &lls[i * W]);
       } else {
-        prod = vmul(prod, q);
-        if ((i % GROUP) == GROUP - 1 || i == NV - 1) { Lj += lg2_approx(vhprod(prod)); prod = one; }
+        prod = (i % GROUP) == 0 ? q : vmul(prod, q);
+        if ((i % GROUP) == GROUP - 1 && i != NV - 1) Lj += lg2_approx(vhprod(prod));
       }
     }
   } else {
@@ -152,11 +165,22 @@ __device__ __forceinline__ void item_evals(const float dmc, const float base, co
       if constexpr (SCORE) {
         vlg2_add(qc, &lls[i * W]);
       } else {
-        prod = vmul(prod, qc);
-        if ((i % GROUP) == GROUP - 1 || i == NV - 1) { Lj += lg2_approx(vhprod(prod)); prod = one; }
+        prod = (i % GROUP) == 0 ? qc : vmul(prod, qc);
+        if ((i % GROUP) == GROUP - 1 && i != NV - 1) Lj += lg2_approx(vhprod(prod));
       }
     }
   }
+  W1o = W1; W2o = W2; A1o = A1; A2o = A2; prodo = prod;
+}
+
+template <int MODEL, bool SCORE, int SC, bool FASTPATH, bool CLAMP = true>
+__device__ __forceinline__ void item_evals(const float dmc, const float base, const float T0, const float T1,
+                                           const typename NoiseVec<SC>::type (&eps)[SC / NoiseVec<SC>::W],
+                                           float (&lls)[SCORE ? SC : 1], float& W1o, float& W2o, float& A1o,
+                                           float& A2o, float& Lj) {
+  typename NoiseVec<SC>::type W1, W2, A1, A2, prod;
+  item_evals_v<MODEL, SCORE, SC, FASTPATH, CLAMP>(dmc, base, T0, T1, eps, lls, W1, W2, A1, A2, prod, Lj);
+  if constexpr (!SCORE) Lj += lg2_approx(vhprod(prod));
   W1o = vhsum(W1); W2o = vhsum(W2); A1o = vhsum(A1); A2o = vhsum(A2);
 }
 
