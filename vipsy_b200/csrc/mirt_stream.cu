@@ -10,7 +10,12 @@
 // (coalesced 128-byte row segments straight from / to global memory, no shared-memory staging, no
 // CTA barriers), 32 rows of partial dot products per lane reduced with one transposing butterfly
 // (31 shuffles per 32 rows), noise regenerated from the Philox counter in both kernels.
+#include <algorithm>
+#include <cstdlib>
+#include <type_traits>
+
 #include "mirt.cuh"
+#include "umma.cuh"
 
 namespace vipsy {
 
@@ -423,6 +428,219 @@ __global__ void __launch_bounds__(kStreamThreads) mirt_cholgrad_stream_multi_ker
   }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Sampler fed by bulk copies (packed per-person factor, S <= 2): the factor stream is pulled through shared
+// memory by one producer thread with cp.async.bulk into a ring of stages that complete on mbarriers, so the
+// bytes in flight (nst x 32-40 KB per SM) no longer depend on how many load registers the math warps can spare,
+// and the math reads rows with conflict-free LDS instead of predicated global loads.
+//   stage  = G consecutive persons, G = 1 / 2 / 4 so that G K(K+1)/2 floats are a multiple of 16 bytes (what a
+//            bulk copy needs; K = 100: two persons, 40 400 B)
+//   group  = 4 warps working on one stage; a person belongs to WPP = 4 / G of them, warp h of a person owns the
+//            rows i = WPP ri + h: the column chunk that holds the diagonal, (WPP ri) / 32, is a compile-time
+//            constant of the unrolled row loop, rows at or beyond K cost nothing but a uniform test
+//   ring   = item n of the CTA -> stage n % nst, group n % 4 (nst = 5 at K = 100: four stages being read, one in
+//            flight); noise, means and the noise stash are prepared BEFORE the warp waits for its stage
+// The diagonal term L_ii eps_i (through exp for a raw factor), diag L and the log-determinant are finished by
+// the lane that owns row i after the transposing butterfly.  aux slot h of a person = its warp h's share.
+constexpr int kBulkGroups = 4, kBulkGroupWarps = 4;
+constexpr int kBulkConsumerWarps = kBulkGroups * kBulkGroupWarps;
+constexpr int kBulkThreads = (kBulkConsumerWarps + 1) * 32;
+constexpr int kBulkMaxStages = 6;
+
+template <int S, int WPP>
+__global__ void __launch_bounds__(kBulkThreads, 1) mirt_sample_bulk_kernel(const MirtParams p, const int nst,
+                                                                         const uint32_t stage_bytes) {
+  extern __shared__ __align__(128) unsigned char bulk_smem[];
+  constexpr int G = 4 / WPP;          // persons per stage
+  constexpr int NBLK = 4 / WPP;       // 32-row blocks a warp can own (K <= 128)
+  const int K = p.K, P = tri_off(K);
+  float* stash_all = reinterpret_cast<float*>(bulk_smem + (size_t)nst * stage_bytes);       // [warp][S][128]
+  uint64_t* full = reinterpret_cast<uint64_t*>(stash_all + kBulkConsumerWarps * S * 128);
+  uint64_t* empty = full + kBulkMaxStages;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < nst; ++i) {
+      umma::mbar_init(full + i, 1);
+      umma::mbar_init(empty + i, kBulkGroupWarps);
+    }
+    umma::fence_mbar_init();
+  }
+  __syncthreads();
+  const int64_t ngroups = (p.B + G - 1) / G;
+  const int64_t nitems = blockIdx.x < ngroups ? (ngroups - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+
+  if (warp == kBulkConsumerWarps) {                       // ---- producer
+    if (lane == 0) {
+      for (int64_t n = 0; n < nitems; ++n) {
+        const int st = (int)(n % nst);
+        const uint32_t use = (uint32_t)(n / nst);
+        if (use > 0) umma::mbar_wait(empty + st, (use - 1) & 1);
+        const int64_t b0 = (blockIdx.x + n * gridDim.x) * G;
+        const int nv = (int)min((int64_t)G, p.B - b0);
+        float* dst = reinterpret_cast<float*>(bulk_smem + (size_t)st * stage_bytes);
+        const float* src = p.chol + b0 * P;
+        const uint32_t bytes = (uint32_t)nv * (uint32_t)P * 4u, bulk = bytes & ~15u;
+        for (uint32_t o = bulk; o < bytes; o += 4) dst[o >> 2] = src[o >> 2];   // last, partial group only
+        umma::bulk_load(dst, src, bulk, full + st);
+      }
+    }
+    return;
+  }
+
+  // ---- consumers
+  const int g = warp / kBulkGroupWarps, wg = warp % kBulkGroupWarps, pi = wg / WPP, h = wg % WPP;
+  float* es = stash_all + (size_t)warp * S * 128;
+  for (int64_t n = g; n < nitems; n += kBulkGroups) {
+    const int st = (int)(n % nst);
+    const uint32_t use = (uint32_t)(n / nst);
+    const int64_t b_raw = (blockIdx.x + n * gridDim.x) * G + pi;
+    const bool valid = b_raw < p.B;                      // warp-uniform; a person beyond the batch (last, partial
+    const int64_t b = valid ? b_raw : p.B - 1;           // group) runs as the last person and stores nothing
+    float e[S][4], mu_l[NBLK];
+#pragma unroll
+    for (int s = 0; s < S; ++s) noise_lane4(p, s, b, lane, e[s]);
+#pragma unroll
+    for (int rblk = 0; rblk < NBLK; ++rblk) {
+      const int il = WPP * (32 * rblk + lane) + h;
+      mu_l[rblk] = il < K ? p.mu[b * K + il] : 0.f;
+    }
+#pragma unroll
+    for (int s = 0; s < S; ++s)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) es[s * 128 + lane + 32 * c] = e[s][c];
+    __syncwarp();
+    umma::mbar_wait(full + st, use & 1);
+    const float* Ls = reinterpret_cast<const float*>(bulk_smem + (size_t)st * stage_bytes) + (size_t)(valid ? pi : 0) * P;
+    const float* Ll = Ls + lane;
+    float auxp = 0.f;
+#pragma unroll
+    for (int rblk = 0; rblk < NBLK; ++rblk) {
+      float part[S][32];
+      // rows of the block, h as a compile-time constant: offsets, chunk counts and diagonal positions are
+      // immediates.  CHECK = false: every row of the group of 8 is below K.
+      auto rows8 = [&](auto hc, auto r8c, auto checkc) {
+        constexpr int H = decltype(hc)::value, R8 = decltype(r8c)::value;
+        constexpr bool CHECK = decltype(checkc)::value;
+#pragma unroll
+        for (int rr = 0; rr < 8; ++rr) {
+          constexpr int kW = WPP;
+          const int r = R8 + rr, i = kW * (32 * rblk + r) + H;           // constants after unrolling
+          const int nch = i >> 5, lim = i - 32 * nch;                    // lanes left of the diagonal in chunk nch
+          // a row at or beyond K reads row 0 instead (in bounds); its sum is never used
+          const float* Lrow = Ll + ((!CHECK || i < K) ? tri_off(i) : 0);
+          float acc[S];
+#pragma unroll
+          for (int s = 0; s < S; ++s) acc[s] = 0.f;
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            if (c < nch) {
+              const float v = Lrow[32 * c];
+#pragma unroll
+              for (int s = 0; s < S; ++s) acc[s] = fmaf(v, e[s][c], acc[s]);
+            } else if (c == nch && lim > 0) {
+              const float v = lane < lim ? Lrow[32 * c] : 0.f;
+#pragma unroll
+              for (int s = 0; s < S; ++s) acc[s] = fmaf(v, e[s][c], acc[s]);
+            }
+          }
+#pragma unroll
+          for (int s = 0; s < S; ++s) part[s][r] = acc[s];
+        }
+      };
+      auto fill = [&](auto hc) {
+        constexpr int H = decltype(hc)::value;
+        auto group = [&](auto r8c) {
+          constexpr int R8 = decltype(r8c)::value;
+          if (WPP * (32 * rblk + R8 + 7) + H < K) {
+            rows8(hc, r8c, std::false_type{});
+          } else if (WPP * (32 * rblk + R8) + H < K) {
+            rows8(hc, r8c, std::true_type{});
+          } else {
+#pragma unroll
+            for (int rr = 0; rr < 8; ++rr)
+#pragma unroll
+              for (int s = 0; s < S; ++s) part[s][R8 + rr] = 0.f;
+          }
+        };
+        group(std::integral_constant<int, 0>{});
+        group(std::integral_constant<int, 8>{});
+        group(std::integral_constant<int, 16>{});
+        group(std::integral_constant<int, 24>{});
+      };
+      if constexpr (WPP == 1) {
+        fill(std::integral_constant<int, 0>{});
+      } else if constexpr (WPP == 2) {
+        if (h == 0) fill(std::integral_constant<int, 0>{});
+        else fill(std::integral_constant<int, 1>{});
+      } else {
+        if (h == 0) fill(std::integral_constant<int, 0>{});
+        else if (h == 1) fill(std::integral_constant<int, 1>{});
+        else if (h == 2) fill(std::integral_constant<int, 2>{});
+        else fill(std::integral_constant<int, 3>{});
+      }
+      // butterfly and the lane's row outside every branch: no convergence bookkeeping around the shuffles
+      const int il = WPP * (32 * rblk + lane) + h;         // the row this lane finishes
+      const bool own = il < K;
+      float lii = 1.f;
+      if (own) {
+        lii = Ls[tri_off(il) + il];
+        if (p.chol_raw) lii = __expf(lii);
+        auxp += (float)S * __logf(lii);
+        if (valid) p.diagL[b * K + il] = lii;
+      }
+#pragma unroll
+      for (int s = 0; s < S; ++s) {
+        const float tot = transpose_reduce32(part[s], lane);
+        if (own) {
+          const float ei = es[s * 128 + il];
+          const float xv = mu_l[rblk] + fmaf(lii, ei, tot);
+          if (valid) p.x[((int64_t)s * p.B + b) * K + il] = xv;
+          auxp = fmaf(0.5f * ei, ei, auxp);
+          auxp = fmaf(-0.5f * xv, xv, auxp);
+        }
+      }
+    }
+    auxp = warp_sum(auxp);
+    if (valid) {
+      if (lane == 0) p.aux[4 * b + h] = auxp;
+      if (h == 0 && lane >= WPP && lane < 4) p.aux[4 * b + lane] = 0.f;
+    }
+    __syncwarp();
+    if (lane == 0) umma::mbar_arrive(empty + st);
+  }
+}
+
+template <int S, int WPP>
+static int launch_sample_bulk_t(const MirtParams& p, int nst, uint32_t stage_bytes, size_t smem, cudaStream_t st) {
+  auto k = mirt_sample_bulk_kernel<S, WPP>;
+  VIPSY_CUDA_CHECK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  constexpr int G = 4 / WPP;
+  const int64_t ngroups = (p.B + G - 1) / G;
+  const int grid = (int)std::min<int64_t>(num_sms(), std::max<int64_t>(ngroups, 1));
+  k<<<grid, kBulkThreads, smem, st>>>(p, nst, stage_bytes);
+  VIPSY_CUDA_CHECK(cudaGetLastError());
+  return VIPSY_OK;
+}
+
+// VIPSY_NO_BULK=1 keeps the register-fed sampler reachable (A/B measurements).
+static bool bulk_disabled() {
+  static const bool v = [] { const char* e = getenv("VIPSY_NO_BULK"); return e && e[0] == '1'; }();
+  return v;
+}
+
+static bool sample_bulk_plan(const MirtParams& p, int* wpp, int* nst, uint32_t* stage_bytes, size_t* smem) {
+  if (bulk_disabled() || p.chol_layout != VIPSY_CHOL_PACKED || p.S > 2 || p.K <= 32 || p.K > 128) return false;
+  if (reinterpret_cast<uintptr_t>(p.chol) & 15) return false;
+  const int P = p.K * (p.K + 1) / 2;
+  *wpp = (P % 4 == 0) ? 4 : ((P % 2 == 0) ? 2 : 1);
+  *stage_bytes = (uint32_t)(4 / *wpp) * (uint32_t)P * 4u;
+  const size_t fixed = (size_t)kBulkConsumerWarps * p.S * 128 * 4 + 2 * kBulkMaxStages * 8;
+  const int fit = (int)((227 * 1024 - fixed) / *stage_bytes);
+  *nst = std::min(kBulkMaxStages, fit);
+  *smem = (size_t)*nst * *stage_bytes + fixed;
+  return *nst >= 2;
+}
+
 bool mirt_stream_supported(const MirtParams& p) {
   return p.cov_mode == VIPSY_COV_PERSON && p.S <= kCgMaxS && p.K <= 128 && p.K > 32;   // noise_lane4 needs the K > 32 layout
 }
@@ -434,6 +652,21 @@ static int stream_grid(const MirtParams& p, int max_grid) {
 }
 
 int launch_sample_stream(const MirtParams& p, int max_grid, cudaStream_t st) {
+  {
+    int wpp = 0, nst = 0;
+    uint32_t sb = 0;
+    size_t smem = 0;
+    if (sample_bulk_plan(p, &wpp, &nst, &sb, &smem)) {
+      if (p.S == 1) {
+        if (wpp == 4) return launch_sample_bulk_t<1, 4>(p, nst, sb, smem, st);
+        if (wpp == 2) return launch_sample_bulk_t<1, 2>(p, nst, sb, smem, st);
+        return launch_sample_bulk_t<1, 1>(p, nst, sb, smem, st);
+      }
+      if (wpp == 4) return launch_sample_bulk_t<2, 4>(p, nst, sb, smem, st);
+      if (wpp == 2) return launch_sample_bulk_t<2, 2>(p, nst, sb, smem, st);
+      return launch_sample_bulk_t<2, 1>(p, nst, sb, smem, st);
+    }
+  }
   const int g = stream_grid(p, max_grid);
   const bool packed = p.chol_layout == VIPSY_CHOL_PACKED;
   if (p.S == 1) {
