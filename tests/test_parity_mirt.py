@@ -211,3 +211,37 @@ def test_fused_small_k_score_function_estimator(ops, K, model, S, raw, layout):
     assert_close(gd if layout == "dense" else gd, rd if layout == "dense" else packed_of(rd), tol, tol, "d_chol")
     assert_close(got["d_a"], ref["d_a"], tol, tol, "d_a")
     assert_close(got["d_b"], ref["d_b"], tol, tol, "d_b")
+
+
+def test_bulk_fed_sampler_repeats_bit_for_bit_with_injected_noise(ops):
+    """The bulk-copy fed sampler (csrc/mirt_stream.cu) hands successive uses of a shared-memory stage to different
+    warp groups.  Injected noise skews the groups (its loads sit in front of the barrier wait); a group that ran a
+    ring ahead once took the pending parity of the previous use for its own (wrong draws, then a hang).  Every
+    kernel on the path is deterministic, so repeated evaluations must agree bit for bit -- and with the oracle."""
+    from vipsy_b200 import workloads
+    B, J, K = 60_000, 40, 100
+    w = workloads.mirt(B, J, K)
+    eps = ops.fill_normal(1, B, K, 3, 1)
+    junk = torch.empty(200 << 20, dtype=torch.uint8, device="cuda")
+    ref = None
+    for i in range(12):
+        junk.random_(0, 255)
+        r = ops.irt_elbo_grad(w["y"], w["mu"], chol=w["chol_packed_raw"], chol_packed=True, chol_raw=True, eps=eps,
+                              a=w["a"], b=w["b"], model="irt_2pl", a_free=w["a_free"])
+        cur = {k: r[k].clone() for k in ("loss", "d_mu", "d_chol", "d_a", "d_b")}
+        if ref is None:
+            ref = cur
+        for k in cur:
+            assert torch.equal(ref[k], cur[k]), (i, k)
+    # the draws themselves: x = mu + L eps against fp64 torch on a slice of persons
+    n = 2000
+    ti = torch.tril_indices(K, K, device="cuda")
+    L = torch.zeros(n, K, K, dtype=torch.float64, device="cuda")
+    L[:, ti[0], ti[1]] = w["chol_packed_raw"][-n:].double()
+    L = L.tril(-1) + torch.diag_embed(torch.diagonal(L, dim1=1, dim2=2).exp())
+    x = w["mu"][-n:].double() + torch.einsum("bij,bj->bi", L, eps[0, -n:].double())
+    # d mu = -scale (sum_j a_j dlb/dlogit_j - x): check it through the likelihood gradient of the same slice
+    y = w["y"][-n:]
+    gl = (y.double().clamp(max=1) - torch.sigmoid(x @ w["a"].double() + w["b"].double())) * (y != 255).double()
+    d_mu = -(gl @ w["a"].double().T - x)
+    assert_close(ref["d_mu"][-n:], d_mu, 2e-5)

@@ -439,7 +439,14 @@ __global__ void __launch_bounds__(kStreamThreads) mirt_cholgrad_stream_multi_ker
 //            rows i = WPP ri + h: the column chunk that holds the diagonal, (WPP ri) / 32, is a compile-time
 //            constant of the unrolled row loop, rows at or beyond K cost nothing but a uniform test
 //   ring   = item n of the CTA -> stage n % nst, group n % 4 (nst = 5 at K = 100: four stages being read, one in
-//            flight); noise, means and the noise stash are prepared BEFORE the warp waits for its stage
+//            flight); noise, means and the noise stash are prepared BEFORE the warp waits for its stage.
+//            Successive uses of a stage belong to DIFFERENT groups, and an mbarrier phase is one bit: a group that
+//            runs a whole ring ahead of a slower one would find the parity of use u - 1 still pending and take it
+//            for "use u has landed" (seen as wrong draws and, once the arrival counts were off, a hang -- with
+//            injected noise, whose loads skew the groups).  The producer therefore publishes how many items it
+//            has issued (`issued`, release / acquire through shared memory) and a group looks at a stage's `full`
+//            barrier only after its own item has been issued: every earlier use of the stage has then completed
+//            and the parity test is unambiguous.
 // The diagonal term L_ii eps_i (through exp for a raw factor), diag L and the log-determinant are finished by
 // the lane that owns row i after the transposing butterfly.  aux slot h of a person = its warp h's share.
 constexpr int kBulkGroups = 4, kBulkGroupWarps = 4;
@@ -457,12 +464,14 @@ __global__ void __launch_bounds__(kBulkThreads, 1) mirt_sample_bulk_kernel(const
   float* stash_all = reinterpret_cast<float*>(bulk_smem + (size_t)nst * stage_bytes);       // [warp][S][128]
   uint64_t* full = reinterpret_cast<uint64_t*>(stash_all + kBulkConsumerWarps * S * 128);
   uint64_t* empty = full + kBulkMaxStages;
+  volatile int* issued = reinterpret_cast<volatile int*>(empty + kBulkMaxStages);   // items the producer has issued
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
     for (int i = 0; i < nst; ++i) {
       umma::mbar_init(full + i, 1);
       umma::mbar_init(empty + i, kBulkGroupWarps);
     }
+    *issued = 0;
     umma::fence_mbar_init();
   }
   __syncthreads();
@@ -482,6 +491,8 @@ __global__ void __launch_bounds__(kBulkThreads, 1) mirt_sample_bulk_kernel(const
         const uint32_t bytes = (uint32_t)nv * (uint32_t)P * 4u, bulk = bytes & ~15u;
         for (uint32_t o = bulk; o < bytes; o += 4) dst[o >> 2] = src[o >> 2];   // last, partial group only
         umma::bulk_load(dst, src, bulk, full + st);
+        __threadfence_block();
+        *issued = (int)n + 1;
       }
     }
     return;
@@ -509,6 +520,8 @@ __global__ void __launch_bounds__(kBulkThreads, 1) mirt_sample_bulk_kernel(const
 #pragma unroll
       for (int c = 0; c < 4; ++c) es[s * 128 + lane + 32 * c] = e[s][c];
     __syncwarp();
+    while (*issued <= (int)n) {}                         // see the header: parity is only meaningful from here on
+    __threadfence_block();
     umma::mbar_wait(full + st, use & 1);
     const float* Ls = reinterpret_cast<const float*>(bulk_smem + (size_t)st * stage_bytes) + (size_t)(valid ? pi : 0) * P;
     const float* Ll = Ls + lane;
@@ -634,7 +647,7 @@ static bool sample_bulk_plan(const MirtParams& p, int* wpp, int* nst, uint32_t* 
   const int P = p.K * (p.K + 1) / 2;
   *wpp = (P % 4 == 0) ? 4 : ((P % 2 == 0) ? 2 : 1);
   *stage_bytes = (uint32_t)(4 / *wpp) * (uint32_t)P * 4u;
-  const size_t fixed = (size_t)kBulkConsumerWarps * p.S * 128 * 4 + 2 * kBulkMaxStages * 8;
+  const size_t fixed = (size_t)kBulkConsumerWarps * p.S * 128 * 4 + 2 * kBulkMaxStages * 8 + 16;
   const int fit = (int)((227 * 1024 - fixed) / *stage_bytes);
   *nst = std::min(kBulkMaxStages, fit);
   *smem = (size_t)*nst * *stage_bytes + fixed;
