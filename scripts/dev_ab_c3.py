@@ -8,7 +8,7 @@ def child(tag):
     from vipsy_b200 import ops, workloads
     from scripts.dev_bench_uni import timeit
     out = {}
-    for ci, (N, K, J, S) in enumerate(((200_000, 100, 500, 1), (30_001, 100, 60, 2), (20_000, 64, 40, 1), (20_003, 50, 40, 1))):
+    for ci, (N, K, J, S) in enumerate(((200_000, 100, 500, 1), (100_001, 100, 60, 2), (200_000, 64, 40, 1), (200_003, 50, 40, 1), (100_000, 128, 40, 1), (100_000, 96, 40, 1), (200_000, 40, 40, 1))):
         w = workloads.mirt(N, J, K)
         dchol = torch.zeros_like(w["chol_packed_raw"])
         dmu = torch.empty_like(w["mu"])
