@@ -405,7 +405,7 @@ def run_ours(args, rank, world, local_rank):
 
     def e2e_step(i):
         r = host(hy, hmu, hsg, hp["a"], hp["b"], hp["c"], hp["d"], n_particles=N_PARTICLES, scale=scale,
-                 seed=20261017, offset=5000 + i, person_offset=person_offset)
+                 seed=20261017, offset=5000 + i, person_offset=person_offset, n_masked=n_masked)
         if world > 1:
             g = r["item_grads"].to(dev, non_blocking=True)
             dist.all_reduce(g)
@@ -459,7 +459,7 @@ def run_ours(args, rank, world, local_rank):
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": host.h2d_bytes,
                 "d2h_bytes_per_step": host.d2h_bytes, "ms_per_step": e2e_s * 1e3,
                 "how": "vipsy_irt_host_step (C ABI, host buffers): pinned host y (2-bit transport rows) / mu / sigma -> "
-                       "6-chunk (wave-aligned, small first chunk) 3-stream pipeline (copy, expand + fused kernel, copy back) -> host per-person and item "
+                       "6-chunk (small first chunk) 3-stream pipeline (copy, fused kernel that expands the 2-bit rows while staging a tile, copy back) -> host per-person and item "
                        "grads + loss"},
         "gpu_launches": gpu_launches,
         "roofline": {"bound": "hbm", "achieved": achieved_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",

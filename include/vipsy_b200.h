@@ -64,8 +64,13 @@ enum { VIPSY_IRT_FLAG_STRICT = 1,
                                           warp-per-person row kernels, J <= 512 (256 for 3PL / 4PL))          */
        VIPSY_IRT_FLAG_MASKED_KNOWN = 16,/* n_masked_cells is valid: saves one counting pass over the batch rows
                                           in the K == 1, S > 1 path (the matrix is constant between steps)   */
-       VIPSY_IRT_FLAG_NO_FUSED = 32 };  /* 2 <= K <= 8, per-person factor: force the three-kernel path (sample,
+       VIPSY_IRT_FLAG_NO_FUSED = 32,    /* 2 <= K <= 8, per-person factor: force the three-kernel path (sample,
                                           contraction, guide gradient) instead of the single fused kernel    */
+       VIPSY_IRT_FLAG_Y_PACKED2 = 64 }; /* K == 1, S > 1, pathwise, J % 4 == 0, no idx: `y` holds the rows in the 2-bit
+                                          transport format (vipsy_pack_responses_2bit_host: 4 cells per byte, 0 / 1 /
+                                          3 = missing), y_row_stride = J / 4 bytes, y 4-byte aligned; the particle
+                                          kernel expands a tile while staging it -- no byte matrix in HBM (what
+                                          vipsy_irt_host_step uses for its chunks)                              */
 enum { VIPSY_CHOL_DENSE = 0,  /* row-major K x K, strict upper triangle ignored        */
        VIPSY_CHOL_PACKED = 1 };/* torch.tril_indices row-major order, K(K+1)/2 (vi.py:453) */
 

@@ -457,3 +457,26 @@ def test_vaeirt_mirt_fused_encoder_tail_equals_torch_autograd():
     for n in pf:
         assert_close(pf[n], pt[n], 2e-4, 2e-4, n)
     assert lf[-1] < lf[0]
+
+
+def test_host_step_direct_two_bit_rows_edge_shapes():
+    """2-bit rows expanded by the particle kernel itself (VIPSY_IRT_FLAG_Y_PACKED2, csrc/irt_uni.cu): ragged last tile,
+    several chunks, the caller's count of missing cells, and the fall-back through the expansion kernel when J % 4 != 0
+    or S == 1 -- all bit-identical per person to the device call on byte codes."""
+    from vipsy_b200 import ops, workloads
+    from vipsy_b200.host_api import IrtHostStep
+    for (N, J, S, model, chunks) in ((4099, 100, 32, "irt_4pl", 3), (777, 8, 4, "irt_2pl", 1), (2050, 36, 2, "irt_3pl", 2),
+                                     (1500, 50, 8, "irt_4pl", 2), (1500, 100, 1, "irt_2pl", 2)):
+        w = workloads.uni_irt(N, J, model, missing=0.2, seed=7)
+        names = ("a", "b", "c", "d")[:int(model[4])]                    # irt_2pl -> a, b; irt_3pl -> a, b, c; ...
+        kw = {k: w[k] for k in names}
+        ref = ops.irt_elbo_grad(w["y"], w["mu"], sigma=w["sigma"], n_particles=S, model=model, seed=9, offset=3, **kw)
+        hy = ops.pack_responses_2bit_host(w["y"].cpu())
+        host = IrtHostStep(N, J, model, n_chunks=chunks)
+        hp = {k: (w[k].cpu() if k in names + ("mu", "sigma") else None) for k in ("a", "b", "c", "d", "mu", "sigma")}
+        for n_masked in (None, int((w["y"] == 255).sum())):
+            got = host(hy, hp["mu"], hp["sigma"], hp["a"], hp["b"], hp["c"], hp["d"], n_particles=S, seed=9, offset=3,
+                       n_masked=n_masked)
+            assert torch.equal(got["d_mu"], ref["d_mu"].cpu()) and torch.equal(got["d_sigma"], ref["d_sigma"].cpu()), (N, J, S)
+            assert_close(got["item_grads"], ref["item_grads"], 1e-5, 1e-5, f"item grads {N}x{J} S={S}")
+            assert_close(got["loss"], ref["loss"], 1e-9, 1e-9, f"loss {N}x{J} S={S}")

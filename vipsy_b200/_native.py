@@ -24,6 +24,7 @@ IRT_FLAG_SPARSE = 4
 IRT_FLAG_NO_ROW = 8
 IRT_FLAG_MASKED_KNOWN = 16
 IRT_FLAG_NO_FUSED = 32
+IRT_FLAG_Y_PACKED2 = 64
 
 _p = C.c_void_p
 

@@ -23,7 +23,15 @@ int check_irt(const VipsyIrtArgs* a) {
                 a->n_particles);
   VIPSY_REQUIRE(a->idx != nullptr || a->batch <= a->n_rows, VIPSY_ERR_ARG,
                 "vipsy_irt: batch %lld > rows %lld without idx", (long long)a->batch, (long long)a->n_rows);
-  VIPSY_REQUIRE(a->y_row_stride >= a->n_items, VIPSY_ERR_ARG, "vipsy_irt: y_row_stride < J");
+  if (a->flags & VIPSY_IRT_FLAG_Y_PACKED2)
+    VIPSY_REQUIRE(a->n_dims == 1 && a->n_particles > 1 && a->estimator == VIPSY_EST_PATHWISE && (a->n_items & 3) == 0 &&
+                      a->idx == nullptr && a->y_row_stride == a->n_items / 4 && a->obs_row_ptr == nullptr &&
+                      !(a->flags & VIPSY_IRT_FLAG_SPARSE) && (reinterpret_cast<uintptr_t>(a->y) & 3) == 0,
+                  VIPSY_ERR_UNSUPPORTED,
+                  "vipsy_irt: VIPSY_IRT_FLAG_Y_PACKED2 needs K == 1, S > 1, the pathwise estimator, J %% 4 == 0, no idx / "
+                  "CSR / sparse hint, y_row_stride == J / 4 and a 4-byte aligned y");
+  else
+    VIPSY_REQUIRE(a->y_row_stride >= a->n_items, VIPSY_ERR_ARG, "vipsy_irt: y_row_stride < J");
   VIPSY_REQUIRE(a->y && a->mu && a->b && a->loss, VIPSY_ERR_ARG, "vipsy_irt: y, mu, b, loss are required");
   VIPSY_REQUIRE(a->model < VIPSY_IRT_2PL || a->a, VIPSY_ERR_ARG, "vipsy_irt: a is required for 2PL+");
   VIPSY_REQUIRE(a->model < VIPSY_IRT_3PL || a->c, VIPSY_ERR_ARG, "vipsy_irt: c is required for 3PL+");

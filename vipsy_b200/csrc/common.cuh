@@ -220,5 +220,8 @@ int launch_finalize(const float* partial, int rows, int cols, float alpha, const
 constexpr int kMaskRows = 296;
 int launch_masked_term(const uint8_t* y, int64_t ld, const int64_t* idx, int64_t B, int J, float scale, int64_t known,
                        double* out_rows, int* n_rows, cudaStream_t st);
+// the same constant from rows in the 2-bit transport format (no padding bits: J % 4 == 0), n_bytes = B J / 4
+int launch_masked_term_2bit(const uint8_t* y2, int64_t n_bytes, float scale, int64_t known, double* out_rows, int* n_rows,
+                            cudaStream_t st);
 
 }  // namespace vipsy

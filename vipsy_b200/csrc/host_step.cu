@@ -108,6 +108,10 @@ int vipsy_irt_host_step(const VipsyIrtHostArgs* h) {
   const int64_t N = a.batch;
   const int J = a.n_items, PB = (J + 3) / 4;
   const bool want_grad = h->item_grads_host != nullptr || h->d_mu_host != nullptr;
+  // 2-bit rows go straight into the particle kernel (expanded while a tile is staged) when it is the kernel that will
+  // run: S > 1, pathwise, J % 4 == 0, no sparse hint; otherwise they are expanded to a byte matrix first
+  const bool direct2 = h->y_packed2 && a.n_particles > 1 && a.estimator == VIPSY_EST_PATHWISE && (J & 3) == 0 &&
+                       !(a.flags & VIPSY_IRT_FLAG_SPARSE);
   static thread_local EventPool pool;
 
   // item parameters: rows b, a, c, d of a 4 x J device table
@@ -161,13 +165,15 @@ int vipsy_irt_host_step(const VipsyIrtHostArgs* h) {
     VIPSY_CUDA_CHECK(cudaEventRecord(ev_in, s_in));
 
     VIPSY_CUDA_CHECK(cudaStreamWaitEvent(s_run, ev_in, 0));
-    if (h->y_packed2) {
+    if (h->y_packed2 && !direct2) {
       int rc = vipsy_unpack_responses_2bit(base + L.y2 + (size_t)s0 * PB, n, J, y, J, s_run);
       if (rc != VIPSY_OK) return rc;
     }
     VipsyIrtArgs c = a;
     c.n_rows = n; c.batch = n; c.n_dims = 1; c.cov_mode = VIPSY_COV_DIAG1;
-    c.y = y; c.y_row_stride = J; c.idx = nullptr; c.mu = mu; c.sigma = sg; c.chol = nullptr; c.eps = nullptr;
+    c.y = direct2 ? base + L.y2 + (size_t)s0 * PB : y;
+    c.y_row_stride = direct2 ? PB : J;
+    c.idx = nullptr; c.mu = mu; c.sigma = sg; c.chol = nullptr; c.eps = nullptr;
     c.person_offset = a.person_offset + s0;
     c.b = items; c.a = a.model >= 2 ? items + J : nullptr; c.c = a.model >= 3 ? items + 2 * J : nullptr;
     c.d = a.model >= 4 ? items + 3 * J : nullptr;
@@ -181,7 +187,9 @@ int vipsy_irt_host_step(const VipsyIrtHostArgs* h) {
     c.d_d = (want_grad && a.model >= 4) ? g + 3 * J : nullptr;
     c.workspace = base + L.ws; c.workspace_bytes = L.ws_bytes;
     c.obs_row_ptr = nullptr; c.obs_entries = nullptr; c.obs_nnz = 0;
-    c.flags = a.flags & ~VIPSY_IRT_FLAG_MASKED_KNOWN;
+    // the caller's count of missing cells covers the whole batch: the first chunk carries it, the others carry 0
+    c.flags = (a.flags & ~VIPSY_IRT_FLAG_Y_PACKED2) | (direct2 ? VIPSY_IRT_FLAG_Y_PACKED2 : 0);
+    if (a.flags & VIPSY_IRT_FLAG_MASKED_KNOWN) c.n_masked_cells = used == 0 ? a.n_masked_cells : 0;
     int rc = vipsy_irt_elbo_grad(&c, s_run);
     if (rc != VIPSY_OK) return rc;
     VIPSY_CUDA_CHECK(cudaEventRecord(ev_run, s_run));

@@ -200,7 +200,26 @@ __global__ void __launch_bounds__(kUniThreads, 4) irt_uni_kernel(const IrtUniPar
 
     // ---- stage the tile's response codes ---------------------------------
     int mis = 0;
-    if (p.contiguous) {
+    if (p.packed2) {
+      // 2-bit transport rows (4 cells per byte, 0 / 1 / 3 = missing; J % 4 == 0, so the tile is one contiguous run
+      // of rows * J / 4 bytes that expands to rows * J contiguous codes): a 32-bit word becomes one 16-byte store
+      const unsigned char* g0 = p.y + b0 * (int64_t)(J >> 2);
+      const int nbytes = rows * (J >> 2), nw = nbytes >> 2;
+      const uint32_t* gw = reinterpret_cast<const uint32_t*>(g0);          // b0 is a multiple of 32: 4-byte aligned
+      int4* dst = reinterpret_cast<int4*>(ytile);
+      auto expand = [](const uint32_t b) {                                  // one packed byte -> four code bytes
+        const uint32_t t = (b | (b << 6) | (b << 12) | (b << 18)) & 0x03030303u;
+        const uint32_t m = t & (t >> 1) & 0x01010101u;                      // 3 -> 255
+        return t | ((m << 8) - m);
+      };
+      for (int v = lane; v < nw; v += 32) {
+        const uint32_t w = __ldg(gw + v);
+        dst[v] = make_int4((int)expand(w & 0xffu), (int)expand((w >> 8) & 0xffu), (int)expand((w >> 16) & 0xffu),
+                           (int)expand(w >> 24));
+      }
+      for (int k = (nw << 2) + lane; k < nbytes; k += 32)                   // last, partial tile: up to 3 bytes
+        reinterpret_cast<uint32_t*>(ytile)[k] = expand(g0[k]);
+    } else if (p.contiguous) {
       const unsigned char* g0 = p.y + b0 * (int64_t)J;
       mis = (int)(reinterpret_cast<uintptr_t>(g0) & 15);
       const int4* gal = reinterpret_cast<const int4*>(g0 - mis);
@@ -475,6 +494,7 @@ int irt_uni_launch(const VipsyIrtArgs* a, cudaStream_t st) {
   p.item_partial = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(a->workspace) +
                                             align16(uni_loss_rows() * 8));
   p.contiguous = (a->idx == nullptr && a->y_row_stride == J) ? 1 : 0;
+  p.packed2 = (a->flags & VIPSY_IRT_FLAG_Y_PACKED2) ? 1 : 0;
   p.want_grad = (a->d_b || a->d_a || a->d_c || a->d_d) ? 1 : 0;
   p.row_ptr = a->obs_row_ptr; p.entries = a->obs_entries;
 
@@ -487,7 +507,10 @@ int irt_uni_launch(const VipsyIrtArgs* a, cudaStream_t st) {
                       irt_uni_sparse_smem_bytes(J, NQ) <= 227 * 1024;
   const bool want_sparse = (a->flags & VIPSY_IRT_FLAG_SPARSE) && a->estimator == VIPSY_EST_PATHWISE;
   int mask_rows = 0;        // extra loss partials written by masked_term_kernel (lane-per-person dense kernel only)
-  if (irt_uni_csr_supported(a))
+  if (p.packed2) {                                                           // 2-bit rows: the pipelined particle kernel
+    rc = launch_model<false>(a->model, fast, SC, p, smem, st, &grid);
+    mask_rows = 1;
+  } else if (irt_uni_csr_supported(a))
     rc = irt_uni_csr_launch(a, fast, p, st, &grid);                          // S == 1 over the observed-cell CSR
   else if (!(a->flags & VIPSY_IRT_FLAG_NO_ROW) && irt_uni_row_supported(a, want_sparse))
     rc = irt_uni_row_launch(a->model, fast, want_sparse, p, st, &grid);     // S == 1: warp per person
@@ -501,8 +524,12 @@ int irt_uni_launch(const VipsyIrtArgs* a, cudaStream_t st) {
   if (rc != VIPSY_OK) return rc;
   if (mask_rows) {
     const int64_t known = (a->flags & VIPSY_IRT_FLAG_MASKED_KNOWN) ? a->n_masked_cells : -1;
-    rc = launch_masked_term(a->y, a->y_row_stride, a->idx, a->batch, J, a->scale, known, p.loss_partial + grid,
-                            &mask_rows, st);
+    if (p.packed2)
+      rc = launch_masked_term_2bit(a->y, a->batch * (int64_t)(J >> 2), a->scale, known, p.loss_partial + grid,
+                                   &mask_rows, st);
+    else
+      rc = launch_masked_term(a->y, a->y_row_stride, a->idx, a->batch, J, a->scale, known, p.loss_partial + grid,
+                              &mask_rows, st);
     if (rc != VIPSY_OK) return rc;
   }
 

@@ -26,6 +26,7 @@ struct IrtUniParams {
   float* item_partial;    // [grid][NQ*J]
   double* loss_partial;   // [grid]
   int contiguous;         // rows of the batch are contiguous in y (no idx, ld == J)
+  int packed2;            // y holds 2-bit rows (J / 4 bytes each, contiguous): expanded while a tile is staged
   int want_grad;
   const int64_t* row_ptr;   // CSR of the observed cells (irt_uni_csr.cu), or null
   const uint16_t* entries;

@@ -3,6 +3,8 @@
 #include <stdarg.h>
 #include <string.h>
 
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace vipsy {
@@ -171,6 +173,43 @@ int launch_masked_term(const uint8_t* y, int64_t ld, const int64_t* idx, int64_t
   int rows = known >= 0 ? 1 : (int)((B + 63) / 64 < kMaskRows ? (B + 63) / 64 : kMaskRows);
   if (rows < 1) rows = 1;
   masked_term_kernel<<<rows, 256, 0, st>>>(y, ld, idx, B, J, scale, known, out_rows);
+  VIPSY_CUDA_CHECK(cudaGetLastError());
+  *n_rows = rows;
+  return VIPSY_OK;
+}
+
+__global__ void __launch_bounds__(256) masked_term_2bit_kernel(const uint8_t* __restrict__ y2, int64_t n_bytes, float scale,
+                                                               double* __restrict__ out) {
+  __shared__ long long part[8];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  long long n = 0;
+  const int64_t nw = n_bytes >> 2;                       // y2 is 4-byte aligned (checked by the caller)
+  const uint32_t* w = reinterpret_cast<const uint32_t*>(y2);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nw; i += (int64_t)gridDim.x * blockDim.x) {
+    const uint32_t v = __ldg(w + i);
+    n += __popc(v & (v >> 1) & 0x55555555u);             // cells coded 3
+  }
+  if (blockIdx.x == 0)
+    for (int64_t k = (nw << 2) + threadIdx.x; k < n_bytes; k += blockDim.x) {
+      const uint32_t v = y2[k];
+      n += __popc(v & (v >> 1) & 0x55u);
+    }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) n += __shfl_xor_sync(0xffffffffu, n, o);
+  if (lane == 0) part[warp] = n;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    long long t = 0;
+    for (int k = 0; k < 8; ++k) t += part[k];
+    out[blockIdx.x] = -(double)scale * (double)kMaskedLogProb * (double)t;
+  }
+}
+
+int launch_masked_term_2bit(const uint8_t* y2, int64_t n_bytes, float scale, int64_t known, double* out_rows, int* n_rows,
+                            cudaStream_t st) {
+  if (known >= 0) return launch_masked_term(y2, 0, nullptr, 0, 0, scale, known, out_rows, n_rows, st);
+  int rows = (int)std::min<int64_t>(std::max<int64_t>((n_bytes + 16383) / 16384, 1), kMaskRows);
+  masked_term_2bit_kernel<<<rows, 256, 0, st>>>(y2, n_bytes, scale, out_rows);
   VIPSY_CUDA_CHECK(cudaGetLastError());
   *n_rows = rows;
   return VIPSY_OK;

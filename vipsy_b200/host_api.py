@@ -38,11 +38,14 @@ class IrtHostStep:
     def __call__(self, y: torch.Tensor, mu: torch.Tensor, sigma: torch.Tensor, a, b, c=None, d=None, *,
                  n_particles: int = 1, D: float = 1.0, scale: float = 1.0, seed: int = 0, offset: int = 0,
                  person_offset: int = 0, estimator: str = "pathwise", baseline: float = 0.0,
-                 a_free=None) -> Dict[str, torch.Tensor]:
+                 a_free=None, n_masked=None) -> Dict[str, torch.Tensor]:
         """All tensor arguments are HOST tensors (pinned for asynchronous copies).  y: N x J uint8 codes, or
         N x ceil(J/4) uint8 rows in the 2-bit transport format.  ``a_free``: optional J-element 0/1 host mask of
-        site 'a' (vi.py:511-512); d_a of frozen entries comes back 0, as on the device entry.  Returns pinned
-        host tensors."""
+        site 'a' (vi.py:511-512); d_a of frozen entries comes back 0, as on the device entry.  ``n_masked``: the
+        number of missing cells of the whole matrix if the caller knows it (it is constant between steps): saves the
+        counting pass of every chunk.  2-bit rows with S > 1, J % 4 == 0 and the pathwise estimator are expanded by
+        the particle kernel itself while it stages a tile (no byte matrix in HBM, no expansion launch).  Returns
+        pinned host tensors."""
         J, m = self.J, self.m
         for t, nm in ((y, "y"), (mu, "mu"), (sigma, "sigma")):
             if t.is_cuda or not t.is_contiguous():
@@ -66,6 +69,9 @@ class IrtHostStep:
         dv.model, dv.estimator = m, N.EST[estimator]
         dv.D, dv.scale, dv.baseline = float(D), float(scale), float(baseline)
         dv.seed, dv.offset, dv.person_offset = seed, offset, person_offset
+        if n_masked is not None:
+            dv.flags |= N.IRT_FLAG_MASKED_KNOWN
+            dv.n_masked_cells = int(n_masked)
         args.y_host, args.y_packed2, args.n_chunks = y.data_ptr(), int(packed), self.n_chunks
         args.mu_host, args.sigma_host = mu.data_ptr(), sigma.data_ptr()
         args.b_host = h[0].data_ptr()
@@ -93,7 +99,8 @@ class IrtHostStep:
         self.s_out.synchronize()
         cur.wait_stream(self.s_run)
         chunks = self.n_chunks
-        self.kernel_launches += chunks * (3 + int(packed)) + 1
+        direct2 = packed and n_particles > 1 and estimator == "pathwise" and J % 4 == 0     # as in csrc/host_step.cu
+        self.kernel_launches += chunks * (3 + int(packed and not direct2)) + 1
         self.h2d_bytes = self.N * (y.shape[1] + 8) + m * J * 4 + (J if args.a_free_host else 0)
         self.d2h_bytes = self.N * 8 + m * J * 4 + 8
         return {"loss": self.h_loss, "d_mu": self.h_d_mu, "d_sigma": self.h_d_sigma, "item_grads": self.h_item_grads}
