@@ -33,11 +33,12 @@ struct FinalizeArgs {
   double* loss_out;
 };
 
-constexpr int kFinWarps = 8;
+constexpr int kFinWarps = 32;   // at most; 8 below 256 partial rows (launch_finalize)
 
 __global__ void __launch_bounds__(kFinWarps * 32) finalize_kernel(const FinalizeArgs a) {
   __shared__ double sm[kFinWarps][33];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int nwarps = blockDim.x >> 5;                  // 8 or 32: many partial rows want more loads in flight
   const int col = blockIdx.x * 32 + lane;
   if (blockIdx.x * 32 < a.cols) {
     double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
@@ -51,21 +52,20 @@ __global__ void __launch_bounds__(kFinWarps * 32) finalize_kernel(const Finalize
     }
     if (col < a.cols && wanted) {
       int r = warp;
-      for (; r + 3 * kFinWarps < a.rows; r += 4 * kFinWarps) {
+      for (; r + 3 * nwarps < a.rows; r += 4 * nwarps) {
         const float v0 = a.partial[(size_t)r * a.cols + col];
-        const float v1 = a.partial[(size_t)(r + kFinWarps) * a.cols + col];
-        const float v2 = a.partial[(size_t)(r + 2 * kFinWarps) * a.cols + col];
-        const float v3 = a.partial[(size_t)(r + 3 * kFinWarps) * a.cols + col];
+        const float v1 = a.partial[(size_t)(r + nwarps) * a.cols + col];
+        const float v2 = a.partial[(size_t)(r + 2 * nwarps) * a.cols + col];
+        const float v3 = a.partial[(size_t)(r + 3 * nwarps) * a.cols + col];
         s0 += v0; s1 += v1; s2 += v2; s3 += v3;
       }
-      for (; r < a.rows; r += kFinWarps) s0 += a.partial[(size_t)r * a.cols + col];
+      for (; r < a.rows; r += nwarps) s0 += a.partial[(size_t)r * a.cols + col];
     }
     sm[warp][lane] = (s0 + s1) + (s2 + s3);
     __syncthreads();
     if (warp == 0 && col < a.cols) {
       double t = 0.0;
-#pragma unroll
-      for (int w = 0; w < kFinWarps; ++w) t += sm[w][lane];
+      for (int w = 0; w < nwarps; ++w) t += sm[w][lane];
       int c = col;
       for (int i = 0; i < a.segs.n; ++i) {
         if (c < a.segs.cols[i]) {
@@ -89,7 +89,7 @@ __global__ void __launch_bounds__(kFinWarps * 32) finalize_kernel(const Finalize
     __syncthreads();
     if (threadIdx.x == 0) {
       double tot = 0.0;
-      for (int w = 0; w < kFinWarps; ++w) tot += sm[w][32];
+      for (int w = 0; w < nwarps; ++w) tot += sm[w][32];
       *a.loss_out = tot;
     }
   }
@@ -100,7 +100,7 @@ int launch_finalize(const float* partial, int rows, int cols, float alpha, const
   FinalizeArgs a{partial, rows, cols, alpha, segs, loss_partial, loss_rows, loss_out};
   int grid = (cols + 31) / 32;
   if (grid < 1) grid = 1;
-  finalize_kernel<<<grid, kFinWarps * 32, 0, stream>>>(a);
+  finalize_kernel<<<grid, (rows >= 256 ? kFinWarps : 8) * 32, 0, stream>>>(a);
   VIPSY_CUDA_CHECK(cudaGetLastError());
   return VIPSY_OK;
 }
