@@ -91,3 +91,22 @@ def test_host_step_rejects_half_a_gradient_pair(lib):
     a.n_chunks = 1
     assert N.lib().vipsy_irt_host_step(C.byref(a)) == N.ERR_ARG
     assert b"go together" in N.lib().vipsy_last_error()
+
+
+def test_two_bit_rows_flag_is_validated_without_a_gpu(lib):
+    """VIPSY_IRT_FLAG_Y_PACKED2 (the particle kernel expands 2-bit transport rows itself) is only defined for
+    K == 1, S > 1, the pathwise estimator, J % 4 == 0, y_row_stride == J / 4: anything else is refused before a launch."""
+    import torch
+    keep = [torch.zeros(64 * 2, dtype=torch.uint8), torch.zeros(64), torch.ones(64), torch.ones(6), torch.zeros(6),
+            torch.zeros(1, dtype=torch.float64)]
+
+    def args(J, S, stride):
+        a = N.IrtArgs()
+        a.n_rows = a.batch = 64
+        a.n_items, a.n_dims, a.n_particles, a.model, a.estimator = J, 1, S, 2, N.EST["pathwise"]
+        a.y, a.mu, a.sigma, a.a, a.b, a.loss = (t.data_ptr() for t in keep)
+        a.y_row_stride, a.flags = stride, N.IRT_FLAG_Y_PACKED2
+        return a
+    for J, S, stride in ((6, 8, 2), (8, 1, 2), (8, 8, 8)):          # J % 4 != 0; S == 1; stride of a byte matrix
+        assert lib.vipsy_irt_elbo_grad(C.byref(args(J, S, stride)), None) == N.ERR_UNSUPPORTED
+        assert b"Y_PACKED2" in lib.vipsy_last_error()
