@@ -8,7 +8,9 @@ from vipsy_b200 import ops, workloads
 dev = torch.device("cuda:0")
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 wave = 148 * 16 * 32
-for N in (13 * wave, 1_000_000, 14 * wave, 2_000_000, 1_000_000):
+import os
+SIZES = (15_360, wave, 3 * wave, 1_000_000) if os.environ.get('VIPSY_SIZES') == 'chunks' else (13 * wave, 1_000_000, 14 * wave, 2_000_000, 1_000_000)
+for N in SIZES:
     w = workloads.uni_irt(N, 100, "irt_4pl", seed=1234, device=dev)
     off = [0]
 

@@ -397,3 +397,22 @@ def test_row_kernels_unaligned_rows(ops, J, sparse):
     got2, _ = run_both(ops, cs, scale=2.0, idx=idx, y_full=y_full, sparse=sparse)
     for k in ("loss", "d_mu", "d_a", "d_b"):
         assert torch.equal(got2[k], got[k]), k
+
+
+def test_large_launch_noise_in_shared_memory_variant(ops):
+    """Launches of at least four rounds of the five-CTA grid keep the noise pairs in shared memory (csrc/irt_uni.cu,
+    ESM).  The same persons evaluated in two half-size launches take the register variant: per-person outputs must be
+    bit-identical (same Philox stream, same arithmetic), item gradients and loss equal to rounding."""
+    from vipsy_b200 import workloads
+    N, J, S = 420_000, 8, 32
+    for model in ("irt_4pl", "irt_2pl"):
+        w = workloads.uni_irt(N, J, model, missing=0.1, seed=3)
+        kw = {k: w[k] for k in ("a", "b", "c", "d")[:int(model[4])]}
+        full = ops.irt_elbo_grad(w["y"], w["mu"], sigma=w["sigma"], n_particles=S, model=model, seed=4, offset=2, **kw)
+        h = N // 2
+        parts = [ops.irt_elbo_grad(w["y"][s:s + h], w["mu"][s:s + h], sigma=w["sigma"][s:s + h], n_particles=S,
+                                   model=model, seed=4, offset=2, person_offset=s, **kw) for s in (0, h)]
+        assert torch.equal(full["d_mu"], torch.cat([p["d_mu"] for p in parts]))
+        assert torch.equal(full["d_sigma"], torch.cat([p["d_sigma"] for p in parts]))
+        assert_close(full["item_grads"], parts[0]["item_grads"].double() + parts[1]["item_grads"].double(), 1e-5, 1e-5, model)
+        assert_close(full["loss"], parts[0]["loss"].double() + parts[1]["loss"].double(), 1e-9, 1e-9, model)

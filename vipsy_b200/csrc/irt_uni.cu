@@ -18,6 +18,7 @@
 // [eps, 1-eps], log, zero gradient where the clamp fires -- see item_evals().
 // Roof: 3-4 MUFU per (person, item, particle) evaluation => SFU-bound, not HBM.
 #include <algorithm>
+#include <cstdlib>
 
 #include "irt_uni.cuh"
 
@@ -37,9 +38,10 @@ template <int MODEL, int SC, int MODE>
 struct UniItem {
   static constexpr int NQ = MODEL;
   // evaluates item j for the lane's person; v[] = the lane's terms of the item-gradient sums (masked)
+  template <typename EpsT>
   static __device__ __forceinline__ void eval(const int j, const unsigned code, const float4* __restrict__ tab,
                                               const float2* __restrict__ tab2, const float mu, const float sg,
-                                              const typename NoiseVec<SC>::type (&eps)[SC / NoiseVec<SC>::W],
+                                              const EpsT& eps,
                                               float (&v)[NQ], float& Lsum, float& G1, float& G2) {
     const bool obs = code != 255u;
     const float4 it = tab[j];
@@ -65,11 +67,11 @@ struct UniItem {
   }
 };
 
-template <int MODEL, int SC, int MODE, int UNR>
+template <int MODEL, int SC, int MODE, int UNR, typename EpsT>
 __device__ __forceinline__ void uni_item_loop(const int J, const float4* __restrict__ tab, const float2* __restrict__ tab2,
                                               const unsigned char* __restrict__ yrow, const bool valid, const int lane,
                                               float* __restrict__ acc, const float mu, const float sg,
-                                              const typename NoiseVec<SC>::type (&eps)[SC / NoiseVec<SC>::W],
+                                              const EpsT& eps,
                                               float& Lsum, float& G1, float& G2) {
   constexpr int NQ = MODEL;
   using It = UniItem<MODEL, SC, MODE>;
@@ -136,8 +138,10 @@ __device__ __forceinline__ void uni_item_loop(const int J, const float4* __restr
 // FAST (4PL only): compile in the rational-form path; each CTA checks the item
 // table once and uses it only if no item can reach the probability clamp.
 // PIPE (pathwise only): the item loop is uni_item_loop above.
-template <int MODEL, bool SCORE, int SC, bool FAST, bool PIPE, int kUniUnroll = 1>
-__global__ void __launch_bounds__(kUniThreads, 4) irt_uni_kernel(const IrtUniParams p) {
+// ESM: the lane's noise pairs live in shared memory ([pair][thread], one conflict-free LDS.64 per pair) instead of 32
+// registers, so that five CTAs fit an SM (96 registers): a fifth warp per scheduler for the MUFU pipe.
+template <int MODEL, bool SCORE, int SC, bool FAST, bool PIPE, int kUniUnroll = 1, bool ESM = false>
+__global__ void __launch_bounds__(kUniThreads, ESM ? 5 : 4) irt_uni_kernel(const IrtUniParams p) {
   static_assert(!(PIPE && SCORE), "the pipelined item loop serves the pathwise estimator");
   constexpr int NQ = MODEL;
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -147,6 +151,8 @@ __global__ void __launch_bounds__(kUniThreads, 4) irt_uni_kernel(const IrtUniPar
   float* acc_all = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(tab2) + align16((size_t)J * 8));
   unsigned char* ytiles = reinterpret_cast<unsigned char*>(acc_all) + align16((size_t)kUniWarps * NQ * J * 4);
   const size_t ytile_bytes = align16((size_t)32 * J + 16);
+  typename NoiseVec<SC>::type* eps_sm =
+      reinterpret_cast<typename NoiseVec<SC>::type*>(ytiles + (size_t)kUniWarps * ytile_bytes) + threadIdx.x;
 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   float* acc = acc_all + (size_t)warp * NQ * J;
@@ -293,8 +299,20 @@ __global__ void __launch_bounds__(kUniThreads, 4) irt_uni_kernel(const IrtUniPar
 
       // ---- items ----------------------------------------------------------
       if constexpr (PIPE) {
-#define UNI_LOOP(MODE) \
-  uni_item_loop<MODEL, SC, MODE, kUniUnroll>(J, tab, tab2, yrow, valid, lane, acc, mu, sg, eps, Lsum, G1, G2)
+        if constexpr (ESM) {
+          __syncwarp();                                  // the previous chunk's readers are done
+#pragma unroll
+          for (int i = 0; i < SC / VW; ++i) eps_sm[i * kUniThreads] = eps[i];
+          __syncwarp();
+        }
+#define UNI_LOOP(MODE)                                                                                              \
+  do {                                                                                                              \
+    if constexpr (ESM)                                                                                              \
+      uni_item_loop<MODEL, SC, MODE, kUniUnroll>(J, tab, tab2, yrow, valid, lane, acc, mu, sg, eps_acc, Lsum, G1, G2);  \
+    else                                                                                                            \
+      uni_item_loop<MODEL, SC, MODE, kUniUnroll>(J, tab, tab2, yrow, valid, lane, acc, mu, sg, eps, Lsum, G1, G2);  \
+  } while (0)
+        EpsShared<SC> eps_acc{eps_sm, kUniThreads};
         if (FAST && use_fast) {
           // |tt| <= max|A'| (|mu| + sigma max|eps|) + max|B'| for every item and particle of the person
           float emax = 0.f;
@@ -415,9 +433,10 @@ __global__ void __launch_bounds__(kUniThreads, 4) irt_uni_kernel(const IrtUniPar
 // ---------------------------------------------------------------------------
 constexpr int kUniMaxCtasPerSM = 8;
 
-template <int MODEL, bool SCORE, int SC, bool FAST, bool PIPE, int UNR = 1>
+template <int MODEL, bool SCORE, int SC, bool FAST, bool PIPE, int UNR = 1, bool ESM = false>
 static int launch_one_k(IrtUniParams& p, size_t smem, cudaStream_t st, int* grid_out) {
-  auto k = irt_uni_kernel<MODEL, SCORE, SC, FAST, PIPE, UNR>;
+  auto k = irt_uni_kernel<MODEL, SCORE, SC, FAST, PIPE, UNR, ESM>;
+  if (ESM) smem += (size_t)kUniThreads * SC * 4;
   static OccCache occ_cache;   // per instantiation
   int occ = 0;
   if (smem > 48 * 1024) VIPSY_CUDA_CHECK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -440,7 +459,18 @@ static int launch_one_k(IrtUniParams& p, size_t smem, cudaStream_t st, int* grid
 template <int MODEL, bool SCORE, int SC, bool FAST>
 static int launch_one(IrtUniParams& p, size_t smem, cudaStream_t st, int* grid_out) {
   if constexpr (SCORE) return launch_one_k<MODEL, SCORE, SC, FAST, false>(p, smem, st, grid_out);
-  else return launch_one_k<MODEL, SCORE, SC, FAST, true, (SC <= 8 ? 2 : 1)>(p, smem, st, grid_out);
+  else {
+    if constexpr (SC == 32) {
+      // 32 particles: the noise pairs in shared memory leave room for a fifth CTA per SM (96 registers).  Worth it for
+      // launches of at least four rounds of that grid (1M x 100 4PL: 2.007 -> 1.946 ms); shorter launches -- the chunks of
+      // the host-buffer pipeline -- measured better with four CTAs (e2e 2.26 vs 2.32 ms), VIPSY_UNI_ESM=0 / 1 forces.
+      static const int esm_env = [] { const char* e = getenv("VIPSY_UNI_ESM"); return e ? atoi(e) : -1; }();
+      const bool fits5 = 5 * (smem + (size_t)kUniThreads * SC * 4 + 1024) <= (size_t)228 * 1024;   // short tests only
+      const bool esm = fits5 && (esm_env >= 0 ? esm_env != 0 : p.B >= (int64_t)4 * num_sms() * 5 * kUniWarps * 32);
+      if (esm) return launch_one_k<MODEL, SCORE, SC, FAST, true, 1, true>(p, smem, st, grid_out);
+    }
+    return launch_one_k<MODEL, SCORE, SC, FAST, true, (SC <= 8 ? 2 : 1)>(p, smem, st, grid_out);
+  }
 }
 
 template <int MODEL, bool SCORE, bool FAST>

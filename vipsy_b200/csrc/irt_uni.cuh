@@ -98,9 +98,16 @@ template <> struct NoiseVec<1> { using type = float; static constexpr int W = 1;
 // packed operations on constants).
 // item_evals_v leaves the sums as pairs and the last group's probability product unlogged; item_evals is the
 // complete form.
-template <int MODEL, bool SCORE, int SC, bool FASTPATH, bool CLAMP = true>
+// eps: anything indexable by pair (the register array, or EpsShared below)
+template <int SC>
+struct EpsShared {                 // the lane's noise pairs in shared memory, [pair][thread]: conflict-free LDS.64
+  const typename NoiseVec<SC>::type* base;
+  int stride;
+  __device__ __forceinline__ typename NoiseVec<SC>::type operator[](int i) const { return base[i * stride]; }
+};
+template <int MODEL, bool SCORE, int SC, bool FASTPATH, bool CLAMP = true, typename EpsT>
 __device__ __forceinline__ void item_evals_v(const float dmc, const float base, const float T0, const float T1,
-                                             const typename NoiseVec<SC>::type (&eps)[SC / NoiseVec<SC>::W],
+                                             const EpsT& eps,
                                              float (&lls)[SCORE ? SC : 1], typename NoiseVec<SC>::type& W1o,
                                              typename NoiseVec<SC>::type& W2o, typename NoiseVec<SC>::type& A1o,
                                              typename NoiseVec<SC>::type& A2o, typename NoiseVec<SC>::type& prodo,
@@ -115,7 +122,8 @@ __device__ __forceinline__ void item_evals_v(const float dmc, const float base, 
     const V basev = vbcast<V>(base), bdv = vbcast<V>(base + dmc);
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
-      V tt = vfma(T1v, eps[i], T0v);
+      const V ep = eps[i];
+      V tt = vfma(T1v, ep, T0v);
       if constexpr (CLAMP) tt = vmin(tt, 60.f);
       const V e = vex2(tt);
       const V ope = vadd(e, one);
@@ -126,12 +134,12 @@ __device__ __forceinline__ void item_evals_v(const float dmc, const float base, 
       const V us = vmul(ope, R);                                 // sp / q = 1 / num
       const V w = vmul(e, R);                                    // sp (1-sp) / q
       if (i == 0) {
-        A1 = us; A2 = vmul(us, e); W1 = w; W2 = vmul(w, eps[i]);
+        A1 = us; A2 = vmul(us, e); W1 = w; W2 = vmul(w, ep);
       } else {
         A1 = vadd(A1, us);
         A2 = vfma(us, e, A2);                                    // (1-sp) / q = e' / num
         W1 = vadd(W1, w);
-        W2 = vfma(w, eps[i], W2);
+        W2 = vfma(w, ep, W2);
       }
       if constexpr (SCORE) {
         vlg2_add(q, &lls[i * W]);
@@ -144,7 +152,8 @@ __device__ __forceinline__ void item_evals_v(const float dmc, const float base, 
     const V dmcv = vbcast<V>(dmc), basev = vbcast<V>(base);
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
-      const V tt = vmin(vfma(T1v, eps[i], T0v), 126.f);          // e' finite: sp, e' sp never NaN
+      const V ep = eps[i];
+      const V tt = vmin(vfma(T1v, ep, T0v), 126.f);              // e' finite: sp, e' sp never NaN
       const V e = vex2(tt);
       const V sp = vrcp(vadd(e, one));
       const V es = vmul(e, sp);                                  // 1 - sp
@@ -162,7 +171,7 @@ __device__ __forceinline__ void item_evals_v(const float dmc, const float base, 
         w = vkeep(es, q, qc);                                    // |y - s|
       }
       W1 = vadd(W1, w);
-      W2 = vfma(w, eps[i], W2);
+      W2 = vfma(w, ep, W2);
       if constexpr (SCORE) {
         vlg2_add(qc, &lls[i * W]);
       } else {
@@ -174,9 +183,9 @@ __device__ __forceinline__ void item_evals_v(const float dmc, const float base, 
   W1o = W1; W2o = W2; A1o = A1; A2o = A2; prodo = prod;
 }
 
-template <int MODEL, bool SCORE, int SC, bool FASTPATH, bool CLAMP = true>
+template <int MODEL, bool SCORE, int SC, bool FASTPATH, bool CLAMP = true, typename EpsT>
 __device__ __forceinline__ void item_evals(const float dmc, const float base, const float T0, const float T1,
-                                           const typename NoiseVec<SC>::type (&eps)[SC / NoiseVec<SC>::W],
+                                           const EpsT& eps,
                                            float (&lls)[SCORE ? SC : 1], float& W1o, float& W2o, float& A1o,
                                            float& A2o, float& Lj) {
   typename NoiseVec<SC>::type W1, W2, A1, A2, prod;
