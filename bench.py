@@ -206,8 +206,14 @@ def other_configs(dev, peaks, flush, iters=5):
                      "frac": algo / ms / 1e6 / hbm}}
     ms32 = timed(lambda: ops.irt_elbo_grad(w["y"], w["mu"], sigma=w["sigma"], n_particles=32, a=w["a"], b=w["b"],
                                            model="irt_2pl", seed=1, offset=nxt(), sparse=True))
-    out["c4_2pl_2Mx200_90pct_missing_S32"] = {"ms": ms32, "nominal_evals_per_s": 4e8 * 32 / ms32 * 1e3,
-                                              "observed_evals_per_s": obs[2] * 32 / ms32 * 1e3, "bound": "sfu"}
+    clk_hz = float(peaks.get("sm_max_mhz", 1965.0)) * 1e6
+    mufu_peak = 148 * 16 * clk_hz                           # MUFU op/s (profiles/r01_mufu_throughput_ubench.txt)
+    mufu32 = obs[2] * 32 * 2.25 / (ms32 * 1e-3)             # 2PL: ex2 + rcp + lg2 / 4 per OBSERVED evaluation
+    out["c4_2pl_2Mx200_90pct_missing_S32"] = {
+        "ms": ms32, "nominal_evals_per_s": 4e8 * 32 / ms32 * 1e3, "observed_evals_per_s": obs[2] * 32 / ms32 * 1e3,
+        "bound": "sfu",
+        "roofline": {"bound": "sfu", "achieved": mufu32, "peak": mufu_peak, "unit": "MUFU op/s", "frac": mufu32 / mufu_peak,
+                     "note": "observed cells only; ragged rows (lane per person) and the per-lane compaction are the rest"}}
     del w, obs
 
     # c5: enumerated DINA and HO-DINA, 1M x 60, K = 10 (1024 patterns)
@@ -216,8 +222,14 @@ def other_configs(dev, peaks, flush, iters=5):
         qm = ops.qmask_from_q(w["q"])
         kw = dict(lam0=w["lam0"], lam1=w["lam1"], mu=w["mu"], sigma=w["sigma"], n_particles=1) if hod else {}
         ms = timed(lambda: ops.cdm_enum_elbo_grad(w["y"], qm, w["g"], w["s"], n_attrs=10, seed=1, offset=nxt(), **kw))
+        adds = 1e6 * 2 * 10 * 512 / (ms * 1e-3)             # forward + transposed lattice transform: 2 K 2^(K-1) per person
+        add_peak = 148 * 128 * clk_hz                       # fp32 adds / s (packed FADD2 counted as two)
         out["c5_hodina_1Mx60_K10" if hod else "c5_dina_1Mx60_K10"] = {
-            "ms": ms, "person_item_pattern_per_s": 1e6 * 60 * 1024 / ms * 1e3, "bound": "fp32 add / sfu"}
+            "ms": ms, "person_item_pattern_per_s": 1e6 * 60 * 1024 / ms * 1e3, "bound": "fp32 add / sfu",
+            "roofline": {"bound": "fp32_add", "achieved": adds, "peak": add_peak, "unit": "fp32 add/s",
+                         "frac": adds / add_peak,
+                         "note": "adds of the two lattice transforms only (the J x 2^K products they replace would be 6.1e10 "
+                                 "MACs per step); log-sum-exp, item scatter / gather, HO-DINA prior not counted"}}
         del w
 
     # c3: 2PL MIRT K = 100, 200k x 500, per-person packed Cholesky, S = 1 (tcgen05 contraction; HBM-bound by L)
