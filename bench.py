@@ -205,7 +205,7 @@ def other_configs(dev, peaks, flush, iters=5):
         "roofline": {"bound": "hbm", "achieved": algo / ms / 1e6, "peak": hbm, "unit": "GB/s",
                      "frac": algo / ms / 1e6 / hbm}}
     ms32 = timed(lambda: ops.irt_elbo_grad(w["y"], w["mu"], sigma=w["sigma"], n_particles=32, a=w["a"], b=w["b"],
-                                           model="irt_2pl", seed=1, offset=nxt(), sparse=True))
+                                           model="irt_2pl", seed=1, offset=nxt(), sparse=True, obs=obs))
     clk_hz = float(peaks.get("sm_max_mhz", 1965.0)) * 1e6
     mufu_peak = 148 * 16 * clk_hz                           # MUFU op/s (profiles/r01_mufu_throughput_ubench.txt)
     mufu32 = obs[2] * 32 * 2.25 / (ms32 * 1e-3)             # 2PL: ex2 + rcp + lg2 / 4 per OBSERVED evaluation
@@ -213,7 +213,7 @@ def other_configs(dev, peaks, flush, iters=5):
         "ms": ms32, "nominal_evals_per_s": 4e8 * 32 / ms32 * 1e3, "observed_evals_per_s": obs[2] * 32 / ms32 * 1e3,
         "bound": "sfu",
         "roofline": {"bound": "sfu", "achieved": mufu32, "peak": mufu_peak, "unit": "MUFU op/s", "frac": mufu32 / mufu_peak,
-                     "note": "observed cells only; ragged rows (lane per person) and the per-lane compaction are the rest"}}
+                     "note": "observed cells only, CSR-fed lane-per-person kernel; ragged rows are the rest"}}
     del w, obs
 
     # c5: enumerated DINA and HO-DINA, 1M x 60, K = 10 (1024 patterns)

@@ -536,6 +536,10 @@ int irt_uni_launch(const VipsyIrtArgs* a, cudaStream_t st) {
   const bool sparse = (a->flags & VIPSY_IRT_FLAG_SPARSE) && a->estimator == VIPSY_EST_PATHWISE && J < 32768 &&
                       irt_uni_sparse_smem_bytes(J, NQ) <= 227 * 1024;
   const bool want_sparse = (a->flags & VIPSY_IRT_FLAG_SPARSE) && a->estimator == VIPSY_EST_PATHWISE;
+  // S > 1 with the observed-cell CSR at hand: the sparse kernel walks it directly (no staging, no compaction)
+  const bool csr_multi = a->obs_row_ptr && a->obs_entries && a->n_particles > 1 &&
+                         a->estimator == VIPSY_EST_PATHWISE && J < 32768 && !p.packed2;
+  if (!csr_multi) { p.row_ptr = irt_uni_csr_supported(a) ? a->obs_row_ptr : nullptr; if (!p.row_ptr) p.entries = nullptr; }
   int mask_rows = 0;        // extra loss partials written by masked_term_kernel (lane-per-person dense kernel only)
   if (p.packed2) {                                                           // 2-bit rows: the pipelined particle kernel
     rc = launch_model<false>(a->model, fast, SC, p, smem, st, &grid);
@@ -544,8 +548,8 @@ int irt_uni_launch(const VipsyIrtArgs* a, cudaStream_t st) {
     rc = irt_uni_csr_launch(a, fast, p, st, &grid);                          // S == 1 over the observed-cell CSR
   else if (!(a->flags & VIPSY_IRT_FLAG_NO_ROW) && irt_uni_row_supported(a, want_sparse))
     rc = irt_uni_row_launch(a->model, fast, want_sparse, p, st, &grid);     // S == 1: warp per person
-  else if (sparse)
-    rc = irt_uni_sparse_launch(a->model, fast, SC, p, st, &grid);
+  else if (sparse || csr_multi)
+    rc = irt_uni_sparse_launch(a->model, fast, SC, p, st, &grid);   // CSR given: its entries are the lists
   else {
     rc = a->estimator == VIPSY_EST_SCORE ? launch_model<true>(a->model, fast, SC, p, smem, st, &grid)
                                          : launch_model<false>(a->model, fast, SC, p, smem, st, &grid);

@@ -11,6 +11,11 @@
 // Integer addition is associative: the result is bit-reproducible whatever the arrival order, and
 // more accurate than an fp32 running sum.  Per-person sums (d mu, d sigma, log-lik) stay in the
 // lane's registers in list order.
+//
+// CSR instantiation (S > 1 with the observed-cell CSR of irt_uni_csr.cu given): the lists already exist in global
+// memory -- no tile staging, no compaction, and above all no 19 KB of shared memory per warp, so four CTAs fit an SM
+// instead of two (the compaction variant runs two warps per scheduler).  A lane walks its person's entries straight
+// from global memory, one entry ahead of its use (40 bytes per person: one or two cache lines, L1 hits after the first).
 #include "irt_uni.cuh"
 
 namespace vipsy {
@@ -25,6 +30,9 @@ size_t irt_uni_sparse_smem_bytes(int J, int NQ) {
   s += (size_t)kUniWarps * align16((size_t)32 * J + 16);   // response tiles
   s += (size_t)kUniWarps * align16((size_t)32 * J * 2);    // compacted (item | response << 15) lists, [t][lane]
   return s;
+}
+static size_t irt_uni_sparse_csr_smem_bytes(int J, int NQ) {
+  return (size_t)J * 16 + align16((size_t)J * 8) + align16((size_t)NQ * J * 8);
 }
 
 // 64-bit fixed-point accumulate built from native 32-bit shared-memory atomics: the low word wraps,
@@ -41,8 +49,8 @@ __device__ __forceinline__ void fix_add(uint32_t* lo, int32_t* hi, float v) {
   if (xh != 0) atomicAdd(hi, xh);
 }
 
-template <int MODEL, int SC, bool FAST>
-__global__ void __launch_bounds__(kUniThreads, 3) irt_uni_sparse_kernel(const IrtUniParams p) {
+template <int MODEL, int SC, bool FAST, bool CSR>
+__global__ void __launch_bounds__(kUniThreads, CSR ? 4 : 3) irt_uni_sparse_kernel(const IrtUniParams p) {
   constexpr int NQ = MODEL;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int J = p.J;
@@ -92,6 +100,16 @@ __global__ void __launch_bounds__(kUniThreads, 3) irt_uni_sparse_kernel(const Ir
     const bool valid = bi < p.B;
     const int rows = (int)min((int64_t)32, p.B - b0);
 
+    int cnt = 0;
+    const uint16_t* ebase = nullptr;                     // CSR: the lane's entries in global memory
+    if constexpr (CSR) {
+      if (valid) {
+        const int64_t row = p.idx ? __ldg(p.idx + bi) : bi;       // minibatch: the CSR is that of the whole matrix
+        const int64_t r0 = p.row_ptr[row];
+        cnt = (int)(p.row_ptr[row + 1] - r0);
+        ebase = p.entries + r0;
+      }
+    } else {
     // ---- stage the tile's response codes (same as the dense kernel) ----------------------------------
     int mis = 0;
     if (p.contiguous) {
@@ -116,7 +134,6 @@ __global__ void __launch_bounds__(kUniThreads, 3) irt_uni_sparse_kernel(const Ir
     __syncwarp();
 
     // ---- compact this lane's row: (item | response << 15) of the observed cells, in item order --------
-    int cnt = 0;
     if (valid) {
       const unsigned char* yrow = ytile + mis + lane * J;
       if (((mis + lane * J) & 3) == 0 && (J & 3) == 0) {
@@ -144,6 +161,7 @@ __global__ void __launch_bounds__(kUniThreads, 3) irt_uni_sparse_kernel(const Ir
         }
       }
     }
+    }   // !CSR
     int maxcnt = cnt;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) maxcnt = max(maxcnt, __shfl_xor_sync(0xffffffffu, maxcnt, o));
@@ -196,14 +214,29 @@ __global__ void __launch_bounds__(kUniThreads, 3) irt_uni_sparse_kernel(const Ir
       // ---- observed cells only; U independent cells per iteration so that their dependency chains
       //      (table look-up -> ex2 -> rcp -> ...) overlap when there are few particles ---------------------
       constexpr int U = SC <= 2 ? 4 : (SC <= 8 ? 2 : 1);
+      uint32_t ahead[U];                                   // CSR: entries of the next step, already in flight
+      if constexpr (CSR) {
+#pragma unroll
+        for (int u = 0; u < U; ++u) ahead[u] = u < cnt ? (uint32_t)__ldg(ebase + u) : 0u;
+      }
       for (int t0 = 0; t0 < maxcnt; t0 += U) {
         int jj[U];
         bool yy[U], act[U];
         float w1[U], w2[U], a1[U], a2[U], lj[U], dm[U];
+        uint32_t cur[U];
+        if constexpr (CSR) {
+#pragma unroll
+          for (int u = 0; u < U; ++u) {
+            cur[u] = ahead[u];
+            ahead[u] = t0 + U + u < cnt ? (uint32_t)__ldg(ebase + t0 + U + u) : 0u;
+          }
+        }
 #pragma unroll
         for (int u = 0; u < U; ++u) {
           act[u] = t0 + u < cnt;
-          const uint32_t ent = act[u] ? list[(t0 + u) * 32 + lane] : 0u;   // inactive slots evaluate item 0, discarded
+          uint32_t ent;
+          if constexpr (CSR) ent = cur[u];
+          else ent = act[u] ? list[(t0 + u) * 32 + lane] : 0u;              // inactive slots evaluate item 0, discarded
           const int j = (int)(ent & 0x7fffu);
           const bool y1 = (ent & 0x8000u) != 0u;
           const float4 it = tab[j];
@@ -272,9 +305,9 @@ __global__ void __launch_bounds__(kUniThreads, 3) irt_uni_sparse_kernel(const Ir
   }
 }
 
-template <int MODEL, int SC, bool FAST>
-static int launch_sparse_one(IrtUniParams& p, size_t smem, cudaStream_t st, int* grid_out) {
-  auto k = irt_uni_sparse_kernel<MODEL, SC, FAST>;
+template <int MODEL, int SC, bool FAST, bool CSR>
+static int launch_sparse_k(IrtUniParams& p, size_t smem, cudaStream_t st, int* grid_out) {
+  auto k = irt_uni_sparse_kernel<MODEL, SC, FAST, CSR>;
   static OccCache occ_cache;   // per instantiation
   int occ = 0;
   if (smem > 48 * 1024) VIPSY_CUDA_CHECK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -288,6 +321,13 @@ static int launch_sparse_one(IrtUniParams& p, size_t smem, cudaStream_t st, int*
   k<<<(int)ctas, kUniThreads, smem, st>>>(p);
   VIPSY_CUDA_CHECK(cudaGetLastError());
   return VIPSY_OK;
+}
+
+template <int MODEL, int SC, bool FAST>
+static int launch_sparse_one(IrtUniParams& p, size_t smem, cudaStream_t st, int* grid_out) {
+  if (p.row_ptr && p.entries)
+    return launch_sparse_k<MODEL, SC, FAST, true>(p, irt_uni_sparse_csr_smem_bytes(p.J, MODEL), st, grid_out);
+  return launch_sparse_k<MODEL, SC, FAST, false>(p, smem, st, grid_out);
 }
 
 template <int MODEL, bool FAST>

@@ -115,7 +115,7 @@ class BasePsy(nn.Module):               # vi.py:521-533
         # mostly-missing matrices take the compaction path of the K = 1 kernel (same results)
         self._n_missing = int((self._codes == 255).sum().item()) if self._codes.numel() else 0
         self._sparse = self._n_missing > 0.5 * self._codes.numel()
-        self._obs_csr = None          # CSR of the observed cells, built on first use (K = 1, S = 1 path)
+        self._obs_csr = None          # CSR of the observed cells, built on first use (K = 1, mostly-missing data)
         self._enc_x_full = None       # encoder input of the full batch (NaN -> -1), built on first use
         self._x_tiles, self._x_tiles_tried = None, False      # resident operand tiles of the encoder kernels
         self._seed, self._calls = int(seed), 0
@@ -310,7 +310,7 @@ class BaseIRT(BasePsy):                 # vi.py:536-656
                                   idx=idx, a_free=self._a_free_dev, estimator=cfg.estimator, baseline=cfg.baseline,
                                   want_grad=want_grad, sparse=self._sparse and self.x_feature == 1,
                                   n_masked=self._n_missing if idx is None else None,
-                                  obs=self._observed_csr() if (self._sparse and self.x_feature == 1 and s == 1) else None,
+                                  obs=self._observed_csr() if (self._sparse and self.x_feature == 1) else None,
                                   **gkw, **noise)
             w = 1.0 / len(groups)
             total = r["loss"] * w if total is None else total + r["loss"] * w
