@@ -539,7 +539,10 @@ int irt_uni_launch(const VipsyIrtArgs* a, cudaStream_t st) {
   // S > 1 with the observed-cell CSR at hand: the sparse kernel walks it directly (no staging, no compaction)
   const bool csr_multi = a->obs_row_ptr && a->obs_entries && a->n_particles > 1 &&
                          a->estimator == VIPSY_EST_PATHWISE && J < 32768 && !p.packed2;
-  if (!csr_multi) { p.row_ptr = irt_uni_csr_supported(a) ? a->obs_row_ptr : nullptr; if (!p.row_ptr) p.entries = nullptr; }
+  if (!csr_multi && !irt_uni_csr_supported(a)) {         // a CSR no kernel of this call can use (e.g. the score estimator)
+    p.row_ptr = nullptr;
+    p.entries = nullptr;
+  }
   int mask_rows = 0;        // extra loss partials written by masked_term_kernel (lane-per-person dense kernel only)
   if (p.packed2) {                                                           // 2-bit rows: the pipelined particle kernel
     rc = launch_model<false>(a->model, fast, SC, p, smem, st, &grid);
