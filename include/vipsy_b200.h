@@ -131,8 +131,10 @@ typedef struct VipsyIrtArgs {
   size_t workspace_bytes;
   /* optional (ABI 2): the observed cells of y as a CSR, built once per response matrix with
    * vipsy_observed_row_ptr + vipsy_observed_fill.  Row r of y owns entries[row_ptr[r] .. row_ptr[r+1]);
-   * an entry is item | response << 15.  Used when K == 1, S == 1 (pathwise): work and traffic scale with
-   * the observed cells, not with n_rows x J.  y must still be valid (other S / estimators read it). */
+   * an entry is item | response << 15.  Used when K == 1 with the pathwise estimator (S == 1: a sub-warp per
+   * person; S > 1: a lane per person walking its entries): work and traffic scale with the observed cells, not
+   * with n_rows x J; with idx the CSR is that of the whole matrix.  y must still be valid (the score estimator
+   * reads it). */
   const int64_t* obs_row_ptr;   /* n_rows + 1, or NULL                               */
   const uint16_t* obs_entries;  /* obs_nnz entries, or NULL                          */
   int64_t obs_nnz;              /* host copy of row_ptr[n_rows] (picks the lane mapping; 0 = unknown) */

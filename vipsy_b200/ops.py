@@ -197,7 +197,7 @@ def irt_elbo_grad(
     per-person gradients (d_sigma for K == 1, d_chol otherwise).  ``tensor_cores=False``
     forces the SIMT contraction for K > 1 (default: tcgen05 for K >= 8).  ``sparse=True`` (K == 1)
     tells the kernel most cells are missing: it compacts each person's observed cells first.
-    ``obs``: the (row_ptr, entries, nnz) triple of ``observed_csr(y)``; used by the K == 1, S == 1 path.
+    ``obs``: the (row_ptr, entries, nnz) triple of ``observed_csr(y)``; used by the K == 1 pathwise kernels at any S.
     ``n_masked``: number of missing cells among the batch rows, if the caller knows it (saves a counting pass).
     ``fused=False`` (2 <= K <= 8, per-person factor) forces the three-kernel path instead of the fused kernel.
     ``row_kernel=False`` (K == 1, S == 1) forces the lane-per-person kernels instead of the warp-per-person ones."""
